@@ -1,0 +1,186 @@
+/*
+ * isaac_ext.h -- C ABI of the B200-native candidate-extension path of the Isaac aligner.
+ *
+ * Drop-in boundary.  The reference has no plugin/FFI layer: its seam is the C++ class API that
+ * alignment::TemplateBuilder calls once per cluster (reference citations are path:line under
+ * src/c++/ of sequencing/isaac_aligner):
+ *
+ *   FragmentBuilder::build                 include/alignment/FragmentBuilder.hh:62-70
+ *   FragmentBuilder::getFragments/Cigar    include/alignment/FragmentBuilder.hh:71-72
+ *   ShadowAligner::rescueShadow            include/alignment/ShadowAligner.hh:81-88
+ *   UngappedAligner::alignUngapped         include/alignment/fragmentBuilder/UngappedAligner.hh:55-60
+ *   GappedAligner::alignGapped             include/alignment/fragmentBuilder/GappedAligner.hh:49-54
+ *   SimpleIndelAligner::alignSimpleIndels  include/alignment/fragmentBuilder/SimpleIndelAligner.hh:50-55
+ *   BandedSmithWaterman::align             include/alignment/BandedSmithWaterman.hh:81-86
+ *
+ * This library replaces those per-cluster calls by per-tile batch calls over plain pointers.  The
+ * C++ classes carrying the reference's names (isaac_aligner_b200/host/, namespace isaac_b200) are
+ * thin callers of this ABI.  There is no CPU fallback: every compute entry point runs CUDA kernels
+ * on an sm_100a device and returns ISAAC_EXT_E_NO_DEVICE when none is usable.
+ *
+ * Conventions: every function returns an int status (0 = ok), no exceptions cross the boundary,
+ * caller owns all buffers it passes in, result buffers owned by the context stay valid until the next
+ * call on that context.  One context per GPU; a context is not re-entrant (like the reference's
+ * builders, MatchSelector.cpp:143-163 keeps one per thread).
+ */
+#ifndef ISAAC_EXT_H
+#define ISAAC_EXT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define ISAAC_EXT_OK             0
+#define ISAAC_EXT_E_INVALID_ARG  1 /* reference: common::InvalidParameterException / assert()       */
+#define ISAAC_EXT_E_NO_DEVICE    2 /* no usable CUDA device: there is deliberately no CPU fallback   */
+#define ISAAC_EXT_E_CUDA         3 /* CUDA runtime error, see isaac_ext_last_error                   */
+#define ISAAC_EXT_E_UNSUPPORTED  4 /* sequencing adapters / avoid-smith-waterman      */
+#define ISAAC_EXT_E_CAPACITY     5 /* a fixed capacity of the reference was exceeded (cigar stride)  */
+#define ISAAC_EXT_E_NO_REFERENCE 6 /* isaac_ext_set_reference has not been called                    */
+
+/* ---- constants fixed by the reference ------------------------------------------------------- */
+#define ISAAC_EXT_BAND_WIDTH          16 /* BandedSmithWaterman::WIDEST_GAP_SIZE  BandedSmithWaterman.hh:88-89   */
+#define ISAAC_EXT_SW_MISMATCH_CUTOFF   5 /* BandedSmithWaterman::mismatchesCutoff BandedSmithWaterman.hh:94      */
+#define ISAAC_EXT_SW_DISTANCE_CUTOFF   7 /* BandedSmithWaterman::distanceCutoff   BandedSmithWaterman.hh:91-92   */
+#define ISAAC_EXT_SHADOW_KMER          7 /* ShadowAligner::shadowKmerLength_      ShadowAligner.hh:95            */
+#define ISAAC_EXT_SHADOW_POSITIONS 10000 /* candidate position cap                ShadowAligner.hh:92            */
+#define ISAAC_EXT_MAX_CYCLES        1024 /* FragmentMetadata::maxCycles_          FragmentMetadata.hh:368        */
+#define ISAAC_EXT_MASK_WORDS (ISAAC_EXT_MAX_CYCLES / 64)
+
+/* CIGAR word = length << 4 | op, ops as in alignment::Cigar::OpCode (Cigar.hh:52-63,156-168). */
+#define ISAAC_EXT_CIGAR_ALIGN     0u
+#define ISAAC_EXT_CIGAR_INSERT    1u
+#define ISAAC_EXT_CIGAR_DELETE    2u
+#define ISAAC_EXT_CIGAR_SOFT_CLIP 4u
+
+typedef struct isaac_ext_ctx isaac_ext_ctx;
+
+/* Mirrors the constructor arguments of FragmentBuilder / ShadowAligner (FragmentBuilder.hh:49-60,
+ * ShadowAligner.hh:52-59) plus the device plumbing.  Scores are passed exactly as the reference takes
+ * them (bwa preset 0:-3:-11:-4:-20, eland 2:-1:-15:-3:-25; AlignOptions.cpp:55-56,687-741). */
+typedef struct isaac_ext_config {
+    int32_t  gapMatchScore;
+    int32_t  gapMismatchScore;
+    int32_t  gapOpenScore;
+    int32_t  gapExtendScore;
+    int32_t  minGapExtendScore;
+    uint32_t repeatThreshold;       /* --repeat-threshold, default 10      */
+    uint32_t maxSeedsPerRead;
+    uint32_t gappedMismatchesMax;   /* --gapped-mismatches, default 5      */
+    uint32_t semialignedGapLimit;   /* --semialigned-gap-limit, default 100; 0 disables simple indels */
+    uint32_t avoidSmithWaterman;    /* must be 0 (ISAAC_EXT_E_UNSUPPORTED) */
+    uint32_t maxReadLength;         /* flowcell::getMaxTotalReadLength; bounds the SW overflow check  */
+    int32_t  device;                /* CUDA device ordinal                                            */
+    uint32_t hostThreads;           /* threads for the per-cluster bookkeeping (0 = hardware)          */
+} isaac_ext_config_t;
+
+/* Flat equivalent of the FragmentMetadata fields the template layer reads (FragmentMetadata.hh:330-414).
+ * 64 bytes.  mismatchCycles[] is replaced by a bit mask over strand-order base indices (see
+ * isaac_ext_*_batch 'mismatchMask'): cycle = reverse ? lastCycle - i : firstCycle + i
+ * (AlignerBase.cpp:171), emitted in increasing i exactly like addMismatchCycle does. */
+typedef struct isaac_ext_fragment {
+    int64_t  position;               /* FragmentMetadata::position                                   */
+    double   logProbability;         /* ordered FP64 sum, bit-identical to the reference             */
+    uint32_t contigId;
+    uint32_t readId;                 /* cluster * readCount + readIndex                              */
+    uint32_t cigarOffset;            /* word index into the cigar pool of the call that produced it  */
+    uint32_t smithWatermanScore;
+    uint32_t observedLength;
+    uint16_t mismatchCount;
+    uint16_t matchesInARow;
+    uint16_t gapCount;
+    uint16_t editDistance;
+    uint16_t uniqueSeedCount;
+    uint16_t repeatSeedsCount;
+    uint16_t nonUniqueSeedOffsetFirst;  /* 0xFFFF = unset (reference: UINT_MAX)                      */
+    uint16_t nonUniqueSeedOffsetSecond;
+    int16_t  firstSeedIndex;
+    uint16_t lowClipped;
+    uint16_t highClipped;
+    uint16_t cigarLength;            /* 0 = unaligned (FragmentMetadata::isAligned)                  */
+    uint8_t  reverse;
+    uint8_t  readIndex;
+    uint16_t matchCount;             /* return value of updateFragmentCigar for this alignment       */
+} isaac_ext_fragment_t;
+
+/* One tile's clusters in the reference's own BclClusters layout (BclClusters.hh:33-124): one byte per
+ * base = quality << 2 | base, bytes 0..3 = N (Nucleotides.hh:91-94), reads of a cluster back to back. */
+typedef struct isaac_ext_reads {
+    uint32_t clusterCount;
+    uint32_t readCount;              /* 1 or 2                                                        */
+    uint32_t readLength[2];          /* flowcell::ReadMetadata::getLength                             */
+    uint32_t firstCycle[2];          /* flowcell::ReadMetadata::getFirstCycle (cycles are contiguous) */
+    const uint8_t  *bcl;             /* clusterCount * (readLength[0] + readLength[1]) bytes          */
+    const uint16_t *endCyclesMasked; /* clusterCount * readCount (Read::endCyclesMasked_) or NULL     */
+} isaac_ext_reads_t;
+
+/* A candidate placement of one read strand (what FragmentBuilder::addMatch / ShadowAligner produce). */
+typedef struct isaac_ext_candidate {
+    int64_t  position;               /* leftmost base on the forward strand, may be negative          */
+    uint32_t readId;                 /* cluster * readCount + readIndex                               */
+    uint32_t contigStrand;           /* contigId << 1 | reverse                                       */
+} isaac_ext_candidate_t;             /* 16 bytes */
+
+/* ---- life cycle ----------------------------------------------------------------------------- */
+int  isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx **ctx);
+void isaac_ext_destroy(isaac_ext_ctx *ctx);
+const char *isaac_ext_last_error(const isaac_ext_ctx *ctx);   /* ctx may be NULL: last create error */
+const char *isaac_ext_version(void);
+
+/* Replaces reference::ContigLoader's product (ContigLoader.cpp:29-65): contigs arrive as 1 byte/base
+ * upper-case ACGTN and are packed to 2 bit + N-mask and kept resident in HBM. */
+int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
+                            const char *const *contigBases, const uint64_t *contigLengths);
+
+/* Decodes one tile's BCL bytes (Read::decodeBcl, Read.cpp:32-73) into the device-resident read set used
+ * by the batch calls below.  Stays valid until the next isaac_ext_set_reads on this context. */
+int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *reads);
+
+/* ---- micro entry points (unit parity + kernel benchmarks) ------------------------------------ */
+
+/* BandedSmithWaterman::align over n independent (query, database) pairs given as ASCII, database i is
+ * queryLength[i] + 15 bytes (BandedSmithWaterman.cpp:93).  Scores as the BandedSmithWaterman constructor
+ * takes them (gapOpen/gapExtend positive, BandedSmithWaterman.hh:44-46).  Query alphabet ACGTn, database
+ * ACGTN.  cigarOut: n * cigarStride words, cigarLengthOut/offsetOut: n.  offsetOut = return value of
+ * align() (stripped leading deletion). */
+int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n,
+                              const char *queries, const uint64_t *queryOffsets, const uint32_t *queryLengths,
+                              const char *databases, const uint64_t *databaseOffsets,
+                              int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                              uint32_t cigarStride, uint32_t *cigarOut, uint32_t *cigarLengthOut,
+                              uint32_t *offsetOut);
+
+/* UngappedAligner::alignUngapped (UngappedAligner.cpp:39-92) on every candidate against the resident
+ * reference and read set.  fragmentsOut: n records; cigarOut: n * 3 words (fragment.cigarOffset = 3 * i);
+ * mismatchMaskOut: n * ISAAC_EXT_MASK_WORDS words or NULL. */
+int isaac_ext_ungapped_batch(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                             isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *mismatchMaskOut);
+
+/* GappedAligner::alignGapped (GappedAligner.cpp:167-249) on every candidate.  matchCount == 0 and
+ * cigarLength == 0 where the reference returns 0 without aligning (GappedAligner.cpp:204-208).
+ * cigarOut: n * cigarStride words (fragment.cigarOffset = cigarStride * i). */
+int isaac_ext_gapped_batch(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                           uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
+                           uint64_t *mismatchMaskOut);
+
+/* Device-resident variants used to time the kernels alone: the candidate and result arrays are device
+ * pointers, the launch goes to 'cudaStream' (a cudaStream_t passed as void*) and returns without
+ * synchronising.  Same semantics as the host variants above. */
+int isaac_ext_ungapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates,
+                                    void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut,
+                                    void *cudaStream);
+int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates,
+                                  uint32_t cigarStride, void *dFragmentsOut, void *dCigarOut,
+                                  void *dMismatchMaskOut, void *cudaStream);
+
+/* Number of kernel launches this context has issued so far (bench.py reports it as gpu_launches). */
+uint64_t isaac_ext_launch_count(const isaac_ext_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISAAC_EXT_H */

@@ -1,0 +1,146 @@
+"""Synthetic genomes, simulated read pairs and candidate lists.
+
+Everything is generated from numpy's counter-based Philox generator with fixed seeds, so the CPU arm and
+the GPU arm of a benchmark regenerate identical inputs.  This is workload generation, not alignment: it is
+shared by bench.py and the tests.
+"""
+import numpy as np
+
+SEED_G5 = 0x15AAC0001
+SEED_G3100 = 0x15AAC0002
+SEED_READS = 0x15AAC0100
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _CODE[_c] = _i
+
+
+def _rng(seed):
+    return np.random.Generator(np.random.Philox(seed))
+
+
+def make_genome(total_bases, n_contigs=1, seed=SEED_G5, n_fraction=0.0, n_run=(100, 10000)):
+    """i.i.d. uniform ACGT contigs of equal length (last one shorter); optionally n_fraction of the bases
+    replaced by runs of 'N' so that the N-mask path is exercised.  Returns a list of uint8 ASCII arrays."""
+    rng = _rng(seed)
+    per = -(-total_bases // n_contigs)
+    contigs = []
+    for c in range(n_contigs):
+        n = min(per, total_bases - c * per)
+        a = _ACGT[rng.integers(0, 4, size=n, dtype=np.uint8)]
+        if n_fraction > 0:
+            target = int(n * n_fraction)
+            done = 0
+            while done < target:
+                run = int(rng.integers(n_run[0], n_run[1] + 1))
+                start = int(rng.integers(0, max(1, n - run)))
+                a[start:start + run] = ord("N")
+                done += run
+        contigs.append(a)
+    return contigs
+
+
+class Simulation:
+    """Simulated FR read pairs.  bcl: [n_pairs, 2L] bytes (quality << 2 | base, 0 = N) in sequencing order;
+    contig/position/reverse: [n_pairs, 2] truth of each read (position = leftmost forward-strand base of the
+    strand-order read); shift1: [n_pairs, 2] net indel shift of the read's last base relative to its first."""
+
+    def __init__(self, L):
+        self.L = L
+        self.bcl = None
+        self.contig = None
+        self.position = None
+        self.reverse = None
+        self.events = None  # [n_pairs, 2, K, 3] (strand-order read offset, +del/-ins length, unused)
+
+
+def simulate_pairs(genome, n_pairs, L=150, seed=SEED_READS, snp_rate=1e-3, indel_rate=5e-4, max_indel=16,
+                   insert=(350.0, 35.0, 200, 500), quality_probs=((40, 0.80), (30, 0.15), (20, 0.04), (2, 0.01)),
+                   chunk=200_000):
+    rng = _rng(seed)
+    lens = np.array([c.size for c in genome], dtype=np.int64)
+    margin = insert[3] + 2 * max_indel + 64
+    weights = np.maximum(lens - margin, 0).astype(np.float64)
+    weights /= weights.sum()
+    sim = Simulation(L)
+    sim.bcl = np.empty((n_pairs, 2 * L), dtype=np.uint8)
+    sim.contig = np.empty((n_pairs, 2), dtype=np.uint32)
+    sim.position = np.empty((n_pairs, 2), dtype=np.int64)
+    sim.reverse = np.zeros((n_pairs, 2), dtype=np.uint8)
+    sim.reverse[:, 1] = 1
+    K = 2
+    sim.events = np.zeros((n_pairs, 2, K, 2), dtype=np.int32)
+    qvals = np.array([q for q, _ in quality_probs], dtype=np.uint8)
+    qp = np.array([p for _, p in quality_probs], dtype=np.float64)
+    qerr = np.power(10.0, -qvals.astype(np.float64) / 10.0)
+    idx = np.arange(L, dtype=np.int64)[None, :]
+    for b in range(0, n_pairs, chunk):
+        n = min(chunk, n_pairs - b)
+        contig = rng.choice(len(genome), size=n, p=weights).astype(np.uint32)
+        ins = np.clip(np.rint(rng.normal(insert[0], insert[1], size=n)), insert[2], insert[3]).astype(np.int64)
+        start = (rng.random(n) * (lens[contig] - margin)).astype(np.int64) + max_indel + 16
+        pos = np.stack([start, start + ins - L], axis=1)            # forward leftmost base of each read
+        for r in range(2):
+            # indel events in strand-order read coordinates
+            nev = np.minimum(rng.poisson(L * indel_rate, size=n), K)
+            epos = np.sort(rng.integers(8, L - 8, size=(n, K)), axis=1)
+            elen = np.minimum(rng.geometric(0.4, size=(n, K)), max_indel).astype(np.int64)
+            isdel = rng.random((n, K)) < 0.5
+            active = np.arange(K)[None, :] < nev[:, None]
+            # keep the second event clear of the first one's inserted bases
+            clash = active[:, 1] & (epos[:, 1] < epos[:, 0] + elen[:, 0] + 4)
+            active[:, 1] &= ~clash
+            goff = np.broadcast_to(idx, (n, L)).copy()
+            inserted = np.zeros((n, L), dtype=bool)
+            for k in range(K):
+                a = active[:, k][:, None]
+                p = epos[:, k][:, None]
+                ln = elen[:, k][:, None]
+                d = isdel[:, k][:, None]
+                goff += np.where(a & d & (idx >= p), ln, 0)
+                goff -= np.where(a & ~d, np.clip(idx - p, 0, ln), 0)
+                inserted |= a & ~d & (idx >= p) & (idx < p + ln)
+                sim.events[b:b + n, r, k, 0] = np.where(active[:, k], epos[:, k], -1)
+                sim.events[b:b + n, r, k, 1] = np.where(active[:, k], np.where(isdel[:, k], elen[:, k], -elen[:, k]), 0)
+            codes = np.empty((n, L), dtype=np.uint8)
+            for c in np.unique(contig):
+                m = contig == c
+                codes[m] = _CODE[genome[c][pos[m, r][:, None] + goff[m]]]
+            rnd = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+            codes = np.where(inserted | (codes > 3), rnd, codes)
+            qi = rng.choice(len(qvals), size=(n, L), p=qp)
+            q = qvals[qi]
+            sub = rng.random((n, L)) < (snp_rate + qerr[qi])
+            codes = np.where(sub, (codes + rng.integers(1, 4, size=(n, L), dtype=np.uint8)) & 3, codes).astype(np.uint8)
+            byte = (q << 2) | codes
+            byte = np.where(q == 2, 0, byte).astype(np.uint8)      # Q2 bases are read as N (bcl byte 0)
+            if r == 1:   # read 2 is sequenced from the other strand: reverse-complement into sequencing order
+                byte = np.where(byte == 0, 0, byte ^ 3)[:, ::-1]
+            sim.bcl[b:b + n, r * L:(r + 1) * L] = byte
+        sim.contig[b:b + n] = contig[:, None]
+        sim.position[b:b + n] = pos
+    return sim
+
+
+def microbench_candidates(sim, genome, per_read=4, seed=SEED_READS + 2, fractions=(0.6, 0.2, 0.2)):
+    """for every read 'per_read' (read, window) pairs: true locus / true locus shifted by
+    +-(1..7) bp / uniform random locus with the given fractions.  Returns a CANDIDATE_DTYPE array."""
+    from .types import CANDIDATE_DTYPE
+    rng = _rng(seed)
+    n_reads = sim.contig.size
+    n = n_reads * per_read
+    read_id = np.repeat(np.arange(n_reads, dtype=np.uint32), per_read)
+    contig = sim.contig.reshape(-1)[read_id]
+    true_pos = sim.position.reshape(-1)[read_id]
+    reverse = sim.reverse.reshape(-1)[read_id].astype(np.uint32)
+    kind = rng.random(n)
+    shift = rng.integers(1, 8, size=n) * np.where(rng.random(n) < 0.5, -1, 1)
+    lens = np.array([c.size for c in genome], dtype=np.int64)
+    rnd = (rng.random(n) * (lens[contig] - sim.L - 64)).astype(np.int64) + 16
+    pos = np.where(kind < fractions[0], true_pos, np.where(kind < fractions[0] + fractions[1], true_pos + shift, rnd))
+    cand = np.empty(n, dtype=CANDIDATE_DTYPE)
+    cand["position"] = pos
+    cand["readId"] = read_id
+    cand["contigStrand"] = (contig << 1) | reverse
+    return cand

@@ -1,0 +1,53 @@
+/*
+ * oracle_api.h -- flat C interface shared by the two CPU checkers of the candidate-extension path:
+ *
+ *   oracle/_ref/libisaac_ref.so   the reference's own sources (BandedSmithWaterman.cpp, FragmentBuilder.cpp, ...)
+ *                                 compiled unmodified from /root/reference by oracle/Makefile behind ref_capi.cpp
+ *   oracle/libisaac_oracle.so     isaac_oracle.cpp, a scalar restatement of the same algorithms
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under isaac_aligner_b200/ may include, link or load this; only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the checker and the
+ * CPU baseline, never as the product.  Both libraries export exactly these symbols so the tests can diff them
+ * against each other and against the CUDA path with one harness.
+ */
+#ifndef ISAAC_ORACLE_API_H
+#define ISAAC_ORACLE_API_H
+#include "../include/isaac_ext.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_genome {
+    uint32_t contigCount;
+    const char *const *contigBases;     /* upper-case ACGTN, 1 byte per base */
+    const uint64_t *contigLengths;
+} oracle_genome_t;
+
+const char *oracle_kind(void);          /* "reference" or "port" */
+
+/* BandedSmithWaterman::align, see isaac_ext_banded_sw_batch.  threads > 1 splits the batch over std::threads
+ * (one BandedSmithWaterman object per thread, like the reference keeps one per TemplateBuilder). */
+int oracle_banded_sw_batch(uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                           const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                           int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                           uint32_t maxReadLength, uint32_t cigarStride, uint32_t *cigarOut,
+                           uint32_t *cigarLengthOut, uint32_t *offsetOut, uint32_t threads);
+
+/* UngappedAligner::alignUngapped on every candidate, see isaac_ext_ungapped_batch. */
+int oracle_ungapped_batch(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                          const isaac_ext_config_t *config, uint32_t n, const isaac_ext_candidate_t *candidates,
+                          isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *mismatchMaskOut,
+                          uint32_t threads);
+
+/* alignUngapped followed by GappedAligner::alignGapped on a copy (what FragmentBuilder::alignFragments does,
+ * FragmentBuilder.cpp:199-200), see isaac_ext_gapped_batch. */
+int oracle_gapped_batch(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                        const isaac_ext_config_t *config, uint32_t n, const isaac_ext_candidate_t *candidates,
+                        uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
+                        uint64_t *mismatchMaskOut, uint32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,228 @@
+/*
+ * ref_capi.cpp -- flat C interface (oracle_api.h) over the reference's OWN classes.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle_api.h).  This file contains no alignment logic: it builds the
+ * reference's value types (reference::Contig, alignment::Cluster, flowcell::ReadMetadataList, ...) from the
+ * flat batch structs, calls the unmodified reference code compiled from /root/reference/src/c++/lib/alignment
+ * (see oracle/Makefile) and flattens the FragmentMetadata results.  It is linked into oracle/_ref/libisaac_ref.so,
+ * which is git-ignored and rebuilt wherever /root/reference is mounted.
+ */
+#include <thread>
+#include <vector>
+#include <memory>
+#include <cstring>
+
+#include "alignment/BandedSmithWaterman.hh"
+#include "alignment/FragmentBuilder.hh"
+#include "alignment/ShadowAligner.hh"
+#include "alignment/Cluster.hh"
+#include "alignment/fragmentBuilder/UngappedAligner.hh"
+#include "alignment/fragmentBuilder/GappedAligner.hh"
+#include "alignment/matchSelector/FragmentSequencingAdapterClipper.hh"
+#include "reference/Contig.hh"
+
+#include "oracle_api.h"
+
+using namespace isaac;
+
+namespace
+{
+
+template <class F> void parallelFor(uint32_t n, uint32_t threads, F f)
+{
+    if (threads <= 1 || n < 2 * threads) { f(0, 0u, n); return; }
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < threads; ++t)
+    {
+        const uint32_t b = uint64_t(n) * t / threads, e = uint64_t(n) * (t + 1) / threads;
+        pool.emplace_back([=]() { f(t, b, e); });
+    }
+    for (std::thread &th : pool) th.join();
+}
+
+std::vector<reference::Contig> makeContigs(const oracle_genome_t *g)
+{
+    std::vector<reference::Contig> contigs;
+    for (uint32_t c = 0; c < g->contigCount; ++c)
+    {
+        contigs.push_back(reference::Contig(c, "c" + std::to_string(c)));
+        contigs.back().forward_.assign(g->contigBases[c], g->contigBases[c] + g->contigLengths[c]);
+    }
+    return contigs;
+}
+
+flowcell::ReadMetadataList makeReadMetadata(const isaac_ext_reads_t *r)
+{
+    std::vector<flowcell::ReadMetadata> v;
+    unsigned offset = 0;
+    for (uint32_t i = 0; i < r->readCount; ++i)
+    {
+        v.push_back(flowcell::ReadMetadata(r->firstCycle[i], r->firstCycle[i] + r->readLength[i] - 1, i, offset));
+        offset += r->readLength[i];
+    }
+    return flowcell::ReadMetadataList(v);
+}
+
+/// holds the BCL bytes of one cluster as the std::vector<char> Cluster::init wants
+struct ClusterHolder
+{
+    std::vector<char> bcl;
+    alignment::Cluster cluster;
+    ClusterHolder(unsigned maxReadLength) : cluster(maxReadLength) {}
+    void load(const isaac_ext_reads_t *r, const flowcell::ReadMetadataList &rml, uint32_t clusterId)
+    {
+        const uint32_t total = r->readLength[0] + (r->readCount > 1 ? r->readLength[1] : 0);
+        bcl.assign(r->bcl + size_t(clusterId) * total, r->bcl + size_t(clusterId + 1) * total);
+        cluster.init(rml, bcl.begin(), 0, clusterId, alignment::ClusterXy(0, 0), true, 0);
+        for (uint32_t i = 0; i < r->readCount; ++i)
+        {
+            cluster[i].maskCyclesFromEnd(r->endCyclesMasked ? r->endCyclesMasked[size_t(clusterId) * r->readCount + i] : 0);
+        }
+    }
+};
+
+void flatten(const alignment::FragmentMetadata &f, uint32_t readId, uint32_t cigarOffset, unsigned matchCount,
+             const flowcell::ReadMetadataList &rml, isaac_ext_fragment_t &o, uint32_t *cigarOut, uint32_t cigarStride,
+             uint64_t *maskOut)
+{
+    std::memset(&o, 0, sizeof(o));
+    o.position = f.position;
+    o.logProbability = f.logProbability;
+    o.contigId = f.contigId;
+    o.readId = readId;
+    o.cigarOffset = cigarOffset;
+    o.smithWatermanScore = f.smithWatermanScore;
+    o.observedLength = f.observedLength;
+    o.mismatchCount = f.mismatchCount;
+    o.matchesInARow = f.matchesInARow;
+    o.gapCount = f.gapCount;
+    o.editDistance = f.editDistance;
+    o.uniqueSeedCount = f.uniqueSeedCount;
+    o.repeatSeedsCount = f.repeatSeedsCount;
+    o.nonUniqueSeedOffsetFirst = uint16_t(std::min<unsigned>(f.nonUniqueSeedOffsets.first, 0xFFFF));
+    o.nonUniqueSeedOffsetSecond = uint16_t(f.nonUniqueSeedOffsets.second);
+    o.firstSeedIndex = int16_t(f.firstSeedIndex);
+    o.lowClipped = f.lowClipped;
+    o.highClipped = f.highClipped;
+    o.cigarLength = f.cigarLength;
+    o.reverse = f.reverse;
+    o.readIndex = f.readIndex;
+    o.matchCount = matchCount;
+    if (f.cigarLength && f.cigarBuffer && cigarOut)
+    {
+        ISAAC_ASSERT_MSG(f.cigarLength <= cigarStride, "cigar stride too small");
+        std::copy(f.cigarBuffer->begin() + f.cigarOffset, f.cigarBuffer->begin() + f.cigarOffset + f.cigarLength, cigarOut);
+    }
+    if (maskOut)
+    {
+        std::fill(maskOut, maskOut + ISAAC_EXT_MASK_WORDS, 0UL);
+        const unsigned firstCycle = rml[f.readIndex].getFirstCycle(), lastCycle = rml[f.readIndex].getLastCycle();
+        for (const unsigned short *c = f.getMismatchCyclesBegin(); c != f.getMismatchCyclesEnd(); ++c)
+        {
+            const unsigned i = f.reverse ? lastCycle - *c : *c - firstCycle;
+            maskOut[i / 64] |= 1UL << (i % 64);
+        }
+    }
+}
+
+} // namespace
+
+extern "C" const char *oracle_kind(void) { return "reference"; }
+
+extern "C" int oracle_banded_sw_batch(uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                                      const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                                      int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                                      uint32_t maxReadLength, uint32_t cigarStride, uint32_t *cigarOut,
+                                      uint32_t *cigarLengthOut, uint32_t *offsetOut, uint32_t threads)
+{
+    try
+    {
+        parallelFor(n, threads, [&](uint32_t, uint32_t b, uint32_t e) {
+            const alignment::BandedSmithWaterman sw(matchScore, mismatchScore, gapOpenScore, gapExtendScore, maxReadLength);
+            std::vector<char> query, database;
+            alignment::Cigar cigar;
+            for (uint32_t i = b; i < e; ++i)
+            {
+                query.assign(queries + queryOffsets[i], queries + queryOffsets[i] + queryLengths[i]);
+                database.assign(databases + databaseOffsets[i], databases + databaseOffsets[i] + queryLengths[i] + 15);
+                cigar.clear();
+                offsetOut[i] = sw.align(query, database.begin(), database.end(), cigar);
+                cigarLengthOut[i] = cigar.size();
+                std::copy(cigar.begin(), cigar.begin() + std::min<size_t>(cigar.size(), cigarStride), cigarOut + size_t(i) * cigarStride);
+            }
+        });
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+    return ISAAC_EXT_OK;
+}
+
+static int extendBatch(const bool gapped, const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                       const isaac_ext_config_t *cfg, uint32_t n, const isaac_ext_candidate_t *candidates,
+                       uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
+                       uint64_t *mismatchMaskOut, uint32_t threads)
+{
+    try
+    {
+        const std::vector<reference::Contig> contigs = makeContigs(genome);
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+        parallelFor(n, threads, [&](uint32_t, uint32_t b, uint32_t e) {
+            const alignment::fragmentBuilder::UngappedAligner ungapped(
+                cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore);
+            alignment::fragmentBuilder::GappedAligner gappedAligner(
+                layouts, false, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore);
+            ClusterHolder holder(maxReadLength);
+            uint32_t loaded = -1U;
+            alignment::Cigar cigar;
+            for (uint32_t i = b; i < e; ++i)
+            {
+                const isaac_ext_candidate_t &c = candidates[i];
+                const uint32_t clusterId = c.readId / reads->readCount, readIndex = c.readId % reads->readCount;
+                if (loaded != clusterId) { holder.load(reads, rml, clusterId); loaded = clusterId; }
+                cigar.clear();
+                alignment::FragmentMetadata fragment(&holder.cluster, &cigar, readIndex);
+                fragment.reverse = (c.contigStrand & 1);
+                fragment.contigId = (c.contigStrand >> 1);
+                fragment.position = c.position;
+                alignment::matchSelector::FragmentSequencingAdapterClipper clipper(noAdapters);
+                clipper.checkInitStrand(fragment, contigs[(c.contigStrand >> 1)]);
+                unsigned matchCount = ungapped.alignUngapped(fragment, cigar, rml, clipper, contigs[(c.contigStrand >> 1)]);
+                if (gapped)
+                {
+                    alignment::FragmentMetadata tmp = fragment;
+                    matchCount = gappedAligner.alignGapped(tmp, cigar, rml, clipper, contigs[(c.contigStrand >> 1)]);
+                    fragment = tmp;
+                }
+                flatten(fragment, c.readId, i * cigarStride, matchCount, rml, fragmentsOut[i],
+                        cigarOut ? cigarOut + size_t(i) * cigarStride : 0, cigarStride,
+                        mismatchMaskOut ? mismatchMaskOut + size_t(i) * ISAAC_EXT_MASK_WORDS : 0);
+            }
+        });
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int oracle_ungapped_batch(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                                     const isaac_ext_config_t *config, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                     isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *mismatchMaskOut,
+                                     uint32_t threads)
+{
+    return extendBatch(false, genome, reads, config, n, candidates, 3, fragmentsOut, cigarOut, mismatchMaskOut, threads);
+}
+
+extern "C" int oracle_gapped_batch(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                                   const isaac_ext_config_t *config, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                   uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
+                                   uint64_t *mismatchMaskOut, uint32_t threads)
+{
+    return extendBatch(true, genome, reads, config, n, candidates, cigarStride, fragmentsOut, cigarOut, mismatchMaskOut, threads);
+}

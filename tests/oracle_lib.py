@@ -1,0 +1,109 @@
+"""ctypes loader of the two CPU checkers (oracle/oracle_api.h).  Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from isaac_aligner_b200.types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, MASK_WORDS, Config, Reads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+PORT_SO = os.path.join(ORACLE_DIR, "libisaac_oracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libisaac_ref.so")
+
+
+class Genome(ctypes.Structure):
+    _fields_ = [("contigCount", ctypes.c_uint32), ("contigBases", ctypes.POINTER(ctypes.c_void_p)),
+                ("contigLengths", ctypes.POINTER(ctypes.c_uint64))]
+
+
+class GenomeHolder:
+    def __init__(self, contigs):
+        self.contigs = [np.ascontiguousarray(c, dtype=np.uint8) for c in contigs]
+        n = len(self.contigs)
+        self.ptrs = (ctypes.c_void_p * n)(*[c.ctypes.data for c in self.contigs])
+        self.lens = (ctypes.c_uint64 * n)(*[c.size for c in self.contigs])
+        self.c = Genome(n, self.ptrs, self.lens)
+
+
+def build(target="port"):
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, target])
+
+
+class Oracle:
+    """One of the two checker libraries; both export the same symbols."""
+
+    def __init__(self, path):
+        self.lib = ctypes.CDLL(path)
+        self.lib.oracle_kind.restype = ctypes.c_char_p
+        self.kind = self.lib.oracle_kind().decode()
+
+    def banded_sw(self, queries, dbs, scores, max_read_length=None, cigar_stride=64, threads=1):
+        """queries/dbs: lists of bytes.  scores = (match, mismatch, gapOpen>0, gapExtend>0).
+        returns (list of cigar word arrays, offsets)"""
+        n = len(queries)
+        qbuf = np.frombuffer(b"".join(queries), dtype=np.uint8)
+        dbuf = np.frombuffer(b"".join(dbs), dtype=np.uint8)
+        qlen = np.array([len(q) for q in queries], dtype=np.uint32)
+        qoff = np.concatenate([[0], np.cumsum(qlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        dlen = np.array([len(d) for d in dbs], dtype=np.uint64)
+        assert np.all(dlen == qlen + 15)
+        doff = np.concatenate([[0], np.cumsum(dlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        return self.banded_sw_flat(qbuf, qoff, qlen, dbuf, doff, scores, max_read_length, cigar_stride, threads)
+
+    def banded_sw_flat(self, qbuf, qoff, qlen, dbuf, doff, scores, max_read_length=None, cigar_stride=64, threads=1):
+        n = len(qlen)
+        if max_read_length is None:
+            max_read_length = int(qlen.max())
+        cig = np.zeros((n, cigar_stride), dtype=np.uint32)
+        ciglen = np.zeros(n, dtype=np.uint32)
+        off = np.zeros(n, dtype=np.uint32)
+        rc = self.lib.oracle_banded_sw_batch(
+            ctypes.c_uint32(n), ctypes.c_void_p(qbuf.ctypes.data), ctypes.c_void_p(qoff.ctypes.data),
+            ctypes.c_void_p(qlen.ctypes.data), ctypes.c_void_p(dbuf.ctypes.data), ctypes.c_void_p(doff.ctypes.data),
+            ctypes.c_int(scores[0]), ctypes.c_int(scores[1]), ctypes.c_int(scores[2]), ctypes.c_int(scores[3]),
+            ctypes.c_uint32(max_read_length), ctypes.c_uint32(cigar_stride), ctypes.c_void_p(cig.ctypes.data),
+            ctypes.c_void_p(ciglen.ctypes.data), ctypes.c_void_p(off.ctypes.data), ctypes.c_uint32(threads))
+        if rc:
+            raise RuntimeError("oracle_banded_sw_batch failed: %d" % rc)
+        return cig, ciglen, off
+
+    def _extend(self, fn, genome, reads, config, candidates, cigar_stride, threads, gapped):
+        n = len(candidates)
+        cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
+        frags = np.zeros(n, dtype=FRAGMENT_DTYPE)
+        cig = np.zeros((n, cigar_stride), dtype=np.uint32)
+        mask = np.zeros((n, MASK_WORDS), dtype=np.uint64)
+        args = [ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.c_uint32(n),
+                ctypes.c_void_p(cand.ctypes.data)]
+        if gapped:
+            args.append(ctypes.c_uint32(cigar_stride))
+        args += [ctypes.c_void_p(frags.ctypes.data), ctypes.c_void_p(cig.ctypes.data),
+                 ctypes.c_void_p(mask.ctypes.data), ctypes.c_uint32(threads)]
+        rc = fn(*args)
+        if rc:
+            raise RuntimeError("oracle extend batch failed: %d" % rc)
+        return frags, cig, mask
+
+    def ungapped(self, genome, reads, config, candidates, threads=1):
+        return self._extend(self.lib.oracle_ungapped_batch, genome, reads, config, candidates, 3, threads, False)
+
+    def gapped(self, genome, reads, config, candidates, cigar_stride=32, threads=1):
+        return self._extend(self.lib.oracle_gapped_batch, genome, reads, config, candidates, cigar_stride, threads, True)
+
+
+def port():
+    if not os.path.exists(PORT_SO):
+        build("port")
+    return Oracle(PORT_SO)
+
+
+def reference():
+    """The reference's own code; None when it was never built (needs /root/reference at build time)."""
+    if not os.path.exists(REF_SO):
+        if os.path.isdir("/root/reference/src/c++"):
+            build("ref")
+        else:
+            return None
+    return Oracle(REF_SO)
