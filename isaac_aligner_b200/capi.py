@@ -1,0 +1,144 @@
+"""ctypes binding of libisaac_ext.so (include/isaac_ext.h).
+
+The library is the product: this module raises at import time when it has not been built and every compute
+call raises ExtError when no CUDA device is usable -- there is no CPU path to fall back to.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, MASK_WORDS, Config, ReadSet
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libisaac_ext.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(isaac_aligner_b200 has no CPU fallback)" % LIB_PATH)
+
+_lib = ctypes.CDLL(LIB_PATH)
+_lib.isaac_ext_last_error.restype = ctypes.c_char_p
+_lib.isaac_ext_last_error.argtypes = [ctypes.c_void_p]
+_lib.isaac_ext_version.restype = ctypes.c_char_p
+_lib.isaac_ext_launch_count.restype = ctypes.c_uint64
+_lib.isaac_ext_launch_count.argtypes = [ctypes.c_void_p]
+_lib.isaac_ext_destroy.argtypes = [ctypes.c_void_p]
+_lib.isaac_ext_destroy.restype = None
+
+# every symbol include/isaac_ext.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = [
+    "isaac_ext_create", "isaac_ext_destroy", "isaac_ext_last_error", "isaac_ext_version",
+    "isaac_ext_set_reference", "isaac_ext_set_reads", "isaac_ext_banded_sw_batch", "isaac_ext_ungapped_batch",
+    "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
+    "isaac_ext_launch_count",
+]
+
+
+class ExtError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "isaac_ext error %d: %s" % (code, message))
+        self.code = code
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Context:
+    """One isaac_ext_ctx (one per GPU)."""
+
+    def __init__(self, config=None):
+        self.config = config if config is not None else Config.default()
+        self._h = ctypes.c_void_p()
+        rc = _lib.isaac_ext_create(ctypes.byref(self.config), ctypes.byref(self._h))
+        if rc:
+            raise ExtError(rc, _lib.isaac_ext_last_error(None).decode())
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            _lib.isaac_ext_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise ExtError(rc, _lib.isaac_ext_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(_lib.isaac_ext_launch_count(self._h))
+
+    def set_reference(self, contigs):
+        contigs = [np.ascontiguousarray(c, dtype=np.uint8) for c in contigs]
+        n = len(contigs)
+        ptrs = (ctypes.c_void_p * n)(*[c.ctypes.data for c in contigs])
+        lens = (ctypes.c_uint64 * n)(*[c.size for c in contigs])
+        self._check(_lib.isaac_ext_set_reference(self._h, ctypes.c_uint32(n), ptrs, lens))
+        self.contig_lengths = [c.size for c in contigs]
+
+    def set_reads(self, reads):
+        assert isinstance(reads, ReadSet)
+        self._check(_lib.isaac_ext_set_reads(self._h, ctypes.byref(reads.c)))
+        self.reads = reads
+
+    def banded_sw(self, queries, dbs, scores, cigar_stride=64):
+        qbuf = np.frombuffer(b"".join(queries), dtype=np.uint8)
+        dbuf = np.frombuffer(b"".join(dbs), dtype=np.uint8)
+        qlen = np.array([len(q) for q in queries], dtype=np.uint32)
+        qoff = np.concatenate([[0], np.cumsum(qlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        dlen = np.array([len(d) for d in dbs], dtype=np.uint64)
+        doff = np.concatenate([[0], np.cumsum(dlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        return self.banded_sw_flat(qbuf, qoff, qlen, dbuf, doff, scores, cigar_stride)
+
+    def banded_sw_flat(self, qbuf, qoff, qlen, dbuf, doff, scores, cigar_stride=64):
+        n = len(qlen)
+        cig = np.zeros((n, cigar_stride), dtype=np.uint32)
+        ciglen = np.zeros(n, dtype=np.uint32)
+        off = np.zeros(n, dtype=np.uint32)
+        self._check(_lib.isaac_ext_banded_sw_batch(
+            self._h, ctypes.c_uint32(n), _p(qbuf), _p(qoff), _p(qlen), _p(dbuf), _p(doff),
+            ctypes.c_int(scores[0]), ctypes.c_int(scores[1]), ctypes.c_int(scores[2]), ctypes.c_int(scores[3]),
+            ctypes.c_uint32(cigar_stride), _p(cig), _p(ciglen), _p(off)))
+        return cig, ciglen, off
+
+    def ungapped(self, candidates, with_masks=True, out=None):
+        cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
+        n = len(cand)
+        frags, cig, mask = out if out is not None else (
+            np.zeros(n, dtype=FRAGMENT_DTYPE), np.zeros((n, 3), dtype=np.uint32),
+            np.zeros((n, MASK_WORDS), dtype=np.uint64) if with_masks else None)
+        self._check(_lib.isaac_ext_ungapped_batch(self._h, ctypes.c_uint32(n), _p(cand), _p(frags), _p(cig), _p(mask)))
+        return frags, cig, mask
+
+    def gapped(self, candidates, cigar_stride=32, with_masks=True, out=None):
+        cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
+        n = len(cand)
+        frags, cig, mask = out if out is not None else (
+            np.zeros(n, dtype=FRAGMENT_DTYPE), np.zeros((n, cigar_stride), dtype=np.uint32),
+            np.zeros((n, MASK_WORDS), dtype=np.uint64) if with_masks else None)
+        self._check(_lib.isaac_ext_gapped_batch(self._h, ctypes.c_uint32(n), _p(cand), ctypes.c_uint32(cigar_stride),
+                                                _p(frags), _p(cig), _p(mask)))
+        return frags, cig, mask
+
+    # device-resident variants: arguments are raw device pointers (e.g. torch tensor .data_ptr()) and a stream handle
+    def ungapped_device(self, n, d_candidates, d_fragments, d_cigars, d_masks, stream):
+        self._check(_lib.isaac_ext_ungapped_batch_device(
+            self._h, ctypes.c_uint32(n), ctypes.c_void_p(d_candidates), ctypes.c_void_p(d_fragments),
+            ctypes.c_void_p(d_cigars), ctypes.c_void_p(d_masks) if d_masks else None, ctypes.c_void_p(stream)))
+
+    def gapped_device(self, n, d_candidates, cigar_stride, d_fragments, d_cigars, d_masks, stream):
+        self._check(_lib.isaac_ext_gapped_batch_device(
+            self._h, ctypes.c_uint32(n), ctypes.c_void_p(d_candidates), ctypes.c_uint32(cigar_stride),
+            ctypes.c_void_p(d_fragments), ctypes.c_void_p(d_cigars), ctypes.c_void_p(d_masks) if d_masks else None,
+            ctypes.c_void_p(stream)))
+
+
+def version():
+    return _lib.isaac_ext_version().decode()

@@ -1,0 +1,70 @@
+// Device-side views of the data that stays resident in HBM: the 2-bit packed reference with its N-mask and the
+// decoded read set of the current tile.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/isaac_ext.h"
+
+namespace isaac_b200
+{
+
+// Base codes used inside the kernels.  A,C,G,T = 0..3; the read's 'n' and the reference's 'N' get two different
+// codes above 3 so that a plain equality test reproduces the reference's raw byte compare inside Smith-Waterman
+// (BandedSmithWaterman.cpp:205: 'n' != 'N' != anything), while isMatch (Alignment.hh:44-47) is
+// read == CODE_READ_N || (read == ref) -- ref 'N' can never equal a read code.
+enum : unsigned { CODE_READ_N = 4, CODE_REF_N = 5 };
+
+/// All contigs back to back, each starting on a 128-base boundary, padded with 128 zero bases at the end.
+struct ReferenceView
+{
+    const uint32_t *bases2;          // 16 bases per word, base g at bits 2*(g%16)
+    const uint32_t *nmask;           // 32 bases per word, bit set = 'N'
+    const uint64_t *contigOffset;    // global base index of the first base of each contig
+    const uint64_t *contigLength;
+    uint32_t contigCount;
+
+    __device__ __forceinline__ unsigned code(uint64_t g) const
+    {
+        const unsigned c = (__ldg(bases2 + (g >> 4)) >> ((unsigned(g) & 15u) * 2u)) & 3u;
+        const unsigned n = (__ldg(nmask + (g >> 5)) >> (unsigned(g) & 31u)) & 1u;
+        return n ? unsigned(CODE_REF_N) : c;
+    }
+};
+
+/// One tile's reads, forward strand only; the reverse strand is read back to front and complemented on the fly
+/// (Read::decodeBcl, Read.cpp:32-73, builds exactly that).  readId = cluster * readCount + readIndex.
+struct ReadSetView
+{
+    const uint32_t *bases2;          // readId * words2 + w, 16 bases per word
+    const uint32_t *nmask;           // readId * wordsN + w, 32 bases per word, bit set = 'n'
+    const uint8_t *quality;          // readId * qualityStride + i (BCL N gets quality 2)
+    const uint16_t *endCyclesMasked; // per readId
+    uint32_t words2, wordsN, qualityStride;
+    uint32_t readCount;
+    uint32_t readLength[2];
+    uint32_t firstCycle[2];
+    uint32_t readTotal;              // clusterCount * readCount
+
+    __device__ __forceinline__ unsigned length(unsigned readId) const { return readLength[readId % readCount]; }
+
+    /// base code and quality of strand-order position i
+    __device__ __forceinline__ unsigned code(unsigned readId, unsigned L, bool reverse, unsigned i, unsigned &q) const
+    {
+        const unsigned f = reverse ? L - 1 - i : i;
+        q = quality[size_t(readId) * qualityStride + f];
+        const unsigned c = (bases2[size_t(readId) * words2 + (f >> 4)] >> ((f & 15u) * 2u)) & 3u;
+        const unsigned n = (nmask[size_t(readId) * wordsN + (f >> 5)] >> (f & 31u)) & 1u;
+        return n ? unsigned(CODE_READ_N) : (reverse ? 3u - c : c);
+    }
+};
+
+/// Normalised penalties of AlignerBase (AlignerBase.cpp:32-43) and the Smith-Waterman scores (GappedAligner.cpp:41).
+struct ScoreParams
+{
+    uint32_t mismatch, gapOpen, gapExtend, maxGapExtend;   // unsigned like the reference (AlignerBase.hh:51-54)
+    int swMatch, swMismatch, swOpen, swExtend;             // open/extend positive
+    const double *logMatch;                                // 100 entries, host libm (Quality.cpp:34-66)
+    const double *logMismatch;
+};
+
+} // namespace isaac_b200

@@ -1,0 +1,434 @@
+// C ABI of the B200 candidate-extension path (include/isaac_ext.h): context, resident data, launches.
+// There is no CPU implementation behind any of these entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace isaac_b200;
+
+namespace
+{
+thread_local std::string g_createError;
+
+template <class T> struct DeviceBuffer
+{
+    T *p = nullptr; size_t capacity = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= capacity) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; capacity = 0;
+        const cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) capacity = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; capacity = 0; }
+};
+} // namespace
+
+struct isaac_ext_ctx
+{
+    isaac_ext_config_t cfg;
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+
+    // score tables (host libm, Quality.cpp:34-66) and parameters
+    DeviceBuffer<double> tables;
+    ScoreParams sp;
+
+    // resident reference
+    DeviceBuffer<uint32_t> refBases2, refNmask;
+    DeviceBuffer<uint64_t> refContigOffset, refContigLength;
+    std::vector<uint64_t> contigLength;
+    ReferenceView ref{};
+    bool haveReference = false;
+
+    // resident read set
+    DeviceBuffer<uint32_t> readBases2, readNmask;
+    DeviceBuffer<uint8_t> readQuality, bclStage;
+    DeviceBuffer<uint16_t> readMasked;
+    ReadSetView reads{};
+    bool haveReads = false;
+
+    // staging for the host-pointer entry points
+    DeviceBuffer<isaac_ext_candidate_t> dCandidates;
+    DeviceBuffer<isaac_ext_fragment_t> dFragments;
+    DeviceBuffer<uint32_t> dCigars;
+    DeviceBuffer<uint64_t> dMasks;
+    DeviceBuffer<uint32_t> tbScratch;
+    DeviceBuffer<uint32_t> errorFlag;
+    DeviceBuffer<unsigned char> dAscii;
+    DeviceBuffer<uint64_t> dOffsets;
+    DeviceBuffer<uint32_t> dLengths;
+
+    int fail(int code, const std::string &what) { error = what; return code; }
+    int cuda(cudaError_t e, const char *what)
+    {
+        if (e == cudaSuccess) return ISAAC_EXT_OK;
+        error = std::string(what) + ": " + cudaGetErrorString(e);
+        return ISAAC_EXT_E_CUDA;
+    }
+};
+
+#define CK(call) do { const int rc_ = ctx->cuda((call), #call); if (rc_) return rc_; } while (0)
+
+namespace
+{
+
+const unsigned SW_BLOCK = 128;
+
+/// grid of a persistent-style launch: a multiple of the SM count, at most 'perSm' blocks per SM
+unsigned gridFor(const isaac_ext_ctx *ctx, uint64_t items, unsigned block, unsigned perSm)
+{
+    const uint64_t needed = (items + block - 1) / block;
+    const uint64_t cap = uint64_t(ctx->smCount) * perSm;
+    return unsigned(std::max<uint64_t>(1, std::min(needed, cap)));
+}
+
+/// The overflow guard of the BandedSmithWaterman constructor (BandedSmithWaterman.cpp:47-53) plus the condition under
+/// which the reference's wrapping int16 arithmetic never wraps (sw.cuh).
+bool swScoresSupported(int match, int mismatch, int open, int ext, unsigned maxReadLength, std::string &why)
+{
+    const int init = -32768 + open;
+    const int maxScore = std::max(std::max(std::max(std::abs(match), std::abs(mismatch)), std::abs(open)), std::abs(ext));
+    if (long(maxReadLength) * maxScore >= std::abs(init))
+    {
+        why = "BandedSmithWaterman: unsupported read length for these scores: use smaller scores or shorter reads";
+        return false;
+    }
+    if (match < 0 || mismatch > 0 || open < 0 || ext < 0 || ext > open)
+    {
+        why = "BandedSmithWaterman: scores must satisfy match >= 0 >= mismatch and 0 <= gapExtend <= gapOpen";
+        return false;
+    }
+    return true;
+}
+
+int ensureTraceback(isaac_ext_ctx *ctx, unsigned grid, unsigned block, unsigned maxQueryLength)
+{
+    const size_t words = size_t(grid) * block * 3 * maxQueryLength;
+    return ctx->cuda(ctx->tbScratch.reserve(words), "cudaMalloc(traceback scratch)");
+}
+
+int checkErrorFlag(isaac_ext_ctx *ctx)
+{
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->errorFlag.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag)
+    {
+        cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream);
+        return ctx->fail(ISAAC_EXT_E_CAPACITY, "a gapped CIGAR did not fit the cigar stride");
+    }
+    return ISAAC_EXT_OK;
+}
+
+} // namespace
+
+extern "C" const char *isaac_ext_version(void) { return "isaac-ext-b200 0.1 (sm_100a)"; }
+
+extern "C" const char *isaac_ext_last_error(const isaac_ext_ctx *ctx)
+{
+    return ctx ? ctx->error.c_str() : g_createError.c_str();
+}
+
+extern "C" uint64_t isaac_ext_launch_count(const isaac_ext_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx **out)
+{
+    if (!config || !out) { g_createError = "null argument"; return ISAAC_EXT_E_INVALID_ARG; }
+    *out = nullptr;
+    if (config->avoidSmithWaterman) { g_createError = "--avoid-smith-waterman is not supported"; return ISAAC_EXT_E_UNSUPPORTED; }
+    std::string why;
+    if (!swScoresSupported(config->gapMatchScore, config->gapMismatchScore, -config->gapOpenScore, -config->gapExtendScore,
+                           config->maxReadLength, why))
+    {
+        g_createError = why;
+        return ISAAC_EXT_E_INVALID_ARG;     // reference: common::InvalidParameterException
+    }
+    if (!config->maxReadLength || config->maxReadLength > ISAAC_EXT_MAX_CYCLES)
+    {
+        g_createError = "maxReadLength must be in [1, 1024]";
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || config->device >= count)
+    {
+        g_createError = "no usable CUDA device (this library has no CPU fallback)";
+        return ISAAC_EXT_E_NO_DEVICE;
+    }
+    isaac_ext_ctx *ctx = new isaac_ext_ctx();
+    ctx->cfg = *config;
+    ctx->device = config->device;
+    int rc = ctx->cuda(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (!rc) rc = ctx->cuda(cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, ctx->device), "cudaDeviceGetAttribute");
+    if (!rc) rc = ctx->cuda(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!rc) rc = ctx->cuda(ctx->tables.reserve(200), "cudaMalloc(tables)");
+    if (!rc) rc = ctx->cuda(ctx->errorFlag.reserve(1), "cudaMalloc(flag)");
+    if (!rc) rc = ctx->cuda(cudaMemset(ctx->errorFlag.p, 0, sizeof(uint32_t)), "cudaMemset(flag)");
+    if (!rc)
+    {
+        // Quality::logMatchLookup / logMismatchLookup, computed with the host libm like the reference (Quality.cpp:34-66)
+        double t[200];
+        t[0] = std::log(1.0 - std::pow(10.0, 1.0 / -10.0));
+        for (int q = 1; q < 100; ++q) t[q] = std::log(1.0 - std::pow(10.0, double(q) / -10.0));
+        t[100] = t[0];
+        for (int q = 1; q < 100; ++q) t[100 + q] = std::log(std::pow(10.0, double(q) / -10.0) / 3.0);
+        rc = ctx->cuda(cudaMemcpy(ctx->tables.p, t, sizeof(t), cudaMemcpyHostToDevice), "cudaMemcpy(tables)");
+    }
+    if (rc) { g_createError = ctx->error; delete ctx; return rc; }
+    ctx->sp.mismatch = uint32_t(config->gapMatchScore - config->gapMismatchScore);     // AlignerBase.cpp:38-41
+    ctx->sp.gapOpen = uint32_t(config->gapMatchScore - config->gapOpenScore);
+    ctx->sp.gapExtend = uint32_t(config->gapMatchScore - config->gapExtendScore);
+    ctx->sp.maxGapExtend = uint32_t(-config->minGapExtendScore);
+    ctx->sp.swMatch = config->gapMatchScore; ctx->sp.swMismatch = config->gapMismatchScore;
+    ctx->sp.swOpen = -config->gapOpenScore; ctx->sp.swExtend = -config->gapExtendScore;   // GappedAligner.cpp:41
+    ctx->sp.logMatch = ctx->tables.p; ctx->sp.logMismatch = ctx->tables.p + 100;
+    *out = ctx;
+    return ISAAC_EXT_OK;
+}
+
+extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->tables.release(); ctx->refBases2.release(); ctx->refNmask.release(); ctx->refContigOffset.release();
+    ctx->refContigLength.release(); ctx->readBases2.release(); ctx->readNmask.release(); ctx->readQuality.release();
+    ctx->bclStage.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
+    ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
+    ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
+    delete ctx;
+}
+
+extern "C" int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount, const char *const *contigBases,
+                                       const uint64_t *contigLengths)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!contigCount || !contigBases || !contigLengths) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "empty reference");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> offset(contigCount);
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < contigCount; ++c)
+    {
+        offset[c] = total;
+        total += (contigLengths[c] + 127) / 128 * 128;     // every contig starts on a 128-base boundary
+    }
+    total += 128;                                          // zero padding so that window reads may run past the end
+    CK(ctx->refBases2.reserve(total / 16));
+    CK(ctx->refNmask.reserve(total / 32));
+    CK(cudaMemsetAsync(ctx->refBases2.p, 0, total / 16 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->refNmask.p, 0, total / 32 * sizeof(uint32_t), ctx->stream));
+    CK(ctx->refContigOffset.reserve(contigCount));
+    CK(ctx->refContigLength.reserve(contigCount));
+    CK(cudaMemcpyAsync(ctx->refContigOffset.p, offset.data(), contigCount * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->refContigLength.p, contigLengths, contigCount * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    // pack in chunks so that a human-size contig does not need its ASCII form resident at once
+    const uint64_t chunk = uint64_t(256) << 20;
+    CK(ctx->dAscii.reserve(std::min<uint64_t>(chunk, *std::max_element(contigLengths, contigLengths + contigCount))));
+    for (uint32_t c = 0; c < contigCount; ++c)
+    {
+        for (uint64_t done = 0; done < contigLengths[c]; done += chunk)
+        {
+            const uint64_t n = std::min(chunk, contigLengths[c] - done);
+            CK(cudaMemcpyAsync(ctx->dAscii.p, contigBases[c] + done, n, cudaMemcpyHostToDevice, ctx->stream));
+            packReferenceKernel<<<gridFor(ctx, (n + 31) / 32, 256, 16), 256, 0, ctx->stream>>>(
+                ctx->dAscii.p, n, offset[c] + done, ctx->refBases2.p, ctx->refNmask.p);
+            ++ctx->launches;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(ctx->stream));       // dAscii is reused by the next chunk
+        }
+    }
+    ctx->contigLength.assign(contigLengths, contigLengths + contigCount);
+    ctx->ref.bases2 = ctx->refBases2.p; ctx->ref.nmask = ctx->refNmask.p;
+    ctx->ref.contigOffset = ctx->refContigOffset.p; ctx->ref.contigLength = ctx->refContigLength.p;
+    ctx->ref.contigCount = contigCount;
+    ctx->haveReference = true;
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *r)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!r || !r->bcl || !r->clusterCount || r->readCount < 1 || r->readCount > 2) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "bad read set");
+    const uint32_t len0 = r->readLength[0], len1 = r->readCount > 1 ? r->readLength[1] : 0;
+    const uint32_t maxLen = std::max(len0, len1);
+    if (!len0 || (r->readCount > 1 && !len1) || maxLen > ISAAC_EXT_MAX_CYCLES || len0 + len1 > ctx->cfg.maxReadLength)
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "read lengths exceed config.maxReadLength (flowcell::getMaxTotalReadLength)");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t readTotal = uint64_t(r->clusterCount) * r->readCount;
+    const uint32_t wordsN = (maxLen + 31) / 32, words2 = wordsN * 2, qualityStride = wordsN * 32;
+    const uint64_t bclBytes = uint64_t(r->clusterCount) * (len0 + len1);
+    CK(ctx->readBases2.reserve(readTotal * words2));
+    CK(ctx->readNmask.reserve(readTotal * wordsN));
+    CK(ctx->readQuality.reserve(readTotal * qualityStride));
+    CK(ctx->readMasked.reserve(readTotal));
+    CK(ctx->bclStage.reserve(bclBytes));
+    CK(cudaMemcpyAsync(ctx->bclStage.p, r->bcl, bclBytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (r->endCyclesMasked)
+        CK(cudaMemcpyAsync(ctx->readMasked.p, r->endCyclesMasked, readTotal * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CK(cudaMemsetAsync(ctx->readMasked.p, 0, readTotal * sizeof(uint16_t), ctx->stream));
+    decodeBclKernel<<<gridFor(ctx, readTotal * wordsN, 256, 16), 256, 0, ctx->stream>>>(
+        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, words2, wordsN, qualityStride,
+        ctx->readBases2.p, ctx->readNmask.p, ctx->readQuality.p);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ReadSetView &v = ctx->reads;
+    v.bases2 = ctx->readBases2.p; v.nmask = ctx->readNmask.p; v.quality = ctx->readQuality.p; v.endCyclesMasked = ctx->readMasked.p;
+    v.words2 = words2; v.wordsN = wordsN; v.qualityStride = qualityStride; v.readCount = r->readCount;
+    v.readLength[0] = len0; v.readLength[1] = len1; v.firstCycle[0] = r->firstCycle[0]; v.firstCycle[1] = r->firstCycle[1];
+    v.readTotal = uint32_t(readTotal);
+    ctx->haveReads = true;
+    return ISAAC_EXT_OK;
+}
+
+static int validateCandidates(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *c)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t contig = c[i].contigStrand >> 1;
+        if (c[i].readId >= ctx->reads.readTotal || contig >= ctx->ref.contigCount)
+            return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "candidate refers to an unknown read or contig");
+        // FragmentBuilder::addMatch / ShadowAligner never place a read beyond the contig end
+        if (c[i].position > int64_t(ctx->contigLength[contig]) || c[i].position < -int64_t(ISAAC_EXT_MAX_CYCLES))
+            return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "candidate position outside [-readLength, contigLength]");
+    }
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_ungapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, void *dFragmentsOut,
+                                               void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
+    if (!n) return ISAAC_EXT_OK;
+    ungappedKernel<<<gridFor(ctx, n, 128, 16), 128, 0, cudaStream_t(cudaStream)>>>(
+        ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates),
+        static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
+        static_cast<uint64_t *>(dMismatchMaskOut));
+    ++ctx->launches;
+    return ctx->cuda(cudaGetLastError(), "ungappedKernel");
+}
+
+extern "C" int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, uint32_t cigarStride,
+                                             void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
+    if (!n) return ISAAC_EXT_OK;
+    const unsigned grid = gridFor(ctx, n, SW_BLOCK, 8);
+    const int rc = ensureTraceback(ctx, grid, SW_BLOCK, std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]));
+    if (rc) return rc;
+    gappedKernel<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
+        ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
+        static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
+        static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p);
+    ++ctx->launches;
+    return ctx->cuda(cudaGetLastError(), "gappedKernel");
+}
+
+static int extendHost(isaac_ext_ctx *ctx, bool gapped, uint32_t n, const isaac_ext_candidate_t *candidates, uint32_t cigarStride,
+                      isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *maskOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
+    if (!n) return ISAAC_EXT_OK;
+    if (!candidates || !fragmentsOut || !cigarOut || cigarStride < 3) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
+    int rc = validateCandidates(ctx, n, candidates);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dCandidates.reserve(n));
+    CK(ctx->dFragments.reserve(n));
+    CK(ctx->dCigars.reserve(size_t(n) * cigarStride));
+    if (maskOut) CK(ctx->dMasks.reserve(size_t(n) * ISAAC_EXT_MASK_WORDS));
+    CK(cudaMemcpyAsync(ctx->dCandidates.p, candidates, size_t(n) * sizeof(*candidates), cudaMemcpyHostToDevice, ctx->stream));
+    rc = gapped ? isaac_ext_gapped_batch_device(ctx, n, ctx->dCandidates.p, cigarStride, ctx->dFragments.p, ctx->dCigars.p,
+                                                maskOut ? ctx->dMasks.p : nullptr, ctx->stream)
+                : isaac_ext_ungapped_batch_device(ctx, n, ctx->dCandidates.p, ctx->dFragments.p, ctx->dCigars.p,
+                                                  maskOut ? ctx->dMasks.p : nullptr, ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(fragmentsOut, ctx->dFragments.p, size_t(n) * sizeof(*fragmentsOut), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cigarOut, ctx->dCigars.p, size_t(n) * cigarStride * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (maskOut)
+        CK(cudaMemcpyAsync(maskOut, ctx->dMasks.p, size_t(n) * ISAAC_EXT_MASK_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return gapped ? checkErrorFlag(ctx) : ctx->cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+}
+
+extern "C" int isaac_ext_ungapped_batch(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                        isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *mismatchMaskOut)
+{
+    return extendHost(ctx, false, n, candidates, 3, fragmentsOut, cigarOut, mismatchMaskOut);
+}
+
+extern "C" int isaac_ext_gapped_batch(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates, uint32_t cigarStride,
+                                      isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *mismatchMaskOut)
+{
+    return extendHost(ctx, true, n, candidates, cigarStride, fragmentsOut, cigarOut, mismatchMaskOut);
+}
+
+extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                                         const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                                         int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                                         uint32_t cigarStride, uint32_t *cigarOut, uint32_t *cigarLengthOut, uint32_t *offsetOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!n) return ISAAC_EXT_OK;
+    if (!queries || !queryOffsets || !queryLengths || !databases || !databaseOffsets || !cigarOut || !cigarLengthOut || !offsetOut || !cigarStride)
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
+    uint32_t maxLen = 0; uint64_t qBytes = 0, dBytes = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (!queryLengths[i]) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "empty query");
+        maxLen = std::max(maxLen, queryLengths[i]);
+        qBytes = std::max(qBytes, queryOffsets[i] + queryLengths[i]);
+        dBytes = std::max(dBytes, databaseOffsets[i] + queryLengths[i] + 15);
+    }
+    std::string why;
+    // assert(querySize <= maxReadLength_) (BandedSmithWaterman.cpp:94) and the constructor's guard
+    if (maxLen > ctx->cfg.maxReadLength) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "query longer than config.maxReadLength");
+    if (!swScoresSupported(matchScore, mismatchScore, gapOpenScore, gapExtendScore, ctx->cfg.maxReadLength, why))
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, why);
+    for (uint64_t i = 0; i < qBytes; ++i)
+    {
+        const char c = queries[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'n') return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "query alphabet is ACGTn");
+    }
+    for (uint64_t i = 0; i < dBytes; ++i)
+    {
+        const char c = databases[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "database alphabet is ACGTN");
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dAscii.reserve(qBytes + dBytes));
+    CK(ctx->dOffsets.reserve(size_t(n) * 2));
+    CK(ctx->dLengths.reserve(size_t(n) * 3));
+    CK(ctx->dCigars.reserve(size_t(n) * cigarStride));
+    CK(cudaMemcpyAsync(ctx->dAscii.p, queries, qBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dAscii.p + qBytes, databases, dBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dOffsets.p, queryOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dOffsets.p + n, databaseOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dLengths.p, queryLengths, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = gridFor(ctx, n, SW_BLOCK, 8);
+    int rc = ensureTraceback(ctx, grid, SW_BLOCK, maxLen);
+    if (rc) return rc;
+    const SwScores sw = {matchScore, mismatchScore, gapOpenScore, gapExtendScore, -32768 + gapOpenScore};
+    bandedSwAsciiKernel<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
+                                                            ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
+                                                            ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cigarOut, ctx->dCigars.p, size_t(n) * cigarStride * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cigarLengthOut, ctx->dLengths.p + n, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(offsetOut, ctx->dLengths.p + 2 * size_t(n), size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return checkErrorFlag(ctx);
+}

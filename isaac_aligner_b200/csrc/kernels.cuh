@@ -1,0 +1,246 @@
+// Kernels of the candidate-extension path (first, scalar generation).
+//   packReferenceKernel   K0  ASCII contig -> 2-bit + N-mask            (ContigLoader product, ContigLoader.cpp:29-65)
+//   decodeBclKernel       K0b BCL bytes -> 2-bit + n-mask + qualities   (Read::decodeBcl, Read.cpp:32-73)
+//   ungappedKernel        K1  UngappedAligner::alignUngapped            (UngappedAligner.cpp:39-92)
+//   gappedKernel          K2+K4 GappedAligner::alignGapped = clipping + banded SW + traceback + re-score
+//                                                                        (GappedAligner.cpp:167-249)
+//   bandedSwAsciiKernel   K2  BandedSmithWaterman::align on explicit (query, database) strings
+#pragma once
+#include "device_types.cuh"
+#include "score.cuh"
+#include "sw.cuh"
+
+namespace isaac_b200
+{
+
+__device__ __forceinline__ unsigned asciiRefCode(unsigned char c)
+{
+    switch (c)
+    {
+    case 'A': case 'a': return 0u;
+    case 'C': case 'c': return 1u;
+    case 'G': case 'g': return 2u;
+    case 'T': case 't': return 3u;
+    default: return CODE_REF_N;
+    }
+}
+
+/// One thread packs 32 bases: two 2-bit words and one mask word.  'ascii' holds 'count' bases that land at global
+/// base index 'dstBase' (a multiple of 32).
+__global__ void packReferenceKernel(const unsigned char *__restrict__ ascii, uint64_t count, uint64_t dstBase,
+                                    uint32_t *__restrict__ bases2, uint32_t *__restrict__ nmask)
+{
+    const uint64_t groups = (count + 31) / 32;
+    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < groups; t += uint64_t(gridDim.x) * blockDim.x)
+    {
+        uint32_t lo = 0, hi = 0, m = 0;
+        const uint64_t first = t * 32;
+#pragma unroll 8
+        for (unsigned k = 0; k < 32; ++k)
+        {
+            const uint64_t i = first + k;
+            const unsigned c = i < count ? asciiRefCode(ascii[i]) : 0u;
+            const unsigned two = c > 3u ? 0u : c;
+            if (k < 16) lo |= two << (2 * k); else hi |= two << (2 * (k - 16));
+            m |= (c > 3u ? 1u : 0u) << k;
+        }
+        const uint64_t w = (dstBase + first) >> 5;
+        bases2[2 * w] = lo; bases2[2 * w + 1] = hi; nmask[w] = m;
+    }
+}
+
+/// One thread decodes 32 consecutive cycles of one read.
+__global__ void decodeBclKernel(const uint8_t *__restrict__ bcl, uint32_t clusterCount, uint32_t readCount,
+                                uint32_t len0, uint32_t len1, uint32_t words2, uint32_t wordsN, uint32_t qualityStride,
+                                uint32_t *__restrict__ bases2, uint32_t *__restrict__ nmask, uint8_t *__restrict__ quality)
+{
+    const uint32_t groupsPerRead = wordsN;
+    const uint64_t total = uint64_t(clusterCount) * readCount * groupsPerRead;
+    const uint32_t clusterBytes = len0 + (readCount > 1 ? len1 : 0);
+    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < total; t += uint64_t(gridDim.x) * blockDim.x)
+    {
+        const uint32_t grp = uint32_t(t % groupsPerRead);
+        const uint64_t readId = t / groupsPerRead;
+        const uint32_t readIndex = uint32_t(readId % readCount);
+        const uint64_t cluster = readId / readCount;
+        const uint32_t L = readIndex ? len1 : len0;
+        const uint8_t *src = bcl + cluster * clusterBytes + (readIndex ? len0 : 0);
+        uint32_t lo = 0, hi = 0, m = 0;
+#pragma unroll 8
+        for (unsigned k = 0; k < 32; ++k)
+        {
+            const uint32_t i = grp * 32 + k;
+            if (i < L)
+            {
+                const unsigned b = src[i];
+                const bool isN = !(b & 0xfcu);                              // oligo::isBclN (Nucleotides.hh:91-94)
+                const unsigned two = isN ? 0u : (b & 3u);
+                if (k < 16) lo |= two << (2 * k); else hi |= two << (2 * (k - 16));
+                m |= (isN ? 1u : 0u) << k;
+                quality[readId * qualityStride + i] = isN ? 2 : uint8_t(b >> 2);   // Read.cpp:60,66
+            }
+        }
+        bases2[readId * words2 + 2 * grp] = lo;
+        if (2 * grp + 1 < words2) bases2[readId * words2 + 2 * grp + 1] = hi;
+        nmask[readId * wordsN + grp] = m;
+    }
+}
+
+__device__ __forceinline__ void initFragment(isaac_ext_fragment_t &o, const isaac_ext_candidate_t &c, uint32_t readCount)
+{
+    o.position = c.position; o.logProbability = 0.0; o.contigId = c.contigStrand >> 1; o.readId = c.readId;
+    o.cigarOffset = 0; o.smithWatermanScore = 0; o.observedLength = 0; o.mismatchCount = 0; o.matchesInARow = 0;
+    o.gapCount = 0; o.editDistance = 0; o.uniqueSeedCount = 0; o.repeatSeedsCount = 0;
+    o.nonUniqueSeedOffsetFirst = 0xFFFF; o.nonUniqueSeedOffsetSecond = 0; o.firstSeedIndex = -1;
+    o.lowClipped = 0; o.highClipped = 0; o.cigarLength = 0; o.reverse = uint8_t(c.contigStrand & 1u);
+    o.readIndex = uint8_t(c.readId % readCount); o.matchCount = 0;
+}
+
+/// K1: one candidate per thread.
+__global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+                               const isaac_ext_candidate_t *__restrict__ candidates,
+                               isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
+                               uint64_t *__restrict__ masks)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const isaac_ext_candidate_t c = candidates[i];
+        isaac_ext_fragment_t o;
+        initFragment(o, c, reads.readCount);
+        const unsigned contigId = c.contigStrand >> 1;
+        const unsigned L = reads.length(c.readId);
+        uint64_t *mask = masks ? masks + size_t(i) * ISAAC_EXT_MASK_WORDS : nullptr;
+        if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
+        uint32_t *cigar = cigars + size_t(i) * 3;
+        o.cigarOffset = i * 3;
+        // resetAlignment + resetClipping: position is the unclipped candidate position, clips are 0 (UngappedAligner.cpp:48-49)
+        FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};
+        long begin = 0, end = L;
+        clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :60
+        const bool inside = clipReference(long(ref.contigLength[contigId]), f, begin, end);   // :62
+        o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;
+        if (inside)
+        {
+            uint32_t ops[3]; unsigned nOps = 0;
+            if (begin) ops[nOps++] = cigarWord(uint32_t(begin), ISAAC_EXT_CIGAR_SOFT_CLIP);            // :64-68
+            if (end - begin) ops[nOps++] = cigarWord(uint32_t(end - begin), ISAAC_EXT_CIGAR_ALIGN);    // :70-75
+            if (long(L) - end) ops[nOps++] = cigarWord(uint32_t(L - end), ISAAC_EXT_CIGAR_SOFT_CLIP);  // :77-81
+            const unsigned matchCount = scoreCigar(ref, reads, sp, c.readId, L, f.reverse, ref.contigOffset[contigId],
+                                                   f.position, ops, nOps, o, mask);
+            for (unsigned k = 0; k < 3; ++k) cigar[k] = k < nOps ? ops[k] : 0u;
+            o.cigarLength = matchCount ? uint16_t(nOps) : 0;                                           // setUnaligned (:86-89)
+        }
+        fragments[i] = o;
+    }
+}
+
+struct ResidentBaseSrc
+{
+    const ReferenceView &ref; const ReadSetView &reads;
+    unsigned readId, L; bool reverse; unsigned qBegin; uint64_t dBegin;
+    __device__ __forceinline__ unsigned q(unsigned i) const { unsigned qq; return reads.code(readId, L, reverse, qBegin + i, qq); }
+    __device__ __forceinline__ unsigned d(unsigned k) const { return ref.code(dBegin + k); }
+};
+
+constexpr unsigned SW_OPS_CAP = 64;
+
+/// K2+K4: one candidate per thread: clip, banded Smith-Waterman, traceback, re-score the gapped CIGAR.
+__global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+                             const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
+                             isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
+                             uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
+{
+    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
+    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
+    const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const isaac_ext_candidate_t c = candidates[i];
+        isaac_ext_fragment_t o;
+        initFragment(o, c, reads.readCount);
+        const unsigned contigId = c.contigStrand >> 1;
+        const unsigned L = reads.length(c.readId);
+        const long contigLength = long(ref.contigLength[contigId]);
+        uint64_t *mask = masks ? masks + size_t(i) * ISAAC_EXT_MASK_WORDS : nullptr;
+        if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
+        uint32_t *cigar = cigars + size_t(i) * cigarStride;
+        o.cigarOffset = i * cigarStride;
+        FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};              // GappedAligner.cpp:175-176
+        long begin = 0, end = L;
+        clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :187
+        const bool inside = clipReference(contigLength, f, begin, end);                 // :189
+        o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;
+        const unsigned sequenceLength = unsigned(end - begin);
+        long strandPosition = f.position;
+        // no gapped alignment if the reference is too short (:204-208)
+        if (inside && sequenceLength && !(contigLength < long(sequenceLength) + strandPosition + 16))
+        {
+            // getFlanks (:51-82)
+            unsigned left, right;
+            if (strandPosition >= 8)
+            {
+                if (strandPosition + sequenceLength + 8 < contigLength) { left = 8; right = 7; }
+                else { right = unsigned(contigLength - sequenceLength - strandPosition); left = 16 - right - 1; }
+            }
+            else { left = unsigned(strandPosition); right = 16 - left - 1; }
+            (void)right;
+            const ResidentBaseSrc src = {ref, reads, c.readId, L, f.reverse, unsigned(begin),
+                                         ref.contigOffset[contigId] + uint64_t(strandPosition - left)};
+            uint32_t ops[SW_OPS_CAP + 2];
+            unsigned nSw = 0; bool overflow = false;
+            unsigned nOps = 0;
+            uint32_t *swOps = ops + 1;
+            const unsigned ret = bandedSwAlign(src, sequenceLength, sw, tb, tbStride, swOps, SW_OPS_CAP, nSw, overflow);   // :231
+            uint32_t *all = swOps;
+            nOps = nSw;
+            if (begin) { ops[0] = cigarWord(uint32_t(begin), ISAAC_EXT_CIGAR_SOFT_CLIP); all = ops; ++nOps; }           // :191-195
+            if (long(L) - end) all[nOps++] = cigarWord(uint32_t(L - end), ISAAC_EXT_CIGAR_SOFT_CLIP);                   // :233-237
+            strandPosition += long(ret) - long(left);                                                                    // :231,240
+            if (overflow || nOps > cigarStride) { atomicOr(errorFlag, 1u); }
+            else
+            {
+                const unsigned matchCount = scoreCigar(ref, reads, sp, c.readId, L, f.reverse, ref.contigOffset[contigId],
+                                                       strandPosition, all, nOps, o, mask);                              // :245
+                for (unsigned k = 0; k < nOps; ++k) cigar[k] = all[k];
+                o.cigarLength = uint16_t(nOps);
+                (void)matchCount;
+            }
+        }
+        fragments[i] = o;
+    }
+}
+
+struct AsciiBaseSrc
+{
+    const unsigned char *query; const unsigned char *database;
+    __device__ __forceinline__ static unsigned qcode(unsigned char c)
+    {
+        switch (c) { case 'A': return 0u; case 'C': return 1u; case 'G': return 2u; case 'T': return 3u; default: return CODE_READ_N; }
+    }
+    __device__ __forceinline__ unsigned q(unsigned i) const { return qcode(query[i]); }
+    __device__ __forceinline__ unsigned d(unsigned k) const { return asciiRefCode(database[k]); }
+};
+
+/// BandedSmithWaterman::align on explicit strings (unit parity with testBandedSmithWaterman.cpp and kernel timing).
+__global__ void bandedSwAsciiKernel(uint32_t n, const unsigned char *__restrict__ queries, const uint64_t *__restrict__ queryOffsets,
+                                    const uint32_t *__restrict__ queryLengths, const unsigned char *__restrict__ databases,
+                                    const uint64_t *__restrict__ databaseOffsets, const SwScores sw, uint32_t cigarStride,
+                                    uint32_t *__restrict__ cigars, uint32_t *__restrict__ cigarLengths, uint32_t *__restrict__ offsets,
+                                    uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
+{
+    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
+    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const AsciiBaseSrc src = {queries + queryOffsets[i], databases + databaseOffsets[i]};
+        uint32_t ops[SW_OPS_CAP];
+        unsigned nOps = 0; bool overflow = false;
+        const unsigned ret = bandedSwAlign(src, queryLengths[i], sw, tb, tbStride, ops, SW_OPS_CAP, nOps, overflow);
+        if (overflow) atomicOr(errorFlag, 1u);
+        offsets[i] = ret;
+        cigarLengths[i] = nOps;
+        for (unsigned k = 0; k < nOps && k < cigarStride; ++k) cigars[size_t(i) * cigarStride + k] = ops[k];
+    }
+}
+
+} // namespace isaac_b200

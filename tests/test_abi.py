@@ -1,0 +1,60 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports exactly what include/isaac_ext.h
+declares; struct layouts agree; compute without a device fails loudly (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "isaac_ext.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(isaac_ext_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from isaac_aligner_b200 import capi
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    declared = header_functions()
+    assert declared, "no functions parsed from the header"
+    for name in declared:
+        assert hasattr(lib, name), "libisaac_ext.so does not export " + name
+    assert sorted(capi.EXPORTS) == declared
+
+
+def test_struct_layouts_match_header():
+    from isaac_aligner_b200.types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, Config, Reads
+    assert FRAGMENT_DTYPE.itemsize == 64 and CANDIDATE_DTYPE.itemsize == 16
+    assert ctypes.sizeof(Config) == 13 * 4
+    assert ctypes.sizeof(Reads) == 6 * 4 + 2 * 8
+    assert FRAGMENT_DTYPE.fields["matchCount"][1] == 62 and FRAGMENT_DTYPE.fields["observedLength"][1] == 32
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the library must refuse to compute instead of silently using the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from isaac_aligner_b200 import capi
+    from isaac_aligner_b200.types import Config
+    with pytest.raises(capi.ExtError) as e:
+        capi.Context(Config.default())
+    assert e.value.code == 2   # ISAAC_EXT_E_NO_DEVICE
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under isaac_aligner_b200/ may include, link or load anything under oracle/."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "isaac_aligner_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hh", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"oracle[_/]|libisaac_oracle|libisaac_ref|oracle_api", text):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,81 @@
+"""Parity of the CUDA path (through the C ABI, libisaac_ext.so) with the CPU oracle, bit-exact.
+The checker is the scalar restatement oracle/isaac_oracle.cpp and, when it travelled to this box, the reference's own
+code (oracle/_ref/libisaac_ref.so).  /root/reference is never read here."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from common import assert_fragments_equal, random_sw_cases, small_workload
+from isaac_aligner_b200.types import BWA_SCORES, ELAND_SCORES, Config
+
+pytestmark = pytest.mark.gpu
+
+
+def checkers():
+    out = [oracle_lib.port()]
+    if os.path.exists(oracle_lib.REF_SO):
+        out.append(oracle_lib.Oracle(oracle_lib.REF_SO))
+    return out
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from isaac_aligner_b200 import capi
+    return capi
+
+
+@pytest.mark.parametrize("scores", [(0, -3, 11, 4), (2, -1, 15, 3)])
+def test_banded_sw_bit_exact(capi, scores):
+    queries, dbs = random_sw_cases(20000, seed=101 + scores[0])
+    ctx = capi.Context(Config.default(max_read_length=300))
+    cg, lg, og = ctx.banded_sw(queries, dbs, scores)
+    for chk in checkers():
+        cr, lr, orf = chk.banded_sw(queries, dbs, scores, max_read_length=300, threads=8)
+        assert np.array_equal(lg, lr), chk.kind
+        assert np.array_equal(og, orf), chk.kind
+        assert np.array_equal(cg, cr), chk.kind
+    ctx.close()
+
+
+@pytest.mark.parametrize("scores,L", [(BWA_SCORES, 100), (ELAND_SCORES, 100), (BWA_SCORES, 150), (BWA_SCORES, 250)])
+def test_ungapped_bit_exact(capi, scores, L):
+    genome, sim, reads, cand = small_workload(n_pairs=3000, L=L, seed=55 + L)
+    ctx = capi.Context(Config.default(scores, max_read_length=2 * L))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    fg, cg, mg = ctx.ungapped(cand)
+    g = oracle_lib.GenomeHolder(genome)
+    for chk in checkers():
+        fr, cr, mr = chk.ungapped(g, reads, ctx.config, cand, threads=8)
+        assert_fragments_equal(fg, fr, cg, cr, mg, mr, "ungapped cuda vs " + chk.kind)
+    ctx.close()
+
+
+@pytest.mark.parametrize("scores,L", [(BWA_SCORES, 100), (ELAND_SCORES, 100), (BWA_SCORES, 150), (BWA_SCORES, 250)])
+def test_gapped_bit_exact(capi, scores, L):
+    genome, sim, reads, cand = small_workload(n_pairs=3000, L=L, seed=77 + L, indel_rate=6e-3)
+    ctx = capi.Context(Config.default(scores, max_read_length=2 * L))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    fg, cg, mg = ctx.gapped(cand)
+    g = oracle_lib.GenomeHolder(genome)
+    for chk in checkers():
+        fr, cr, mr = chk.gapped(g, reads, ctx.config, cand, threads=8)
+        assert_fragments_equal(fg, fr, cg, cr, mg, mr, "gapped cuda vs " + chk.kind)
+    assert (fg["gapCount"] > 0).any()
+    ctx.close()
+
+
+def test_errors_are_loud(capi):
+    # the reference throws InvalidParameterException for overflow-prone score/length combinations
+    # (BandedSmithWaterman.cpp:47-53, testBandedSmithWaterman.cpp:214-225)
+    with pytest.raises(capi.ExtError) as e:
+        capi.Context(Config.default((2, -1, -15, -3, -25), max_read_length=1024 * 3))
+    assert e.value.code == 1
+    ctx = capi.Context(Config.default(max_read_length=300))
+    with pytest.raises(capi.ExtError) as e:
+        ctx.ungapped(np.zeros(1, dtype=capi.CANDIDATE_DTYPE))
+    assert e.value.code == 6      # no reference yet
+    ctx.close()
