@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the candidate-extension hot path (BASELINE.json configs[1]).
+
+One "step" = one pass of the hot path over one batch of synthetic candidates: ungapped scoring (K1) of every candidate
+followed by banded Smith-Waterman + traceback + re-scoring (K2+K4) of every candidate, 150 bp reads.
+  value          banded-SW GCUPS = candidates * 16 * L cell updates / step time, inputs resident in HBM
+  e2e            the same through the C ABI with pinned HOST buffers (H2D of the candidates, D2H of all results inside
+                 the timed region)
+  roofline       dominant kernel (gappedKernel): algorithmic integer operations (23 per cell) per second
+                 against the integer-pipe peak measured live on this GPU (MEASURED_PEAKS.json has no INT32 figure)
+  cpu_baseline   the reference's own code (oracle/_ref, kind "reference") or the scalar restatement (kind "port")
+                 timed on this box's host cores on a bounded sample of the same workload
+`--impl reference` times only that CPU arm.  N > 1: one rank per GPU (torchrun), candidates sharded with no data-path
+collective (weak scaling, a fixed batch per GPU); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+OPS_PER_CELL = 23          # F 7 + G 8 + E 8 integer operations per (G,E,F) cell
+BAND = 16
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--candidates", type=int, default=10_000_000, help="(read, window) pairs per GPU and step")
+    p.add_argument("--read-length", type=int, default=150)
+    p.add_argument("--genome-bases", type=int, default=5_000_000)
+    p.add_argument("--per-read", type=int, default=8, help="candidates generated per read")
+    p.add_argument("--cigar-stride", type=int, default=32)
+    p.add_argument("--cpu-sample-per-core", type=int, default=40_000)
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def make_workload(args, rank, n_candidates):
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.types import ReadSet
+    L = args.read_length
+    genome = synth.make_genome(args.genome_bases, n_contigs=1, seed=synth.SEED_G5)
+    n_pairs = max(1, -(-n_candidates // (2 * args.per_read)))
+    sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 1 + 1000 * rank)
+    reads = ReadSet(sim.bcl, (L, L))
+    cand = synth.microbench_candidates(sim, genome, per_read=args.per_read, seed=synth.SEED_READS + 2 + 1000 * rank)
+    return genome, reads, cand[:n_candidates]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(args, genome, reads, cand, config, steps, warmup):
+    """Times the CPU implementation (all host threads) on `cand`; returns (GCUPS, seconds per step, kind, cores)."""
+    import oracle_lib
+    chk = oracle_lib.Oracle(oracle_lib.REF_SO) if os.path.exists(oracle_lib.REF_SO) else oracle_lib.port()
+    cores = os.cpu_count() or 1
+    g = oracle_lib.GenomeHolder(genome)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        chk.gapped(g, reads, config, cand, cigar_stride=args.cigar_stride, threads=cores)   # alignUngapped + alignGapped
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    cells = len(cand) * BAND * args.read_length
+    return cells / sec / 1e9, sec, chk.kind, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from isaac_aligner_b200.types import Config
+    cores = os.cpu_count() or 1
+    n = min(args.candidates, args.cpu_sample_per_core * cores)
+    genome, reads, cand = make_workload(args, 0, n)
+    config = Config.default(max_read_length=2 * args.read_length)
+    gcups, sec, kind, cores = cpu_arm(args, genome, reads, cand, config, args.steps, args.warmup)
+    sample = "%d of %d candidates per step (same generator, ungapped + gapped per candidate), %d host threads" % (
+        n, args.candidates, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "banded_sw_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": "BASELINE configs[1]: candidate-fragment microbench, %d ungapped + banded-SW extensions per GPU "
+                        "per step, %d bp reads, %d bp random genome, 60%% true / 20%% shifted / 20%% random loci, bwa scores"
+                        % (args.candidates, args.read_length, args.genome_bases),
+            "candidates_per_gpu": args.candidates, "read_length": args.read_length, "band": BAND,
+            "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2, no flush needed"
+                  % (args.candidates * (16 + 2 * 64 + (3 + args.cigar_stride) * 4) / 1e9)}
+
+
+def run_b200(args):
+    import torch
+    from isaac_aligner_b200 import capi
+    from isaac_aligner_b200.types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, Config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    L, n, stride = args.read_length, args.candidates, args.cigar_stride
+    genome, reads, cand = make_workload(args, rank, n)
+    n = len(cand)
+    config = Config.default(max_read_length=2 * L, device=local_rank)
+    ctx = capi.Context(config)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+
+    dev = torch.device("cuda", local_rank)
+    d_cand = torch.from_numpy(cand.view(np.uint8).reshape(n, 16)).to(dev)
+    d_frag_u = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    d_cig_u = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    d_frag_g = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    d_cig_g = torch.empty((n, stride), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(events=None):
+        if events:
+            events[0].record()
+        ctx.ungapped_device(n, d_cand.data_ptr(), d_frag_u.data_ptr(), d_cig_u.data_ptr(), 0, stream)
+        if events:
+            events[1].record()
+        ctx.gapped_device(n, d_cand.data_ptr(), stride, d_frag_g.data_ptr(), d_cig_g.data_ptr(), 0, stream)
+        if events:
+            events[2].record()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ctx.launches
+    t_wall0 = time.time()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for s in range(args.steps):
+        step(evs[s])
+    stop.record()
+    barrier()
+    gpu_launches = ctx.launches - launches0
+    total_ms = start.elapsed_time(stop)
+    ms_ungapped = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    ms_gapped = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    cells = float(n) * BAND * L
+
+    # ---- end to end through the host-pointer ABI, pinned buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        h_cand_t = pin((n, 16), torch.uint8)
+        h_cand_t.numpy()[:] = cand.view(np.uint8).reshape(n, 16)
+        h_cand = h_cand_t.numpy().reshape(-1).view(CANDIDATE_DTYPE)
+        out_u = (pin((n, 64), torch.uint8), pin((n, 3), torch.int32))
+        out_g = (pin((n, 64), torch.uint8), pin((n, stride), torch.int32))
+        as_out = lambda o: (o[0].numpy().reshape(-1).view(FRAGMENT_DTYPE), o[1].numpy().view(np.uint32), None)
+
+        def e2e_step():
+            ctx.ungapped(h_cand, with_masks=False, out=as_out(out_u))
+            ctx.gapped(h_cand, cigar_stride=stride, with_masks=False, out=as_out(out_g))
+
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item()) / args.steps
+        # the device results of the resident path and the host results of the e2e path must agree
+        assert np.array_equal(d_frag_g.cpu().numpy(), out_g[0].numpy()), "resident and end-to-end results differ"
+        e2e = {"value": world * cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 2 * n * 16, "d2h_bytes_per_step": n * (64 + 3 * 4) + n * (64 + stride * 4)}
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel, integer-pipe peak measured live
+    peak_add = ctx.measure_int32_peak(0)
+    peak_max = ctx.measure_int32_peak(1)
+    peak_dpx = ctx.measure_int32_peak(2)
+    sw_gcups_kernel = cells / (ms_gapped * 1e-3) / 1e9
+    achieved = sw_gcups_kernel * 1e9 * OPS_PER_CELL
+    hbm_peak = 6545.6
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "MEASURED_PEAKS.json"
+    except (OSError, KeyError, ValueError):
+        hbm_src = "fallback"
+    per_cand = -(-L // 4) + -(-L // 8) + 16 + 64 + 12       # window 2-bit + mask, descriptor, record, cigar
+    per_read = -(-L // 4) + -(-L // 8) + L
+    ungapped_gbs = (n * per_cand + reads.cluster_count * 2 * per_read) / (ms_ungapped * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gappedKernel"]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
+    # ---- CPU baseline on a bounded sample, same box
+    cores = os.cpu_count() or 1
+    ns = min(n, args.cpu_sample_per_core * cores)
+    cpu_gcups, cpu_sec, kind, cores = cpu_arm(args, genome, reads, cand[:ns], config, 1, 0)
+
+    print(json.dumps({
+        "metric": "banded_sw_gcups", "value": world * cells / (ms_per_step * 1e-3) / 1e9, "unit": "GCUPS",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "roofline": {"bound": "int32", "kernel": "gappedKernel", "achieved": achieved / 1e12, "peak": peak_add / 1e12,
+                     "unit": "TOP/s", "frac": achieved / peak_add, "traffic": traffic,
+                     "ops_per_cell": OPS_PER_CELL, "gcups_kernel": sw_gcups_kernel, "ms_per_launch": ms_gapped,
+                     "peak_source": "measured live by isaac_ext_measure_int32_peak: add.s32 %.1f, max.s32 %.1f, "
+                                    "16x2 max %.1f TOP/s" % (peak_add / 1e12, peak_max / 1e12, peak_dpx / 1e12)},
+        "roofline_ungapped": {"bound": "hbm", "kernel": "ungappedKernel", "achieved": ungapped_gbs, "peak": hbm_peak,
+                              "unit": "GB/s", "frac": ungapped_gbs / hbm_peak, "ms_per_launch": ms_ungapped,
+                              "peak_source": hbm_src, "candidates_per_s": n / (ms_ungapped * 1e-3)},
+        "cpu_baseline": {"value": cpu_gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
+                         "sample": "first %d of the %d candidates of rank 0, one pass, %d host threads, %.2f s"
+                                   % (ns, n, cores, cpu_sec)},
+    }))
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -177,6 +177,10 @@ int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dC
                                   uint32_t cigarStride, void *dFragmentsOut, void *dCigarOut,
                                   void *dMismatchMaskOut, void *cudaStream);
 
+/* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
+ * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
+int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);
+
 /* Number of kernel launches this context has issued so far (bench.py reports it as gpu_launches). */
 uint64_t isaac_ext_launch_count(const isaac_ext_ctx *ctx);
 

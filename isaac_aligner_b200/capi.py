@@ -31,7 +31,7 @@ EXPORTS = [
     "isaac_ext_create", "isaac_ext_destroy", "isaac_ext_last_error", "isaac_ext_version",
     "isaac_ext_set_reference", "isaac_ext_set_reads", "isaac_ext_banded_sw_batch", "isaac_ext_ungapped_batch",
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
-    "isaac_ext_launch_count",
+    "isaac_ext_launch_count", "isaac_ext_measure_int32_peak",
 ]
 
 
@@ -126,6 +126,12 @@ class Context:
         self._check(_lib.isaac_ext_gapped_batch(self._h, ctypes.c_uint32(n), _p(cand), ctypes.c_uint32(cigar_stride),
                                                 _p(frags), _p(cig), _p(mask)))
         return frags, cig, mask
+
+    def measure_int32_peak(self, kind=0):
+        """operations per second of the integer pipes (0: add.s32, 1: max.s32, 2: 16x2 max counted twice)"""
+        v = ctypes.c_double()
+        self._check(_lib.isaac_ext_measure_int32_peak(self._h, ctypes.c_int(kind), ctypes.byref(v)))
+        return v.value
 
     # device-resident variants: arguments are raw device pointers (e.g. torch tensor .data_ptr()) and a stream handle
     def ungapped_device(self, n, d_candidates, d_fragments, d_cigars, d_masks, stream):

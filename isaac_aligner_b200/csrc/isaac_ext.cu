@@ -432,3 +432,30 @@ extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const c
     CK(cudaMemcpyAsync(offsetOut, ctx->dLengths.p + 2 * size_t(n), size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     return checkErrorFlag(ctx);
 }
+
+extern "C" int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond)
+{
+    if (!ctx || !opsPerSecond || kind < 0 || kind > 2) return ISAAC_EXT_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = 2048; const unsigned grid = ctx->smCount * 8, block = 256;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep)       // first repetition warms up
+    {
+        CK(cudaEventRecord(e0, ctx->stream));
+        if (kind == 0) intPeakKernel<0><<<grid, block, 0, ctx->stream>>>(iters, rep, ctx->errorFlag.p);
+        else if (kind == 1) intPeakKernel<1><<<grid, block, 0, ctx->stream>>>(iters, rep, ctx->errorFlag.p);
+        else intPeakKernel<2><<<grid, block, 0, ctx->stream>>>(iters, rep, ctx->errorFlag.p);
+        ++ctx->launches;
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = double(iters) * 16 * 8 * double(grid) * block * (kind == 2 ? 2 : 1);
+        if (rep) best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));
+    *opsPerSecond = best;
+    return ISAAC_EXT_OK;
+}

@@ -117,9 +117,8 @@ __global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads,
         FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};
         long begin = 0, end = L;
         clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :60
-        const bool inside = clipReference(long(ref.contigLength[contigId]), f, begin, end);   // :62
+        clipReference(long(ref.contigLength[contigId]), f, begin, end);                 // :62
         o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;
-        if (inside)
         {
             uint32_t ops[3]; unsigned nOps = 0;
             if (begin) ops[nOps++] = cigarWord(uint32_t(begin), ISAAC_EXT_CIGAR_SOFT_CLIP);            // :64-68
@@ -168,12 +167,12 @@ __global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, c
         FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};              // GappedAligner.cpp:175-176
         long begin = 0, end = L;
         clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :187
-        const bool inside = clipReference(contigLength, f, begin, end);                 // :189
+        clipReference(contigLength, f, begin, end);                                     // :189
         o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;
         const unsigned sequenceLength = unsigned(end - begin);
         long strandPosition = f.position;
         // no gapped alignment if the reference is too short (:204-208)
-        if (inside && sequenceLength && !(contigLength < long(sequenceLength) + strandPosition + 16))
+        if (sequenceLength && !(contigLength < long(sequenceLength) + strandPosition + 16))
         {
             // getFlanks (:51-82)
             unsigned left, right;
@@ -243,4 +242,36 @@ __global__ void bandedSwAsciiKernel(uint32_t n, const unsigned char *__restrict_
     }
 }
 
+} // namespace isaac_b200
+
+namespace isaac_b200
+{
+/// Integer-pipe throughput probe for the Smith-Waterman roofline denominator (MEASURED_PEAKS.json has no INT32 figure).
+/// 8 independent chains per thread, 'iters' x 16 x 8 operations per thread.  kind 0: add.s32 (IADD3 / IMAD.IADD),
+/// 1: max.s32 (VIMNMX), 2: packed 16x2 max (VIMNMX.S16x2, counted as 2 operations by the caller).
+template <int KIND> __global__ void intPeakKernel(int iters, unsigned seed, unsigned *out)
+{
+    unsigned a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 8u + k + seed;
+    const unsigned b = (blockIdx.x + seed) | 1u;
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+        {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                if (KIND == 0) asm volatile("add.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
+                else if (KIND == 1) asm volatile("max.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(b + u));
+                else a[k] = __vmaxs2(a[k], b + u);
+            }
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 0x12345678u) out[0] = s;
+}
 } // namespace isaac_b200

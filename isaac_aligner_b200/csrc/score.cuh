@@ -35,17 +35,25 @@ __device__ __forceinline__ void clipReadMasking(unsigned L, unsigned endCyclesMa
     if (maskedEnd < end) { f.incrementClipRight(unsigned(end - maskedEnd)); end = maskedEnd; }
 }
 
-/// AlignerBase::clipReference (AlignerBase.cpp:50-82).  \return false for the reference's "fragment starts past the
-/// end of the contig" branch (:74-81), which no caller of the path can produce and which the kernels report as an
-/// unaligned fragment.
-__device__ __forceinline__ bool clipReference(long referenceSize, FragmentState &f, long &begin, long &end)
+/// AlignerBase::clipReference (AlignerBase.cpp:50-82).  The second branch (:74-81) is reached when quality trimming
+/// moved the first unmasked base of a reverse-strand read past the contig end: the position is pulled back to the
+/// last contig base and the mapped range becomes empty.  (begin cannot go below 0 for candidates the host accepts,
+/// position <= contigLength - 2 or no left masking; the reference would walk off its sequence there.)
+__device__ __forceinline__ void clipReference(long referenceSize, FragmentState &f, long &begin, long &end)
 {
     const long referenceLeft = referenceSize - f.position;
-    if (referenceLeft < 0) return false;
-    if (referenceLeft < end - begin) end = begin + referenceLeft;
-    if (0 > f.position) { begin -= f.position; f.position = 0; }
-    end = max(end, begin);
-    return true;
+    if (referenceLeft >= 0)
+    {
+        if (referenceLeft < end - begin) end = begin + referenceLeft;
+        if (0 > f.position) { begin -= f.position; f.position = 0; }
+        end = max(end, begin);
+    }
+    else
+    {
+        f.position += referenceLeft - 1;
+        begin = max(0L, begin + referenceLeft - 2);
+        end = begin;
+    }
 }
 
 /// AlignerBase::updateFragmentCigar (AlignerBase.cpp:121-227): walks the CIGAR against the reference and fills

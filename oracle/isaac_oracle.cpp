@@ -468,7 +468,9 @@ int extendBatch(bool gapped, const oracle_genome_t *genome, const isaac_ext_read
             Fragment f(&cluster, &cigar, readIndex);
             f.reverse = (c.contigStrand & 1); f.contigId = (c.contigStrand >> 1); f.position = c.position;
             unsigned matchCount = alignUngapped(scores, *reads, contig, f, cigar);
-            if (gapped)
+            // the reference only gap-aligns fragments whose ungapped alignment kept at least one match
+            // (FragmentBuilder.cpp:179 drops the others first, ShadowAligner.cpp:223-226 never lists them)
+            if (gapped && matchCount)
             {
                 Fragment tmp = f;                                                  // FragmentBuilder.cpp:199-200
                 matchCount = alignGapped(scores, sw, *reads, contig, tmp, cigar);

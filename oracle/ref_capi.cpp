@@ -192,7 +192,9 @@ static int extendBatch(const bool gapped, const oracle_genome_t *genome, const i
                 alignment::matchSelector::FragmentSequencingAdapterClipper clipper(noAdapters);
                 clipper.checkInitStrand(fragment, contigs[(c.contigStrand >> 1)]);
                 unsigned matchCount = ungapped.alignUngapped(fragment, cigar, rml, clipper, contigs[(c.contigStrand >> 1)]);
-                if (gapped)
+                // the reference only gap-aligns fragments whose ungapped alignment kept at least one match
+                // (FragmentBuilder.cpp:179 drops the others first, ShadowAligner.cpp:223-226 never lists them)
+                if (gapped && matchCount)
                 {
                     alignment::FragmentMetadata tmp = fragment;
                     matchCount = gappedAligner.alignGapped(tmp, cigar, rml, clipper, contigs[(c.contigStrand >> 1)]);

@@ -64,7 +64,7 @@ def small_workload(n_pairs=2000, L=100, seed=7, genome_bases=200_000, n_contigs=
     edge["contigStrand"] = (contig << 1) | rng.integers(0, 2, size=n_edge)
     lens = np.array([g.size for g in genome])
     at_end = rng.random(n_edge) < 0.5
-    edge["position"] = np.where(at_end, lens[contig] - rng.integers(0, L + 5, size=n_edge), rng.integers(-L + 1, 20, size=n_edge))
+    edge["position"] = np.where(at_end, lens[contig] - rng.integers(2, L + 5, size=n_edge), rng.integers(-L + 1, 20, size=n_edge))
     return genome, sim, reads, np.concatenate([cand, edge])
 
 
