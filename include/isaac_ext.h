@@ -125,6 +125,74 @@ typedef struct isaac_ext_candidate {
     uint32_t contigStrand;           /* contigId << 1 | reverse                                       */
 } isaac_ext_candidate_t;             /* 16 bytes */
 
+/* The reference's 16-byte Match record, bit for bit (Match.hh:38-73): seedId packs tile:12 barcode:12 cluster:31
+ * seed:8 reverse:1 from the top (SeedId.hh:37-127), location packs (contigId+1):23 position:40 neighbors:1
+ * (ReferencePosition.hh:51-188; contig field 0 = TooManyMatch, all ones = NoMatch).  A tile's match file can be
+ * handed over unchanged. */
+typedef struct isaac_ext_match {
+    uint64_t seedId;
+    uint64_t location;
+} isaac_ext_match_t;
+
+/* alignment::SeedMetadata (SeedMetadata.hh:46-98); the index of a seed is its position in the array. */
+typedef struct isaac_ext_seed {
+    uint16_t offset;
+    uint16_t length;                 /* 16, 32 or 64 */
+    uint32_t readIndex;
+} isaac_ext_seed_t;
+
+/* FragmentBuilder::build for every cluster of the resident read set (FragmentBuilder.cpp:82-145).  Matches are sorted
+ * the way SelectMatchesTransition sorts them (cluster, location, seed; SelectMatchesTransition.cpp:242-254) and
+ * delimited per cluster by clusterMatchBegin (clusterCount + 1 offsets; the cluster field of seedId is not consulted). */
+typedef struct isaac_ext_build_batch {
+    const isaac_ext_match_t *matches;
+    const uint64_t *clusterMatchBegin;
+    const isaac_ext_seed_t *seeds;
+    uint32_t seedCount;
+    uint32_t withGaps;               /* the 'withGaps' argument of build()                              */
+} isaac_ext_build_batch_t;
+
+/* getFragments() / getCigarBuffer() of all clusters, flattened.  Fragments of (cluster, readIndex) are
+ * fragments[readFragmentBegin[cluster * readCount + readIndex] .. readFragmentBegin[... + 1]) in the reference's
+ * final order; fragment.cigarOffset indexes 'cigars'.  Owned by the context, valid until its next call. */
+typedef struct isaac_ext_build_result {
+    const isaac_ext_fragment_t *fragments;
+    const uint64_t *readFragmentBegin;   /* clusterCount * readCount + 1                                 */
+    const uint32_t *cigars;
+    const uint8_t *built;                /* per cluster: return value of build()                         */
+    uint64_t fragmentCount;
+    uint64_t cigarWords;
+} isaac_ext_build_result_t;
+
+/* alignment::TemplateLengthStatistics as its unit-test constructor takes it (TemplateLengthStatistics.hh:66-81);
+ * models are the AlignmentModel enum values FFp=0 FRp=1 RFp=2 RRp=3 FFm=4 FRm=5 RFm=6 RRm=7 (:48-59). */
+typedef struct isaac_ext_tls {
+    uint32_t min, max, median, lowStdDev, highStdDev;
+    uint32_t bestModel[2];
+    int32_t  mateDriftRange;         /* -1: mateMin = min, mateMax = max (TemplateLengthStatistics.hh:205-214) */
+} isaac_ext_tls_t;
+
+/* One ShadowAligner::rescueShadow call (ShadowAligner.hh:81-88): the orphan fields the call reads. */
+typedef struct isaac_ext_rescue_request {
+    int64_t  orphanPosition;
+    int64_t  bestTemplateLength;     /* 0 = no best template                                            */
+    uint32_t orphanReadId;           /* cluster * readCount + readIndex of the ORPHAN; the mate is rescued */
+    uint32_t orphanContigStrand;     /* contigId << 1 | reverse                                         */
+    uint32_t orphanObservedLength;
+    uint32_t pad;
+} isaac_ext_rescue_request_t;
+
+/* shadowList + getCigarBuffer() of every request, flattened like isaac_ext_build_result_t; rescued[i] is the return
+ * value of rescueShadow (the list can be non-empty when it is 0, ShadowAligner.cpp:151-154). */
+typedef struct isaac_ext_rescue_result {
+    const isaac_ext_fragment_t *fragments;
+    const uint64_t *requestFragmentBegin;   /* requestCount + 1 */
+    const uint32_t *cigars;
+    const uint8_t *rescued;
+    uint64_t fragmentCount;
+    uint64_t cigarWords;
+} isaac_ext_rescue_result_t;
+
 /* ---- life cycle ----------------------------------------------------------------------------- */
 int  isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx **ctx);
 void isaac_ext_destroy(isaac_ext_ctx *ctx);
@@ -139,6 +207,18 @@ int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
 /* Decodes one tile's BCL bytes (Read::decodeBcl, Read.cpp:32-73) into the device-resident read set used
  * by the batch calls below.  Stays valid until the next isaac_ext_set_reads on this context. */
 int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *reads);
+
+/* ---- the two calls TemplateBuilder makes --------------------------------------------------------- */
+
+/* FragmentBuilder::build over the resident read set: seeds -> candidates -> ungapped -> simple indels -> gapped, with
+ * the reference's consolidation and acceptance rules (FragmentBuilder.cpp:82-324).  The per-cluster bookkeeping
+ * (candidate lists, std::sort + consolidate, acceptance) runs on config.hostThreads host threads between the kernel
+ * passes; every base comparison, score and Smith-Waterman cell runs on the GPU. */
+int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, isaac_ext_build_result_t *result);
+
+/* ShadowAligner::rescueShadow for every request against the resident read set (ShadowAligner.cpp:155-291). */
+int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t requestCount,
+                             const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result);
 
 /* ---- micro entry points (unit parity + kernel benchmarks) ------------------------------------ */
 

@@ -1,0 +1,81 @@
+"""ctypes / numpy mirrors of the batch structs of the two TemplateBuilder-facing calls (include/isaac_ext.h):
+isaac_ext_build_fragments and isaac_ext_rescue_shadows."""
+import ctypes
+
+import numpy as np
+
+from .synth import MATCH_DTYPE, SEED_DTYPE
+from .types import FRAGMENT_DTYPE
+
+# isaac_ext_rescue_request_t, 32 bytes
+RESCUE_REQUEST_DTYPE = np.dtype([("orphanPosition", "<i8"), ("bestTemplateLength", "<i8"), ("orphanReadId", "<u4"),
+                                 ("orphanContigStrand", "<u4"), ("orphanObservedLength", "<u4"), ("pad", "<u4")])
+assert RESCUE_REQUEST_DTYPE.itemsize == 32
+
+# TemplateLengthStatistics::AlignmentModel (TemplateLengthStatistics.hh:48-59)
+FFp, FRp, RFp, RRp, FFm, FRm, RFm, RRm = range(8)
+
+
+class BuildBatch(ctypes.Structure):
+    """isaac_ext_build_batch_t"""
+    _fields_ = [("matches", ctypes.c_void_p), ("clusterMatchBegin", ctypes.c_void_p), ("seeds", ctypes.c_void_p),
+                ("seedCount", ctypes.c_uint32), ("withGaps", ctypes.c_uint32)]
+
+
+class BuildResult(ctypes.Structure):
+    """isaac_ext_build_result_t"""
+    _fields_ = [("fragments", ctypes.c_void_p), ("readFragmentBegin", ctypes.c_void_p), ("cigars", ctypes.c_void_p),
+                ("built", ctypes.c_void_p), ("fragmentCount", ctypes.c_uint64), ("cigarWords", ctypes.c_uint64)]
+
+
+class Tls(ctypes.Structure):
+    """isaac_ext_tls_t"""
+    _fields_ = [("min", ctypes.c_uint32), ("max", ctypes.c_uint32), ("median", ctypes.c_uint32),
+                ("lowStdDev", ctypes.c_uint32), ("highStdDev", ctypes.c_uint32), ("bestModel", ctypes.c_uint32 * 2),
+                ("mateDriftRange", ctypes.c_int32)]
+
+    @classmethod
+    def make(cls, mn=245, mx=455, median=350, low=35, high=35, m0=FRp, m1=RFm, drift=-1):
+        """explicit template length statistics min 245, median 350, max 455, FRp / RFm"""
+        return cls(mn, mx, median, low, high, (ctypes.c_uint32 * 2)(m0, m1), drift)
+
+
+class RescueResult(ctypes.Structure):
+    """isaac_ext_rescue_result_t"""
+    _fields_ = [("fragments", ctypes.c_void_p), ("requestFragmentBegin", ctypes.c_void_p), ("cigars", ctypes.c_void_p),
+                ("rescued", ctypes.c_void_p), ("fragmentCount", ctypes.c_uint64), ("cigarWords", ctypes.c_uint64)]
+
+
+class MatchBatch:
+    """Host-side owner of a tile's matches, CSR offsets and seed table plus the ctypes view."""
+
+    def __init__(self, matches, cluster_match_begin, seeds, with_gaps=True):
+        self.matches = np.ascontiguousarray(matches, dtype=MATCH_DTYPE)
+        self.begin = np.ascontiguousarray(cluster_match_begin, dtype=np.uint64)
+        self.seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+        self.c = BuildBatch(self.matches.ctypes.data, self.begin.ctypes.data, self.seeds.ctypes.data,
+                            len(self.seeds), 1 if with_gaps else 0)
+
+
+class FlatFragments:
+    """fragments + CSR + cigar pool copied out of a result struct (or filled by the oracle)."""
+
+    def __init__(self, fragments, begin, cigars, flags):
+        self.fragments, self.begin, self.cigars, self.flags = fragments, begin, cigars, flags
+
+    def cigar(self, i):
+        f = self.fragments[i]
+        return self.cigars[int(f["cigarOffset"]):int(f["cigarOffset"]) + int(f["cigarLength"])]
+
+
+def copy_result(res, n_groups, begin_field, flag_field, n_flags):
+    nf, nc = int(res.fragmentCount), int(res.cigarWords)
+
+    def arr(ptr, dtype, count):
+        if not count:
+            return np.zeros(0, dtype=dtype)
+        buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    return FlatFragments(arr(res.fragments, FRAGMENT_DTYPE, nf), arr(getattr(res, begin_field), np.uint64, n_groups + 1),
+                         arr(res.cigars, np.uint32, nc), arr(getattr(res, flag_field), np.uint8, n_flags))

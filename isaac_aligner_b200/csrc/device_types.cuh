@@ -22,6 +22,7 @@ struct ReferenceView
     const uint64_t *contigOffset;    // global base index of the first base of each contig
     const uint64_t *contigLength;
     uint32_t contigCount;
+    uint64_t totalBases;             // padded size of the packed arrays in bases
 
     __device__ __forceinline__ unsigned code(uint64_t g) const
     {
@@ -39,6 +40,11 @@ struct ReadSetView
     const uint32_t *nmask;           // readId * wordsN + w, 32 bases per word, bit set = 'n'
     const uint8_t *quality;          // readId * qualityStride + i (BCL N gets quality 2)
     const uint16_t *endCyclesMasked; // per readId
+    // Both strands again as 4-bit codes in strand order (0..3, CODE_READ_N), 16 bases per 64-bit word, for the
+    // Smith-Waterman query stream: (readId * 2 + reverse) * wordsC + w.  The last TWO words of every strand are spare
+    // zeros so that a 16-base fetch may start anywhere in the strand.
+    const uint64_t *codes4;
+    uint32_t wordsC;
     uint32_t words2, wordsN, qualityStride;
     uint32_t readCount;
     uint32_t readLength[2];
@@ -46,6 +52,12 @@ struct ReadSetView
     uint32_t readTotal;              // clusterCount * readCount
 
     __device__ __forceinline__ unsigned length(unsigned readId) const { return readLength[readId % readCount]; }
+    __device__ __forceinline__ const uint64_t *strandCodes(unsigned readId, bool reverse) const
+    {
+        return codes4 + (size_t(readId) * 2 + (reverse ? 1u : 0u)) * wordsC;
+    }
+    /// highest strand position a 16-base fetch may start at
+    __device__ __forceinline__ unsigned codesClamp() const { return (wordsC - 2u) * 16u; }
 
     /// base code and quality of strand-order position i
     __device__ __forceinline__ unsigned code(unsigned readId, unsigned L, bool reverse, unsigned i, unsigned &q) const

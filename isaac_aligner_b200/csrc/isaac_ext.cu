@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "kernels2.cuh"
 
 using namespace isaac_b200;
 
@@ -39,6 +40,10 @@ struct isaac_ext_ctx
     cudaStream_t stream = nullptr;
     std::string error;
     uint64_t launches = 0;
+    // Tuning knobs (environment, read once at isaac_ext_create): ISAAC_EXT_SW_IMPL = 2 (packed 16x2, two alignments per
+    // thread, default) or 1 (scalar, one alignment per thread); ISAAC_EXT_SW_BLOCKS_PER_SM bounds the persistent grid.
+    int swImpl = 2;
+    unsigned swBlocksPerSm = 4;
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
     DeviceBuffer<double> tables;
@@ -54,6 +59,7 @@ struct isaac_ext_ctx
     // resident read set
     DeviceBuffer<uint32_t> readBases2, readNmask;
     DeviceBuffer<uint8_t> readQuality, bclStage;
+    DeviceBuffer<uint64_t> readCodes4;
     DeviceBuffer<uint16_t> readMasked;
     ReadSetView reads{};
     bool haveReads = false;
@@ -114,7 +120,7 @@ bool swScoresSupported(int match, int mismatch, int open, int ext, unsigned maxR
 
 int ensureTraceback(isaac_ext_ctx *ctx, unsigned grid, unsigned block, unsigned maxQueryLength)
 {
-    const size_t words = size_t(grid) * block * 3 * maxQueryLength;
+    const size_t words = size_t(grid) * block * (ctx->swImpl == 2 ? SW2_FLAG_WORDS : 3u) * maxQueryLength;
     return ctx->cuda(ctx->tbScratch.reserve(words), "cudaMalloc(traceback scratch)");
 }
 
@@ -167,6 +173,8 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
     }
     isaac_ext_ctx *ctx = new isaac_ext_ctx();
     ctx->cfg = *config;
+    if (const char *e = std::getenv("ISAAC_EXT_SW_IMPL")) ctx->swImpl = std::atoi(e) == 1 ? 1 : 2;
+    if (const char *e = std::getenv("ISAAC_EXT_SW_BLOCKS_PER_SM")) ctx->swBlocksPerSm = std::max(1, std::min(16, std::atoi(e)));
     ctx->device = config->device;
     int rc = ctx->cuda(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (!rc) rc = ctx->cuda(cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, ctx->device), "cudaDeviceGetAttribute");
@@ -203,7 +211,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     ctx->tables.release(); ctx->refBases2.release(); ctx->refNmask.release(); ctx->refContigOffset.release();
     ctx->refContigLength.release(); ctx->readBases2.release(); ctx->readNmask.release(); ctx->readQuality.release();
-    ctx->bclStage.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
+    ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
     delete ctx;
@@ -251,6 +259,7 @@ extern "C" int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
     ctx->ref.bases2 = ctx->refBases2.p; ctx->ref.nmask = ctx->refNmask.p;
     ctx->ref.contigOffset = ctx->refContigOffset.p; ctx->ref.contigLength = ctx->refContigLength.p;
     ctx->ref.contigCount = contigCount;
+    ctx->ref.totalBases = total;
     ctx->haveReference = true;
     return ISAAC_EXT_OK;
 }
@@ -282,8 +291,15 @@ extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *
         ctx->readBases2.p, ctx->readNmask.p, ctx->readQuality.p);
     ++ctx->launches;
     CK(cudaGetLastError());
+    const uint32_t wordsC = (maxLen + 15) / 16 + 2;
+    CK(ctx->readCodes4.reserve(readTotal * 2 * wordsC));
+    encodeStrandCodesKernel<<<gridFor(ctx, readTotal * 2 * wordsC, 256, 16), 256, 0, ctx->stream>>>(
+        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, ctx->readCodes4.p);
+    ++ctx->launches;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     ReadSetView &v = ctx->reads;
+    v.codes4 = ctx->readCodes4.p; v.wordsC = wordsC;
     v.bases2 = ctx->readBases2.p; v.nmask = ctx->readNmask.p; v.quality = ctx->readQuality.p; v.endCyclesMasked = ctx->readMasked.p;
     v.words2 = words2; v.wordsN = wordsN; v.qualityStride = qualityStride; v.readCount = r->readCount;
     v.readLength[0] = len0; v.readLength[1] = len1; v.firstCycle[0] = r->firstCycle[0]; v.firstCycle[1] = r->firstCycle[1];
@@ -326,13 +342,20 @@ extern "C" int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, con
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
-    const unsigned grid = gridFor(ctx, n, SW_BLOCK, 8);
+    const unsigned items = ctx->swImpl == 2 ? (n + 1) / 2 : n;     // the packed kernel takes two candidates per thread
+    const unsigned grid = gridFor(ctx, items, SW_BLOCK, ctx->swBlocksPerSm);
     const int rc = ensureTraceback(ctx, grid, SW_BLOCK, std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]));
     if (rc) return rc;
-    gappedKernel<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
-        ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
-        static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-        static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p);
+    if (ctx->swImpl == 2)
+        gappedKernel2<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
+            ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
+            static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
+            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p);
+    else
+        gappedKernel<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
+            ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
+            static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
+            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p);
     ++ctx->launches;
     return ctx->cuda(cudaGetLastError(), "gappedKernel");
 }
@@ -418,13 +441,18 @@ extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const c
     CK(cudaMemcpyAsync(ctx->dOffsets.p, queryOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dOffsets.p + n, databaseOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dLengths.p, queryLengths, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    const unsigned grid = gridFor(ctx, n, SW_BLOCK, 8);
+    const unsigned grid = gridFor(ctx, ctx->swImpl == 2 ? (n + 1) / 2 : n, SW_BLOCK, ctx->swBlocksPerSm);
     int rc = ensureTraceback(ctx, grid, SW_BLOCK, maxLen);
     if (rc) return rc;
     const SwScores sw = {matchScore, mismatchScore, gapOpenScore, gapExtendScore, -32768 + gapOpenScore};
-    bandedSwAsciiKernel<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
-                                                            ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
-                                                            ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
+    if (ctx->swImpl == 2)
+        bandedSwAsciiKernel2<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
+                                                                 ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
+                                                                 ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
+    else
+        bandedSwAsciiKernel<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
+                                                                ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
+                                                                ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cigarOut, ctx->dCigars.p, size_t(n) * cigarStride * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

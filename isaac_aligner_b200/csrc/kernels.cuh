@@ -86,6 +86,36 @@ __global__ void decodeBclKernel(const uint8_t *__restrict__ bcl, uint32_t cluste
     }
 }
 
+/// Both strands of every read as 4-bit codes in strand order (ReadSetView::codes4); one thread per 64-bit word.
+__global__ void encodeStrandCodesKernel(const uint8_t *__restrict__ bcl, uint32_t clusterCount, uint32_t readCount,
+                                        uint32_t len0, uint32_t len1, uint32_t wordsC, uint64_t *__restrict__ codes4)
+{
+    const uint64_t total = uint64_t(clusterCount) * readCount * 2 * wordsC;
+    const uint32_t clusterBytes = len0 + (readCount > 1 ? len1 : 0);
+    for (uint64_t t = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; t < total; t += uint64_t(gridDim.x) * blockDim.x)
+    {
+        const uint32_t w = uint32_t(t % wordsC);
+        const uint64_t strandId = t / wordsC;
+        const bool reverse = strandId & 1u;
+        const uint64_t readId = strandId >> 1;
+        const uint32_t readIndex = uint32_t(readId % readCount);
+        const uint32_t L = readIndex ? len1 : len0;
+        const uint8_t *src = bcl + (readId / readCount) * clusterBytes + (readIndex ? len0 : 0);
+        uint64_t word = 0;
+        for (unsigned k = 0; k < 16; ++k)
+        {
+            const uint32_t p = w * 16 + k;
+            if (p < L)
+            {
+                const unsigned b = src[reverse ? L - 1 - p : p];
+                const unsigned code = !(b & 0xfcu) ? unsigned(CODE_READ_N) : (reverse ? 3u - (b & 3u) : (b & 3u));   // Read.cpp:56-69
+                word |= uint64_t(code) << (4 * k);
+            }
+        }
+        codes4[t] = word;
+    }
+}
+
 __device__ __forceinline__ void initFragment(isaac_ext_fragment_t &o, const isaac_ext_candidate_t &c, uint32_t readCount)
 {
     o.position = c.position; o.logProbability = 0.0; o.contigId = c.contigStrand >> 1; o.readId = c.readId;

@@ -1,0 +1,198 @@
+// Second-generation Smith-Waterman kernels: two alignments per thread in packed 16x2 form (sw2.cuh).
+//   gappedKernel2         GappedAligner::alignGapped for candidates (2t, 2t+1) in thread t
+//   bandedSwAsciiKernel2  BandedSmithWaterman::align on explicit strings, pairs (2t, 2t+1)
+#pragma once
+#include "kernels.cuh"
+#include "sw2.cuh"
+
+namespace isaac_b200
+{
+
+/// What GappedAligner::alignGapped derives for one candidate before it calls the Smith-Waterman (GappedAligner.cpp:174-215).
+struct GappedPrep
+{
+    isaac_ext_candidate_t c;
+    FragmentState f;
+    long begin, end, strandPosition;
+    unsigned L, sequenceLength, left, contigId;
+    bool run;
+};
+
+__device__ __forceinline__ GappedPrep prepareGapped(const ReferenceView &ref, const ReadSetView &reads,
+                                                    const isaac_ext_candidate_t c)
+{
+    GappedPrep p;
+    p.c = c;
+    p.contigId = c.contigStrand >> 1;
+    p.L = reads.length(c.readId);
+    const long contigLength = long(ref.contigLength[p.contigId]);
+    p.f = FragmentState{c.position, 0u, 0u, bool(c.contigStrand & 1u)};          // :175-176
+    p.begin = 0; p.end = p.L;
+    clipReadMasking(p.L, reads.endCyclesMasked[c.readId], p.f, p.begin, p.end);  // :187
+    clipReference(contigLength, p.f, p.begin, p.end);                            // :189
+    p.sequenceLength = unsigned(p.end - p.begin);
+    p.strandPosition = p.f.position;
+    // no gapped alignment if the reference is too short (:204-208)
+    p.run = p.sequenceLength && !(contigLength < long(p.sequenceLength) + p.strandPosition + 16);
+    p.left = 0;
+    if (p.run) p.left = p.strandPosition >= 8 ? 8u : unsigned(p.strandPosition);   // getFlanks (:51-82), see gappedKernel
+    return p;
+}
+
+/// Finishes one candidate after its Smith-Waterman: soft clips, position, re-score, store (GappedAligner.cpp:231-248).
+__device__ __forceinline__ void finishGapped(const ReferenceView &ref, const ReadSetView &reads, const ScoreParams &sp,
+                                             const GappedPrep &p, const uint32_t i, uint32_t *ops /* ops[1..1+nSw) hold the SW cigar */,
+                                             unsigned nSw, const unsigned ret, const bool overflow, const uint32_t cigarStride,
+                                             isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
+                                             uint64_t *__restrict__ masks, uint32_t *__restrict__ errorFlag)
+{
+    isaac_ext_fragment_t o;
+    initFragment(o, p.c, reads.readCount);
+    uint64_t *mask = masks ? masks + size_t(i) * ISAAC_EXT_MASK_WORDS : nullptr;
+    if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
+    o.cigarOffset = i * cigarStride;
+    o.lowClipped = uint16_t(p.f.lowClipped); o.highClipped = uint16_t(p.f.highClipped); o.position = p.f.position;
+    if (p.run)
+    {
+        uint32_t *all = ops + 1;
+        unsigned nOps = nSw;
+        if (p.begin) { ops[0] = cigarWord(uint32_t(p.begin), ISAAC_EXT_CIGAR_SOFT_CLIP); all = ops; ++nOps; }        // :191-195
+        if (long(p.L) - p.end) all[nOps++] = cigarWord(uint32_t(p.L - p.end), ISAAC_EXT_CIGAR_SOFT_CLIP);          // :233-237
+        const long strandPosition = p.strandPosition + long(ret) - long(p.left);                                   // :231,240
+        if (overflow || nOps > cigarStride) { atomicOr(errorFlag, 1u); }
+        else
+        {
+            scoreCigar(ref, reads, sp, p.c.readId, p.L, p.f.reverse, ref.contigOffset[p.contigId], strandPosition, all, nOps, o, mask);
+            uint32_t *cigar = cigars + size_t(i) * cigarStride;
+            for (unsigned k = 0; k < nOps; ++k) cigar[k] = all[k];
+            o.cigarLength = uint16_t(nOps);
+        }
+    }
+    fragments[i] = o;
+}
+
+/// Sequential code streams of a pair of (read strand window, reference window).  q2()/d2() must be called in
+/// increasing order of their argument (sw2Forward does); every 16th call refills from memory, in lock-step for the
+/// whole warp.
+struct ResidentPairSrc
+{
+    const ReferenceView &ref;
+    const uint64_t *qWords[2]; unsigned qPos[2]; uint64_t dPos[2];
+    uint64_t qBuf[2], dBuf[2];
+    unsigned qClamp;        // the shorter alignment of a pair keeps streaming past its own end: keep it inside its buffers
+    __device__ __forceinline__ uint32_t q2(unsigned i)
+    {
+        if ((i & 15u) == 0)
+        {
+            qBuf[0] = readCodes16(qWords[0], min(qPos[0] + i, qClamp));
+            qBuf[1] = readCodes16(qWords[1], min(qPos[1] + i, qClamp));
+        }
+        const uint32_t r = (uint32_t(qBuf[0]) & 15u) | ((uint32_t(qBuf[1]) & 15u) << 16);
+        qBuf[0] >>= 4; qBuf[1] >>= 4;
+        return r;
+    }
+    __device__ __forceinline__ uint32_t d2(unsigned k)
+    {
+        if ((k & 15u) == 0)
+        {
+            dBuf[0] = referenceCodes16(ref, min(dPos[0] + k, ref.totalBases - 64));
+            dBuf[1] = referenceCodes16(ref, min(dPos[1] + k, ref.totalBases - 64));
+        }
+        const uint32_t r = (uint32_t(dBuf[0]) & 15u) | ((uint32_t(dBuf[1]) & 15u) << 16);
+        dBuf[0] >>= 4; dBuf[1] >>= 4;
+        return r;
+    }
+};
+
+__global__ void __launch_bounds__(128)
+gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+              const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
+              isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
+              uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
+{
+    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
+    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
+    const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};
+    const uint32_t pairs = (n + 1) / 2;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += gridDim.x * blockDim.x)
+    {
+        const uint32_t iA = 2 * t, iB = 2 * t + 1;
+        const bool haveB = iB < n;
+        const GappedPrep pa = prepareGapped(ref, reads, candidates[iA]);
+        GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA]);
+        if (!haveB) pb.run = false;
+        const unsigned LA = pa.run ? pa.sequenceLength : 0u, LB = pb.run ? pb.sequenceLength : 0u;
+        int jj[2] = {0, 0}; unsigned type[2] = {0, 0};
+        if (LA | LB)
+        {
+            // a half that is not aligned (run == false) streams its own first bases: harmless, never stored
+            ResidentPairSrc src = {ref,
+                                   {reads.strandCodes(pa.c.readId, pa.f.reverse), reads.strandCodes(pb.c.readId, pb.f.reverse)},
+                                   {LA ? unsigned(pa.begin) : 0u, LB ? unsigned(pb.begin) : 0u},
+                                   {LA ? ref.contigOffset[pa.contigId] + uint64_t(pa.strandPosition - long(pa.left)) : 0ull,
+                                    LB ? ref.contigOffset[pb.contigId] + uint64_t(pb.strandPosition - long(pb.left)) : 0ull},
+                                   {0, 0}, {0, 0}, reads.codesClamp()};
+            sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);
+        }
+        uint32_t ops[SW_OPS_CAP + 2];
+        {
+            unsigned nSw = 0, ret = 0; bool overflow = false;
+            if (LA) ret = sw2Traceback(tb, tbStride, 0, LA, jj[0], type[0], ops + 1, SW_OPS_CAP, nSw, overflow);
+            finishGapped(ref, reads, sp, pa, iA, ops, nSw, ret, overflow, cigarStride, fragments, cigars, masks, errorFlag);
+        }
+        if (haveB)
+        {
+            unsigned nSw = 0, ret = 0; bool overflow = false;
+            if (LB) ret = sw2Traceback(tb, tbStride, 1, LB, jj[1], type[1], ops + 1, SW_OPS_CAP, nSw, overflow);
+            finishGapped(ref, reads, sp, pb, iB, ops, nSw, ret, overflow, cigarStride, fragments, cigars, masks, errorFlag);
+        }
+    }
+}
+
+struct AsciiPairSrc
+{
+    const unsigned char *query[2]; const unsigned char *database[2]; unsigned n[2];
+    __device__ __forceinline__ uint32_t q2(unsigned i) const
+    {
+        return (i < n[0] ? AsciiBaseSrc::qcode(query[0][i]) : 0u) | ((i < n[1] ? AsciiBaseSrc::qcode(query[1][i]) : 0u) << 16);
+    }
+    __device__ __forceinline__ uint32_t d2(unsigned k) const
+    {
+        return (k < n[0] + 15 ? asciiRefCode(database[0][k]) : 0u) | ((k < n[1] + 15 ? asciiRefCode(database[1][k]) : 0u) << 16);
+    }
+};
+
+__global__ void __launch_bounds__(128)
+bandedSwAsciiKernel2(uint32_t n, const unsigned char *__restrict__ queries, const uint64_t *__restrict__ queryOffsets,
+                     const uint32_t *__restrict__ queryLengths, const unsigned char *__restrict__ databases,
+                     const uint64_t *__restrict__ databaseOffsets, const SwScores sw, uint32_t cigarStride,
+                     uint32_t *__restrict__ cigars, uint32_t *__restrict__ cigarLengths, uint32_t *__restrict__ offsets,
+                     uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
+{
+    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
+    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
+    const uint32_t pairs = (n + 1) / 2;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += gridDim.x * blockDim.x)
+    {
+        const uint32_t iA = 2 * t, iB = 2 * t + 1 < n ? 2 * t + 1 : 2 * t;
+        const bool haveB = 2 * t + 1 < n;
+        const unsigned LA = queryLengths[iA], LB = haveB ? queryLengths[iB] : 0u;
+        AsciiPairSrc src = {{queries + queryOffsets[iA], queries + queryOffsets[iB]},
+                            {databases + databaseOffsets[iA], databases + databaseOffsets[iB]}, {LA, LB}};
+        int jj[2]; unsigned type[2];
+        sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);
+        uint32_t ops[SW_OPS_CAP];
+        for (unsigned h = 0; h < (haveB ? 2u : 1u); ++h)
+        {
+            const uint32_t i = h ? iB : iA;
+            unsigned nOps = 0; bool overflow = false;
+            const unsigned ret = sw2Traceback(tb, tbStride, h, h ? LB : LA, jj[h], type[h], ops, SW_OPS_CAP, nOps, overflow);
+            if (overflow) atomicOr(errorFlag, 1u);
+            offsets[i] = ret;
+            cigarLengths[i] = nOps;
+            for (unsigned k = 0; k < nOps && k < cigarStride; ++k) cigars[size_t(i) * cigarStride + k] = ops[k];
+        }
+    }
+}
+
+} // namespace isaac_b200

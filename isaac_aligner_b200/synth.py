@@ -57,7 +57,7 @@ class Simulation:
 
 def simulate_pairs(genome, n_pairs, L=150, seed=SEED_READS, snp_rate=1e-3, indel_rate=5e-4, max_indel=16,
                    insert=(350.0, 35.0, 200, 500), quality_probs=((40, 0.80), (30, 0.15), (20, 0.04), (2, 0.01)),
-                   chunk=200_000):
+                   chunk=200_000, seed_offsets=None, seed_length=32):
     rng = _rng(seed)
     lens = np.array([c.size for c in genome], dtype=np.int64)
     margin = insert[3] + 2 * max_indel + 64
@@ -71,6 +71,11 @@ def simulate_pairs(genome, n_pairs, L=150, seed=SEED_READS, snp_rate=1e-3, indel
     sim.reverse[:, 1] = 1
     K = 2
     sim.events = np.zeros((n_pairs, 2, K, 2), dtype=np.int32)
+    if seed_offsets is not None:
+        sim.seed_offsets = tuple(seed_offsets)
+        sim.seed_length = seed_length
+        sim.seed_clean = np.zeros((n_pairs, 2, len(seed_offsets)), dtype=bool)
+        sim.seed_shift = np.zeros((n_pairs, 2, len(seed_offsets)), dtype=np.int32)
     qvals = np.array([q for q, _ in quality_probs], dtype=np.uint8)
     qp = np.array([p for _, p in quality_probs], dtype=np.float64)
     qerr = np.power(10.0, -qvals.astype(np.float64) / 10.0)
@@ -115,6 +120,18 @@ def simulate_pairs(genome, n_pairs, L=150, seed=SEED_READS, snp_rate=1e-3, indel
             codes = np.where(sub, (codes + rng.integers(1, 4, size=(n, L), dtype=np.uint8)) & 3, codes).astype(np.uint8)
             byte = (q << 2) | codes
             byte = np.where(q == 2, 0, byte).astype(np.uint8)      # Q2 bases are read as N (bcl byte 0)
+            if seed_offsets is not None:
+                # a seed yields a match at the true locus iff none of its 32 bases is an error, an N or an inserted base
+                # and no deletion falls inside it; its locus is shifted by the net indel length left of it
+                dirty = sub | inserted | (q == 2)
+                csum = np.concatenate([np.zeros((n, 1), dtype=np.int32), np.cumsum(dirty, axis=1, dtype=np.int32)], axis=1)
+                for s, o in enumerate(seed_offsets):
+                    fo = o if r == 0 else L - o - seed_length
+                    clean = (csum[:, fo + seed_length] - csum[:, fo]) == 0
+                    for k in range(K):
+                        clean &= ~(active[:, k] & isdel[:, k] & (epos[:, k] > fo) & (epos[:, k] < fo + seed_length))
+                    sim.seed_clean[b:b + n, r, s] = clean
+                    sim.seed_shift[b:b + n, r, s] = goff[:, fo] - fo
             if r == 1:   # read 2 is sequenced from the other strand: reverse-complement into sequencing order
                 byte = np.where(byte == 0, 0, byte ^ 3)[:, ::-1]
             sim.bcl[b:b + n, r * L:(r + 1) * L] = byte
@@ -144,3 +161,79 @@ def microbench_candidates(sim, genome, per_read=4, seed=SEED_READS + 2, fraction
     cand["readId"] = read_id
     cand["contigStrand"] = (contig << 1) | reverse
     return cand
+
+
+MATCH_DTYPE = np.dtype([("seedId", "<u8"), ("location", "<u8")])    # isaac_ext_match_t == the reference's Match
+SEED_DTYPE = np.dtype([("offset", "<u2"), ("length", "<u2"), ("readIndex", "<u4")])   # isaac_ext_seed_t
+
+
+def auto_seed_offsets(L, seed_length=32):
+    """--seeds auto of the reference (SeedDescriptorOption.cpp:86-151): offset 0, the last full seed, then every
+    seed_length bases in between: (0, 118, 32, 64) at 150 bp."""
+    offs = [0, L - seed_length]
+    o = seed_length
+    while o + seed_length <= L - seed_length:
+        offs.append(o)
+        o += seed_length
+    return tuple(offs)
+
+
+def seed_table(sim):
+    """isaac_ext_seed_t array: seeds of read 0 first, then read 1 (index = readIndex * S + k)."""
+    S = len(sim.seed_offsets)
+    seeds = np.zeros(2 * S, dtype=SEED_DTYPE)
+    for r in range(2):
+        for k, o in enumerate(sim.seed_offsets):
+            seeds[r * S + k] = (o, sim.seed_length, r)
+    return seeds
+
+
+def make_matches(sim, genome, seed=SEED_READS + 3, decoy_rate=0.2, neighbor_rate=0.0, repeat_rate=0.0,
+                 too_many_rate=0.0, repeat_matches=12):
+    """Seed-free stand-in for the seed-matching stage: every error-free seed yields a Match at the true
+    locus shifted by the net indel length left of it, plus decoys at uniform random loci; optionally seeds with
+    neighbours, over-represented seeds and TooManyMatch records.  Returns (matches sorted like
+    SelectMatchesTransition.cpp:242-254, clusterMatchBegin)."""
+    rng = _rng(seed)
+    n = sim.contig.shape[0]
+    S = len(sim.seed_offsets)
+    L, sl = sim.L, sim.seed_length
+    lens = np.array([c.size for c in genome], dtype=np.int64)
+    cl, rd, sd = np.nonzero(sim.seed_clean)                       # cluster, read, seed
+    fo = np.where(rd == 0, np.array(sim.seed_offsets)[sd], L - np.array(sim.seed_offsets)[sd] - sl)
+    position = sim.position[cl, rd] + fo + sim.seed_shift[cl, rd, sd]
+    parts = [(cl, rd * S + sd, sim.reverse[cl, rd].astype(np.int64), sim.contig[cl, rd].astype(np.int64), position,
+              (rng.random(cl.size) < neighbor_rate).astype(np.int64))]
+
+    def random_matches(mask_rate, per):
+        pick = np.nonzero(rng.random(2 * n) < mask_rate)[0]
+        c, r = np.repeat(pick // 2, per), np.repeat(pick % 2, per)
+        s = np.repeat(rng.integers(0, S, size=pick.size), per)
+        contig = rng.integers(0, len(genome), size=c.size)
+        pos = (rng.random(c.size) * (lens[contig] - L - 64)).astype(np.int64) + 16
+        return (c, r * S + s, rng.integers(0, 2, size=c.size), contig, pos, np.zeros(c.size, dtype=np.int64))
+
+    if decoy_rate > 0:
+        parts.append(random_matches(decoy_rate, 1))
+    if repeat_rate > 0:
+        parts.append(random_matches(repeat_rate, repeat_matches))
+    cluster = np.concatenate([p[0] for p in parts]).astype(np.uint64)
+    seed_index = np.concatenate([p[1] for p in parts]).astype(np.uint64)
+    reverse = np.concatenate([p[2] for p in parts]).astype(np.uint64)
+    contig = np.concatenate([p[3] for p in parts]).astype(np.uint64)
+    pos = np.concatenate([p[4] for p in parts]).astype(np.uint64)
+    neighbors = np.concatenate([p[5] for p in parts]).astype(np.uint64)
+    location = ((((contig + np.uint64(1)) << np.uint64(40)) | pos) << np.uint64(1)) | neighbors
+    if too_many_rate > 0:
+        pick = np.nonzero(rng.random(2 * n) < too_many_rate)[0]
+        cluster = np.concatenate([cluster, (pick // 2).astype(np.uint64)])
+        seed_index = np.concatenate([seed_index, ((pick % 2) * S + rng.integers(0, S, size=pick.size)).astype(np.uint64)])
+        reverse = np.concatenate([reverse, np.zeros(pick.size, dtype=np.uint64)])
+        location = np.concatenate([location, np.zeros(pick.size, dtype=np.uint64)])      # ReferencePosition::TooManyMatch
+    order = np.lexsort((seed_index, location, cluster))
+    m = np.empty(order.size, dtype=MATCH_DTYPE)
+    m["seedId"] = (cluster[order] << np.uint64(9)) | (seed_index[order] << np.uint64(1)) | reverse[order]
+    m["location"] = location[order]
+    begin = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(np.bincount(cluster.astype(np.int64), minlength=n), out=begin[1:])
+    return m, begin

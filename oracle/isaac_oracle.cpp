@@ -525,3 +525,6 @@ extern "C" int oracle_gapped_batch(const oracle_genome_t *genome, const isaac_ex
 {
     return extendBatch(true, genome, reads, config, n, candidates, cigarStride, fragmentsOut, cigarOut, mismatchMaskOut, threads);
 }
+
+// SimpleIndelAligner, FragmentBuilder::build, ShadowAligner::rescueShadow
+#include "isaac_oracle_build.inc"

@@ -47,6 +47,22 @@ int oracle_gapped_batch(const oracle_genome_t *genome, const isaac_ext_reads_t *
                         uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
                         uint64_t *mismatchMaskOut, uint32_t threads);
 
+/* FragmentBuilder::build for every cluster, see isaac_ext_build_fragments.  Outputs go to caller-provided buffers
+ * (ISAAC_EXT_E_CAPACITY if too small): fragmentsOut[fragmentCapacity], cigarsOut[cigarCapacity],
+ * readFragmentBegin[clusterCount * readCount + 1], builtOut[clusterCount]. */
+int oracle_build_fragments(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *config,
+                           const isaac_ext_build_batch_t *batch, uint64_t fragmentCapacity, isaac_ext_fragment_t *fragmentsOut,
+                           uint64_t *readFragmentBegin, uint64_t cigarCapacity, uint32_t *cigarsOut, uint8_t *builtOut,
+                           uint64_t *fragmentCount, uint64_t *cigarWords, uint32_t threads);
+
+/* ShadowAligner::rescueShadow for every request, see isaac_ext_rescue_shadows.  requestFragmentBegin[requestCount + 1],
+ * rescuedOut[requestCount]. */
+int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *config,
+                          const isaac_ext_tls_t *tls, uint32_t requestCount, const isaac_ext_rescue_request_t *requests,
+                          uint64_t fragmentCapacity, isaac_ext_fragment_t *fragmentsOut, uint64_t *requestFragmentBegin,
+                          uint64_t cigarCapacity, uint32_t *cigarsOut, uint8_t *rescuedOut,
+                          uint64_t *fragmentCount, uint64_t *cigarWords, uint32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,3 +228,154 @@ extern "C" int oracle_gapped_batch(const oracle_genome_t *genome, const isaac_ex
 {
     return extendBatch(true, genome, reads, config, n, candidates, cigarStride, fragmentsOut, cigarOut, mismatchMaskOut, threads);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * FragmentBuilder::build and ShadowAligner::rescueShadow over flat batches (glue only, the logic is the reference's)
+ * ------------------------------------------------------------------------------------------------------------------ */
+namespace
+{
+
+struct FlatOut
+{
+    std::vector<isaac_ext_fragment_t> fragments;
+    std::vector<uint32_t> cigars;
+    void add(const alignment::FragmentMetadata &f, uint32_t readId, const flowcell::ReadMetadataList &rml)
+    {
+        isaac_ext_fragment_t o;
+        const uint32_t offset = cigars.size();
+        if (f.cigarLength && f.cigarBuffer)
+            cigars.insert(cigars.end(), f.cigarBuffer->begin() + f.cigarOffset, f.cigarBuffer->begin() + f.cigarOffset + f.cigarLength);
+        flatten(f, readId, offset, 0, rml, o, 0, 0, 0);
+        fragments.push_back(o);
+    }
+};
+
+int concatenate(const std::vector<FlatOut> &parts, uint64_t fragmentCapacity, isaac_ext_fragment_t *fragmentsOut,
+                uint64_t cigarCapacity, uint32_t *cigarsOut, uint64_t *fragmentCount, uint64_t *cigarWords)
+{
+    uint64_t nf = 0, nc = 0;
+    for (const FlatOut &p : parts) { nf += p.fragments.size(); nc += p.cigars.size(); }
+    *fragmentCount = nf; *cigarWords = nc;
+    if (nf > fragmentCapacity || nc > cigarCapacity) return ISAAC_EXT_E_CAPACITY;
+    nf = 0; nc = 0;
+    for (const FlatOut &p : parts)
+    {
+        for (isaac_ext_fragment_t f : p.fragments) { f.cigarOffset += nc; fragmentsOut[nf++] = f; }
+        std::copy(p.cigars.begin(), p.cigars.end(), cigarsOut + nc);
+        nc += p.cigars.size();
+    }
+    return ISAAC_EXT_OK;
+}
+
+} // namespace
+
+extern "C" int oracle_build_fragments(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
+                                      const isaac_ext_build_batch_t *batch, uint64_t fragmentCapacity, isaac_ext_fragment_t *fragmentsOut,
+                                      uint64_t *readFragmentBegin, uint64_t cigarCapacity, uint32_t *cigarsOut, uint8_t *builtOut,
+                                      uint64_t *fragmentCount, uint64_t *cigarWords, uint32_t threads)
+{
+    try
+    {
+        const std::vector<reference::Contig> contigs = makeContigs(genome);
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        alignment::SeedMetadataList seeds;
+        for (uint32_t s = 0; s < batch->seedCount; ++s)
+            seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
+        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+        const uint32_t n = reads->clusterCount, rc = reads->readCount;
+        if (threads < 1) threads = 1;
+        if (n < 2 * threads) threads = 1;
+        std::vector<FlatOut> parts(threads);
+        std::vector<uint64_t> counts(size_t(n) * rc, 0);
+        parallelFor(n, threads, [&](uint32_t t, uint32_t b, uint32_t e) {
+            alignment::FragmentBuilder builder(layouts, cfg->repeatThreshold, cfg->maxSeedsPerRead, cfg->gappedMismatchesMax,
+                                               cfg->avoidSmithWaterman, cfg->gapMatchScore, cfg->gapMismatchScore,
+                                               cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore, cfg->semialignedGapLimit);
+            ClusterHolder holder(maxReadLength);
+            std::vector<alignment::Match> matches;
+            for (uint32_t c = b; c < e; ++c)
+            {
+                holder.load(reads, rml, c);
+                matches.clear();
+                for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
+                    matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
+                                                       reference::ReferencePosition(batch->matches[m].location)));
+                builtOut[c] = builder.build(contigs, rml, seeds, noAdapters, matches.begin(), matches.end(), holder.cluster,
+                                            batch->withGaps != 0);
+                if (builtOut[c] || !matches.empty())
+                {
+                    for (uint32_t r = 0; r < rc; ++r)
+                    {
+                        for (const alignment::FragmentMetadata &f : builder.getFragments()[r]) parts[t].add(f, c * rc + r, rml);
+                        counts[size_t(c) * rc + r] = builder.getFragments()[r].size();
+                    }
+                }
+            }
+        });
+        readFragmentBegin[0] = 0;
+        for (size_t i = 0; i < counts.size(); ++i) readFragmentBegin[i + 1] = readFragmentBegin[i] + counts[i];
+        return concatenate(parts, fragmentCapacity, fragmentsOut, cigarCapacity, cigarsOut, fragmentCount, cigarWords);
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+}
+
+extern "C" int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
+                                     const isaac_ext_tls_t *tls, uint32_t requestCount, const isaac_ext_rescue_request_t *requests,
+                                     uint64_t fragmentCapacity, isaac_ext_fragment_t *fragmentsOut, uint64_t *requestFragmentBegin,
+                                     uint64_t cigarCapacity, uint32_t *cigarsOut, uint8_t *rescuedOut,
+                                     uint64_t *fragmentCount, uint64_t *cigarWords, uint32_t threads)
+{
+    try
+    {
+        const std::vector<reference::Contig> contigs = makeContigs(genome);
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        const alignment::TemplateLengthStatistics stats(
+            tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[1]), tls->mateDriftRange);
+        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+        const uint32_t rc = reads->readCount;
+        if (threads < 1) threads = 1;
+        if (requestCount < 2 * threads) threads = 1;
+        std::vector<FlatOut> parts(threads);
+        std::vector<uint64_t> counts(requestCount, 0);
+        parallelFor(requestCount, threads, [&](uint32_t t, uint32_t b, uint32_t e) {
+            alignment::ShadowAligner aligner(layouts, cfg->gappedMismatchesMax, cfg->avoidSmithWaterman, cfg->gapMatchScore,
+                                             cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore);
+            ClusterHolder holder(maxReadLength);
+            uint32_t loaded = -1U;
+            std::vector<alignment::FragmentMetadata> shadowList;
+            shadowList.reserve(1000);            // TemplateBuilder::TRACKED_REPEATS_MAX_ONE_READ (TemplateBuilder.hh:145, TemplateBuilder.cpp:82)
+            for (uint32_t i = b; i < e; ++i)
+            {
+                const isaac_ext_rescue_request_t &q = requests[i];
+                const uint32_t clusterId = q.orphanReadId / rc, readIndex = q.orphanReadId % rc;
+                if (loaded != clusterId) { holder.load(reads, rml, clusterId); loaded = clusterId; }
+                alignment::FragmentMetadata orphan(&holder.cluster, 0, readIndex);
+                orphan.reverse = q.orphanContigStrand & 1;
+                orphan.contigId = q.orphanContigStrand >> 1;
+                orphan.position = q.orphanPosition;
+                orphan.observedLength = q.orphanObservedLength;
+                shadowList.clear();
+                rescuedOut[i] = aligner.rescueShadow(contigs, orphan, shadowList, rml, noAdapters, stats, q.bestTemplateLength);
+                const uint32_t shadowReadId = clusterId * rc + (readIndex + 1) % 2;
+                for (const alignment::FragmentMetadata &f : shadowList) parts[t].add(f, shadowReadId, rml);
+                counts[i] = shadowList.size();
+            }
+        });
+        requestFragmentBegin[0] = 0;
+        for (uint32_t i = 0; i < requestCount; ++i) requestFragmentBegin[i + 1] = requestFragmentBegin[i] + counts[i];
+        return concatenate(parts, fragmentCapacity, fragmentsOut, cigarCapacity, cigarsOut, fragmentCount, cigarWords);
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+}

@@ -93,6 +93,40 @@ class Oracle:
         return self._extend(self.lib.oracle_gapped_batch, genome, reads, config, candidates, cigar_stride, threads, True)
 
 
+def _flat_call(fn, head_args, n_groups, n_flags, fragment_capacity, cigar_capacity, threads):
+    from isaac_aligner_b200.batch import FlatFragments
+    frags = np.zeros(fragment_capacity, dtype=FRAGMENT_DTYPE)
+    begin = np.zeros(n_groups + 1, dtype=np.uint64)
+    cigars = np.zeros(cigar_capacity, dtype=np.uint32)
+    flags = np.zeros(n_flags, dtype=np.uint8)
+    nf, nc = ctypes.c_uint64(), ctypes.c_uint64()
+    rc = fn(*head_args, ctypes.c_uint64(fragment_capacity), ctypes.c_void_p(frags.ctypes.data),
+            ctypes.c_void_p(begin.ctypes.data), ctypes.c_uint64(cigar_capacity), ctypes.c_void_p(cigars.ctypes.data),
+            ctypes.c_void_p(flags.ctypes.data), ctypes.byref(nf), ctypes.byref(nc), ctypes.c_uint32(threads))
+    if rc:
+        raise RuntimeError("oracle call failed: %d (fragments %d, cigar words %d)" % (rc, nf.value, nc.value))
+    return FlatFragments(frags[:nf.value].copy(), begin, cigars[:nc.value].copy(), flags)
+
+
+def build_fragments(oracle, genome, reads, config, match_batch, threads=1):
+    """FragmentBuilder::build for every cluster -> FlatFragments (begin per cluster*readCount, flags = built)"""
+    cap = len(match_batch.matches) + 16
+    return _flat_call(oracle.lib.oracle_build_fragments,
+                      [ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.byref(match_batch.c)],
+                      reads.cluster_count * reads.read_count, reads.cluster_count, cap, cap * 12, threads)
+
+
+def rescue_shadows(oracle, genome, reads, config, tls, requests, threads=1, fragments_per_request=64):
+    """ShadowAligner::rescueShadow for every request -> FlatFragments (begin per request, flags = rescued)"""
+    from isaac_aligner_b200.batch import RESCUE_REQUEST_DTYPE
+    req = np.ascontiguousarray(requests, dtype=RESCUE_REQUEST_DTYPE)
+    cap = len(req) * fragments_per_request + 1024
+    return _flat_call(oracle.lib.oracle_rescue_shadows,
+                      [ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.byref(tls),
+                       ctypes.c_uint32(len(req)), ctypes.c_void_p(req.ctypes.data)],
+                      len(req), len(req), cap, cap * 4, threads)
+
+
 def port():
     if not os.path.exists(PORT_SO):
         build("port")
