@@ -31,7 +31,7 @@ EXPORTS = [
     "isaac_ext_create", "isaac_ext_destroy", "isaac_ext_last_error", "isaac_ext_version",
     "isaac_ext_set_reference", "isaac_ext_set_reads", "isaac_ext_banded_sw_batch", "isaac_ext_ungapped_batch",
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
-    "isaac_ext_launch_count", "isaac_ext_measure_int32_peak",
+    "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
 ]
 
 
@@ -126,6 +126,28 @@ class Context:
         self._check(_lib.isaac_ext_gapped_batch(self._h, ctypes.c_uint32(n), _p(cand), ctypes.c_uint32(cigar_stride),
                                                 _p(frags), _p(cig), _p(mask)))
         return frags, cig, mask
+
+    def build_fragments(self, match_batch, copy=True):
+        """FragmentBuilder::build for every cluster of the resident read set -> batch.FlatFragments
+        (begin per cluster * readCount + readIndex, flags = return value of build())"""
+        from .batch import BuildResult, copy_result
+        res = BuildResult()
+        self._check(_lib.isaac_ext_build_fragments(self._h, ctypes.byref(match_batch.c), ctypes.byref(res)))
+        if not copy:
+            return res
+        return copy_result(res, self.reads.cluster_count * self.reads.read_count, "readFragmentBegin", "built",
+                           self.reads.cluster_count)
+
+    def rescue_shadows(self, tls, requests, copy=True):
+        """ShadowAligner::rescueShadow for every request -> batch.FlatFragments (begin per request, flags = rescued)"""
+        from .batch import RESCUE_REQUEST_DTYPE, RescueResult, copy_result
+        req = np.ascontiguousarray(requests, dtype=RESCUE_REQUEST_DTYPE)
+        res = RescueResult()
+        self._check(_lib.isaac_ext_rescue_shadows(self._h, ctypes.byref(tls), ctypes.c_uint32(len(req)), _p(req),
+                                                  ctypes.byref(res)))
+        if not copy:
+            return res
+        return copy_result(res, len(req), "requestFragmentBegin", "rescued", len(req))
 
     def measure_int32_peak(self, kind=0):
         """operations per second of the integer pipes (0: add.s32, 1: max.s32, 2: 16x2 max counted twice)"""

@@ -1,0 +1,46 @@
+// isaac_ext_build_fragments / isaac_ext_rescue_shadows: the phase drivers (see host_pipeline.cuh for the plan).
+// Included by isaac_ext.cu after the context definition.
+#pragma once
+#include "host_pipeline.cuh"
+
+namespace isaac_b200
+{
+
+/// Buffers of the two pipelines, owned by the context and reused across calls.
+struct PipelineState
+{
+    // host (pinned): kernel inputs and outputs of each pass
+    PinnedBuffer<isaac_ext_candidate_t> hCand1, hCand3;
+    PinnedBuffer<isaac_ext_fragment_t> hFrag1, hFrag3;
+    PinnedBuffer<uint32_t> hCig1, hCig3;
+    PinnedBuffer<IndelTask> hTasks;
+    PinnedBuffer<IndelResult> hIndel;
+    PinnedBuffer<ShadowTask> hShadowTasks;
+    PinnedBuffer<uint32_t> hTaskBegin, hTaskCount;
+    // device
+    DeviceBuffer<isaac_ext_candidate_t> dCand;
+    DeviceBuffer<isaac_ext_fragment_t> dFrag;
+    DeviceBuffer<uint32_t> dCig;
+    DeviceBuffer<IndelTask> dTasks;
+    DeviceBuffer<IndelResult> dIndel;
+    DeviceBuffer<ShadowTask> dShadowTasks;
+    DeviceBuffer<int> dShadowScratch;
+    DeviceBuffer<uint32_t> dTaskBegin, dTaskCount, dPoolSize;
+    // flattened results handed back to the caller
+    std::vector<WorkFragment> work;
+    std::vector<uint32_t> indelCigars;
+    std::vector<isaac_ext_fragment_t> outFragments;
+    std::vector<uint64_t> outBegin;
+    std::vector<uint32_t> outCigars;
+    std::vector<uint8_t> outFlags;
+
+    void release()
+    {
+        hCand1.release(); hCand3.release(); hFrag1.release(); hFrag3.release(); hCig1.release(); hCig3.release();
+        hTasks.release(); hIndel.release(); hShadowTasks.release(); hTaskBegin.release(); hTaskCount.release();
+        dCand.release(); dFrag.release(); dCig.release(); dTasks.release(); dIndel.release(); dShadowTasks.release();
+        dShadowScratch.release(); dTaskBegin.release(); dTaskCount.release(); dPoolSize.release();
+    }
+};
+
+} // namespace isaac_b200

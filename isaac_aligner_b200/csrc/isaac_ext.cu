@@ -7,29 +7,16 @@
 #include <string>
 #include <vector>
 
+#include "device_buffer.cuh"
 #include "kernels.cuh"
 #include "kernels2.cuh"
+#include "host_build.cuh"
 
 using namespace isaac_b200;
 
 namespace
 {
 thread_local std::string g_createError;
-
-template <class T> struct DeviceBuffer
-{
-    T *p = nullptr; size_t capacity = 0;
-    cudaError_t reserve(size_t n)
-    {
-        if (n <= capacity) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; capacity = 0;
-        const cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) capacity = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; capacity = 0; }
-};
 } // namespace
 
 struct isaac_ext_ctx
@@ -44,6 +31,9 @@ struct isaac_ext_ctx
     // thread, default) or 1 (scalar, one alignment per thread); ISAAC_EXT_SW_BLOCKS_PER_SM bounds the persistent grid.
     int swImpl = 2;
     unsigned swBlocksPerSm = 4;
+    unsigned hostThreads = 1;     // config.hostThreads (0 = hardware concurrency)
+    uint32_t clusterCount = 0;    // of the resident read set
+    PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
     DeviceBuffer<double> tables;
@@ -173,6 +163,7 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
     }
     isaac_ext_ctx *ctx = new isaac_ext_ctx();
     ctx->cfg = *config;
+    ctx->hostThreads = config->hostThreads ? config->hostThreads : std::max(1u, std::thread::hardware_concurrency());
     if (const char *e = std::getenv("ISAAC_EXT_SW_IMPL")) ctx->swImpl = std::atoi(e) == 1 ? 1 : 2;
     if (const char *e = std::getenv("ISAAC_EXT_SW_BLOCKS_PER_SM")) ctx->swBlocksPerSm = std::max(1, std::min(16, std::atoi(e)));
     ctx->device = config->device;
@@ -214,6 +205,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
+    ctx->pipeline.release();
     delete ctx;
 }
 
@@ -304,6 +296,7 @@ extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *
     v.words2 = words2; v.wordsN = wordsN; v.qualityStride = qualityStride; v.readCount = r->readCount;
     v.readLength[0] = len0; v.readLength[1] = len1; v.firstCycle[0] = r->firstCycle[0]; v.firstCycle[1] = r->firstCycle[1];
     v.readTotal = uint32_t(readTotal);
+    ctx->clusterCount = r->clusterCount;
     ctx->haveReads = true;
     return ISAAC_EXT_OK;
 }
@@ -487,3 +480,6 @@ extern "C" int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double
     *opsPerSecond = best;
     return ISAAC_EXT_OK;
 }
+
+// isaac_ext_build_fragments, isaac_ext_rescue_shadows
+#include "isaac_ext_pipelines.cuh"
