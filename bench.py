@@ -182,6 +182,8 @@ def run_b200(args):
     d_frag_g = torch.empty((n, 64), dtype=torch.uint8, device=dev)
     d_cig_g = torch.empty((n, stride), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    d_stats = torch.zeros(64, dtype=torch.int64, device=dev)
+    from isaac_aligner_b200 import distributed
 
     def step(events=None):
         if events:
@@ -192,6 +194,10 @@ def run_b200(args):
         ctx.gapped_device(n, d_cand.data_ptr(), stride, d_frag_g.data_ptr(), d_cig_g.data_ptr(), 0, stream)
         if events:
             events[2].record()
+        # per-tile statistics: K6 counters of this rank's results, summed over the ranks (the path's only collective)
+        d_stats.zero_()
+        ctx.tile_stats_device(n, d_frag_g.data_ptr(), d_stats.data_ptr(), stream)
+        distributed.allreduce_stats(d_stats)
 
     def barrier():
         if world > 1:
@@ -291,6 +297,7 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": workload_config(args),
         "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "tile_stats": dict(zip(distributed.STAT_NAMES, (int(x) for x in d_stats.cpu().numpy().view(np.uint64)[:8]))),
         "roofline": {"bound": "int32", "kernel": "gappedKernel", "achieved": achieved / 1e12, "peak": peak_add / 1e12,
                      "unit": "TOP/s", "frac": achieved / peak_add, "traffic": traffic,
                      "ops_per_cell": OPS_PER_CELL, "gcups_kernel": sw_gcups_kernel, "ms_per_launch": ms_gapped,

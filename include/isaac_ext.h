@@ -257,6 +257,14 @@ int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dC
                                   uint32_t cigarStride, void *dFragmentsOut, void *dCigarOut,
                                   void *dMismatchMaskOut, void *cudaStream);
 
+/* Per-tile statistics (K6).  Adds the counters of n fragment records that live in DEVICE memory to the 64 u64
+ * counters at dStats (device memory, caller zeroes them) on 'cudaStream': [0] records, [1] aligned, [2] with gaps,
+ * [3] edit distance 0, [4] mismatches, [5] edit distance, [6] gaps, [7] observed bases, [8..40] histogram of the
+ * mismatch count clipped at 32.  The ranks of a multi-GPU run sum these vectors with one NCCL all-reduce, the only
+ * collective of the path (the reference sums per-thread TileStats the same way, MatchSelector.cpp:439-442). */
+#define ISAAC_EXT_STATS_COUNTERS 64
+int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const void *dFragments, void *dStats, void *cudaStream);
+
 /* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
  * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
 int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);

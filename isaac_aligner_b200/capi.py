@@ -32,6 +32,7 @@ EXPORTS = [
     "isaac_ext_set_reference", "isaac_ext_set_reads", "isaac_ext_banded_sw_batch", "isaac_ext_ungapped_batch",
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
+    "isaac_ext_tile_stats_device",
 ]
 
 
@@ -148,6 +149,11 @@ class Context:
         if not copy:
             return res
         return copy_result(res, len(req), "requestFragmentBegin", "rescued", len(req))
+
+    def tile_stats_device(self, n, d_fragments, d_stats, stream):
+        """adds the K6 counters of n device-resident fragment records to the 64 u64 at d_stats"""
+        self._check(_lib.isaac_ext_tile_stats_device(self._h, ctypes.c_uint32(n), ctypes.c_void_p(d_fragments),
+                                                     ctypes.c_void_p(d_stats), ctypes.c_void_p(stream)))
 
     def measure_int32_peak(self, kind=0):
         """operations per second of the integer pipes (0: add.s32, 1: max.s32, 2: 16x2 max counted twice)"""

@@ -45,6 +45,7 @@ struct ReadSetView
     // zeros so that a 16-base fetch may start anywhere in the strand.
     const uint64_t *codes4;
     uint32_t wordsC;
+    const uint8_t *qualityStrand;    // qualities again per strand in strand order: (readId * 2 + reverse) * qualityStride + p
     uint32_t words2, wordsN, qualityStride;
     uint32_t readCount;
     uint32_t readLength[2];
@@ -55,6 +56,10 @@ struct ReadSetView
     __device__ __forceinline__ const uint64_t *strandCodes(unsigned readId, bool reverse) const
     {
         return codes4 + (size_t(readId) * 2 + (reverse ? 1u : 0u)) * wordsC;
+    }
+    __device__ __forceinline__ const uint8_t *strandQuality(unsigned readId, bool reverse) const
+    {
+        return qualityStrand + (size_t(readId) * 2 + (reverse ? 1u : 0u)) * qualityStride;
     }
     /// highest strand position a 16-base fetch may start at
     __device__ __forceinline__ unsigned codesClamp() const { return (wordsC - 2u) * 16u; }

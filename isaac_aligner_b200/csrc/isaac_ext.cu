@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "kernels2.cuh"
 #include "host_build.cuh"
+#include "kernels_stats.cuh"
 
 using namespace isaac_b200;
 
@@ -50,6 +51,7 @@ struct isaac_ext_ctx
     DeviceBuffer<uint32_t> readBases2, readNmask;
     DeviceBuffer<uint8_t> readQuality, bclStage;
     DeviceBuffer<uint64_t> readCodes4;
+    DeviceBuffer<uint8_t> readQualityStrand;
     DeviceBuffer<uint16_t> readMasked;
     ReadSetView reads{};
     bool haveReads = false;
@@ -170,13 +172,15 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
     int rc = ctx->cuda(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (!rc) rc = ctx->cuda(cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, ctx->device), "cudaDeviceGetAttribute");
     if (!rc) rc = ctx->cuda(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    if (!rc) rc = ctx->cuda(ctx->tables.reserve(200), "cudaMalloc(tables)");
+    if (!rc) rc = ctx->cuda(ctx->tables.reserve(201), "cudaMalloc(tables)");
     if (!rc) rc = ctx->cuda(ctx->errorFlag.reserve(1), "cudaMalloc(flag)");
     if (!rc) rc = ctx->cuda(cudaMemset(ctx->errorFlag.p, 0, sizeof(uint32_t)), "cudaMemset(flag)");
     if (!rc)
     {
         // Quality::logMatchLookup / logMismatchLookup, computed with the host libm like the reference (Quality.cpp:34-66)
-        double t[200];
+        // entry 200 = 0.0 is what an inserted base adds to logProbability (x + 0.0 == x bit for bit)
+        double t[201];
+        t[200] = 0.0;
         t[0] = std::log(1.0 - std::pow(10.0, 1.0 / -10.0));
         for (int q = 1; q < 100; ++q) t[q] = std::log(1.0 - std::pow(10.0, double(q) / -10.0));
         t[100] = t[0];
@@ -202,7 +206,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     ctx->tables.release(); ctx->refBases2.release(); ctx->refNmask.release(); ctx->refContigOffset.release();
     ctx->refContigLength.release(); ctx->readBases2.release(); ctx->readNmask.release(); ctx->readQuality.release();
-    ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
+    ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readQualityStrand.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
     ctx->pipeline.release();
@@ -285,13 +289,14 @@ extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *
     CK(cudaGetLastError());
     const uint32_t wordsC = (maxLen + 15) / 16 + 2;
     CK(ctx->readCodes4.reserve(readTotal * 2 * wordsC));
+    CK(ctx->readQualityStrand.reserve(readTotal * 2 * qualityStride));
     encodeStrandCodesKernel<<<gridFor(ctx, readTotal * 2 * wordsC, 256, 16), 256, 0, ctx->stream>>>(
-        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, ctx->readCodes4.p);
+        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, ctx->readCodes4.p, qualityStride, ctx->readQualityStrand.p);
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     ReadSetView &v = ctx->reads;
-    v.codes4 = ctx->readCodes4.p; v.wordsC = wordsC;
+    v.codes4 = ctx->readCodes4.p; v.wordsC = wordsC; v.qualityStrand = ctx->readQualityStrand.p;
     v.bases2 = ctx->readBases2.p; v.nmask = ctx->readNmask.p; v.quality = ctx->readQuality.p; v.endCyclesMasked = ctx->readMasked.p;
     v.words2 = words2; v.wordsN = wordsN; v.qualityStride = qualityStride; v.readCount = r->readCount;
     v.readLength[0] = len0; v.readLength[1] = len1; v.firstCycle[0] = r->firstCycle[0]; v.firstCycle[1] = r->firstCycle[1];
@@ -479,6 +484,17 @@ extern "C" int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double
     CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));
     *opsPerSecond = best;
     return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const void *dFragments, void *dStats, void *cudaStream)
+{
+    if (!ctx || !dStats || (n && !dFragments)) return ISAAC_EXT_E_INVALID_ARG;
+    static_assert(STAT_COUNT == ISAAC_EXT_STATS_COUNTERS, "counter layout");
+    if (!n) return ISAAC_EXT_OK;
+    tileStatsKernel<<<gridFor(ctx, n, 256, 8), 256, 0, cudaStream_t(cudaStream)>>>(
+        n, static_cast<const isaac_ext_fragment_t *>(dFragments), static_cast<unsigned long long *>(dStats));
+    ++ctx->launches;
+    return ctx->cuda(cudaGetLastError(), "tileStatsKernel");
 }
 
 // isaac_ext_build_fragments, isaac_ext_rescue_shadows

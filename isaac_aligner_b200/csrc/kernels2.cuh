@@ -34,41 +34,20 @@ __device__ __forceinline__ GappedPrep prepareGapped(const ReferenceView &ref, co
     p.strandPosition = p.f.position;
     // no gapped alignment if the reference is too short (:204-208)
     p.run = p.sequenceLength && !(contigLength < long(p.sequenceLength) + p.strandPosition + 16);
-    p.left = 0;
-    if (p.run) p.left = p.strandPosition >= 8 ? 8u : unsigned(p.strandPosition);   // getFlanks (:51-82), see gappedKernel
+    // getFlanks (:51-82): once the "too short" test has passed the right flank is never squeezed
+    p.left = p.run ? (p.strandPosition >= 8 ? 8u : unsigned(p.strandPosition)) : 0u;
     return p;
 }
 
-/// Finishes one candidate after its Smith-Waterman: soft clips, position, re-score, store (GappedAligner.cpp:231-248).
-__device__ __forceinline__ void finishGapped(const ReferenceView &ref, const ReadSetView &reads, const ScoreParams &sp,
-                                             const GappedPrep &p, const uint32_t i, uint32_t *ops /* ops[1..1+nSw) hold the SW cigar */,
-                                             unsigned nSw, const unsigned ret, const bool overflow, const uint32_t cigarStride,
-                                             isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
-                                             uint64_t *__restrict__ masks, uint32_t *__restrict__ errorFlag)
+/// The CIGAR of one gapped candidate assembled around the Smith-Waterman operations (GappedAligner.cpp:191-240):
+/// ops[1..1+nSw) hold the SW CIGAR on entry; returns the first word of the complete CIGAR and its length.
+__device__ __forceinline__ uint32_t *assembleGappedCigar(const GappedPrep &p, uint32_t *ops, unsigned nSw, unsigned &nOps)
 {
-    isaac_ext_fragment_t o;
-    initFragment(o, p.c, reads.readCount);
-    uint64_t *mask = masks ? masks + size_t(i) * ISAAC_EXT_MASK_WORDS : nullptr;
-    if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
-    o.cigarOffset = i * cigarStride;
-    o.lowClipped = uint16_t(p.f.lowClipped); o.highClipped = uint16_t(p.f.highClipped); o.position = p.f.position;
-    if (p.run)
-    {
-        uint32_t *all = ops + 1;
-        unsigned nOps = nSw;
-        if (p.begin) { ops[0] = cigarWord(uint32_t(p.begin), ISAAC_EXT_CIGAR_SOFT_CLIP); all = ops; ++nOps; }        // :191-195
-        if (long(p.L) - p.end) all[nOps++] = cigarWord(uint32_t(p.L - p.end), ISAAC_EXT_CIGAR_SOFT_CLIP);          // :233-237
-        const long strandPosition = p.strandPosition + long(ret) - long(p.left);                                   // :231,240
-        if (overflow || nOps > cigarStride) { atomicOr(errorFlag, 1u); }
-        else
-        {
-            scoreCigar(ref, reads, sp, p.c.readId, p.L, p.f.reverse, ref.contigOffset[p.contigId], strandPosition, all, nOps, o, mask);
-            uint32_t *cigar = cigars + size_t(i) * cigarStride;
-            for (unsigned k = 0; k < nOps; ++k) cigar[k] = all[k];
-            o.cigarLength = uint16_t(nOps);
-        }
-    }
-    fragments[i] = o;
+    uint32_t *all = ops + 1;
+    nOps = nSw;
+    if (p.begin) { ops[0] = cigarWord(uint32_t(p.begin), ISAAC_EXT_CIGAR_SOFT_CLIP); all = ops; ++nOps; }      // :191-195
+    if (long(p.L) - p.end) all[nOps++] = cigarWord(uint32_t(p.L - p.end), ISAAC_EXT_CIGAR_SOFT_CLIP);        // :233-237
+    return all;
 }
 
 /// Sequential code streams of a pair of (read strand window, reference window).  q2()/d2() must be called in
@@ -105,11 +84,18 @@ struct ResidentPairSrc
 };
 
 __global__ void __launch_bounds__(128)
-gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
               const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
               isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
               uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
 {
+    // the two 100-entry log-probability tables are looked up once per base: keep them in shared memory
+    __shared__ double tables[201];      // [0,100) logMatch, [100,200) logMismatch, [200] = 0.0 (contiguous in global too)
+    for (unsigned i = threadIdx.x; i < 201; i += blockDim.x) tables[i] = spGlobal.logMatch[i];
+    __syncthreads();
+    ScoreParams sp = spGlobal;
+    sp.logMatch = tables; sp.logMismatch = tables + 100;
+
     const size_t tbStride = size_t(gridDim.x) * blockDim.x;
     uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
     const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};
@@ -132,19 +118,59 @@ gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParam
                                    {LA ? ref.contigOffset[pa.contigId] + uint64_t(pa.strandPosition - long(pa.left)) : 0ull,
                                     LB ? ref.contigOffset[pb.contigId] + uint64_t(pb.strandPosition - long(pb.left)) : 0ull},
                                    {0, 0}, {0, 0}, reads.codesClamp()};
-            sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);
+            sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);                                                 // :231
         }
-        uint32_t ops[SW_OPS_CAP + 2];
+        // ---- traceback of both halves in one pass over the rows
+        uint32_t opsA[SW_OPS_CAP + 2], opsB[SW_OPS_CAP + 2];
+        Sw2Walker wa, wb;
+        wa.start(LA, jj[0], type[0], opsA + 1, SW_OPS_CAP);
+        wb.start(LB, jj[1], type[1], opsB + 1, SW_OPS_CAP);
+        sw2TracebackPair(tb, tbStride, wa, wb);
+        unsigned nSwA = 0, nSwB = 0;
+        const unsigned retA = LA ? wa.finish(nSwA) : 0u, retB = LB ? wb.finish(nSwB) : 0u;
+        // ---- soft clips, position (:233-240) and updateFragmentCigar of both halves side by side (:245)
+        unsigned nOpsA = 0, nOpsB = 0;
+        uint32_t *allA = assembleGappedCigar(pa, opsA, nSwA, nOpsA), *allB = assembleGappedCigar(pb, opsB, nSwB, nOpsB);
+        const long posA = pa.strandPosition + long(retA) - long(pa.left), posB = pb.strandPosition + long(retB) - long(pb.left);
+        const bool okA = pa.run && !(wa.overflow || nOpsA > cigarStride), okB = haveB && pb.run && !(wb.overflow || nOpsB > cigarStride);
+        if ((pa.run && !okA) || (haveB && pb.run && !okB)) atomicOr(errorFlag, 1u);
+        uint64_t *maskA = masks ? masks + size_t(iA) * ISAAC_EXT_MASK_WORDS : nullptr;
+        uint64_t *maskB = masks && haveB ? masks + size_t(iB) * ISAAC_EXT_MASK_WORDS : nullptr;
+        if (maskA) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) maskA[k] = 0;
+        if (maskB) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) maskB[k] = 0;
+        CigarScorer sa, sb;
+        sa.start(ref, reads, sp, pa.c.readId, okA ? pa.L : 0u, pa.f.reverse, ref.contigOffset[pa.contigId], posA, allA, nOpsA, maskA);
+        sb.start(ref, reads, sp, pb.c.readId, okB ? pb.L : 0u, pb.f.reverse, ref.contigOffset[pb.contigId], posB, allB, nOpsB, maskB);
+        const unsigned Lmax = max(sa.L, sb.L);
+        for (unsigned w = 0; w * 16u < Lmax; ++w) { sa.stepWord(w); sb.stepWord(w); }
         {
-            unsigned nSw = 0, ret = 0; bool overflow = false;
-            if (LA) ret = sw2Traceback(tb, tbStride, 0, LA, jj[0], type[0], ops + 1, SW_OPS_CAP, nSw, overflow);
-            finishGapped(ref, reads, sp, pa, iA, ops, nSw, ret, overflow, cigarStride, fragments, cigars, masks, errorFlag);
+            isaac_ext_fragment_t o;
+            initFragment(o, pa.c, reads.readCount);
+            o.cigarOffset = iA * cigarStride;
+            o.lowClipped = uint16_t(pa.f.lowClipped); o.highClipped = uint16_t(pa.f.highClipped); o.position = pa.f.position;
+            if (okA)
+            {
+                sa.finish(o);
+                o.position = posA;
+                for (unsigned k = 0; k < nOpsA; ++k) cigars[size_t(iA) * cigarStride + k] = allA[k];
+                o.cigarLength = uint16_t(nOpsA);
+            }
+            fragments[iA] = o;
         }
         if (haveB)
         {
-            unsigned nSw = 0, ret = 0; bool overflow = false;
-            if (LB) ret = sw2Traceback(tb, tbStride, 1, LB, jj[1], type[1], ops + 1, SW_OPS_CAP, nSw, overflow);
-            finishGapped(ref, reads, sp, pb, iB, ops, nSw, ret, overflow, cigarStride, fragments, cigars, masks, errorFlag);
+            isaac_ext_fragment_t o;
+            initFragment(o, pb.c, reads.readCount);
+            o.cigarOffset = iB * cigarStride;
+            o.lowClipped = uint16_t(pb.f.lowClipped); o.highClipped = uint16_t(pb.f.highClipped); o.position = pb.f.position;
+            if (okB)
+            {
+                sb.finish(o);
+                o.position = posB;
+                for (unsigned k = 0; k < nOpsB; ++k) cigars[size_t(iB) * cigarStride + k] = allB[k];
+                o.cigarLength = uint16_t(nOpsB);
+            }
+            fragments[iB] = o;
         }
     }
 }
@@ -181,16 +207,21 @@ bandedSwAsciiKernel2(uint32_t n, const unsigned char *__restrict__ queries, cons
                             {databases + databaseOffsets[iA], databases + databaseOffsets[iB]}, {LA, LB}};
         int jj[2]; unsigned type[2];
         sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);
-        uint32_t ops[SW_OPS_CAP];
+        uint32_t opsA[SW_OPS_CAP], opsB[SW_OPS_CAP];
+        Sw2Walker wa, wb;
+        wa.start(LA, jj[0], type[0], opsA, SW_OPS_CAP);
+        wb.start(LB, jj[1], type[1], opsB, SW_OPS_CAP);
+        sw2TracebackPair(tb, tbStride, wa, wb);
         for (unsigned h = 0; h < (haveB ? 2u : 1u); ++h)
         {
             const uint32_t i = h ? iB : iA;
-            unsigned nOps = 0; bool overflow = false;
-            const unsigned ret = sw2Traceback(tb, tbStride, h, h ? LB : LA, jj[h], type[h], ops, SW_OPS_CAP, nOps, overflow);
-            if (overflow) atomicOr(errorFlag, 1u);
+            Sw2Walker &w = h ? wb : wa;
+            unsigned nOps = 0;
+            const unsigned ret = w.finish(nOps);
+            if (w.overflow) atomicOr(errorFlag, 1u);
             offsets[i] = ret;
             cigarLengths[i] = nOps;
-            for (unsigned k = 0; k < nOps && k < cigarStride; ++k) cigars[size_t(i) * cigarStride + k] = ops[k];
+            for (unsigned k = 0; k < nOps && k < cigarStride; ++k) cigars[size_t(i) * cigarStride + k] = w.ops[k];
         }
     }
 }

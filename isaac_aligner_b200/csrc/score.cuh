@@ -96,93 +96,146 @@ __device__ __forceinline__ uint64_t referenceCodes16(const ReferenceView &ref, u
     return spread2to4(two) | (spread1to4(n16) * uint64_t(CODE_REF_N));
 }
 
-/// AlignerBase::updateFragmentCigar (AlignerBase.cpp:121-227): walks the CIGAR against the reference and fills
-/// the scores of 'out'.  logProbability is the reference's left-to-right FP64 sum starting from 0.0 (soft-clipped
-/// bases add logMatch, inserted bases add nothing, AlignerBase.cpp:165-213).
-///
-/// The walk is organised as ONE loop over the L read bases with the CIGAR operation as loop-carried state, so that
-/// all threads of a warp run the same trip count whatever their CIGARs look like; deletions are consumed when the
-/// operation changes.  \return matchCount
+/// AlignerBase::updateFragmentCigar (AlignerBase.cpp:121-227) as a walker over the read, 16 bases (one 64-bit word of
+/// 4-bit codes) per step:
+///   * word level: the CIGAR operations overlapping the word are turned into one-bit-per-nibble masks (mismatch,
+///     inserted, not-a-match, run boundary) by XOR-ing the read word with the 16 reference codes fetched for each
+///     ALIGN piece; mismatchCount / matchCount / editDistance are popcounts of those masks;
+///   * base level: only what must stay sequential is left in the per-base loop -- the reference's left-to-right FP64
+///     sum (one shared-memory table lookup + one DADD per base; soft-clipped bases add logMatch, inserted bases add the
+///     table's 0.0 entry, AlignerBase.cpp:165-213) and the longest-run-of-matches counter.
+/// All threads of a warp run the same trip count whatever their CIGARs look like, and two walkers can be stepped side
+/// by side (two independent FP64 chains).
+struct CigarScorer
+{
+    const ReferenceView *ref; const ScoreParams *sp;
+    const uint64_t *strandWords; const uint8_t *quality; const uint32_t *cigar; uint64_t *mask;
+    uint64_t g, g0;
+    double lp;
+    unsigned L, nOps, k, remaining, op;
+    unsigned matchCount, mismatchCount, matchesInARow, gapCount, editDistance, sws, run;
+    bool fresh;
+
+    __device__ __forceinline__ void start(const ReferenceView &r, const ReadSetView &reads, const ScoreParams &s, unsigned readId,
+                                          unsigned length, bool reverse, uint64_t contigOffset, long strandPosition,
+                                          const uint32_t *ops, unsigned n, uint64_t *maskOut)
+    {
+        ref = &r; sp = &s; strandWords = reads.strandCodes(readId, reverse); quality = reads.strandQuality(readId, reverse);
+        cigar = ops; mask = maskOut; g0 = contigOffset + uint64_t(strandPosition); g = g0; lp = 0.0;
+        L = length; nOps = n; k = 0; remaining = 0; op = ISAAC_EXT_CIGAR_SOFT_CLIP; fresh = false;
+        matchCount = mismatchCount = matchesInARow = gapCount = editDistance = sws = run = 0;
+    }
+
+    __device__ __forceinline__ void stepWord(const unsigned w)
+    {
+        const unsigned P0 = w * 16u;
+        if (P0 >= L) return;
+        const unsigned cnt = min(16u, L - P0);
+        const uint64_t ONES = 0x1111111111111111ull;
+        const uint64_t rword = strandWords[w];
+        const uint64_t readN = (rword >> 2) & ONES;                  // CODE_READ_N == 4
+        uint64_t mism = 0, skip = 0, notm = 0, bnd = 0;
+        unsigned off = 0;
+        while (off < cnt)
+        {
+            while (remaining == 0 && k < nOps)
+            {
+                const uint32_t word = cigar[k++];
+                const unsigned length = word >> 4;
+                op = word & 0xFu;
+                if (op == ISAAC_EXT_CIGAR_DELETE)                                                // :192-198
+                {
+                    g += length; editDistance += length; ++gapCount;
+                    sws += sp->gapOpen + min(sp->maxGapExtend, (length - 1) * sp->gapExtend);
+                }
+                else
+                {
+                    remaining = length;
+                    fresh = true;                                                                // a new run of matches (:158)
+                    if (op == ISAAC_EXT_CIGAR_INSERT)                                            // :185-191
+                    {
+                        editDistance += length; ++gapCount;
+                        sws += sp->gapOpen + min(sp->maxGapExtend, (length - 1) * sp->gapExtend);
+                    }
+                }
+            }
+            if (remaining == 0) { remaining = cnt - off; op = ISAAC_EXT_CIGAR_SOFT_CLIP; }        // malformed CIGAR: never for our callers
+            const unsigned take = min(remaining, cnt - off);
+            const uint64_t seg = ((take >= 16u ? 0ull : (1ull << (4u * take))) - 1ull) << (4u * off);
+            if (op == ISAAC_EXT_CIGAR_ALIGN)
+            {
+                const uint64_t d = referenceCodes16(*ref, g) << (4u * off);
+                const uint64_t x = rword ^ d;
+                const uint64_t neq = (x | (x >> 1) | (x >> 2)) & ONES & seg;                     // byte inequality (:176-179)
+                mism |= neq & ~readN;                                                            // !isMatch (Alignment.hh:44-47)
+                editDistance += __popcll(neq);
+                if (fresh) bnd |= 1ull << (4u * off);
+                g += take;
+            }
+            else if (op == ISAAC_EXT_CIGAR_INSERT) { skip |= seg & ONES; notm |= seg & ONES; }
+            else { notm |= seg & ONES; }                                                         // SOFT_CLIP (:199-213)
+            fresh = false;
+            off += take; remaining -= take;
+        }
+        notm |= mism;
+        const uint64_t valid = ONES & (cnt >= 16u ? ~0ull : ((1ull << (4u * cnt)) - 1ull));
+        matchCount += __popcll(~notm & valid);
+        mismatchCount += __popcll(mism);
+        if (mask && mism)                                            // addMismatchCycle (:171), as a bit over base index
+        {
+            uint64_t c = mism;
+            c = (c | (c >> 3)) & 0x0303030303030303ull;
+            c = (c | (c >> 6)) & 0x000F000F000F000Full;
+            c = (c | (c >> 12)) & 0x000000FF000000FFull;
+            c = (c | (c >> 24)) & 0xFFFFull;
+            mask[P0 >> 6] |= c << (P0 & 63u);
+        }
+        // ---- the sequential part: FP64 sum and longest run of matches
+        const uint4 qv = *reinterpret_cast<const uint4 *>(quality + P0);
+        const unsigned qw[4] = {qv.x, qv.y, qv.z, qv.w};
+        const double *table = sp->logMatch;                          // [0,100) match, [100,200) mismatch, [200] = 0.0
+#pragma unroll
+        for (unsigned b = 0; b < 16; ++b)
+        {
+            if (b < cnt)
+            {
+                const unsigned q = (qw[b >> 2] >> ((b & 3u) * 8u)) & 0xFFu;
+                const unsigned m = unsigned(mism >> (4u * b)) & 1u, s = unsigned(skip >> (4u * b)) & 1u;
+                lp += table[s ? 200u : q + 100u * m];
+                if (unsigned(bnd >> (4u * b)) & 1u) run = 0;
+                if (unsigned(notm >> (4u * b)) & 1u) run = 0;
+                else { ++run; matchesInARow = max(matchesInARow, run); }
+            }
+        }
+    }
+
+    __device__ __forceinline__ unsigned finish(isaac_ext_fragment_t &out)
+    {
+        // a well-formed CIGAR has no operation left here (trailing deletions are stripped, BandedSmithWaterman.cpp:447-452)
+        out.observedLength = uint32_t(g - g0);
+        out.logProbability = lp;
+        out.mismatchCount = uint16_t(mismatchCount);
+        out.matchesInARow = uint16_t(matchesInARow);
+        out.gapCount = uint16_t(gapCount);
+        out.editDistance = uint16_t(editDistance);
+        out.smithWatermanScore = sws + mismatchCount * sp->mismatch;                             // :173
+        out.matchCount = uint16_t(matchCount);
+        return matchCount;
+    }
+};
+
+/// updateFragmentCigar of one fragment.  \return matchCount
 __device__ __forceinline__ unsigned scoreCigar(const ReferenceView &ref, const ReadSetView &reads, const ScoreParams &sp,
                                                const unsigned readId, const unsigned L, const bool reverse,
                                                const uint64_t contigOffset, const long strandPosition,
                                                const uint32_t *cigar, const unsigned nOps,
                                                isaac_ext_fragment_t &out, uint64_t *mask)
 {
-    uint64_t g = contigOffset + uint64_t(strandPosition);
-    const uint64_t *strandWords = reads.strandCodes(readId, reverse);
-    const uint8_t *quality = reads.quality + size_t(readId) * reads.qualityStride;
-    unsigned matchCount = 0, mismatchCount = 0, matchesInARow = 0, gapCount = 0, editDistance = 0, sws = 0, run = 0;
-    double lp = 0.0;
-    unsigned k = 0, remaining = 0, op = ISAAC_EXT_CIGAR_SOFT_CLIP;
-    uint64_t qBuf = 0, rBuf = 0;
-    unsigned rLeft = 0;
-    for (unsigned p = 0; p < L; ++p)
-    {
-        if ((p & 15u) == 0) qBuf = readCodes16(strandWords, p);
-        const unsigned rc = unsigned(qBuf) & 15u;
-        qBuf >>= 4;
-        const unsigned q = quality[reverse ? L - 1 - p : p];
-        while (remaining == 0 && k < nOps)
-        {
-            if (op == ISAAC_EXT_CIGAR_ALIGN) { matchesInARow = max(matchesInARow, run); }   // :183
-            const uint32_t word = cigar[k++];
-            const unsigned length = word >> 4;
-            op = word & 0xFu;
-            if (op == ISAAC_EXT_CIGAR_DELETE)                                              // :192-198
-            {
-                g += length; editDistance += length; ++gapCount; rLeft = 0;
-                sws += sp.gapOpen + min(sp.maxGapExtend, (length - 1) * sp.gapExtend);
-            }
-            else
-            {
-                remaining = length;
-                run = 0;                                                                   // :158
-                if (op == ISAAC_EXT_CIGAR_INSERT)                                          // :185-191
-                {
-                    editDistance += length; ++gapCount;
-                    sws += sp.gapOpen + min(sp.maxGapExtend, (length - 1) * sp.gapExtend);
-                }
-            }
-        }
-        if (op == ISAAC_EXT_CIGAR_ALIGN)
-        {
-            if (rLeft == 0) { rBuf = referenceCodes16(ref, g); rLeft = 16; }
-            const unsigned gc = unsigned(rBuf) & 15u;
-            rBuf >>= 4; --rLeft; ++g;
-            if (rc == CODE_READ_N || rc == gc)                   // isMatch (Alignment.hh:44-47)
-            {
-                ++matchCount; ++run;
-                lp += sp.logMatch[q];
-            }
-            else
-            {
-                matchesInARow = max(matchesInARow, run); run = 0;
-                if (mask) mask[p >> 6] |= 1ull << (p & 63u);     // addMismatchCycle (:171), as a bit over base index
-                ++mismatchCount;
-                lp += sp.logMismatch[q];
-                sws += sp.mismatch;
-            }
-            editDistance += rc != gc;                             // byte inequality, so Ns count (:175-179)
-        }
-        else if (op == ISAAC_EXT_CIGAR_SOFT_CLIP)                 // :199-213
-        {
-            lp += sp.logMatch[q];
-        }
-        --remaining;
-    }
-    if (op == ISAAC_EXT_CIGAR_ALIGN) matchesInARow = max(matchesInARow, run);
-    // a well-formed CIGAR has no operation left here (trailing deletions are stripped, BandedSmithWaterman.cpp:447-452)
-    out.observedLength = uint32_t(g - contigOffset - uint64_t(strandPosition));
+    CigarScorer s;
+    s.start(ref, reads, sp, readId, L, reverse, contigOffset, strandPosition, cigar, nOps, mask);
+    for (unsigned w = 0; w * 16u < L; ++w) s.stepWord(w);
     out.position = strandPosition;
-    out.logProbability = lp;
-    out.mismatchCount = uint16_t(mismatchCount);
-    out.matchesInARow = uint16_t(matchesInARow);
-    out.gapCount = uint16_t(gapCount);
-    out.editDistance = uint16_t(editDistance);
-    out.smithWatermanScore = sws;
-    out.matchCount = uint16_t(matchCount);
-    return matchCount;
+    return s.finish(out);
 }
 
 } // namespace isaac_b200

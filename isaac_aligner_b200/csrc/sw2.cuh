@@ -141,6 +141,94 @@ __device__ __forceinline__ unsigned sw2Traceback(const uint32_t *__restrict__ tb
     return ret;
 }
 
+/// One traceback in progress (one half of a pair).
+struct Sw2Walker
+{
+    int ii, jj;                 // current row / lane
+    unsigned type;              // 0 G (ALIGN), 1 E (DELETE), 2 F (INSERT)
+    unsigned opLength;
+    unsigned w;                 // next free slot is ops[w-1]; operations are written tail first from the back
+    bool active, overflow;
+    uint32_t *ops; unsigned cap;
+
+    __device__ __forceinline__ void push(unsigned length, unsigned type3)
+    {
+        const uint32_t op = type3 == 0 ? ISAAC_EXT_CIGAR_ALIGN : (type3 == 1 ? ISAAC_EXT_CIGAR_DELETE : ISAAC_EXT_CIGAR_INSERT);
+        if (w == 0) { overflow = true; return; }
+        ops[--w] = cigarWord(length, op);
+    }
+    __device__ __forceinline__ void start(unsigned L, int endLane, unsigned endType, uint32_t *buffer, unsigned capacity)
+    {
+        ii = int(L) - 1; jj = endLane; type = endType; opLength = 0; ops = buffer; cap = capacity; w = capacity;
+        overflow = false; active = L != 0;
+        if (active && jj > 0) push(unsigned(jj), 1);                           // :388-391
+    }
+    /// all steps of this walk that happen in row 'row' (:392-423); f = the 16 flag bits of this half of the 5 row words
+    __device__ __forceinline__ void stepRow(int row, unsigned fE, unsigned fF, unsigned fAB, unsigned fGF, unsigned fHE)
+    {
+        while (active && ii == row)
+        {
+            ++opLength;
+            unsigned next;
+            if (type == 0)
+            {
+                // _mm_max_epi16 on byte pairs (:197): the odd lane decides which whole pair wins
+                const unsigned lo = unsigned(jj) & ~1u;
+                const unsigned loE = (fE >> lo) & 1u, hiE = (fE >> lo) & 2u, loF = (fF >> lo) & 1u, hiF = (fF >> lo) & 2u;
+                if (jj & 1) next = hiF ? 2u : (hiE >> 1);
+                else next = hiF ? loF * 2u : (hiE ? loE : max(loF * 2u, loE));
+            }
+            else if (type == 1) next = ((fHE >> jj) & 1u) ? 1u : (((fGF >> (jj + 1)) & 1u) ? 2u : 0u);
+            else next = jj == 0 ? 0u : (((fAB >> jj) & 1u) ? 2u : ((fE >> (jj - 1)) & 1u));
+            if (next != type) { push(opLength, type); opLength = 0; }
+            if (type == 0) { --ii; } else if (type == 1) { ++jj; } else { --ii; --jj; }
+            type = next;
+            active = ii >= 0 && jj >= 0 && jj <= 15;
+        }
+    }
+    /// :425-453: flush, strip a deletion at either end; \return the stripped leading deletion, ops[0..nOps) head first
+    __device__ __forceinline__ unsigned finish(unsigned &nOps)
+    {
+        if (type != 1 && opLength) { push(opLength, type); opLength = 0; }
+        if (jj < 15) { push(opLength + 15 - jj, 1); opLength = 0; }
+        unsigned ret = 0, e = cap;
+        if (w < e && (ops[w] & 0xFu) == ISAAC_EXT_CIGAR_DELETE) { ret = ops[w] >> 4; ++w; }
+        if (w < e && (ops[e - 1] & 0xFu) == ISAAC_EXT_CIGAR_DELETE) { --e; }
+        nOps = e - w;
+        for (unsigned k = 0; k < nOps; ++k) ops[k] = ops[w + k];
+        return ret;
+    }
+};
+
+/// Traceback of both halves of a pair in one pass over the rows (every row from L-1 down to 0 is visited exactly once
+/// by each walk, so the row order is known in advance): the five flag words of four rows ahead are kept in flight in
+/// registers, turning the walk's chain of dependent loads into a software pipeline.
+__device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb, const size_t tbStride,
+                                                 Sw2Walker &a, Sw2Walker &b)
+{
+    const int top = max(a.active ? a.ii : -1, b.active ? b.ii : -1);
+    if (top < 0) return;
+    auto load = [&](int r, uint32_t (&w)[SW2_FLAG_WORDS]) {
+        const uint32_t *p = tb + size_t(max(r, 0)) * SW2_FLAG_WORDS * tbStride;
+#pragma unroll
+        for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) w[k] = p[k * tbStride];
+    };
+    auto process = [&](int r, const uint32_t (&w)[SW2_FLAG_WORDS]) {
+        if (r < 0) return;
+        a.stepRow(r, w[0] & 0xFFFFu, w[1] & 0xFFFFu, w[2] & 0xFFFFu, w[3] & 0xFFFFu, w[4] & 0xFFFFu);
+        b.stepRow(r, w[0] >> 16, w[1] >> 16, w[2] >> 16, w[3] >> 16, w[4] >> 16);
+    };
+    uint32_t w0[SW2_FLAG_WORDS], w1[SW2_FLAG_WORDS], w2[SW2_FLAG_WORDS], w3[SW2_FLAG_WORDS];
+    load(top, w0); load(top - 1, w1); load(top - 2, w2); load(top - 3, w3);
+    for (int r = top; r >= 0 && (a.active || b.active); r -= 4)
+    {
+        process(r, w0); load(r - 4, w0);
+        process(r - 1, w1); load(r - 5, w1);
+        process(r - 2, w2); load(r - 6, w2);
+        process(r - 3, w3); load(r - 7, w3);
+    }
+}
+
 /// Forward pass over max(LA, LB) rows for the pair.  src.q(half, i) / src.d(half, k) return base codes (they must
 /// tolerate indices past the own length of a half: any code will do there).  On return jj/type hold the end cell of
 /// each half.

@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing of the candidate-extension path.
+
+The path shards with no data-path collective: clusters (read pairs) are independent once the reference and the template
+length statistics are fixed, so rank r of G takes tiles r, r+G, ... (the reference strides clusters over its threads
+the same way, MatchSelector.cpp:279-291) with the packed reference replicated per GPU.  The only exchange is the sum
+of the per-tile statistics counters (one all-reduce of 64 u64, NCCL on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+STATS_COUNTERS = 64   # ISAAC_EXT_STATS_COUNTERS
+STAT_NAMES = ("fragments", "aligned", "gapped", "perfect", "mismatches", "editDistance", "gaps", "bases")
+
+
+def tiles_of_rank(n_tiles, rank, world):
+    """tile indices processed by `rank`: r, r + G, r + 2G, ..."""
+    return list(range(rank, n_tiles, world))
+
+
+def cluster_range_of_rank(n_clusters, rank, world):
+    """contiguous cluster range of `rank` when one tile is split (balanced to within one cluster)"""
+    return n_clusters * rank // world, n_clusters * (rank + 1) // world
+
+
+def stats_from_fragments(fragments):
+    """numpy statement of the K6 counters (kernels_stats.cuh) for host-side checks"""
+    s = np.zeros(STATS_COUNTERS, dtype=np.uint64)
+    aligned = fragments["cigarLength"] != 0
+    a = fragments[aligned]
+    s[0] = fragments.size
+    s[1] = a.size
+    s[2] = int((a["gapCount"] != 0).sum())
+    s[3] = int((a["editDistance"] == 0).sum())
+    s[4] = int(a["mismatchCount"].astype(np.uint64).sum())
+    s[5] = int(a["editDistance"].astype(np.uint64).sum())
+    s[6] = int(a["gapCount"].astype(np.uint64).sum())
+    s[7] = int(a["observedLength"].astype(np.uint64).sum())
+    s[8:41] = np.bincount(np.minimum(a["mismatchCount"], 32), minlength=33).astype(np.uint64)
+    return s
+
+
+def allreduce_stats(stats):
+    """sums the counter vector over all ranks in place.  `stats` is a torch int64 tensor (cuda -> NCCL, cpu -> gloo)
+    holding the u64 counters bit for bit; returns it.  A single-process run returns it unchanged."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats

@@ -1,0 +1,81 @@
+"""The N > 1 path: tiles / cluster ranges shard over ranks with no data-path collective; the per-tile statistics are
+summed with one all-reduce.  The CPU tests run the host logic on a world of 2 gloo ranks (the CPU oracle stands in for
+the kernels as the checker); the GPU test checks the K6 counters kernel against its numpy statement."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rank_main(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    from common import small_workload
+    from isaac_aligner_b200 import distributed
+    from isaac_aligner_b200.types import Config
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    genome, sim, reads, cand = small_workload(n_pairs=600, L=100, seed=12)
+    cfg = Config.default(max_read_length=200)
+    g = oracle_lib.GenomeHolder(genome)
+    chk = oracle_lib.port()
+    # every rank extends only the candidates of its own cluster range
+    b, e = distributed.cluster_range_of_rank(reads.cluster_count, rank, world)
+    cluster_of = cand["readId"] // 2
+    mine = cand[(cluster_of >= b) & (cluster_of < e)]
+    frags, _, _ = chk.ungapped(g, reads, cfg, mine)
+    local = distributed.stats_from_fragments(frags)
+    t = torch.from_numpy(local.view(np.int64).copy())
+    distributed.allreduce_stats(t)
+    if rank == 0:
+        full, _, _ = chk.ungapped(g, reads, cfg, cand)
+        want = distributed.stats_from_fragments(full)
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([np.array_equal(t.numpy().view(np.uint64), want), int(want[0]), int(local[0])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_stats_allreduce(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 500
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok, total, local = np.load(os.path.join(str(tmp_path), "ok.npy"))
+    assert ok == 1 and 0 < local < total
+
+
+def test_shard_helpers_cover_everything_once():
+    from isaac_aligner_b200 import distributed
+    for world in (1, 2, 3, 8):
+        tiles = sorted(t for r in range(world) for t in distributed.tiles_of_rank(21, r, world))
+        assert tiles == list(range(21))
+        ranges = [distributed.cluster_range_of_rank(1001, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == 1001
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+
+
+@pytest.mark.gpu
+def test_tile_stats_kernel_matches_numpy():
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import small_workload
+    from isaac_aligner_b200 import capi, distributed
+    from isaac_aligner_b200.types import Config
+    genome, sim, reads, cand = small_workload(n_pairs=2000, L=100, seed=14, indel_rate=5e-3)
+    ctx = capi.Context(Config.default(max_read_length=200))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    cand = cand[ctx.ungapped(cand)[0]["cigarLength"] > 0]
+    frags, _, _ = ctx.gapped(cand)
+    d = torch.from_numpy(frags.view(np.uint8).reshape(-1, 64)).cuda()
+    stats = torch.zeros(distributed.STATS_COUNTERS, dtype=torch.int64, device="cuda")
+    ctx.tile_stats_device(len(frags), d.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(stats.cpu().numpy().view(np.uint64), distributed.stats_from_fragments(frags))
+    ctx.close()
