@@ -11,7 +11,7 @@ import numpy as np
 from .types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, MASK_WORDS, Config, ReadSet
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libisaac_ext.so")
+LIB_PATH = os.environ.get("ISAAC_EXT_LIB", os.path.join(_HERE, "libisaac_ext.so"))   # override: kernel-variant experiments
 
 if not os.path.exists(LIB_PATH):
     raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "

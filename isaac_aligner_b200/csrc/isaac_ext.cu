@@ -31,7 +31,7 @@ struct isaac_ext_ctx
     // Tuning knobs (environment, read once at isaac_ext_create): ISAAC_EXT_SW_IMPL = 2 (packed 16x2, two alignments per
     // thread, default) or 1 (scalar, one alignment per thread); ISAAC_EXT_SW_BLOCKS_PER_SM bounds the persistent grid.
     int swImpl = 2;
-    unsigned swBlocksPerSm = 4;
+    unsigned swBlocksPerSm = 8;
     unsigned hostThreads = 1;     // config.hostThreads (0 = hardware concurrency)
     uint32_t clusterCount = 0;    // of the resident read set
     PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows

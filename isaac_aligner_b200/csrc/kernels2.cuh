@@ -83,7 +83,10 @@ struct ResidentPairSrc
     }
 };
 
-__global__ void __launch_bounds__(128)
+#ifndef ISAAC_SW2_MIN_BLOCKS
+#define ISAAC_SW2_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, ISAAC_SW2_MIN_BLOCKS)
 gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
               const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
               isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
