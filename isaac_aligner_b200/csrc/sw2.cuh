@@ -166,6 +166,15 @@ struct Sw2Walker
     /// all steps of this walk that happen in row 'row' (:392-423); f = the 16 flag bits of this half of the 5 row words
     __device__ __forceinline__ void stepRow(int row, unsigned fE, unsigned fF, unsigned fAB, unsigned fGF, unsigned fHE)
     {
+        if (!active || ii != row) return;
+        // fast path, the overwhelmingly common step: on the diagonal, and neither lane of the byte pair (2p, 2p+1)
+        // has a direction flag set, so the direction of G is G again whatever the _mm_max_epi16 coupling does
+        if (type == 0 && (((fE | fF) >> (unsigned(jj) & ~1u)) & 3u) == 0)
+        {
+            ++opLength; --ii;
+            active = ii >= 0;
+            return;
+        }
         while (active && ii == row)
         {
             ++opLength;
