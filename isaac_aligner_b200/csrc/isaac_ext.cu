@@ -152,9 +152,9 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
         g_createError = why;
         return ISAAC_EXT_E_INVALID_ARG;     // reference: common::InvalidParameterException
     }
-    if (!config->maxReadLength || config->maxReadLength > ISAAC_EXT_MAX_CYCLES)
+    if (!config->maxReadLength)     // (reads longer than FragmentMetadata::maxCycles_ = 1024 are refused by isaac_ext_set_reads)
     {
-        g_createError = "maxReadLength must be in [1, 1024]";
+        g_createError = "maxReadLength must not be 0";
         return ISAAC_EXT_E_INVALID_ARG;
     }
     int count = 0;

@@ -1,0 +1,279 @@
+// isaac_b200.hh -- C++ classes carrying the reference's names on top of the C ABI (include/isaac_ext.h).
+//
+// These are the batch-of-one adapters that let code written against the reference's alignment classes (and the
+// reference's own unit tests) run against the GPU path unchanged in spirit: same class names, same argument meaning,
+// same error behaviour (the constructors throw isaac_b200::common::InvalidParameterException where the reference throws
+// common::InvalidParameterException, BandedSmithWaterman.cpp:49-53).  Production use does NOT go through them: a tile
+// is handed over in one isaac_ext_build_fragments / isaac_ext_rescue_shadows call.
+//
+//   reference class                                   here
+//   alignment::BandedSmithWaterman  (.hh:37-105)      isaac_b200::alignment::BandedSmithWaterman
+//   alignment::FragmentBuilder      (.hh:46-72)       isaac_b200::alignment::FragmentBuilder
+//   alignment::ShadowAligner        (.hh:45-89)       isaac_b200::alignment::ShadowAligner
+//   fragmentBuilder::UngappedAligner / GappedAligner  isaac_b200::alignment::fragmentBuilder::{UngappedAligner,GappedAligner}
+//   alignment::FragmentMetadata     (.hh:47-444)      isaac_b200::alignment::FragmentMetadata (the fields of isaac_ext_fragment_t)
+//   alignment::Cigar                (.hh:41-216)      isaac_b200::alignment::Cigar
+//
+// Header only; link with libisaac_ext.so.
+#ifndef ISAAC_B200_HH
+#define ISAAC_B200_HH
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/isaac_ext.h"
+
+namespace isaac_b200
+{
+namespace common
+{
+struct InvalidParameterException : public std::logic_error { explicit InvalidParameterException(const std::string &m) : std::logic_error(m) {} };
+struct DeviceException : public std::runtime_error { explicit DeviceException(const std::string &m) : std::runtime_error(m) {} };
+} // namespace common
+
+namespace reference
+{
+/// reference::Contig (include/reference/Contig.hh:31-39): 1 byte per base, upper-case ACGTN
+struct Contig
+{
+    unsigned index_; std::string name_; std::vector<char> forward_;
+    Contig(unsigned index, const std::string &name) : index_(index), name_(name) {}
+    size_t getLength() const { return forward_.size(); }
+};
+} // namespace reference
+
+/// RAII owner of one isaac_ext_ctx
+class Context
+{
+public:
+    explicit Context(const isaac_ext_config_t &config) : ctx_(0), config_(config)
+    {
+        const int rc = isaac_ext_create(&config, &ctx_);
+        if (rc == ISAAC_EXT_E_INVALID_ARG) throw common::InvalidParameterException(isaac_ext_last_error(0));
+        if (rc) throw common::DeviceException(isaac_ext_last_error(0));
+    }
+    ~Context() { isaac_ext_destroy(ctx_); }
+    isaac_ext_ctx *get() const { return ctx_; }
+    const isaac_ext_config_t &config() const { return config_; }
+    void check(int rc) const
+    {
+        if (rc == ISAAC_EXT_E_INVALID_ARG) throw common::InvalidParameterException(isaac_ext_last_error(ctx_));
+        if (rc) throw common::DeviceException(isaac_ext_last_error(ctx_));
+    }
+    void setReference(const std::vector<reference::Contig> &contigs)
+    {
+        std::vector<const char *> bases; std::vector<uint64_t> lengths;
+        for (size_t i = 0; i < contigs.size(); ++i) { bases.push_back(contigs[i].forward_.data()); lengths.push_back(contigs[i].forward_.size()); }
+        check(isaac_ext_set_reference(ctx_, uint32_t(contigs.size()), bases.data(), lengths.data()));
+    }
+private:
+    Context(const Context &); Context &operator=(const Context &);
+    isaac_ext_ctx *ctx_;
+    isaac_ext_config_t config_;
+};
+
+inline isaac_ext_config_t makeConfig(int gapMatchScore, int gapMismatchScore, int gapOpenScore, int gapExtendScore, int minGapExtendScore,
+                                     unsigned maxReadLength, unsigned repeatThreshold = 10, unsigned maxSeedsPerRead = 8,
+                                     unsigned gappedMismatchesMax = 5, unsigned semialignedGapLimit = 100, bool avoidSmithWaterman = false)
+{
+    isaac_ext_config_t c = {gapMatchScore, gapMismatchScore, gapOpenScore, gapExtendScore, minGapExtendScore, repeatThreshold,
+                            maxSeedsPerRead, gappedMismatchesMax, semialignedGapLimit, avoidSmithWaterman ? 1u : 0u, maxReadLength, 0, 0};
+    return c;
+}
+
+namespace alignment
+{
+
+/// alignment::Cigar (Cigar.hh:41-216): word = length << 4 | op
+class Cigar : public std::vector<uint32_t>
+{
+public:
+    enum OpCode { ALIGN = 0, INSERT = 1, DELETE = 2, SKIP = 3, SOFT_CLIP = 4, HARD_CLIP = 5, PAD = 6, MATCH = 7, MISMATCH = 8, UNKNOWN = 9 };
+    static uint32_t encode(unsigned length, OpCode op) { return (length << 4) | op; }
+    static std::pair<unsigned, OpCode> decode(uint32_t v) { return std::make_pair(v >> 4, OpCode(std::min<unsigned>(v & 0xF, UNKNOWN))); }
+    void addOperation(unsigned length, OpCode op) { push_back(encode(length, op)); }
+    static std::string toString(const uint32_t *begin, const uint32_t *end)
+    {
+        static const char ops[] = "MIDNSHP=X?";
+        std::string s;
+        for (; begin != end; ++begin) { s += std::to_string(*begin >> 4); s += ops[std::min<unsigned>(*begin & 0xF, 9)]; }
+        return s;
+    }
+    std::string toString() const { return toString(data(), data() + size()); }
+};
+
+/// the FragmentMetadata fields the template layer reads (FragmentMetadata.hh:330-414) + its CIGAR
+struct FragmentMetadata : public isaac_ext_fragment_t
+{
+    const std::vector<uint32_t> *cigarBuffer;
+    FragmentMetadata() : cigarBuffer(0) { isaac_ext_fragment_t z = isaac_ext_fragment_t(); static_cast<isaac_ext_fragment_t &>(*this) = z; }
+    FragmentMetadata(const isaac_ext_fragment_t &f, const std::vector<uint32_t> *buffer) : isaac_ext_fragment_t(f), cigarBuffer(buffer) {}
+    bool isAligned() const { return 0 != cigarLength; }
+    bool isReverse() const { return reverse; }
+    unsigned getObservedLength() const { return isAligned() ? observedLength : 0; }
+    unsigned getMismatchCount() const { return mismatchCount; }
+    unsigned getEditDistance() const { return editDistance; }
+    unsigned getGapCount() const { return gapCount; }
+    long getPosition() const { return position; }
+    unsigned getContigId() const { return contigId; }
+    std::string getCigarString() const
+    {
+        return cigarBuffer && cigarLength ? Cigar::toString(cigarBuffer->data() + cigarOffset, cigarBuffer->data() + cigarOffset + cigarLength) : std::string();
+    }
+    bool isWellAnchored() const         // FragmentMetadata.hh:477-483, WEAK_SEED_LENGTH = 32
+    {
+        return uniqueSeedCount || (nonUniqueSeedOffsetSecond > nonUniqueSeedOffsetFirst && unsigned(nonUniqueSeedOffsetSecond - nonUniqueSeedOffsetFirst) >= 32);
+    }
+};
+
+/// alignment::BandedSmithWaterman (BandedSmithWaterman.hh:37-105): same constructor arguments and overflow check, align()
+/// appends to the CIGAR and returns the stripped leading deletion.
+class BandedSmithWaterman
+{
+public:
+    static const unsigned WIDEST_GAP_SIZE = ISAAC_EXT_BAND_WIDTH, distanceCutoff = ISAAC_EXT_SW_DISTANCE_CUTOFF, mismatchesCutoff = ISAAC_EXT_SW_MISMATCH_CUTOFF;
+    BandedSmithWaterman(int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore, int maxReadLength)
+        : match_(matchScore), mismatch_(mismatchScore), open_(gapOpenScore), extend_(gapExtendScore),
+          context_(makeConfig(matchScore, mismatchScore, -gapOpenScore, -gapExtendScore, -gapExtendScore, unsigned(maxReadLength))) {}
+    unsigned align(const std::vector<char> &query, std::vector<char>::const_iterator databaseBegin, std::vector<char>::const_iterator databaseEnd,
+                   Cigar &cigar) const
+    {
+        const uint64_t zero = 0; const uint32_t length = uint32_t(query.size());
+        if (size_t(databaseEnd - databaseBegin) != query.size() + WIDEST_GAP_SIZE - 1)
+            throw common::InvalidParameterException("database must be query + 15 bases (BandedSmithWaterman.cpp:93)");
+        uint32_t words[64], count = 0, offset = 0;
+        context_.check(isaac_ext_banded_sw_batch(context_.get(), 1, query.data(), &zero, &length, &*databaseBegin, &zero,
+                                                 match_, mismatch_, open_, extend_, 64, words, &count, &offset));
+        cigar.insert(cigar.end(), words, words + count);
+        return offset;
+    }
+private:
+    int match_, mismatch_, open_, extend_;
+    Context context_;
+};
+
+/// One cluster's reads in BCL form plus the read geometry (alignment::Cluster / flowcell::ReadMetadataList)
+struct Cluster
+{
+    std::vector<uint8_t> bcl;            // read 0 then read 1, quality << 2 | base, 0..3 = N (BclClusters.hh:33-124)
+    unsigned readLength[2]; unsigned firstCycle[2]; unsigned readCount;
+    uint16_t endCyclesMasked[2];
+    Cluster() : readCount(0) { readLength[0] = readLength[1] = 0; firstCycle[0] = 1; firstCycle[1] = 1; endCyclesMasked[0] = endCyclesMasked[1] = 0; }
+    isaac_ext_reads_t view() const
+    {
+        isaac_ext_reads_t r = {1, readCount, {readLength[0], readLength[1]}, {firstCycle[0], firstCycle[1]}, bcl.data(), endCyclesMasked};
+        return r;
+    }
+};
+
+typedef isaac_ext_match_t Match;             // alignment::Match (Match.hh:38-73), bit-compatible
+typedef isaac_ext_seed_t SeedMetadata;       // alignment::SeedMetadata (SeedMetadata.hh:46-98)
+typedef std::vector<SeedMetadata> SeedMetadataList;
+typedef isaac_ext_tls_t TemplateLengthStatistics;
+
+/// alignment::FragmentBuilder (FragmentBuilder.hh:46-72): build() for one cluster, results through getFragments() /
+/// getCigarBuffer() exactly like the reference (valid until the next build()).
+class FragmentBuilder
+{
+public:
+    FragmentBuilder(Context &context) : context_(context), fragments_(2) {}
+    bool build(const SeedMetadataList &seedMetadataList, std::vector<Match>::const_iterator matchBegin,
+               std::vector<Match>::const_iterator matchEnd, const Cluster &cluster, bool withGaps)
+    {
+        const isaac_ext_reads_t reads = cluster.view();
+        context_.check(isaac_ext_set_reads(context_.get(), &reads));
+        const uint64_t begin[2] = {0, uint64_t(matchEnd - matchBegin)};
+        const isaac_ext_build_batch_t batch = {begin[1] ? &*matchBegin : 0, begin, seedMetadataList.data(), uint32_t(seedMetadataList.size()), withGaps ? 1u : 0u};
+        isaac_ext_build_result_t r;
+        context_.check(isaac_ext_build_fragments(context_.get(), &batch, &r));
+        cigarBuffer_.assign(r.cigars, r.cigars + r.cigarWords);
+        for (unsigned read = 0; read < 2; ++read)
+        {
+            fragments_[read].clear();
+            if (read < cluster.readCount)
+                for (uint64_t i = r.readFragmentBegin[read]; i < r.readFragmentBegin[read + 1]; ++i)
+                    fragments_[read].push_back(FragmentMetadata(r.fragments[i], &cigarBuffer_));
+        }
+        return r.built[0] != 0;
+    }
+    const std::vector<std::vector<FragmentMetadata> > &getFragments() const { return fragments_; }
+    const std::vector<uint32_t> &getCigarBuffer() const { return cigarBuffer_; }
+private:
+    Context &context_;
+    std::vector<std::vector<FragmentMetadata> > fragments_;
+    std::vector<uint32_t> cigarBuffer_;
+};
+
+/// alignment::ShadowAligner (ShadowAligner.hh:45-89): rescueShadow() for one orphan of the cluster last given to
+/// FragmentBuilder::build (or to setCluster).
+class ShadowAligner
+{
+public:
+    ShadowAligner(Context &context) : context_(context) {}
+    void setCluster(const Cluster &cluster) { const isaac_ext_reads_t reads = cluster.view(); context_.check(isaac_ext_set_reads(context_.get(), &reads)); }
+    bool rescueShadow(const FragmentMetadata &orphan, std::vector<FragmentMetadata> &shadowList,
+                      const TemplateLengthStatistics &templateLengthStatistics, long bestTemplateLength)
+    {
+        const isaac_ext_rescue_request_t q = {orphan.position, bestTemplateLength, orphan.readIndex, (orphan.contigId << 1) | (orphan.reverse ? 1u : 0u),
+                                              orphan.observedLength, 0};
+        isaac_ext_rescue_result_t r;
+        context_.check(isaac_ext_rescue_shadows(context_.get(), &templateLengthStatistics, 1, &q, &r));
+        shadowCigarBuffer_.assign(r.cigars, r.cigars + r.cigarWords);
+        shadowList.clear();
+        for (uint64_t i = 0; i < r.fragmentCount; ++i) shadowList.push_back(FragmentMetadata(r.fragments[i], &shadowCigarBuffer_));
+        return r.rescued[0] != 0;
+    }
+    const std::vector<uint32_t> &getCigarBuffer() const { return shadowCigarBuffer_; }
+private:
+    Context &context_;
+    std::vector<uint32_t> shadowCigarBuffer_;
+};
+
+namespace fragmentBuilder
+{
+/// fragmentBuilder::UngappedAligner / GappedAligner (UngappedAligner.hh:55-60, GappedAligner.hh:49-54): re-align one
+/// fragment of the cluster resident in the context; the fragment is updated in place, the CIGAR appended to cigarBuffer,
+/// the match count returned.
+class UngappedAligner
+{
+public:
+    UngappedAligner(Context &context) : context_(context) {}
+    unsigned alignUngapped(FragmentMetadata &fragment, Cigar &cigarBuffer) const { return align(fragment, cigarBuffer, false); }
+protected:
+    unsigned align(FragmentMetadata &fragment, Cigar &cigarBuffer, bool gapped) const
+    {
+        long unclipped = fragment.position;                                   // resetAlignment() (FragmentMetadata.hh:297-313)
+        if (fragment.cigarBuffer && fragment.cigarLength && ((*fragment.cigarBuffer)[fragment.cigarOffset] & 0xF) == Cigar::SOFT_CLIP)
+            unclipped -= (*fragment.cigarBuffer)[fragment.cigarOffset] >> 4;
+        const isaac_ext_candidate_t c = {unclipped, fragment.readId, (fragment.contigId << 1) | (fragment.reverse ? 1u : 0u)};
+        isaac_ext_fragment_t out; uint32_t words[64];
+        context_.check(gapped ? isaac_ext_gapped_batch(context_.get(), 1, &c, 64, &out, words, 0)
+                              : isaac_ext_ungapped_batch(context_.get(), 1, &c, &out, words, 0));
+        const unsigned matchCount = out.matchCount;
+        if (gapped && !out.cigarLength) return 0;                             // alignGapped returned 0: fragment untouched
+        out.uniqueSeedCount = fragment.uniqueSeedCount; out.repeatSeedsCount = fragment.repeatSeedsCount;
+        out.nonUniqueSeedOffsetFirst = fragment.nonUniqueSeedOffsetFirst; out.nonUniqueSeedOffsetSecond = fragment.nonUniqueSeedOffsetSecond;
+        out.firstSeedIndex = fragment.firstSeedIndex;
+        out.cigarOffset = uint32_t(cigarBuffer.size());
+        cigarBuffer.insert(cigarBuffer.end(), words, words + out.cigarLength);
+        static_cast<isaac_ext_fragment_t &>(fragment) = out;
+        fragment.cigarBuffer = &cigarBuffer;
+        return matchCount;
+    }
+    Context &context_;
+};
+
+class GappedAligner : public UngappedAligner
+{
+public:
+    GappedAligner(Context &context) : UngappedAligner(context) {}
+    unsigned alignGapped(FragmentMetadata &fragment, Cigar &cigarBuffer) const { return align(fragment, cigarBuffer, true); }
+};
+} // namespace fragmentBuilder
+
+} // namespace alignment
+} // namespace isaac_b200
+
+#endif // ISAAC_B200_HH

@@ -1,0 +1,134 @@
+// The reference's own unit tests, restated against the classes of isaac_aligner_b200/host/isaac_b200.hh (GPU behind them).
+// Mirrors lib/alignment/cppunit/testBandedSmithWaterman.cpp (testUngapped :79-103, testSingleDeletion :105-131,
+// testSingleInsertion :133-154, testMultipleIndels :156-212, testOverflow :214-225) and the two-seed deletion case of
+// testSimpleIndelAligner.cpp:264-277 through FragmentBuilder::build.  Exits 0 when every check passes.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../isaac_aligner_b200/host/isaac_b200.hh"
+
+using namespace isaac_b200;
+using isaac_b200::alignment::Cigar;
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
+#define CHECK_EQ(a, b) do { if (!((a) == (b))) { std::printf("FAILED %s:%d: %s == %s\n", __FILE__, __LINE__, #a, #b); ++failures; } } while (0)
+
+static std::vector<char> v(const std::string &s) { return std::vector<char>(s.begin(), s.end()); }
+
+static std::string getGenome(unsigned size = 1000)
+{
+    static const std::string bases = "ACGT";
+    std::string genome;
+    unsigned state = 12345;
+    while (size--) { state = state * 1103515245u + 12345u; genome.push_back(bases[(state >> 16) % 4]); }
+    return genome;
+}
+
+static std::string align(const alignment::BandedSmithWaterman &bsw, const std::string &query, const std::string &database, unsigned *ret = 0)
+{
+    Cigar cigar;
+    const std::vector<char> q = v(query), d = v(database);
+    const unsigned r = bsw.align(q, d.begin(), d.end(), cigar);
+    if (ret) *ret = r;
+    return cigar.toString();
+}
+
+static void testBandedSmithWaterman()
+{
+    const alignment::BandedSmithWaterman bsw(2, -1, 15, 3, 300);
+    const std::string genome = getGenome();
+    {   // testUngapped
+        const std::string database = genome.substr(100, 115);
+        for (unsigned i = 0; i <= 15; ++i) CHECK_EQ(align(bsw, database.substr(i, 100), database), "100M");
+    }
+    {   // testSingleDeletion
+        const unsigned left = 40, right = 40;
+        const std::string deletion = "AGAGCAGCGAGCGACAGCAGCAGCAAA";
+        for (unsigned deletionLength = 1; 13 >= deletionLength; ++deletionLength)
+        {
+            const unsigned dl = 7 - (deletionLength / 2);
+            const std::string leftS = genome.substr(100 + dl, left - 1) + "T", rightS = genome.substr(100 + dl + left, right);
+            const std::string databaseD = genome.substr(100, dl) + leftS + deletion.substr(0, deletionLength) + rightS +
+                                          genome.substr(100 + dl + left + right, 15 - dl - deletionLength);
+            CHECK_EQ(align(bsw, leftS + rightS, databaseD), "40M" + std::to_string(deletionLength) + "D40M");
+        }
+    }
+    {   // testSingleInsertion
+        const std::string database = genome.substr(100, 220);
+        const unsigned queryLength = unsigned(database.size()) - 15;
+        for (unsigned insertLength = 1; 9 >= insertLength; ++insertLength)
+        {
+            const unsigned left = 100, right = queryLength - left - insertLength, dl = 9;
+            const std::string query = database.substr(dl, left) + std::string(insertLength, 'T') + database.substr(left + dl, right);
+            CHECK_EQ(align(bsw, query, database), "100M" + std::to_string(insertLength) + "I" + std::to_string(right) + "M");
+        }
+    }
+    {   // testMultipleIndels
+        const unsigned dl = 6;
+        const std::string dlS = genome.substr(100, dl), leftS = genome.substr(100 + dl, 19) + "T", centerS = genome.substr(100 + dl + 20, 19) + "T";
+        const std::string rightS = genome.substr(100 + dl + 40, 20);
+        auto tail = [&](unsigned n) { return genome.substr(100 + dl + 60, n); };
+        CHECK_EQ(align(bsw, leftS + "A" + centerS + rightS, dlS + leftS + centerS + "ACAG" + rightS + tail(15 - dl + 1 - 4)), "20M1I20M4D20M");
+        CHECK_EQ(align(bsw, leftS + "A" + centerS + "CG" + rightS, dlS + leftS + centerS + rightS + tail(15 - dl + 1 + 2)), "20M1I20M2I20M");
+        CHECK_EQ(align(bsw, leftS + centerS + rightS, dlS + leftS + "AAG" + centerS + "ACAG" + rightS + tail(15 - dl - 3 - 4)), "20M3D20M4D20M");
+    }
+}
+
+template <class F> static bool throwsInvalidParameter(F f)
+{
+    try { f(); } catch (const common::InvalidParameterException &) { return true; }
+    return false;
+}
+
+static void testOverflow()
+{
+    CHECK(!throwsInvalidParameter([] { alignment::BandedSmithWaterman(2, -1, 6, 3, 5460); }));
+    CHECK(throwsInvalidParameter([] { alignment::BandedSmithWaterman(2, -1, 7, 3, 4681); }));
+    CHECK(throwsInvalidParameter([] { alignment::BandedSmithWaterman(2, -1, 17, 3, 3681); }));
+    CHECK(throwsInvalidParameter([] { alignment::BandedSmithWaterman(2, -1, 11, 3, 13681); }));
+}
+
+static void testSimpleDeletionThroughFragmentBuilder()
+{
+    // testSimpleIndelAligner.cpp:264-277: a 14-base deletion between two 32-mer seeds -> 71M14D68M, 0 mismatches, edit distance 14
+    const std::string read = "ATTTGGTTAAGGTAGCGGTAAAAGCGTGTTACCGCAATGTTCTGTCTCTTATACAACATCTAGATGTGTAT"
+                             "AAGAGACAGGTGCACCGCCTATACACATCTAGAATAAGAGACAGGTGCACCGCCTATACACATCTAGA";
+    const std::string ref = "ATTTGGTTAAGGTAGCGGTAAAAGCGTGTTACCGCAATGTTCTGTCTCTTATACAACATCTAGATGTGTATAAAAAAAAAAAAAAAAGAGACAGGTGCACCGCCTATACACATCTAGAATAAGAGACAGGTGCACCGCCTATACACATCTAGA";
+    isaac_ext_config_t cfg = makeConfig(0, -1, -2, -1, -5, unsigned(read.size()), 10, 8, 5, 20000);
+    Context context(cfg);
+    std::vector<reference::Contig> contigs(1, reference::Contig(0, "vasja"));
+    contigs[0].forward_ = v(ref);
+    context.setReference(contigs);
+    alignment::Cluster cluster;
+    cluster.readCount = 1; cluster.readLength[0] = unsigned(read.size());
+    for (char c : read) cluster.bcl.push_back(uint8_t((35 << 2) | std::string("ACGT").find(c)));
+    const unsigned L = unsigned(read.size());
+    alignment::SeedMetadataList seeds(2);
+    seeds[0].offset = 0; seeds[0].length = 32; seeds[0].readIndex = 0;
+    seeds[1].offset = uint16_t(L - 32 - 1); seeds[1].length = 32; seeds[1].readIndex = 0;
+    const uint64_t headLocation = 0, tailLocation = (ref.size() - L) + seeds[1].offset;
+    std::vector<alignment::Match> matches(2);
+    matches[0].seedId = 0u << 1; matches[0].location = (((uint64_t(1) << 40) | headLocation) << 1);
+    matches[1].seedId = 1u << 1; matches[1].location = (((uint64_t(1) << 40) | tailLocation) << 1);
+    alignment::FragmentBuilder builder(context);
+    CHECK(builder.build(seeds, matches.begin(), matches.end(), cluster, false));
+    const std::vector<alignment::FragmentMetadata> &list = builder.getFragments()[0];
+    CHECK(!list.empty());
+    if (!list.empty())
+    {
+        CHECK_EQ(list[0].getCigarString(), "71M14D68M");
+        CHECK_EQ(list[0].getMismatchCount(), 0u);
+        CHECK_EQ(list[0].getEditDistance(), 14u);
+    }
+}
+
+int main()
+{
+    testOverflow();
+    testBandedSmithWaterman();
+    testSimpleDeletionThroughFragmentBuilder();
+    std::printf(failures ? "%d checks FAILED\n" : "all checks passed\n", failures);
+    return failures ? 1 : 0;
+}
