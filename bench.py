@@ -44,6 +44,11 @@ def parse_args():
     p.add_argument("--cigar-stride", type=int, default=32)
     p.add_argument("--cpu-sample-per-core", type=int, default=40_000)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--workload", default="micro", choices=["micro", "pairs"],
+                   help="micro: BASELINE configs[1] (default, the bench line); pairs: build + rescue pipeline, read pairs/s")
+    p.add_argument("--pairs", type=int, default=None,
+                   help="read pairs per GPU of the pairs pipeline (default 200k as a side measurement of the micro run, 1M for --workload pairs; 0 disables)")
+    p.add_argument("--indel-rate", type=float, default=5e-4, help="indel events per base of the simulated pairs (config 4: 1e-2)")
     return p.parse_args()
 
 
@@ -150,6 +155,73 @@ def workload_config(args):
             "candidates_per_gpu": args.candidates, "read_length": args.read_length, "band": BAND,
             "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2, no flush needed"
                   % (args.candidates * (16 + 2 * 64 + (3 + args.cigar_stride) * 4) / 1e9)}
+
+
+def make_pairs_workload(args, rank, n_pairs):
+    """BASELINE configs[0]/[2]-style input: simulated FR pairs, seed matches from the error-free auto seeds + decoys,
+    explicit template length statistics."""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch, Tls
+    from isaac_aligner_b200.types import ReadSet
+    L = args.read_length
+    genome = synth.make_genome(args.genome_bases, n_contigs=1, seed=synth.SEED_G5)
+    sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 7 + 1000 * rank, indel_rate=args.indel_rate,
+                               seed_offsets=synth.auto_seed_offsets(L))
+    matches, begin = synth.make_matches(sim, genome, seed=synth.SEED_READS + 8 + 1000 * rank, decoy_rate=0.2)
+    return genome, ReadSet(sim.bcl, (L, L)), MatchBatch(matches, begin, synth.seed_table(sim), with_gaps=True), Tls.make()
+
+
+def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup):
+    """FragmentBuilder::build for every cluster, then ShadowAligner::rescueShadow for every request of the stand-in
+    template policy, both through the host-pointer ABI (H2D / D2H inside).  Returns a dict with pairs/s."""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import copy_result
+    n = reads.cluster_count
+    flat = ctx.build_fragments(mb)                                       # also the first warm-up pass
+    req = synth.rescue_policy(flat.fragments, flat.begin, n)
+    resc = ctx.rescue_shadows(tls, req)
+    for _ in range(max(0, warmup - 1)):
+        ctx.build_fragments(mb, copy=False); ctx.rescue_shadows(tls, req, copy=False)
+    tb = tr = 0.0
+    l0 = ctx.launches
+    for _ in range(steps):
+        t0 = time.perf_counter(); ctx.build_fragments(mb, copy=False)
+        t1 = time.perf_counter(); ctx.rescue_shadows(tls, req, copy=False)
+        t2 = time.perf_counter()
+        tb += t1 - t0; tr += t2 - t1
+    tb /= steps; tr /= steps
+    gaps = flat.fragments["gapCount"] > 0
+    return {"pairs": n, "pairs_per_s": n / (tb + tr), "build_ms": tb * 1e3, "rescue_ms": tr * 1e3,
+            "matches": int(len(mb.matches)), "fragments": int(flat.fragments.size), "fragments_with_gaps": int(gaps.sum()),
+            "rescue_requests": int(len(req)), "rescued": int(resc.flags.sum()), "shadow_candidates": int(resc.fragments.size),
+            "gpu_launches_per_step": (ctx.launches - l0) // max(1, steps),
+            "policy": "stand-in for TemplateBuilder (out of scope): mates of all candidates are rescued unless both reads have an "
+                      "edit-distance-0 candidate (TemplateBuilder.cpp:1073-1081, 737-757)"}, flat, req
+
+
+def pairs_pipeline_cpu(genome, reads, mb, tls, config, sample_clusters):
+    """the same two calls through the reference's own code (or the scalar restatement) on all host threads, on the first
+    `sample_clusters` clusters"""
+    import oracle_lib
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch
+    from isaac_aligner_b200.types import ReadSet
+    chk = oracle_lib.Oracle(oracle_lib.REF_SO) if os.path.exists(oracle_lib.REF_SO) else oracle_lib.port()
+    cores = os.cpu_count() or 1
+    k = min(sample_clusters, reads.cluster_count)
+    sub_reads = ReadSet(reads.bcl[:k], reads.read_lengths)
+    sub_mb = MatchBatch(mb.matches[:int(mb.begin[k])], mb.begin[:k + 1], mb.seeds, with_gaps=True)
+    g = oracle_lib.GenomeHolder(genome)
+    t0 = time.perf_counter()
+    flat = oracle_lib.build_fragments(chk, g, sub_reads, config, sub_mb, threads=cores)
+    t1 = time.perf_counter()
+    req = synth.rescue_policy(flat.fragments, flat.begin, k)
+    t2 = time.perf_counter()
+    oracle_lib.rescue_shadows(chk, g, sub_reads, config, tls, req, threads=cores, fragments_per_request=96)
+    t3 = time.perf_counter()
+    sec = (t1 - t0) + (t3 - t2)
+    return {"pairs": k, "pairs_per_s": k / sec, "build_ms": (t1 - t0) * 1e3, "rescue_ms": (t3 - t2) * 1e3, "cores": cores,
+            "kind": chk.kind}
 
 
 def run_b200(args):
@@ -290,6 +362,14 @@ def run_b200(args):
     cores = os.cpu_count() or 1
     ns = min(n, args.cpu_sample_per_core * cores)
     cpu_gcups, cpu_sec, kind, cores = cpu_arm(args, genome, reads, cand[:ns], config, 1, 0)
+    # ---- side measurement: the two TemplateBuilder-facing calls on simulated pairs (BASELINE "aligned read pairs/sec")
+    pairs_line = None
+    n_pairs = 200_000 if args.pairs is None else args.pairs
+    if n_pairs:
+        pgenome, preads, pmb, ptls = make_pairs_workload(args, rank, n_pairs)
+        ctx.set_reads(preads)
+        pairs_line, _, _ = pairs_pipeline_gpu(ctx, preads, pmb, ptls, max(1, args.steps // 2), 1)
+        pairs_line["cpu_baseline"] = pairs_pipeline_cpu(pgenome, preads, pmb, ptls, config, 4000 * cores)
 
     print(json.dumps({
         "metric": "banded_sw_gcups", "value": world * cells / (ms_per_step * 1e-3) / 1e9, "unit": "GCUPS",
@@ -298,6 +378,7 @@ def run_b200(args):
         "config": workload_config(args),
         "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         "tile_stats": dict(zip(distributed.STAT_NAMES, (int(x) for x in d_stats.cpu().numpy().view(np.uint64)[:8]))),
+        "pairs_pipeline": pairs_line,
         "roofline": {"bound": "int32", "kernel": "gappedKernel", "achieved": achieved / 1e12, "peak": peak_add / 1e12,
                      "unit": "TOP/s", "frac": achieved / peak_add, "traffic": traffic,
                      "ops_per_cell": OPS_PER_CELL, "gcups_kernel": sw_gcups_kernel, "ms_per_launch": ms_gapped,
@@ -316,9 +397,82 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def pairs_config(args, n_pairs):
+    return {"workload": "BASELINE configs[0]/[2] style: %d simulated 2x%d bp FR pairs per GPU per step on a %d bp random genome, "
+                        "indel events %.0e/base, seed matches from error-free auto seeds + 20%% decoys, explicit TLS 245/350/455, "
+                        "FragmentBuilder::build of every cluster then ShadowAligner::rescueShadow per the stand-in template policy"
+                        % (n_pairs, args.read_length, args.genome_bases, args.indel_rate),
+            "pairs_per_gpu": n_pairs, "read_length": args.read_length,
+            "l2": "per-step inputs+outputs exceed the 126 MB L2 for >= 500k pairs"}
+
+
+def run_pairs(args):
+    """--workload pairs: read pairs/s of the two TemplateBuilder-facing calls (host-pointer ABI = end to end)."""
+    import torch
+    from isaac_aligner_b200 import capi
+    from isaac_aligner_b200.types import Config
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_pairs = 1_000_000 if args.pairs is None else args.pairs
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        genome, reads, mb, tls = make_pairs_workload(args, 0, min(n_pairs, 6000 * cores))
+        config = Config.default(max_read_length=2 * args.read_length)
+        runs = [pairs_pipeline_cpu(genome, reads, mb, tls, config, reads.cluster_count) for _ in range(args.warmup + args.steps)][args.warmup:]
+        v = float(np.mean([r["pairs_per_s"] for r in runs]))
+        sample = "%d pairs per step of the same generator, %d host threads" % (reads.cluster_count, cores)
+        print(json.dumps({"impl": "reference", "metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": reads.cluster_count / v * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16+f64", "data": "synthetic",
+                          "config": pairs_config(args, n_pairs),
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": runs[0]["kind"], "sample": sample},
+                          "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    genome, reads, mb, tls = make_pairs_workload(args, rank, n_pairs)
+    config = Config.default(max_read_length=2 * args.read_length, device=local_rank)
+    ctx = capi.Context(config)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    line, flat, req = pairs_pipeline_gpu(ctx, reads, mb, tls, args.steps, args.warmup)
+    t = torch.tensor([line["build_ms"] + line["rescue_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cpu = pairs_pipeline_cpu(genome, reads, mb, tls, config, 4000 * cores)
+    h2d = len(mb.matches) * 16 + reads.bcl.size * 0 + len(req) * 32
+    d2h = flat.fragments.size * 64 + flat.cigars.size * 4
+    v = world * n_pairs / (ms * 1e-3)
+    print(json.dumps({"metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "int16+f64", "data": "synthetic", "config": pairs_config(args, n_pairs),
+                      "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                      "gpu_launches": int(line["gpu_launches_per_step"] * args.steps), "pipeline": line,
+                      "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                       "sample": "first %d pairs of rank 0, one pass, %d host threads" % (cpu["pairs"], cpu["cores"])}}))
+    ctx.close()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.workload == "pairs":
+        run_pairs(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)

@@ -6,6 +6,20 @@
 namespace isaac_b200
 {
 
+/// grow-only host array that is never zero-filled (std::vector::resize would touch hundreds of MB per call)
+template <class T> struct HostBuffer
+{
+    T *p = nullptr; size_t capacity = 0;
+    void reserve(size_t n)
+    {
+        if (n <= capacity) return;
+        std::free(p);
+        capacity = n + n / 4 + 1024;
+        p = static_cast<T *>(std::malloc(capacity * sizeof(T)));
+    }
+    ~HostBuffer() { std::free(p); }
+};
+
 /// Buffers of the two pipelines, owned by the context and reused across calls.
 struct PipelineState
 {
@@ -29,9 +43,10 @@ struct PipelineState
     // flattened results handed back to the caller
     std::vector<WorkFragment> work;
     std::vector<uint32_t> indelCigars;
-    std::vector<isaac_ext_fragment_t> outFragments;
-    std::vector<uint64_t> outBegin;
-    std::vector<uint32_t> outCigars;
+    HostBuffer<isaac_ext_fragment_t> outFragments;
+    HostBuffer<uint64_t> outBegin;
+    HostBuffer<uint32_t> outCigars;
+    uint64_t outFragmentCount = 0, outCigarWords = 0;
     std::vector<uint8_t> outFlags;
 
     void release()

@@ -14,6 +14,8 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <thread>
@@ -41,6 +43,20 @@ template <class T> struct PinnedBuffer
         return e;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; capacity = 0; }
+};
+
+/// Phase timing to stderr when the environment variable ISAAC_EXT_TRACE is set (development aid).
+struct PhaseTimer
+{
+    bool on; const char *what; std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(const char *w) : on(std::getenv("ISAAC_EXT_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *phase)
+    {
+        if (!on) return;
+        const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[isaac_ext] %s %-28s %8.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
 };
 
 /// runs f(threadIndex, begin, end) over a fixed partition of [0, n) (the same partition on every call with the same n)

@@ -39,38 +39,47 @@ isaac_ext_candidate_t candidateOf(const isaac_ext_fragment_t &f, long position)
     return c;
 }
 
-/// copies the surviving fragments of every group, in order, into the flat result arrays
+/// copies the surviving fragments of every group, in order, into the flat result arrays (two parallel passes:
+/// count per partition, then fill; the output buffers are grow-only and never zero-filled)
 template <class ListOf>
 void flatten(isaac_ext_ctx *ctx, const HostPools &pools, size_t groups, ListOf listOf)
 {
     PipelineState &ps = ctx->pipeline;
-    ps.outBegin.assign(groups + 1, 0);
-    for (size_t g = 0; g < groups; ++g) ps.outBegin[g + 1] = ps.outBegin[g] + listOf(g).second;
-    ps.outFragments.resize(ps.outBegin[groups]);
-    std::vector<uint64_t> cigarBegin(groups + 1, 0);
-    for (size_t g = 0; g < groups; ++g)
-    {
-        uint64_t words = 0;
-        const std::pair<const WorkFragment *, unsigned> l = listOf(g);
-        for (unsigned k = 0; k < l.second; ++k) words += l.first[k].f.cigarLength;
-        cigarBegin[g + 1] = cigarBegin[g] + words;
-    }
-    ps.outCigars.resize(cigarBegin[groups]);
-    parallelRanges(ctx->hostThreads, groups, [&](unsigned, size_t b, size_t e) {
+    const unsigned T = ctx->hostThreads;
+    const unsigned parts = partitionCount(T, groups);
+    std::vector<uint64_t> partFragments(parts + 1, 0), partWords(parts + 1, 0);
+    ps.outBegin.reserve(groups + 1);
+    parallelRanges(T, groups, [&](unsigned t, size_t b, size_t e) {
+        uint64_t nf = 0, nw = 0;
         for (size_t g = b; g < e; ++g)
         {
             const std::pair<const WorkFragment *, unsigned> l = listOf(g);
-            uint64_t at = cigarBegin[g];
+            nf += l.second;
+            for (unsigned k = 0; k < l.second; ++k) nw += l.first[k].f.cigarLength;
+        }
+        partFragments[t + 1] = nf; partWords[t + 1] = nw;
+    });
+    for (unsigned p = 0; p < parts; ++p) { partFragments[p + 1] += partFragments[p]; partWords[p + 1] += partWords[p]; }
+    ps.outFragments.reserve(partFragments[parts]);
+    ps.outCigars.reserve(partWords[parts]);
+    ps.outFragmentCount = partFragments[parts]; ps.outCigarWords = partWords[parts];
+    parallelRanges(T, groups, [&](unsigned t, size_t b, size_t e) {
+        uint64_t nf = partFragments[t], at = partWords[t];
+        for (size_t g = b; g < e; ++g)
+        {
+            const std::pair<const WorkFragment *, unsigned> l = listOf(g);
+            ps.outBegin.p[g] = nf;
             for (unsigned k = 0; k < l.second; ++k)
             {
                 isaac_ext_fragment_t f = l.first[k].f;
-                std::copy(pools.cigar(l.first[k]), pools.cigar(l.first[k]) + f.cigarLength, ps.outCigars.begin() + at);
+                std::copy(pools.cigar(l.first[k]), pools.cigar(l.first[k]) + f.cigarLength, ps.outCigars.p + at);
                 f.cigarOffset = uint32_t(at);
                 at += f.cigarLength;
-                ps.outFragments[ps.outBegin[g] + k] = f;
+                ps.outFragments.p[nf++] = f;
             }
         }
     });
+    ps.outBegin.p[groups] = partFragments[parts];
 }
 
 } // namespace
@@ -100,6 +109,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
     std::atomic<int> bad(0);
     HostPools pools;
 
+    PhaseTimer timer("build");
     // ---- P1: FragmentBuilder::build up to alignFragments (FragmentBuilder.cpp:92-134) + consolidate (:159)
     parallelRanges(T, nClusters, [&](unsigned t, size_t b, size_t e) {
         std::vector<unsigned> seedMatchCounts(batch->seedCount);
@@ -166,6 +176,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         }
         partCount[t + 1] = total;
     });
+    timer.mark("P1 candidates");
     if (bad) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "malformed match batch (offsets, seed index or contig out of range)");
     for (unsigned p = 0; p < parts; ++p) partCount[p + 1] += partCount[p];
     const uint64_t n1 = partCount[parts];
@@ -181,9 +192,11 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
                 ps.hCand1.p[at++] = candidateOf(w.f, w.f.position);
             }
     });
+    timer.mark("P1 dense write");
     // ---- K1: UngappedAligner::alignUngapped of every candidate (:174)
     int rcode = runUngapped(ctx, uint32_t(n1), ps.hCand1.p, ps.hFrag1.p, ps.hCig1.p);
     if (rcode) return rcode;
+    timer.mark("K1 ungapped + copies");
     pools.pools[0] = ps.hCig1.p;
 
     // ---- P2: consolidate (:179), SimpleIndelAligner::alignSimpleIndels pairing (SimpleIndelAligner.cpp:460-518)
@@ -243,6 +256,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
             }
         }
     });
+    timer.mark("P2 consolidate + pairing");
     std::vector<uint64_t> taskBegin(parts + 1, 0);
     for (unsigned p = 0; p < parts; ++p) taskBegin[p + 1] = taskBegin[p] + partTasks[p].size();
     const uint64_t nTasks = taskBegin[parts];
@@ -262,6 +276,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         pools.pools[1] = ps.indelCigars.data();
     }
 
+    timer.mark("simple indel kernel + copies");
     // ---- P3: apply the patches, consolidate (:184), pick the fragments for the gapped aligner (:190-200)
     const bool withGaps = batch->withGaps != 0;
     std::vector<std::vector<uint64_t>> gapTargets(parts);
@@ -282,6 +297,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         }
         gapBegin[t + 1] = gapTargets[t].size();
     });
+    timer.mark("P3 apply + consolidate");
     for (unsigned p = 0; p < parts; ++p) gapBegin[p + 1] += gapBegin[p];
     const uint64_t n3 = gapBegin[parts];
     if (n3)
@@ -300,6 +316,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         pools.pools[2] = ps.hCig3.p;
     }
 
+    timer.mark("K2 gapped + copies");
     // ---- P4: acceptance rule (:202-209), final consolidate (:213)
     parallelRanges(T, nClusters, [&](unsigned t, size_t b, size_t e) {
         for (size_t i = 0; i < gapTargets[t].size(); ++i)
@@ -311,9 +328,11 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         for (size_t l = b * rc; l < e * rc; ++l)
             if (listCount[l]) listCount[l] = consolidateDuplicateFragments(ps.work.data() + listBegin[l], listCount[l], true);
     });
+    timer.mark("P4 accept + consolidate");
     flatten(ctx, pools, lists, [&](size_t l) { return std::pair<const WorkFragment *, unsigned>(ps.work.data() + listBegin[l], listCount[l]); });
-    result->fragments = ps.outFragments.data(); result->readFragmentBegin = ps.outBegin.data(); result->cigars = ps.outCigars.data();
-    result->built = ps.outFlags.data(); result->fragmentCount = ps.outFragments.size(); result->cigarWords = ps.outCigars.size();
+    timer.mark("flatten");
+    result->fragments = ps.outFragments.p; result->readFragmentBegin = ps.outBegin.p; result->cigars = ps.outCigars.p;
+    result->built = ps.outFlags.data(); result->fragmentCount = ps.outFragmentCount; result->cigarWords = ps.outCigarWords;
     return ISAAC_EXT_OK;
 }
 
@@ -379,6 +398,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
     std::vector<uint32_t> listCount(n, 0);
     std::vector<uint64_t> listBegin(n, 0);
     uint64_t total = 0;
+    PhaseTimer timer("rescue");
     if (n && stats.coherent())                                                   // :164-168
     {
         // ---- R1: rescue windows (calculateShadowRescueRange :119-149, rescueShadow :170-198)
@@ -412,6 +432,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
                 if (second < first || second + 1 + long(len[shadowReadIndex]) < 0) task.windowEnd = task.windowBegin;   // :179-190
             }
         });
+        timer.mark("R1 windows");
         if (bad) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "rescue request refers to an unknown read or contig");
         // ---- K5: candidate positions of every request, then K1 on all of them (:195-236)
         const unsigned grid = std::min<unsigned>(n, unsigned(ctx->smCount) * 6);
@@ -435,6 +456,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             capacity = uint64_t(poolSize) + 1024;                                // the pool was too small: the kernel reported the need
             CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));
         }
+        timer.mark("K5 shadow candidates");
         CK(cudaMemcpyAsync(ps.hTaskBegin.p, ps.dTaskBegin.p, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ps.hTaskCount.p, ps.dTaskCount.p, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (poolSize)
@@ -447,6 +469,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             CK(cudaMemcpyAsync(ps.hCig1.p, ps.dCig.p, size_t(poolSize) * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         }
         CK(cudaStreamSynchronize(ctx->stream));
+        timer.mark("K1 ungapped + copies");
         pools.pools[0] = ps.hCig1.p;
 
         // ---- R2: shadow lists, best shadow, neighbours to gap-align (:205-256)
@@ -483,6 +506,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             }
             gapBegin[t + 1] = gapTargets[t].size();
         });
+        timer.mark("R2 lists + best");
         for (unsigned p = 0; p < parts; ++p) gapBegin[p + 1] += gapBegin[p];
         const uint64_t n3 = gapBegin[parts];
         if (n3)
@@ -499,6 +523,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             if (rc) return rc;
             pools.pools[2] = ps.hCig3.p;
         }
+        timer.mark("K2 gapped + copies");
         // ---- R3: acceptance in list order, best shadow first (:255-290)
         parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
             size_t g = 0;
@@ -520,11 +545,13 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
                 ps.outFlags[i] = 1;
             }
         });
+        timer.mark("R3 accept + best first");
         for (size_t i = 0; i < n; ++i) total += listCount[i];
     }
     (void)total;
     flatten(ctx, pools, n, [&](size_t i) { return std::pair<const WorkFragment *, unsigned>(ps.work.data() + listBegin[i], listCount[i]); });
-    result->fragments = ps.outFragments.data(); result->requestFragmentBegin = ps.outBegin.data(); result->cigars = ps.outCigars.data();
-    result->rescued = ps.outFlags.data(); result->fragmentCount = ps.outFragments.size(); result->cigarWords = ps.outCigars.size();
+    timer.mark("flatten");
+    result->fragments = ps.outFragments.p; result->requestFragmentBegin = ps.outBegin.p; result->cigars = ps.outCigars.p;
+    result->rescued = ps.outFlags.data(); result->fragmentCount = ps.outFragmentCount; result->cigarWords = ps.outCigarWords;
     return ISAAC_EXT_OK;
 }

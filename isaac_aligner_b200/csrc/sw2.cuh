@@ -10,14 +10,17 @@
 //     borrow can cross the halves), and the match/mismatch score of both alignments is one IMAD;
 //   * the "which operand won" flags the traceback needs are recovered without predicates: max(a,b) != a  <=>  a < b,
 //     so flag = min((max ^ a), 1) per half (XOR + VIMNMX.U16x2), shifted into a per-row accumulator by an IMAD on the
-//     FMA pipe.  5 flag words per row and thread pair are stored (10 bytes per alignment row):
+//     FMA pipe.  Five 16-lane flag masks per half and row:
 //        fE  bit j: G[j] <  E[j]                 (previous row; TG and the TF of lane j+1)
 //        fF  bit j: max(G[j],E[j]) < F[j]        (previous row; TG)
 //        fAB bit j: max(G,E)[j-1]-open < F[j-1]-ext   (TF of lane j)
 //        fGF bit j: newG[j] < newF[j]            (TE of lane j-1)
 //        fHE bit j: max(newG,newF)[j+1]-open < newE[j+1]-ext   (TE of lane j)
-//     The direction codes (including the reference's _mm_max_epi16-on-bytes coupling of lanes 2p/2p+1, :197) are
-//     decoded from these bits only along the traceback path.
+//   * at the end of a row the five masks are turned, with a dozen bitwise operations on whole masks (both halves at
+//     once), into the SIX bit planes the traceback reads: (tg1,tg2) (te1,te2) (tf1,tf2), plane 1 = "direction is E",
+//     plane 2 = "direction is F" of the three direction matrices TG/TE/TF -- including the reference's
+//     _mm_max_epi16-on-byte-pairs coupling of lanes 2p/2p+1 in TG (:197).  6 words per row and thread pair are stored
+//     (12 bytes per alignment row, what the reference's 3 x 16 direction bytes compress to).
 #pragma once
 #include "device_types.cuh"
 #include "sw.cuh"
@@ -45,7 +48,7 @@ __device__ __forceinline__ Sw2Consts makeSw2Consts(const SwScores s)
     return c;
 }
 
-constexpr unsigned SW2_FLAG_WORDS = 5;
+constexpr unsigned SW2_FLAG_WORDS = 6;
 
 /// End-cell scan of one half (:349-379): lanes 15..0, matrices G,E,F in that order, strict '>'.
 __device__ __forceinline__ void sw2ScanEnd(const uint32_t (&G)[16], const uint32_t (&E)[16], const uint32_t (&F)[16],
@@ -64,81 +67,23 @@ __device__ __forceinline__ void sw2ScanEnd(const uint32_t (&G)[16], const uint32
     }
 }
 
-/// Traceback of one half from the stored flag words (:381-453).  ops receives the CIGAR head first.
-__device__ __forceinline__ unsigned sw2Traceback(const uint32_t *__restrict__ tb, const size_t tbStride, const unsigned half,
-                                                 const unsigned L, int jj, unsigned type, uint32_t *ops, const unsigned cap,
-                                                 unsigned &nOps, bool &overflow)
+/// The six direction planes of a row from its five flag masks; every word holds the 16 lanes of half A in its low and
+/// of half B in its high 16 bits, shifts by one lane are masked so that nothing crosses the halves.
+__device__ __forceinline__ void sw2Planes(uint32_t fE, uint32_t fF, uint32_t fAB, uint32_t fGF, uint32_t fHE, uint32_t (&p)[SW2_FLAG_WORDS])
 {
-    const unsigned sh = half * 16;
-    int ii = int(L) - 1;
-    unsigned w = cap;
-    overflow = false;
-    auto push = [&](unsigned length, unsigned type3) {
-        const uint32_t op = type3 == 0 ? ISAAC_EXT_CIGAR_ALIGN : (type3 == 1 ? ISAAC_EXT_CIGAR_DELETE : ISAAC_EXT_CIGAR_INSERT);
-        if (w == 0) { overflow = true; return; }
-        ops[--w] = cigarWord(length, op);
-    };
-    unsigned opLength = 0;
-    if (jj > 0) push(unsigned(jj), 1);
-    // Every row from L-1 down to 0 is visited exactly once, so the flag words of the rows ahead can be pulled into
-    // L1 while the current row is decoded: the walk is a chain of dependent loads otherwise.
-    constexpr int PREFETCH_ROWS = 8;
-    auto prefetchRow = [&](int r) {
-        if (r >= 0)
-        {
-            const uint32_t *p = tb + size_t(r) * SW2_FLAG_WORDS * tbStride;
-#pragma unroll
-            for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + k * tbStride));
-        }
-    };
-    for (int r = 0; r < PREFETCH_ROWS; ++r) prefetchRow(ii - r);
-    int cachedRow = -1;
-    uint32_t row[SW2_FLAG_WORDS] = {0, 0, 0, 0, 0};
-    while (ii >= 0 && jj >= 0 && jj <= 15)
-    {
-        ++opLength;
-        if (cachedRow != ii)
-        {
-            const uint32_t *p = tb + size_t(ii) * SW2_FLAG_WORDS * tbStride;
-#pragma unroll
-            for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) row[k] = p[k * tbStride];
-            cachedRow = ii;
-            prefetchRow(ii - PREFETCH_ROWS);
-        }
-        unsigned next;
-        if (type == 0)
-        {
-            const unsigned fE = (row[0] >> sh) & 0xFFFFu, fF = (row[1] >> sh) & 0xFFFFu;
-            const unsigned lo = unsigned(jj) & ~1u, hi = lo + 1;
-            const unsigned tgElo = (fE >> lo) & 1u, tgEhi = (fE >> hi) & 1u;
-            const unsigned tgFlo = ((fF >> lo) & 1u) * 2u, tgFhi = ((fF >> hi) & 1u) * 2u;
-            // _mm_max_epi16 on byte pairs (:197): the odd lane decides which whole pair wins
-            if (jj & 1) next = tgFhi ? 2u : tgEhi;
-            else next = tgFhi ? tgFlo : (tgEhi ? tgElo : max(tgFlo, tgElo));
-        }
-        else if (type == 1)
-        {
-            const unsigned fHE = (row[4] >> sh) & 0xFFFFu, fGF = (row[3] >> sh) & 0xFFFFu;
-            next = ((fHE >> jj) & 1u) ? 1u : (((fGF >> (jj + 1)) & 1u) ? 2u : 0u);
-        }
-        else
-        {
-            const unsigned fAB = (row[2] >> sh) & 0xFFFFu, fE = (row[0] >> sh) & 0xFFFFu;
-            next = jj == 0 ? 0u : (((fAB >> jj) & 1u) ? 2u : ((fE >> (jj - 1)) & 1u));
-        }
-        if (next != type) { push(opLength, type); opLength = 0; }
-        if (type == 0) { --ii; } else if (type == 1) { ++jj; } else { --ii; --jj; }
-        type = next;
-    }
-    if (type != 1 && opLength) { push(opLength, type); opLength = 0; }
-    if (jj < 15) { push(opLength + 15 - jj, 1); opLength = 0; }
-    unsigned ret = 0;
-    unsigned e = cap;
-    if (w < e && (ops[w] & 0xFu) == ISAAC_EXT_CIGAR_DELETE) { ret = ops[w] >> 4; ++w; }
-    if (w < e && (ops[e - 1] & 0xFu) == ISAAC_EXT_CIGAR_DELETE) { --e; }
-    nOps = e - w;
-    for (unsigned k = 0; k < nOps; ++k) ops[k] = ops[w + k];
-    return ret;
+    const uint32_t EVEN = 0x55555555u, ODD = 0xAAAAAAAAu;
+    // TG (:176-197).  Odd lane (high byte of the pair): F wins over E.  Even lane: the pair with the larger high byte
+    // wins as a whole, so the odd lane's flags decide which of the even lane's own flags survive.
+    const uint32_t hF = (fF >> 1) & EVEN, hE = (fE >> 1) & EVEN;                 // the odd lane's flags at the even lane's bit
+    const uint32_t tg2 = (fF & ODD) | (fF & EVEN & (hF | ~hE));
+    const uint32_t tg1 = (fE & ~fF & ODD) | (fE & EVEN & ~hF & (hE | ~fF));
+    // TE (:261-297): 1 if e beats both, else 2 if f > g (flags of lane j+1)
+    const uint32_t te1 = fHE;
+    const uint32_t te2 = ~fHE & ((fGF >> 1) & 0x7FFF7FFFu);
+    // TF (:142-167): 2 if a < b, else 1 if G[j-1] < E[j-1]; lane 0 is forced to 0
+    const uint32_t tf2 = fAB & 0xFFFEFFFEu;
+    const uint32_t tf1 = ~fAB & ((fE << 1) & 0xFFFEFFFEu);
+    p[0] = tg1; p[1] = tg2; p[2] = te1; p[3] = te2; p[4] = tf1; p[5] = tf2;
 }
 
 /// One traceback in progress (one half of a pair).
@@ -163,13 +108,12 @@ struct Sw2Walker
         overflow = false; active = L != 0;
         if (active && jj > 0) push(unsigned(jj), 1);                           // :388-391
     }
-    /// all steps of this walk that happen in row 'row' (:392-423); f = the 16 flag bits of this half of the 5 row words
-    __device__ __forceinline__ void stepRow(int row, unsigned fE, unsigned fF, unsigned fAB, unsigned fGF, unsigned fHE)
+    /// all steps of this walk that happen in row 'row' (:392-423); p = the 16 lanes of this half of the six planes
+    __device__ __forceinline__ void stepRow(int row, const unsigned (&p)[SW2_FLAG_WORDS])
     {
         if (!active || ii != row) return;
-        // fast path, the overwhelmingly common step: on the diagonal, and neither lane of the byte pair (2p, 2p+1)
-        // has a direction flag set, so the direction of G is G again whatever the _mm_max_epi16 coupling does
-        if (type == 0 && (((fE | fF) >> (unsigned(jj) & ~1u)) & 3u) == 0)
+        // the overwhelmingly common step: on the diagonal and staying there
+        if (type == 0 && (((p[0] | p[1]) >> jj) & 1u) == 0)
         {
             ++opLength; --ii;
             active = ii >= 0;
@@ -178,17 +122,9 @@ struct Sw2Walker
         while (active && ii == row)
         {
             ++opLength;
-            unsigned next;
-            if (type == 0)
-            {
-                // _mm_max_epi16 on byte pairs (:197): the odd lane decides which whole pair wins
-                const unsigned lo = unsigned(jj) & ~1u;
-                const unsigned loE = (fE >> lo) & 1u, hiE = (fE >> lo) & 2u, loF = (fF >> lo) & 1u, hiF = (fF >> lo) & 2u;
-                if (jj & 1) next = hiF ? 2u : (hiE >> 1);
-                else next = hiF ? loF * 2u : (hiE ? loE : max(loF * 2u, loE));
-            }
-            else if (type == 1) next = ((fHE >> jj) & 1u) ? 1u : (((fGF >> (jj + 1)) & 1u) ? 2u : 0u);
-            else next = jj == 0 ? 0u : (((fAB >> jj) & 1u) ? 2u : ((fE >> (jj - 1)) & 1u));
+            const unsigned p1 = type == 0 ? p[0] : (type == 1 ? p[2] : p[4]);
+            const unsigned p2 = type == 0 ? p[1] : (type == 1 ? p[3] : p[5]);
+            const unsigned next = ((p1 >> jj) & 1u) | (((p2 >> jj) & 1u) << 1);
             if (next != type) { push(opLength, type); opLength = 0; }
             if (type == 0) { --ii; } else if (type == 1) { ++jj; } else { --ii; --jj; }
             type = next;
@@ -210,7 +146,7 @@ struct Sw2Walker
 };
 
 /// Traceback of both halves of a pair in one pass over the rows (every row from L-1 down to 0 is visited exactly once
-/// by each walk, so the row order is known in advance): the five flag words of four rows ahead are kept in flight in
+/// by each walk, so the row order is known in advance): the six plane words of four rows ahead are kept in flight in
 /// registers, turning the walk's chain of dependent loads into a software pipeline.
 __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb, const size_t tbStride,
                                                  Sw2Walker &a, Sw2Walker &b)
@@ -224,8 +160,11 @@ __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb
     };
     auto process = [&](int r, const uint32_t (&w)[SW2_FLAG_WORDS]) {
         if (r < 0) return;
-        a.stepRow(r, w[0] & 0xFFFFu, w[1] & 0xFFFFu, w[2] & 0xFFFFu, w[3] & 0xFFFFu, w[4] & 0xFFFFu);
-        b.stepRow(r, w[0] >> 16, w[1] >> 16, w[2] >> 16, w[3] >> 16, w[4] >> 16);
+        unsigned lo[SW2_FLAG_WORDS], hi[SW2_FLAG_WORDS];
+#pragma unroll
+        for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) { lo[k] = w[k] & 0xFFFFu; hi[k] = w[k] >> 16; }
+        a.stepRow(r, lo);
+        b.stepRow(r, hi);
     };
     uint32_t w0[SW2_FLAG_WORDS], w1[SW2_FLAG_WORDS], w2[SW2_FLAG_WORDS], w3[SW2_FLAG_WORDS];
     load(top, w0); load(top - 1, w1); load(top - 2, w2); load(top - 3, w3);
@@ -238,9 +177,9 @@ __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb
     }
 }
 
-/// Forward pass over max(LA, LB) rows for the pair.  src.q(half, i) / src.d(half, k) return base codes (they must
-/// tolerate indices past the own length of a half: any code will do there).  On return jj/type hold the end cell of
-/// each half.
+/// Forward pass over max(LA, LB) rows for the pair.  src.q2(i) / src.d2(k) return the base codes of both halves (they
+/// must tolerate indices past the own length of a half: any code will do there).  On return jj/type hold the end cell
+/// of each half.
 template <class PairSrc>
 __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, const unsigned LB, const SwScores s,
                                            uint32_t *__restrict__ tb, const size_t tbStride,
@@ -307,8 +246,11 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
             G[j] = nG; E[j] = nE; F[j] = nF;
             mCur = mPrev; xE = xEprev;
         }
-        uint32_t *row = tb + size_t(i) * SW2_FLAG_WORDS * tbStride;
-        row[0] = fE; row[tbStride] = fF; row[2 * tbStride] = fAB; row[3 * tbStride] = fGF; row[4 * tbStride] = fHE;
+        uint32_t planes[SW2_FLAG_WORDS];
+        sw2Planes(fE, fF, fAB, fGF, fHE, planes);
+        uint32_t *row = tb + size_t(i) * SW2_FLAG_WORDS * tbStride;                                      // :306-308
+#pragma unroll
+        for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) row[k * tbStride] = planes[k];
         if (LA != LB)
         {
             if (i + 1 == LA) sw2ScanEnd(G, E, F, 0, jj[0], type[0]);

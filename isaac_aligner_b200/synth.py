@@ -163,6 +163,29 @@ def microbench_candidates(sim, genome, per_read=4, seed=SEED_READS + 2, fraction
     return cand
 
 
+def rescue_policy(fragments, begin, n_clusters):
+    """Stand-in for the decision TemplateBuilder takes between the two calls of the path (out of scope):
+    a pair goes to buildDisjoinedTemplate whenever its best pair has any edit distance (TemplateBuilder.cpp:1073-1081),
+    which rescues the mate of EVERY candidate of both reads (:737-757).  Here: every aligned fragment of a cluster
+    becomes an orphan unless both reads of the cluster have a perfect (edit distance 0) candidate.  Both arms of the
+    benchmark are driven by this same function.  Returns an isaac_ext_rescue_request_t array."""
+    counts = np.diff(begin.astype(np.int64))
+    list_of = np.repeat(np.arange(2 * n_clusters), counts)
+    aligned = fragments["cigarLength"] > 0
+    perfect = aligned & (fragments["editDistance"] == 0)
+    read_perfect = np.bincount(list_of, weights=perfect, minlength=2 * n_clusters) > 0
+    cluster_done = read_perfect[0::2] & read_perfect[1::2]
+    need = aligned & ~cluster_done[list_of // 2]
+    f = fragments[need]
+    req = np.zeros(f.size, dtype=[("orphanPosition", "<i8"), ("bestTemplateLength", "<i8"), ("orphanReadId", "<u4"),
+                                  ("orphanContigStrand", "<u4"), ("orphanObservedLength", "<u4"), ("pad", "<u4")])
+    req["orphanPosition"] = f["position"]
+    req["orphanReadId"] = f["readId"]
+    req["orphanContigStrand"] = (f["contigId"] << 1) | f["reverse"]
+    req["orphanObservedLength"] = f["observedLength"]
+    return req
+
+
 MATCH_DTYPE = np.dtype([("seedId", "<u8"), ("location", "<u8")])    # isaac_ext_match_t == the reference's Match
 SEED_DTYPE = np.dtype([("offset", "<u2"), ("length", "<u2"), ("readIndex", "<u4")])   # isaac_ext_seed_t
 
