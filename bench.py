@@ -48,6 +48,8 @@ def parse_args():
                    help="micro: BASELINE configs[1] (default, the bench line); pairs: build + rescue pipeline, read pairs/s")
     p.add_argument("--pairs", type=int, default=None,
                    help="read pairs per GPU of the pairs pipeline (default 200k as a side measurement of the micro run, 1M for --workload pairs; 0 disables)")
+    p.add_argument("--contigs", type=int, default=1, help="contigs of the synthetic genome (SURVEY 8(d) G3100: 24)")
+    p.add_argument("--n-fraction", type=float, default=0.0, help="fraction of the genome replaced by runs of N (G3100: 0.001)")
     p.add_argument("--indel-rate", type=float, default=5e-4, help="indel events per base of the simulated pairs (config 4: 1e-2)")
     return p.parse_args()
 
@@ -56,7 +58,7 @@ def make_workload(args, rank, n_candidates):
     from isaac_aligner_b200 import synth
     from isaac_aligner_b200.types import ReadSet
     L = args.read_length
-    genome = synth.make_genome(args.genome_bases, n_contigs=1, seed=synth.SEED_G5)
+    genome = synth.make_genome(args.genome_bases, n_contigs=args.contigs, seed=synth.SEED_G5, n_fraction=args.n_fraction)
     n_pairs = max(1, -(-n_candidates // (2 * args.per_read)))
     sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 1 + 1000 * rank)
     reads = ReadSet(sim.bcl, (L, L))
@@ -164,7 +166,7 @@ def make_pairs_workload(args, rank, n_pairs):
     from isaac_aligner_b200.batch import MatchBatch, Tls
     from isaac_aligner_b200.types import ReadSet
     L = args.read_length
-    genome = synth.make_genome(args.genome_bases, n_contigs=1, seed=synth.SEED_G5)
+    genome = synth.make_genome(args.genome_bases, n_contigs=args.contigs, seed=synth.SEED_G5, n_fraction=args.n_fraction)
     sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 7 + 1000 * rank, indel_rate=args.indel_rate,
                                seed_offsets=synth.auto_seed_offsets(L))
     matches, begin = synth.make_matches(sim, genome, seed=synth.SEED_READS + 8 + 1000 * rank, decoy_rate=0.2)

@@ -7,6 +7,7 @@
  * (see oracle/Makefile) and flattens the FragmentMetadata results.  It is linked into oracle/_ref/libisaac_ref.so,
  * which is git-ignored and rebuilt wherever /root/reference is mounted.
  */
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <memory>
@@ -40,15 +41,36 @@ template <class F> void parallelFor(uint32_t n, uint32_t threads, F f)
     for (std::thread &th : pool) th.join();
 }
 
-std::vector<reference::Contig> makeContigs(const oracle_genome_t *g)
+/// reference::Contig copies of the caller's genome, cached across calls (keyed on the caller's pointers) so that timing
+/// a batch does not include copying a human-size genome every time
+const std::vector<reference::Contig> &makeContigs(const oracle_genome_t *g)
 {
-    std::vector<reference::Contig> contigs;
+    static std::mutex mutex;
+    static std::vector<reference::Contig> cached;
+    static std::vector<std::pair<const char *, uint64_t> > key;
+    std::lock_guard<std::mutex> lock(mutex);
+    std::vector<std::pair<const char *, uint64_t> > want;
     for (uint32_t c = 0; c < g->contigCount; ++c)
     {
-        contigs.push_back(reference::Contig(c, "c" + std::to_string(c)));
-        contigs.back().forward_.assign(g->contigBases[c], g->contigBases[c] + g->contigLengths[c]);
+        // the caller may reuse an address for another genome: fold a content fingerprint into the key (every byte up
+        // to 64 MB, a strided sample beyond)
+        const char *b = g->contigBases[c];
+        const uint64_t n = g->contigLengths[c], step = n > (64u << 20) ? n / (1u << 20) : 1;
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t i = 0; i < n; i += step) h = (h ^ uint8_t(b[i])) * 1099511628211ull;
+        want.push_back(std::make_pair(b, n ^ (h << 20)));
     }
-    return contigs;
+    if (want != key)
+    {
+        cached.clear();
+        for (uint32_t c = 0; c < g->contigCount; ++c)
+        {
+            cached.push_back(reference::Contig(c, "c" + std::to_string(c)));
+            cached.back().forward_.assign(g->contigBases[c], g->contigBases[c] + g->contigLengths[c]);
+        }
+        key = want;
+    }
+    return cached;
 }
 
 flowcell::ReadMetadataList makeReadMetadata(const isaac_ext_reads_t *r)
@@ -166,7 +188,7 @@ static int extendBatch(const bool gapped, const oracle_genome_t *genome, const i
 {
     try
     {
-        const std::vector<reference::Contig> contigs = makeContigs(genome);
+        const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
         const alignment::matchSelector::SequencingAdapterList noAdapters;
@@ -276,7 +298,7 @@ extern "C" int oracle_build_fragments(const oracle_genome_t *genome, const isaac
 {
     try
     {
-        const std::vector<reference::Contig> contigs = makeContigs(genome);
+        const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
         const alignment::matchSelector::SequencingAdapterList noAdapters;
@@ -332,7 +354,7 @@ extern "C" int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_
 {
     try
     {
-        const std::vector<reference::Contig> contigs = makeContigs(genome);
+        const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
         const alignment::matchSelector::SequencingAdapterList noAdapters;
