@@ -310,13 +310,15 @@ def run_b200(args):
         h_cand_t = pin((n, 16), torch.uint8)
         h_cand_t.numpy()[:] = cand.view(np.uint8).reshape(n, 16)
         h_cand = h_cand_t.numpy().reshape(-1).view(CANDIDATE_DTYPE)
-        out_u = (pin((n, 64), torch.uint8), pin((n, 3), torch.int32))
-        out_g = (pin((n, 64), torch.uint8), pin((n, stride), torch.int32))
-        as_out = lambda o: (o[0].numpy().reshape(-1).view(FRAGMENT_DTYPE), o[1].numpy().view(np.uint32), None)
+        # isaac_ext_*_batch_compact: 64-byte records + a dense CIGAR pool, chunked with overlapped copies
+        out_u = (pin((n, 64), torch.uint8), pin((n * 3,), torch.int32))
+        out_g = (pin((n, 64), torch.uint8), pin((n * 12,), torch.int32))
+        views = [(o[0].numpy().reshape(-1).view(FRAGMENT_DTYPE), o[1].numpy().view(np.uint32)) for o in (out_u, out_g)]
+        words = [0, 0]
 
         def e2e_step():
-            ctx.ungapped(h_cand, with_masks=False, out=as_out(out_u))
-            ctx.gapped(h_cand, cigar_stride=stride, with_masks=False, out=as_out(out_g))
+            words[0] = ctx.extend_compact(h_cand, False, views[0][0], views[0][1])
+            words[1] = ctx.extend_compact(h_cand, True, views[1][0], views[1][1])
 
         for _ in range(max(1, args.warmup // 2)):
             e2e_step()
@@ -331,10 +333,14 @@ def run_b200(args):
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item()) / args.steps
-        # the device results of the resident path and the host results of the e2e path must agree
-        assert np.array_equal(d_frag_g.cpu().numpy(), out_g[0].numpy()), "resident and end-to-end results differ"
+        # the device results of the resident path and the host results of the e2e path must agree (all but cigarOffset)
+        res_dev = d_frag_g.cpu().numpy().reshape(-1).view(FRAGMENT_DTYPE)
+        for name in FRAGMENT_DTYPE.names:
+            if name != "cigarOffset":
+                assert np.array_equal(res_dev[name], views[1][0][name]), "resident and end-to-end results differ: " + name
         e2e = {"value": world * cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": 2 * n * 16, "d2h_bytes_per_step": n * (64 + 3 * 4) + n * (64 + stride * 4)}
+               "h2d_bytes_per_step": 2 * n * 16, "d2h_bytes_per_step": 2 * n * 64 + 4 * (words[0] + words[1]),
+               "api": "isaac_ext_ungapped_batch_compact + isaac_ext_gapped_batch_compact, pinned host buffers"}
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 

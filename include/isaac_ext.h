@@ -247,6 +247,17 @@ int isaac_ext_gapped_batch(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candi
                            uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
                            uint64_t *mismatchMaskOut);
 
+/* End-to-end variants of the two calls above for large batches: same semantics, but the CIGARs come back as a DENSE pool
+ * (fragment.cigarOffset indexes cigarPoolOut; *cigarWordsOut = words used) and the batch is processed in chunks whose
+ * host-to-device copy, kernels and device-to-host copies overlap.  Pass page-locked host buffers for full copy speed.
+ * ISAAC_EXT_E_CAPACITY if cigarPoolCapacity (in words) is too small; *cigarWordsOut then holds the required size. */
+int isaac_ext_ungapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                     isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
+                                     uint64_t *cigarWordsOut);
+int isaac_ext_gapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                   isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
+                                   uint64_t *cigarWordsOut);
+
 /* Device-resident variants used to time the kernels alone: the candidate and result arrays are device
  * pointers, the launch goes to 'cudaStream' (a cudaStream_t passed as void*) and returns without
  * synchronising.  Same semantics as the host variants above. */

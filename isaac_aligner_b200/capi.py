@@ -32,7 +32,7 @@ EXPORTS = [
     "isaac_ext_set_reference", "isaac_ext_set_reads", "isaac_ext_banded_sw_batch", "isaac_ext_ungapped_batch",
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
-    "isaac_ext_tile_stats_device",
+    "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
 ]
 
 
@@ -127,6 +127,15 @@ class Context:
         self._check(_lib.isaac_ext_gapped_batch(self._h, ctypes.c_uint32(n), _p(cand), ctypes.c_uint32(cigar_stride),
                                                 _p(frags), _p(cig), _p(mask)))
         return frags, cig, mask
+
+    def extend_compact(self, candidates, gapped, fragments_out, pool_out):
+        """end-to-end variant: fixed 64-byte records + dense CIGAR pool, chunked and overlapped; returns words used"""
+        cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
+        words = ctypes.c_uint64()
+        fn = _lib.isaac_ext_gapped_batch_compact if gapped else _lib.isaac_ext_ungapped_batch_compact
+        self._check(fn(self._h, ctypes.c_uint32(len(cand)), _p(cand), _p(fragments_out), _p(pool_out),
+                       ctypes.c_uint64(pool_out.size), ctypes.byref(words)))
+        return int(words.value)
 
     def build_fragments(self, match_batch, copy=True):
         """FragmentBuilder::build for every cluster of the resident read set -> batch.FlatFragments

@@ -18,6 +18,8 @@ using namespace isaac_b200;
 namespace
 {
 thread_local std::string g_createError;
+struct E2eState;                       // isaac_ext_e2e.cuh
+void releaseE2e(E2eState *state);
 } // namespace
 
 struct isaac_ext_ctx
@@ -35,6 +37,7 @@ struct isaac_ext_ctx
     unsigned hostThreads = 1;     // config.hostThreads (0 = hardware concurrency)
     uint32_t clusterCount = 0;    // of the resident read set
     PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows
+    E2eState *e2e = nullptr;      // streams and chunk buffers of the *_batch_compact entry points
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
     DeviceBuffer<double> tables;
@@ -210,6 +213,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
     ctx->pipeline.release();
+    releaseE2e(ctx->e2e);
     delete ctx;
 }
 
@@ -308,15 +312,20 @@ extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *
 
 static int validateCandidates(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *c)
 {
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        const uint32_t contig = c[i].contigStrand >> 1;
-        if (c[i].readId >= ctx->reads.readTotal || contig >= ctx->ref.contigCount)
-            return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "candidate refers to an unknown read or contig");
-        // FragmentBuilder::addMatch / ShadowAligner never place a read beyond the contig end
-        if (c[i].position > int64_t(ctx->contigLength[contig]) || c[i].position < -int64_t(ISAAC_EXT_MAX_CYCLES))
-            return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "candidate position outside [-readLength, contigLength]");
-    }
+    std::atomic<int> bad(0);
+    parallelRanges(ctx->hostThreads, n, [&](unsigned, size_t b, size_t e) {
+        int mine = 0;
+        for (size_t i = b; i < e; ++i)
+        {
+            const uint32_t contig = c[i].contigStrand >> 1;
+            if (c[i].readId >= ctx->reads.readTotal || contig >= ctx->ref.contigCount) { mine = 1; continue; }
+            // FragmentBuilder::addMatch / ShadowAligner never place a read beyond the contig end
+            if (c[i].position > int64_t(ctx->contigLength[contig]) || c[i].position < -int64_t(ISAAC_EXT_MAX_CYCLES)) mine = 2;
+        }
+        if (mine) bad = mine;
+    });
+    if (bad == 1) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "candidate refers to an unknown read or contig");
+    if (bad == 2) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "candidate position outside [-readLength, contigLength]");
     return ISAAC_EXT_OK;
 }
 
@@ -499,3 +508,29 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 
 // isaac_ext_build_fragments, isaac_ext_rescue_shadows
 #include "isaac_ext_pipelines.cuh"
+
+// isaac_ext_ungapped_batch_compact, isaac_ext_gapped_batch_compact
+#include "isaac_ext_e2e.cuh"
+
+namespace
+{
+void releaseE2e(E2eState *state) { if (state) { state->release(); delete state; } }
+} // namespace
+
+extern "C" int isaac_ext_ungapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                                isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
+                                                uint64_t *cigarWordsOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->e2e) ctx->e2e = new E2eState();
+    return extendCompact(ctx, *ctx->e2e, false, n, candidates, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut);
+}
+
+extern "C" int isaac_ext_gapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                              isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
+                                              uint64_t *cigarWordsOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->e2e) ctx->e2e = new E2eState();
+    return extendCompact(ctx, *ctx->e2e, true, n, candidates, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut);
+}

@@ -1,0 +1,97 @@
+// Compaction of the fixed-stride CIGAR slots a kernel pass wrote into a dense pool (deterministic 3-pass exclusive scan
+// over cigarLength): the end-to-end entry points return 64-byte records + a dense CIGAR pool instead of 'stride' words
+// per candidate, which is what bounds them on PCIe.
+#pragma once
+#include "device_types.cuh"
+
+namespace isaac_b200
+{
+
+constexpr unsigned COMPACT_BLOCK = 256, COMPACT_ITEMS = 4;      // 1024 records per block
+
+__global__ void __launch_bounds__(COMPACT_BLOCK)
+cigarBlockSumsKernel(uint32_t n, const isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ blockSums)
+{
+    __shared__ uint32_t warpSums[COMPACT_BLOCK / 32];
+    const uint32_t first = (blockIdx.x * COMPACT_BLOCK + threadIdx.x) * COMPACT_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (unsigned k = 0; k < COMPACT_ITEMS; ++k) if (first + k < n) s += fragments[first + k].cigarLength;
+    for (unsigned d = 16; d; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+    if ((threadIdx.x & 31u) == 0) warpSums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t t = 0;
+        for (unsigned w = 0; w < COMPACT_BLOCK / 32; ++w) t += warpSums[w];
+        blockSums[blockIdx.x] = t;
+    }
+}
+
+/// exclusive scan of the block sums by one block; total[0] = grand total
+__global__ void __launch_bounds__(1024) cigarScanBlockSumsKernel(uint32_t blocks, uint32_t *__restrict__ blockSums, uint32_t *__restrict__ total)
+{
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < blocks; base += 1024)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < blocks ? blockSums[i] : 0u;
+        uint32_t incl = v;
+        for (unsigned d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((threadIdx.x & 31u) >= d) incl += o; }
+        if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            uint32_t w = warpSums[threadIdx.x];
+            for (unsigned d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, w, d); if (threadIdx.x >= d) w += o; }
+            warpSums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warpOffset = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
+        if (i < blocks) blockSums[i] = carry + warpOffset + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += warpOffset + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = carry;
+}
+
+/// writes the dense pool and points every record at its words (cigarOffset = poolBase + dense offset)
+__global__ void __launch_bounds__(COMPACT_BLOCK)
+cigarCompactKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, const uint32_t *__restrict__ strided, uint32_t stride,
+                   const uint32_t *__restrict__ blockOffsets, uint32_t *__restrict__ pool, uint32_t poolCapacity)
+{
+    __shared__ uint32_t warpSums[COMPACT_BLOCK / 32];
+    const uint32_t first = (blockIdx.x * COMPACT_BLOCK + threadIdx.x) * COMPACT_ITEMS;
+    uint32_t len[COMPACT_ITEMS], s = 0;
+#pragma unroll
+    for (unsigned k = 0; k < COMPACT_ITEMS; ++k) { len[k] = first + k < n ? fragments[first + k].cigarLength : 0u; s += len[k]; }
+    uint32_t incl = s;
+    for (unsigned d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((threadIdx.x & 31u) >= d) incl += o; }
+    if ((threadIdx.x & 31u) == 31u) warpSums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t offset = blockOffsets[blockIdx.x] + incl - s;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) offset += warpSums[w];
+#pragma unroll
+    for (unsigned k = 0; k < COMPACT_ITEMS; ++k)
+    {
+        if (first + k < n)
+        {
+            if (offset + len[k] <= poolCapacity)
+                for (unsigned j = 0; j < len[k]; ++j) pool[offset + j] = strided[size_t(first + k) * stride + j];
+            fragments[first + k].cigarOffset = offset;
+            offset += len[k];
+        }
+    }
+}
+
+/// cigarOffset += base for a chunk whose pool lands at 'base' of the caller's pool
+__global__ void addCigarBaseKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, uint32_t base)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) fragments[i].cigarOffset += base;
+}
+
+} // namespace isaac_b200

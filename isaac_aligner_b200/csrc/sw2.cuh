@@ -9,8 +9,9 @@
 //     no value leaves the int16 range, hence adding a constant to both halves is ONE 32-bit add of c * 0x10001 (no
 //     borrow can cross the halves), and the match/mismatch score of both alignments is one IMAD;
 //   * the "which operand won" flags the traceback needs are recovered without predicates: max(a,b) != a  <=>  a < b,
-//     so flag = min((max ^ a), 1) per half (XOR + VIMNMX.U16x2), shifted into a per-row accumulator by an IMAD on the
-//     FMA pipe.  Five 16-lane flag masks per half and row:
+//     so flag = min(max - a, 1) per half (the halves of max - a cannot borrow from each other because max >= a in
+//     both, so it is ONE 32-bit subtract that ptxas is free to place on either integer pipe, + one VIMNMX.U16x2),
+//     shifted into a per-row accumulator by an IMAD on the FMA pipe.  Five 16-lane flag masks per half and row:
 //        fE  bit j: G[j] <  E[j]                 (previous row; TG and the TF of lane j+1)
 //        fF  bit j: max(G[j],E[j]) < F[j]        (previous row; TG)
 //        fAB bit j: max(G,E)[j-1]-open < F[j-1]-ext   (TF of lane j)
@@ -204,7 +205,7 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
         const uint32_t Q = src.q2(i);
         uint32_t fE = 0, fF = 0, fAB = 0, fGF = 0, fHE = 0;
         uint32_t mCur = __vmaxu2(G[15], E[15]);
-        uint32_t xE = mCur ^ G[15];
+        uint32_t xE = mCur - G[15];
         uint32_t hOnext = 0, nEnext = 0;
 #pragma unroll
         for (int j = 15; j >= 0; --j)
@@ -214,15 +215,15 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
             if (j > 0)
             {
                 mPrev = __vmaxu2(G[j - 1], E[j - 1]);
-                xEprev = mPrev ^ G[j - 1];
+                xEprev = mPrev - G[j - 1];
                 const uint32_t a = mPrev + c.negOpen32;
                 nF = __viaddmax_u16x2(F[j - 1], c.negExt16x2, a);
-                xAB = nF ^ a;
+                xAB = nF - a;
             }
             else { nF = c.init2; xAB = 0; }                                       // :167, :173
             // ---- G of lane j from the same lane (:176-190, :230-244)
             const uint32_t g = __vmaxu2(mCur, F[j]);
-            const uint32_t xF = g ^ mCur;
+            const uint32_t xF = g - mCur;
             const uint32_t t = __vminu2(D[j] ^ Q, 0x00010001u);
             const uint32_t nG = g + c.match32 + t * uint32_t(c.delta);
             // ---- E of lane j from lane j+1 of THIS row (:261-297)
@@ -230,11 +231,11 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
             if (j < 15)
             {
                 nE = __viaddmax_u16x2(nEnext, c.negExt16x2, hOnext);
-                xHE = nE ^ hOnext;
+                xHE = nE - hOnext;
             }
             else { nE = c.init2; xHE = 0; }
             const uint32_t h = __vmaxu2(nG, nF);
-            const uint32_t xGF = h ^ nG;
+            const uint32_t xGF = h - nG;
             hOnext = h + c.negOpen32;
             nEnext = nE;
             // ---- flags, bit j of each half

@@ -81,3 +81,33 @@ def test_errors_are_loud(capi):
         ctx.ungapped(np.zeros(1, dtype=capi.CANDIDATE_DTYPE))
     assert e.value.code == 6      # no reference yet
     ctx.close()
+
+
+@pytest.mark.parametrize("gapped", [False, True])
+def test_compact_end_to_end_variant_matches_fixed_stride(capi, gapped):
+    """isaac_ext_*_batch_compact: same records, CIGARs in a dense pool; several chunks and an odd tail"""
+    genome, sim, reads, cand = small_workload(n_pairs=3000, L=100, seed=91, indel_rate=6e-3)
+    ctx = capi.Context(Config.default(max_read_length=200))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    cand = cand[ctx.ungapped(cand)[0]["cigarLength"] > 0]
+    cand = np.concatenate([cand] * 130)[:(1 << 21) + 12345]          # > 2 chunks of 2^20
+    f0, c0, _ = (ctx.gapped(cand, with_masks=False) if gapped else ctx.ungapped(cand, with_masks=False))
+    f1 = np.zeros(len(cand), dtype=capi.FRAGMENT_DTYPE)
+    pool = np.zeros(len(cand) * 10, dtype=np.uint32)
+    words = ctx.extend_compact(cand, gapped, f1, pool)
+    assert words == int(f0["cigarLength"].sum())
+    for name in capi.FRAGMENT_DTYPE.names:
+        if name != "cigarOffset":
+            assert np.array_equal(f0[name], f1[name]), name
+    off = np.concatenate([[0], np.cumsum(f0["cigarLength"][:-1], dtype=np.uint64)])
+    assert np.array_equal(f1["cigarOffset"], off.astype(np.uint32))
+    idx = np.random.default_rng(3).integers(0, len(cand), size=5000)
+    for i in idx:
+        n = int(f0["cigarLength"][i])
+        assert np.array_equal(c0[i][:n], pool[int(f1["cigarOffset"][i]):int(f1["cigarOffset"][i]) + n])
+    # a pool that is too small is reported, with the required size
+    with pytest.raises(capi.ExtError) as e:
+        ctx.extend_compact(cand, gapped, f1, pool[:1000])
+    assert e.value.code == 5
+    ctx.close()
