@@ -6,7 +6,8 @@ followed by banded Smith-Waterman + traceback + re-scoring (K2+K4) of every cand
   value          banded-SW GCUPS = candidates * 16 * L cell updates / step time, inputs resident in HBM
   e2e            the same through the C ABI with pinned HOST buffers (H2D of the candidates, D2H of all results inside
                  the timed region)
-  roofline       dominant kernel (gappedKernel): algorithmic integer operations (23 per cell) per second
+  roofline       dominant kernel (swForwardKernel, timed together with the swTraceScoreKernel launches that overlap it =
+                 the isaac_ext_gapped_batch_device call): algorithmic integer operations (23 per cell) per second
                  against the integer-pipe peak measured live on this GPU (MEASURED_PEAKS.json has no INT32 figure)
   cpu_baseline   the reference's own code (oracle/_ref, kind "reference") or the scalar restatement (kind "port")
                  timed on this box's host cores on a bounded sample of the same workload
@@ -363,7 +364,7 @@ def run_b200(args):
     ungapped_gbs = (n * per_cand + reads.cluster_count * 2 * per_read) / (ms_ungapped * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gappedKernel"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gapped_pass"]["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
     # ---- CPU baseline on a bounded sample, same box
@@ -387,8 +388,11 @@ def run_b200(args):
         "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
         "tile_stats": dict(zip(distributed.STAT_NAMES, (int(x) for x in d_stats.cpu().numpy().view(np.uint64)[:8]))),
         "pairs_pipeline": pairs_line,
-        "roofline": {"bound": "int32", "kernel": "gappedKernel", "achieved": achieved / 1e12, "peak": peak_add / 1e12,
+        "roofline": {"bound": "int32", "kernel": "swForwardKernel (timed with the swTraceScoreKernel launches it overlaps: "
+                                                  "the whole isaac_ext_gapped_batch_device call)",
+                     "achieved": achieved / 1e12, "peak": peak_add / 1e12,
                      "unit": "TOP/s", "frac": achieved / peak_add, "traffic": traffic,
+                     "plane_bytes_per_launch": int(n) * L * 12 * 2,
                      "ops_per_cell": OPS_PER_CELL, "gcups_kernel": sw_gcups_kernel, "ms_per_launch": ms_gapped,
                      "peak_source": "measured live by isaac_ext_measure_int32_peak: add.s32 %.1f, max.s32 %.1f, "
                                     "16x2 max %.1f TOP/s" % (peak_add / 1e12, peak_max / 1e12, peak_dpx / 1e12)},

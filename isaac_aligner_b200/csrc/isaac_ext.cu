@@ -10,6 +10,7 @@
 #include "device_buffer.cuh"
 #include "kernels.cuh"
 #include "kernels2.cuh"
+#include "kernels3.cuh"
 #include "host_build.cuh"
 #include "kernels_stats.cuh"
 
@@ -32,8 +33,14 @@ struct isaac_ext_ctx
     uint64_t launches = 0;
     // Tuning knobs (environment, read once at isaac_ext_create): ISAAC_EXT_SW_IMPL = 2 (packed 16x2, two alignments per
     // thread, default) or 1 (scalar, one alignment per thread); ISAAC_EXT_SW_BLOCKS_PER_SM bounds the persistent grid.
-    int swImpl = 2;
+    // ISAAC_EXT_SW_IMPL = 3 (default): the packed kernel split into a forward and a trace+score kernel (kernels3.cuh),
+    // ISAAC_EXT_SW_CHUNK_WAVES = waves of forward blocks per chunk of that path.
+    int swImpl = 3;
     unsigned swBlocksPerSm = 8;
+    unsigned swChunkWaves = 2;
+    cudaStream_t swStream[2] = {nullptr, nullptr};
+    cudaEvent_t swDone[2] = {nullptr, nullptr}, swStart = nullptr;
+    DeviceBuffer<uint32_t> swPlanes[2], swEndCells[2];
     unsigned hostThreads = 1;     // config.hostThreads (0 = hardware concurrency)
     uint32_t clusterCount = 0;    // of the resident read set
     PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows
@@ -115,7 +122,7 @@ bool swScoresSupported(int match, int mismatch, int open, int ext, unsigned maxR
 
 int ensureTraceback(isaac_ext_ctx *ctx, unsigned grid, unsigned block, unsigned maxQueryLength)
 {
-    const size_t words = size_t(grid) * block * (ctx->swImpl == 2 ? SW2_FLAG_WORDS : 3u) * maxQueryLength;
+    const size_t words = size_t(grid) * block * (ctx->swImpl >= 2 ? SW2_FLAG_WORDS : 3u) * maxQueryLength;
     return ctx->cuda(ctx->tbScratch.reserve(words), "cudaMalloc(traceback scratch)");
 }
 
@@ -169,12 +176,19 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
     isaac_ext_ctx *ctx = new isaac_ext_ctx();
     ctx->cfg = *config;
     ctx->hostThreads = config->hostThreads ? config->hostThreads : std::max(1u, std::thread::hardware_concurrency());
-    if (const char *e = std::getenv("ISAAC_EXT_SW_IMPL")) ctx->swImpl = std::atoi(e) == 1 ? 1 : 2;
+    if (const char *e = std::getenv("ISAAC_EXT_SW_IMPL")) ctx->swImpl = std::max(1, std::min(3, std::atoi(e)));
+    if (const char *e = std::getenv("ISAAC_EXT_SW_CHUNK_WAVES")) ctx->swChunkWaves = std::max(1, std::min(64, std::atoi(e)));
     if (const char *e = std::getenv("ISAAC_EXT_SW_BLOCKS_PER_SM")) ctx->swBlocksPerSm = std::max(1, std::min(16, std::atoi(e)));
     ctx->device = config->device;
     int rc = ctx->cuda(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (!rc) rc = ctx->cuda(cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, ctx->device), "cudaDeviceGetAttribute");
     if (!rc) rc = ctx->cuda(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int k = 0; k < 2 && !rc; ++k)
+    {
+        rc = ctx->cuda(cudaStreamCreateWithFlags(&ctx->swStream[k], cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!rc) rc = ctx->cuda(cudaEventCreateWithFlags(&ctx->swDone[k], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (!rc) rc = ctx->cuda(cudaEventCreateWithFlags(&ctx->swStart, cudaEventDisableTiming), "cudaEventCreate");
     if (!rc) rc = ctx->cuda(ctx->tables.reserve(201), "cudaMalloc(tables)");
     if (!rc) rc = ctx->cuda(ctx->errorFlag.reserve(1), "cudaMalloc(flag)");
     if (!rc) rc = ctx->cuda(cudaMemset(ctx->errorFlag.p, 0, sizeof(uint32_t)), "cudaMemset(flag)");
@@ -212,6 +226,13 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readQualityStrand.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
+    for (int k = 0; k < 2; ++k)
+    {
+        if (ctx->swStream[k]) { cudaStreamSynchronize(ctx->swStream[k]); cudaStreamDestroy(ctx->swStream[k]); }
+        if (ctx->swDone[k]) cudaEventDestroy(ctx->swDone[k]);
+        ctx->swPlanes[k].release(); ctx->swEndCells[k].release();
+    }
+    if (ctx->swStart) cudaEventDestroy(ctx->swStart);
     ctx->pipeline.release();
     releaseE2e(ctx->e2e);
     delete ctx;
@@ -343,12 +364,60 @@ extern "C" int isaac_ext_ungapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, c
     return ctx->cuda(cudaGetLastError(), "ungappedKernel");
 }
 
+/// Split path (kernels3.cuh): chunks of pairs alternate between two streams so that the forward kernel of one chunk
+/// overlaps the trace+score kernel of the previous one; each stream owns one set of direction planes.
+static int gappedSplit(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *dCandidates, uint32_t cigarStride,
+                       isaac_ext_fragment_t *dFragments, uint32_t *dCigars, uint64_t *dMasks, cudaStream_t user)
+{
+    const unsigned maxLength = std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]);
+    const size_t rowWords = size_t(SW2_FLAG_WORDS) * maxLength;
+    // whole waves of 4 resident forward blocks per SM; planes of one chunk bounded to 2 GiB
+    size_t chunkPairs = size_t(ctx->smCount) * 4 * SW_BLOCK * ctx->swChunkWaves;
+    const size_t cap = std::max<size_t>(SW_BLOCK, ((size_t(2) << 30) / 4 / rowWords) / SW_BLOCK * SW_BLOCK);
+    chunkPairs = std::min(chunkPairs, cap);
+    const size_t pairs = (size_t(n) + 1) / 2;
+    const size_t stride = std::min(chunkPairs, (pairs + SW_BLOCK - 1) / SW_BLOCK * SW_BLOCK);
+    const unsigned buffers = pairs > chunkPairs ? 2 : 1;
+    for (unsigned k = 0; k < buffers; ++k)
+    {
+        CK(ctx->swPlanes[k].reserve(stride * rowWords));
+        CK(ctx->swEndCells[k].reserve(stride));
+    }
+    CK(cudaEventRecord(ctx->swStart, user));
+    for (unsigned k = 0; k < buffers; ++k) CK(cudaStreamWaitEvent(ctx->swStream[k], ctx->swStart, 0));
+    unsigned k = 0;
+    for (size_t first = 0; first < pairs; first += chunkPairs, k ^= 1u)
+    {
+        const size_t firstCandidate = first * 2;
+        const uint32_t count = uint32_t(std::min<size_t>(chunkPairs * 2, n - firstCandidate));
+        const uint32_t chunk = (count + 1) / 2;
+        swForwardKernel<<<(chunk + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
+            ctx->ref, ctx->reads, ctx->sp, count, dCandidates + firstCandidate, ctx->swPlanes[k].p, uint32_t(stride),
+            ctx->swEndCells[k].p);
+        swTraceScoreKernel<<<(count + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
+            ctx->ref, ctx->reads, ctx->sp, count, uint32_t(firstCandidate), dCandidates + firstCandidate, ctx->swPlanes[k].p,
+            uint32_t(stride), ctx->swEndCells[k].p, cigarStride, dFragments + firstCandidate, dCigars + firstCandidate * cigarStride,
+            dMasks ? dMasks + firstCandidate * ISAAC_EXT_MASK_WORDS : nullptr, ctx->errorFlag.p);
+        ctx->launches += 2;
+    }
+    for (unsigned b = 0; b < buffers; ++b)
+    {
+        CK(cudaEventRecord(ctx->swDone[b], ctx->swStream[b]));
+        CK(cudaStreamWaitEvent(user, ctx->swDone[b], 0));
+    }
+    return ctx->cuda(cudaGetLastError(), "swForwardKernel / swTraceScoreKernel");
+}
+
 extern "C" int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, uint32_t cigarStride,
                                              void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
+    if (ctx->swImpl == 3)
+        return gappedSplit(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
+                           static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
+                           static_cast<uint64_t *>(dMismatchMaskOut), cudaStream_t(cudaStream));
     const unsigned items = ctx->swImpl == 2 ? (n + 1) / 2 : n;     // the packed kernel takes two candidates per thread
     const unsigned grid = gridFor(ctx, items, SW_BLOCK, ctx->swBlocksPerSm);
     const int rc = ensureTraceback(ctx, grid, SW_BLOCK, std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]));

@@ -1,0 +1,112 @@
+// Third-generation gapped path: the packed 16x2 Smith-Waterman of sw2.cuh split into two kernels.
+//
+//   swForwardKernel      forward DP of candidate pairs (2t, 2t+1): writes the six direction planes of every row and the
+//                        end cell of both halves.  128 registers, nothing but the DP loop in its instruction footprint.
+//   swTraceScoreKernel   one thread per candidate: traceback from the planes, CIGAR assembly, updateFragmentCigar.  These
+//                        phases are chains of dependent loads and FP64 adds; with a third of the registers they run at
+//                        three times the occupancy of the fused kernel and no longer evict the DP loop from the
+//                        instruction cache (the fused kernel's top stall was "no instruction").
+//
+// The batch is cut into chunks of pairs; the plane buffers of two chunks are alive at a time so that the forward kernel
+// of chunk k+1 overlaps the trace kernel of chunk k on two streams (isaac_ext.cu).
+#pragma once
+#include "kernels2.cuh"
+
+namespace isaac_b200
+{
+
+/// plane layout of a chunk: planes[(row * SW2_FLAG_WORDS + k) * pairStride + pair]
+__global__ void __launch_bounds__(128, 4)
+swForwardKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+                const isaac_ext_candidate_t *__restrict__ candidates, uint32_t *__restrict__ planes, uint32_t pairStride,
+                uint32_t *__restrict__ endCells)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pairs = (n + 1) / 2;
+    if (t >= pairs) return;
+    const uint32_t iA = 2 * t, iB = 2 * t + 1;
+    const bool haveB = iB < n;
+    const GappedPrep pa = prepareGapped(ref, reads, candidates[iA]);
+    GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA]);
+    if (!haveB) pb.run = false;
+    const unsigned LA = pa.run ? pa.sequenceLength : 0u, LB = pb.run ? pb.sequenceLength : 0u;
+    int jj[2] = {0, 0}; unsigned type[2] = {0, 0};
+    if (LA | LB)
+    {
+        const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};
+        ResidentPairSrc src = {ref,
+                               {reads.strandCodes(pa.c.readId, pa.f.reverse), reads.strandCodes(pb.c.readId, pb.f.reverse)},
+                               {LA ? unsigned(pa.begin) : 0u, LB ? unsigned(pb.begin) : 0u},
+                               {LA ? ref.contigOffset[pa.contigId] + uint64_t(pa.strandPosition - long(pa.left)) : 0ull,
+                                LB ? ref.contigOffset[pb.contigId] + uint64_t(pb.strandPosition - long(pb.left)) : 0ull},
+                               {0, 0}, {0, 0}, reads.codesClamp()};
+        sw2Forward(src, LA, LB, sw, planes + t, pairStride, jj, type);
+    }
+    endCells[t] = uint32_t(jj[0] & 0xFF) | (type[0] << 8) | (uint32_t(jj[1] & 0xFF) << 16) | (type[1] << 24);
+}
+
+/// One thread per candidate of the chunk; 'base' = index of the chunk's first candidate in the batch (the output
+/// pointers are already advanced to it).
+__global__ void __launch_bounds__(128)
+swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n, uint32_t base,
+                   const isaac_ext_candidate_t *__restrict__ candidates, const uint32_t *__restrict__ planes, uint32_t pairStride,
+                   const uint32_t *__restrict__ endCells, uint32_t cigarStride, isaac_ext_fragment_t *__restrict__ fragments,
+                   uint32_t *__restrict__ cigars, uint64_t *__restrict__ masks, uint32_t *__restrict__ errorFlag)
+{
+    __shared__ double tables[201];
+    for (unsigned i = threadIdx.x; i < 201; i += blockDim.x) tables[i] = spGlobal.logMatch[i];
+    __syncthreads();
+    ScoreParams sp = spGlobal;
+    sp.logMatch = tables; sp.logMismatch = tables + 100;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pair = i >> 1, sh = (i & 1u) * 16u;
+    const GappedPrep p = prepareGapped(ref, reads, candidates[i]);
+    isaac_ext_fragment_t o;
+    initFragment(o, p.c, reads.readCount);
+    o.cigarOffset = (base + i) * cigarStride;      // records and CIGAR rows are addressed from the batch start
+    o.lowClipped = uint16_t(p.f.lowClipped); o.highClipped = uint16_t(p.f.highClipped); o.position = p.f.position;
+    uint64_t *mask = masks ? masks + size_t(i) * ISAAC_EXT_MASK_WORDS : nullptr;
+    if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
+    if (p.run)
+    {
+        const uint32_t cell = endCells[pair] >> sh;
+        uint32_t ops[SW_OPS_CAP + 2];
+        Sw2Walker w;
+        w.start(p.sequenceLength, int(cell & 0xFFu), (cell >> 8) & 0xFFu, ops + 1, SW_OPS_CAP);
+        // every row from L-1 down to 0 is visited once: keep the six plane words of four rows ahead in flight
+        const uint32_t *tb = planes + pair;
+        auto load = [&](int r, uint32_t (&q)[SW2_FLAG_WORDS]) {
+            const uint32_t *row = tb + size_t(max(r, 0)) * SW2_FLAG_WORDS * pairStride;
+#pragma unroll
+            for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) q[k] = (row[size_t(k) * pairStride] >> sh) & 0xFFFFu;
+        };
+        uint32_t q0[SW2_FLAG_WORDS], q1[SW2_FLAG_WORDS], q2[SW2_FLAG_WORDS], q3[SW2_FLAG_WORDS];
+        const int top = w.ii;
+        load(top, q0); load(top - 1, q1); load(top - 2, q2); load(top - 3, q3);
+        for (int r = top; r >= 0 && w.active; r -= 4)
+        {
+            w.stepRow(r, q0); load(r - 4, q0);
+            if (r >= 1) w.stepRow(r - 1, q1);
+            load(r - 5, q1);
+            if (r >= 2) w.stepRow(r - 2, q2);
+            load(r - 6, q2);
+            if (r >= 3) w.stepRow(r - 3, q3);
+            load(r - 7, q3);
+        }
+        unsigned nSw = 0, nOps = 0;
+        const unsigned ret = w.finish(nSw);
+        uint32_t *all = assembleGappedCigar(p, ops, nSw, nOps);
+        const long position = p.strandPosition + long(ret) - long(p.left);                       // GappedAligner.cpp:231,240
+        if (w.overflow || nOps > cigarStride) atomicOr(errorFlag, 1u);
+        else
+        {
+            scoreCigar(ref, reads, sp, p.c.readId, p.L, p.f.reverse, ref.contigOffset[p.contigId], position, all, nOps, o, mask);
+            for (unsigned k = 0; k < nOps; ++k) cigars[size_t(i) * cigarStride + k] = all[k];
+            o.cigarLength = uint16_t(nOps);
+        }
+    }
+    fragments[i] = o;
+}
+
+} // namespace isaac_b200
