@@ -60,7 +60,7 @@ swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const Score
     sp.logMatch = tables; sp.logMismatch = tables + 100;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t pair = i >> 1, sh = (i & 1u) * 16u;
+    const uint32_t pair = i >> 1;
     const GappedPrep p = prepareGapped(ref, reads, candidates[i]);
     isaac_ext_fragment_t o;
     initFragment(o, p.c, reads.readCount);
@@ -70,28 +70,28 @@ swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const Score
     if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
     if (p.run)
     {
-        const uint32_t cell = endCells[pair] >> sh;
+        const uint32_t cell = endCells[pair] >> ((i & 1u) * 16u);
         uint32_t ops[SW_OPS_CAP + 2];
         Sw2Walker w;
         w.start(p.sequenceLength, int(cell & 0xFFu), (cell >> 8) & 0xFFu, ops + 1, SW_OPS_CAP);
-        // every row from L-1 down to 0 is visited once: keep the six plane words of four rows ahead in flight
-        const uint32_t *tb = planes + pair;
-        auto load = [&](int r, uint32_t (&q)[SW2_FLAG_WORDS]) {
-            const uint32_t *row = tb + size_t(max(r, 0)) * SW2_FLAG_WORDS * pairStride;
-#pragma unroll
-            for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) q[k] = (row[size_t(k) * pairStride] >> sh) & 0xFFFFu;
+        // every row from L-1 down to 0 is visited once: keep the three plane words of this half of four rows ahead in flight
+        const uint32_t *tb = planes + size_t(i & 1u) * 3u * pairStride + pair;
+        const size_t rowStride = size_t(SW2_FLAG_WORDS) * pairStride;
+        auto load = [&](int r, uint32_t (&q)[3]) {
+            const uint32_t *row = tb + size_t(max(r, 0)) * rowStride;
+            q[0] = row[0]; q[1] = row[pairStride]; q[2] = row[2 * size_t(pairStride)];
         };
-        uint32_t q0[SW2_FLAG_WORDS], q1[SW2_FLAG_WORDS], q2[SW2_FLAG_WORDS], q3[SW2_FLAG_WORDS];
+        uint32_t q0[3], q1[3], q2[3], q3[3];
         const int top = w.ii;
         load(top, q0); load(top - 1, q1); load(top - 2, q2); load(top - 3, q3);
         for (int r = top; r >= 0 && w.active; r -= 4)
         {
-            w.stepRow(r, q0); load(r - 4, q0);
-            if (r >= 1) w.stepRow(r - 1, q1);
+            w.stepRow(r, q0[0], q0[1], q0[2]); load(r - 4, q0);
+            if (r >= 1) w.stepRow(r - 1, q1[0], q1[1], q1[2]);
             load(r - 5, q1);
-            if (r >= 2) w.stepRow(r - 2, q2);
+            if (r >= 2) w.stepRow(r - 2, q2[0], q2[1], q2[2]);
             load(r - 6, q2);
-            if (r >= 3) w.stepRow(r - 3, q3);
+            if (r >= 3) w.stepRow(r - 3, q3[0], q3[1], q3[2]);
             load(r - 7, q3);
         }
         unsigned nSw = 0, nOps = 0;

@@ -8,10 +8,11 @@
 //   * cell values are kept biased (value + 32768) as unsigned 16-bit.  Under the score conditions the host enforces
 //     no value leaves the int16 range, hence adding a constant to both halves is ONE 32-bit add of c * 0x10001 (no
 //     borrow can cross the halves), and the match/mismatch score of both alignments is one IMAD;
-//   * the "which operand won" flags the traceback needs are recovered without predicates: max(a,b) != a  <=>  a < b,
-//     so flag = min(max - a, 1) per half (the halves of max - a cannot borrow from each other because max >= a in
-//     both, so it is ONE 32-bit subtract that ptxas is free to place on either integer pipe, + one VIMNMX.U16x2),
-//     shifted into a per-row accumulator by an IMAD on the FMA pipe.  Five 16-lane flag masks per half and row:
+//   * the "which operand won" flags the traceback needs: max(a,b) != a  <=>  a < b.  For the three plain maxima the
+//     VIMNMX.U16x2 itself delivers "max == a" of both halves as predicates and a predicated add sets the lane's bit
+//     (sw2MaxFlag); for the two fused add-max (VIADDMNMX.U16x2 has no predicate output) flag = min(max - a, 1) per
+//     half (the halves of max - a cannot borrow from each other because max >= a in both: ONE 32-bit subtract + one
+//     VIMNMX.U16x2), shifted into a per-row accumulator.  Five 16-lane flag masks per half and row:
 //        fE  bit j: G[j] <  E[j]                 (previous row; TG and the TF of lane j+1)
 //        fF  bit j: max(G[j],E[j]) < F[j]        (previous row; TG)
 //        fAB bit j: max(G,E)[j-1]-open < F[j-1]-ext   (TF of lane j)
@@ -21,7 +22,8 @@
 //     once), into the SIX bit planes the traceback reads: (tg1,tg2) (te1,te2) (tf1,tf2), plane 1 = "direction is E",
 //     plane 2 = "direction is F" of the three direction matrices TG/TE/TF -- including the reference's
 //     _mm_max_epi16-on-byte-pairs coupling of lanes 2p/2p+1 in TG (:197).  6 words per row and thread pair are stored
-//     (12 bytes per alignment row, what the reference's 3 x 16 direction bytes compress to).
+//     (12 bytes per alignment row, what the reference's 3 x 16 direction bytes compress to), three per half, each
+//     holding plane 1 in its low and plane 2 in its high 16 bits.
 #pragma once
 #include "device_types.cuh"
 #include "sw.cuh"
@@ -50,6 +52,23 @@ __device__ __forceinline__ Sw2Consts makeSw2Consts(const SwScores s)
 }
 
 constexpr unsigned SW2_FLAG_WORDS = 6;
+
+/// max(a, b) of both halves, and bit J (half A) / bit 16+J (half B) of 'flags' set where the maximum is not a, i.e. a < b.
+/// ptxas folds the max and the two equality tests into ONE VIMNMX.U16x2 with two predicate outputs; each flag then
+/// costs one predicated add instead of subtract + min + shift-add.
+template <int J>
+__device__ __forceinline__ uint32_t sw2MaxFlag(const uint32_t a, const uint32_t b, uint32_t &flags)
+{
+    uint32_t m;
+    asm("{.reg .pred pu, pv;\n\t.reg .u16 rs0, rs1, rs2, rs3;\n\t"
+        "max.u16x2 %0, %2, %3;\n\tmov.b32 {rs0, rs1}, %0;\n\tmov.b32 {rs2, rs3}, %2;\n\t"
+        "setp.eq.u16 pv, rs0, rs2;\n\tsetp.eq.u16 pu, rs1, rs3;\n\t"
+        "@!pv or.b32 %1, %1, %4;\n\t@!pu or.b32 %1, %1, %5;}"
+        : "=r"(m), "+r"(flags) : "r"(a), "r"(b), "n"(1u << J), "n"(0x10000u << J));
+    return m;
+}
+
+template <int J> struct Sw2Lane { static constexpr int value = J; };
 
 /// End-cell scan of one half (:349-379): lanes 15..0, matrices G,E,F in that order, strict '>'.
 __device__ __forceinline__ void sw2ScanEnd(const uint32_t (&G)[16], const uint32_t (&E)[16], const uint32_t (&F)[16],
@@ -84,7 +103,10 @@ __device__ __forceinline__ void sw2Planes(uint32_t fE, uint32_t fF, uint32_t fAB
     // TF (:142-167): 2 if a < b, else 1 if G[j-1] < E[j-1]; lane 0 is forced to 0
     const uint32_t tf2 = fAB & 0xFFFEFFFEu;
     const uint32_t tf1 = ~fAB & ((fE << 1) & 0xFFFEFFFEu);
-    p[0] = tg1; p[1] = tg2; p[2] = te1; p[3] = te2; p[4] = tf1; p[5] = tf2;
+    // stored per half: words 0..2 = (tg1 | tg2 << 16), (te1 | te2 << 16), (tf1 | tf2 << 16) of half A, words 3..5 of half B,
+    // so that a walk reads three words per row and finds both planes of its state in one of them
+    p[0] = __byte_perm(tg1, tg2, 0x5410); p[1] = __byte_perm(te1, te2, 0x5410); p[2] = __byte_perm(tf1, tf2, 0x5410);
+    p[3] = __byte_perm(tg1, tg2, 0x7632); p[4] = __byte_perm(te1, te2, 0x7632); p[5] = __byte_perm(tf1, tf2, 0x7632);
 }
 
 /// One traceback in progress (one half of a pair).
@@ -109,12 +131,13 @@ struct Sw2Walker
         overflow = false; active = L != 0;
         if (active && jj > 0) push(unsigned(jj), 1);                           // :388-391
     }
-    /// all steps of this walk that happen in row 'row' (:392-423); p = the 16 lanes of this half of the six planes
-    __device__ __forceinline__ void stepRow(int row, const unsigned (&p)[SW2_FLAG_WORDS])
+    /// all steps of this walk that happen in row 'row' (:392-423); tg/te/tf = the three plane words of this half
+    /// (plane 1 in the low, plane 2 in the high 16 bits)
+    __device__ __forceinline__ void stepRow(int row, const uint32_t tg, const uint32_t te, const uint32_t tf)
     {
         if (!active || ii != row) return;
         // the overwhelmingly common step: on the diagonal and staying there
-        if (type == 0 && (((p[0] | p[1]) >> jj) & 1u) == 0)
+        if (type == 0 && (((tg | (tg >> 16)) >> jj) & 1u) == 0)
         {
             ++opLength; --ii;
             active = ii >= 0;
@@ -123,9 +146,8 @@ struct Sw2Walker
         while (active && ii == row)
         {
             ++opLength;
-            const unsigned p1 = type == 0 ? p[0] : (type == 1 ? p[2] : p[4]);
-            const unsigned p2 = type == 0 ? p[1] : (type == 1 ? p[3] : p[5]);
-            const unsigned next = ((p1 >> jj) & 1u) | (((p2 >> jj) & 1u) << 1);
+            const uint32_t p = (type == 0 ? tg : (type == 1 ? te : tf)) >> jj;
+            const unsigned next = (p & 1u) | ((p >> 15) & 2u);
             if (next != type) { push(opLength, type); opLength = 0; }
             if (type == 0) { --ii; } else if (type == 1) { ++jj; } else { --ii; --jj; }
             type = next;
@@ -161,11 +183,8 @@ __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb
     };
     auto process = [&](int r, const uint32_t (&w)[SW2_FLAG_WORDS]) {
         if (r < 0) return;
-        unsigned lo[SW2_FLAG_WORDS], hi[SW2_FLAG_WORDS];
-#pragma unroll
-        for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) { lo[k] = w[k] & 0xFFFFu; hi[k] = w[k] >> 16; }
-        a.stepRow(r, lo);
-        b.stepRow(r, hi);
+        a.stepRow(r, w[0], w[1], w[2]);
+        b.stepRow(r, w[3], w[4], w[5]);
     };
     uint32_t w0[SW2_FLAG_WORDS], w1[SW2_FLAG_WORDS], w2[SW2_FLAG_WORDS], w3[SW2_FLAG_WORDS];
     load(top, w0); load(top - 1, w1); load(top - 2, w2); load(top - 3, w3);
@@ -204,64 +223,54 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
         D[0] = src.d2(i + 15);
         const uint32_t Q = src.q2(i);
         uint32_t fE = 0, fF = 0, fAB = 0, fGF = 0, fHE = 0;
-        uint32_t mCur = __vmaxu2(G[15], E[15]);
-        uint32_t xE = mCur - G[15];
+        uint32_t mCur = sw2MaxFlag<15>(G[15], E[15], fE);
         uint32_t hOnext = 0, nEnext = 0;
-#pragma unroll
-        for (int j = 15; j >= 0; --j)
-        {
+        auto lane = [&](auto laneTag) {
+            constexpr int j = decltype(laneTag)::value;
             // ---- F of lane j from lane j-1 of the previous row (:132-173)
-            uint32_t nF, xAB, mPrev = 0, xEprev = 0;
+            uint32_t nF, mPrev = 0;
             if (j > 0)
             {
-                mPrev = __vmaxu2(G[j - 1], E[j - 1]);
-                xEprev = mPrev - G[j - 1];
+                constexpr int jm = j > 0 ? j - 1 : 0;
+                mPrev = sw2MaxFlag<jm>(G[jm], E[jm], fE);
                 const uint32_t a = mPrev + c.negOpen32;
-                nF = __viaddmax_u16x2(F[j - 1], c.negExt16x2, a);
-                xAB = nF - a;
+                nF = __viaddmax_u16x2(F[jm], c.negExt16x2, a);
+                fAB = fAB * 2u + __vminu2(nF - a, 0x00010001u);
             }
-            else { nF = c.init2; xAB = 0; }                                       // :167, :173
+            else { nF = c.init2; fAB = fAB * 2u; }                                // :167, :173
             // ---- G of lane j from the same lane (:176-190, :230-244)
-            const uint32_t g = __vmaxu2(mCur, F[j]);
-            const uint32_t xF = g - mCur;
+            const uint32_t g = sw2MaxFlag<j>(mCur, F[j], fF);
             const uint32_t t = __vminu2(D[j] ^ Q, 0x00010001u);
             const uint32_t nG = g + c.match32 + t * uint32_t(c.delta);
             // ---- E of lane j from lane j+1 of THIS row (:261-297)
-            uint32_t nE, xHE;
+            uint32_t nE;
             if (j < 15)
             {
                 nE = __viaddmax_u16x2(nEnext, c.negExt16x2, hOnext);
-                xHE = nE - hOnext;
+                fHE = fHE * 2u + __vminu2(nE - hOnext, 0x00010001u);
             }
-            else { nE = c.init2; xHE = 0; }
-            const uint32_t h = __vmaxu2(nG, nF);
-            const uint32_t xGF = h - nG;
+            else { nE = c.init2; fHE = fHE * 2u; }
+            const uint32_t h = sw2MaxFlag<j>(nG, nF, fGF);
             hOnext = h + c.negOpen32;
             nEnext = nE;
-            // ---- flags, bit j of each half
-            fE = fE * 2u + __vminu2(xE, 0x00010001u);
-            fF = fF * 2u + __vminu2(xF, 0x00010001u);
-            fAB = fAB * 2u + __vminu2(xAB, 0x00010001u);
-            fGF = fGF * 2u + __vminu2(xGF, 0x00010001u);
-            fHE = fHE * 2u + __vminu2(xHE, 0x00010001u);
             G[j] = nG; E[j] = nE; F[j] = nF;
-            mCur = mPrev; xE = xEprev;
-        }
+            mCur = mPrev;
+        };
+        lane(Sw2Lane<15>()); lane(Sw2Lane<14>()); lane(Sw2Lane<13>()); lane(Sw2Lane<12>());
+        lane(Sw2Lane<11>()); lane(Sw2Lane<10>()); lane(Sw2Lane<9>()); lane(Sw2Lane<8>());
+        lane(Sw2Lane<7>()); lane(Sw2Lane<6>()); lane(Sw2Lane<5>()); lane(Sw2Lane<4>());
+        lane(Sw2Lane<3>()); lane(Sw2Lane<2>()); lane(Sw2Lane<1>()); lane(Sw2Lane<0>());
         uint32_t planes[SW2_FLAG_WORDS];
         sw2Planes(fE, fF, fAB, fGF, fHE, planes);
         uint32_t *row = tb + size_t(i) * SW2_FLAG_WORDS * tbStride;                                      // :306-308
 #pragma unroll
         for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) row[k * tbStride] = planes[k];
-        if (LA != LB)
+        if (i + 1 == LA || i + 1 == LB)                        // last row of a half: its end cell (one copy of the scan)
         {
-            if (i + 1 == LA) sw2ScanEnd(G, E, F, 0, jj[0], type[0]);
-            if (i + 1 == LB) sw2ScanEnd(G, E, F, 1, jj[1], type[1]);
+#pragma unroll 1
+            for (unsigned half = 0; half < 2; ++half)
+                if (i + 1 == (half ? LB : LA)) sw2ScanEnd(G, E, F, half, jj[half], type[half]);
         }
-    }
-    if (LA == LB && LA)
-    {
-        sw2ScanEnd(G, E, F, 0, jj[0], type[0]);
-        sw2ScanEnd(G, E, F, 1, jj[1], type[1]);
     }
 }
 

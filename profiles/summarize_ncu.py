@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: headline metrics plus the kernel split into regions of equal execution count (loop bodies)
-with their share of executed instructions and of stall samples.  Usage: summarize_ncu.py file.ncu-rep"""
+with their share of executed instructions and of stall samples.
+Usage: summarize_ncu.py file.ncu-rep [kernel-name-regex]"""
 import csv
 import io
 import subprocess
 import sys
 
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+flt = ["-k", "regex:" + sys.argv[2]] if len(sys.argv) > 2 else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
 want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -24,7 +26,7 @@ for r in rows[2:]:
     for i, n in enumerate(h):
         if "issue_stalled" in n and n.endswith("per_warp_active.pct") and float(r[i] or 0) > 3:
             print("  stall %-56s %s" % (n.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", ""), r[i]))
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
 h = rows[hi]
