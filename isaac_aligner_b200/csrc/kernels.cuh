@@ -130,11 +130,13 @@ __device__ __forceinline__ void initFragment(isaac_ext_fragment_t &o, const isaa
 }
 
 /// K1: one candidate per thread.
-__global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+__global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
                                const isaac_ext_candidate_t *__restrict__ candidates,
                                isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
                                uint64_t *__restrict__ masks)
 {
+    __shared__ double tables[201];
+    const ScoreParams sp = stageScoreTables(spGlobal, tables);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const isaac_ext_candidate_t c = candidates[i];
@@ -177,11 +179,13 @@ struct ResidentBaseSrc
 constexpr unsigned SW_OPS_CAP = 64;
 
 /// K2+K4: one candidate per thread: clip, banded Smith-Waterman, traceback, re-score the gapped CIGAR.
-__global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+__global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
                              const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
                              isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
                              uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
 {
+    __shared__ double tables[201];
+    const ScoreParams sp = stageScoreTables(spGlobal, tables);
     const size_t tbStride = size_t(gridDim.x) * blockDim.x;
     uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
     const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};

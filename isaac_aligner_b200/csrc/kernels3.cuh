@@ -54,10 +54,7 @@ swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const Score
                    uint32_t *__restrict__ cigars, uint64_t *__restrict__ masks, uint32_t *__restrict__ errorFlag)
 {
     __shared__ double tables[201];
-    for (unsigned i = threadIdx.x; i < 201; i += blockDim.x) tables[i] = spGlobal.logMatch[i];
-    __syncthreads();
-    ScoreParams sp = spGlobal;
-    sp.logMatch = tables; sp.logMismatch = tables + 100;
+    const ScoreParams sp = stageScoreTables(spGlobal, tables);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t pair = i >> 1;

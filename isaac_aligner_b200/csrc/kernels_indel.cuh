@@ -61,9 +61,11 @@ struct IndelView
     }
 };
 
-__global__ void simpleIndelKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
+__global__ void simpleIndelKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
                                   const IndelTask *__restrict__ tasks, IndelResult *__restrict__ results)
 {
+    __shared__ double tables[201];
+    const ScoreParams sp = stageScoreTables(spGlobal, tables);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const IndelTask t = tasks[i];

@@ -96,6 +96,17 @@ __device__ __forceinline__ uint64_t referenceCodes16(const ReferenceView &ref, u
     return spread2to4(two) | (spread1to4(n16) * uint64_t(CODE_REF_N));
 }
 
+/// The score tables in shared memory: CigarScorer reads them with ld.shared.  Every thread of the block must call this
+/// before anything else (barrier inside); returns the parameters with the table pointers redirected.
+__device__ __forceinline__ ScoreParams stageScoreTables(const ScoreParams &global, double (&tables)[201])
+{
+    for (unsigned i = threadIdx.x; i < 201; i += blockDim.x) tables[i] = global.logMatch[i];
+    __syncthreads();
+    ScoreParams sp = global;
+    sp.logMatch = tables; sp.logMismatch = tables + 100;
+    return sp;
+}
+
 /// AlignerBase::updateFragmentCigar (AlignerBase.cpp:121-227) as a walker over the read, 16 bases (one 64-bit word of
 /// 4-bit codes) per step:
 ///   * word level: the CIGAR operations overlapping the word are turned into one-bit-per-nibble masks (mismatch,
@@ -114,6 +125,7 @@ struct CigarScorer
     double lp;
     unsigned L, nOps, k, remaining, op;
     unsigned matchCount, mismatchCount, matchesInARow, gapCount, editDistance, sws, run;
+    uint32_t tableShared;       // shared-window address of the [0,100) match, [100,200) mismatch, [200] = 0.0 table
     bool fresh;
 
     __device__ __forceinline__ void start(const ReferenceView &r, const ReadSetView &reads, const ScoreParams &s, unsigned readId,
@@ -124,6 +136,7 @@ struct CigarScorer
         cigar = ops; mask = maskOut; g0 = contigOffset + uint64_t(strandPosition); g = g0; lp = 0.0;
         L = length; nOps = n; k = 0; remaining = 0; op = ISAAC_EXT_CIGAR_SOFT_CLIP; fresh = false;
         matchCount = mismatchCount = matchesInARow = gapCount = editDistance = sws = run = 0;
+        tableShared = uint32_t(__cvta_generic_to_shared(s.logMatch));
     }
 
     __device__ __forceinline__ void stepWord(const unsigned w)
@@ -192,20 +205,37 @@ struct CigarScorer
         }
         // ---- the sequential part: FP64 sum and longest run of matches
         const uint4 qv = *reinterpret_cast<const uint4 *>(quality + P0);
-        const unsigned qw[4] = {qv.x, qv.y, qv.z, qv.w};
-        const double *table = sp->logMatch;                          // [0,100) match, [100,200) mismatch, [200] = 0.0
+        unsigned qw[4] = {qv.x, qv.y, qv.z, qv.w};
+        // Inserted bases and the positions of the last word past the end of the read take table entry 200 (+0.0; the
+        // sum never is -0.0, so it is unchanged bit for bit): patch their quality byte once per word instead of testing
+        // every base.  Positions past the end also reset the run, after the last base that can raise the maximum.
+        const uint64_t zero = skip | (ONES & ~valid);
+        notm |= ONES & ~valid;
+        if (zero)
+        {
+#pragma unroll
+            for (unsigned k = 0; k < 4; ++k)
+            {
+                const uint32_t nib = uint32_t(zero >> (16u * k)) & 0x1111u;                  // bits 0,4,8,12 -> 0,8,16,24
+                const uint32_t x = (nib & 0x0011u) | ((nib & 0x1100u) << 8);
+                const uint32_t bytes = ((x & 0x00010001u) | ((x & 0x00100010u) << 4)) * 0xFFu;
+                qw[k] = (qw[k] & ~bytes) | (bytes & 0xC8C8C8C8u);
+            }
+        }
+        const uint32_t mismLo = uint32_t(mism), mismHi = uint32_t(mism >> 32);
+        const uint32_t resetLo = uint32_t(notm | bnd), resetHi = uint32_t((notm | bnd) >> 32);
+        const uint32_t notmLo = uint32_t(notm), notmHi = uint32_t(notm >> 32);
 #pragma unroll
         for (unsigned b = 0; b < 16; ++b)
         {
-            if (b < cnt)
-            {
-                const unsigned q = (qw[b >> 2] >> ((b & 3u) * 8u)) & 0xFFu;
-                const unsigned m = unsigned(mism >> (4u * b)) & 1u, s = unsigned(skip >> (4u * b)) & 1u;
-                lp += table[s ? 200u : q + 100u * m];
-                if (unsigned(bnd >> (4u * b)) & 1u) run = 0;
-                if (unsigned(notm >> (4u * b)) & 1u) run = 0;
-                else { ++run; matchesInARow = max(matchesInARow, run); }
-            }
+            const uint32_t bit = 1u << (4u * (b & 7u));
+            unsigned idx = (qw[b >> 2] >> ((b & 3u) * 8u)) & 0xFFu;
+            if ((b < 8 ? mismLo : mismHi) & bit) idx += 100u;
+            double v;
+            asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tableShared + idx * 8u));
+            lp += v;
+            if ((b < 8 ? resetLo : resetHi) & bit) run = 0;
+            if (!((b < 8 ? notmLo : notmHi) & bit)) { ++run; matchesInARow = max(matchesInARow, run); }
         }
     }
 
