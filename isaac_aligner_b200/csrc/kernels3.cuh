@@ -12,6 +12,16 @@
 #pragma once
 #include "kernels2.cuh"
 
+// rows of direction planes a walk keeps in flight, and resident blocks per SM the trace kernel is compiled for
+// (measured on B200, 10M x 150 bp: 4 rows beat 8, 12 and 16 rows, which cost occupancy; 12 blocks = 40 registers with
+// a few spilled words beat 10 and 8 blocks: the kernel waits on loads, not on the issue slots)
+#ifndef ISAAC_TRACE_ROWS_AHEAD
+#define ISAAC_TRACE_ROWS_AHEAD 4
+#endif
+#ifndef ISAAC_TRACE_MIN_BLOCKS
+#define ISAAC_TRACE_MIN_BLOCKS 12
+#endif
+
 namespace isaac_b200
 {
 
@@ -47,7 +57,7 @@ swForwardKernel(const ReferenceView ref, const ReadSetView reads, const ScorePar
 
 /// One thread per candidate of the chunk; 'base' = index of the chunk's first candidate in the batch (the output
 /// pointers are already advanced to it).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, ISAAC_TRACE_MIN_BLOCKS)
 swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n, uint32_t base,
                    const isaac_ext_candidate_t *__restrict__ candidates, const uint32_t *__restrict__ planes, uint32_t pairStride,
                    const uint32_t *__restrict__ endCells, uint32_t cigarStride, isaac_ext_fragment_t *__restrict__ fragments,
@@ -71,25 +81,26 @@ swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const Score
         uint32_t ops[SW_OPS_CAP + 2];
         Sw2Walker w;
         w.start(p.sequenceLength, int(cell & 0xFFu), (cell >> 8) & 0xFFu, ops + 1, SW_OPS_CAP);
-        // every row from L-1 down to 0 is visited once: keep the three plane words of this half of four rows ahead in flight
+        // every row from L-1 down to 0 is visited once: keep the three plane words of this half of AHEAD rows in flight
         const uint32_t *tb = planes + size_t(i & 1u) * 3u * pairStride + pair;
         const size_t rowStride = size_t(SW2_FLAG_WORDS) * pairStride;
         auto load = [&](int r, uint32_t (&q)[3]) {
             const uint32_t *row = tb + size_t(max(r, 0)) * rowStride;
             q[0] = row[0]; q[1] = row[pairStride]; q[2] = row[2 * size_t(pairStride)];
         };
-        uint32_t q0[3], q1[3], q2[3], q3[3];
+        constexpr int AHEAD = ISAAC_TRACE_ROWS_AHEAD;
+        uint32_t q[AHEAD][3];
         const int top = w.ii;
-        load(top, q0); load(top - 1, q1); load(top - 2, q2); load(top - 3, q3);
-        for (int r = top; r >= 0 && w.active; r -= 4)
+#pragma unroll
+        for (int k = 0; k < AHEAD; ++k) load(top - k, q[k]);
+        for (int r = top; r >= 0 && w.active; r -= AHEAD)
         {
-            w.stepRow(r, q0[0], q0[1], q0[2]); load(r - 4, q0);
-            if (r >= 1) w.stepRow(r - 1, q1[0], q1[1], q1[2]);
-            load(r - 5, q1);
-            if (r >= 2) w.stepRow(r - 2, q2[0], q2[1], q2[2]);
-            load(r - 6, q2);
-            if (r >= 3) w.stepRow(r - 3, q3[0], q3[1], q3[2]);
-            load(r - 7, q3);
+#pragma unroll
+            for (int k = 0; k < AHEAD; ++k)
+            {
+                if (r >= k) w.stepRowConverged(r - k, q[k][0], q[k][1], q[k][2]);
+                load(r - k - AHEAD, q[k]);
+            }
         }
         unsigned nSw = 0, nOps = 0;
         const unsigned ret = w.finish(nSw);

@@ -154,6 +154,31 @@ struct Sw2Walker
             active = ii >= 0 && jj >= 0 && jj <= 15;
         }
     }
+    /// stepRow for a kernel in which every lane of the warp walks its own alignment through the same rows: when all
+    /// lanes stay on the diagonal the row costs a handful of instructions; otherwise all lanes run the same general
+    /// step once (no per-lane slow path for the others to wait for) and only a walk in a deletion iterates again.
+    __device__ __forceinline__ void stepRowConverged(int row, const uint32_t tg, const uint32_t te, const uint32_t tf)
+    {
+        if (!active || ii != row) return;
+        const bool diagonal = type == 0 && (((tg | (tg >> 16)) >> jj) & 1u) == 0;
+        if (__all_sync(__activemask(), diagonal))
+        {
+            ++opLength; --ii;
+            active = ii >= 0;
+            return;
+        }
+        do
+        {
+            ++opLength;
+            const uint32_t p = (type == 0 ? tg : (type == 1 ? te : tf)) >> jj;
+            const unsigned next = (p & 1u) | ((p >> 15) & 2u);
+            if (next != type) { push(opLength, type); opLength = 0; }
+            ii -= int(type != 1);
+            jj += int(type == 1) - int(type == 2);
+            type = next;
+            active = ii >= 0 && jj >= 0 && jj <= 15;
+        } while (active && ii == row);
+    }
     /// :425-453: flush, strip a deletion at either end; \return the stripped leading deletion, ops[0..nOps) head first
     __device__ __forceinline__ unsigned finish(unsigned &nOps)
     {
