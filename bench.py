@@ -364,7 +364,8 @@ def run_b200(args):
     ungapped_gbs = (n * per_cand + reads.cluster_count * 2 * per_read) / (ms_ungapped * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gapped_pass"]["dram_bytes_per_launch"]
+        entry = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["gapped_pass"]     # one ncu --set full capture
+        traffic = int(entry["dram_bytes_per_launch"] * float(n) / entry["candidates"]) if L == 150 else None
     except (OSError, KeyError, ValueError):
         pass
     # ---- CPU baseline on a bounded sample, same box
