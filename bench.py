@@ -28,6 +28,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+# Only the JSON line may reach stdout: NCCL and other libraries print there (e.g. "NCCL version ..."), so file
+# descriptor 1 points at stderr for the whole run and emit() writes the line to the saved descriptor.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_STDOUT_FD, (line + "\n").encode())
+
+
 OPS_PER_CELL = 23          # F 7 + G 8 + E 8 integer operations per (G,E,F) cell
 BAND = 16
 
@@ -141,7 +151,7 @@ def run_reference(args):
     gcups, sec, kind, cores = cpu_arm(args, genome, reads, cand, config, args.steps, args.warmup)
     sample = "%d of %d candidates per step (same generator, ungapped + gapped per candidate), %d host threads" % (
         n, args.candidates, cores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "banded_sw_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
@@ -245,7 +255,8 @@ def run_b200(args):
     L, n, stride = args.read_length, args.candidates, args.cigar_stride
     genome, reads, cand = make_workload(args, rank, n)
     n = len(cand)
-    config = Config.default(max_read_length=2 * L, device=local_rank)
+    # the ranks of one box share its host cores: each context gets its share of the host threads
+    config = Config.default(max_read_length=2 * L, device=local_rank, host_threads=max(1, (os.cpu_count() or 1) // world))
     ctx = capi.Context(config)
     ctx.set_reference(genome)
     ctx.set_reads(reads)
@@ -381,7 +392,7 @@ def run_b200(args):
         pairs_line, _, _ = pairs_pipeline_gpu(ctx, preads, pmb, ptls, max(1, args.steps // 2), 1)
         pairs_line["cpu_baseline"] = pairs_pipeline_cpu(pgenome, preads, pmb, ptls, config, 4000 * cores)
 
-    print(json.dumps({
+    emit(json.dumps({
         "metric": "banded_sw_gcups", "value": world * cells / (ms_per_step * 1e-3) / 1e9, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
@@ -437,7 +448,7 @@ def run_pairs(args):
         runs = [pairs_pipeline_cpu(genome, reads, mb, tls, config, reads.cluster_count) for _ in range(args.warmup + args.steps)][args.warmup:]
         v = float(np.mean([r["pairs_per_s"] for r in runs]))
         sample = "%d pairs per step of the same generator, %d host threads" % (reads.cluster_count, cores)
-        print(json.dumps({"impl": "reference", "metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        emit(json.dumps({"impl": "reference", "metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": reads.cluster_count / v * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16+f64", "data": "synthetic",
                           "config": pairs_config(args, n_pairs),
@@ -451,7 +462,8 @@ def run_pairs(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     genome, reads, mb, tls = make_pairs_workload(args, rank, n_pairs)
-    config = Config.default(max_read_length=2 * args.read_length, device=local_rank)
+    config = Config.default(max_read_length=2 * args.read_length, device=local_rank,
+                            host_threads=max(1, (os.cpu_count() or 1) // world))
     ctx = capi.Context(config)
     ctx.set_reference(genome)
     ctx.set_reads(reads)
@@ -471,7 +483,7 @@ def run_pairs(args):
     h2d = len(mb.matches) * 16 + reads.bcl.size * 0 + len(req) * 32
     d2h = flat.fragments.size * 64 + flat.cigars.size * 4
     v = world * n_pairs / (ms * 1e-3)
-    print(json.dumps({"metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+    emit(json.dumps({"metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "int16+f64", "data": "synthetic", "config": pairs_config(args, n_pairs),
                       "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

@@ -45,8 +45,7 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
     if (wordsOut) *wordsOut = 0;
     if (!n) return ISAAC_EXT_OK;
     if (!candidates || !fragmentsOut || !poolOut || !wordsOut) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
-    int rc = validateCandidates(ctx, n, candidates);
-    if (rc) return rc;
+    int rc = ISAAC_EXT_OK;
     CK(cudaSetDevice(ctx->device));
     if (!st.ready)
     {
@@ -75,6 +74,9 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
     auto enqueue = [&](uint32_t k) -> int {
         const int b = k & 1;
         const uint32_t m = chunkSize(k);
+        // the host checks a chunk while the device works on the previous ones; a bad candidate fails the whole call
+        const int bad = validateCandidates(ctx, m, candidates + size_t(k) * E2E_CHUNK);
+        if (bad) { cudaDeviceSynchronize(); return bad; }
         if (k >= 2) CK(cudaStreamWaitEvent(st.sH, st.evD[b], 0));          // the buffer set is free once chunk k-2 left the device
         CK(cudaMemcpyAsync(st.dCand[b].p, candidates + size_t(k) * E2E_CHUNK, size_t(m) * sizeof(isaac_ext_candidate_t), cudaMemcpyHostToDevice, st.sH));
         CK(cudaEventRecord(st.evH[b], st.sH));
