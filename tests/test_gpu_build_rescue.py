@@ -112,3 +112,35 @@ def test_rescue_low_complexity_hits_the_candidate_cap(capi):
         assert_flat_equal(got, want, "rescue cap cuda vs " + chk.kind)
     assert (np.diff(got.begin.astype(np.int64)) == 1000).any()
     ctx.close()
+
+
+@pytest.mark.parametrize("indel_rate", [5e-4, 1e-2])
+def test_baseline_config0_full_size_bit_exact(capi, indel_rate):
+    """BASELINE.json configs[0] at its full size (100 000 simulated 2x150 pairs on the 5 Mbp genome, the generator and seeds
+    of bench.py) and the indel-rich variant of configs[3]: every fragment of build + rescue equals both CPU checkers"""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch
+    from isaac_aligner_b200.types import ReadSet
+    L, n_pairs = 150, 100_000
+    genome = synth.make_genome(5_000_000, n_contigs=1, seed=synth.SEED_G5)
+    sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 7, indel_rate=indel_rate,
+                               seed_offsets=synth.auto_seed_offsets(L))
+    matches, begin = synth.make_matches(sim, genome, seed=synth.SEED_READS + 8, decoy_rate=0.2)
+    reads = ReadSet(sim.bcl, (L, L))
+    mb = MatchBatch(matches, begin, synth.seed_table(sim), with_gaps=True)
+    cfg = Config.default(BWA_SCORES, max_read_length=2 * L)
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    tls = Tls.make()
+    built = ctx.build_fragments(mb)
+    req = synth.rescue_policy(built.fragments, built.begin, n_pairs)
+    rescued = ctx.rescue_shadows(tls, req)
+    g = oracle_lib.GenomeHolder(genome)
+    for chk in checkers():
+        assert_flat_equal(built, oracle_lib.build_fragments(chk, g, reads, cfg, mb, threads=8), "config0 build vs " + chk.kind)
+        assert_flat_equal(rescued, oracle_lib.rescue_shadows(chk, g, reads, cfg, tls, req, threads=8),
+                          "config0 rescue vs " + chk.kind)
+    assert built.flags.mean() > 0.95 and rescued.flags.mean() > 0.8
+    assert (built.fragments["gapCount"] > 0).sum() > (2000 if indel_rate > 1e-3 else 200)
+    ctx.close()
