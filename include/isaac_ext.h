@@ -193,6 +193,36 @@ typedef struct isaac_ext_rescue_result {
     uint64_t cigarWords;
 } isaac_ext_rescue_result_t;
 
+/* What alignment::TemplateBuilder is constructed / called with beyond isaac_ext_config_t (TemplateBuilder.hh:68-82,
+ * MatchSelector.cpp:330-334). */
+typedef struct isaac_ext_template_options {
+    uint32_t scatterRepeats;         /* --scatter-repeats                                                        */
+    int32_t  dodgyAlignmentScore;    /* -1 = DODGY_ALIGNMENT_SCORE_UNALIGNED, 255 = _UNKNOWN, else numeric (:60-61) */
+    uint32_t mapqThreshold;          /* --mapq-threshold                                                          */
+    uint32_t pad;
+} isaac_ext_template_options_t;
+
+/* alignment::BamTemplate of one cluster (BamTemplate.hh:40-137) next to its two fragment records. */
+typedef struct isaac_ext_template {
+    uint32_t alignmentScore;             /* BamTemplate::getAlignmentScore(), 0xFFFFFFFF = unknown (-1U)          */
+    uint32_t fragmentAlignmentScore[2];  /* FragmentMetadata::alignmentScore of read 1 / read 2                   */
+    uint8_t  properPair;
+    uint8_t  built;                      /* buildFragments() && buildTemplate() (MatchSelector.cpp:323-334)       */
+    uint8_t  hadFragments;               /* buildFragments()                                                       */
+    uint8_t  pad;
+} isaac_ext_template_t;
+
+/* Owned by the context, valid until its next call.  fragments[cluster * readCount + readIndex] =
+ * BamTemplate::getFragmentMetadata(readIndex); unaligned / no-match records keep the reference's field values
+ * (contigId 0x7FFFFF = ReferencePosition::MAX_CONTIG_ID for "no match", FragmentMetadata.hh:258-260). */
+typedef struct isaac_ext_template_result {
+    const isaac_ext_template_t *templates;   /* clusterCount                                                  */
+    const isaac_ext_fragment_t *fragments;   /* clusterCount * readCount                                      */
+    const uint32_t *cigars;
+    uint64_t cigarWords;
+    uint64_t rescueRequests;                 /* ShadowAligner::rescueShadow calls the tile needed             */
+} isaac_ext_template_result_t;
+
 /* ---- life cycle ----------------------------------------------------------------------------- */
 int  isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx **ctx);
 void isaac_ext_destroy(isaac_ext_ctx *ctx);
@@ -219,6 +249,15 @@ int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t 
 /* ShadowAligner::rescueShadow for every request against the resident read set (ShadowAligner.cpp:155-291). */
 int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t requestCount,
                              const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result);
+
+/* SURVEY 8(f) #1, the caller of the two: TemplateBuilder::buildFragments + buildTemplate for every cluster of the resident
+ * read set (MatchSelector.cpp:323-334; TemplateBuilder.cpp:97-1089: pickBestPair / locateBestPair /
+ * buildPairedEndTemplate / buildDisjoinedTemplate / rescueShadow / scoreDisjoinedTemplate / updateMappingScore, MAPQ
+ * threshold filter).  One isaac_ext_build_fragments pass, the rescue requests the templates need in one
+ * isaac_ext_rescue_shadows pass, then pair selection and mapping scores per cluster on the host threads.  The
+ * rest-of-genome correction is computed from the resident reference and read lengths (RestOfGenomeCorrection.hh:45-57). */
+int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                              const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result);
 
 /* ---- micro entry points (unit parity + kernel benchmarks) ------------------------------------ */
 

@@ -79,3 +79,38 @@ def copy_result(res, n_groups, begin_field, flag_field, n_flags):
 
     return FlatFragments(arr(res.fragments, FRAGMENT_DTYPE, nf), arr(getattr(res, begin_field), np.uint64, n_groups + 1),
                          arr(res.cigars, np.uint32, nc), arr(getattr(res, flag_field), np.uint8, n_flags))
+
+
+# isaac_ext_template_t, 16 bytes
+TEMPLATE_DTYPE = np.dtype([("alignmentScore", "<u4"), ("fragmentAlignmentScore", "<u4", (2,)), ("properPair", "u1"),
+                           ("built", "u1"), ("hadFragments", "u1"), ("pad", "u1")])
+assert TEMPLATE_DTYPE.itemsize == 16
+
+DODGY_ALIGNMENT_SCORE_UNKNOWN, DODGY_ALIGNMENT_SCORE_UNALIGNED = 255, -1      # TemplateBuilder.hh:60-61
+
+
+class TemplateOptions(ctypes.Structure):
+    """isaac_ext_template_options_t (isaac-align defaults: --scatter-repeats 0, --dodgy-alignment-score 0, --mapq-threshold 0)"""
+    _fields_ = [("scatterRepeats", ctypes.c_uint32), ("dodgyAlignmentScore", ctypes.c_int32),
+                ("mapqThreshold", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
+
+    @classmethod
+    def make(cls, scatter_repeats=False, dodgy=0, mapq_threshold=0):
+        return cls(1 if scatter_repeats else 0, dodgy, mapq_threshold, 0)
+
+
+class TemplateResult(ctypes.Structure):
+    """isaac_ext_template_result_t"""
+    _fields_ = [("templates", ctypes.c_void_p), ("fragments", ctypes.c_void_p), ("cigars", ctypes.c_void_p),
+                ("cigarWords", ctypes.c_uint64), ("rescueRequests", ctypes.c_uint64)]
+
+
+class Templates:
+    """templates[cluster], fragments[cluster * readCount + readIndex] and their CIGAR pool"""
+
+    def __init__(self, templates, fragments, cigars, rescue_requests=0):
+        self.templates, self.fragments, self.cigars, self.rescue_requests = templates, fragments, cigars, rescue_requests
+
+    def cigar(self, i):
+        f = self.fragments[i]
+        return self.cigars[int(f["cigarOffset"]):int(f["cigarOffset"]) + int(f["cigarLength"])]

@@ -33,6 +33,7 @@ EXPORTS = [
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
+    "isaac_ext_build_templates",
 ]
 
 
@@ -158,6 +159,26 @@ class Context:
         if not copy:
             return res
         return copy_result(res, len(req), "requestFragmentBegin", "rescued", len(req))
+
+    def build_templates(self, match_batch, tls, options=None, copy=True):
+        """TemplateBuilder::buildFragments + buildTemplate for every cluster of the resident read set -> batch.Templates"""
+        from .batch import TEMPLATE_DTYPE, TemplateOptions, TemplateResult, Templates
+        options = options if options is not None else TemplateOptions.make()
+        res = TemplateResult()
+        self._check(_lib.isaac_ext_build_templates(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(options),
+                                                   ctypes.byref(res)))
+        if not copy:
+            return res
+        n = self.reads.cluster_count
+
+        def arr(ptr, dtype, count):
+            if not count:
+                return np.zeros(0, dtype=dtype)
+            buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype).copy()
+
+        return Templates(arr(res.templates, TEMPLATE_DTYPE, n), arr(res.fragments, FRAGMENT_DTYPE, n * self.reads.read_count),
+                         arr(res.cigars, np.uint32, int(res.cigarWords)), int(res.rescueRequests))
 
     def tile_stats_device(self, n, d_fragments, d_stats, stream):
         """adds the K6 counters of n device-resident fragment records to the 64 u64 at d_stats"""

@@ -21,7 +21,9 @@ namespace
 thread_local std::string g_createError;
 struct E2eState;                       // isaac_ext_e2e.cuh
 void releaseE2e(E2eState *state);
+struct TemplateState;                  // isaac_ext_templates.cuh
 } // namespace
+void releaseTemplates(TemplateState *state);
 
 struct isaac_ext_ctx
 {
@@ -45,6 +47,8 @@ struct isaac_ext_ctx
     uint32_t clusterCount = 0;    // of the resident read set
     PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows
     E2eState *e2e = nullptr;      // streams and chunk buffers of the *_batch_compact entry points
+    TemplateState *templates = nullptr;   // buffers of isaac_ext_build_templates
+    double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
     DeviceBuffer<double> tables;
@@ -202,6 +206,7 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
         for (int q = 1; q < 100; ++q) t[q] = std::log(1.0 - std::pow(10.0, double(q) / -10.0));
         t[100] = t[0];
         for (int q = 1; q < 100; ++q) t[100 + q] = std::log(std::pow(10.0, double(q) / -10.0) / 3.0);
+        ctx->logMismatchQ40 = t[100 + 40];
         rc = ctx->cuda(cudaMemcpy(ctx->tables.p, t, sizeof(t), cudaMemcpyHostToDevice), "cudaMemcpy(tables)");
     }
     if (rc) { g_createError = ctx->error; delete ctx; return rc; }
@@ -235,6 +240,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     if (ctx->swStart) cudaEventDestroy(ctx->swStart);
     ctx->pipeline.release();
     releaseE2e(ctx->e2e);
+    releaseTemplates(ctx->templates);
     delete ctx;
 }
 
@@ -580,6 +586,7 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 
 // isaac_ext_ungapped_batch_compact, isaac_ext_gapped_batch_compact
 #include "isaac_ext_e2e.cuh"
+#include "isaac_ext_templates.cuh"
 
 namespace
 {

@@ -63,6 +63,15 @@ int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_ext_reads_t
                           uint64_t cigarCapacity, uint32_t *cigarsOut, uint8_t *rescuedOut,
                           uint64_t *fragmentCount, uint64_t *cigarWords, uint32_t threads);
 
+/* TemplateBuilder::buildFragments + buildTemplate for every cluster the way MatchSelector::processMatchList drives them
+ * (MatchSelector.cpp:323-349), see isaac_ext_build_templates.  templatesOut[clusterCount],
+ * fragmentsOut[clusterCount * readCount].  Only the reference build exports it. */
+int oracle_build_templates(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *config,
+                           const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                           const isaac_ext_template_options_t *options, isaac_ext_template_t *templatesOut,
+                           isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut,
+                           uint64_t *cigarWords, uint32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@
 #include "alignment/BandedSmithWaterman.hh"
 #include "alignment/FragmentBuilder.hh"
 #include "alignment/ShadowAligner.hh"
+#include "alignment/TemplateBuilder.hh"
+#include "alignment/RestOfGenomeCorrection.hh"
 #include "alignment/Cluster.hh"
 #include "alignment/fragmentBuilder/UngappedAligner.hh"
 #include "alignment/fragmentBuilder/GappedAligner.hh"
@@ -395,6 +397,85 @@ extern "C" int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_
         requestFragmentBegin[0] = 0;
         for (uint32_t i = 0; i < requestCount; ++i) requestFragmentBegin[i + 1] = requestFragmentBegin[i] + counts[i];
         return concatenate(parts, fragmentCapacity, fragmentsOut, cigarCapacity, cigarsOut, fragmentCount, cigarWords);
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * TemplateBuilder over a flat batch (glue only; the pair selection and mapping scores are the reference's)
+ * ------------------------------------------------------------------------------------------------------------------ */
+extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
+                                      const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                      const isaac_ext_template_options_t *options, isaac_ext_template_t *templatesOut,
+                                      isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut,
+                                      uint64_t *cigarWords, uint32_t threads)
+{
+    try
+    {
+        const std::vector<reference::Contig> &contigs = makeContigs(genome);
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        alignment::SeedMetadataList seeds;
+        for (uint32_t s = 0; s < batch->seedCount; ++s)
+            seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
+        const alignment::TemplateLengthStatistics stats(
+            tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[1]), tls->mateDriftRange);
+        const alignment::RestOfGenomeCorrection rog(contigs, rml);
+        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+        const uint32_t n = reads->clusterCount, rc = reads->readCount;
+        if (threads < 1) threads = 1;
+        if (n < 2 * threads) threads = 1;
+        std::vector<FlatOut> parts(threads);
+        parallelFor(n, threads, [&](uint32_t t, uint32_t b, uint32_t e) {
+            // on the heap like MatchSelector.cpp:150: the builder embeds ~32 MB of fixed-capacity vectors
+            std::unique_ptr<alignment::TemplateBuilder> builder(new alignment::TemplateBuilder(
+                layouts, cfg->repeatThreshold, cfg->maxSeedsPerRead, options->scatterRepeats != 0, cfg->gappedMismatchesMax,
+                cfg->avoidSmithWaterman, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore,
+                cfg->minGapExtendScore, cfg->semialignedGapLimit,
+                alignment::TemplateBuilder::DodgyAlignmentScore(options->dodgyAlignmentScore)));
+            ClusterHolder holder(maxReadLength);
+            std::vector<alignment::Match> matches;
+            for (uint32_t c = b; c < e; ++c)
+            {
+                holder.load(reads, rml, c);
+                matches.clear();
+                for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
+                    matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
+                                                       reference::ReferencePosition(batch->matches[m].location)));
+                alignment::BamTemplate &bam = builder->getBamTemplate();
+                isaac_ext_template_t &o = templatesOut[c];
+                std::memset(&o, 0, sizeof(o));
+                // MatchSelector.cpp:300-349: clusters without matches and clusters whose fragments did not build get an
+                // initialised (unaligned) template
+                if (!matches.empty() && !matches.front().location.isNoMatch() &&
+                    builder->buildFragments(contigs, rml, seeds, noAdapters, matches.begin(), matches.end(), holder.cluster,
+                                            batch->withGaps != 0))
+                {
+                    o.hadFragments = 1;
+                    o.built = builder->buildTemplate(contigs, rog, rml, noAdapters, holder.cluster, stats, options->mapqThreshold);
+                }
+                else
+                {
+                    bam.initialize(rml, holder.cluster);
+                }
+                o.alignmentScore = bam.getAlignmentScore();
+                o.properPair = bam.isProperPair();
+                for (uint32_t r = 0; r < rc; ++r)
+                {
+                    const alignment::FragmentMetadata &f = bam.getFragmentMetadata(r);
+                    o.fragmentAlignmentScore[r] = f.alignmentScore;
+                    parts[t].add(f, c * rc + r, rml);
+                }
+            }
+        });
+        uint64_t fragmentCount = 0;
+        return concatenate(parts, uint64_t(n) * rc, fragmentsOut, cigarCapacity, cigarsOut, &fragmentCount, cigarWords);
     }
     catch (const std::exception &e)
     {

@@ -127,6 +127,23 @@ def rescue_shadows(oracle, genome, reads, config, tls, requests, threads=1, frag
                       len(req), len(req), cap, cap * 4, threads)
 
 
+def build_templates(oracle, genome, reads, config, match_batch, tls, options, threads=1, cigar_capacity=None):
+    """TemplateBuilder over every cluster (reference build only) -> batch.Templates"""
+    from isaac_aligner_b200.batch import TEMPLATE_DTYPE, Templates
+    n = reads.cluster_count
+    templates = np.zeros(n, dtype=TEMPLATE_DTYPE)
+    frags = np.zeros(n * reads.read_count, dtype=FRAGMENT_DTYPE)
+    cigars = np.zeros(cigar_capacity or 64 * n + 1024, dtype=np.uint32)
+    nc = ctypes.c_uint64()
+    rc = oracle.lib.oracle_build_templates(
+        ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.byref(match_batch.c), ctypes.byref(tls),
+        ctypes.byref(options), ctypes.c_void_p(templates.ctypes.data), ctypes.c_void_p(frags.ctypes.data),
+        ctypes.c_uint64(cigars.size), ctypes.c_void_p(cigars.ctypes.data), ctypes.byref(nc), ctypes.c_uint32(threads))
+    if rc:
+        raise RuntimeError("oracle_build_templates failed: %d" % rc)
+    return Templates(templates, frags, cigars[:nc.value].copy())
+
+
 def port():
     if not os.path.exists(PORT_SO):
         build("port")

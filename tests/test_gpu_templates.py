@@ -1,0 +1,138 @@
+"""Parity of isaac_ext_build_templates (TemplateBuilder::buildFragments + buildTemplate per cluster) with the
+reference's own TemplateBuilder compiled unmodified (oracle/_ref), bit-exact: template and fragment mapping scores, proper-pair
+flags, the chosen fragment records and their CIGARs."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from common import FRAGMENT_FIELDS
+from common_build import build_workload
+from isaac_aligner_b200.batch import DODGY_ALIGNMENT_SCORE_UNALIGNED, DODGY_ALIGNMENT_SCORE_UNKNOWN, Tls, TemplateOptions
+from isaac_aligner_b200.types import BWA_SCORES, ELAND_SCORES, Config, cigar_to_string
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(oracle_lib.REF_SO), reason="the TemplateBuilder checker is the reference build only")]
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from isaac_aligner_b200 import capi
+    return capi
+
+
+def assert_templates_equal(got, want, what):
+    for name in ("hadFragments", "built", "properPair", "alignmentScore", "fragmentAlignmentScore"):
+        bad = np.nonzero((got.templates[name] != want.templates[name]).reshape(len(got.templates), -1).any(axis=1))[0]
+        assert not bad.size, "%s: template field %s differs at %d clusters, first %d: %r vs %r\n%r\n%r" % (
+            what, name, bad.size, bad[0], got.templates[name][bad[0]], want.templates[name][bad[0]],
+            got.fragments[2 * bad[0]:2 * bad[0] + 2], want.fragments[2 * bad[0]:2 * bad[0] + 2])
+    for name in FRAGMENT_FIELDS:
+        if name in ("cigarOffset", "matchCount"):
+            continue
+        x, y = got.fragments[name], want.fragments[name]
+        if name == "logProbability":
+            x, y = x.view(np.uint64), y.view(np.uint64)
+        bad = np.nonzero(x != y)[0]
+        assert not bad.size, "%s: fragment field %s differs at %d records, first %d: %r vs %r\n%r\n%r" % (
+            what, name, bad.size, bad[0], got.fragments[name][bad[0]], want.fragments[name][bad[0]],
+            got.fragments[bad[0]], want.fragments[bad[0]])
+    for i in np.nonzero(got.fragments["cigarLength"])[0]:
+        assert np.array_equal(got.cigar(i), want.cigar(i)), "%s: cigar of record %d: %s vs %s" % (
+            what, i, cigar_to_string(got.cigar(i)), cigar_to_string(want.cigar(i)))
+
+
+def run_both(capi, genome, reads, mb, cfg, tls, options):
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    got = ctx.build_templates(mb, tls, options)
+    ctx.close()
+    ref = oracle_lib.Oracle(oracle_lib.REF_SO)
+    want = oracle_lib.build_templates(ref, oracle_lib.GenomeHolder(genome), reads, cfg, mb, tls, options, threads=8)
+    return got, want
+
+
+@pytest.mark.parametrize("scores,L,options", [
+    (BWA_SCORES, 150, TemplateOptions.make()),
+    (BWA_SCORES, 100, TemplateOptions.make(scatter_repeats=True, dodgy=DODGY_ALIGNMENT_SCORE_UNKNOWN)),
+    (ELAND_SCORES, 100, TemplateOptions.make(dodgy=DODGY_ALIGNMENT_SCORE_UNALIGNED, mapq_threshold=20)),
+    (BWA_SCORES, 250, TemplateOptions.make(mapq_threshold=3)),
+])
+def test_build_templates_bit_exact(capi, scores, L, options):
+    genome, sim, reads, mb = build_workload(n_pairs=6000, L=L, seed=300 + L, indel_rate=4e-3)
+    cfg = Config.default(scores, max_read_length=2 * L)
+    got, want = run_both(capi, genome, reads, mb, cfg, Tls.make(), options)
+    assert_templates_equal(got, want, "build_templates L=%d" % L)
+    t = got.templates
+    assert t["built"].mean() > 0.9 and t["properPair"].mean() > 0.8 and got.rescue_requests > 100
+
+
+def test_build_templates_baseline_config0(capi):
+    """BASELINE configs[0]: 100 000 simulated 2x150 pairs on the 5 Mbp genome, the generator and seeds of bench.py"""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch
+    from isaac_aligner_b200.types import ReadSet
+    L, n_pairs = 150, 100_000
+    genome = synth.make_genome(5_000_000, n_contigs=1, seed=synth.SEED_G5)
+    sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 7, indel_rate=5e-4, seed_offsets=synth.auto_seed_offsets(L))
+    matches, begin = synth.make_matches(sim, genome, seed=synth.SEED_READS + 8, decoy_rate=0.2)
+    reads = ReadSet(sim.bcl, (L, L))
+    mb = MatchBatch(matches, begin, synth.seed_table(sim), with_gaps=True)
+    cfg = Config.default(BWA_SCORES, max_read_length=2 * L)
+    got, want = run_both(capi, genome, reads, mb, cfg, Tls.make(), TemplateOptions.make())
+    assert_templates_equal(got, want, "config0 templates")
+    assert got.templates["built"].mean() > 0.99
+
+
+@pytest.mark.parametrize("seed,kw,options", [
+    (411, dict(neighbor_rate=0.7), TemplateOptions.make()),                                  # few well-anchored candidates
+    (412, dict(neighbor_rate=0.7, repeat_rate=0.1), TemplateOptions.make(scatter_repeats=True, dodgy=3)),
+    (413, dict(genome_bases=40_000, n_contigs=3, indel_rate=1e-2), TemplateOptions.make(mapq_threshold=10)),   # crowded genome
+    (414, dict(too_many_rate=0.1, masked=False), TemplateOptions.make(dodgy=DODGY_ALIGNMENT_SCORE_UNALIGNED)),
+])
+def test_build_templates_hard_cases(capi, seed, kw, options):
+    genome, sim, reads, mb = build_workload(n_pairs=5000, L=100, seed=seed, **kw)
+    cfg = Config.default(BWA_SCORES, max_read_length=200)
+    got, want = run_both(capi, genome, reads, mb, cfg, Tls.make(), options)
+    assert_templates_equal(got, want, "hard case %d" % seed)
+
+
+def test_build_templates_tandem_repeats(capi):
+    """a genome made of a repeated unit: many equally good placements per read, so the repeat bookkeeping (equal template
+    scores, ISAAC_LP_EQUALS ties, unique-probability sums, --scatter-repeats) decides the result"""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch
+    from isaac_aligner_b200.types import ReadSet
+    rng = np.random.default_rng(77)
+    unit = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=700)]
+    contig = np.concatenate([np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=3000)], np.tile(unit, 12),
+                             np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=3000)]]).copy()
+    genome = [contig]
+    L = 100
+    sim = synth.simulate_pairs(genome, 3000, L=L, seed=78, indel_rate=1e-3, seed_offsets=synth.auto_seed_offsets(L))
+    matches, begin = synth.make_matches(sim, genome, seed=79, decoy_rate=0.1)
+    # every seed match also matches at the same offset in the other copies of the unit: add them as extra matches
+    reads = ReadSet(sim.bcl, (L, L))
+    extra = []
+    loc = matches["location"]
+    pos = (loc >> np.uint64(1)) & np.uint64((1 << 40) - 1)
+    inside = (pos >= 3000) & (pos < 3000 + 700 * 12 - 64)
+    for k in range(1, 4):
+        m = matches[inside].copy()
+        p = (pos[inside].astype(np.int64) - 3000 + 700 * k) % (700 * 12 - 64) + 3000
+        m["location"] = (m["location"] & ~np.uint64(((1 << 40) - 1) << 1)) | (p.astype(np.uint64) << np.uint64(1))
+        extra.append((m, np.repeat(np.arange(len(begin) - 1), np.diff(begin.astype(np.int64)))[inside]))
+    cluster_of = np.concatenate([np.repeat(np.arange(len(begin) - 1), np.diff(begin.astype(np.int64)))] + [e[1] for e in extra])
+    allm = np.concatenate([matches] + [e[0] for e in extra])
+    # a cluster's matches arrive sorted by (location, seed) (SelectMatchesTransition.cpp:242-254)
+    order = np.lexsort((allm["seedId"], allm["location"], cluster_of))
+    allm, cluster_of = allm[order], cluster_of[order]
+    nb = np.zeros(len(begin), dtype=np.uint64)
+    np.cumsum(np.bincount(cluster_of, minlength=len(begin) - 1), out=nb[1:])
+    mb = MatchBatch(allm, nb, synth.seed_table(sim), with_gaps=True)
+    cfg = Config.default(BWA_SCORES, max_read_length=2 * L)
+    for options in (TemplateOptions.make(), TemplateOptions.make(scatter_repeats=True)):
+        got, want = run_both(capi, genome, reads, mb, cfg, Tls.make(), options)
+        assert_templates_equal(got, want, "tandem repeats")
