@@ -203,13 +203,23 @@ def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup):
         t2 = time.perf_counter()
         tb += t1 - t0; tr += t2 - t1
     tb /= steps; tr /= steps
+    # the whole TemplateBuilder: build + the rescues the templates really ask for + pair selection / MAPQ
+    templates = ctx.build_templates(mb, tls)
+    tt = 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter(); ctx.build_templates(mb, tls, copy=False); tt += time.perf_counter() - t0
+    tt /= steps
     gaps = flat.fragments["gapCount"] > 0
-    return {"pairs": n, "pairs_per_s": n / (tb + tr), "build_ms": tb * 1e3, "rescue_ms": tr * 1e3,
+    return {"pairs": n, "template_pairs_per_s": n / tt, "templates_ms": tt * 1e3,
+            "template_rescue_requests": int(templates.rescue_requests),
+            "templates_built": int(templates.templates["built"].sum()), "proper_pairs": int(templates.templates["properPair"].sum()),
+            "pairs_per_s": n / (tb + tr), "build_ms": tb * 1e3, "rescue_ms": tr * 1e3,
             "matches": int(len(mb.matches)), "fragments": int(flat.fragments.size), "fragments_with_gaps": int(gaps.sum()),
             "rescue_requests": int(len(req)), "rescued": int(resc.flags.sum()), "shadow_candidates": int(resc.fragments.size),
             "gpu_launches_per_step": (ctx.launches - l0) // max(1, steps),
-            "policy": "stand-in for TemplateBuilder (out of scope): mates of all candidates are rescued unless both reads have an "
-                      "edit-distance-0 candidate (TemplateBuilder.cpp:1073-1081, 737-757)"}, flat, req
+            "policy": "template_*: isaac_ext_build_templates = the reference's TemplateBuilder end to end; pairs_per_s / build_ms / "
+                      "rescue_ms: the two batch calls alone with a stand-in policy (mates of all candidates are rescued unless both "
+                      "reads have an edit-distance-0 candidate)"}, flat, req
 
 
 def pairs_pipeline_cpu(genome, reads, mb, tls, config, sample_clusters):
@@ -233,8 +243,16 @@ def pairs_pipeline_cpu(genome, reads, mb, tls, config, sample_clusters):
     oracle_lib.rescue_shadows(chk, g, sub_reads, config, tls, req, threads=cores, fragments_per_request=96)
     t3 = time.perf_counter()
     sec = (t1 - t0) + (t3 - t2)
-    return {"pairs": k, "pairs_per_s": k / sec, "build_ms": (t1 - t0) * 1e3, "rescue_ms": (t3 - t2) * 1e3, "cores": cores,
-            "kind": chk.kind}
+    out = {"pairs": k, "pairs_per_s": k / sec, "build_ms": (t1 - t0) * 1e3, "rescue_ms": (t3 - t2) * 1e3, "cores": cores,
+           "kind": chk.kind}
+    if chk.kind == "reference":                          # the verbatim TemplateBuilder, one per host thread
+        from isaac_aligner_b200.batch import TemplateOptions
+        oracle_lib.build_templates(chk, g, sub_reads, config, sub_mb, tls, TemplateOptions.make(), threads=cores)   # warm the genome cache
+        t4 = time.perf_counter()
+        oracle_lib.build_templates(chk, g, sub_reads, config, sub_mb, tls, TemplateOptions.make(), threads=cores)
+        out["templates_ms"] = (time.perf_counter() - t4) * 1e3
+        out["template_pairs_per_s"] = k / (out["templates_ms"] * 1e-3)
+    return out
 
 
 def run_b200(args):
@@ -424,14 +442,15 @@ def run_b200(args):
 def pairs_config(args, n_pairs):
     return {"workload": "BASELINE configs[0]/[2] style: %d simulated 2x%d bp FR pairs per GPU per step on a %d bp random genome, "
                         "indel events %.0e/base, seed matches from error-free auto seeds + 20%% decoys, explicit TLS 245/350/455, "
-                        "FragmentBuilder::build of every cluster then ShadowAligner::rescueShadow per the stand-in template policy"
+                        "TemplateBuilder::buildFragments + buildTemplate of every cluster (isaac_ext_build_templates)"
                         % (n_pairs, args.read_length, args.genome_bases, args.indel_rate),
             "pairs_per_gpu": n_pairs, "read_length": args.read_length,
             "l2": "per-step inputs+outputs exceed the 126 MB L2 for >= 500k pairs"}
 
 
 def run_pairs(args):
-    """--workload pairs: read pairs/s of the two TemplateBuilder-facing calls (host-pointer ABI = end to end)."""
+    """--workload pairs: aligned read pairs/s of isaac_ext_build_templates (seed matches in, templates out, host-pointer ABI =
+    end to end), with the two batch calls underneath it timed separately in "pipeline"."""
     import torch
     from isaac_aligner_b200 import capi
     from isaac_aligner_b200.types import Config
@@ -446,7 +465,7 @@ def run_pairs(args):
         genome, reads, mb, tls = make_pairs_workload(args, 0, min(n_pairs, 6000 * cores))
         config = Config.default(max_read_length=2 * args.read_length)
         runs = [pairs_pipeline_cpu(genome, reads, mb, tls, config, reads.cluster_count) for _ in range(args.warmup + args.steps)][args.warmup:]
-        v = float(np.mean([r["pairs_per_s"] for r in runs]))
+        v = float(np.mean([r.get("template_pairs_per_s", r["pairs_per_s"]) for r in runs]))
         sample = "%d pairs per step of the same generator, %d host threads" % (reads.cluster_count, cores)
         emit(json.dumps({"impl": "reference", "metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": reads.cluster_count / v * 1e3,
@@ -471,7 +490,7 @@ def run_pairs(args):
         import torch.distributed as dist
         dist.barrier()
     line, flat, req = pairs_pipeline_gpu(ctx, reads, mb, tls, args.steps, args.warmup)
-    t = torch.tensor([line["build_ms"] + line["rescue_ms"]], dtype=torch.float64, device="cuda")
+    t = torch.tensor([line["templates_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -480,7 +499,8 @@ def run_pairs(args):
         return
     cores = os.cpu_count() or 1
     cpu = pairs_pipeline_cpu(genome, reads, mb, tls, config, 4000 * cores)
-    h2d = len(mb.matches) * 16 + reads.bcl.size * 0 + len(req) * 32
+    # one build_templates call: matches in; candidate records, rescue requests and shadow records cross PCIe inside it
+    h2d = len(mb.matches) * 16 + line["template_rescue_requests"] * 32
     d2h = flat.fragments.size * 64 + flat.cigars.size * 4
     v = world * n_pairs / (ms * 1e-3)
     emit(json.dumps({"metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -488,7 +508,7 @@ def run_pairs(args):
                       "dtype": "int16+f64", "data": "synthetic", "config": pairs_config(args, n_pairs),
                       "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                       "gpu_launches": int(line["gpu_launches_per_step"] * args.steps), "pipeline": line,
-                      "cpu_baseline": {"value": cpu["pairs_per_s"], "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                      "cpu_baseline": {"value": cpu.get("template_pairs_per_s", cpu["pairs_per_s"]), "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
                                        "sample": "first %d pairs of rank 0, one pass, %d host threads" % (cpu["pairs"], cpu["cores"])}}))
     ctx.close()
 

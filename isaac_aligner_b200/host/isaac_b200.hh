@@ -231,6 +231,85 @@ private:
     std::vector<uint32_t> shadowCigarBuffer_;
 };
 
+/// alignment::BamTemplate (BamTemplate.hh:40-137): the two fragments chosen for a cluster, the template mapping score
+/// and the proper-pair flag.  FragmentMetadata::alignmentScore travels next to the flat record.
+class BamTemplate
+{
+public:
+    BamTemplate() : fragmentCount_(0), alignmentScore_(0), properPair_(false) { fragmentAlignmentScore_[0] = fragmentAlignmentScore_[1] = -1U; }
+    unsigned getFragmentCount() const { return fragmentCount_; }
+    const FragmentMetadata &getFragmentMetadata(unsigned i) const { return fragments_[i]; }
+    unsigned getFragmentAlignmentScore(unsigned i) const { return fragmentAlignmentScore_[i]; }
+    unsigned getAlignmentScore() const { return alignmentScore_; }
+    bool hasAlignmentScore() const { return -1U != alignmentScore_; }
+    bool isProperPair() const { return properPair_; }
+    bool isUnanchored() const { return 0 == fragmentAlignmentScore_[0] && (fragmentCount_ < 2 || 0 == fragmentAlignmentScore_[1]); }
+private:
+    friend class TemplateBuilder;
+    FragmentMetadata fragments_[2];
+    unsigned fragmentAlignmentScore_[2];
+    unsigned fragmentCount_, alignmentScore_;
+    bool properPair_;
+};
+
+/// alignment::TemplateBuilder (TemplateBuilder.hh:56-137) for one cluster: buildFragments() then buildTemplate(), the result
+/// through getBamTemplate() like the reference.  Pair selection, shadow rescue and mapping scores happen behind
+/// isaac_ext_build_templates.
+class TemplateBuilder
+{
+public:
+    typedef short DodgyAlignmentScore;
+    static const DodgyAlignmentScore DODGY_ALIGNMENT_SCORE_UNKNOWN = 255;
+    static const DodgyAlignmentScore DODGY_ALIGNMENT_SCORE_UNALIGNED = -1;
+    TemplateBuilder(Context &context, bool scatterRepeats, DodgyAlignmentScore dodgyAlignmentScore)
+        : context_(context), built_(false)
+    {
+        options_.scatterRepeats = scatterRepeats ? 1u : 0u; options_.dodgyAlignmentScore = dodgyAlignmentScore;
+        options_.mapqThreshold = 0; options_.pad = 0;
+    }
+    /// keeps the cluster and its matches for buildTemplate (the reference builds the candidate fragments here)
+    bool buildFragments(const SeedMetadataList &seedMetadataList, std::vector<Match>::const_iterator matchBegin,
+                        std::vector<Match>::const_iterator matchEnd, const Cluster &cluster, bool withGaps)
+    {
+        seeds_ = seedMetadataList; matches_.assign(matchBegin, matchEnd); withGaps_ = withGaps;
+        const isaac_ext_reads_t reads = cluster.view();
+        context_.check(isaac_ext_set_reads(context_.get(), &reads));
+        readCount_ = cluster.readCount;
+        built_ = false;
+        return !matches_.empty();
+    }
+    /// \return false when the template ended up without a single aligned read
+    bool buildTemplate(const TemplateLengthStatistics &templateLengthStatistics, unsigned mapqThreshold)
+    {
+        options_.mapqThreshold = mapqThreshold;
+        const uint64_t begin[2] = {0, uint64_t(matches_.size())};
+        const isaac_ext_build_batch_t batch = {matches_.empty() ? 0 : matches_.data(), begin, seeds_.data(), uint32_t(seeds_.size()), withGaps_ ? 1u : 0u};
+        isaac_ext_template_result_t r;
+        context_.check(isaac_ext_build_templates(context_.get(), &batch, &templateLengthStatistics, &options_, &r));
+        cigarBuffer_.assign(r.cigars, r.cigars + r.cigarWords);
+        bamTemplate_.fragmentCount_ = readCount_;
+        for (unsigned i = 0; i < readCount_; ++i)
+        {
+            bamTemplate_.fragments_[i] = FragmentMetadata(r.fragments[i], &cigarBuffer_);
+            bamTemplate_.fragmentAlignmentScore_[i] = r.templates[0].fragmentAlignmentScore[i];
+        }
+        bamTemplate_.alignmentScore_ = r.templates[0].alignmentScore;
+        bamTemplate_.properPair_ = r.templates[0].properPair != 0;
+        built_ = r.templates[0].built != 0;
+        return built_;
+    }
+    const BamTemplate &getBamTemplate() const { return bamTemplate_; }
+private:
+    Context &context_;
+    isaac_ext_template_options_t options_;
+    SeedMetadataList seeds_;
+    std::vector<Match> matches_;
+    bool withGaps_, built_;
+    unsigned readCount_;
+    BamTemplate bamTemplate_;
+    std::vector<uint32_t> cigarBuffer_;
+};
+
 namespace fragmentBuilder
 {
 /// fragmentBuilder::UngappedAligner / GappedAligner (UngappedAligner.hh:55-60, GappedAligner.hh:49-54): re-align one

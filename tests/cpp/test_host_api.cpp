@@ -124,11 +124,78 @@ static void testSimpleDeletionThroughFragmentBuilder()
     }
 }
 
+// testTemplateBuilder.cpp: testEmptyMatchList (:149-177, an empty match list leaves two unaligned fragments and template
+// score 0) and the shape of testUnique (:230-281): a forward read 1 and a reverse read 2 a nominal template length apart,
+// seeded without neighbours, come out as a proper pair with positive mapping scores.
+static void testTemplateBuilder()
+{
+    const std::string genome = getGenome(4000);
+    isaac_ext_config_t cfg = makeConfig(0, -3, -11, -4, -20, 200);          // bwa scores
+    Context context(cfg);
+    std::vector<reference::Contig> contigs(1, reference::Contig(0, "chr"));
+    contigs[0].forward_ = v(genome);
+    context.setReference(contigs);
+    const unsigned L = 100, r1 = 1000, r2 = 1000 + 300 - L;          // template length 300
+    const std::string read1 = genome.substr(r1, L);
+    std::string read2;                                                // reverse complement of the mate
+    for (unsigned i = 0; i < L; ++i)
+    {
+        const char c = genome[r2 + L - 1 - i];
+        read2.push_back(c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A');
+    }
+    alignment::Cluster cluster;
+    cluster.readCount = 2; cluster.readLength[0] = cluster.readLength[1] = L; cluster.firstCycle[0] = 1; cluster.firstCycle[1] = 1 + L;
+    for (char c : read1 + read2) cluster.bcl.push_back(uint8_t((35 << 2) | std::string("ACGT").find(c)));
+    alignment::SeedMetadataList seeds(2);
+    seeds[0].offset = 0; seeds[0].length = 32; seeds[0].readIndex = 0;
+    seeds[1].offset = 0; seeds[1].length = 32; seeds[1].readIndex = 1;
+    const alignment::TemplateLengthStatistics tls = {200, 400, 300, 30, 30, {1, 6}, -1};      // FRp / RFm
+    alignment::TemplateBuilder builder(context, false, alignment::TemplateBuilder::DODGY_ALIGNMENT_SCORE_UNALIGNED);
+    {
+        std::vector<alignment::Match> none;
+        CHECK(!builder.buildFragments(seeds, none.begin(), none.end(), cluster, true));
+        CHECK(!builder.buildTemplate(tls, 0));
+        const alignment::BamTemplate &t = builder.getBamTemplate();
+        CHECK_EQ(t.getFragmentCount(), 2u);
+        CHECK_EQ(t.getAlignmentScore(), 0u);
+        CHECK(!t.getFragmentMetadata(0).isAligned() && !t.getFragmentMetadata(1).isAligned());
+        CHECK(!t.isProperPair());
+    }
+    {
+        std::vector<alignment::Match> matches(2);
+        // read 1 forward: the seed sits at the read start; read 2 reverse: its first 32 bases are the LAST 32 of the window
+        matches[0].seedId = (0u << 1) | 0u; matches[0].location = (((uint64_t(1) << 40) | uint64_t(r1)) << 1);
+        matches[1].seedId = (1u << 1) | 1u; matches[1].location = (((uint64_t(1) << 40) | uint64_t(r2 + L - 32)) << 1);
+        CHECK(builder.buildFragments(seeds, matches.begin(), matches.end(), cluster, true));
+        CHECK(builder.buildTemplate(tls, 0));
+        const alignment::BamTemplate &t = builder.getBamTemplate();
+        CHECK(t.isProperPair());
+        CHECK(t.hasAlignmentScore() && t.getAlignmentScore() > 100);
+        CHECK_EQ(t.getFragmentMetadata(0).getPosition(), long(r1));
+        CHECK_EQ(t.getFragmentMetadata(1).getPosition(), long(r2));
+        CHECK(!t.getFragmentMetadata(0).isReverse() && t.getFragmentMetadata(1).isReverse());
+        CHECK_EQ(t.getFragmentMetadata(0).getCigarString(), "100M");
+        CHECK_EQ(t.getFragmentMetadata(1).getCigarString(), "100M");
+        CHECK(t.getFragmentAlignmentScore(0) > 100 && t.getFragmentAlignmentScore(1) > 100);
+    }
+    {   // only read 1 has a seed match: the mate must be rescued into a proper pair (testOrphan :179-228)
+        std::vector<alignment::Match> matches(1);
+        matches[0].seedId = (0u << 1) | 0u; matches[0].location = (((uint64_t(1) << 40) | uint64_t(r1)) << 1);
+        CHECK(builder.buildFragments(seeds, matches.begin(), matches.end(), cluster, true));
+        CHECK(builder.buildTemplate(tls, 0));
+        const alignment::BamTemplate &t = builder.getBamTemplate();
+        CHECK(t.isProperPair());
+        CHECK_EQ(t.getFragmentMetadata(1).getPosition(), long(r2));
+        CHECK_EQ(t.getFragmentMetadata(1).getCigarString(), "100M");
+    }
+}
+
 int main()
 {
     testOverflow();
     testBandedSmithWaterman();
     testSimpleDeletionThroughFragmentBuilder();
+    testTemplateBuilder();
     std::printf(failures ? "%d checks FAILED\n" : "all checks passed\n", failures);
     return failures ? 1 : 0;
 }

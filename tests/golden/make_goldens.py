@@ -12,6 +12,10 @@ committed and are what the test-suite reads -- nothing under tests/ touches /roo
                       use the default two seeds, parsed from the test source, with the CIGAR / mismatch count / edit
                       distance the unit test asserts next to the output of the reference's FragmentBuilder::build on the
                       equivalent two-match batch
+  templates.json      the reference's TemplateBuilder (buildFragments + buildTemplate per cluster, verbatim sources) on a
+                      seeded 200-pair workload of tests/common_build.py for three option sets: template / fragment mapping
+                      scores, proper-pair flags, placements and CIGARs of both reads; the inputs are regenerated from the
+                      seeds at test time and checked against the recorded SHA-256
 """
 import json
 import os
@@ -217,5 +221,64 @@ def main():
           % (len(vectors), len(kept), reproduced))
 
 
+TEMPLATE_CASES = [("default", dict(scatter_repeats=False, dodgy=0, mapq_threshold=0)),
+                  ("scatter_unknown", dict(scatter_repeats=True, dodgy=255, mapq_threshold=0)),
+                  ("unaligned_mapq10", dict(scatter_repeats=False, dodgy=-1, mapq_threshold=10))]
+
+
+def template_workload():
+    """shared with tests/test_reference_goldens.py"""
+    import hashlib
+    from common_build import build_workload
+    genome, sim, reads, mb = build_workload(n_pairs=200, L=100, seed=901, genome_bases=60_000, n_contigs=2, indel_rate=6e-3,
+                                            neighbor_rate=0.4, repeat_rate=0.03)
+    h = hashlib.sha256()
+    for c in genome:
+        h.update(np.ascontiguousarray(c).tobytes())
+    h.update(np.ascontiguousarray(reads.bcl).tobytes())
+    h.update(mb.matches.tobytes()); h.update(mb.begin.tobytes()); h.update(mb.seeds.tobytes())
+    return genome, reads, mb, h.hexdigest()
+
+
+TEMPLATE_FIELDS = ["alignmentScore", "fragmentAlignmentScore0", "fragmentAlignmentScore1", "properPair", "built", "hadFragments"]
+TEMPLATE_READ_FIELDS = ["contigId", "position", "reverse", "observedLength", "mismatchCount", "editDistance", "smithWatermanScore",
+                        "logProbabilityBits", "cigar"]
+
+
+def templates_as_json(t):
+    """one row per cluster: TEMPLATE_FIELDS then TEMPLATE_READ_FIELDS of read 1 and of read 2"""
+    out = []
+    for c in range(len(t.templates)):
+        T = t.templates[c]
+        row = [int(T["alignmentScore"]), int(T["fragmentAlignmentScore"][0]), int(T["fragmentAlignmentScore"][1]),
+               int(T["properPair"]), int(T["built"]), int(T["hadFragments"])]
+        for r in range(2):
+            f = t.fragments[2 * c + r]
+            row += [int(f["contigId"]), int(f["position"]), int(f["reverse"]), int(f["observedLength"]), int(f["mismatchCount"]),
+                    int(f["editDistance"]), int(f["smithWatermanScore"]), int(np.float64(f["logProbability"]).view(np.uint64)),
+                    cigar_to_string(t.cigar(2 * c + r))]
+        out.append(row)
+    return out
+
+
+def make_templates(ref):
+    from isaac_aligner_b200.batch import Tls, TemplateOptions
+    genome, reads, mb, digest = template_workload()
+    cfg = Config.default((0, -3, -11, -4, -20), max_read_length=200)
+    cases = []
+    for name, kw in TEMPLATE_CASES:
+        t = oracle_lib.build_templates(ref, oracle_lib.GenomeHolder(genome), reads, cfg, mb, Tls.make(), TemplateOptions.make(**kw))
+        cases.append({"name": name, "options": kw, "templates": templates_as_json(t)})
+    json.dump({"source": "lib/alignment/TemplateBuilder.cpp via oracle/ref_capi.cpp:oracle_build_templates", "inputSha256": digest,
+               "templateFields": TEMPLATE_FIELDS, "readFields": TEMPLATE_READ_FIELDS, "cases": cases},
+              open(os.path.join(HERE, "templates.json"), "w"), separators=(",", ":"))
+    built = sum(x[4] for x in cases[0]["templates"])
+    print("templates.json: %d clusters x %d option sets, %d templates built in the default case" % (len(cases[0]["templates"]), len(cases), built))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "templates":
+        make_templates(oracle_lib.reference())
+    else:
+        main()
+        make_templates(oracle_lib.reference())
