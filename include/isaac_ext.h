@@ -199,8 +199,10 @@ typedef struct isaac_ext_template_options {
     uint32_t scatterRepeats;         /* --scatter-repeats                                                        */
     int32_t  dodgyAlignmentScore;    /* -1 = DODGY_ALIGNMENT_SCORE_UNALIGNED, 255 = _UNKNOWN, else numeric (:60-61) */
     uint32_t mapqThreshold;          /* --mapq-threshold                                                          */
-    uint32_t pad;
+    uint32_t clipFlags;              /* ISAAC_EXT_CLIP_* applied to every template that is kept (MatchSelector.cpp:336-346) */
 } isaac_ext_template_options_t;
+#define ISAAC_EXT_CLIP_SEMIALIGNED 1u    /* --clip-semialigned: matchSelector::SemialignedEndsClipper               */
+#define ISAAC_EXT_CLIP_OVERLAPPING 2u    /* --clip-overlapping: matchSelector::OverlappingEndsClipper               */
 
 /* alignment::BamTemplate of one cluster (BamTemplate.hh:40-137) next to its two fragment records. */
 typedef struct isaac_ext_template {
@@ -238,6 +240,11 @@ int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
  * by the batch calls below.  Stays valid until the next isaac_ext_set_reads on this context. */
 int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *reads);
 
+/* alignment::trimLowQualityEnds (Quality.cpp:71-120, --base-quality-cutoff, MatchSelector.cpp:300): recomputes
+ * Read::endCyclesMasked_ of every resident read from its qualities, replacing what isaac_ext_set_reads was given.
+ * baseQualityCutoff 0 = no masking.  endCyclesMaskedOut (clusterCount * readCount values) may be NULL. */
+int isaac_ext_trim_low_quality_ends(isaac_ext_ctx *ctx, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut);
+
 /* ---- the two calls TemplateBuilder makes --------------------------------------------------------- */
 
 /* FragmentBuilder::build over the resident read set: seeds -> candidates -> ungapped -> simple indels -> gapped, with
@@ -255,7 +262,9 @@ int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
  * buildPairedEndTemplate / buildDisjoinedTemplate / rescueShadow / scoreDisjoinedTemplate / updateMappingScore, MAPQ
  * threshold filter).  One isaac_ext_build_fragments pass, the rescue requests the templates need in one
  * isaac_ext_rescue_shadows pass, then pair selection and mapping scores per cluster on the host threads.  The
- * rest-of-genome correction is computed from the resident reference and read lengths (RestOfGenomeCorrection.hh:45-57). */
+ * rest-of-genome correction is computed from the resident reference and read lengths (RestOfGenomeCorrection.hh:45-57).
+ * With options.clipFlags the kept templates then go through the end clippers (SemialignedEndsClipper.cpp:32-205,
+ * OverlappingEndsClipper.cpp:45-180) in one kernel pass. */
 int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
                               const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result);
 

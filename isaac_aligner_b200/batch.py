@@ -87,16 +87,18 @@ TEMPLATE_DTYPE = np.dtype([("alignmentScore", "<u4"), ("fragmentAlignmentScore",
 assert TEMPLATE_DTYPE.itemsize == 16
 
 DODGY_ALIGNMENT_SCORE_UNKNOWN, DODGY_ALIGNMENT_SCORE_UNALIGNED = 255, -1      # TemplateBuilder.hh:60-61
+CLIP_SEMIALIGNED, CLIP_OVERLAPPING = 1, 2                                     # ISAAC_EXT_CLIP_*
 
 
 class TemplateOptions(ctypes.Structure):
     """isaac_ext_template_options_t (isaac-align defaults: --scatter-repeats 0, --dodgy-alignment-score 0, --mapq-threshold 0)"""
     _fields_ = [("scatterRepeats", ctypes.c_uint32), ("dodgyAlignmentScore", ctypes.c_int32),
-                ("mapqThreshold", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
+                ("mapqThreshold", ctypes.c_uint32), ("clipFlags", ctypes.c_uint32)]
 
     @classmethod
-    def make(cls, scatter_repeats=False, dodgy=0, mapq_threshold=0):
-        return cls(1 if scatter_repeats else 0, dodgy, mapq_threshold, 0)
+    def make(cls, scatter_repeats=False, dodgy=0, mapq_threshold=0, clip_semialigned=False, clip_overlapping=False):
+        return cls(1 if scatter_repeats else 0, dodgy, mapq_threshold,
+                   (CLIP_SEMIALIGNED if clip_semialigned else 0) | (CLIP_OVERLAPPING if clip_overlapping else 0))
 
 
 class TemplateResult(ctypes.Structure):

@@ -33,7 +33,7 @@ EXPORTS = [
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
-    "isaac_ext_build_templates",
+    "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends",
 ]
 
 
@@ -159,6 +159,12 @@ class Context:
         if not copy:
             return res
         return copy_result(res, len(req), "requestFragmentBegin", "rescued", len(req))
+
+    def trim_low_quality_ends(self, base_quality_cutoff):
+        """alignment::trimLowQualityEnds on the resident reads; returns the new endCyclesMasked [clusters, readCount]"""
+        out = np.zeros((self.reads.cluster_count, self.reads.read_count), dtype=np.uint16)
+        self._check(_lib.isaac_ext_trim_low_quality_ends(self._h, ctypes.c_uint32(base_quality_cutoff), _p(out)))
+        return out
 
     def build_templates(self, match_batch, tls, options=None, copy=True):
         """TemplateBuilder::buildFragments + buildTemplate for every cluster of the resident read set -> batch.Templates"""

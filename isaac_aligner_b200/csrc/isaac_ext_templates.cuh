@@ -13,6 +13,8 @@
 #include <cfloat>
 #include <cmath>
 
+#include "kernels_clip.cuh"
+
 namespace
 {
 
@@ -746,6 +748,11 @@ struct TemplateState
     std::vector<isaac_ext_rescue_request_t> requests;
     std::vector<uint64_t> clusterRequestBegin;
     HostBuffer<isaac_ext_template_t> templates;  HostBuffer<isaac_ext_fragment_t> fragments;  HostBuffer<uint32_t> cigars;
+    // end clippers
+    DeviceBuffer<isaac_ext_template_t> dTemplates;  DeviceBuffer<isaac_ext_fragment_t> dFragments;
+    DeviceBuffer<uint32_t> dCigarsIn, dCigarsOut;
+    HostBuffer<uint32_t> clippedCigars;
+    ~TemplateState() { dTemplates.release(); dFragments.release(); dCigarsIn.release(); dCigarsOut.release(); }
 };
 
 template <class T> void swapBuffers(HostBuffer<T> &a, HostBuffer<T> &b) { std::swap(a.p, b.p); std::swap(a.capacity, b.capacity); }
@@ -886,5 +893,46 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
 
     result->templates = st.templates.p; result->fragments = st.fragments.p; result->cigars = st.cigars.p;
     result->cigarWords = words; result->rescueRequests = st.requests.size();
+
+    // ---- end clippers on the kept templates (MatchSelector.cpp:336-346): one kernel pass over the tile
+    if (options->clipFlags & (ISAAC_EXT_CLIP_SEMIALIGNED | ISAAC_EXT_CLIP_OVERLAPPING))
+    {
+        const size_t count = size_t(n) * readCount;
+        const size_t outWords = words + 4 * count;                       // a clip adds at most two operations per side
+        if (outWords > 0xFFFFFFFFull) return ctx->fail(ISAAC_EXT_E_CAPACITY, "CIGAR pool of the tile exceeds 2^32 words");
+        CK(cudaSetDevice(ctx->device));
+        CK(st.dTemplates.reserve(n)); CK(st.dFragments.reserve(count)); CK(st.dCigarsIn.reserve(words + 1)); CK(st.dCigarsOut.reserve(outWords));
+        st.clippedCigars.reserve(outWords);
+        CK(cudaMemcpyAsync(st.dTemplates.p, st.templates.p, size_t(n) * sizeof(isaac_ext_template_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(st.dFragments.p, st.fragments.p, count * sizeof(isaac_ext_fragment_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (words) CK(cudaMemcpyAsync(st.dCigarsIn.p, st.cigars.p, words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(st.dCigarsOut.p, 0, outWords * sizeof(uint32_t), ctx->stream));
+        clipTemplateEndsKernel<<<gridFor(ctx, n, 128, 16), 128, 0, ctx->stream>>>(
+            ctx->ref, ctx->reads, n, options->clipFlags, st.dTemplates.p, st.dFragments.p, st.dCigarsIn.p, st.dCigarsOut.p, ctx->errorFlag.p);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(st.fragments.p, st.dFragments.p, count * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(st.clippedCigars.p, st.dCigarsOut.p, outWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        uint32_t flag = 0;
+        CK(cudaMemcpyAsync(&flag, ctx->errorFlag.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (flag) { cudaMemset(ctx->errorFlag.p, 0, sizeof(uint32_t)); return ctx->fail(ISAAC_EXT_E_CAPACITY, "a template CIGAR exceeds 60 operations"); }
+        result->cigars = st.clippedCigars.p; result->cigarWords = outWords;
+        timer.mark("end clippers");
+    }
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_trim_low_quality_ends(isaac_ext_ctx *ctx, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reads first");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->reads.readTotal;
+    trimLowQualityEndsKernel<<<gridFor(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->reads, baseQualityCutoff, ctx->readMasked.p);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if (endCyclesMaskedOut) CK(cudaMemcpyAsync(endCyclesMaskedOut, ctx->readMasked.p, size_t(n) * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return ISAAC_EXT_OK;
 }

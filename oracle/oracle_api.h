@@ -72,6 +72,10 @@ int oracle_build_templates(const oracle_genome_t *genome, const isaac_ext_reads_
                            isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut,
                            uint64_t *cigarWords, uint32_t threads);
 
+/* alignment::trimLowQualityEnds on every cluster (Quality.cpp:71-120), see isaac_ext_trim_low_quality_ends.  Only the
+ * reference build exports it. */
+int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,9 @@
 #include "alignment/ShadowAligner.hh"
 #include "alignment/TemplateBuilder.hh"
 #include "alignment/RestOfGenomeCorrection.hh"
+#include "alignment/Quality.hh"
+#include "alignment/matchSelector/SemialignedEndsClipper.hh"
+#include "alignment/matchSelector/OverlappingEndsClipper.hh"
 #include "alignment/Cluster.hh"
 #include "alignment/fragmentBuilder/UngappedAligner.hh"
 #include "alignment/fragmentBuilder/GappedAligner.hh"
@@ -441,6 +444,8 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
                 alignment::TemplateBuilder::DodgyAlignmentScore(options->dodgyAlignmentScore)));
             ClusterHolder holder(maxReadLength);
             std::vector<alignment::Match> matches;
+            alignment::matchSelector::SemialignedEndsClipper semialignedClipper;
+            alignment::matchSelector::OverlappingEndsClipper overlappingClipper;
             for (uint32_t c = b; c < e; ++c)
             {
                 holder.load(reads, rml, c);
@@ -459,6 +464,11 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
                 {
                     o.hadFragments = 1;
                     o.built = builder->buildTemplate(contigs, rog, rml, noAdapters, holder.cluster, stats, options->mapqThreshold);
+                    if (o.built)                                                       // MatchSelector.cpp:336-346
+                    {
+                        if (options->clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED) { semialignedClipper.reset(); semialignedClipper.clip(contigs, bam); }
+                        if (options->clipFlags & ISAAC_EXT_CLIP_OVERLAPPING) { overlappingClipper.reset(); overlappingClipper.clip(contigs, bam); }
+                    }
                 }
                 else
                 {
@@ -476,6 +486,30 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
         });
         uint64_t fragmentCount = 0;
         return concatenate(parts, uint64_t(n) * rc, fragmentsOut, cigarCapacity, cigarsOut, &fragmentCount, cigarWords);
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+}
+
+extern "C" int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut)
+{
+    try
+    {
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+        ClusterHolder holder(maxReadLength);
+        isaac_ext_reads_t unmasked = *reads;
+        unmasked.endCyclesMasked = 0;                                                 // Cluster::init starts from unmasked reads
+        for (uint32_t c = 0; c < reads->clusterCount; ++c)
+        {
+            holder.load(&unmasked, rml, c);
+            alignment::trimLowQualityEnds(holder.cluster, baseQualityCutoff);
+            for (uint32_t r = 0; r < reads->readCount; ++r)
+                endCyclesMaskedOut[size_t(c) * reads->readCount + r] = uint16_t(holder.cluster[r].getEndCyclesMasked());
+        }
+        return ISAAC_EXT_OK;
     }
     catch (const std::exception &e)
     {

@@ -144,6 +144,16 @@ def build_templates(oracle, genome, reads, config, match_batch, tls, options, th
     return Templates(templates, frags, cigars[:nc.value].copy())
 
 
+def trim_low_quality_ends(oracle, reads, base_quality_cutoff):
+    """alignment::trimLowQualityEnds on every cluster (reference build only) -> endCyclesMasked [clusters, readCount]"""
+    out = np.zeros((reads.cluster_count, reads.read_count), dtype=np.uint16)
+    rc = oracle.lib.oracle_trim_low_quality_ends(ctypes.byref(reads.c), ctypes.c_uint32(base_quality_cutoff),
+                                                 ctypes.c_void_p(out.ctypes.data))
+    if rc:
+        raise RuntimeError("oracle_trim_low_quality_ends failed: %d" % rc)
+    return out
+
+
 def port():
     if not os.path.exists(PORT_SO):
         build("port")

@@ -136,3 +136,49 @@ def test_build_templates_tandem_repeats(capi):
     for options in (TemplateOptions.make(), TemplateOptions.make(scatter_repeats=True)):
         got, want = run_both(capi, genome, reads, mb, cfg, Tls.make(), options)
         assert_templates_equal(got, want, "tandem repeats")
+
+
+@pytest.mark.parametrize("L,cutoff", [(100, 25), (150, 30), (36, 25), (30, 25), (100, 0)])
+def test_trim_low_quality_ends_bit_exact(capi, L, cutoff):
+    """alignment::trimLowQualityEnds (Quality.cpp:71-120): reads with decaying, noisy and flat quality profiles"""
+    from isaac_aligner_b200.types import ReadSet
+    rng = np.random.default_rng(500 + L)
+    n = 4000
+    decay = np.clip(40 - (np.arange(L)[None, :] * rng.uniform(0, 0.6, size=(2 * n, 1))) + rng.normal(0, 6, size=(2 * n, L)), 2, 41)
+    decay[rng.random(2 * n) < 0.1] = 40                         # flat high quality: nothing to trim
+    decay[rng.random(2 * n) < 0.05] = 2                          # all bad: everything but the last 35 cycles goes
+    q = decay.astype(np.uint8).reshape(n, 2 * L)
+    bases = rng.integers(0, 4, size=(n, 2 * L)).astype(np.uint8)
+    bcl = (q << 2) | bases
+    bcl[rng.random(bcl.shape) < 0.01] = 0                       # N: quality 2 (Read.cpp:63-68)
+    reads = ReadSet(bcl, (L, L))
+    ctx = capi.Context(Config.default(max_read_length=2 * L))
+    ctx.set_reads(reads)
+    got = ctx.trim_low_quality_ends(cutoff)
+    want = oracle_lib.trim_low_quality_ends(oracle_lib.Oracle(oracle_lib.REF_SO), reads, cutoff)
+    assert np.array_equal(got, want)
+    if cutoff and L >= 100:
+        assert (got > 0).mean() > 0.3 and (got == 0).any() and got.max() == L - 35
+    ctx.close()
+
+
+@pytest.mark.parametrize("L,seed,kw,options", [
+    (100, 601, dict(), TemplateOptions.make(clip_semialigned=True)),
+    (150, 602, dict(), TemplateOptions.make(clip_overlapping=True)),
+    (150, 603, dict(indel_rate=8e-3), TemplateOptions.make(clip_semialigned=True, clip_overlapping=True)),
+    (100, 604, dict(genome_bases=40_000, n_contigs=3), TemplateOptions.make(clip_semialigned=True, clip_overlapping=True, mapq_threshold=5,
+                                                                           dodgy=DODGY_ALIGNMENT_SCORE_UNALIGNED)),
+])
+def test_end_clippers_bit_exact(capi, L, seed, kw, options):
+    """SemialignedEndsClipper + OverlappingEndsClipper after buildTemplate (MatchSelector.cpp:336-346).  Short inserts make the
+    mates overlap; substitution-rich read ends trigger the semialigned clipper."""
+    from isaac_aligner_b200 import synth
+    genome, sim, reads, mb = build_workload(n_pairs=5000, L=L, seed=seed, **kw)
+    cfg = Config.default(BWA_SCORES, max_read_length=2 * L)
+    tls = Tls.make()
+    got, want = run_both(capi, genome, reads, mb, cfg, tls, options)
+    assert_templates_equal(got, want, "end clippers %d" % seed)
+    plain, _ = run_both(capi, genome, reads, mb, cfg, tls, TemplateOptions.make(dodgy=options.dodgyAlignmentScore,
+                                                                                  mapq_threshold=options.mapqThreshold))
+    changed = (plain.fragments["observedLength"] != got.fragments["observedLength"]).sum()
+    assert changed > 20, "the clippers did not fire (%d)" % changed
