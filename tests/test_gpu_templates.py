@@ -182,3 +182,53 @@ def test_end_clippers_bit_exact(capi, L, seed, kw, options):
                                                                                   mapq_threshold=options.mapqThreshold))
     changed = (plain.fragments["observedLength"] != got.fragments["observedLength"]).sum()
     assert changed > 20, "the clippers did not fire (%d)" % changed
+
+
+def single_ended(genome, sim, reads, mb):
+    """read 1 of a paired workload as a single-ended tile: its bases, its seeds, its matches"""
+    from isaac_aligner_b200.batch import MatchBatch
+    from isaac_aligner_b200.types import ReadSet
+    L = reads.read_lengths[0]
+    S = len(sim.seed_offsets)
+    seed_index = (mb.matches["seedId"] >> np.uint64(1)) & np.uint64(0xFF)
+    keep = seed_index < S
+    cluster_of = np.repeat(np.arange(len(mb.begin) - 1), np.diff(mb.begin.astype(np.int64)))
+    begin = np.zeros(len(mb.begin), dtype=np.uint64)
+    np.cumsum(np.bincount(cluster_of[keep], minlength=len(mb.begin) - 1), out=begin[1:])
+    ecm = reads.end_cycles_masked[:, :1] if reads.end_cycles_masked is not None else None
+    return ReadSet(np.ascontiguousarray(reads.bcl[:, :L]), (L,), end_cycles_masked=ecm), \
+        MatchBatch(mb.matches[keep], begin, mb.seeds[:S], with_gaps=True)
+
+
+@pytest.mark.parametrize("options", [TemplateOptions.make(), TemplateOptions.make(dodgy=DODGY_ALIGNMENT_SCORE_UNALIGNED, mapq_threshold=4,
+                                                                               clip_semialigned=True, scatter_repeats=True)])
+def test_single_ended_templates_bit_exact(capi, options):
+    """single-ended data: pickBestFragment (TemplateBuilder.cpp:1035-1058), one fragment per BamTemplate"""
+    genome, sim, reads, mb = build_workload(n_pairs=5000, L=100, seed=700, neighbor_rate=0.5, repeat_rate=0.05)
+    reads1, mb1 = single_ended(genome, sim, reads, mb)
+    cfg = Config.default(BWA_SCORES, max_read_length=200)
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads1)
+    got = ctx.build_templates(mb1, Tls.make(), options)
+    built = ctx.build_fragments(mb1)
+    ctx.close()
+    ref = oracle_lib.Oracle(oracle_lib.REF_SO)
+    g = oracle_lib.GenomeHolder(genome)
+    want = oracle_lib.build_templates(ref, g, reads1, cfg, mb1, Tls.make(), options, threads=4)
+    from common_build import assert_flat_equal
+    assert_flat_equal(built, oracle_lib.build_fragments(ref, g, reads1, cfg, mb1, threads=4), "single-ended build_fragments")
+    # one fragment per cluster
+    for name in ("hadFragments", "built", "properPair", "alignmentScore"):
+        assert np.array_equal(got.templates[name], want.templates[name]), name
+    assert np.array_equal(got.templates["fragmentAlignmentScore"][:, 0], want.templates["fragmentAlignmentScore"][:, 0])
+    for name in FRAGMENT_FIELDS:
+        if name in ("cigarOffset", "matchCount"):
+            continue
+        x, y = got.fragments[name], want.fragments[name]
+        if name == "logProbability":
+            x, y = x.view(np.uint64), y.view(np.uint64)
+        assert np.array_equal(x, y), name
+    for i in np.nonzero(got.fragments["cigarLength"])[0]:
+        assert np.array_equal(got.cigar(i), want.cigar(i)), i
+    assert got.templates["built"].mean() > 0.5 and got.rescue_requests == 0
