@@ -7,7 +7,13 @@
 namespace
 {
 
-const uint32_t E2E_CHUNK = 1u << 20;
+// candidates per chunk: four chunks of the split Smith-Waterman path (2 waves x 148 SMs x 4 blocks x 128 pairs each);
+// ISAAC_EXT_E2E_CHUNK overrides it for experiments
+static uint32_t e2eChunk()
+{
+    static const uint32_t value = [] { const char *e = std::getenv("ISAAC_EXT_E2E_CHUNK"); const long v = e ? std::atol(e) : 0; return uint32_t(v > 0 ? v : 4 * 303104); }();
+    return value;
+}
 
 struct E2eState
 {
@@ -61,6 +67,7 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
         CK(st.hTotal.reserve(2));
         st.ready = true;
     }
+    const uint32_t E2E_CHUNK = e2eChunk();
     const uint32_t stride = gapped ? 32u : 3u;
     const uint32_t chunkMax = std::min(n, E2E_CHUNK);
     const uint32_t blocksMax = (chunkMax + COMPACT_BLOCK * COMPACT_ITEMS - 1) / (COMPACT_BLOCK * COMPACT_ITEMS);
@@ -71,6 +78,10 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
     }
     const uint32_t chunks = (n + E2E_CHUNK - 1) / E2E_CHUNK;
     auto chunkSize = [&](uint32_t k) { return std::min(E2E_CHUNK, n - k * E2E_CHUNK); };
+    // ISAAC_EXT_TRACE: device-side time stamps of every chunk (compute begin/end on sC, copy-out begin/end on sD)
+    const bool trace = std::getenv("ISAAC_EXT_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) { tev.resize(size_t(chunks) * 4 + 1); for (cudaEvent_t &e : tev) cudaEventCreate(&e); cudaEventRecord(tev.back(), st.sH); }
     auto enqueue = [&](uint32_t k) -> int {
         const int b = k & 1;
         const uint32_t m = chunkSize(k);
@@ -81,6 +92,7 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
         CK(cudaMemcpyAsync(st.dCand[b].p, candidates + size_t(k) * E2E_CHUNK, size_t(m) * sizeof(isaac_ext_candidate_t), cudaMemcpyHostToDevice, st.sH));
         CK(cudaEventRecord(st.evH[b], st.sH));
         CK(cudaStreamWaitEvent(st.sC, st.evH[b], 0));
+        if (trace) cudaEventRecord(tev[size_t(k) * 4], st.sC);
         const int r = gapped ? isaac_ext_gapped_batch_device(ctx, m, st.dCand[b].p, stride, st.dFrag[b].p, st.dCig[b].p, nullptr, st.sC)
                              : isaac_ext_ungapped_batch_device(ctx, m, st.dCand[b].p, st.dFrag[b].p, st.dCig[b].p, nullptr, st.sC);
         if (r) return r;
@@ -92,6 +104,7 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
         ctx->launches += 3;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(st.hTotal.p + b, st.dTotal[b].p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st.sC));
+        if (trace) cudaEventRecord(tev[size_t(k) * 4 + 1], st.sC);
         CK(cudaEventRecord(st.evC[b], st.sC));
         return ISAAC_EXT_OK;
     };
@@ -107,6 +120,7 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
         CK(cudaEventSynchronize(st.evC[b]));
         const uint32_t words = st.hTotal.p[b];
         CK(cudaStreamWaitEvent(st.sD, st.evC[b], 0));
+        if (trace) cudaEventRecord(tev[size_t(k) * 4 + 2], st.sD);
         if (base + words > poolCapacity || base + words > 0xFFFFFFFFull) overflow = true;
         else
         {
@@ -118,10 +132,22 @@ static int extendCompact(isaac_ext_ctx *ctx, E2eState &st, bool gapped, uint32_t
             CK(cudaMemcpyAsync(fragmentsOut + size_t(k) * E2E_CHUNK, st.dFrag[b].p, size_t(m) * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, st.sD));
             if (words) CK(cudaMemcpyAsync(poolOut + base, st.dPool[b].p, size_t(words) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st.sD));
         }
+        if (trace) cudaEventRecord(tev[size_t(k) * 4 + 3], st.sD);
         CK(cudaEventRecord(st.evD[b], st.sD));
         base += words;
     }
     CK(cudaStreamSynchronize(st.sD));
+    if (trace)
+    {
+        for (uint32_t k = 0; k < chunks; ++k)
+        {
+            float t[4];
+            for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev.back(), tev[size_t(k) * 4 + j]);
+            std::fprintf(stderr, "[isaac_ext] e2e %s chunk %2u: compute %7.3f .. %7.3f ms, copy out %7.3f .. %7.3f ms\n",
+                         gapped ? "gapped" : "ungapped", k, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t &e : tev) cudaEventDestroy(e);
+    }
     *wordsOut = base;
     if (overflow) return ctx->fail(ISAAC_EXT_E_CAPACITY, "CIGAR pool too small: *cigarWordsOut holds the required number of words");
     if (gapped)

@@ -265,7 +265,7 @@ public:
         : context_(context), built_(false)
     {
         options_.scatterRepeats = scatterRepeats ? 1u : 0u; options_.dodgyAlignmentScore = dodgyAlignmentScore;
-        options_.mapqThreshold = 0; options_.pad = 0;
+        options_.mapqThreshold = 0; options_.clipFlags = 0;
     }
     /// keeps the cluster and its matches for buildTemplate (the reference builds the candidate fragments here)
     bool buildFragments(const SeedMetadataList &seedMetadataList, std::vector<Match>::const_iterator matchBegin,
