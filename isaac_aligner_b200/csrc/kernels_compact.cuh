@@ -28,8 +28,13 @@ cigarBlockSumsKernel(uint32_t n, const isaac_ext_fragment_t *__restrict__ fragme
     }
 }
 
-/// exclusive scan of the block sums by one block; total[0] = grand total
-__global__ void __launch_bounds__(1024) cigarScanBlockSumsKernel(uint32_t blocks, uint32_t *__restrict__ blockSums, uint32_t *__restrict__ total)
+/// exclusive scan of the block sums by one block; total[0] = grand total of this chunk.  'running' (optional) carries the
+/// pool offset across the chunks of one call in stream order: chunkBase[0] = words of all earlier chunks, running[0] += total;
+/// 'hostTotal' (optional) is a word of mapped pinned memory the host reads after the chunk's event (no copy engine involved).
+__global__ void __launch_bounds__(1024) cigarScanBlockSumsKernel(uint32_t blocks, uint32_t *__restrict__ blockSums, uint32_t *__restrict__ total,
+                                                                 unsigned long long *__restrict__ running = nullptr,
+                                                                 unsigned long long *__restrict__ chunkBase = nullptr,
+                                                                 volatile uint32_t *hostTotal = nullptr)
 {
     __shared__ uint32_t warpSums[32];
     __shared__ uint32_t carry;
@@ -56,13 +61,19 @@ __global__ void __launch_bounds__(1024) cigarScanBlockSumsKernel(uint32_t blocks
         if (threadIdx.x == 1023) carry += warpOffset + incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) total[0] = carry;
+    if (threadIdx.x == 0)
+    {
+        total[0] = carry;
+        if (running) { chunkBase[0] = running[0]; running[0] += carry; }
+        if (hostTotal) { hostTotal[0] = carry; __threadfence_system(); }
+    }
 }
 
 /// writes the dense pool and points every record at its words (cigarOffset = poolBase + dense offset)
 __global__ void __launch_bounds__(COMPACT_BLOCK)
 cigarCompactKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, const uint32_t *__restrict__ strided, uint32_t stride,
-                   const uint32_t *__restrict__ blockOffsets, uint32_t *__restrict__ pool, uint32_t poolCapacity)
+                   const uint32_t *__restrict__ blockOffsets, uint32_t *__restrict__ pool, uint32_t poolCapacity,
+                   const unsigned long long *__restrict__ chunkBase = nullptr)
 {
     __shared__ uint32_t warpSums[COMPACT_BLOCK / 32];
     const uint32_t first = (blockIdx.x * COMPACT_BLOCK + threadIdx.x) * COMPACT_ITEMS;
@@ -75,6 +86,7 @@ cigarCompactKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, con
     __syncthreads();
     uint32_t offset = blockOffsets[blockIdx.x] + incl - s;
     for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) offset += warpSums[w];
+    const uint32_t poolBase = chunkBase ? uint32_t(chunkBase[0]) : 0u;      // the caller's pool is addressed with 32 bits
 #pragma unroll
     for (unsigned k = 0; k < COMPACT_ITEMS; ++k)
     {
@@ -82,16 +94,33 @@ cigarCompactKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, con
         {
             if (offset + len[k] <= poolCapacity)
                 for (unsigned j = 0; j < len[k]; ++j) pool[offset + j] = strided[size_t(first + k) * stride + j];
-            fragments[first + k].cigarOffset = offset;
+            fragments[first + k].cigarOffset = offset + poolBase;
             offset += len[k];
         }
     }
 }
 
-/// cigarOffset += base for a chunk whose pool lands at 'base' of the caller's pool
-__global__ void addCigarBaseKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, uint32_t base)
+/// What validateCandidates does on the host for the one-shot entry points, on the device copy of a chunk: a candidate that
+/// names an unknown read / contig or lies outside [-ISAAC_EXT_MAX_CYCLES, contigLength] raises bit 1 / bit 2 of 'flag' (the
+/// call then fails as a whole) and is replaced by a harmless one so that the kernels behind never read out of bounds.
+__global__ void validateCandidatesKernel(ReferenceView ref, ReadSetView reads, uint32_t n, isaac_ext_candidate_t *__restrict__ candidates,
+                                         uint32_t *__restrict__ flag)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) fragments[i].cigarOffset += base;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const isaac_ext_candidate_t c = candidates[i];
+        const uint32_t contig = c.contigStrand >> 1;
+        uint32_t bad = 0;
+        if (c.readId >= reads.readTotal || contig >= ref.contigCount) bad = 2u;
+        else if (c.position > int64_t(ref.contigLength[contig]) || c.position < -int64_t(ISAAC_EXT_MAX_CYCLES)) bad = 4u;
+        if (bad)
+        {
+            atomicOr(flag, bad);
+            isaac_ext_candidate_t z = c;
+            z.readId = 0; z.contigStrand = 0; z.position = 0;
+            candidates[i] = z;
+        }
+    }
 }
 
 } // namespace isaac_b200

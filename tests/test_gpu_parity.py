@@ -111,3 +111,26 @@ def test_compact_end_to_end_variant_matches_fixed_stride(capi, gapped):
         ctx.extend_compact(cand, gapped, f1, pool[:1000])
     assert e.value.code == 5
     ctx.close()
+
+
+@pytest.mark.parametrize("gapped", [False, True])
+def test_compact_rejects_bad_candidates(capi, gapped):
+    """the chunked entry points validate on the device: one bad candidate anywhere fails the whole call, and the next call is clean"""
+    genome, sim, reads, cand = small_workload(n_pairs=500, L=100, seed=92)
+    ctx = capi.Context(Config.default(max_read_length=200))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    cand = cand[ctx.ungapped(cand)[0]["cigarLength"] > 0]
+    f1 = np.zeros(len(cand), dtype=capi.FRAGMENT_DTYPE)
+    pool = np.zeros(len(cand) * 10, dtype=np.uint32)
+    for field, value in (("readId", 1 << 30), ("contigStrand", 77 << 1), ("position", 1 << 40), ("position", -5000)):
+        bad = cand.copy()
+        bad[field][len(bad) // 2] = value
+        with pytest.raises(capi.ExtError) as e:
+            ctx.extend_compact(bad, gapped, f1, pool)
+        assert e.value.code == 1, field
+    words = ctx.extend_compact(cand, gapped, f1, pool)
+    f0 = (ctx.gapped(cand, with_masks=False) if gapped else ctx.ungapped(cand, with_masks=False))[0]
+    assert words == int(f0["cigarLength"].sum())
+    assert np.array_equal(f0["mismatchCount"], f1["mismatchCount"])
+    ctx.close()
