@@ -194,49 +194,75 @@ struct CigarScorer
         const uint64_t valid = ONES & (cnt >= 16u ? ~0ull : ((1ull << (4u * cnt)) - 1ull));
         matchCount += __popcll(~notm & valid);
         mismatchCount += __popcll(mism);
-        if (mask && mism)                                            // addMismatchCycle (:171), as a bit over base index
-        {
-            uint64_t c = mism;
-            c = (c | (c >> 3)) & 0x0303030303030303ull;
-            c = (c | (c >> 6)) & 0x000F000F000F000Full;
-            c = (c | (c >> 12)) & 0x000000FF000000FFull;
-            c = (c | (c >> 24)) & 0xFFFFull;
-            mask[P0 >> 6] |= c << (P0 & 63u);
-        }
-        // ---- the sequential part: FP64 sum and longest run of matches
+        const uint32_t mism16 = compactNibbleFlags(mism);            // bit b = base P0 + b is a mismatch
+        if (mask && mism16) mask[P0 >> 6] |= uint64_t(mism16) << (P0 & 63u);   // addMismatchCycle (:171), as a bit over base index
+        // ---- the sequential part: the FP64 sum, one table lookup + one DADD per base in read order.  The table index of
+        // all 16 bases is prepared as bytes first: quality, + 100 for a mismatch, 200 (the +0.0 entry; the sum never is
+        // -0.0, so it is unchanged bit for bit) for inserted bases and the positions past the end of the read.
         const uint4 qv = *reinterpret_cast<const uint4 *>(quality + P0);
         unsigned qw[4] = {qv.x, qv.y, qv.z, qv.w};
-        // Inserted bases and the positions of the last word past the end of the read take table entry 200 (+0.0; the
-        // sum never is -0.0, so it is unchanged bit for bit): patch their quality byte once per word instead of testing
-        // every base.  Positions past the end also reset the run, after the last base that can raise the maximum.
         const uint64_t zero = skip | (ONES & ~valid);
-        notm |= ONES & ~valid;
         if (zero)
         {
+            const uint32_t zero16 = compactNibbleFlags(zero);
 #pragma unroll
             for (unsigned k = 0; k < 4; ++k)
             {
-                const uint32_t nib = uint32_t(zero >> (16u * k)) & 0x1111u;                  // bits 0,4,8,12 -> 0,8,16,24
-                const uint32_t x = (nib & 0x0011u) | ((nib & 0x1100u) << 8);
-                const uint32_t bytes = ((x & 0x00010001u) | ((x & 0x00100010u) << 4)) * 0xFFu;
+                const uint32_t bytes = ((((zero16 >> (4u * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
                 qw[k] = (qw[k] & ~bytes) | (bytes & 0xC8C8C8C8u);
             }
         }
-        const uint32_t mismLo = uint32_t(mism), mismHi = uint32_t(mism >> 32);
-        const uint32_t resetLo = uint32_t(notm | bnd), resetHi = uint32_t((notm | bnd) >> 32);
-        const uint32_t notmLo = uint32_t(notm), notmHi = uint32_t(notm >> 32);
+#pragma unroll
+        for (unsigned k = 0; k < 4; ++k)
+            qw[k] += ((((mism16 >> (4u * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 100u;
 #pragma unroll
         for (unsigned b = 0; b < 16; ++b)
         {
-            const uint32_t bit = 1u << (4u * (b & 7u));
-            unsigned idx = (qw[b >> 2] >> ((b & 3u) * 8u)) & 0xFFu;
-            if ((b < 8 ? mismLo : mismHi) & bit) idx += 100u;
+            const unsigned idx = __byte_perm(qw[b >> 2], 0u, 0x4440u + (b & 3u));
             double v;
             asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tableShared + idx * 8u));
             lp += v;
-            if ((b < 8 ? resetLo : resetHi) & bit) run = 0;
-            if (!((b < 8 ? notmLo : notmHi) & bit)) { ++run; matchesInARow = max(matchesInARow, run); }
         }
+        // ---- longest run of matches (:158-170), on the 16 match bits of the word: 'run' enters from the previous word;
+        // a run also ends in front of the first base of every ALIGN operation ('fresh', bits of bnd)
+        const uint32_t match16 = compactNibbleFlags(~notm & valid);
+        uint32_t bnd16 = compactNibbleFlags(bnd);
+        unsigned start = 0;
+        while (bnd16)
+        {
+            const unsigned j = __ffs(bnd16) - 1u;
+            bnd16 &= bnd16 - 1u;
+            runSegment((match16 >> start) & ((1u << (j - start)) - 1u), j - start);
+            run = 0; start = j;
+        }
+        runSegment(match16 >> start, 16u - start);
+    }
+
+    /// the word's match bits [0, len) (bits above are zero) appended to the current run
+    __device__ __forceinline__ void runSegment(const uint32_t m, const unsigned len)
+    {
+        const unsigned lead = __ffs(~m) - 1u;                        // ones at the bottom; <= len
+        matchesInARow = max(matchesInARow, run + lead);
+        if (lead >= len) { run += len; return; }
+        // longest run inside: y_n = starts of runs of at least n ones, y_(n+k) = y_n & (y_k >> n); greedy over k = 8,4,2,1
+        const uint32_t p2 = m & (m >> 1), p4 = p2 & (p2 >> 2), p8 = p4 & (p4 >> 4);
+        uint32_t cur = ~0u, t; unsigned n = 0;
+        t = cur & p8;        if (t) { cur = t; n = 8; }
+        t = cur & (p4 >> n); if (t) { cur = t; n += 4; }
+        t = cur & (p2 >> n); if (t) { cur = t; n += 2; }
+        t = cur & (m >> n);  if (t) { n += 1; }
+        matchesInARow = max(matchesInARow, n);
+        run = __clz(~(m << (32u - len)));                           // ones at the top of the segment
+    }
+
+    /// bit 4b of a nibble-flag word -> bit b
+    static __device__ __forceinline__ uint32_t compactNibbleFlags(uint64_t c)
+    {
+        c = (c | (c >> 3)) & 0x0303030303030303ull;
+        c = (c | (c >> 6)) & 0x000F000F000F000Full;
+        c = (c | (c >> 12)) & 0x000000FF000000FFull;
+        c = (c | (c >> 24)) & 0xFFFFull;
+        return uint32_t(c);
     }
 
     __device__ __forceinline__ unsigned finish(isaac_ext_fragment_t &out)
