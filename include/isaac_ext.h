@@ -38,7 +38,7 @@ extern "C" {
 #define ISAAC_EXT_E_INVALID_ARG  1 /* reference: common::InvalidParameterException / assert()       */
 #define ISAAC_EXT_E_NO_DEVICE    2 /* no usable CUDA device: there is deliberately no CPU fallback   */
 #define ISAAC_EXT_E_CUDA         3 /* CUDA runtime error, see isaac_ext_last_error                   */
-#define ISAAC_EXT_E_UNSUPPORTED  4 /* sequencing adapters / avoid-smith-waterman      */
+#define ISAAC_EXT_E_UNSUPPORTED  4 /* a combination this library refuses (see isaac_ext_create)       */
 #define ISAAC_EXT_E_CAPACITY     5 /* a fixed capacity of the reference was exceeded (cigar stride)  */
 #define ISAAC_EXT_E_NO_REFERENCE 6 /* isaac_ext_set_reference has not been called                    */
 
@@ -235,6 +235,22 @@ const char *isaac_ext_version(void);
  * upper-case ACGTN and are packed to 2 bit + N-mask and kept resident in HBM. */
 int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
                             const char *const *contigBases, const uint64_t *contigLengths);
+
+/* flowcell::SequencingAdapterMetadata (SequencingAdapterMetadata.hh:36-72). */
+typedef struct isaac_ext_adapter {
+    const char *sequence;            /* in the direction of the reference, upper-case ACGT, 5..126 bases            */
+    uint32_t reverse;                /* isReverse(): the direction the adapter is sequenced in                      */
+    uint32_t clipLength;             /* getClipLength(): 0 = unbounded (clip to the end of the read)               */
+} isaac_ext_adapter_t;
+
+/* The matchSelector::SequencingAdapterList every later call clips with: what FragmentBuilder::build / rescueShadow take as
+ * 'sequencingAdapters' (FragmentBuilder.hh:62-70, ShadowAligner.hh:81-88) and hand to
+ * matchSelector::FragmentSequencingAdapterClipper (FragmentSequencingAdapterClipper.cpp:102-277, SequencingAdapter.cpp:30-139).
+ * The tile calls keep one clipper per read list / rescue like the reference (the first candidate of a strand locates the
+ * adapter); the micro entry points treat every candidate as its own clipper.  count = 0 removes the adapters (the default:
+ * empty list, DefaultAdaptersOption).  One deviation: decideWhichSideToClip reads the contig without a bounds check when
+ * the adapter reaches one end of the read (:190-216); here bases outside the contig count as mismatches. */
+int isaac_ext_set_adapters(isaac_ext_ctx *ctx, uint32_t count, const isaac_ext_adapter_t *adapters);
 
 /* Decodes one tile's BCL bytes (Read::decodeBcl, Read.cpp:32-73) into the device-resident read set used
  * by the batch calls below.  Stays valid until the next isaac_ext_set_reads on this context. */

@@ -33,7 +33,7 @@ EXPORTS = [
     "isaac_ext_gapped_batch", "isaac_ext_ungapped_batch_device", "isaac_ext_gapped_batch_device",
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
-    "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends",
+    "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
 ]
 
 
@@ -84,6 +84,12 @@ class Context:
         lens = (ctypes.c_uint64 * n)(*[c.size for c in contigs])
         self._check(_lib.isaac_ext_set_reference(self._h, ctypes.c_uint32(n), ptrs, lens))
         self.contig_lengths = [c.size for c in contigs]
+
+    def set_adapters(self, adapters):
+        """matchSelector::SequencingAdapterList for every later call: (sequence, reverse, clipLength) tuples; () clears"""
+        from .types import adapter_array
+        arr = adapter_array(adapters)
+        self._check(_lib.isaac_ext_set_adapters(self._h, ctypes.c_uint32(len(adapters)), arr))
 
     def set_reads(self, reads):
         assert isinstance(reads, ReadSet)

@@ -40,6 +40,11 @@ struct PipelineState
     DeviceBuffer<ShadowTask> dShadowTasks;
     DeviceBuffer<int> dShadowScratch;
     DeviceBuffer<uint32_t> dTaskBegin, dTaskCount, dPoolSize;
+    // sequencing adapters: first candidate of every clipper slot, slot of every candidate (rescue)
+    PinnedBuffer<isaac_ext_candidate_t> hAdapterFirst;
+    DeviceBuffer<isaac_ext_candidate_t> dAdapterFirst;
+    PinnedBuffer<uint32_t> hSlot;
+    DeviceBuffer<uint32_t> dSlot;
     // flattened results handed back to the caller
     std::vector<WorkFragment> work;
     std::vector<uint32_t> indelCigars;
@@ -53,6 +58,7 @@ struct PipelineState
     {
         hCand1.release(); hCand3.release(); hFrag1.release(); hFrag3.release(); hCig1.release(); hCig3.release();
         hTasks.release(); hIndel.release(); hShadowTasks.release(); hTaskBegin.release(); hTaskCount.release();
+        hAdapterFirst.release(); dAdapterFirst.release(); hSlot.release(); dSlot.release();
         dCand.release(); dFrag.release(); dCig.release(); dTasks.release(); dIndel.release(); dShadowTasks.release();
         dShadowScratch.release(); dTaskBegin.release(); dTaskCount.release(); dPoolSize.release();
     }

@@ -70,6 +70,14 @@ struct isaac_ext_ctx
     ReadSetView reads{};
     bool haveReads = false;
 
+    // sequencing adapters (isaac_ext_set_adapters; kernels_adapter.cuh); count == 0: no adapter kernel ever runs
+    DeviceBuffer<uint8_t> adapterCodes, adapterReverse;
+    DeviceBuffer<int8_t> adapterKmers;
+    DeviceBuffer<uint32_t> adapterLength, adapterClipLength;
+    AdapterView adapters{};
+    DeviceBuffer<uint32_t> dAdapterClip;          // one packed clip word per candidate of the pass in flight
+    DeviceBuffer<AdapterRange> dAdapterRanges;    // one per clipper slot of the tile call in flight
+
     // staging for the host-pointer entry points
     DeviceBuffer<isaac_ext_candidate_t> dCandidates;
     DeviceBuffer<isaac_ext_fragment_t> dFragments;
@@ -231,6 +239,8 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readQualityStrand.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
+    ctx->adapterCodes.release(); ctx->adapterReverse.release(); ctx->adapterKmers.release(); ctx->adapterLength.release();
+    ctx->adapterClipLength.release(); ctx->dAdapterClip.release(); ctx->dAdapterRanges.release();
     for (int k = 0; k < 2; ++k)
     {
         if (ctx->swStream[k]) { cudaStreamSynchronize(ctx->swStream[k]); cudaStreamDestroy(ctx->swStream[k]); }
@@ -288,6 +298,53 @@ extern "C" int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
     ctx->ref.contigCount = contigCount;
     ctx->ref.totalBases = total;
     ctx->haveReference = true;
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_set_adapters(isaac_ext_ctx *ctx, uint32_t count, const isaac_ext_adapter_t *adapters)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (count && !adapters) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null adapter list");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    ctx->adapters = AdapterView{};
+    if (!count) return ISAAC_EXT_OK;
+    std::vector<uint8_t> codes(size_t(count) * ADAPTER_STRIDE, 0), reverse(count);
+    std::vector<int8_t> kmers(size_t(count) * ADAPTER_KMERS, int8_t(-1));            // UNINITIALIZED_POSITION (SequencingAdapter.hh:41)
+    std::vector<uint32_t> length(count), clipLength(count);
+    for (uint32_t a = 0; a < count; ++a)
+    {
+        const char *s = adapters[a].sequence;
+        const size_t n = s ? std::strlen(s) : 0;
+        // SequencingAdapter.cpp:35-38; shorter than one k-mer could never be found
+        if (n < ADAPTER_KMER || n >= 127) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "adapter sequence must have 5..126 bases");
+        if (adapters[a].clipLength && n > adapters[a].clipLength)
+            return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "Clip length cannot be shorter than the adapter sequence");
+        for (size_t i = 0; i < n; ++i)
+        {
+            const char *at = std::strchr("ACGT", s[i]);
+            if (!at || !s[i]) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "adapter sequences must be upper-case ACGT");
+            codes[size_t(a) * ADAPTER_STRIDE + i] = uint8_t(at - "ACGT");
+        }
+        // kmerPositions_ (SequencingAdapter.cpp:40-57): first position of every 5-mer, -2 once it repeats
+        for (size_t i = 0; i + ADAPTER_KMER <= n; ++i)
+        {
+            unsigned kmer = 0;
+            for (unsigned j = 0; j < ADAPTER_KMER; ++j) kmer = (kmer << 2) | codes[size_t(a) * ADAPTER_STRIDE + i + j];
+            int8_t &pos = kmers[size_t(a) * ADAPTER_KMERS + kmer];
+            if (pos == -1) pos = int8_t(i); else pos = int8_t(-2);                  // NON_UNIQUE_KMER_POSITION
+        }
+        length[a] = uint32_t(n); clipLength[a] = adapters[a].clipLength; reverse[a] = adapters[a].reverse ? 1 : 0;
+    }
+    CK(ctx->adapterCodes.reserve(codes.size())); CK(ctx->adapterReverse.reserve(count)); CK(ctx->adapterKmers.reserve(kmers.size()));
+    CK(ctx->adapterLength.reserve(count)); CK(ctx->adapterClipLength.reserve(count));
+    CK(cudaMemcpy(ctx->adapterCodes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->adapterReverse.p, reverse.data(), count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->adapterKmers.p, kmers.data(), kmers.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->adapterLength.p, length.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->adapterClipLength.p, clipLength.data(), count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->adapters = AdapterView{count, ctx->adapterCodes.p, ctx->adapterKmers.p, ctx->adapterLength.p, ctx->adapterClipLength.p,
+                                ctx->adapterReverse.p};
     return ISAAC_EXT_OK;
 }
 
@@ -356,24 +413,65 @@ static int validateCandidates(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_ca
     return ISAAC_EXT_OK;
 }
 
+/// The micro entry points treat every candidate as its own adapter clipper (checkInitStrand + clip on the same candidate,
+/// like testSequencingAdapter.cpp:159-182); *clipOut = nullptr when no adapters are set.
+static int adapterSelfClip(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *dCandidates, cudaStream_t stream,
+                           const uint32_t **clipOut)
+{
+    *clipOut = nullptr;
+    if (!ctx->adapters.count || !n) return ISAAC_EXT_OK;
+    if (n > ctx->dAdapterClip.capacity) CK(cudaStreamSynchronize(stream));      // an earlier pass may still read the old buffer
+    CK(ctx->dAdapterClip.reserve(n));
+    adapterSelfClipKernel<<<gridFor(ctx, n, 128, 16), 128, 0, stream>>>(ctx->adapters, ctx->ref, ctx->reads, n, dCandidates, ctx->dAdapterClip.p);
+    ++ctx->launches;
+    *clipOut = ctx->dAdapterClip.p;
+    return ctx->cuda(cudaGetLastError(), "adapterSelfClipKernel");
+}
+
+/// Clip words of candidates that share clippers: ranges[slot] was filled by adapterInitKernel, slot = dSlotOf[i] or, with
+/// dSlotOf == nullptr, readId * 2 + reverse.
+static int adapterSlotClip(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *dCandidates, const uint32_t *dSlotOf,
+                           cudaStream_t stream, const uint32_t **clipOut)
+{
+    *clipOut = nullptr;
+    if (!ctx->adapters.count || !n) return ISAAC_EXT_OK;
+    if (n > ctx->dAdapterClip.capacity) CK(cudaStreamSynchronize(stream));
+    CK(ctx->dAdapterClip.reserve(n));
+    adapterClipKernel<<<gridFor(ctx, n, 128, 16), 128, 0, stream>>>(ctx->ref, ctx->reads, n, dCandidates, dSlotOf, ctx->dAdapterRanges.p,
+                                                                    ctx->dAdapterClip.p);
+    ++ctx->launches;
+    *clipOut = ctx->dAdapterClip.p;
+    return ctx->cuda(cudaGetLastError(), "adapterClipKernel");
+}
+
+static int ungappedDevice(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *dCandidates, isaac_ext_fragment_t *dFragmentsOut,
+                          uint32_t *dCigarOut, uint64_t *dMismatchMaskOut, cudaStream_t stream, const uint32_t *adapterClip)
+{
+    if (!n) return ISAAC_EXT_OK;
+    ungappedKernel<<<gridFor(ctx, n, 128, 16), 128, 0, stream>>>(ctx->ref, ctx->reads, ctx->sp, n, dCandidates, dFragmentsOut, dCigarOut,
+                                                                 dMismatchMaskOut, adapterClip);
+    ++ctx->launches;
+    return ctx->cuda(cudaGetLastError(), "ungappedKernel");
+}
+
 extern "C" int isaac_ext_ungapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, void *dFragmentsOut,
                                                void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
-    ungappedKernel<<<gridFor(ctx, n, 128, 16), 128, 0, cudaStream_t(cudaStream)>>>(
-        ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates),
-        static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-        static_cast<uint64_t *>(dMismatchMaskOut));
-    ++ctx->launches;
-    return ctx->cuda(cudaGetLastError(), "ungappedKernel");
+    const uint32_t *clip = nullptr;
+    const int rc = adapterSelfClip(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cudaStream_t(cudaStream), &clip);
+    if (rc) return rc;
+    return ungappedDevice(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), static_cast<isaac_ext_fragment_t *>(dFragmentsOut),
+                          static_cast<uint32_t *>(dCigarOut), static_cast<uint64_t *>(dMismatchMaskOut), cudaStream_t(cudaStream), clip);
 }
 
 /// Split path (kernels3.cuh): chunks of pairs alternate between two streams so that the forward kernel of one chunk
 /// overlaps the trace+score kernel of the previous one; each stream owns one set of direction planes.
 static int gappedSplit(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *dCandidates, uint32_t cigarStride,
-                       isaac_ext_fragment_t *dFragments, uint32_t *dCigars, uint64_t *dMasks, cudaStream_t user)
+                       isaac_ext_fragment_t *dFragments, uint32_t *dCigars, uint64_t *dMasks, cudaStream_t user,
+                       const uint32_t *adapterClip)
 {
     const unsigned maxLength = std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]);
     const size_t rowWords = size_t(SW2_FLAG_WORDS) * maxLength;
@@ -399,11 +497,12 @@ static int gappedSplit(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate
         const uint32_t chunk = (count + 1) / 2;
         swForwardKernel<<<(chunk + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
             ctx->ref, ctx->reads, ctx->sp, count, dCandidates + firstCandidate, ctx->swPlanes[k].p, uint32_t(stride),
-            ctx->swEndCells[k].p);
+            ctx->swEndCells[k].p, adapterClip ? adapterClip + firstCandidate : nullptr);
         swTraceScoreKernel<<<(count + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
             ctx->ref, ctx->reads, ctx->sp, count, uint32_t(firstCandidate), dCandidates + firstCandidate, ctx->swPlanes[k].p,
             uint32_t(stride), ctx->swEndCells[k].p, cigarStride, dFragments + firstCandidate, dCigars + firstCandidate * cigarStride,
-            dMasks ? dMasks + firstCandidate * ISAAC_EXT_MASK_WORDS : nullptr, ctx->errorFlag.p);
+            dMasks ? dMasks + firstCandidate * ISAAC_EXT_MASK_WORDS : nullptr, ctx->errorFlag.p,
+            adapterClip ? adapterClip + firstCandidate : nullptr);
         ctx->launches += 2;
     }
     for (unsigned b = 0; b < buffers; ++b)
@@ -414,16 +513,29 @@ static int gappedSplit(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate
     return ctx->cuda(cudaGetLastError(), "swForwardKernel / swTraceScoreKernel");
 }
 
+static int gappedDevice(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, uint32_t cigarStride,
+                        void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream, const uint32_t *adapterClip);
+
 extern "C" int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, uint32_t cigarStride,
                                              void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
+    const uint32_t *clip = nullptr;
+    const int rc = adapterSelfClip(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cudaStream_t(cudaStream), &clip);
+    if (rc) return rc;
+    return gappedDevice(ctx, n, dCandidates, cigarStride, dFragmentsOut, dCigarOut, dMismatchMaskOut, cudaStream, clip);
+}
+
+static int gappedDevice(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates, uint32_t cigarStride,
+                        void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream, const uint32_t *adapterClip)
+{
+    if (!n) return ISAAC_EXT_OK;
     if (ctx->swImpl == 3)
         return gappedSplit(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
                            static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-                           static_cast<uint64_t *>(dMismatchMaskOut), cudaStream_t(cudaStream));
+                           static_cast<uint64_t *>(dMismatchMaskOut), cudaStream_t(cudaStream), adapterClip);
     const unsigned items = ctx->swImpl == 2 ? (n + 1) / 2 : n;     // the packed kernel takes two candidates per thread
     const unsigned grid = gridFor(ctx, items, SW_BLOCK, ctx->swBlocksPerSm);
     const int rc = ensureTraceback(ctx, grid, SW_BLOCK, std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]));
@@ -432,12 +544,12 @@ extern "C" int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, con
         gappedKernel2<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
             ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
             static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p);
+            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p, adapterClip);
     else
         gappedKernel<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
             ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
             static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p);
+            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p, adapterClip);
     ++ctx->launches;
     return ctx->cuda(cudaGetLastError(), "gappedKernel");
 }

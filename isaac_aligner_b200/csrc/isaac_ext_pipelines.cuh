@@ -4,26 +4,57 @@
 namespace
 {
 
+/// the clippers of a tile call: ranges[slot] from the first candidate of every slot (checkInitStrand, FragmentBuilder.cpp:173)
+int initAdapterSlots(isaac_ext_ctx *ctx, uint32_t slots, const isaac_ext_candidate_t *dFirst)
+{
+    if (!ctx->adapters.count || !slots) return ISAAC_EXT_OK;
+    CK(ctx->dAdapterRanges.reserve(slots));
+    adapterInitKernel<<<gridFor(ctx, slots, 128, 16), 128, 0, ctx->stream>>>(ctx->adapters, ctx->ref, ctx->reads, slots, dFirst, ctx->dAdapterRanges.p);
+    ++ctx->launches;
+    return ctx->cuda(cudaGetLastError(), "adapterInitKernel");
+}
+
+/// the candidates of the tile calls share clippers: slot = hSlotOf[i], or readId * 2 + reverse with hSlotOf == nullptr
+int tileAdapterClip(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *dCand, const uint32_t *hSlotOf, const uint32_t **clip)
+{
+    *clip = nullptr;
+    if (!ctx->adapters.count || !n) return ISAAC_EXT_OK;
+    PipelineState &ps = ctx->pipeline;
+    if (hSlotOf)
+    {
+        CK(ps.dSlot.reserve(n));
+        CK(cudaMemcpyAsync(ps.dSlot.p, hSlotOf, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return adapterSlotClip(ctx, n, dCand, hSlotOf ? ps.dSlot.p : nullptr, ctx->stream, clip);
+}
+
 int runUngapped(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *hCand, isaac_ext_fragment_t *hFrag, uint32_t *hCig)
 {
     PipelineState &ps = ctx->pipeline;
     if (!n) return ISAAC_EXT_OK;
     CK(ps.dCand.reserve(n)); CK(ps.dFrag.reserve(n)); CK(ps.dCig.reserve(size_t(n) * 3));
     CK(cudaMemcpyAsync(ps.dCand.p, hCand, size_t(n) * sizeof(*hCand), cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = isaac_ext_ungapped_batch_device(ctx, n, ps.dCand.p, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream);
+    const uint32_t *clip = nullptr;
+    int rc = tileAdapterClip(ctx, n, ps.dCand.p, nullptr, &clip);
+    if (rc) return rc;
+    rc = ungappedDevice(ctx, n, ps.dCand.p, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream, clip);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hFrag, ps.dFrag.p, size_t(n) * sizeof(*hFrag), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hCig, ps.dCig.p, size_t(n) * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     return ctx->cuda(cudaStreamSynchronize(ctx->stream), "ungapped pass");
 }
 
-int runGapped(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *hCand, uint32_t stride, isaac_ext_fragment_t *hFrag, uint32_t *hCig)
+int runGapped(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *hCand, uint32_t stride, isaac_ext_fragment_t *hFrag, uint32_t *hCig,
+              const uint32_t *hSlotOf = nullptr)
 {
     PipelineState &ps = ctx->pipeline;
     if (!n) return ISAAC_EXT_OK;
     CK(ps.dCand.reserve(n)); CK(ps.dFrag.reserve(n)); CK(ps.dCig.reserve(size_t(n) * stride));
     CK(cudaMemcpyAsync(ps.dCand.p, hCand, size_t(n) * sizeof(*hCand), cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = isaac_ext_gapped_batch_device(ctx, n, ps.dCand.p, stride, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream);
+    const uint32_t *clip = nullptr;
+    int rc = tileAdapterClip(ctx, n, ps.dCand.p, hSlotOf, &clip);
+    if (rc) return rc;
+    rc = gappedDevice(ctx, n, ps.dCand.p, stride, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream, clip);
     if (rc) return rc;
     CK(cudaMemcpyAsync(hFrag, ps.dFrag.p, size_t(n) * sizeof(*hFrag), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hCig, ps.dCig.p, size_t(n) * stride * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -182,17 +213,34 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
     const uint64_t n1 = partCount[parts];
     if (n1 > 0xFFFFFFF0ull / GAPPED_STRIDE) return ctx->fail(ISAAC_EXT_E_CAPACITY, "too many candidates in one batch");
     CK(ps.hCand1.reserve(n1)); CK(ps.hFrag1.reserve(n1)); CK(ps.hCig1.reserve(n1 * 3));
+    const bool withAdapters = ctx->adapters.count != 0;
+    if (withAdapters) CK(ps.hAdapterFirst.reserve(lists * 2));
     parallelRanges(T, nClusters, [&](unsigned t, size_t b, size_t e) {
         uint64_t at = partCount[t];
         for (size_t l = b * rc; l < e * rc; ++l)
+        {
+            // one FragmentSequencingAdapterClipper per read list (:164): its two strands are slots l * 2 + reverse, each
+            // initialised by the first fragment of that strand in list order (:173)
+            if (withAdapters) ps.hAdapterFirst.p[l * 2].readId = ps.hAdapterFirst.p[l * 2 + 1].readId = ADAPTER_NO_CANDIDATE;
             for (unsigned k = 0; k < listCount[l]; ++k)
             {
                 WorkFragment &w = ps.work[listBegin[l] + k];
                 w.slot = uint32_t(at);
-                ps.hCand1.p[at++] = candidateOf(w.f, w.f.position);
+                ps.hCand1.p[at] = candidateOf(w.f, w.f.position);
+                if (withAdapters && ps.hAdapterFirst.p[l * 2 + (w.f.reverse ? 1 : 0)].readId == ADAPTER_NO_CANDIDATE)
+                    ps.hAdapterFirst.p[l * 2 + (w.f.reverse ? 1 : 0)] = ps.hCand1.p[at];
+                ++at;
             }
+        }
     });
     timer.mark("P1 dense write");
+    if (withAdapters)
+    {
+        CK(ps.dAdapterFirst.reserve(lists * 2));
+        CK(cudaMemcpyAsync(ps.dAdapterFirst.p, ps.hAdapterFirst.p, lists * 2 * sizeof(isaac_ext_candidate_t), cudaMemcpyHostToDevice, ctx->stream));
+        const int rca = initAdapterSlots(ctx, uint32_t(lists * 2), ps.dAdapterFirst.p);
+        if (rca) return rca;
+    }
     // ---- K1: UngappedAligner::alignUngapped of every candidate (:174)
     int rcode = runUngapped(ctx, uint32_t(n1), ps.hCand1.p, ps.hFrag1.p, ps.hCig1.p);
     if (rcode) return rcode;
@@ -463,7 +511,19 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
         {
             CK(ps.dFrag.reserve(poolSize)); CK(ps.dCig.reserve(size_t(poolSize) * 3));
             CK(ps.hFrag1.reserve(poolSize)); CK(ps.hCig1.reserve(size_t(poolSize) * 3));
-            const int rc = isaac_ext_ungapped_batch_device(ctx, poolSize, ps.dCand.p, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream);
+            const uint32_t *clip = nullptr;
+            if (ctx->adapters.count)
+            {
+                CK(ps.dAdapterFirst.reserve(n)); CK(ps.dSlot.reserve(poolSize));
+                shadowAdapterSlotsKernel<<<gridFor(ctx, uint64_t(n) * 32, 128, 16), 128, 0, ctx->stream>>>(
+                    n, ps.dTaskBegin.p, ps.dTaskCount.p, ps.dCand.p, ps.dAdapterFirst.p, ps.dSlot.p);
+                ++ctx->launches;
+                CK(cudaGetLastError());
+                int rca = initAdapterSlots(ctx, n, ps.dAdapterFirst.p);
+                if (!rca) rca = adapterSlotClip(ctx, poolSize, ps.dCand.p, ps.dSlot.p, ctx->stream, &clip);
+                if (rca) return rca;
+            }
+            const int rc = ungappedDevice(ctx, poolSize, ps.dCand.p, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream, clip);
             if (rc) return rc;
             CK(cudaMemcpyAsync(ps.hFrag1.p, ps.dFrag.p, size_t(poolSize) * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(ps.hCig1.p, ps.dCig.p, size_t(poolSize) * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -478,6 +538,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
         std::vector<int64_t> best(n, -1);
         std::vector<uint8_t> full(n, 0);
         std::vector<std::vector<uint64_t>> gapTargets(parts);
+        std::vector<std::vector<uint32_t>> gapRequests(parts);     // the rescue call (= adapter clipper) of every target
         std::vector<uint64_t> gapBegin(parts + 1, 0);
         parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
             for (size_t i = b; i < e; ++i)
@@ -502,7 +563,10 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
                     for (unsigned k = 0; k + 1 < size; ++k)
                         if (list[k + 1].f.position - list[k].f.position < long(ISAAC_EXT_SW_DISTANCE_CUTOFF) &&
                             ISAAC_EXT_SW_MISMATCH_CUTOFF < list[k].f.mismatchCount)                   // :249-253
+                        {
                             gapTargets[t].push_back(begin + k);
+                            gapRequests[t].push_back(uint32_t(i));
+                        }
             }
             gapBegin[t + 1] = gapTargets[t].size();
         });
@@ -512,14 +576,16 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
         if (n3)
         {
             CK(ps.hCand3.reserve(n3)); CK(ps.hFrag3.reserve(n3)); CK(ps.hCig3.reserve(n3 * GAPPED_STRIDE));
+            CK(ps.hSlot.reserve(n3));
             parallelRanges(T, n, [&](unsigned t, size_t, size_t) {
                 for (size_t k = 0; k < gapTargets[t].size(); ++k)
                 {
                     const WorkFragment &w = ps.work[gapTargets[t][k]];
                     ps.hCand3.p[gapBegin[t] + k] = candidateOf(w.f, pools.unclippedPosition(w));
+                    ps.hSlot.p[gapBegin[t] + k] = gapRequests[t][k];
                 }
             });
-            const int rc = runGapped(ctx, uint32_t(n3), ps.hCand3.p, GAPPED_STRIDE, ps.hFrag3.p, ps.hCig3.p);
+            const int rc = runGapped(ctx, uint32_t(n3), ps.hCand3.p, GAPPED_STRIDE, ps.hFrag3.p, ps.hCig3.p, ps.hSlot.p);
             if (rc) return rc;
             pools.pools[2] = ps.hCig3.p;
         }

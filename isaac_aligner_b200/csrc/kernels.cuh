@@ -8,6 +8,7 @@
 #pragma once
 #include "device_types.cuh"
 #include "score.cuh"
+#include "kernels_adapter.cuh"
 #include "sw.cuh"
 
 namespace isaac_b200
@@ -133,7 +134,7 @@ __device__ __forceinline__ void initFragment(isaac_ext_fragment_t &o, const isaa
 __global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
                                const isaac_ext_candidate_t *__restrict__ candidates,
                                isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
-                               uint64_t *__restrict__ masks)
+                               uint64_t *__restrict__ masks, const uint32_t *__restrict__ adapterClip = nullptr)
 {
     __shared__ double tables[201];
     const ScoreParams sp = stageScoreTables(spGlobal, tables);
@@ -151,6 +152,7 @@ __global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads,
         // resetAlignment + resetClipping: position is the unclipped candidate position, clips are 0 (UngappedAligner.cpp:48-49)
         FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};
         long begin = 0, end = L;
+        if (adapterClip) applyAdapterClip(adapterClip[i], L, f, begin, end);            // :59
         clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :60
         clipReference(long(ref.contigLength[contigId]), f, begin, end);                 // :62
         o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;
@@ -182,7 +184,8 @@ constexpr unsigned SW_OPS_CAP = 64;
 __global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
                              const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
                              isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
-                             uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
+                             uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag,
+                             const uint32_t *__restrict__ adapterClip = nullptr)
 {
     __shared__ double tables[201];
     const ScoreParams sp = stageScoreTables(spGlobal, tables);
@@ -203,6 +206,7 @@ __global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, c
         o.cigarOffset = i * cigarStride;
         FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};              // GappedAligner.cpp:175-176
         long begin = 0, end = L;
+        if (adapterClip) applyAdapterClip(adapterClip[i], L, f, begin, end);            // :186
         clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :187
         clipReference(contigLength, f, begin, end);                                     // :189
         o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;

@@ -19,7 +19,8 @@ struct GappedPrep
 };
 
 __device__ __forceinline__ GappedPrep prepareGapped(const ReferenceView &ref, const ReadSetView &reads,
-                                                    const isaac_ext_candidate_t c)
+                                                    const isaac_ext_candidate_t c,
+                                                    const uint32_t *__restrict__ adapterClip = nullptr, const uint32_t index = 0)
 {
     GappedPrep p;
     p.c = c;
@@ -28,6 +29,7 @@ __device__ __forceinline__ GappedPrep prepareGapped(const ReferenceView &ref, co
     const long contigLength = long(ref.contigLength[p.contigId]);
     p.f = FragmentState{c.position, 0u, 0u, bool(c.contigStrand & 1u)};          // :175-176
     p.begin = 0; p.end = p.L;
+    if (adapterClip) applyAdapterClip(adapterClip[index], p.L, p.f, p.begin, p.end);   // :186
     clipReadMasking(p.L, reads.endCyclesMasked[c.readId], p.f, p.begin, p.end);  // :187
     clipReference(contigLength, p.f, p.begin, p.end);                            // :189
     p.sequenceLength = unsigned(p.end - p.begin);
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(128, ISAAC_SW2_MIN_BLOCKS)
 gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
               const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
               isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
-              uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
+              uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag,
+              const uint32_t *__restrict__ adapterClip = nullptr)
 {
     // the two 100-entry log-probability tables are looked up once per base: keep them in shared memory
     __shared__ double tables[201];      // [0,100) logMatch, [100,200) logMismatch, [200] = 0.0 (contiguous in global too)
@@ -107,8 +110,8 @@ gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParam
     {
         const uint32_t iA = 2 * t, iB = 2 * t + 1;
         const bool haveB = iB < n;
-        const GappedPrep pa = prepareGapped(ref, reads, candidates[iA]);
-        GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA]);
+        const GappedPrep pa = prepareGapped(ref, reads, candidates[iA], adapterClip, iA);
+        GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA], adapterClip, haveB ? iB : iA);
         if (!haveB) pb.run = false;
         const unsigned LA = pa.run ? pa.sequenceLength : 0u, LB = pb.run ? pb.sequenceLength : 0u;
         int jj[2] = {0, 0}; unsigned type[2] = {0, 0};

@@ -29,15 +29,15 @@ namespace isaac_b200
 __global__ void __launch_bounds__(128, 4)
 swForwardKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
                 const isaac_ext_candidate_t *__restrict__ candidates, uint32_t *__restrict__ planes, uint32_t pairStride,
-                uint32_t *__restrict__ endCells)
+                uint32_t *__restrict__ endCells, const uint32_t *__restrict__ adapterClip = nullptr)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t pairs = (n + 1) / 2;
     if (t >= pairs) return;
     const uint32_t iA = 2 * t, iB = 2 * t + 1;
     const bool haveB = iB < n;
-    const GappedPrep pa = prepareGapped(ref, reads, candidates[iA]);
-    GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA]);
+    const GappedPrep pa = prepareGapped(ref, reads, candidates[iA], adapterClip, iA);
+    GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA], adapterClip, haveB ? iB : iA);
     if (!haveB) pb.run = false;
     const unsigned LA = pa.run ? pa.sequenceLength : 0u, LB = pb.run ? pb.sequenceLength : 0u;
     int jj[2] = {0, 0}; unsigned type[2] = {0, 0};
@@ -61,14 +61,15 @@ __global__ void __launch_bounds__(128, ISAAC_TRACE_MIN_BLOCKS)
 swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n, uint32_t base,
                    const isaac_ext_candidate_t *__restrict__ candidates, const uint32_t *__restrict__ planes, uint32_t pairStride,
                    const uint32_t *__restrict__ endCells, uint32_t cigarStride, isaac_ext_fragment_t *__restrict__ fragments,
-                   uint32_t *__restrict__ cigars, uint64_t *__restrict__ masks, uint32_t *__restrict__ errorFlag)
+                   uint32_t *__restrict__ cigars, uint64_t *__restrict__ masks, uint32_t *__restrict__ errorFlag,
+                   const uint32_t *__restrict__ adapterClip = nullptr)
 {
     __shared__ double tables[201];
     const ScoreParams sp = stageScoreTables(spGlobal, tables);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t pair = i >> 1;
-    const GappedPrep p = prepareGapped(ref, reads, candidates[i]);
+    const GappedPrep p = prepareGapped(ref, reads, candidates[i], adapterClip, i);
     isaac_ext_fragment_t o;
     initFragment(o, p.c, reads.readCount);
     o.cigarOffset = (base + i) * cigarStride;      // records and CIGAR rows are addressed from the batch start

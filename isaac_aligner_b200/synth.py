@@ -140,6 +140,34 @@ def simulate_pairs(genome, n_pairs, L=150, seed=SEED_READS, snp_rate=1e-3, indel
     return sim
 
 
+def insert_adapters(sim, sequences, fraction=0.3, seed=SEED_READS + 7, read_through=True, min_keep=20):
+    """Puts sequencing adapters into a fraction of the simulated reads, in sequencing order (the BCL order): bases
+    [cut, cut + len) become one of 'sequences' (chosen at random); with read_through the bases behind it are random (a short
+    insert: the read runs through the adapter into the flowcell oligos), otherwise they stay as simulated (a mate-pair style
+    junction adapter: both sides still match the genome).  Qualities and N calls are kept.  Returns the cut points
+    (n_pairs, 2), -1 = untouched."""
+    rng = _rng(seed)
+    L = sim.L
+    n = sim.bcl.shape[0]
+    cuts = np.full((n, 2), -1, dtype=np.int32)
+    codes = [np.array([_CODE[ord(ch)] for ch in s], dtype=np.uint8) for s in sequences]
+    for r in range(2):
+        view = sim.bcl[:, r * L:(r + 1) * L]
+        pick = np.nonzero(rng.random(n) < fraction)[0]
+        for i in pick:
+            a = codes[int(rng.integers(0, len(codes)))]
+            cut = int(rng.integers(min_keep, L - 4))
+            cuts[i, r] = cut
+            row = view[i]
+            new = (row & 3).copy()
+            m = min(a.size, L - cut)
+            new[cut:cut + m] = a[:m]
+            if read_through and cut + m < L:
+                new[cut + m:] = rng.integers(0, 4, size=L - cut - m)
+            view[i] = np.where(row == 0, 0, (row & 0xFC) | new)
+    return cuts
+
+
 def microbench_candidates(sim, genome, per_read=4, seed=SEED_READS + 2, fractions=(0.6, 0.2, 0.2)):
     """for every read 'per_read' (read, window) pairs: true locus / true locus shifted by
     +-(1..7) bp / uniform random locus with the given fractions.  Returns a CANDIDATE_DTYPE array."""

@@ -43,6 +43,25 @@ class Config(ctypes.Structure):
                    max_read_length, device, host_threads)
 
 
+class Adapter(ctypes.Structure):
+    """isaac_ext_adapter_t = flowcell::SequencingAdapterMetadata"""
+    _fields_ = [("sequence", ctypes.c_char_p), ("reverse", ctypes.c_uint32), ("clipLength", ctypes.c_uint32)]
+
+
+# flowcell/SequencingAdapterMetadata.cpp:29-39: (sequence, reverse, clipLength; 0 = unbounded)
+STANDARD_ADAPTERS = (("AGATCGGAAGAGC", False, 0), ("GCTCTTCCGATCT", True, 0))
+NEXTERA_STANDARD_ADAPTERS = (("CTGTCTCTTATACACATCT", False, 0), ("AGATGTGTATAAGAGACAG", True, 0))
+NEXTERA_MATEPAIR_ADAPTERS = (("CTGTCTCTTATACACATCT", False, 19), ("AGATGTGTATAAGAGACAG", False, 19))
+
+
+def adapter_array(adapters):
+    """(sequence, reverse, clipLength) tuples -> ctypes array of isaac_ext_adapter_t"""
+    arr = (Adapter * max(1, len(adapters)))()
+    for i, (seq, reverse, clip) in enumerate(adapters):
+        arr[i] = Adapter(seq.encode() if isinstance(seq, str) else seq, 1 if reverse else 0, int(clip))
+    return arr
+
+
 class Reads(ctypes.Structure):
     """isaac_ext_reads_t"""
     _fields_ = [

@@ -26,6 +26,10 @@ typedef struct oracle_genome {
 
 const char *oracle_kind(void);          /* "reference" or "port" */
 
+/* The matchSelector::SequencingAdapterList every later call of this library clips with (see isaac_ext_set_adapters);
+ * process-wide, count = 0 clears it. */
+int oracle_set_adapters(uint32_t count, const isaac_ext_adapter_t *adapters);
+
 /* BandedSmithWaterman::align, see isaac_ext_banded_sw_batch.  threads > 1 splits the batch over std::threads
  * (one BandedSmithWaterman object per thread, like the reference keeps one per TemplateBuilder). */
 int oracle_banded_sw_batch(uint32_t n, const char *queries, const uint64_t *queryOffsets,

@@ -186,6 +186,23 @@ extern "C" int oracle_banded_sw_batch(uint32_t n, const char *queries, const uin
     return ISAAC_EXT_OK;
 }
 
+/// the adapter list of oracle_set_adapters: what isaac-align builds from --default-adapters (process-wide, test harness only)
+static alignment::matchSelector::SequencingAdapterList &currentAdapters()
+{
+    static alignment::matchSelector::SequencingAdapterList adapters;
+    return adapters;
+}
+
+extern "C" int oracle_set_adapters(uint32_t count, const isaac_ext_adapter_t *adapters)
+{
+    alignment::matchSelector::SequencingAdapterList &list = currentAdapters();
+    list.clear();
+    for (uint32_t a = 0; a < count; ++a)
+        list.push_back(alignment::matchSelector::SequencingAdapter(
+            flowcell::SequencingAdapterMetadata(adapters[a].sequence, adapters[a].reverse != 0, adapters[a].clipLength)));
+    return ISAAC_EXT_OK;
+}
+
 static int extendBatch(const bool gapped, const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
                        const isaac_ext_config_t *cfg, uint32_t n, const isaac_ext_candidate_t *candidates,
                        uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
@@ -196,7 +213,7 @@ static int extendBatch(const bool gapped, const oracle_genome_t *genome, const i
         const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
-        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        const alignment::matchSelector::SequencingAdapterList &adapterList = currentAdapters();
         const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
         parallelFor(n, threads, [&](uint32_t, uint32_t b, uint32_t e) {
             const alignment::fragmentBuilder::UngappedAligner ungapped(
@@ -216,7 +233,7 @@ static int extendBatch(const bool gapped, const oracle_genome_t *genome, const i
                 fragment.reverse = (c.contigStrand & 1);
                 fragment.contigId = (c.contigStrand >> 1);
                 fragment.position = c.position;
-                alignment::matchSelector::FragmentSequencingAdapterClipper clipper(noAdapters);
+                alignment::matchSelector::FragmentSequencingAdapterClipper clipper(adapterList);
                 clipper.checkInitStrand(fragment, contigs[(c.contigStrand >> 1)]);
                 unsigned matchCount = ungapped.alignUngapped(fragment, cigar, rml, clipper, contigs[(c.contigStrand >> 1)]);
                 // the reference only gap-aligns fragments whose ungapped alignment kept at least one match
@@ -306,7 +323,7 @@ extern "C" int oracle_build_fragments(const oracle_genome_t *genome, const isaac
         const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
-        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        const alignment::matchSelector::SequencingAdapterList &adapterList = currentAdapters();
         alignment::SeedMetadataList seeds;
         for (uint32_t s = 0; s < batch->seedCount; ++s)
             seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
@@ -329,7 +346,7 @@ extern "C" int oracle_build_fragments(const oracle_genome_t *genome, const isaac
                 for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
                     matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
                                                        reference::ReferencePosition(batch->matches[m].location)));
-                builtOut[c] = builder.build(contigs, rml, seeds, noAdapters, matches.begin(), matches.end(), holder.cluster,
+                builtOut[c] = builder.build(contigs, rml, seeds, adapterList, matches.begin(), matches.end(), holder.cluster,
                                             batch->withGaps != 0);
                 if (builtOut[c] || !matches.empty())
                 {
@@ -362,7 +379,7 @@ extern "C" int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_
         const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
-        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        const alignment::matchSelector::SequencingAdapterList &adapterList = currentAdapters();
         const alignment::TemplateLengthStatistics stats(
             tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
             alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
@@ -391,7 +408,7 @@ extern "C" int oracle_rescue_shadows(const oracle_genome_t *genome, const isaac_
                 orphan.position = q.orphanPosition;
                 orphan.observedLength = q.orphanObservedLength;
                 shadowList.clear();
-                rescuedOut[i] = aligner.rescueShadow(contigs, orphan, shadowList, rml, noAdapters, stats, q.bestTemplateLength);
+                rescuedOut[i] = aligner.rescueShadow(contigs, orphan, shadowList, rml, adapterList, stats, q.bestTemplateLength);
                 const uint32_t shadowReadId = clusterId * rc + (readIndex + 1) % 2;
                 for (const alignment::FragmentMetadata &f : shadowList) parts[t].add(f, shadowReadId, rml);
                 counts[i] = shadowList.size();
@@ -421,7 +438,7 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
         const std::vector<reference::Contig> &contigs = makeContigs(genome);
         const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
         const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
-        const alignment::matchSelector::SequencingAdapterList noAdapters;
+        const alignment::matchSelector::SequencingAdapterList &adapterList = currentAdapters();
         alignment::SeedMetadataList seeds;
         for (uint32_t s = 0; s < batch->seedCount; ++s)
             seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
@@ -459,11 +476,11 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
                 // MatchSelector.cpp:300-349: clusters without matches and clusters whose fragments did not build get an
                 // initialised (unaligned) template
                 if (!matches.empty() && !matches.front().location.isNoMatch() &&
-                    builder->buildFragments(contigs, rml, seeds, noAdapters, matches.begin(), matches.end(), holder.cluster,
+                    builder->buildFragments(contigs, rml, seeds, adapterList, matches.begin(), matches.end(), holder.cluster,
                                             batch->withGaps != 0))
                 {
                     o.hadFragments = 1;
-                    o.built = builder->buildTemplate(contigs, rog, rml, noAdapters, holder.cluster, stats, options->mapqThreshold);
+                    o.built = builder->buildTemplate(contigs, rog, rml, adapterList, holder.cluster, stats, options->mapqThreshold);
                     if (o.built)                                                       // MatchSelector.cpp:336-346
                     {
                         if (options->clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED) { semialignedClipper.reset(); semialignedClipper.clip(contigs, bam); }

@@ -39,6 +39,16 @@ class Oracle:
         self.lib.oracle_kind.restype = ctypes.c_char_p
         self.kind = self.lib.oracle_kind().decode()
 
+    def set_adapters(self, adapters):
+        """process-wide adapter list of this checker: (sequence, reverse, clipLength) tuples; () clears"""
+        from isaac_aligner_b200.types import adapter_array
+        if not hasattr(self.lib, "oracle_set_adapters"):
+            raise RuntimeError("this checker has no adapter support")
+        arr = adapter_array(adapters)
+        rc = self.lib.oracle_set_adapters(ctypes.c_uint32(len(adapters)), arr)
+        if rc:
+            raise RuntimeError("oracle_set_adapters failed: %d" % rc)
+
     def banded_sw(self, queries, dbs, scores, max_read_length=None, cigar_stride=64, threads=1):
         """queries/dbs: lists of bytes.  scores = (match, mismatch, gapOpen>0, gapExtend>0).
         returns (list of cigar word arrays, offsets)"""
