@@ -72,7 +72,7 @@ typedef struct isaac_ext_config {
     uint32_t maxSeedsPerRead;
     uint32_t gappedMismatchesMax;   /* --gapped-mismatches, default 5      */
     uint32_t semialignedGapLimit;   /* --semialigned-gap-limit, default 100; 0 disables simple indels */
-    uint32_t avoidSmithWaterman;    /* must be 0 (ISAAC_EXT_E_UNSUPPORTED) */
+    uint32_t avoidSmithWaterman;    /* --avoid-smith-waterman: GappedAligner::makesSenseToGapAlign decides (GappedAligner.cpp:88-165) */
     uint32_t maxReadLength;         /* flowcell::getMaxTotalReadLength; bounds the SW overflow check  */
     int32_t  device;                /* CUDA device ordinal                                            */
     uint32_t hostThreads;           /* threads for the per-cluster bookkeeping (0 = hardware)          */

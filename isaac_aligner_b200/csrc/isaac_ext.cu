@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "kernels2.cuh"
 #include "kernels3.cuh"
+#include "kernels_avoid.cuh"
 #include "host_build.cuh"
 #include "kernels_stats.cuh"
 
@@ -76,6 +77,7 @@ struct isaac_ext_ctx
     DeviceBuffer<uint32_t> adapterLength, adapterClipLength;
     AdapterView adapters{};
     DeviceBuffer<uint32_t> dAdapterClip;          // one packed clip word per candidate of the pass in flight
+    DeviceBuffer<uint32_t> dSwOwner, dPrepWords;  // --avoid-smith-waterman: owner of the 7-mer table, clip word | skip flag
     DeviceBuffer<AdapterRange> dAdapterRanges;    // one per clipper slot of the tile call in flight
 
     // staging for the host-pointer entry points
@@ -166,7 +168,6 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
 {
     if (!config || !out) { g_createError = "null argument"; return ISAAC_EXT_E_INVALID_ARG; }
     *out = nullptr;
-    if (config->avoidSmithWaterman) { g_createError = "--avoid-smith-waterman is not supported"; return ISAAC_EXT_E_UNSUPPORTED; }
     std::string why;
     if (!swScoresSupported(config->gapMatchScore, config->gapMismatchScore, -config->gapOpenScore, -config->gapExtendScore,
                            config->maxReadLength, why))
@@ -241,6 +242,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
     ctx->adapterCodes.release(); ctx->adapterReverse.release(); ctx->adapterKmers.release(); ctx->adapterLength.release();
     ctx->adapterClipLength.release(); ctx->dAdapterClip.release(); ctx->dAdapterRanges.release();
+    ctx->dSwOwner.release(); ctx->dPrepWords.release();
     for (int k = 0; k < 2; ++k)
     {
         if (ctx->swStream[k]) { cudaStreamSynchronize(ctx->swStream[k]); cudaStreamDestroy(ctx->swStream[k]); }
@@ -532,6 +534,24 @@ static int gappedDevice(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates,
                         void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream, const uint32_t *adapterClip)
 {
     if (!n) return ISAAC_EXT_OK;
+    if (ctx->cfg.avoidSmithWaterman)
+    {
+        // makesSenseToGapAlign of every candidate first (kernels_avoid.cuh); its verdict rides on the clip words
+        const isaac_ext_candidate_t *cand = static_cast<const isaac_ext_candidate_t *>(dCandidates);
+        const cudaStream_t stream = cudaStream_t(cudaStream);
+        if (n > ctx->dSwOwner.capacity) CK(cudaStreamSynchronize(stream));
+        CK(ctx->dSwOwner.reserve(n)); CK(ctx->dPrepWords.reserve(n));
+        const uint32_t maxLength = std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]);
+        swHashOwnerKernel<<<gridFor(ctx, n, 128, 16), 128, 0, stream>>>(ctx->ref, ctx->reads, n, cand, adapterClip, ctx->dSwOwner.p);
+        const size_t shared = size_t(AVOID_WARPS) * (maxLength + 3u * maxLength + 32u) * sizeof(uint32_t);
+        if (shared > 48 * 1024)
+            CK(cudaFuncSetAttribute(avoidSwKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shared)));
+        avoidSwKernel<<<gridFor(ctx, (uint64_t(n) + AVOID_WARPS - 1) / AVOID_WARPS * (AVOID_WARPS * 32), AVOID_WARPS * 32, 8), AVOID_WARPS * 32, shared, stream>>>(
+            ctx->ref, ctx->reads, n, cand, adapterClip, ctx->dSwOwner.p, maxLength, ctx->dPrepWords.p);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        adapterClip = ctx->dPrepWords.p;
+    }
     if (ctx->swImpl == 3)
         return gappedSplit(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
                            static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),

@@ -213,7 +213,8 @@ __global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, c
         const unsigned sequenceLength = unsigned(end - begin);
         long strandPosition = f.position;
         // no gapped alignment if the reference is too short (:204-208)
-        if (sequenceLength && !(contigLength < long(sequenceLength) + strandPosition + 16))
+        if (sequenceLength && !(contigLength < long(sequenceLength) + strandPosition + 16) &&
+            !(adapterClip && (adapterClip[i] >> 31)))                                    // --avoid-smith-waterman (:218-226)
         {
             // getFlanks (:51-82)
             unsigned left, right;

@@ -36,6 +36,8 @@ __device__ __forceinline__ GappedPrep prepareGapped(const ReferenceView &ref, co
     p.strandPosition = p.f.position;
     // no gapped alignment if the reference is too short (:204-208)
     p.run = p.sequenceLength && !(contigLength < long(p.sequenceLength) + p.strandPosition + 16);
+    // --avoid-smith-waterman: makesSenseToGapAlign said no (:218-226, kernels_avoid.cuh)
+    if (adapterClip && (adapterClip[index] >> 31)) p.run = false;
     // getFlanks (:51-82): once the "too short" test has passed the right flank is never squeezed
     p.left = p.run ? (p.strandPosition >= 8 ? 8u : unsigned(p.strandPosition)) : 0u;
     return p;

@@ -200,7 +200,7 @@ __device__ inline uint32_t adapterClipCandidate(const AdapterRange range, const 
 /// what the scoring kernels do with the packed word in place of FragmentSequencingAdapterClipper::clip
 __device__ __forceinline__ void applyAdapterClip(const uint32_t packed, const unsigned L, FragmentState &f, long &begin, long &end)
 {
-    const unsigned b = packed & 0xFFFFu, e = packed >> 16;
+    const unsigned b = packed & 0xFFFFu, e = (packed >> 16) & 0x7FFFu;       // bit 31: kernels_avoid.cuh
     if (b) { f.incrementClipLeft(b); begin = b; }
     if (e < L) { f.incrementClipRight(L - e); end = e; }
 }

@@ -36,10 +36,10 @@ class Config(ctypes.Structure):
     ]
 
     @classmethod
-    def default(cls, scores=BWA_SCORES, max_read_length=300, device=0, host_threads=0):
+    def default(cls, scores=BWA_SCORES, max_read_length=300, device=0, host_threads=0, avoid_smith_waterman=False):
         """The reference's defaults (AlignOptions.cpp:84-133): repeat threshold 10, gapped mismatches 5,
         semialigned gap limit 100, Smith-Waterman always on."""
-        return cls(scores[0], scores[1], scores[2], scores[3], scores[4], 10, 8, 5, 100, 0,
+        return cls(scores[0], scores[1], scores[2], scores[3], scores[4], 10, 8, 5, 100, 1 if avoid_smith_waterman else 0,
                    max_read_length, device, host_threads)
 
 

@@ -219,7 +219,7 @@ static int extendBatch(const bool gapped, const oracle_genome_t *genome, const i
             const alignment::fragmentBuilder::UngappedAligner ungapped(
                 cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore);
             alignment::fragmentBuilder::GappedAligner gappedAligner(
-                layouts, false, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore);
+                layouts, cfg->avoidSmithWaterman != 0, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore, cfg->minGapExtendScore);
             ClusterHolder holder(maxReadLength);
             uint32_t loaded = -1U;
             alignment::Cigar cigar;

@@ -188,3 +188,70 @@ def test_tile_calls_with_adapters(capi, kind, L):
     finally:
         chk.set_adapters(())
     ctx.close()
+
+
+# ---- --avoid-smith-waterman: GappedAligner::makesSenseToGapAlign -------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [None, "matepair"])
+def test_avoid_smith_waterman_micro(capi, kind):
+    """alignGapped with the 7-mer heuristic in front, candidates in call order through one GappedAligner (its table is cached
+    per read and strand); with adapters the clipped range differs between candidates of a read, which is what the cache
+    does not notice"""
+    chk = reference_checker()
+    genome, sim, reads, cand = small_workload(n_pairs=3000, L=100, seed=321, indel_rate=8e-3)
+    adapters = ()
+    if kind:
+        adapters, inserted, read_through = ADAPTER_SETS[kind]
+        synth.insert_adapters(sim, inserted, fraction=0.4, seed=322, read_through=read_through)
+        reads = ReadSet(sim.bcl, (100, 100), end_cycles_masked=reads.end_cycles_masked)
+    lens = np.array([g.size for g in genome])
+    cand = cand[(cand["position"] >= 0) & (cand["position"] + 100 <= lens[cand["contigStrand"] >> 1])]
+    cfg = Config.default(BWA_SCORES, max_read_length=200, avoid_smith_waterman=True)
+    plain = Config.default(BWA_SCORES, max_read_length=200)
+    g = oracle_lib.GenomeHolder(genome)
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    ctx.set_adapters(adapters)
+    try:
+        chk.set_adapters(adapters)
+        gc = cand[ctx.ungapped(cand)[0]["cigarLength"] > 0]
+        fg, cg, mg = ctx.gapped(gc)
+        rg = chk.gapped(g, reads, cfg, gc, threads=1)
+        assert_fragments_equal(fg, rg[0], cg, rg[1], mg, rg[2], "gapped with --avoid-smith-waterman")
+        every = chk.gapped(g, reads, plain, gc, threads=8)[0]
+        skipped = (fg["cigarLength"] == 0) & (every["cigarLength"] > 0)
+        kept = (fg["cigarLength"] > 0) & (fg["gapCount"] > 0)
+        assert skipped.sum() > 1000 and kept.sum() > 100, (skipped.sum(), kept.sum())
+    finally:
+        chk.set_adapters(())
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_avoid_smith_waterman_tile_calls(capi):
+    from isaac_aligner_b200.batch import Tls, TemplateOptions
+    chk = reference_checker()
+    L = 150
+    genome, sim, reads, mb = build_workload(n_pairs=4000, L=L, seed=330, indel_rate=8e-3)
+    cfg = Config.default(BWA_SCORES, max_read_length=2 * L, avoid_smith_waterman=True)
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    g = oracle_lib.GenomeHolder(genome)
+    got = ctx.build_fragments(mb)
+    assert_flat_equal(got, oracle_lib.build_fragments(chk, g, reads, cfg, mb, threads=8), "build_fragments, --avoid-smith-waterman")
+    assert (got.fragments["gapCount"] > 0).sum() > 50
+    tls = Tls.make()
+    req = rescue_requests(sim, seed=331)
+    gotr = ctx.rescue_shadows(tls, req)
+    assert_flat_equal(gotr, oracle_lib.rescue_shadows(chk, g, reads, cfg, tls, req, threads=8), "rescue_shadows, --avoid-smith-waterman")
+    options = TemplateOptions.make()
+    t = ctx.build_templates(mb, tls, options)
+    want = oracle_lib.build_templates(chk, g, reads, cfg, mb, tls, options, threads=8)
+    for name in ("built", "properPair", "alignmentScore", "fragmentAlignmentScore"):
+        assert np.array_equal(t.templates[name], want.templates[name]), name
+    for name in ("position", "contigId", "observedLength", "editDistance", "cigarLength", "mismatchCount", "gapCount"):
+        assert np.array_equal(t.fragments[name], want.fragments[name]), name
+    ctx.close()
