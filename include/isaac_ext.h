@@ -172,6 +172,15 @@ typedef struct isaac_ext_tls {
     int32_t  mateDriftRange;         /* -1: mateMin = min, mateMax = max (TemplateLengthStatistics.hh:205-214) */
 } isaac_ext_tls_t;
 
+/* MatchSelector::determineTemplateLength for the resident tile (MatchSelector.cpp:188-249): FragmentBuilder::build without gaps
+ * for every cluster (one GPU pass), then TemplateLengthDistribution::addTemplate cluster by cluster in match-list order until
+ * the statistics are stable, or finalize() at the end of the tile (TemplateLengthStatistics.cpp:95-160,266-357).  pf: one byte
+ * per cluster (BclClusters::pf, only passing clusters are used) or NULL = all pass.  batch->withGaps is ignored.  Single-ended
+ * read sets give the cleared statistics (all fields -1U, models 8 = InvalidAlignmentModel), like the reference.
+ * With several GPUs the rank that owns the first tile calls this and broadcasts the eight words (MatchSelector.cpp:401-417). */
+int isaac_ext_determine_template_length(isaac_ext_ctx *ctx, const struct isaac_ext_build_batch *batch, const uint8_t *pf,
+                                        int32_t mateDriftRange, struct isaac_ext_tls *tlsOut, uint32_t *stableOut);
+
 /* One ShadowAligner::rescueShadow call (ShadowAligner.hh:81-88): the orphan fields the call reads. */
 typedef struct isaac_ext_rescue_request {
     int64_t  orphanPosition;

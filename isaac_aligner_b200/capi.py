@@ -34,6 +34,7 @@ EXPORTS = [
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
+    "isaac_ext_determine_template_length",
 ]
 
 
@@ -154,6 +155,16 @@ class Context:
             return res
         return copy_result(res, self.reads.cluster_count * self.reads.read_count, "readFragmentBegin", "built",
                            self.reads.cluster_count)
+
+    def determine_template_length(self, match_batch, pf=None, mate_drift_range=-1):
+        """MatchSelector::determineTemplateLength for the resident tile -> (batch.Tls, stable)"""
+        from .batch import Tls
+        tls = Tls()
+        stable = ctypes.c_uint32()
+        pf_arr = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+        self._check(_lib.isaac_ext_determine_template_length(self._h, ctypes.byref(match_batch.c), _p(pf_arr),
+                                                             ctypes.c_int32(mate_drift_range), ctypes.byref(tls), ctypes.byref(stable)))
+        return tls, bool(stable.value)
 
     def rescue_shadows(self, tls, requests, copy=True):
         """ShadowAligner::rescueShadow for every request -> batch.FlatFragments (begin per request, flags = rescued)"""

@@ -719,6 +719,7 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 // isaac_ext_ungapped_batch_compact, isaac_ext_gapped_batch_compact
 #include "isaac_ext_e2e.cuh"
 #include "isaac_ext_templates.cuh"
+#include "isaac_ext_tls.cuh"
 
 namespace
 {

@@ -38,6 +38,30 @@ def stats_from_fragments(fragments):
     return s
 
 
+TLS_WORDS = 8   # isaac_ext_tls_t: min, max, median, lowStdDev, highStdDev, bestModel[2], mateDriftRange
+
+
+def broadcast_tls(tls, src=0, device="cpu"):
+    """The reference determines the template length statistics on the first tile and uses them for all later tiles unless
+    --per-tile-tls (MatchSelector.cpp:401-417).  With the tiles dealt over ranks, the rank that owns the first tile (src)
+    runs isaac_ext_determine_template_length and every other rank receives the eight words of its isaac_ext_tls_t.
+    `tls` is a batch.Tls (ignored on the receiving ranks, may be None there); returns the Tls every rank continues with."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from .batch import Tls
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return tls
+    words = torch.zeros(TLS_WORDS, dtype=torch.int32, device=device)
+    if dist.get_rank() == src:
+        raw = np.frombuffer(ctypes.string_at(ctypes.addressof(tls), ctypes.sizeof(Tls)), dtype=np.int32)
+        words.copy_(torch.from_numpy(raw.copy()))
+    dist.broadcast(words, src=src)
+    out = Tls()
+    ctypes.memmove(ctypes.addressof(out), words.cpu().numpy().tobytes(), ctypes.sizeof(Tls))
+    return out
+
+
 def allreduce_stats(stats):
     """sums the counter vector over all ranks in place.  `stats` is a torch int64 tensor (cuda -> NCCL, cpu -> gloo)
     holding the u64 counters bit for bit; returns it.  A single-process run returns it unchanged."""

@@ -76,6 +76,12 @@ int oracle_build_templates(const oracle_genome_t *genome, const isaac_ext_reads_
                            isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut,
                            uint64_t *cigarWords, uint32_t threads);
 
+/* MatchSelector::determineTemplateLength for the tile (MatchSelector.cpp:188-249), see isaac_ext_determine_template_length.
+ * Only the reference build exports it. */
+int oracle_determine_template_length(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                                     const isaac_ext_config_t *config, const isaac_ext_build_batch_t *batch,
+                                     const uint8_t *pf, int32_t mateDriftRange, isaac_ext_tls_t *tlsOut, uint32_t *stableOut);
+
 /* alignment::trimLowQualityEnds on every cluster (Quality.cpp:71-120), see isaac_ext_trim_low_quality_ends.  Only the
  * reference build exports it. */
 int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut);

@@ -510,6 +510,59 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
     }
 }
 
+/* MatchSelector::determineTemplateLength (MatchSelector.cpp:188-249) for one tile: the loop is restated here (MatchSelector.cpp
+ * itself drags in the whole workflow), everything it calls -- TemplateBuilder::buildFragments without gaps and
+ * TemplateLengthDistribution::addTemplate / finalize -- is the reference's own code. */
+extern "C" int oracle_determine_template_length(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
+                                                const isaac_ext_config_t *cfg, const isaac_ext_build_batch_t *batch,
+                                                const uint8_t *pf, int32_t mateDriftRange, isaac_ext_tls_t *tlsOut, uint32_t *stableOut)
+{
+    try
+    {
+        const std::vector<reference::Contig> &contigs = makeContigs(genome);
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+        const alignment::matchSelector::SequencingAdapterList &adapterList = currentAdapters();
+        alignment::SeedMetadataList seeds;
+        for (uint32_t s = 0; s < batch->seedCount; ++s)
+            seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
+        alignment::TemplateLengthDistribution distribution(mateDriftRange);
+        distribution.reset(contigs, rml);
+        if (reads->readCount == 2)
+        {
+            std::unique_ptr<alignment::TemplateBuilder> builder(new alignment::TemplateBuilder(
+                layouts, cfg->repeatThreshold, cfg->maxSeedsPerRead, false, cfg->gappedMismatchesMax,
+                cfg->avoidSmithWaterman, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore,
+                cfg->minGapExtendScore, cfg->semialignedGapLimit, alignment::TemplateBuilder::DODGY_ALIGNMENT_SCORE_UNALIGNED));
+            ClusterHolder holder(std::max(reads->readLength[0], reads->readLength[1]));
+            std::vector<alignment::Match> matches;
+            for (uint32_t c = 0; c < reads->clusterCount && !distribution.getStatistics().isStable(); ++c)
+            {
+                matches.clear();
+                for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
+                    matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
+                                                       reference::ReferencePosition(batch->matches[m].location)));
+                if (matches.empty() || (pf && !pf[c]) || matches.front().location.isNoMatch()) continue;      // :226-230
+                holder.load(reads, rml, c);
+                builder->buildFragments(contigs, rml, seeds, adapterList, matches.begin(), matches.end(), holder.cluster, false);
+                distribution.addTemplate(builder->getFragments());
+            }
+            if (!distribution.isStable()) distribution.finalize();
+        }
+        const alignment::TemplateLengthStatistics &s = distribution.getStatistics();
+        tlsOut->min = s.getMin(); tlsOut->max = s.getMax(); tlsOut->median = s.getMedian();
+        tlsOut->lowStdDev = s.getLowStdDev(); tlsOut->highStdDev = s.getHighStdDev();
+        tlsOut->bestModel[0] = s.getBestModel(0); tlsOut->bestModel[1] = s.getBestModel(1);
+        tlsOut->mateDriftRange = mateDriftRange;
+        *stableOut = s.isStable();
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+    return ISAAC_EXT_OK;
+}
+
 extern "C" int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut)
 {
     try

@@ -4,7 +4,9 @@
 #define iSAAC_LOG_THREAD_TIMESTAMP_HH
 #include <iostream>
 #include <cstdlib>
-#define ISAAC_THREAD_CERR std::cerr
+// the reference's progress / warning messages go nowhere: a stream without a buffer drops everything before any formatting
+namespace isaac_shim { inline std::ostream &quietLog() { static std::ostream quiet(nullptr); return quiet; } }
+#define ISAAC_THREAD_CERR isaac_shim::quietLog()
 #define ISAAC_ASSERT_MSG(expr, msg) {if (expr) {} else \
 { std::cerr << "ERROR: ***** Internal Program Error - assertion (" << #expr << ") failed in " \
     << __FILE__ << '(' << __LINE__ << "): " << msg << std::endl; ::abort();}}

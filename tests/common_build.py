@@ -7,11 +7,11 @@ from isaac_aligner_b200.types import FRAGMENT_DTYPE, ReadSet, cigar_to_string
 
 
 def build_workload(n_pairs=1500, L=150, seed=5, genome_bases=300_000, n_contigs=2, indel_rate=4e-3, masked=True,
-                   with_gaps=True, neighbor_rate=0.15, repeat_rate=0.01, too_many_rate=0.005, repeat_threshold=10):
+                   with_gaps=True, neighbor_rate=0.15, repeat_rate=0.01, too_many_rate=0.005, repeat_threshold=10, **simulate):
     """genome + simulated pairs + seed matches with decoys, neighbours, over-represented seeds and TooManyMatch records"""
     genome = synth.make_genome(genome_bases, n_contigs=n_contigs, seed=seed, n_fraction=0.002, n_run=(20, 200))
     sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=seed + 1, indel_rate=indel_rate,
-                               seed_offsets=synth.auto_seed_offsets(L))
+                               seed_offsets=synth.auto_seed_offsets(L), **simulate)
     rng = np.random.default_rng(seed + 2)
     ecm = None
     if masked:

@@ -154,6 +154,21 @@ def build_templates(oracle, genome, reads, config, match_batch, tls, options, th
     return Templates(templates, frags, cigars[:nc.value].copy())
 
 
+def determine_template_length(oracle, genome, reads, config, match_batch, pf=None, mate_drift_range=-1):
+    """MatchSelector::determineTemplateLength for the tile (reference build only) -> (batch.Tls, stable)"""
+    from isaac_aligner_b200.batch import Tls
+    tls = Tls()
+    stable = ctypes.c_uint32()
+    pf_arr = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+    rc = oracle.lib.oracle_determine_template_length(
+        ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.byref(match_batch.c),
+        ctypes.c_void_p(pf_arr.ctypes.data) if pf_arr is not None else None, ctypes.c_int32(mate_drift_range),
+        ctypes.byref(tls), ctypes.byref(stable))
+    if rc:
+        raise RuntimeError("oracle_determine_template_length failed: %d" % rc)
+    return tls, bool(stable.value)
+
+
 def trim_low_quality_ends(oracle, reads, base_quality_cutoff):
     """alignment::trimLowQualityEnds on every cluster (reference build only) -> endCyclesMasked [clusters, readCount]"""
     out = np.zeros((reads.cluster_count, reads.read_count), dtype=np.uint16)

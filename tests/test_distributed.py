@@ -79,3 +79,30 @@ def test_tile_stats_kernel_matches_numpy():
     torch.cuda.synchronize()
     assert np.array_equal(stats.cpu().numpy().view(np.uint64), distributed.stats_from_fragments(frags))
     ctx.close()
+
+
+def _tls_rank_main(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import torch.distributed as dist
+    from isaac_aligner_b200 import distributed
+    from isaac_aligner_b200.batch import FRm, RFp, Tls
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 0 owns the first tile: it determined these statistics; the others start with nothing
+    mine = Tls.make(mn=211, mx=498, median=347, low=33, high=36, m0=RFp, m1=FRm, drift=-1) if rank == 0 else None
+    got = distributed.broadcast_tls(mine, src=0)
+    np.save(os.path.join(out_dir, "tls%d.npy" % rank),
+            np.frombuffer(ctypes.string_at(ctypes.addressof(got), ctypes.sizeof(Tls)), dtype=np.int32).copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_tls_broadcast(tmp_path):
+    """the template length statistics of the first tile reach every rank bit for bit (MatchSelector.cpp:401-417)"""
+    import torch.multiprocessing as mp
+    port = 30100 + os.getpid() % 500
+    mp.spawn(_tls_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (np.load(os.path.join(str(tmp_path), "tls%d.npy" % r)) for r in range(2))
+    assert np.array_equal(a, b) and list(a) == [211, 498, 347, 33, 36, 2, 5, -1]
