@@ -331,6 +331,14 @@ int isaac_ext_gapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_e
                                    isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
                                    uint64_t *cigarWordsOut);
 
+/* Both calls above over the same candidates in one pass over the batch: what FragmentBuilder::alignFragments does with a
+ * candidate (alignUngapped, then alignGapped on a copy, FragmentBuilder.cpp:174,199-200), here for every candidate.  The
+ * candidates are uploaded once and the ungapped records of a chunk travel back while its Smith-Waterman runs. */
+int isaac_ext_extend_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                   isaac_ext_fragment_t *ungappedOut, uint32_t *ungappedPoolOut, uint64_t ungappedPoolCapacity,
+                                   uint64_t *ungappedWordsOut, isaac_ext_fragment_t *gappedOut, uint32_t *gappedPoolOut,
+                                   uint64_t gappedPoolCapacity, uint64_t *gappedWordsOut);
+
 /* Device-resident variants used to time the kernels alone: the candidate and result arrays are device
  * pointers, the launch goes to 'cudaStream' (a cudaStream_t passed as void*) and returns without
  * synchronising.  Same semantics as the host variants above. */

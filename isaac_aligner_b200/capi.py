@@ -34,7 +34,7 @@ EXPORTS = [
     "isaac_ext_launch_count", "isaac_ext_measure_int32_peak", "isaac_ext_build_fragments", "isaac_ext_rescue_shadows",
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
-    "isaac_ext_determine_template_length",
+    "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
 ]
 
 
@@ -144,6 +144,15 @@ class Context:
         self._check(fn(self._h, ctypes.c_uint32(len(cand)), _p(cand), _p(fragments_out), _p(pool_out),
                        ctypes.c_uint64(pool_out.size), ctypes.byref(words)))
         return int(words.value)
+
+    def extend_compact_both(self, candidates, ungapped_out, ungapped_pool, gapped_out, gapped_pool):
+        """ungapped + gapped pass over the same candidates in one chunked call; returns (ungapped words, gapped words)"""
+        cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
+        wu, wg = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(_lib.isaac_ext_extend_batch_compact(
+            self._h, ctypes.c_uint32(len(cand)), _p(cand), _p(ungapped_out), _p(ungapped_pool), ctypes.c_uint64(ungapped_pool.size),
+            ctypes.byref(wu), _p(gapped_out), _p(gapped_pool), ctypes.c_uint64(gapped_pool.size), ctypes.byref(wg)))
+        return int(wu.value), int(wg.value)
 
     def build_fragments(self, match_batch, copy=True):
         """FragmentBuilder::build for every cluster of the resident read set -> batch.FlatFragments

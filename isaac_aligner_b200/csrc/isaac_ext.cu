@@ -732,7 +732,8 @@ extern "C" int isaac_ext_ungapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, 
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->e2e) ctx->e2e = new E2eState();
-    return extendCompact(ctx, *ctx->e2e, false, n, candidates, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut);
+    E2ePass pass = {false, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut};
+    return extendCompact(ctx, *ctx->e2e, n, candidates, &pass, 1);
 }
 
 extern "C" int isaac_ext_gapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
@@ -741,5 +742,18 @@ extern "C" int isaac_ext_gapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, co
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->e2e) ctx->e2e = new E2eState();
-    return extendCompact(ctx, *ctx->e2e, true, n, candidates, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut);
+    E2ePass pass = {true, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut};
+    return extendCompact(ctx, *ctx->e2e, n, candidates, &pass, 1);
+}
+
+extern "C" int isaac_ext_extend_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                              isaac_ext_fragment_t *ungappedOut, uint32_t *ungappedPoolOut, uint64_t ungappedPoolCapacity,
+                                              uint64_t *ungappedWordsOut, isaac_ext_fragment_t *gappedOut, uint32_t *gappedPoolOut,
+                                              uint64_t gappedPoolCapacity, uint64_t *gappedWordsOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->e2e) ctx->e2e = new E2eState();
+    E2ePass passes[2] = {{false, ungappedOut, ungappedPoolOut, ungappedPoolCapacity, ungappedWordsOut},
+                         {true, gappedOut, gappedPoolOut, gappedPoolCapacity, gappedWordsOut}};
+    return extendCompact(ctx, *ctx->e2e, n, candidates, passes, 2);
 }

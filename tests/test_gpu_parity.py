@@ -134,3 +134,28 @@ def test_compact_rejects_bad_candidates(capi, gapped):
     assert words == int(f0["cigarLength"].sum())
     assert np.array_equal(f0["mismatchCount"], f1["mismatchCount"])
     ctx.close()
+
+
+def test_compact_both_passes_in_one_call(capi):
+    """isaac_ext_extend_batch_compact = the two *_batch_compact calls over the same candidates, several chunks"""
+    genome, sim, reads, cand = small_workload(n_pairs=3000, L=100, seed=93, indel_rate=6e-3)
+    ctx = capi.Context(Config.default(max_read_length=200))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    cand = cand[ctx.ungapped(cand)[0]["cigarLength"] > 0]
+    cand = np.concatenate([cand] * 180)[:3 * 1212416 + 4321]
+    n = len(cand)
+    fu, fg = np.zeros(n, dtype=capi.FRAGMENT_DTYPE), np.zeros(n, dtype=capi.FRAGMENT_DTYPE)
+    pu, pg = np.zeros(n * 3, dtype=np.uint32), np.zeros(n * 10, dtype=np.uint32)
+    wu, wg = ctx.extend_compact_both(cand, fu, pu, fg, pg)
+    su, sg = np.zeros(n, dtype=capi.FRAGMENT_DTYPE), np.zeros(n, dtype=capi.FRAGMENT_DTYPE)
+    qu, qg = np.zeros(n * 3, dtype=np.uint32), np.zeros(n * 10, dtype=np.uint32)
+    assert wu == ctx.extend_compact(cand, False, su, qu) and wg == ctx.extend_compact(cand, True, sg, qg)
+    assert fu.tobytes() == su.tobytes() and fg.tobytes() == sg.tobytes()
+    assert np.array_equal(pu[:wu], qu[:wu]) and np.array_equal(pg[:wg], qg[:wg])
+    assert (fg["gapCount"] > 0).sum() > 1000
+    # too small a pool for one of the passes is reported with the sizes both need
+    with pytest.raises(capi.ExtError) as e:
+        ctx.extend_compact_both(cand, fu, pu, fg, pg[:1000])
+    assert e.value.code == 5
+    ctx.close()
