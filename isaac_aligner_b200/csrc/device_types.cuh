@@ -44,6 +44,9 @@ struct ReadSetView
     // Smith-Waterman query stream: (readId * 2 + reverse) * wordsC + w.  The last TWO words of every strand are spare
     // zeros so that a 16-base fetch may start anywhere in the strand.
     const uint64_t *codes4;
+    // The same strands once more for the scorer, 16 bases per 64-bit word at the same index: bits 0..31 the 2-bit codes in
+    // strand order (complemented on the reverse strand), bits 32..47 one flag per base = 'n'.
+    const uint64_t *strand2;
     uint32_t wordsC;
     const uint8_t *qualityStrand;    // qualities again per strand in strand order: (readId * 2 + reverse) * qualityStride + p
     uint32_t words2, wordsN, qualityStride;
@@ -56,6 +59,10 @@ struct ReadSetView
     __device__ __forceinline__ const uint64_t *strandCodes(unsigned readId, bool reverse) const
     {
         return codes4 + (size_t(readId) * 2 + (reverse ? 1u : 0u)) * wordsC;
+    }
+    __device__ __forceinline__ const uint64_t *strandWords2(unsigned readId, bool reverse) const
+    {
+        return strand2 + (size_t(readId) * 2 + (reverse ? 1u : 0u)) * wordsC;
     }
     __device__ __forceinline__ const uint8_t *strandQuality(unsigned readId, bool reverse) const
     {

@@ -65,7 +65,7 @@ struct isaac_ext_ctx
     // resident read set
     DeviceBuffer<uint32_t> readBases2, readNmask;
     DeviceBuffer<uint8_t> readQuality, bclStage;
-    DeviceBuffer<uint64_t> readCodes4;
+    DeviceBuffer<uint64_t> readCodes4, readStrand2;
     DeviceBuffer<uint8_t> readQualityStrand;
     DeviceBuffer<uint16_t> readMasked;
     ReadSetView reads{};
@@ -237,7 +237,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     ctx->tables.release(); ctx->refBases2.release(); ctx->refNmask.release(); ctx->refContigOffset.release();
     ctx->refContigLength.release(); ctx->readBases2.release(); ctx->readNmask.release(); ctx->readQuality.release();
-    ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readQualityStrand.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
+    ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readStrand2.release(); ctx->readQualityStrand.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
     ctx->adapterCodes.release(); ctx->adapterReverse.release(); ctx->adapterKmers.release(); ctx->adapterLength.release();
@@ -379,14 +379,16 @@ extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *
     CK(cudaGetLastError());
     const uint32_t wordsC = (maxLen + 15) / 16 + 2;
     CK(ctx->readCodes4.reserve(readTotal * 2 * wordsC));
+    CK(ctx->readStrand2.reserve(readTotal * 2 * wordsC));
     CK(ctx->readQualityStrand.reserve(readTotal * 2 * qualityStride));
     encodeStrandCodesKernel<<<gridFor(ctx, readTotal * 2 * wordsC, 256, 16), 256, 0, ctx->stream>>>(
-        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, ctx->readCodes4.p, qualityStride, ctx->readQualityStrand.p);
+        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, ctx->readCodes4.p, ctx->readStrand2.p, qualityStride,
+        ctx->readQualityStrand.p);
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     ReadSetView &v = ctx->reads;
-    v.codes4 = ctx->readCodes4.p; v.wordsC = wordsC; v.qualityStrand = ctx->readQualityStrand.p;
+    v.codes4 = ctx->readCodes4.p; v.strand2 = ctx->readStrand2.p; v.wordsC = wordsC; v.qualityStrand = ctx->readQualityStrand.p;
     v.bases2 = ctx->readBases2.p; v.nmask = ctx->readNmask.p; v.quality = ctx->readQuality.p; v.endCyclesMasked = ctx->readMasked.p;
     v.words2 = words2; v.wordsN = wordsN; v.qualityStride = qualityStride; v.readCount = r->readCount;
     v.readLength[0] = len0; v.readLength[1] = len1; v.firstCycle[0] = r->firstCycle[0]; v.firstCycle[1] = r->firstCycle[1];

@@ -90,7 +90,7 @@ __global__ void decodeBclKernel(const uint8_t *__restrict__ bcl, uint32_t cluste
 /// Both strands of every read as 4-bit codes in strand order (ReadSetView::codes4); one thread per 64-bit word.
 __global__ void encodeStrandCodesKernel(const uint8_t *__restrict__ bcl, uint32_t clusterCount, uint32_t readCount,
                                         uint32_t len0, uint32_t len1, uint32_t wordsC, uint64_t *__restrict__ codes4,
-                                        uint32_t qualityStride, uint8_t *__restrict__ qualityStrand)
+                                        uint64_t *__restrict__ strand2, uint32_t qualityStride, uint8_t *__restrict__ qualityStrand)
 {
     const uint64_t total = uint64_t(clusterCount) * readCount * 2 * wordsC;
     const uint32_t clusterBytes = len0 + (readCount > 1 ? len1 : 0);
@@ -103,7 +103,7 @@ __global__ void encodeStrandCodesKernel(const uint8_t *__restrict__ bcl, uint32_
         const uint32_t readIndex = uint32_t(readId % readCount);
         const uint32_t L = readIndex ? len1 : len0;
         const uint8_t *src = bcl + (readId / readCount) * clusterBytes + (readIndex ? len0 : 0);
-        uint64_t word = 0;
+        uint64_t word = 0, two = 0;
         for (unsigned k = 0; k < 16; ++k)
         {
             const uint32_t p = w * 16 + k;
@@ -112,11 +112,13 @@ __global__ void encodeStrandCodesKernel(const uint8_t *__restrict__ bcl, uint32_
                 const unsigned b = src[reverse ? L - 1 - p : p];
                 const unsigned code = !(b & 0xfcu) ? unsigned(CODE_READ_N) : (reverse ? 3u - (b & 3u) : (b & 3u));   // Read.cpp:56-69
                 word |= uint64_t(code) << (4 * k);
+                two |= code > 3u ? 1ull << (32 + k) : uint64_t(code) << (2 * k);
                 qualityStrand[strandId * qualityStride + p] = !(b & 0xfcu) ? 2 : uint8_t(b >> 2);                 // Read.cpp:60,66
             }
             else if (p < qualityStride) qualityStrand[strandId * qualityStride + p] = 0;
         }
         codes4[t] = word;
+        strand2[t] = two;
     }
 }
 

@@ -132,7 +132,7 @@ struct CigarScorer
                                           unsigned length, bool reverse, uint64_t contigOffset, long strandPosition,
                                           const uint32_t *ops, unsigned n, uint64_t *maskOut)
     {
-        ref = &r; sp = &s; strandWords = reads.strandCodes(readId, reverse); quality = reads.strandQuality(readId, reverse);
+        ref = &r; sp = &s; strandWords = reads.strandWords2(readId, reverse); quality = reads.strandQuality(readId, reverse);
         cigar = ops; mask = maskOut; g0 = contigOffset + uint64_t(strandPosition); g = g0; lp = 0.0;
         L = length; nOps = n; k = 0; remaining = 0; op = ISAAC_EXT_CIGAR_SOFT_CLIP; fresh = false;
         matchCount = mismatchCount = matchesInARow = gapCount = editDistance = sws = run = 0;
@@ -144,10 +144,11 @@ struct CigarScorer
         const unsigned P0 = w * 16u;
         if (P0 >= L) return;
         const unsigned cnt = min(16u, L - P0);
-        const uint64_t ONES = 0x1111111111111111ull;
-        const uint64_t rword = strandWords[w];
-        const uint64_t readN = (rword >> 2) & ONES;                  // CODE_READ_N == 4
-        uint64_t mism = 0, skip = 0, notm = 0, bnd = 0;
+        const uint64_t sword = strandWords[w];
+        const uint32_t read2 = uint32_t(sword), readN = uint32_t(sword >> 32);     // 2-bit codes, 'n' flags of the 16 bases
+        // per base of the word: codes differ (even bits of neq2, ALIGN pieces only), reference 'N', under an ALIGN operation,
+        // inserted, first base of an ALIGN operation
+        uint32_t neq2 = 0, refN = 0, aligned = 0, skip = 0, bnd = 0;
         unsigned off = 0;
         while (off < cnt)
         {
@@ -174,37 +175,46 @@ struct CigarScorer
             }
             if (remaining == 0) { remaining = cnt - off; op = ISAAC_EXT_CIGAR_SOFT_CLIP; }        // malformed CIGAR: never for our callers
             const unsigned take = min(remaining, cnt - off);
-            const uint64_t seg = ((take >= 16u ? 0ull : (1ull << (4u * take))) - 1ull) << (4u * off);
+            const uint32_t seg = ((1u << take) - 1u) << off;                                     // take <= 16
             if (op == ISAAC_EXT_CIGAR_ALIGN)
             {
-                const uint64_t d = referenceCodes16(*ref, g) << (4u * off);
-                const uint64_t x = rword ^ d;
-                const uint64_t neq = (x | (x >> 1) | (x >> 2)) & ONES & seg;                     // byte inequality (:176-179)
-                mism |= neq & ~readN;                                                            // !isMatch (Alignment.hh:44-47)
-                editDistance += __popcll(neq);
-                if (fresh) bnd |= 1ull << (4u * off);
+                // 16 reference bases from g on, moved to the piece's place in the word
+                const uint32_t *b2 = ref->bases2 + (g >> 4);
+                const uint32_t d2 = __funnelshift_r(__ldg(b2), __ldg(b2 + 1), (unsigned(g) & 15u) * 2u);
+                const uint32_t *bn = ref->nmask + (g >> 5);
+                const uint32_t dN = __funnelshift_r(__ldg(bn), __ldg(bn + 1), unsigned(g) & 31u);
+                const uint32_t x = read2 ^ (d2 << (2u * off));
+                const uint32_t seg2 = ((take >= 16u ? 0u : (1u << (2u * take))) - 1u) << (2u * off);
+                neq2 |= (x | (x >> 1)) & 0x55555555u & seg2;
+                refN |= (dN << off) & seg;
+                aligned |= seg;
+                if (fresh) bnd |= 1u << off;
                 g += take;
             }
-            else if (op == ISAAC_EXT_CIGAR_INSERT) { skip |= seg & ONES; notm |= seg & ONES; }
-            else { notm |= seg & ONES; }                                                         // SOFT_CLIP (:199-213)
+            else if (op == ISAAC_EXT_CIGAR_INSERT) skip |= seg;
             fresh = false;
             off += take; remaining -= take;
         }
-        notm |= mism;
-        const uint64_t valid = ONES & (cnt >= 16u ? ~0ull : ((1ull << (4u * cnt)) - 1ull));
-        matchCount += __popcll(~notm & valid);
-        mismatchCount += __popcll(mism);
-        const uint32_t mism16 = compactNibbleFlags(mism);            // bit b = base P0 + b is a mismatch
+        uint32_t neq = neq2;                                         // even bits -> 16 dense bits
+        neq = (neq | (neq >> 1)) & 0x33333333u;
+        neq = (neq | (neq >> 2)) & 0x0F0F0F0Fu;
+        neq = (neq | (neq >> 4)) & 0x00FF00FFu;
+        neq = (neq | (neq >> 8)) & 0x0000FFFFu;
+        const uint32_t valid = (1u << cnt) - 1u;
+        const uint32_t mism16 = aligned & ~readN & (neq | refN);     // !isMatch (Alignment.hh:44-47): 'n' in the read matches anything
+        const uint32_t match16 = aligned & ~mism16;
+        editDistance += __popc(aligned & (neq | refN | readN));     // the bytes differ (:176-179): 'n' and 'N' differ from everything
+        matchCount += __popc(match16);
+        mismatchCount += __popc(mism16);
         if (mask && mism16) mask[P0 >> 6] |= uint64_t(mism16) << (P0 & 63u);   // addMismatchCycle (:171), as a bit over base index
         // ---- the sequential part: the FP64 sum, one table lookup + one DADD per base in read order.  The table index of
         // all 16 bases is prepared as bytes first: quality, + 100 for a mismatch, 200 (the +0.0 entry; the sum never is
         // -0.0, so it is unchanged bit for bit) for inserted bases and the positions past the end of the read.
         const uint4 qv = *reinterpret_cast<const uint4 *>(quality + P0);
         unsigned qw[4] = {qv.x, qv.y, qv.z, qv.w};
-        const uint64_t zero = skip | (ONES & ~valid);
-        if (zero)
+        const uint32_t zero16 = skip | (0xFFFFu & ~valid);
+        if (zero16)
         {
-            const uint32_t zero16 = compactNibbleFlags(zero);
 #pragma unroll
             for (unsigned k = 0; k < 4; ++k)
             {
@@ -225,8 +235,7 @@ struct CigarScorer
         }
         // ---- longest run of matches (:158-170), on the 16 match bits of the word: 'run' enters from the previous word;
         // a run also ends in front of the first base of every ALIGN operation ('fresh', bits of bnd)
-        const uint32_t match16 = compactNibbleFlags(~notm & valid);
-        uint32_t bnd16 = compactNibbleFlags(bnd);
+        uint32_t bnd16 = bnd;
         unsigned start = 0;
         while (bnd16)
         {
