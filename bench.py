@@ -210,7 +210,18 @@ def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup):
         t0 = time.perf_counter(); ctx.build_templates(mb, tls, copy=False); tt += time.perf_counter() - t0
     tt /= steps
     gaps = flat.fragments["gapCount"] > 0
-    return {"pairs": n, "template_pairs_per_s": n / tt, "templates_ms": tt * 1e3,
+    # MatchSelectorStats of the tile (TileBarcodeStats per read and pass filter), summed over the ranks: the path's one exchange
+    import torch
+    from isaac_aligner_b200 import distributed
+    t0 = time.perf_counter()
+    tile_stats = ctx.template_stats(mb, tls, templates)
+    stats_ms = (time.perf_counter() - t0) * 1e3
+    summed = torch.from_numpy(tile_stats.view(np.int64).copy())
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        summed = distributed.allreduce_stats(summed.cuda()).cpu()
+    read1 = summed.numpy().view(np.uint64)[0]
+    return {"pairs": n, "template_pairs_per_s": n / tt, "templates_ms": tt * 1e3, "template_stats_ms": stats_ms,
+            "match_selector_stats_all_ranks": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16]))),
             "template_rescue_requests": int(templates.rescue_requests),
             "templates_built": int(templates.templates["built"].sum()), "proper_pairs": int(templates.templates["properPair"].sum()),
             "pairs_per_s": n / (tb + tr), "build_ms": tb * 1e3, "rescue_ms": tr * 1e3,
@@ -396,6 +407,12 @@ def run_b200(args):
         traffic = int(entry["dram_bytes_per_launch"] * float(n) / entry["candidates"]) if L == 150 else None
     except (OSError, KeyError, ValueError):
         pass
+    traffic_ungapped = None
+    try:
+        entry = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["ungapped_pass"]
+        traffic_ungapped = int(entry["dram_bytes_per_launch"] * float(n) / entry["candidates"]) if L == 150 else None
+    except (OSError, KeyError, ValueError):
+        pass
     # ---- CPU baseline on a bounded sample, same box
     cores = os.cpu_count() or 1
     ns = min(n, args.cpu_sample_per_core * cores)
@@ -426,7 +443,9 @@ def run_b200(args):
                      "peak_source": "measured live by isaac_ext_measure_int32_peak: add.s32 %.1f, max.s32 %.1f, "
                                     "16x2 max %.1f TOP/s" % (peak_add / 1e12, peak_max / 1e12, peak_dpx / 1e12)},
         "roofline_ungapped": {"bound": "hbm", "kernel": "ungappedKernel", "achieved": ungapped_gbs, "peak": hbm_peak,
-                              "unit": "GB/s", "frac": ungapped_gbs / hbm_peak, "ms_per_launch": ms_ungapped,
+                              "unit": "GB/s", "frac": ungapped_gbs / hbm_peak, "traffic": traffic_ungapped, "ms_per_launch": ms_ungapped,
+                              "limited_by": "integer pipe (ncu: ALU 66 %, issue 61 %; profiles/r1_u_ncu_ungappedKernel.txt): the ordered "
+                                            "FP64 sum and the longest-run counter cost about 290 instructions per 16 bases",
                               "peak_source": hbm_src, "candidates_per_s": n / (ms_ungapped * 1e-3)},
         "cpu_baseline": {"value": cpu_gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
                          "sample": "first %d of the %d candidates of rank 0, one pass, %d host threads, %.2f s"

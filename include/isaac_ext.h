@@ -357,6 +357,22 @@ int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dC
 #define ISAAC_EXT_STATS_COUNTERS 64
 int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const void *dFragments, void *dStats, void *cudaStream);
 
+/* matchSelector::TileBarcodeStats of MatchSelectorStats (TileBarcodeStats.hh:40-160, MatchSelectorStats.hh:77-103) for the
+ * templates of one tile (the result of isaac_ext_build_templates, host pointers): one kernel pass over the tile on the GPU.
+ * statsOut: 4 blocks of ISAAC_EXT_TEMPLATE_STATS_COUNTERS u64, block = readIndex * 2 + passesFilter (the pass-filter block
+ * counts pf clusters only, the other one all clusters; pair-level counters live under read index 0).  Counters of a block:
+ * [0] yield [1] yieldQ30 [2] qualityScoreSum [3] clusterCount [4] unanchoredClusterCount [5] nmnmClusterCount
+ * [6] rmClusterCount [7] qcClusterCount [8] alignedFragmentCount [9] uniquelyAlignedFragmentCount
+ * [10] uniquelyAlignedPerfectFragmentCount [11] alignmentScoreSum [12] basesOutsideIndels [13] uniquelyAlignedBasesOutsideIndels
+ * [14] mismatches [15] uniquelyAlignedMismatches [16..24] alignmentModelCounts (FFp..RRm, Invalid) [25..28] nominalModelCounts
+ * (Oversized, Undersized, Nominal, NoMatch) [29] fragmentCount.  The template type of a cluster follows
+ * MatchSelector.cpp:300-365: no match list or a NoMatch record first = NmNm (Qc if that record carries the N-seed id), match
+ * list whose fragments did not build = Rm.  pf: one byte per cluster or NULL = all pass.  The ranks of a multi-GPU run sum
+ * these vectors with one all-reduce (the reference sums its per-thread MatchSelectorStats, MatchSelector.cpp:439-442). */
+#define ISAAC_EXT_TEMPLATE_STATS_COUNTERS 32
+int isaac_ext_template_stats(isaac_ext_ctx *ctx, const struct isaac_ext_build_batch *batch, const struct isaac_ext_tls *tls,
+                             const struct isaac_ext_template_result *templates, const uint8_t *pf, uint64_t *statsOut);
+
 /* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
  * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
 int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);

@@ -35,6 +35,7 @@ EXPORTS = [
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
+    "isaac_ext_template_stats",
 ]
 
 
@@ -211,6 +212,21 @@ class Context:
 
         return Templates(arr(res.templates, TEMPLATE_DTYPE, n), arr(res.fragments, FRAGMENT_DTYPE, n * self.reads.read_count),
                          arr(res.cigars, np.uint32, int(res.cigarWords)), int(res.rescueRequests))
+
+    def template_stats(self, match_batch, tls, templates, pf=None):
+        """matchSelector::TileBarcodeStats of a tile's templates (batch.Templates) -> uint64 [4, TEMPLATE_STATS_COUNTERS],
+        row = readIndex * 2 + passesFilter"""
+        from .batch import TemplateResult
+        from .distributed import TEMPLATE_STATS_COUNTERS
+        t = np.ascontiguousarray(templates.templates)
+        f = np.ascontiguousarray(templates.fragments)
+        cig = np.ascontiguousarray(templates.cigars, dtype=np.uint32)
+        res = TemplateResult(t.ctypes.data, f.ctypes.data, cig.ctypes.data if cig.size else None, cig.size, 0)
+        pf_arr = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+        out = np.zeros((4, TEMPLATE_STATS_COUNTERS), dtype=np.uint64)
+        self._check(_lib.isaac_ext_template_stats(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(res),
+                                                  _p(pf_arr), _p(out)))
+        return out
 
     def tile_stats_device(self, n, d_fragments, d_stats, stream):
         """adds the K6 counters of n device-resident fragment records to the 64 u64 at d_stats"""

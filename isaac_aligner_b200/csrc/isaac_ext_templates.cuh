@@ -752,7 +752,14 @@ struct TemplateState
     DeviceBuffer<isaac_ext_template_t> dTemplates;  DeviceBuffer<isaac_ext_fragment_t> dFragments;
     DeviceBuffer<uint32_t> dCigarsIn, dCigarsOut;
     HostBuffer<uint32_t> clippedCigars;
-    ~TemplateState() { dTemplates.release(); dFragments.release(); dCigarsIn.release(); dCigarsOut.release(); }
+    // isaac_ext_template_stats
+    DeviceBuffer<isaac_ext_template_t> dStatTemplates;  DeviceBuffer<isaac_ext_fragment_t> dStatFragments;
+    DeviceBuffer<uint32_t> dStatCigars;  DeviceBuffer<uint8_t> dStatBytes;  DeviceBuffer<unsigned long long> dStats;
+    ~TemplateState()
+    {
+        dTemplates.release(); dFragments.release(); dCigarsIn.release(); dCigarsOut.release();
+        dStatTemplates.release(); dStatFragments.release(); dStatCigars.release(); dStatBytes.release(); dStats.release();
+    }
 };
 
 template <class T> void swapBuffers(HostBuffer<T> &a, HostBuffer<T> &b) { std::swap(a.p, b.p); std::swap(a.capacity, b.capacity); }

@@ -136,3 +136,49 @@ extern "C" int isaac_ext_determine_template_length(isaac_ext_ctx *ctx, const isa
     *stableOut = distribution.stable ? 1u : 0u;
     return ISAAC_EXT_OK;
 }
+
+/// matchSelector::TileBarcodeStats of the tile's templates (see include/isaac_ext.h)
+extern "C" int isaac_ext_template_stats(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                        const isaac_ext_template_result_t *templates, const uint8_t *pf, uint64_t *statsOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!batch || !tls || !templates || !statsOut) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
+    if (!ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reads first");
+    const uint32_t n = ctx->clusterCount, rc = ctx->reads.readCount;
+    const size_t counters = 4 * size_t(ISAAC_EXT_TEMPLATE_STATS_COUNTERS);
+    std::memset(statsOut, 0, counters * sizeof(uint64_t));
+    if (!n) return ISAAC_EXT_OK;
+    if (!templates->templates || !templates->fragments || (templates->cigarWords && !templates->cigars))
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null template result");
+    CK(cudaSetDevice(ctx->device));
+    // the template type of every cluster (MatchSelector.cpp:300-365)
+    std::vector<uint8_t> types(n);
+    parallelRanges(ctx->hostThreads, n, [&](unsigned, size_t b, size_t e) {
+        for (size_t c = b; c < e; ++c)
+        {
+            const uint64_t mb = batch->clusterMatchBegin[c], me = batch->clusterMatchBegin[c + 1];
+            if (mb == me) types[c] = TEMPLATE_NMNM;
+            else if (matchIsNoMatch(batch->matches[mb])) types[c] = ((batch->matches[mb].seedId >> 1) & 0xFFu) == 0xFFu ? TEMPLATE_QC : TEMPLATE_NMNM;   // SeedId::isNSeedId (SeedId.hh:117)
+            else types[c] = templates->templates[c].hadFragments ? TEMPLATE_NORMAL : TEMPLATE_RM;
+        }
+    });
+    if (!ctx->templates) ctx->templates = new TemplateState();
+    TemplateState &st = *ctx->templates;
+    const size_t count = size_t(n) * rc;
+    CK(st.dStatTemplates.reserve(n)); CK(st.dStatFragments.reserve(count)); CK(st.dStatCigars.reserve(templates->cigarWords + 1));
+    CK(st.dStatBytes.reserve(2 * size_t(n))); CK(st.dStats.reserve(counters));
+    CK(cudaMemcpyAsync(st.dStatTemplates.p, templates->templates, size_t(n) * sizeof(isaac_ext_template_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(st.dStatFragments.p, templates->fragments, count * sizeof(isaac_ext_fragment_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (templates->cigarWords)
+        CK(cudaMemcpyAsync(st.dStatCigars.p, templates->cigars, templates->cigarWords * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(st.dStatBytes.p, types.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+    if (pf) CK(cudaMemcpyAsync(st.dStatBytes.p + n, pf, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(st.dStats.p, 0, counters * sizeof(unsigned long long), ctx->stream));
+    const TlsDevice t = {tls->min, tls->max, {tls->bestModel[0], tls->bestModel[1]}};
+    templateStatsKernel<<<gridFor(ctx, n, 128, 16), 128, 0, ctx->stream>>>(ctx->reads, t, n, st.dStatTemplates.p, st.dStatFragments.p, st.dStatCigars.p,
+                                                                          st.dStatBytes.p, pf ? st.dStatBytes.p + n : nullptr, st.dStats.p);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(statsOut, st.dStats.p, counters * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return ctx->cuda(cudaStreamSynchronize(ctx->stream), "templateStatsKernel");
+}

@@ -38,6 +38,11 @@ def stats_from_fragments(fragments):
     return s
 
 
+TEMPLATE_STATS_COUNTERS = 32   # ISAAC_EXT_TEMPLATE_STATS_COUNTERS: one matchSelector::TileBarcodeStats per (read, pass filter)
+TEMPLATE_STAT_NAMES = ("yield", "yieldQ30", "qualityScoreSum", "clusterCount", "unanchoredClusterCount", "nmnmClusterCount",
+                       "rmClusterCount", "qcClusterCount", "alignedFragmentCount", "uniquelyAlignedFragmentCount",
+                       "uniquelyAlignedPerfectFragmentCount", "alignmentScoreSum", "basesOutsideIndels",
+                       "uniquelyAlignedBasesOutsideIndels", "mismatches", "uniquelyAlignedMismatches")
 TLS_WORDS = 8   # isaac_ext_tls_t: min, max, median, lowStdDev, highStdDev, bestModel[2], mateDriftRange
 
 

@@ -76,6 +76,12 @@ int oracle_build_templates(const oracle_genome_t *genome, const isaac_ext_reads_
                            isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut,
                            uint64_t *cigarWords, uint32_t threads);
 
+/* TileBarcodeStats of the tile's templates, see isaac_ext_template_stats (statsOut: 4 * ISAAC_EXT_TEMPLATE_STATS_COUNTERS).
+ * Only the reference build exports it. */
+int oracle_template_stats(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *config,
+                          const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                          const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t threads);
+
 /* MatchSelector::determineTemplateLength for the tile (MatchSelector.cpp:188-249), see isaac_ext_determine_template_length.
  * Only the reference build exports it. */
 int oracle_determine_template_length(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,

@@ -24,6 +24,9 @@
 #include "alignment/Cluster.hh"
 #include "alignment/fragmentBuilder/UngappedAligner.hh"
 #include "alignment/fragmentBuilder/GappedAligner.hh"
+#include "alignment/matchSelector/TileBarcodeStats.hh"
+#include "alignment/matchSelector/FragmentMetadataTileStatsAdapter.hh"
+#include "alignment/matchSelector/BamTemplateTileStatsAdapter.hh"
 #include "alignment/matchSelector/FragmentSequencingAdapterClipper.hh"
 #include "reference/Contig.hh"
 
@@ -96,11 +99,11 @@ struct ClusterHolder
     std::vector<char> bcl;
     alignment::Cluster cluster;
     ClusterHolder(unsigned maxReadLength) : cluster(maxReadLength) {}
-    void load(const isaac_ext_reads_t *r, const flowcell::ReadMetadataList &rml, uint32_t clusterId)
+    void load(const isaac_ext_reads_t *r, const flowcell::ReadMetadataList &rml, uint32_t clusterId, bool pf = true)
     {
         const uint32_t total = r->readLength[0] + (r->readCount > 1 ? r->readLength[1] : 0);
         bcl.assign(r->bcl + size_t(clusterId) * total, r->bcl + size_t(clusterId + 1) * total);
-        cluster.init(rml, bcl.begin(), 0, clusterId, alignment::ClusterXy(0, 0), true, 0);
+        cluster.init(rml, bcl.begin(), 0, clusterId, alignment::ClusterXy(0, 0), pf, 0);
         for (uint32_t i = 0; i < r->readCount; ++i)
         {
             cluster[i].maskCyclesFromEnd(r->endCyclesMasked ? r->endCyclesMasked[size_t(clusterId) * r->readCount + i] : 0);
@@ -508,6 +511,114 @@ extern "C" int oracle_build_templates(const oracle_genome_t *genome, const isaac
     {
         return ISAAC_EXT_E_INVALID_ARG;
     }
+}
+
+/* The TileBarcodeStats of MatchSelectorStats (MatchSelectorStats.hh:77-103) for one tile and one barcode: every cluster goes
+ * through the template pipeline like in oracle_build_templates and is recorded the way MatchSelector::processMatchList records it
+ * (MatchSelector.cpp:300-365; pfOnly off).  MatchSelectorStats.hh itself needs Boost.Filesystem and the barcode metadata; its
+ * recordTemplate dispatch (:77-103) is restated here on the reference's own TileBarcodeStats and its two adapters. */
+static void flattenStats(const alignment::matchSelector::TileBarcodeStats &s, uint64_t *out)
+{
+    out[0] += s.yield_; out[1] += s.yieldQ30_; out[2] += s.qualityScoreSum_; out[3] += s.clusterCount_;
+    out[4] += s.unanchoredClusterCount_; out[5] += s.nmnmClusterCount_; out[6] += s.rmClusterCount_; out[7] += s.qcClusterCount_;
+    out[8] += s.alignedFragmentCount_; out[9] += s.uniquelyAlignedFragmentCount_; out[10] += s.uniquelyAlignedPerfectFragmentCount_;
+    out[11] += s.alignmentScoreSum_; out[12] += s.basesOutsideIndels_; out[13] += s.uniquelyAlignedBasesOutsideIndels_;
+    out[14] += s.mismatches_; out[15] += s.uniquelyAlignedMismatches_;
+    for (unsigned m = 0; m < 9; ++m) out[16 + m] += s.alignmentModelCounts_[m];
+    for (unsigned m = 0; m < 4; ++m) out[25 + m] += s.nominalModelCounts_[m];
+    out[29] += s.fragmentCount_;
+}
+
+extern "C" int oracle_template_stats(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
+                                     const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                     const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t threads)
+{
+    using namespace alignment::matchSelector;
+    try
+    {
+        const std::vector<reference::Contig> &contigs = makeContigs(genome);
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+        const SequencingAdapterList &adapterList = currentAdapters();
+        alignment::SeedMetadataList seeds;
+        for (uint32_t s = 0; s < batch->seedCount; ++s)
+            seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
+        const alignment::TemplateLengthStatistics stats(
+            tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[1]), tls->mateDriftRange);
+        const alignment::RestOfGenomeCorrection rog(contigs, rml);
+        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+        const uint32_t n = reads->clusterCount;
+        if (threads < 1) threads = 1;
+        if (n < 2 * threads) threads = 1;
+        std::vector<std::vector<TileBarcodeStats> > parts(threads, std::vector<TileBarcodeStats>(4));   // [readIndex * 2 + passesFilter]
+        // TileBarcodeStats::reset() zeroes the eight real models but not alignmentModelCounts_[InvalidAlignmentModel]
+        // (TileBarcodeStats.hh:62-69): the reference counts the pairs without a model on top of uninitialised memory
+        for (std::vector<TileBarcodeStats> &p : parts)
+            for (TileBarcodeStats &s : p) s.alignmentModelCounts_[alignment::TemplateLengthStatistics::InvalidAlignmentModel] = 0;
+        parallelFor(n, threads, [&](uint32_t t, uint32_t b, uint32_t e) {
+            std::unique_ptr<alignment::TemplateBuilder> builder(new alignment::TemplateBuilder(
+                layouts, cfg->repeatThreshold, cfg->maxSeedsPerRead, options->scatterRepeats != 0, cfg->gappedMismatchesMax,
+                cfg->avoidSmithWaterman, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore,
+                cfg->minGapExtendScore, cfg->semialignedGapLimit,
+                alignment::TemplateBuilder::DodgyAlignmentScore(options->dodgyAlignmentScore)));
+            ClusterHolder holder(maxReadLength);
+            std::vector<alignment::Match> matches;
+            SemialignedEndsClipper semialignedClipper;
+            OverlappingEndsClipper overlappingClipper;
+            std::vector<TileBarcodeStats> &mine = parts[t];
+            for (uint32_t c = b; c < e; ++c)
+            {
+                holder.load(reads, rml, c, !pf || pf[c]);
+                matches.clear();
+                for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
+                    matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
+                                                       reference::ReferencePosition(batch->matches[m].location)));
+                alignment::BamTemplate &bam = builder->getBamTemplate();
+                TemplateAlignmentType type = Normal;
+                if (matches.empty() || matches.front().location.isNoMatch())                      // MatchSelector.cpp:302-313
+                {
+                    bam.initialize(rml, holder.cluster);
+                    type = !matches.empty() && matches.front().getSeedId().isNSeedId() ? Qc : NmNm;
+                }
+                else if (builder->buildFragments(contigs, rml, seeds, adapterList, matches.begin(), matches.end(), holder.cluster,
+                                                 batch->withGaps != 0))
+                {
+                    if (builder->buildTemplate(contigs, rog, rml, adapterList, holder.cluster, stats, options->mapqThreshold)) // :329-347
+                    {
+                        if (options->clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED) { semialignedClipper.reset(); semialignedClipper.clip(contigs, bam); }
+                        if (options->clipFlags & ISAAC_EXT_CLIP_OVERLAPPING) { overlappingClipper.reset(); overlappingClipper.clip(contigs, bam); }
+                    }
+                }
+                else
+                {
+                    bam.initialize(rml, holder.cluster);
+                    type = Rm;
+                }
+                // MatchSelectorStats::recordTemplate (MatchSelectorStats.hh:77-103)
+                BamTemplateTileStatsAdapter templateAdapter(stats, bam, type);
+                const unsigned r0 = bam.getFragmentMetadata(0).getReadIndex();
+                if (bam.getPassesFilter()) mine[r0 * 2 + 1].recordTemplate(templateAdapter);
+                mine[r0 * 2].recordTemplate(templateAdapter);
+                for (unsigned i = 0; bam.getFragmentCount() > i; ++i)
+                {
+                    const alignment::FragmentMetadata &fragment = bam.getFragmentMetadata(i);
+                    FragmentMetadataTileStatsAdapter fragmentAdapter(fragment);
+                    if (bam.getPassesFilter()) mine[fragment.getReadIndex() * 2 + 1].recordFragment(fragmentAdapter, rml.at(i));
+                    mine[fragment.getReadIndex() * 2].recordFragment(fragmentAdapter, rml.at(i));
+                }
+            }
+        });
+        std::memset(statsOut, 0, 4 * ISAAC_EXT_TEMPLATE_STATS_COUNTERS * sizeof(uint64_t));
+        for (const std::vector<TileBarcodeStats> &p : parts)
+            for (unsigned k = 0; k < 4; ++k) flattenStats(p[k], statsOut + k * ISAAC_EXT_TEMPLATE_STATS_COUNTERS);
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+    return ISAAC_EXT_OK;
 }
 
 /* MatchSelector::determineTemplateLength (MatchSelector.cpp:188-249) for one tile: the loop is restated here (MatchSelector.cpp

@@ -6,8 +6,12 @@
 namespace boost {
 using std::bind;
 using std::ref;
-// the reference takes the address of boost::cref<char>, so it must be a real function template
-template <class T> inline const std::reference_wrapper<const T> cref(const T &t) { return std::cref(t); }
+// The reference takes the address of boost::cref<char> / boost::cref<unsigned char>, so it must be a real function template.
+// It calls cref<unsigned char> on 'char' elements (FragmentMetadataTileStatsAdapter.hh:49-50): the argument is a converted
+// temporary and a reference to it dangles once cref returns (with the real Boost too; there the stack slot happens to
+// survive until the comparison).  This stand-in carries the value instead, which is what the code means.
+template <class T> struct ValueRef { T value; operator const T &() const { return value; } };
+template <class T> inline const ValueRef<T> cref(const T &t) { return ValueRef<T>{t}; }
 }
 using namespace std::placeholders;
 namespace boost_shim {
@@ -25,3 +29,9 @@ template <class L, class V, class = typename std::enable_if<std::is_bind_express
 boost_shim::EqualsValue<L, V> operator!=(L l, V v) { return boost_shim::EqualsValue<L, V>{l, v, false}; }
 template <class L, class V, class = typename std::enable_if<std::is_bind_expression<L>::value && std::is_arithmetic<V>::value>::type>
 boost_shim::EqualsValue<L, V> operator==(L l, V v) { return boost_shim::EqualsValue<L, V>{l, v, true}; }
+// bind expression >= plain value (FragmentMetadataTileStatsAdapter.hh:49-50: quality >= 30u)
+namespace boost_shim {
+template <class L, class V> struct AtLeastValue { L l; V v; template <class... A> bool operator()(A &&...a) { return l(a...) >= v; } };
+}
+template <class L, class V, class = typename std::enable_if<std::is_bind_expression<L>::value && std::is_arithmetic<V>::value>::type>
+boost_shim::AtLeastValue<L, V> operator>=(L l, V v) { return boost_shim::AtLeastValue<L, V>{l, v}; }

@@ -154,6 +154,19 @@ def build_templates(oracle, genome, reads, config, match_batch, tls, options, th
     return Templates(templates, frags, cigars[:nc.value].copy())
 
 
+def template_stats(oracle, genome, reads, config, match_batch, tls, options, pf=None, threads=1):
+    """TileBarcodeStats of the tile's templates through the reference's own classes (reference build only) -> uint64 [4, 32]"""
+    pf_arr = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+    out = np.zeros((4, 32), dtype=np.uint64)
+    rc = oracle.lib.oracle_template_stats(
+        ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.byref(match_batch.c), ctypes.byref(tls),
+        ctypes.byref(options), ctypes.c_void_p(pf_arr.ctypes.data) if pf_arr is not None else None,
+        ctypes.c_void_p(out.ctypes.data), ctypes.c_uint32(threads))
+    if rc:
+        raise RuntimeError("oracle_template_stats failed: %d" % rc)
+    return out
+
+
 def determine_template_length(oracle, genome, reads, config, match_batch, pf=None, mate_drift_range=-1):
     """MatchSelector::determineTemplateLength for the tile (reference build only) -> (batch.Tls, stable)"""
     from isaac_aligner_b200.batch import Tls

@@ -104,3 +104,43 @@ def test_template_length_statistics_single_ended(capi):
     assert words(got) == words(want) and not stable and not want_stable
     assert got.min == 0xFFFFFFFF and got.bestModel[0] == 8
     ctx.close()
+
+
+@pytest.mark.parametrize("clip,with_pf", [(False, False), (True, True)])
+def test_template_stats_bit_exact(capi, clip, with_pf):
+    """the TileBarcodeStats MatchSelector keeps per (read, pass filter) over the templates of a tile, against the reference's own
+    TileBarcodeStats fed by the reference's TemplateBuilder; clusters without matches, with NoMatch / N-seed records and with
+    match lists that do not build are in the tile"""
+    from isaac_aligner_b200.batch import TemplateOptions
+    if not hasattr(reference_checker().lib, "oracle_template_stats"):
+        pytest.skip("reference checker without oracle_template_stats")
+    chk = reference_checker()
+    n = 6000
+    genome, sim, reads, mb = build_workload(n_pairs=n, L=100, seed=431, genome_bases=1_000_000, indel_rate=4e-3)
+    reads, mb = swap_reads(sim, reads, mb)
+    # a few clusters whose match list is a single NoMatch record, half of them with the N-seed id (all seeds contain Ns)
+    matches, begin = mb.matches.copy(), mb.begin.astype(np.int64)
+    rng = np.random.default_rng(8)
+    for c in rng.choice(n, size=60, replace=False):
+        if begin[c + 1] > begin[c]:
+            m = int(begin[c])
+            matches["location"][m] = np.uint64(0xFFFFFE0000000000)                       # ReferencePosition::NoMatch
+            if c % 2:
+                matches["seedId"][m] |= np.uint64(0xFF << 1)                              # SeedId::setNSeedId
+    mb = MatchBatch(matches, mb.begin, mb.seeds)
+    cfg = Config.default(BWA_SCORES, max_read_length=200)
+    pf = (rng.random(n) < 0.85).astype(np.uint8) if with_pf else None
+    options = TemplateOptions.make(clip_semialigned=clip, clip_overlapping=clip)
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    tls, _ = ctx.determine_template_length(mb, pf)
+    templates = ctx.build_templates(mb, tls, options)
+    got = ctx.template_stats(mb, tls, templates, pf)
+    want = oracle_lib.template_stats(chk, oracle_lib.GenomeHolder(genome), reads, cfg, mb, tls, options, pf, threads=8)
+    assert np.array_equal(got, want), (got[:, :30], want[:, :30])
+    all_clusters = got[0]                                                                  # read 1, all clusters
+    assert all_clusters[3] == n and all_clusters[5] > 0 and all_clusters[7] > 0
+    assert all_clusters[16 + 1] + all_clusters[16 + 6] > 0.5 * n and all_clusters[25 + 2] > 0.5 * n     # FRp / RFm, nominal
+    assert got[2][29] == n and (got[1][3] == n) == (pf is None)
+    ctx.close()
