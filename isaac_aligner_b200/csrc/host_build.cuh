@@ -46,13 +46,17 @@ struct PipelineState
     PinnedBuffer<uint32_t> hSlot;
     DeviceBuffer<uint32_t> dSlot;
     // flattened results handed back to the caller
-    std::vector<WorkFragment> work;
+    HostBuffer<WorkFragment> work;          // grow-only, never value-initialised (every live element is written before it is read)
     std::vector<uint32_t> indelCigars;
     HostBuffer<isaac_ext_fragment_t> outFragments;
     HostBuffer<uint64_t> outBegin;
     HostBuffer<uint32_t> outCigars;
     uint64_t outFragmentCount = 0, outCigarWords = 0;
     std::vector<uint8_t> outFlags;
+    // the shadow lists of the last rescue pass before flattening: list i = work[rescueListBegin[i] .. + rescueListCount[i])
+    std::vector<uint64_t> rescueListBegin;
+    std::vector<uint32_t> rescueListCount;
+    HostPools rescuePools;
 
     void release()
     {

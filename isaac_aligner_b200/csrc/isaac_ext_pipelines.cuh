@@ -132,7 +132,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
     const unsigned T = ctx->hostThreads;
     const unsigned parts = partitionCount(T, nClusters);
     const unsigned repeatThreshold = ctx->cfg.repeatThreshold;
-    ps.work.resize(M);
+    ps.work.reserve(M);
     ps.outFlags.assign(nClusters, 0);
     std::vector<uint64_t> listBegin(lists, 0);
     std::vector<uint32_t> listCount(lists, 0);
@@ -200,7 +200,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
             for (unsigned r = 0; r < rc; ++r)
             {
                 const unsigned n = consolidateDuplicateFragments(tmp[r].data(), unsigned(tmp[r].size()), false);    // :159
-                for (unsigned k = 0; k < n; ++k) { tmp[r][k].f.repeatSeedsCount = uint16_t(repeatSeedsCount); ps.work[at + k] = tmp[r][k]; }   // :167
+                for (unsigned k = 0; k < n; ++k) { tmp[r][k].f.repeatSeedsCount = uint16_t(repeatSeedsCount); ps.work.p[at + k] = tmp[r][k]; }   // :167
                 listBegin[c * rc + r] = at; listCount[c * rc + r] = n;
                 at += n; total += n;
             }
@@ -224,7 +224,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
             if (withAdapters) ps.hAdapterFirst.p[l * 2].readId = ps.hAdapterFirst.p[l * 2 + 1].readId = ADAPTER_NO_CANDIDATE;
             for (unsigned k = 0; k < listCount[l]; ++k)
             {
-                WorkFragment &w = ps.work[listBegin[l] + k];
+                WorkFragment &w = ps.work.p[listBegin[l] + k];
                 w.slot = uint32_t(at);
                 ps.hCand1.p[at] = candidateOf(w.f, w.f.position);
                 if (withAdapters && ps.hAdapterFirst.p[l * 2 + (w.f.reverse ? 1 : 0)].readId == ADAPTER_NO_CANDIDATE)
@@ -254,7 +254,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
     parallelRanges(T, nClusters, [&](unsigned t, size_t b, size_t e) {
         for (size_t l = b * rc; l < e * rc; ++l)
         {
-            WorkFragment *list = ps.work.data() + listBegin[l];
+            WorkFragment *list = ps.work.p + listBegin[l];
             unsigned n = listCount[l];
             for (unsigned k = 0; k < n; ++k) adoptAlignment(list[k], ps.hFrag1.p[list[k].slot], 0, list[k].slot);
             n = consolidateDuplicateFragments(list, n, true);
@@ -333,11 +333,11 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         for (size_t i = 0; i < partTasks[t].size(); ++i)
         {
             const IndelResult &r = ps.hIndel.p[taskBegin[t] + i];
-            if (r.accepted) adoptAlignment(ps.work[partTargets[t][i]], r.fragment, 1, uint32_t(taskBegin[t] + i));
+            if (r.accepted) adoptAlignment(ps.work.p[partTargets[t][i]], r.fragment, 1, uint32_t(taskBegin[t] + i));
         }
         for (size_t l = b * rc; l < e * rc; ++l)
         {
-            WorkFragment *list = ps.work.data() + listBegin[l];
+            WorkFragment *list = ps.work.p + listBegin[l];
             if (gapLimit) listCount[l] = consolidateDuplicateFragments(list, listCount[l], true);
             if (!withGaps) continue;
             for (unsigned k = 0; k < listCount[l]; ++k)
@@ -354,7 +354,7 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
         parallelRanges(T, nClusters, [&](unsigned t, size_t, size_t) {
             for (size_t i = 0; i < gapTargets[t].size(); ++i)
             {
-                const WorkFragment &w = ps.work[gapTargets[t][i]];
+                const WorkFragment &w = ps.work.p[gapTargets[t][i]];
                 // alignGapped starts from resetAlignment(): the unclipped position of the current alignment (GappedAligner.cpp:175)
                 ps.hCand3.p[gapBegin[t] + i] = candidateOf(w.f, pools.unclippedPosition(w));
             }
@@ -369,15 +369,15 @@ extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_bui
     parallelRanges(T, nClusters, [&](unsigned t, size_t b, size_t e) {
         for (size_t i = 0; i < gapTargets[t].size(); ++i)
         {
-            WorkFragment &w = ps.work[gapTargets[t][i]];
+            WorkFragment &w = ps.work.p[gapTargets[t][i]];
             const isaac_ext_fragment_t &g = ps.hFrag3.p[gapBegin[t] + i];
             if (acceptGapped(w.f, g, ctx->cfg.gappedMismatchesMax)) adoptAlignment(w, g, 2, uint32_t(gapBegin[t] + i));
         }
         for (size_t l = b * rc; l < e * rc; ++l)
-            if (listCount[l]) listCount[l] = consolidateDuplicateFragments(ps.work.data() + listBegin[l], listCount[l], true);
+            if (listCount[l]) listCount[l] = consolidateDuplicateFragments(ps.work.p + listBegin[l], listCount[l], true);
     });
     timer.mark("P4 accept + consolidate");
-    flatten(ctx, pools, lists, [&](size_t l) { return std::pair<const WorkFragment *, unsigned>(ps.work.data() + listBegin[l], listCount[l]); });
+    flatten(ctx, pools, lists, [&](size_t l) { return std::pair<const WorkFragment *, unsigned>(ps.work.p + listBegin[l], listCount[l]); });
     timer.mark("flatten");
     result->fragments = ps.outFragments.p; result->readFragmentBegin = ps.outBegin.p; result->cigars = ps.outCigars.p;
     result->built = ps.outFlags.data(); result->fragmentCount = ps.outFragmentCount; result->cigarWords = ps.outCigarWords;
@@ -430,22 +430,25 @@ struct TlsHost
 const unsigned SHADOW_LIST_CAPACITY = 1000;      // TemplateBuilder::TRACKED_REPEATS_MAX_ONE_READ (TemplateBuilder.hh:145, .cpp:82)
 } // namespace
 
-extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
-                                        const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
+/// ShadowAligner::rescueShadow of every request up to the point where the shadow lists stand in PipelineState::work
+/// (rescueListBegin / rescueListCount / rescuePools, outFlags = rescued); isaac_ext_rescue_shadows flattens them for its
+/// caller, isaac_ext_build_templates reads them where they are.
+static int rescueShadowLists(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n, const isaac_ext_rescue_request_t *requests)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
-    if (!tls || !result || (n && !requests)) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
+    if (!tls || (n && !requests)) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (ctx->reads.readCount != 2) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "shadow rescue needs paired reads (ShadowAligner.cpp:170)");
     CK(cudaSetDevice(ctx->device));
     PipelineState &ps = ctx->pipeline;
     const unsigned T = ctx->hostThreads;
     const TlsHost stats(*tls);
-    HostPools pools;
+    HostPools &pools = ps.rescuePools;
+    pools = HostPools();
     ps.outFlags.assign(n, 0);
-    std::vector<uint32_t> listCount(n, 0);
-    std::vector<uint64_t> listBegin(n, 0);
-    uint64_t total = 0;
+    std::vector<uint32_t> &listCount = ps.rescueListCount;
+    std::vector<uint64_t> &listBegin = ps.rescueListBegin;
+    listCount.assign(n, 0); listBegin.assign(n, 0);
     PhaseTimer timer("rescue");
     if (n && stats.coherent())                                                   // :164-168
     {
@@ -533,7 +536,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
         pools.pools[0] = ps.hCig1.p;
 
         // ---- R2: shadow lists, best shadow, neighbours to gap-align (:205-256)
-        ps.work.resize(poolSize);
+        ps.work.reserve(poolSize);
         const unsigned parts = partitionCount(T, n);
         std::vector<int64_t> best(n, -1);
         std::vector<uint8_t> full(n, 0);
@@ -545,7 +548,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             {
                 const uint64_t begin = ps.hTaskBegin.p[i];
                 const unsigned count = ps.hTaskCount.p[i];
-                WorkFragment *list = ps.work.data() + begin;
+                WorkFragment *list = ps.work.p + begin;
                 listBegin[i] = begin;
                 unsigned size = 0;
                 for (unsigned k = 0; k < count; ++k)
@@ -580,7 +583,7 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             parallelRanges(T, n, [&](unsigned t, size_t, size_t) {
                 for (size_t k = 0; k < gapTargets[t].size(); ++k)
                 {
-                    const WorkFragment &w = ps.work[gapTargets[t][k]];
+                    const WorkFragment &w = ps.work.p[gapTargets[t][k]];
                     ps.hCand3.p[gapBegin[t] + k] = candidateOf(w.f, pools.unclippedPosition(w));
                     ps.hSlot.p[gapBegin[t] + k] = gapRequests[t][k];
                 }
@@ -595,10 +598,10 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             size_t g = 0;
             for (size_t i = b; i < e; ++i)
             {
-                WorkFragment *list = ps.work.data() + listBegin[i];
+                WorkFragment *list = ps.work.p + listBegin[i];
                 for (; g < gapTargets[t].size() && gapTargets[t][g] < listBegin[i] + listCount[i] && gapTargets[t][g] >= listBegin[i]; ++g)
                 {
-                    WorkFragment &w = ps.work[gapTargets[t][g]];
+                    WorkFragment &w = ps.work.p[gapTargets[t][g]];
                     const isaac_ext_fragment_t &gf = ps.hFrag3.p[gapBegin[t] + g];
                     if (acceptGapped(w.f, gf, ctx->cfg.gappedMismatchesMax))
                     {
@@ -612,10 +615,20 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
             }
         });
         timer.mark("R3 accept + best first");
-        for (size_t i = 0; i < n; ++i) total += listCount[i];
     }
-    (void)total;
-    flatten(ctx, pools, n, [&](size_t i) { return std::pair<const WorkFragment *, unsigned>(ps.work.data() + listBegin[i], listCount[i]); });
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
+                                        const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!result) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
+    const int rc = rescueShadowLists(ctx, tls, n, requests);
+    if (rc) return rc;
+    PipelineState &ps = ctx->pipeline;
+    PhaseTimer timer("rescue");
+    flatten(ctx, ps.rescuePools, n, [&](size_t i) { return std::pair<const WorkFragment *, unsigned>(ps.work.p + ps.rescueListBegin[i], ps.rescueListCount[i]); });
     timer.mark("flatten");
     result->fragments = ps.outFragments.p; result->requestFragmentBegin = ps.outBegin.p; result->cigars = ps.outCigars.p;
     result->rescued = ps.outFlags.data(); result->fragmentCount = ps.outFragmentCount; result->cigarWords = ps.outCigarWords;

@@ -192,8 +192,7 @@ struct BestPairInfo
 struct RescueAnswer
 {
     bool rescued = false;
-    const isaac_ext_fragment_t *begin = nullptr, *end = nullptr;
-    const uint32_t *cigars = nullptr;
+    const WorkFragment *begin = nullptr, *end = nullptr;      // the shadow list where the rescue pass left it
 };
 
 struct TemplateContext
@@ -214,7 +213,7 @@ struct TemplateWorker
     // rescue plumbing
     bool planning = true;
     std::vector<isaac_ext_rescue_request_t> *requests = nullptr;       // plan: appended to
-    const isaac_ext_rescue_result_t *rescueResult = nullptr;          // finish: answers, consumed from nextRequest on
+    const PipelineState *rescued = nullptr;                           // finish: the shadow lists of the rescue pass, consumed from nextRequest on
     uint64_t nextRequest = 0;
     // BamTemplate
     TFrag bam[2]; uint32_t bamAlignmentScore = 0; bool bamProperPair = false;
@@ -242,18 +241,17 @@ struct TemplateWorker
             return a;
         }
         const uint64_t i = nextRequest++;
-        a.rescued = rescueResult->rescued[i] != 0;
-        a.begin = rescueResult->fragments + rescueResult->requestFragmentBegin[i];
-        a.end = rescueResult->fragments + rescueResult->requestFragmentBegin[i + 1];
-        a.cigars = rescueResult->cigars;
+        a.rescued = rescued->outFlags[i] != 0;
+        a.begin = rescued->work.p + rescued->rescueListBegin[i];
+        a.end = a.begin + rescued->rescueListCount[i];
         return a;
     }
     void loadShadowList(const RescueAnswer &a)
     {
         shadowList.clear();
-        for (const isaac_ext_fragment_t *p = a.begin; p != a.end; ++p)
+        for (const WorkFragment *p = a.begin; p != a.end; ++p)
         {
-            TFrag t; t.f = *p; t.alignmentScore = -1U; t.cigar = a.cigars + p->cigarOffset;
+            TFrag t; t.f = p->f; t.alignmentScore = -1U; t.cigar = rescued->rescuePools.cigar(*p);
             shadowList.push_back(t);
         }
     }
@@ -837,11 +835,10 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     timer.mark("plan");
 
     // ---- one rescue batch
-    isaac_ext_rescue_result_t rescued;
-    std::memset(&rescued, 0, sizeof(rescued));
+    // (the shadow lists stay where the rescue pass builds them, PipelineState::work: the per-cluster code reads them in place)
     if (!st.requests.empty())
     {
-        rc = isaac_ext_rescue_shadows(ctx, tls, uint32_t(st.requests.size()), st.requests.data(), &rescued);
+        rc = rescueShadowLists(ctx, tls, uint32_t(st.requests.size()), st.requests.data());
         if (rc) return rc;
     }
     timer.mark("rescue_shadows");
@@ -852,7 +849,7 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     std::vector<uint64_t> partFirstCluster(parts + 1, n);
     parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
         TemplateWorker w(cx);
-        w.planning = false; w.rescueResult = &rescued;
+        w.planning = false; w.rescued = &ctx->pipeline;
         std::vector<uint32_t> &pool = partCigars[t];
         partFirstCluster[t] = b;
         for (size_t c = b; c < e; ++c)
