@@ -53,16 +53,27 @@ struct PipelineState
     HostBuffer<uint32_t> outCigars;
     uint64_t outFragmentCount = 0, outCigarWords = 0;
     std::vector<uint8_t> outFlags;
-    // the shadow lists of the last rescue pass before flattening: list i = work[rescueListBegin[i] .. + rescueListCount[i])
-    std::vector<uint64_t> rescueListBegin;
-    std::vector<uint32_t> rescueListCount;
-    HostPools rescuePools;
+    // isaac_ext_rescue_shadows: list bookkeeping on the device (kernels_rescue.cuh) and its flat result in pinned memory
+    DeviceBuffer<uint32_t> dKept, dAdoptedBy, dCounts, dBegins, dSlot3, dSources, dCig3, dOutCigars;
+    DeviceBuffer<ShadowListState> dListState;
+    DeviceBuffer<uint8_t> dRescued, dScanTemp;
+    DeviceBuffer<isaac_ext_candidate_t> dCand3;
+    DeviceBuffer<isaac_ext_fragment_t> dFrag3, dOutFragments;
+    DeviceBuffer<uint64_t> dOutBegin;
+    PinnedBuffer<uint32_t> hTotals, hOutCigars;
+    PinnedBuffer<isaac_ext_fragment_t> hOutFragments;
+    PinnedBuffer<uint64_t> hOutBegin;
+    PinnedBuffer<uint8_t> hRescued;
 
     void release()
     {
         hCand1.release(); hCand3.release(); hFrag1.release(); hFrag3.release(); hCig1.release(); hCig3.release();
         hTasks.release(); hIndel.release(); hShadowTasks.release(); hTaskBegin.release(); hTaskCount.release();
         hAdapterFirst.release(); dAdapterFirst.release(); hSlot.release(); dSlot.release();
+        dKept.release(); dAdoptedBy.release(); dCounts.release(); dBegins.release(); dSlot3.release(); dSources.release(); dCig3.release();
+        dOutCigars.release(); dListState.release(); dRescued.release(); dScanTemp.release(); dCand3.release(); dFrag3.release();
+        dOutFragments.release(); dOutBegin.release(); hTotals.release(); hOutCigars.release(); hOutFragments.release(); hOutBegin.release();
+        hRescued.release();
         dCand.release(); dFrag.release(); dCig.release(); dTasks.release(); dIndel.release(); dShadowTasks.release();
         dShadowScratch.release(); dTaskBegin.release(); dTaskCount.release(); dPoolSize.release();
     }

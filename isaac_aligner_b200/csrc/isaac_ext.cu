@@ -7,11 +7,13 @@
 #include <string>
 #include <vector>
 
+#include <cub/cub.cuh>
 #include "device_buffer.cuh"
 #include "kernels.cuh"
 #include "kernels2.cuh"
 #include "kernels3.cuh"
 #include "kernels_avoid.cuh"
+#include "kernels_rescue.cuh"
 #include "host_build.cuh"
 #include "kernels_stats.cuh"
 

@@ -430,25 +430,31 @@ struct TlsHost
 const unsigned SHADOW_LIST_CAPACITY = 1000;      // TemplateBuilder::TRACKED_REPEATS_MAX_ONE_READ (TemplateBuilder.hh:145, .cpp:82)
 } // namespace
 
-/// ShadowAligner::rescueShadow of every request up to the point where the shadow lists stand in PipelineState::work
-/// (rescueListBegin / rescueListCount / rescuePools, outFlags = rescued); isaac_ext_rescue_shadows flattens them for its
-/// caller, isaac_ext_build_templates reads them where they are.
-static int rescueShadowLists(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n, const isaac_ext_rescue_request_t *requests)
+/// exclusive prefix sum of n 32-bit counts; out[n] = total (cub::DeviceScan over n + 1 items, the last input is ignored)
+static cudaError_t exclusiveSum(isaac_ext_ctx *ctx, uint32_t *counts, uint32_t *out, uint32_t n)
+{
+    PipelineState &ps = ctx->pipeline;
+    size_t bytes = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, bytes, counts, out, int(n) + 1, ctx->stream);
+    if (e != cudaSuccess) return e;
+    e = ps.dScanTemp.reserve(bytes + 16);
+    if (e != cudaSuccess) return e;
+    ++ctx->launches;
+    return cub::DeviceScan::ExclusiveSum(ps.dScanTemp.p, bytes, counts, out, int(n) + 1, ctx->stream);
+}
+
+extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
+                                        const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
-    if (!tls || (n && !requests)) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
+    if (!tls || !result || (n && !requests)) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (ctx->reads.readCount != 2) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "shadow rescue needs paired reads (ShadowAligner.cpp:170)");
     CK(cudaSetDevice(ctx->device));
     PipelineState &ps = ctx->pipeline;
     const unsigned T = ctx->hostThreads;
     const TlsHost stats(*tls);
-    HostPools &pools = ps.rescuePools;
-    pools = HostPools();
-    ps.outFlags.assign(n, 0);
-    std::vector<uint32_t> &listCount = ps.rescueListCount;
-    std::vector<uint64_t> &listBegin = ps.rescueListBegin;
-    listCount.assign(n, 0); listBegin.assign(n, 0);
+    uint32_t fragmentTotal = 0, wordTotal = 0;
     PhaseTimer timer("rescue");
     if (n && stats.coherent())                                                   // :164-168
     {
@@ -508,12 +514,10 @@ static int rescueShadowLists(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
             CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));
         }
         timer.mark("K5 shadow candidates");
-        CK(cudaMemcpyAsync(ps.hTaskBegin.p, ps.dTaskBegin.p, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ps.hTaskCount.p, ps.dTaskCount.p, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (poolSize)
         {
+            // ---- K1: UngappedAligner::alignUngapped of every candidate position (:205-236)
             CK(ps.dFrag.reserve(poolSize)); CK(ps.dCig.reserve(size_t(poolSize) * 3));
-            CK(ps.hFrag1.reserve(poolSize)); CK(ps.hCig1.reserve(size_t(poolSize) * 3));
             const uint32_t *clip = nullptr;
             if (ctx->adapters.count)
             {
@@ -528,109 +532,79 @@ static int rescueShadowLists(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
             }
             const int rc = ungappedDevice(ctx, poolSize, ps.dCand.p, ps.dFrag.p, ps.dCig.p, nullptr, ctx->stream, clip);
             if (rc) return rc;
-            CK(cudaMemcpyAsync(ps.hFrag1.p, ps.dFrag.p, size_t(poolSize) * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(ps.hCig1.p, ps.dCig.p, size_t(poolSize) * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         }
+        // ---- R2 on the device: shadow lists, best shadow, neighbours to gap-align (:205-256)
+        const unsigned rgrid = gridFor(ctx, n, 128, 16);
+        CK(ps.dKept.reserve(size_t(poolSize) + 1)); CK(ps.dAdoptedBy.reserve(size_t(poolSize) + 1)); CK(ps.dListState.reserve(n));
+        CK(ps.dCounts.reserve(size_t(n) * 3 + 1)); CK(ps.dBegins.reserve(size_t(n) * 3 + 3)); CK(ps.dRescued.reserve(n)); CK(ps.hTotals.reserve(4));
+        uint32_t *gapCounts = ps.dCounts.p, *listCounts = ps.dCounts.p + n, *wordCounts = ps.dCounts.p + 2 * size_t(n);
+        uint32_t *gapBegin = ps.dBegins.p, *fragmentBegin = ps.dBegins.p + (n + 1), *wordBegin = ps.dBegins.p + 2 * (size_t(n) + 1);
+        shadowSelectKernel<<<rgrid, 128, 0, ctx->stream>>>(n, ps.dTaskBegin.p, ps.dTaskCount.p, ps.dFrag.p, ps.dKept.p, ps.dListState.p, gapCounts);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(exclusiveSum(ctx, gapCounts, gapBegin, n));
+        CK(cudaMemcpyAsync(ps.hTotals.p, gapBegin + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        timer.mark("K1 ungapped + copies");
-        pools.pools[0] = ps.hCig1.p;
-
-        // ---- R2: shadow lists, best shadow, neighbours to gap-align (:205-256)
-        ps.work.reserve(poolSize);
-        const unsigned parts = partitionCount(T, n);
-        std::vector<int64_t> best(n, -1);
-        std::vector<uint8_t> full(n, 0);
-        std::vector<std::vector<uint64_t>> gapTargets(parts);
-        std::vector<std::vector<uint32_t>> gapRequests(parts);     // the rescue call (= adapter clipper) of every target
-        std::vector<uint64_t> gapBegin(parts + 1, 0);
-        parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
-            for (size_t i = b; i < e; ++i)
-            {
-                const uint64_t begin = ps.hTaskBegin.p[i];
-                const unsigned count = ps.hTaskCount.p[i];
-                WorkFragment *list = ps.work.p + begin;
-                listBegin[i] = begin;
-                unsigned size = 0;
-                for (unsigned k = 0; k < count; ++k)
-                {
-                    if (size == SHADOW_LIST_CAPACITY) { full[i] = 1; break; }                        // :212-215
-                    const isaac_ext_fragment_t &f = ps.hFrag1.p[begin + k];
-                    if (!f.cigarLength) continue;                                                    // alignUngapped returned 0 (:223)
-                    list[size].f = f; list[size].pool = 0; list[size].slot = uint32_t(begin + k);
-                    if (best[i] < 0 || lpLess(list[best[i]].f.logProbability, f.logProbability)) best[i] = size;   // :227-230
-                    ++size;
-                }
-                listCount[i] = size;
-                if (full[i] || best[i] < 0) continue;                                                // :238-241
-                if (ISAAC_EXT_SW_MISMATCH_CUTOFF < list[best[i]].f.mismatchCount)                     // :243
-                    for (unsigned k = 0; k + 1 < size; ++k)
-                        if (list[k + 1].f.position - list[k].f.position < long(ISAAC_EXT_SW_DISTANCE_CUTOFF) &&
-                            ISAAC_EXT_SW_MISMATCH_CUTOFF < list[k].f.mismatchCount)                   // :249-253
-                        {
-                            gapTargets[t].push_back(begin + k);
-                            gapRequests[t].push_back(uint32_t(i));
-                        }
-            }
-            gapBegin[t + 1] = gapTargets[t].size();
-        });
-        timer.mark("R2 lists + best");
-        for (unsigned p = 0; p < parts; ++p) gapBegin[p + 1] += gapBegin[p];
-        const uint64_t n3 = gapBegin[parts];
+        const uint32_t n3 = ps.hTotals.p[0];
+        timer.mark("K1 ungapped + R2 lists");
         if (n3)
         {
-            CK(ps.hCand3.reserve(n3)); CK(ps.hFrag3.reserve(n3)); CK(ps.hCig3.reserve(n3 * GAPPED_STRIDE));
-            CK(ps.hSlot.reserve(n3));
-            parallelRanges(T, n, [&](unsigned t, size_t, size_t) {
-                for (size_t k = 0; k < gapTargets[t].size(); ++k)
-                {
-                    const WorkFragment &w = ps.work.p[gapTargets[t][k]];
-                    ps.hCand3.p[gapBegin[t] + k] = candidateOf(w.f, pools.unclippedPosition(w));
-                    ps.hSlot.p[gapBegin[t] + k] = gapRequests[t][k];
-                }
-            });
-            const int rc = runGapped(ctx, uint32_t(n3), ps.hCand3.p, GAPPED_STRIDE, ps.hFrag3.p, ps.hCig3.p, ps.hSlot.p);
+            // ---- K2: the gapped aligner on the neighbours (:249-262), candidates written in list order by the device
+            CK(ps.dCand3.reserve(n3)); CK(ps.dFrag3.reserve(n3)); CK(ps.dCig3.reserve(size_t(n3) * GAPPED_STRIDE));
+            CK(ps.dSlot3.reserve(n3)); CK(ps.dSources.reserve(n3));
+            shadowGapKernel<<<rgrid, 128, 0, ctx->stream>>>(n, ps.dTaskBegin.p, ps.dListState.p, gapBegin, ps.dFrag.p, ps.dCig.p, ps.dKept.p,
+                                                            ps.dCand3.p, ps.dSlot3.p, ps.dSources.p);
+            ++ctx->launches;
+            CK(cudaGetLastError());
+            const uint32_t *clip = nullptr;
+            int rc = adapterSlotClip(ctx, n3, ps.dCand3.p, ps.dSlot3.p, ctx->stream, &clip);
+            if (!rc) rc = gappedDevice(ctx, n3, ps.dCand3.p, GAPPED_STRIDE, ps.dFrag3.p, ps.dCig3.p, nullptr, ctx->stream, clip);
             if (rc) return rc;
-            pools.pools[2] = ps.hCig3.p;
         }
-        timer.mark("K2 gapped + copies");
-        // ---- R3: acceptance in list order, best shadow first (:255-290)
-        parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
-            size_t g = 0;
-            for (size_t i = b; i < e; ++i)
-            {
-                WorkFragment *list = ps.work.p + listBegin[i];
-                for (; g < gapTargets[t].size() && gapTargets[t][g] < listBegin[i] + listCount[i] && gapTargets[t][g] >= listBegin[i]; ++g)
-                {
-                    WorkFragment &w = ps.work.p[gapTargets[t][g]];
-                    const isaac_ext_fragment_t &gf = ps.hFrag3.p[gapBegin[t] + g];
-                    if (acceptGapped(w.f, gf, ctx->cfg.gappedMismatchesMax))
-                    {
-                        adoptAlignment(w, gf, 2, uint32_t(gapBegin[t] + g));
-                        if (lpLess(list[best[i]].f.logProbability, w.f.logProbability)) best[i] = int64_t(&w - list);   // :265-268
-                    }
-                }
-                if (full[i] || best[i] < 0) continue;
-                if (best[i] != 0) std::swap(list[0], list[best[i]]);                                  // :285-288
-                ps.outFlags[i] = 1;
-            }
-        });
-        timer.mark("R3 accept + best first");
+        // ---- R3 on the device: acceptance in list order, best shadow first (:255-290), then the flat result
+        shadowAcceptKernel<<<rgrid, 128, 0, ctx->stream>>>(n, ps.dTaskBegin.p, ps.dListState.p, gapBegin, ps.dSources.p, ps.dFrag.p, ps.dFrag3.p,
+                                                           ctx->cfg.gappedMismatchesMax, ps.dKept.p, ps.dAdoptedBy.p, listCounts, wordCounts,
+                                                           ps.dRescued.p);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        CK(exclusiveSum(ctx, listCounts, fragmentBegin, n));
+        CK(exclusiveSum(ctx, wordCounts, wordBegin, n));
+        CK(cudaMemcpyAsync(ps.hTotals.p + 1, fragmentBegin + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ps.hTotals.p + 2, wordBegin + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        uint32_t flag = 0;
+        CK(cudaMemcpyAsync(&flag, ctx->errorFlag.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (flag)
+        {
+            CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));
+            return ctx->fail(ISAAC_EXT_E_CAPACITY, "a gapped CIGAR did not fit the cigar stride");
+        }
+        fragmentTotal = ps.hTotals.p[1]; wordTotal = ps.hTotals.p[2];
+        timer.mark("K2 gapped + R3 accept");
+        CK(ps.dOutFragments.reserve(fragmentTotal + 1)); CK(ps.dOutCigars.reserve(wordTotal + 1)); CK(ps.dOutBegin.reserve(size_t(n) + 1));
+        CK(ps.hOutFragments.reserve(fragmentTotal + 1)); CK(ps.hOutCigars.reserve(wordTotal + 1)); CK(ps.hOutBegin.reserve(size_t(n) + 1));
+        CK(ps.hRescued.reserve(n));
+        shadowFlattenKernel<<<gridFor(ctx, uint64_t(n) * 32, 128, 16), 128, 0, ctx->stream>>>(
+            n, ps.dTaskBegin.p, listCounts, fragmentBegin, wordBegin, ps.dKept.p, ps.dAdoptedBy.p, ps.dFrag.p, ps.dCig.p, ps.dFrag3.p, ps.dCig3.p,
+            GAPPED_STRIDE, ps.dOutFragments.p, ps.dOutCigars.p, ps.dOutBegin.p);
+        ++ctx->launches;
+        CK(cudaGetLastError());
+        if (fragmentTotal) CK(cudaMemcpyAsync(ps.hOutFragments.p, ps.dOutFragments.p, size_t(fragmentTotal) * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (wordTotal) CK(cudaMemcpyAsync(ps.hOutCigars.p, ps.dOutCigars.p, size_t(wordTotal) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ps.hOutBegin.p, ps.dOutBegin.p, size_t(n) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ps.hRescued.p, ps.dRescued.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ps.hOutBegin.p[n] = fragmentTotal;
+        timer.mark("flatten + copies");
+        result->fragments = ps.hOutFragments.p; result->requestFragmentBegin = ps.hOutBegin.p; result->cigars = ps.hOutCigars.p;
+        result->rescued = ps.hRescued.p; result->fragmentCount = fragmentTotal; result->cigarWords = wordTotal;
+        return ISAAC_EXT_OK;
     }
-    return ISAAC_EXT_OK;
-}
-
-extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
-                                        const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
-{
-    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
-    if (!result) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
-    const int rc = rescueShadowLists(ctx, tls, n, requests);
-    if (rc) return rc;
-    PipelineState &ps = ctx->pipeline;
-    PhaseTimer timer("rescue");
-    flatten(ctx, ps.rescuePools, n, [&](size_t i) { return std::pair<const WorkFragment *, unsigned>(ps.work.p + ps.rescueListBegin[i], ps.rescueListCount[i]); });
-    timer.mark("flatten");
-    result->fragments = ps.outFragments.p; result->requestFragmentBegin = ps.outBegin.p; result->cigars = ps.outCigars.p;
-    result->rescued = ps.outFlags.data(); result->fragmentCount = ps.outFragmentCount; result->cigarWords = ps.outCigarWords;
+    // nothing to rescue (no requests, or template length statistics without a coherent pair of models, :164-168)
+    CK(ps.hOutBegin.reserve(size_t(n) + 1)); CK(ps.hRescued.reserve(size_t(n) + 1));
+    std::fill(ps.hOutBegin.p, ps.hOutBegin.p + n + 1, uint64_t(0));
+    std::fill(ps.hRescued.p, ps.hRescued.p + n, uint8_t(0));
+    result->fragments = ps.hOutFragments.p; result->requestFragmentBegin = ps.hOutBegin.p; result->cigars = ps.hOutCigars.p;
+    result->rescued = ps.hRescued.p; result->fragmentCount = 0; result->cigarWords = 0;
     return ISAAC_EXT_OK;
 }

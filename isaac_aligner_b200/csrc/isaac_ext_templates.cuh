@@ -192,7 +192,8 @@ struct BestPairInfo
 struct RescueAnswer
 {
     bool rescued = false;
-    const WorkFragment *begin = nullptr, *end = nullptr;      // the shadow list where the rescue pass left it
+    const isaac_ext_fragment_t *begin = nullptr, *end = nullptr;
+    const uint32_t *cigars = nullptr;
 };
 
 struct TemplateContext
@@ -213,7 +214,7 @@ struct TemplateWorker
     // rescue plumbing
     bool planning = true;
     std::vector<isaac_ext_rescue_request_t> *requests = nullptr;       // plan: appended to
-    const PipelineState *rescued = nullptr;                           // finish: the shadow lists of the rescue pass, consumed from nextRequest on
+    const isaac_ext_rescue_result_t *rescueResult = nullptr;          // finish: answers, consumed from nextRequest on
     uint64_t nextRequest = 0;
     // BamTemplate
     TFrag bam[2]; uint32_t bamAlignmentScore = 0; bool bamProperPair = false;
@@ -241,17 +242,18 @@ struct TemplateWorker
             return a;
         }
         const uint64_t i = nextRequest++;
-        a.rescued = rescued->outFlags[i] != 0;
-        a.begin = rescued->work.p + rescued->rescueListBegin[i];
-        a.end = a.begin + rescued->rescueListCount[i];
+        a.rescued = rescueResult->rescued[i] != 0;
+        a.begin = rescueResult->fragments + rescueResult->requestFragmentBegin[i];
+        a.end = rescueResult->fragments + rescueResult->requestFragmentBegin[i + 1];
+        a.cigars = rescueResult->cigars;
         return a;
     }
     void loadShadowList(const RescueAnswer &a)
     {
         shadowList.clear();
-        for (const WorkFragment *p = a.begin; p != a.end; ++p)
+        for (const isaac_ext_fragment_t *p = a.begin; p != a.end; ++p)
         {
-            TFrag t; t.f = p->f; t.alignmentScore = -1U; t.cigar = rescued->rescuePools.cigar(*p);
+            TFrag t; t.f = *p; t.alignmentScore = -1U; t.cigar = a.cigars + p->cigarOffset;
             shadowList.push_back(t);
         }
     }
@@ -835,10 +837,11 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     timer.mark("plan");
 
     // ---- one rescue batch
-    // (the shadow lists stay where the rescue pass builds them, PipelineState::work: the per-cluster code reads them in place)
+    isaac_ext_rescue_result_t rescued;
+    std::memset(&rescued, 0, sizeof(rescued));
     if (!st.requests.empty())
     {
-        rc = rescueShadowLists(ctx, tls, uint32_t(st.requests.size()), st.requests.data());
+        rc = isaac_ext_rescue_shadows(ctx, tls, uint32_t(st.requests.size()), st.requests.data(), &rescued);
         if (rc) return rc;
     }
     timer.mark("rescue_shadows");
@@ -849,7 +852,7 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     std::vector<uint64_t> partFirstCluster(parts + 1, n);
     parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
         TemplateWorker w(cx);
-        w.planning = false; w.rescued = &ctx->pipeline;
+        w.planning = false; w.rescueResult = &rescued;
         std::vector<uint32_t> &pool = partCigars[t];
         partFirstCluster[t] = b;
         for (size_t c = b; c < e; ++c)
