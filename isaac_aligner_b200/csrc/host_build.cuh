@@ -60,10 +60,11 @@ struct PipelineState
     DeviceBuffer<isaac_ext_candidate_t> dCand3;
     DeviceBuffer<isaac_ext_fragment_t> dFrag3, dOutFragments;
     DeviceBuffer<uint64_t> dOutBegin;
-    PinnedBuffer<uint32_t> hTotals, hOutCigars;
-    PinnedBuffer<isaac_ext_fragment_t> hOutFragments;
-    PinnedBuffer<uint64_t> hOutBegin;
-    PinnedBuffer<uint8_t> hRescued;
+    // two result sets: isaac_ext_build_templates reads one while the next slice's rescue pass fills the other
+    PinnedBuffer<uint32_t> hTotals, hOutCigars[2];
+    PinnedBuffer<isaac_ext_fragment_t> hOutFragments[2];
+    PinnedBuffer<uint64_t> hOutBegin[2];
+    PinnedBuffer<uint8_t> hRescued[2];
 
     void release()
     {
@@ -72,8 +73,8 @@ struct PipelineState
         hAdapterFirst.release(); dAdapterFirst.release(); hSlot.release(); dSlot.release();
         dKept.release(); dAdoptedBy.release(); dCounts.release(); dBegins.release(); dSlot3.release(); dSources.release(); dCig3.release();
         dOutCigars.release(); dListState.release(); dRescued.release(); dScanTemp.release(); dCand3.release(); dFrag3.release();
-        dOutFragments.release(); dOutBegin.release(); hTotals.release(); hOutCigars.release(); hOutFragments.release(); hOutBegin.release();
-        hRescued.release();
+        dOutFragments.release(); dOutBegin.release(); hTotals.release();
+        for (int k = 0; k < 2; ++k) { hOutCigars[k].release(); hOutFragments[k].release(); hOutBegin[k].release(); hRescued[k].release(); }
         dCand.release(); dFrag.release(); dCig.release(); dTasks.release(); dIndel.release(); dShadowTasks.release();
         dShadowScratch.release(); dTaskBegin.release(); dTaskCount.release(); dPoolSize.release();
     }

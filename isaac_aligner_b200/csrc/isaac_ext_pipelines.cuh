@@ -443,8 +443,9 @@ static cudaError_t exclusiveSum(isaac_ext_ctx *ctx, uint32_t *counts, uint32_t *
     return cub::DeviceScan::ExclusiveSum(ps.dScanTemp.p, bytes, counts, out, int(n) + 1, ctx->stream);
 }
 
-extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
-                                        const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
+/// isaac_ext_rescue_shadows with its flat result in result set 'slot' (0 or 1) of the context
+static int rescueShadowsInto(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n, const isaac_ext_rescue_request_t *requests,
+                             isaac_ext_rescue_result_t *result, const unsigned slot)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
@@ -582,29 +583,35 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
         fragmentTotal = ps.hTotals.p[1]; wordTotal = ps.hTotals.p[2];
         timer.mark("K2 gapped + R3 accept");
         CK(ps.dOutFragments.reserve(fragmentTotal + 1)); CK(ps.dOutCigars.reserve(wordTotal + 1)); CK(ps.dOutBegin.reserve(size_t(n) + 1));
-        CK(ps.hOutFragments.reserve(fragmentTotal + 1)); CK(ps.hOutCigars.reserve(wordTotal + 1)); CK(ps.hOutBegin.reserve(size_t(n) + 1));
-        CK(ps.hRescued.reserve(n));
+        CK(ps.hOutFragments[slot].reserve(fragmentTotal + 1)); CK(ps.hOutCigars[slot].reserve(wordTotal + 1)); CK(ps.hOutBegin[slot].reserve(size_t(n) + 1));
+        CK(ps.hRescued[slot].reserve(n));
         shadowFlattenKernel<<<gridFor(ctx, uint64_t(n) * 32, 128, 16), 128, 0, ctx->stream>>>(
             n, ps.dTaskBegin.p, listCounts, fragmentBegin, wordBegin, ps.dKept.p, ps.dAdoptedBy.p, ps.dFrag.p, ps.dCig.p, ps.dFrag3.p, ps.dCig3.p,
             GAPPED_STRIDE, ps.dOutFragments.p, ps.dOutCigars.p, ps.dOutBegin.p);
         ++ctx->launches;
         CK(cudaGetLastError());
-        if (fragmentTotal) CK(cudaMemcpyAsync(ps.hOutFragments.p, ps.dOutFragments.p, size_t(fragmentTotal) * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (wordTotal) CK(cudaMemcpyAsync(ps.hOutCigars.p, ps.dOutCigars.p, size_t(wordTotal) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ps.hOutBegin.p, ps.dOutBegin.p, size_t(n) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ps.hRescued.p, ps.dRescued.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (fragmentTotal) CK(cudaMemcpyAsync(ps.hOutFragments[slot].p, ps.dOutFragments.p, size_t(fragmentTotal) * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (wordTotal) CK(cudaMemcpyAsync(ps.hOutCigars[slot].p, ps.dOutCigars.p, size_t(wordTotal) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ps.hOutBegin[slot].p, ps.dOutBegin.p, size_t(n) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ps.hRescued[slot].p, ps.dRescued.p, n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ps.hOutBegin.p[n] = fragmentTotal;
+        ps.hOutBegin[slot].p[n] = fragmentTotal;
         timer.mark("flatten + copies");
-        result->fragments = ps.hOutFragments.p; result->requestFragmentBegin = ps.hOutBegin.p; result->cigars = ps.hOutCigars.p;
-        result->rescued = ps.hRescued.p; result->fragmentCount = fragmentTotal; result->cigarWords = wordTotal;
+        result->fragments = ps.hOutFragments[slot].p; result->requestFragmentBegin = ps.hOutBegin[slot].p; result->cigars = ps.hOutCigars[slot].p;
+        result->rescued = ps.hRescued[slot].p; result->fragmentCount = fragmentTotal; result->cigarWords = wordTotal;
         return ISAAC_EXT_OK;
     }
     // nothing to rescue (no requests, or template length statistics without a coherent pair of models, :164-168)
-    CK(ps.hOutBegin.reserve(size_t(n) + 1)); CK(ps.hRescued.reserve(size_t(n) + 1));
-    std::fill(ps.hOutBegin.p, ps.hOutBegin.p + n + 1, uint64_t(0));
-    std::fill(ps.hRescued.p, ps.hRescued.p + n, uint8_t(0));
-    result->fragments = ps.hOutFragments.p; result->requestFragmentBegin = ps.hOutBegin.p; result->cigars = ps.hOutCigars.p;
-    result->rescued = ps.hRescued.p; result->fragmentCount = 0; result->cigarWords = 0;
+    CK(ps.hOutBegin[slot].reserve(size_t(n) + 1)); CK(ps.hRescued[slot].reserve(size_t(n) + 1));
+    std::fill(ps.hOutBegin[slot].p, ps.hOutBegin[slot].p + n + 1, uint64_t(0));
+    std::fill(ps.hRescued[slot].p, ps.hRescued[slot].p + n, uint8_t(0));
+    result->fragments = ps.hOutFragments[slot].p; result->requestFragmentBegin = ps.hOutBegin[slot].p; result->cigars = ps.hOutCigars[slot].p;
+    result->rescued = ps.hRescued[slot].p; result->fragmentCount = 0; result->cigarWords = 0;
     return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
+                                        const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
+{
+    return rescueShadowsInto(ctx, tls, n, requests, result, 0);
 }

@@ -817,89 +817,140 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
         }
     };
 
-    // ---- plan: which rescueShadow calls does every cluster make
-    const unsigned parts = partitionCount(T, n);
-    std::vector<std::vector<isaac_ext_rescue_request_t>> partRequests(parts);
-    st.clusterRequestBegin.assign(size_t(n) + 1, 0);
-    parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
-        TemplateWorker w(cx);
-        w.planning = true; w.requests = &partRequests[t];
-        for (size_t c = b; c < e; ++c)
-        {
-            const size_t before = partRequests[t].size();
-            if (st.buildFlags[c]) { loadCluster(w, uint32_t(c)); w.run(); }
-            st.clusterRequestBegin[c + 1] = partRequests[t].size() - before;
-        }
-    });
-    for (size_t c = 0; c < n; ++c) st.clusterRequestBegin[c + 1] += st.clusterRequestBegin[c];
-    st.requests.clear();
-    for (const std::vector<isaac_ext_rescue_request_t> &p : partRequests) st.requests.insert(st.requests.end(), p.begin(), p.end());
-    timer.mark("plan");
-
-    // ---- one rescue batch
-    isaac_ext_rescue_result_t rescued;
-    std::memset(&rescued, 0, sizeof(rescued));
-    if (!st.requests.empty())
-    {
-        rc = isaac_ext_rescue_shadows(ctx, tls, uint32_t(st.requests.size()), st.requests.data(), &rescued);
-        if (rc) return rc;
-    }
-    timer.mark("rescue_shadows");
-
-    // ---- finish: pair selection and mapping scores with the answers
+    // ---- plan / rescue / finish, software-pipelined over slices of the tile: while the GPU answers the rescueShadow calls of
+    // slice s (one isaac_ext_rescue_shadows batch, on a helper thread), the host threads finish slice s - 1 and plan slice s + 1.
+    // Clusters are independent, so slicing changes nothing in the results.
+    // (measured on 500 k pairs and 16 host threads: 109 ms in one piece, 103 ms in two slices, 107 ms in four)
+    unsigned slices = n >= 100000 ? 2u : 1u;
+    if (const char *e = std::getenv("ISAAC_EXT_TEMPLATE_SLICES")) slices = unsigned(std::max(1, std::min(16, std::atoi(e))));
+    slices = std::max(1u, std::min(slices, std::max(1u, n)));
+    auto sliceBegin = [&](unsigned s) { return uint32_t(uint64_t(n) * s / slices); };
     st.templates.reserve(n); st.fragments.reserve(size_t(n) * readCount);
-    std::vector<std::vector<uint32_t>> partCigars(parts);
-    std::vector<uint64_t> partFirstCluster(parts + 1, n);
-    parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
-        TemplateWorker w(cx);
-        w.planning = false; w.rescueResult = &rescued;
-        std::vector<uint32_t> &pool = partCigars[t];
-        partFirstCluster[t] = b;
-        for (size_t c = b; c < e; ++c)
-        {
-            isaac_ext_template_t &o = st.templates.p[c];
-            std::memset(&o, 0, sizeof(o));
-            w.clusterId = uint32_t(c);
-            bool ok = false;
-            if (st.buildFlags[c])
+    st.clusterRequestBegin.assign(size_t(n) + 1, 0);
+    struct Slice
+    {
+        std::vector<isaac_ext_rescue_request_t> requests;
+        isaac_ext_rescue_result_t rescued;
+        int rc = ISAAC_EXT_OK;
+        std::thread worker;
+    };
+    std::vector<Slice> slice(slices);
+    struct CigarPart { std::vector<uint32_t> words; size_t firstCluster, endCluster; };
+    std::vector<CigarPart> cigarParts;
+    uint64_t requestTotal = 0;
+
+    auto planSlice = [&](unsigned s) {
+        const uint32_t cb = sliceBegin(s), ce = sliceBegin(s + 1);
+        const unsigned parts = partitionCount(T, ce - cb);
+        std::vector<std::vector<isaac_ext_rescue_request_t>> partRequests(parts);
+        parallelRanges(T, ce - cb, [&](unsigned t, size_t b, size_t e) {
+            TemplateWorker w(cx);
+            w.planning = true; w.requests = &partRequests[t];
+            for (size_t c = cb + b; c < cb + e; ++c)
             {
-                loadCluster(w, uint32_t(c));
-                w.nextRequest = st.clusterRequestBegin[c];
-                ok = w.run();
-                o.hadFragments = 1;
+                const size_t before = partRequests[t].size();
+                if (st.buildFlags[c]) { loadCluster(w, uint32_t(c)); w.run(); }
+                st.clusterRequestBegin[c + 1] = partRequests[t].size() - before;     // per cluster for now, offsets below
             }
-            else
+        });
+        uint64_t at = 0;                                                             // offsets within the slice's own batch
+        for (size_t c = cb; c < ce; ++c) { const uint64_t k = st.clusterRequestBegin[c + 1]; st.clusterRequestBegin[c + 1] = at; at += k; }
+        slice[s].requests.clear();
+        for (const std::vector<isaac_ext_rescue_request_t> &p : partRequests) slice[s].requests.insert(slice[s].requests.end(), p.begin(), p.end());
+        requestTotal += slice[s].requests.size();
+    };
+    auto startRescue = [&](unsigned s) {
+        Slice &sl = slice[s];
+        std::memset(&sl.rescued, 0, sizeof(sl.rescued));
+        if (sl.requests.empty()) return;
+        sl.worker = std::thread([&sl, ctx, tls, s] {
+            sl.rc = rescueShadowsInto(ctx, tls, uint32_t(sl.requests.size()), sl.requests.data(), &sl.rescued, s & 1u);
+        });
+    };
+    auto finishSlice = [&](unsigned s) {
+        Slice &sl = slice[s];
+        const uint32_t cb = sliceBegin(s), ce = sliceBegin(s + 1);
+        const unsigned parts = partitionCount(T, ce - cb);
+        const size_t firstPart = cigarParts.size();
+        cigarParts.resize(firstPart + parts);
+        for (unsigned t = 0; t < parts; ++t) cigarParts[firstPart + t].firstCluster = cigarParts[firstPart + t].endCluster = ce;
+        parallelRanges(T, ce - cb, [&](unsigned t, size_t b, size_t e) {
+            TemplateWorker w(cx);
+            w.planning = false; w.rescueResult = &sl.rescued;
+            CigarPart &part = cigarParts[firstPart + t];
+            std::vector<uint32_t> &pool = part.words;
+            part.firstCluster = cb + b; part.endCluster = cb + e;
+            for (size_t c = cb + b; c < cb + e; ++c)
             {
-                w.frags[0].clear(); w.frags[1].clear(); w.ownCigars.clear();
-                for (unsigned r = 0; r < 2; ++r) w.bam[r] = TFrag::unaligned(uint32_t(c) * readCount + std::min(r, readCount - 1), r);
-                w.bamAlignmentScore = 0; w.bamProperPair = false;
+                isaac_ext_template_t &o = st.templates.p[c];
+                std::memset(&o, 0, sizeof(o));
+                w.clusterId = uint32_t(c);
+                bool ok = false;
+                if (st.buildFlags[c])
+                {
+                    loadCluster(w, uint32_t(c));
+                    w.nextRequest = st.clusterRequestBegin[c + 1];                   // offset of the cluster's first call in the slice's batch
+                    ok = w.run();
+                    o.hadFragments = 1;
+                }
+                else
+                {
+                    w.frags[0].clear(); w.frags[1].clear(); w.ownCigars.clear();
+                    for (unsigned r = 0; r < 2; ++r) w.bam[r] = TFrag::unaligned(uint32_t(c) * readCount + std::min(r, readCount - 1), r);
+                    w.bamAlignmentScore = 0; w.bamProperPair = false;
+                }
+                o.built = ok; o.alignmentScore = w.bamAlignmentScore; o.properPair = w.bamProperPair;
+                for (unsigned r = 0; r < readCount; ++r)
+                {
+                    const TFrag &src = w.bam[r];
+                    isaac_ext_fragment_t f = src.f;
+                    f.readId = uint32_t(c) * readCount + r;
+                    o.fragmentAlignmentScore[r] = src.alignmentScore;
+                    const uint32_t *words = w.cigarOf(src);
+                    f.cigarOffset = uint32_t(pool.size());                 // relative to this part, rebased below
+                    if (f.cigarLength && words) pool.insert(pool.end(), words, words + f.cigarLength);
+                    st.fragments.p[c * readCount + r] = f;
+                }
             }
-            o.built = ok; o.alignmentScore = w.bamAlignmentScore; o.properPair = w.bamProperPair;
-            for (unsigned r = 0; r < readCount; ++r)
-            {
-                const TFrag &src = w.bam[r];
-                isaac_ext_fragment_t f = src.f;
-                f.readId = uint32_t(c) * readCount + r;
-                o.fragmentAlignmentScore[r] = src.alignmentScore;
-                const uint32_t *words = w.cigarOf(src);
-                f.cigarOffset = uint32_t(pool.size());                 // relative to this partition, rebased below
-                if (f.cigarLength && words) pool.insert(pool.end(), words, words + f.cigarLength);
-                st.fragments.p[c * readCount + r] = f;
-            }
-        }
-    });
+        });
+    };
+    auto joinRescue = [&](unsigned s) -> int {
+        if (slice[s].worker.joinable()) slice[s].worker.join();
+        return slice[s].rc;
+    };
+
+    planSlice(0);
+    startRescue(0);
+    for (unsigned s = 0; s < slices; ++s)
+    {
+        if (s + 1 < slices) planSlice(s + 1);                       // host, while the GPU works on slice s
+        rc = joinRescue(s);
+        if (rc) { for (unsigned k = s + 1; k < slices; ++k) joinRescue(k); return rc; }
+        if (s + 1 < slices) startRescue(s + 1);                     // its result set (s + 1) & 1 was last read by finishSlice(s - 1)
+        finishSlice(s);                                             // host, while the GPU works on slice s + 1
+    }
+    timer.mark("plan / rescue_shadows / finish");
+
     uint64_t words = 0;
-    std::vector<uint64_t> partBase(parts, 0);
-    for (unsigned t = 0; t < parts; ++t) { partBase[t] = words; words += partCigars[t].size(); }
+    for (CigarPart &part : cigarParts) { const uint64_t k = part.words.size(); part.endCluster = std::max(part.endCluster, part.firstCluster); words += k; }
     st.cigars.reserve(words);
-    parallelRanges(T, n, [&](unsigned t, size_t b, size_t e) {
-        if (!partCigars[t].empty()) std::memcpy(st.cigars.p + partBase[t], partCigars[t].data(), partCigars[t].size() * sizeof(uint32_t));
-        for (size_t i = b * readCount; i < e * readCount; ++i) st.fragments.p[i].cigarOffset += uint32_t(partBase[t]);
-    });
-    timer.mark("finish");
+    {
+        std::vector<uint64_t> partBase(cigarParts.size(), 0);
+        uint64_t at = 0;
+        for (size_t k = 0; k < cigarParts.size(); ++k) { partBase[k] = at; at += cigarParts[k].words.size(); }
+        parallelRanges(T, cigarParts.size(), [&](unsigned, size_t b, size_t e) {
+            for (size_t k = b; k < e; ++k)
+            {
+                const CigarPart &part = cigarParts[k];
+                if (!part.words.empty()) std::memcpy(st.cigars.p + partBase[k], part.words.data(), part.words.size() * sizeof(uint32_t));
+                for (size_t i = part.firstCluster * readCount; i < part.endCluster * readCount; ++i) st.fragments.p[i].cigarOffset += uint32_t(partBase[k]);
+            }
+        });
+    }
+    timer.mark("cigar pool");
 
     result->templates = st.templates.p; result->fragments = st.fragments.p; result->cigars = st.cigars.p;
-    result->cigarWords = words; result->rescueRequests = st.requests.size();
+    result->cigarWords = words; result->rescueRequests = requestTotal;
 
     // ---- end clippers on the kept templates (MatchSelector.cpp:336-346): one kernel pass over the tile
     if (options->clipFlags & (ISAAC_EXT_CLIP_SEMIALIGNED | ISAAC_EXT_CLIP_OVERLAPPING))
