@@ -44,6 +44,22 @@ struct Contig
 };
 } // namespace reference
 
+namespace flowcell
+{
+/// flowcell::SequencingAdapterMetadata (SequencingAdapterMetadata.hh:36-72): clipLength 0 = unbounded
+struct SequencingAdapterMetadata
+{
+    std::string sequence_; bool reverse_; unsigned clipLength_;
+    SequencingAdapterMetadata(const std::string &sequence, bool reverse) : sequence_(sequence), reverse_(reverse), clipLength_(unsigned(sequence.size())) {}
+    SequencingAdapterMetadata(const std::string &sequence, bool reverse, unsigned clipLength) : sequence_(sequence), reverse_(reverse), clipLength_(clipLength) {}
+    const std::string &getSequence() const { return sequence_; }
+    bool isReverse() const { return reverse_; }
+    unsigned getClipLength() const { return clipLength_; }
+    bool isUnbounded() const { return !clipLength_; }
+};
+typedef std::vector<SequencingAdapterMetadata> SequencingAdapterMetadataList;
+} // namespace flowcell
+
 /// RAII owner of one isaac_ext_ctx
 class Context
 {
@@ -67,6 +83,17 @@ public:
         std::vector<const char *> bases; std::vector<uint64_t> lengths;
         for (size_t i = 0; i < contigs.size(); ++i) { bases.push_back(contigs[i].forward_.data()); lengths.push_back(contigs[i].forward_.size()); }
         check(isaac_ext_set_reference(ctx_, uint32_t(contigs.size()), bases.data(), lengths.data()));
+    }
+    /// the matchSelector::SequencingAdapterList every later build() / rescueShadow() / alignUngapped() clips with
+    void setAdapters(const flowcell::SequencingAdapterMetadataList &adapters)
+    {
+        std::vector<isaac_ext_adapter_t> flat;
+        for (size_t i = 0; i < adapters.size(); ++i)
+        {
+            const isaac_ext_adapter_t a = {adapters[i].getSequence().c_str(), adapters[i].isReverse() ? 1u : 0u, adapters[i].getClipLength()};
+            flat.push_back(a);
+        }
+        check(isaac_ext_set_adapters(ctx_, uint32_t(flat.size()), flat.empty() ? 0 : flat.data()));
     }
 private:
     Context(const Context &); Context &operator=(const Context &);

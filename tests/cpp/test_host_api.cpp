@@ -190,8 +190,58 @@ static void testTemplateBuilder()
     }
 }
 
+// testSequencingAdapter.cpp: testMp51M49S (:184-204, a mate-pair junction adapter in the middle of the read: the longer, matching
+// side is kept) and testStd38M62S (:376-401, an unbounded standard adapter: everything from the adapter on is clipped), aligned
+// through FragmentBuilder::build with one seed match at position 0 like the reference's harness aligns at position 0.
+static void testSequencingAdapter()
+{
+    struct Case { const char *read, *reference; bool matePair; const char *cigar; unsigned observedLength; };
+    const Case cases[2] = {
+        {"CGATTGTCTTTGCTGCCAATTTTAGCGTTGGCGTTAACGTCATGCTTAAGCCTGTCTCTTATACACATCTAGATGTGTATAAGAGACAGCTGCTACGCCA",
+         "CGATTGTCTTTGCTGCCAATTTTAGCGTTGGCGTTAACGTCATGCTTAAGCCAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", true, "51M49S", 51},
+        {"TGGTTAAGGTAGCGGTAAAAGCGTGTTACCGCAATGTTCTGTCTCTTATACACATCTAGATGTGTATAAGAGACAGGTGCACCGCCTATACACATCTAGA",
+         "TGGTTAAGGTAGCGGTAAAAGCGTGTTACCGCAATGTTCTCTCTTCTCTGGAATATGATAAAAAAAAAAAAAAAAAGTGCACCGCCAAAAAAAAAAAAAA", false, "38M62S", 38}};
+    for (const Case &c : cases)
+    {
+        const std::string read = c.read, ref = c.reference;
+        isaac_ext_config_t cfg = makeConfig(2, -1, -15, -3, -25, unsigned(read.size()), 10, 8, 5, 0);
+        Context context(cfg);
+        std::vector<reference::Contig> contigs(1, reference::Contig(0, "vasja"));
+        contigs[0].forward_ = v(ref);
+        context.setReference(contigs);
+        flowcell::SequencingAdapterMetadataList adapters;
+        adapters.push_back(flowcell::SequencingAdapterMetadata("CTGTCTCTTATACACATCT", false, c.matePair ? 19u : 0u));
+        adapters.push_back(flowcell::SequencingAdapterMetadata("AGATGTGTATAAGAGACAG", true, c.matePair ? 19u : 0u));
+        context.setAdapters(adapters);
+        alignment::Cluster cluster;
+        cluster.readCount = 1; cluster.readLength[0] = unsigned(read.size());
+        for (char b : read) cluster.bcl.push_back(uint8_t((35 << 2) | std::string("ACGT").find(b)));
+        alignment::SeedMetadataList seeds(1);
+        seeds[0].offset = 0; seeds[0].length = 32; seeds[0].readIndex = 0;
+        std::vector<alignment::Match> matches(1);
+        matches[0].seedId = 0u << 1; matches[0].location = ((uint64_t(1) << 40) << 1);
+        alignment::FragmentBuilder builder(context);
+        CHECK(builder.build(seeds, matches.begin(), matches.end(), cluster, false));
+        const std::vector<alignment::FragmentMetadata> &list = builder.getFragments()[0];
+        CHECK_EQ(list.size(), size_t(1));
+        if (!list.empty())
+        {
+            CHECK_EQ(list[0].getCigarString(), c.cigar);
+            CHECK_EQ(list[0].getMismatchCount(), 0u);
+            CHECK_EQ(list[0].getObservedLength(), c.observedLength);
+            CHECK_EQ(list[0].getPosition(), 0L);
+        }
+        // a 2-base sequence is refused like the SequencingAdapter constructor's assertions refuse what it cannot hash
+        bool thrown = false;
+        try { context.setAdapters(flowcell::SequencingAdapterMetadataList(1, flowcell::SequencingAdapterMetadata("AC", false))); }
+        catch (const common::InvalidParameterException &) { thrown = true; }
+        CHECK(thrown);
+    }
+}
+
 int main()
 {
+    testSequencingAdapter();
     testOverflow();
     testBandedSmithWaterman();
     testSimpleDeletionThroughFragmentBuilder();
