@@ -57,11 +57,21 @@ __device__ __forceinline__ void bitonicSort(int *a, unsigned n2)
         }
 }
 
+// Requests whose window fits one warp's scratch go to shadowCandidatesWarpKernel (below), the others to the CTA kernel; both
+// kernels get the whole task list and skip what is not theirs.
+constexpr unsigned SHADOW_WARP_WINDOW = 1024;       // window positions a warp handles (hits <= positions)
+constexpr unsigned SHADOW_WARP_MAX_READ = 1000;     // read positions must fit the low 16 bits of a hash entry with room to spare
+__device__ __forceinline__ bool shadowTaskIsSmall(const ShadowTask &task, const unsigned readLength)
+{
+    return readLength <= SHADOW_WARP_MAX_READ && task.windowEnd - task.windowBegin - long(ISAAC_EXT_SHADOW_KMER) + 1 <= long(SHADOW_WARP_WINDOW);
+}
+
 __global__ void __launch_bounds__(SHADOW_BLOCK)
 shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_t n, const ShadowTask *__restrict__ tasks,
                        int *__restrict__ scratch /* gridDim.x * SHADOW_SCRATCH */,
                        isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity, uint32_t *__restrict__ poolSize,
-                       uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount, uint32_t *__restrict__ errorFlag)
+                       uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount, uint32_t *__restrict__ errorFlag,
+                       const bool largeOnly = false)
 {
     __shared__ uint16_t table[SHADOW_TABLE];
     __shared__ int warpLast[SHADOW_BLOCK / 32];
@@ -77,6 +87,7 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
     {
         const ShadowTask task = tasks[t];
         const unsigned L = reads.length(task.shadowReadId);
+        if (largeOnly && shadowTaskIsSmall(task, L)) continue;       // uniform for the CTA, before any barrier of this request
         const uint64_t *strandWords = reads.strandCodes(task.shadowReadId, task.contigStrand & 1u);
         const long window = task.windowEnd - task.windowBegin;
         // ---- hashShadowKmers (:53-72): first position of every 7-mer of the shadow; warp 0 walks the read in order
@@ -227,6 +238,168 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
             }
         }
         __syncthreads();
+    }
+}
+
+// ---- the same for requests with a small rescue window (nearly all of them: the window is the template length range plus
+// a read length, a few hundred bases): ONE WARP per request, eight requests per CTA, no block barrier anywhere.
+//   * the shadow's 7-mers go into a 512-slot open-addressing hash per warp (key << 16 | first position; atomicMin keeps the
+//     first position) instead of the 4^7-entry table, so that 8 warps x 6 KB fit a CTA and the SM holds 32 warps of them;
+//   * lane l scans the l-th contiguous piece of the window, which keeps the hits in scan order across the warp; the
+//     "drop a hit equal to the previous one" rule (:90-91) is applied inside the lane and then against the last hit of the
+//     nearest lane before it that had one;
+//   * the kept hits (at most one per window position, far below the 10000 cap) are compacted in order, sorted by a bitonic
+//     network in shared memory and made unique in order.
+constexpr unsigned SHADOW_WARP_SLOTS = 512;
+constexpr unsigned SHADOW_WARPS = 8;
+
+__global__ void __launch_bounds__(SHADOW_WARPS * 32)
+shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uint32_t n, const ShadowTask *__restrict__ tasks, isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity,
+                           uint32_t *__restrict__ poolSize, uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount,
+                           uint32_t *__restrict__ errorFlag)
+{
+    __shared__ uint32_t hashAll[SHADOW_WARPS][SHADOW_WARP_SLOTS];
+    __shared__ short candAll[SHADOW_WARPS][SHADOW_WARP_WINDOW];     // a hit = window position - read position: within +-1024
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t *hash = hashAll[warp];
+    short *cand = candAll[warp];
+    const int NONE = INT_MIN;
+    const uint32_t EMPTY = 0xFFFFFFFFu;
+    for (uint32_t t = blockIdx.x * SHADOW_WARPS + warp; t < n; t += gridDim.x * SHADOW_WARPS)
+    {
+        const ShadowTask task = tasks[t];
+        const unsigned L = reads.length(task.shadowReadId);
+        if (!shadowTaskIsSmall(task, L)) continue;
+        const uint64_t *strandWords = reads.strandCodes(task.shadowReadId, task.contigStrand & 1u);
+        const long window = task.windowEnd - task.windowBegin;
+        for (unsigned i = lane; i < SHADOW_WARP_SLOTS; i += 32) hash[i] = EMPTY;
+        __syncwarp();
+        // ---- hashShadowKmers (:53-72): the first position of every 7-mer of the shadow
+        for (unsigned p = lane; p + ISAAC_EXT_SHADOW_KMER <= L; p += 32)
+        {
+            unsigned kmer;
+            if (!kmerOf(readCodes16(strandWords, p), kmer)) continue;
+            const uint32_t entry = (kmer << 16) | p;
+            unsigned h = (kmer ^ (kmer >> 5)) & (SHADOW_WARP_SLOTS - 1u);
+            while (true)
+            {
+                const uint32_t seen = atomicCAS(&hash[h], EMPTY, entry);
+                if (seen == EMPTY) break;
+                if ((seen >> 16) == kmer) { atomicMin(&hash[h], entry); break; }
+                h = (h + 1u) & (SHADOW_WARP_SLOTS - 1u);
+            }
+        }
+        __syncwarp();
+        // ---- findShadowCandidatePositions (:74-102): lane l scans positions [l * piece, (l + 1) * piece) of the window
+        const unsigned positions = window >= long(ISAAC_EXT_SHADOW_KMER) ? unsigned(window - long(ISAAC_EXT_SHADOW_KMER) + 1) : 0u;
+        const unsigned piece = (positions + 31u) / 32u;
+        const unsigned first = lane * piece, last = min(first + piece, positions);
+        const uint64_t g0 = ref.contigOffset[task.contigStrand >> 1] + uint64_t(task.windowBegin);
+        short *mine = cand + first;                     // at most 'piece' (<= 32) hits, kept in place until the compaction
+        unsigned nKeep = 0;
+        int firstHit = NONE, lastHit = NONE;
+        for (unsigned p0 = first; p0 < last; p0 += 10)  // a 16-base fetch holds ten 7-mers
+        {
+            uint64_t x = referenceCodes16(ref, g0 + p0);
+            const unsigned stop = min(p0 + 10u, last);
+            for (unsigned p = p0; p < stop; ++p, x >>= 4)
+            {
+                unsigned kmer;
+                if (!kmerOf(x, kmer)) continue;
+                unsigned h = (kmer ^ (kmer >> 5)) & (SHADOW_WARP_SLOTS - 1u);
+                uint32_t seen;
+                while ((seen = hash[h]) != EMPTY && (seen >> 16) != kmer) h = (h + 1u) & (SHADOW_WARP_SLOTS - 1u);
+                if (seen == EMPTY) continue;
+                const int hit = int(p) - int(seen & 0xFFFFu);                                           // :89
+                if (firstHit == NONE) firstHit = hit;
+                if (hit != lastHit) mine[nKeep++] = short(hit);                                         // :90-91 inside the lane
+                lastHit = hit;
+            }
+        }
+        // the last hit of the nearest lane before this one that had a hit: its equal drops this lane's first kept hit
+        int incl = lastHit;
+#pragma unroll
+        for (unsigned d = 1; d < 32; d <<= 1)
+        {
+            const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d && incl == NONE) incl = o;
+        }
+        int prev = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if (lane == 0) prev = NONE;
+        const bool dropFirst = firstHit != NONE && firstHit == prev;
+        const unsigned kept = nKeep - (dropFirst ? 1u : 0u);
+        unsigned scan = kept;
+#pragma unroll
+        for (unsigned d = 1; d < 32; d <<= 1)
+        {
+            const unsigned o = __shfl_up_sync(0xFFFFFFFFu, scan, d);
+            if (lane >= d) scan += o;
+        }
+        const unsigned count = __shfl_sync(0xFFFFFFFFu, scan, 31);
+        // compaction in scan order: read all own hits first (the destinations of lower lanes may overlap this lane's piece)
+        short hold[32];
+#pragma unroll
+        for (unsigned k = 0; k < 32; ++k) hold[k] = k < kept ? mine[k + (dropFirst ? 1u : 0u)] : short(0);
+        __syncwarp();
+        const unsigned at = scan - kept;
+#pragma unroll
+        for (unsigned k = 0; k < 32; ++k) if (k < kept) cand[at + k] = hold[k];
+        __syncwarp();
+        // ---- sort + unique (:105-111)
+        unsigned n2 = 1;
+        while (n2 < count) n2 <<= 1;
+        for (unsigned i = count + lane; i < n2; i += 32) cand[i] = SHRT_MAX;
+        __syncwarp();
+        for (unsigned k = 2; k <= n2; k <<= 1)
+            for (unsigned j = k >> 1; j > 0; j >>= 1)
+            {
+                for (unsigned i = lane; i < n2; i += 32)
+                {
+                    const unsigned l = i ^ j;
+                    if (l > i)
+                    {
+                        const short a = cand[i], b = cand[l];
+                        if (((i & k) == 0) == (a > b)) { cand[i] = b; cand[l] = a; }
+                    }
+                }
+                __syncwarp();
+            }
+        // ordered unique: heads counted per group of 32 elements
+        unsigned uniqueCount = 0;
+        for (unsigned i0 = 0; i0 < count; i0 += 32)
+        {
+            const unsigned i = i0 + lane;
+            const bool head = i < count && (i == 0 || cand[i] != cand[i - 1]);
+            uniqueCount += __popc(__ballot_sync(0xFFFFFFFFu, head));
+        }
+        unsigned base = 0;
+        if (lane == 0 && uniqueCount)
+        {
+            base = atomicAdd(poolSize, uniqueCount);
+            if (base + uniqueCount > poolCapacity) atomicOr(errorFlag, 2u);
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (uniqueCount && base + uniqueCount <= poolCapacity)
+        {
+            unsigned before = 0;
+            for (unsigned i0 = 0; i0 < count; i0 += 32)
+            {
+                const unsigned i = i0 + lane;
+                const bool head = i < count && (i == 0 || cand[i] != cand[i - 1]);
+                const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+                if (head)
+                {
+                    isaac_ext_candidate_t c;
+                    c.position = task.windowBegin + long(cand[i]);                                      // :216
+                    c.readId = task.shadowReadId;
+                    c.contigStrand = task.contigStrand;
+                    pool[base + before + __popc(heads & ((1u << lane) - 1u))] = c;
+                }
+                before += __popc(heads);
+            }
+        }
+        if (lane == 0) { taskBegin[t] = count ? base : 0u; taskCount[t] = uniqueCount; }
+        __syncwarp();
     }
 }
 
