@@ -184,7 +184,7 @@ def make_pairs_workload(args, rank, n_pairs):
     return genome, ReadSet(sim.bcl, (L, L)), MatchBatch(matches, begin, synth.seed_table(sim), with_gaps=True), Tls.make()
 
 
-def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup):
+def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup, all_ranks=False):
     """FragmentBuilder::build for every cluster, then ShadowAligner::rescueShadow for every request of the stand-in
     template policy, both through the host-pointer ABI (H2D / D2H inside).  Returns a dict with pairs/s."""
     from isaac_aligner_b200 import synth
@@ -217,11 +217,13 @@ def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup):
     tile_stats = ctx.template_stats(mb, tls, templates)
     stats_ms = (time.perf_counter() - t0) * 1e3
     summed = torch.from_numpy(tile_stats.view(np.int64).copy())
-    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+    # the all-reduce is a collective: only where every rank runs this function (the pairs workload; the side measurement of the
+    # micro workload runs on rank 0 alone)
+    if all_ranks and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         summed = distributed.allreduce_stats(summed.cuda()).cpu()
     read1 = summed.numpy().view(np.uint64)[0]
     return {"pairs": n, "template_pairs_per_s": n / tt, "templates_ms": tt * 1e3, "template_stats_ms": stats_ms,
-            "match_selector_stats_all_ranks": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16]))),
+            "match_selector_stats": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16]))),
             "template_rescue_requests": int(templates.rescue_requests),
             "templates_built": int(templates.templates["built"].sum()), "proper_pairs": int(templates.templates["properPair"].sum()),
             "pairs_per_s": n / (tb + tr), "build_ms": tb * 1e3, "rescue_ms": tr * 1e3,
@@ -507,7 +509,7 @@ def run_pairs(args):
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-    line, flat, req = pairs_pipeline_gpu(ctx, reads, mb, tls, args.steps, args.warmup)
+    line, flat, req = pairs_pipeline_gpu(ctx, reads, mb, tls, args.steps, args.warmup, all_ranks=True)
     t = torch.tensor([line["templates_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist

@@ -60,7 +60,7 @@ __device__ __forceinline__ void bitonicSort(int *a, unsigned n2)
 // Requests whose window fits one warp's scratch go to shadowCandidatesWarpKernel (below), the others to the CTA kernel; both
 // kernels get the whole task list and skip what is not theirs.
 constexpr unsigned SHADOW_WARP_WINDOW = 1024;       // window positions a warp handles (hits <= positions)
-constexpr unsigned SHADOW_WARP_MAX_READ = 1000;     // read positions must fit the low 16 bits of a hash entry with room to spare
+constexpr unsigned SHADOW_WARP_MAX_READ = 256;      // at most 250 distinct 7-mers in the 512-slot hash of a warp: it can never fill up
 __device__ __forceinline__ bool shadowTaskIsSmall(const ShadowTask &task, const unsigned readLength)
 {
     return readLength <= SHADOW_WARP_MAX_READ && task.windowEnd - task.windowBegin - long(ISAAC_EXT_SHADOW_KMER) + 1 <= long(SHADOW_WARP_WINDOW);
