@@ -15,9 +15,11 @@
  * iterator-based clipping as index arithmetic.
  */
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -190,8 +192,10 @@ struct Read
 struct Cluster
 {
     Read reads[2];
+    uint32_t id;
     void load(const isaac_ext_reads_t *r, uint32_t clusterId)
     {
+        id = clusterId;
         const uint32_t total = r->readLength[0] + (r->readCount > 1 ? r->readLength[1] : 0);
         const uint8_t *p = r->bcl + size_t(clusterId) * total;
         for (uint32_t i = 0; i < r->readCount; ++i)
@@ -352,15 +356,243 @@ unsigned updateFragmentCigar(const Scores &s, const isaac_ext_reads_t &rm, const
     return matchCount;
 }
 
-/// UngappedAligner::alignUngapped  lib/alignment/fragmentBuilder/UngappedAligner.cpp:39-92 (no adapters)
+/* -------------------------------------------------------------------------------------------------
+ * matchSelector::SequencingAdapter  lib/alignment/matchSelector/SequencingAdapter.cpp:30-139
+ * ------------------------------------------------------------------------------------------------- */
+struct AdapterPort
+{
+    std::string sequence; bool reverse; unsigned clipLength;          // flowcell::SequencingAdapterMetadata (0 = unbounded)
+    std::vector<signed char> kmerPositions;                           // -1 uninitialised, -2 not unique (SequencingAdapter.hh:41-42)
+    static const unsigned MATCH_BASES_MIN = 5;                        // adapterMatchBasesMin_ (:40)
+    static unsigned translate(char c)                                 // oligo::getTranslator(): everything but ACGT is 4 (Nucleotides.hh:41-59)
+    {
+        switch (c) { case 'a': case 'A': return 0; case 'c': case 'C': return 1; case 'g': case 'G': return 2; case 't': case 'T': return 3; default: return 4; }
+    }
+    AdapterPort(const std::string &s, bool r, unsigned clip) : sequence(s), reverse(r), clipLength(clip), kmerPositions(1u << (2 * MATCH_BASES_MIN), -1)
+    {
+        // oligo::KmerGenerator over the adapter (KmerGenerator.hpp:38-124): every window of 5 bases without a non-ACGT base
+        for (size_t i = 0; i + MATCH_BASES_MIN <= sequence.size(); ++i)                               // :40-57
+        {
+            unsigned kmer = 0; bool valid = true;
+            for (unsigned j = 0; j < MATCH_BASES_MIN; ++j) { const unsigned v = translate(sequence[i + j]); valid &= v < 4; kmer = (kmer << 2) | (v & 3); }
+            if (!valid) continue;
+            signed char &pos = kmerPositions[kmer];
+            if (pos == -1) pos = (signed char)i; else pos = -2;
+        }
+    }
+    bool isUnbounded() const { return !clipLength; }
+    bool isStrandCompatible(bool strandReverse) const { return !isUnbounded() || strandReverse == reverse; }   // SequencingAdapter.hh:58-61
+
+    /// getMatchRange (:58-139); positions index the strand sequence; \return false = (mismatchBase, mismatchBase)
+    bool getMatchRange(const std::vector<char> &seq, long sequenceBegin, long sequenceEnd, long mismatchBase, long &first, long &second) const
+    {
+        if (sequenceEnd - mismatchBase < long(MATCH_BASES_MIN)) return false;                       // oligo::generateKmer (KmerGenerator.hpp:150-169)
+        unsigned short kmer = 0;
+        for (unsigned j = 0; j < MATCH_BASES_MIN; ++j) { kmer <<= 2; kmer |= translate(seq[mismatchBase + j]); }   // 'n' = 4 spills into the base before
+        kmer &= (1u << (2 * MATCH_BASES_MIN)) - 1;
+        const int pos = kmerPositions[kmer];
+        if (pos < 0) return false;
+        const unsigned mismatchBaseOffset = unsigned(mismatchBase - sequenceBegin);
+        const unsigned adapterBasesBeforeSequence = mismatchBaseOffset < unsigned(pos) ? unsigned(pos) - mismatchBaseOffset : 0;
+        if (adapterBasesBeforeSequence && isUnbounded()) return false;                              // :74, :127-132
+        const long testBase = mismatchBase - (long(pos) - long(adapterBasesBeforeSequence));
+        const unsigned testSequenceLength = unsigned(sequenceEnd - testBase);
+        const unsigned adapterSequenceSize = unsigned(sequence.size());
+        const unsigned leftClippedAdapterLength = adapterSequenceSize - adapterBasesBeforeSequence;
+        const unsigned overlapLength = std::min(testSequenceLength, leftClippedAdapterLength);
+        if (overlapLength < leftClippedAdapterLength && isUnbounded() && reverse) return false;     // :81-88
+        if (!(overlapLength >= MATCH_BASES_MIN &&
+              !sequence.compare(adapterBasesBeforeSequence, overlapLength, &seq[testBase], overlapLength))) return false;   // :91-92
+        if (reverse)                                                                                // :99-105
+        {
+            first = isUnbounded() ? sequenceBegin : testBase - long(std::min<unsigned>(unsigned(testBase - sequenceBegin), clipLength - adapterSequenceSize));
+            second = testBase + overlapLength;
+        }
+        else                                                                                        // :107-111
+        {
+            first = testBase;
+            second = isUnbounded() ? sequenceEnd : testBase + long(std::min(overlapLength, clipLength));
+        }
+        return first != second;
+    }
+};
+
+/// the adapter list of oracle_set_adapters (process-wide, like the reference build of the checker keeps it)
+std::vector<AdapterPort> &portAdapters()
+{
+    static std::vector<AdapterPort> adapters;
+    return adapters;
+}
+
+/* -------------------------------------------------------------------------------------------------
+ * matchSelector::FragmentSequencingAdapterClipper  lib/alignment/matchSelector/FragmentSequencingAdapterClipper.cpp:40-277
+ * ------------------------------------------------------------------------------------------------- */
+struct AdapterClipperPort
+{
+    struct Range { bool initialized, empty; long begin, end; Range() : initialized(false), empty(true), begin(0), end(0) {} } strandRange[2];
+    const std::vector<AdapterPort> &adapters;
+    AdapterClipperPort() : adapters(portAdapters()) {}
+
+    static unsigned countMatches(const std::vector<char> &seq, long b, long e, const Contig &contig, long referenceBegin)   // Alignment.hh:89-104
+    {
+        unsigned ret = 0;
+        for (long i = b; i < e; ++i) ret += isMatch(seq[i], contig.bases[referenceBegin + (i - b)]);
+        return ret;
+    }
+    /// percentMismatches (:62-71); like the CUDA path, reference positions outside the contig count as mismatches where the
+    /// reference would read past its vector (:190-216)
+    static unsigned percentMismatches(const std::vector<char> &seq, long b, long e, const Contig &contig, long referenceBegin)
+    {
+        unsigned mismatches = 0;
+        for (long i = b; i < e; ++i)
+        {
+            const long r = referenceBegin + (i - b);
+            mismatches += !(r >= 0 && r < long(contig.length) && isMatch(seq[i], contig.bases[r]));
+        }
+        return mismatches * 100 / unsigned(e - b);
+    }
+
+    void checkInitStrand(const Fragment &f, const Contig &contig)                                   // :102-147
+    {
+        Range &range = strandRange[f.reverse];
+        if (range.initialized) return;
+        const std::vector<char> &sequence = f.read().seq[f.reverse];
+        long sequenceBegin = 0, sequenceEnd = long(sequence.size());
+        // the clipper's own clipReference (:40-59)
+        const long referenceLeft = long(contig.length) - f.position;
+        if (referenceLeft < sequenceEnd - sequenceBegin) sequenceEnd = sequenceBegin + referenceLeft;
+        long newFragmentPos = f.position;
+        if (0 > f.position) { sequenceBegin -= f.position; newFragmentPos = 0; }
+        range.begin = sequenceEnd; range.end = sequenceBegin;                                       // :124-125
+        for (const AdapterPort &adapter : adapters)
+        {
+            if (!adapter.isStrandCompatible(f.reverse)) continue;
+            // findSequencingAdapter (:79-100) from the end of what has been found so far
+            const long searchBegin = range.end;
+            long reference = newFragmentPos + (searchBegin - sequenceBegin);
+            for (long current = searchBegin; current < sequenceEnd; ++current, ++reference)
+            {
+                if (!isMatch(sequence[current], contig.bases[reference]))
+                {
+                    long first, second;
+                    if (adapter.getMatchRange(sequence, searchBegin, sequenceEnd, current, first, second))
+                    {
+                        range.begin = std::min(first, range.begin);                                 // :138-139
+                        range.end = std::max(second, range.end);
+                        break;
+                    }
+                }
+            }
+        }
+        range.initialized = true;
+        range.empty = sequenceBegin == range.end;                                                   // :145
+    }
+
+    /// clip + decideWhichSideToClip (:149-277); begin/end index the strand sequence
+    void clip(const Contig &contig, Fragment &f, long &begin, long &end) const
+    {
+        const Range &range = strandRange[f.reverse];
+        if (range.empty) return;
+        const std::vector<char> &sequence = f.read().seq[f.reverse];
+        const long contigPosition = f.position;
+        const unsigned backwardsClipped = unsigned(range.begin - begin), forwardsClipped = unsigned(end - range.end);   // :158-159
+        bool clipBackwards = backwardsClipped < forwardsClipped;
+        const unsigned sequenceLength = unsigned(end - begin);
+        bool doClip = true;
+        if (backwardsClipped && forwardsClipped && std::abs(int(backwardsClipped - forwardsClipped)) < 9)             // :166
+        {
+            if (contigPosition >= 0 && contig.length >= uint64_t(contigPosition + sequenceLength))                     // :169
+            {
+                const long referenceEnd = contigPosition + sequenceLength;
+                const unsigned backwardsMatches = countMatches(sequence, begin, range.begin, contig, contigPosition);
+                const unsigned forwardsMatches = countMatches(sequence, range.end, end, contig, referenceEnd - forwardsClipped);
+                clipBackwards = backwardsMatches < forwardsMatches || (backwardsMatches == forwardsMatches && backwardsClipped < forwardsClipped);
+            }
+        }
+        else if (!backwardsClipped || !forwardsClipped)                                                                // :190-216
+        {
+            if (clipBackwards && !backwardsClipped)
+                doClip = percentMismatches(sequence, begin, range.end, contig, contigPosition) > 40;                   // TOO_GOOD_READ_MISMATCH_PERCENT
+            else if (!clipBackwards && !forwardsClipped)
+            {
+                const long basesClipped = end - range.begin;
+                doClip = percentMismatches(sequence, range.begin, end, contig, contigPosition + sequenceLength - basesClipped) > 40;
+            }
+        }
+        if (!doClip) return;
+        if (clipBackwards) { f.incrementClipLeft(range.end - begin); begin = range.end; }                             // :240-249
+        else { f.incrementClipRight(end - range.begin); end = range.begin; }                                           // :252-261
+    }
+};
+
+/* -------------------------------------------------------------------------------------------------
+ * GappedAligner::makesSenseToGapAlign (--avoid-smith-waterman)  lib/alignment/fragmentBuilder/GappedAligner.cpp:88-165
+ * The 7-mer table of the query is cached per strand under (cluster, read) and NOT rebuilt while that key stays, whatever
+ * the query range of the later calls is (:95-121).
+ * ------------------------------------------------------------------------------------------------- */
+struct GapHeuristicPort
+{
+    static const unsigned KMER = 7, SUFFICIENT_HITS = 8;                                            // GappedAligner.hh:59,75
+    static const unsigned short UNINITIALIZED = 0xFFFF, REPEAT = 0xFFFE;                            // :70-71
+    unsigned hashedCluster[2], hashedRead[2];
+    std::vector<unsigned short> queryKmerOffsets;
+    std::vector<unsigned char> trackedOffsets;
+    GapHeuristicPort() : queryKmerOffsets(1u << (2 * KMER), UNINITIALIZED) { hashedCluster[0] = hashedCluster[1] = hashedRead[0] = hashedRead[1] = -1U; }
+
+    /// oligo::KmerGenerator (KmerGenerator.hpp:38-124): the k-mers without a non-ACGT base, in order, with their positions
+    template <class F> static void forEachKmer(const char *begin, const char *end, F f)
+    {
+        unsigned kmer = 0, valid = 0;
+        for (const char *p = begin; p != end; ++p)
+        {
+            const unsigned v = AdapterPort::translate(*p);
+            if (v > 3) { valid = 0; kmer = 0; continue; }
+            kmer = ((kmer << 2) | v) & ((1u << (2 * KMER)) - 1);
+            if (++valid >= KMER) f(kmer, long(p - begin) - long(KMER) + 1);
+        }
+    }
+
+    bool makesSense(unsigned cluster, unsigned read, bool reverse, const char *queryBegin, const char *queryEnd,
+                    const char *databaseBegin, const char *databaseEnd)
+    {
+        if (hashedCluster[reverse] != cluster || hashedRead[reverse] != read)                       // :95-121 (the tile is constant here)
+        {
+            std::fill(queryKmerOffsets.begin(), queryKmerOffsets.end(), UNINITIALIZED);
+            forEachKmer(queryBegin, queryEnd, [&](unsigned kmer, long position) {
+                queryKmerOffsets[kmer] = queryKmerOffsets[kmer] == UNINITIALIZED ? (unsigned short)position : REPEAT;
+            });
+            hashedCluster[reverse] = cluster; hashedRead[reverse] = read;
+        }
+        const int queryLength = int(queryEnd - queryBegin);
+        trackedOffsets.assign(size_t(queryLength) * 2 + size_t(databaseEnd - databaseBegin) + 65536, 0);   // QUERY_LENGTH_MAX counters (:124)
+        int lastConfirmedOffset = INT_MAX;
+        bool ret = false, done = false;
+        forEachKmer(databaseBegin, databaseEnd, [&](unsigned kmer, long databaseOffset) {
+            if (done) return;
+            const int queryOffset = queryKmerOffsets[kmer];
+            if (queryOffset == REPEAT || queryOffset == UNINITIALIZED) return;                      // :136-141
+            const int firstBaseOffset = int(databaseOffset) - queryOffset + queryLength;            // :144
+            if (firstBaseOffset < 0) return;                                                        // (the reference would index before its array)
+            if (++trackedOffsets[firstBaseOffset] == SUFFICIENT_HITS)                               // :147-157
+            {
+                if (lastConfirmedOffset == INT_MAX) lastConfirmedOffset = firstBaseOffset;
+                else if (lastConfirmedOffset != firstBaseOffset) { ret = true; done = true; }
+            }
+        });
+        return ret;
+    }
+};
+
+/// UngappedAligner::alignUngapped  lib/alignment/fragmentBuilder/UngappedAligner.cpp:39-92
 unsigned alignUngapped(const Scores &s, const isaac_ext_reads_t &rm, const Contig &contig, Fragment &f,
-                       std::vector<uint32_t> &cigarBuffer)
+                       std::vector<uint32_t> &cigarBuffer, const AdapterClipperPort &clipper)
 {
     const unsigned cigarOffset = cigarBuffer.size();
     f.resetAlignment(cigarBuffer);
     f.resetClipping();
     const Read &read = f.read();
     long begin = 0, end = read.length();
+    clipper.clip(contig, f, begin, end);                                                            // :59
     clipReadMasking(read, f, begin, end);
     clipReference(contig.length, f, begin, end);
     if (begin) cigarBuffer.push_back(cigarWord(begin, ISAAC_EXT_CIGAR_SOFT_CLIP));
@@ -383,9 +615,9 @@ void getFlanks(long strandPosition, unsigned readLength, uint64_t referenceSize,
     else { left = strandPosition; right = w - left - 1; }
 }
 
-/// GappedAligner::alignGapped  lib/alignment/fragmentBuilder/GappedAligner.cpp:167-249 (no adapters, avoidSW off)
+/// GappedAligner::alignGapped  lib/alignment/fragmentBuilder/GappedAligner.cpp:167-249; heuristic = 0: --avoid-smith-waterman off
 unsigned alignGapped(const Scores &s, BandedSw &sw, const isaac_ext_reads_t &rm, const Contig &contig, Fragment &f,
-                     std::vector<uint32_t> &cigarBuffer)
+                     std::vector<uint32_t> &cigarBuffer, const AdapterClipperPort &clipper, GapHeuristicPort *heuristic)
 {
     const unsigned cigarOffset = cigarBuffer.size();
     f.resetAlignment(cigarBuffer);
@@ -393,6 +625,7 @@ unsigned alignGapped(const Scores &s, BandedSw &sw, const isaac_ext_reads_t &rm,
     const Read &read = f.read();
     const std::vector<char> &sequence = read.seq[f.reverse];
     long begin = 0, end = read.length();
+    clipper.clip(contig, f, begin, end);                                                            // :186
     clipReadMasking(read, f, begin, end);
     clipReference(contig.length, f, begin, end);
     if (begin) cigarBuffer.push_back(cigarWord(begin, ISAAC_EXT_CIGAR_SOFT_CLIP));
@@ -401,6 +634,10 @@ unsigned alignGapped(const Scores &s, BandedSw &sw, const isaac_ext_reads_t &rm,
     if (long(contig.length) < long(sequenceLength) + strandPosition + long(BAND)) return 0;   // :204-208
     unsigned left, right;
     getFlanks(strandPosition, sequenceLength, contig.length, left, right);
+    if (heuristic && !heuristic->makesSense(f.cluster->id, f.readIndex, f.reverse, &sequence[0] + begin, &sequence[0] + end,
+                                            contig.bases + strandPosition - left,
+                                            contig.bases + strandPosition - left + (left + sequenceLength + right)))   // :218-226
+        return 0;
     strandPosition += sw.align(&sequence[begin], sequenceLength, contig.bases + strandPosition - left, cigarBuffer);
     if (long(read.length()) - end) cigarBuffer.push_back(cigarWord(read.length() - end, ISAAC_EXT_CIGAR_SOFT_CLIP));
     strandPosition -= left;
@@ -456,6 +693,7 @@ int extendBatch(bool gapped, const oracle_genome_t *genome, const isaac_ext_read
     bool overflow = false;
     parallelFor(n, threads, [&](uint32_t b, uint32_t e) {
         BandedSw sw(cfg->gapMatchScore, cfg->gapMismatchScore, -cfg->gapOpenScore, -cfg->gapExtendScore, totalReadLength);   // GappedAligner.cpp:41-42
+        GapHeuristicPort heuristic;
         Cluster cluster; uint32_t loaded = -1U;
         std::vector<uint32_t> cigar;
         for (uint32_t i = b; i < e; ++i)
@@ -467,13 +705,15 @@ int extendBatch(bool gapped, const oracle_genome_t *genome, const isaac_ext_read
             cigar.clear();
             Fragment f(&cluster, &cigar, readIndex);
             f.reverse = (c.contigStrand & 1); f.contigId = (c.contigStrand >> 1); f.position = c.position;
-            unsigned matchCount = alignUngapped(scores, *reads, contig, f, cigar);
+            AdapterClipperPort clipper;                                            // one clipper per candidate (testSequencingAdapter.cpp:159-182)
+            clipper.checkInitStrand(f, contig);
+            unsigned matchCount = alignUngapped(scores, *reads, contig, f, cigar, clipper);
             // the reference only gap-aligns fragments whose ungapped alignment kept at least one match
             // (FragmentBuilder.cpp:179 drops the others first, ShadowAligner.cpp:223-226 never lists them)
             if (gapped && matchCount)
             {
                 Fragment tmp = f;                                                  // FragmentBuilder.cpp:199-200
-                matchCount = alignGapped(scores, sw, *reads, contig, tmp, cigar);
+                matchCount = alignGapped(scores, sw, *reads, contig, tmp, cigar, clipper, cfg->avoidSmithWaterman ? &heuristic : 0);
                 f = tmp;
             }
             if (f.cigarLength > cigarStride) { overflow = true; f.cigarLength = 0; }
@@ -487,6 +727,14 @@ int extendBatch(bool gapped, const oracle_genome_t *genome, const isaac_ext_read
 } // namespace
 
 extern "C" const char *oracle_kind(void) { return "port"; }
+
+extern "C" int oracle_set_adapters(uint32_t count, const isaac_ext_adapter_t *adapters)
+{
+    std::vector<AdapterPort> &list = portAdapters();
+    list.clear();
+    for (uint32_t a = 0; a < count; ++a) list.push_back(AdapterPort(adapters[a].sequence, adapters[a].reverse != 0, adapters[a].clipLength));
+    return ISAAC_EXT_OK;
+}
 
 extern "C" int oracle_banded_sw_batch(uint32_t n, const char *queries, const uint64_t *queryOffsets,
                                       const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
