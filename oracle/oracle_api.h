@@ -82,8 +82,7 @@ int oracle_template_stats(const oracle_genome_t *genome, const isaac_ext_reads_t
                           const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
                           const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t threads);
 
-/* MatchSelector::determineTemplateLength for the tile (MatchSelector.cpp:188-249), see isaac_ext_determine_template_length.
- * Only the reference build exports it. */
+/* MatchSelector::determineTemplateLength for the tile (MatchSelector.cpp:188-249), see isaac_ext_determine_template_length. */
 int oracle_determine_template_length(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,
                                      const isaac_ext_config_t *config, const isaac_ext_build_batch_t *batch,
                                      const uint8_t *pf, int32_t mateDriftRange, isaac_ext_tls_t *tlsOut, uint32_t *stableOut);

@@ -84,3 +84,23 @@ def test_tile_calls_port_matches_reference(kind, avoid, L):
     r, p = both(lambda chk: oracle_lib.rescue_shadows(chk, g, reads, cfg, tls, req), adapters)
     assert_flat_equal(r, p, "rescue port vs reference (adapters %s, avoid %s)" % (kind, avoid))
     assert r.flags.mean() > 0.5
+
+
+@needs_ref
+@pytest.mark.parametrize("n_pairs,drift,with_pf,fixed_insert", [(3000, -1, True, False), (26000, 40, False, False), (30000, -1, False, True)])
+def test_template_length_port_matches_reference(n_pairs, drift, with_pf, fixed_insert):
+    """MatchSelector::determineTemplateLength + TemplateLengthDistribution: tiles that end before stability (finalize), a mate
+    drift range, filtered clusters, and a single-insert-size library that turns stable at the second update"""
+    import ctypes
+    from test_gpu_tls import swap_reads, words
+    extra = dict(insert=(350, 0, 350, 350), indel_rate=0.0) if fixed_insert else dict(indel_rate=2e-3)
+    genome, sim, reads, mb = build_workload(n_pairs=n_pairs, L=100, seed=800 + n_pairs % 89, genome_bases=2_000_000, **extra)
+    reads, mb = swap_reads(sim, reads, mb)
+    cfg = Config.default(BWA_SCORES, max_read_length=200)
+    pf = (np.random.default_rng(6).random(n_pairs) < 0.9).astype(np.uint8) if with_pf else None
+    g = oracle_lib.GenomeHolder(genome)
+    r, r_stable = oracle_lib.determine_template_length(REF, g, reads, cfg, mb, pf, drift)
+    p, p_stable = oracle_lib.determine_template_length(PORT, g, reads, cfg, mb, pf, drift)
+    assert words(r) == words(p) and r_stable == p_stable, (words(r), words(p), r_stable, p_stable)
+    assert r_stable or not fixed_insert
+    assert sorted([r.bestModel[0], r.bestModel[1]]) == [1, 6]
