@@ -29,3 +29,14 @@ def test_sort_replay_compiles_for_the_device():
                 '}\n')
     subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--extended-lambda",
                            "-c", src, "-o", os.path.join(ROOT, "build", "sort_replay_device.o")])
+
+
+def test_consolidate_replay_matches_the_host_consolidate():
+    """consolidate_device.cuh (the replay under consolidateDuplicateFragments) against the std::sort-based function the product's
+    host phases use, on 300 k random candidate lists; host code of an nvcc-compiled binary, no GPU involved"""
+    exe = os.path.join(ROOT, "build", "test_consolidate_replay")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-cudart", "shared", os.path.join(ROOT, "tests", "cpp", "test_consolidate_replay.cu"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
