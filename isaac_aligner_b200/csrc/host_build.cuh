@@ -30,7 +30,6 @@ struct PipelineState
     PinnedBuffer<IndelTask> hTasks;
     PinnedBuffer<IndelResult> hIndel;
     PinnedBuffer<ShadowTask> hShadowTasks;
-    PinnedBuffer<uint32_t> hTaskBegin, hTaskCount;
     // device
     DeviceBuffer<isaac_ext_candidate_t> dCand;
     DeviceBuffer<isaac_ext_fragment_t> dFrag;
@@ -69,7 +68,7 @@ struct PipelineState
     void release()
     {
         hCand1.release(); hCand3.release(); hFrag1.release(); hFrag3.release(); hCig1.release(); hCig3.release();
-        hTasks.release(); hIndel.release(); hShadowTasks.release(); hTaskBegin.release(); hTaskCount.release();
+        hTasks.release(); hIndel.release(); hShadowTasks.release();
         hAdapterFirst.release(); dAdapterFirst.release(); hSlot.release(); dSlot.release();
         dKept.release(); dAdoptedBy.release(); dCounts.release(); dBegins.release(); dSlot3.release(); dSources.release(); dCig3.release();
         dOutCigars.release(); dListState.release(); dRescued.release(); dScanTemp.release(); dCand3.release(); dFrag3.release();

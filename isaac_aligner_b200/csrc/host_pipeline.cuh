@@ -8,9 +8,8 @@
 //            P2 consolidate, pair adjacent candidates                   -> simpleIndelKernel
 //            P3 apply patches, consolidate, pick mismatchCount > 5      -> gappedKernel2
 //            P4 acceptance rule, consolidate, flatten
-//   rescue:  R1 rescue windows from the template length statistics      -> shadowCandidatesKernel, K1 ungappedKernel
-//            R2 best shadow, pick neighbours for the gapped aligner     -> gappedKernel2
-//            R3 acceptance rule, best first, flatten
+//   rescue:  R1 rescue windows from the template length statistics      -> shadowCandidates*Kernel, K1 ungappedKernel
+//            (everything behind R1 is on the device: the list bookkeeping R2 / R3 and the flat result are kernels_rescue.cuh)
 #pragma once
 #include <algorithm>
 #include <atomic>

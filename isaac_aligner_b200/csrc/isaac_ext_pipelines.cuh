@@ -460,7 +460,7 @@ static int rescueShadowsInto(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
     if (n && stats.coherent())                                                   // :164-168
     {
         // ---- R1: rescue windows (calculateShadowRescueRange :119-149, rescueShadow :170-198)
-        CK(ps.hShadowTasks.reserve(n)); CK(ps.hTaskBegin.reserve(n)); CK(ps.hTaskCount.reserve(n));
+        CK(ps.hShadowTasks.reserve(n));
         std::atomic<int> bad(0);
         std::atomic<uint32_t> largeWindows(0);
         parallelRanges(T, n, [&](unsigned, size_t b, size_t e) {

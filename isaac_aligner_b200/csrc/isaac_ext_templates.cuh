@@ -745,7 +745,6 @@ struct TemplateState
 {
     HostBuffer<isaac_ext_fragment_t> buildFragments;  HostBuffer<uint64_t> buildBegin;  HostBuffer<uint32_t> buildCigars;
     std::vector<uint8_t> buildFlags;
-    std::vector<isaac_ext_rescue_request_t> requests;
     std::vector<uint64_t> clusterRequestBegin;
     HostBuffer<isaac_ext_template_t> templates;  HostBuffer<isaac_ext_fragment_t> fragments;  HostBuffer<uint32_t> cigars;
     // end clippers
