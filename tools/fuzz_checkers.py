@@ -1,6 +1,6 @@
 """Differential campaign between the two CPU checkers (the reference's own code in oracle/_ref and the scalar restatement):
 random seeds, read lengths, score presets, adapter sets, --avoid-smith-waterman, quality masking.  Development aid, CPU only:
-  python tools/fuzz_checkers.py [rounds]"""
+  python tools/fuzz_checkers.py [rounds [campaign seed]]"""
 import os
 import sys
 
@@ -22,9 +22,9 @@ SETS = [((), None, True), (STANDARD_ADAPTERS, ["AGATCGGAAGAGC"], True), (NEXTERA
         (NEXTERA_MATEPAIR_ADAPTERS, ["CTGTCTCTTATACACATCT", "AGATGTGTATAAGAGACAG", "CTGTCTCTTATACACATCTAGATGTGTATAAGAGACAG"], False)]
 
 
-def main(rounds):
+def main(rounds, campaign=20261017):
     ref, port = oracle_lib.reference(), oracle_lib.port()
-    rng = np.random.default_rng(20261017)
+    rng = np.random.default_rng(campaign)
     for k in range(rounds):
         seed = int(rng.integers(1, 1 << 30))
         L = int(rng.choice([36, 50, 75, 100, 150, 250]))
@@ -33,7 +33,11 @@ def main(rounds):
         avoid = bool(rng.random() < 0.4)
         indel = float(rng.choice([5e-4, 4e-3, 1e-2]))
         cfg = Config.default(scores, max_read_length=2 * L, avoid_smith_waterman=avoid)
-        what = "seed %d L %d scores %s adapters %d avoid %s indel %g" % (seed, L, scores[0], len(adapters), avoid, indel)
+        cfg.repeatThreshold = int(rng.choice([2, 10, 10, 100]))
+        cfg.gappedMismatchesMax = int(rng.choice([3, 5, 5, 8]))
+        cfg.semialignedGapLimit = int(rng.choice([0, 100, 100, 20000]))
+        what = "seed %d L %d scores %s adapters %d avoid %s indel %g repeat %d gmm %d sgl %d" % (
+            seed, L, scores[0], len(adapters), avoid, indel, cfg.repeatThreshold, cfg.gappedMismatchesMax, cfg.semialignedGapLimit)
         genome, sim, reads, mb = build_workload(n_pairs=500, L=L, seed=seed, indel_rate=indel)
         if inserted and L >= 75:
             synth.insert_adapters(sim, inserted, fraction=0.4, seed=seed + 5, read_through=read_through, min_keep=min(40, L // 2))
@@ -59,4 +63,4 @@ def main(rounds):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 20)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 20, int(sys.argv[2]) if len(sys.argv) > 2 else 20261017)
