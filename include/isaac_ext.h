@@ -235,6 +235,10 @@ typedef struct isaac_ext_template_result {
 } isaac_ext_template_result_t;
 
 /* ---- life cycle ----------------------------------------------------------------------------- */
+/* One context per GPU stands for what MatchSelector keeps per compute thread: a TemplateBuilder with its FragmentBuilder and
+ * ShadowAligner (MatchSelector.cpp:143-163; constructor arguments FragmentBuilder.hh:49-60, ShadowAligner.hh:52-59).
+ * isaac_ext_create fails with ISAAC_EXT_E_INVALID_ARG where the BandedSmithWaterman constructor throws
+ * common::InvalidParameterException (BandedSmithWaterman.cpp:47-53). */
 int  isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx **ctx);
 void isaac_ext_destroy(isaac_ext_ctx *ctx);
 const char *isaac_ext_last_error(const isaac_ext_ctx *ctx);   /* ctx may be NULL: last create error */
@@ -320,7 +324,8 @@ int isaac_ext_gapped_batch(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candi
                            uint32_t cigarStride, isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut,
                            uint64_t *mismatchMaskOut);
 
-/* End-to-end variants of the two calls above for large batches: same semantics, but the CIGARs come back as a DENSE pool
+/* End-to-end variants of the two calls above (UngappedAligner.cpp:39-92, GappedAligner.cpp:167-249) for large batches: same
+ * semantics, but the CIGARs come back as a DENSE pool
  * (fragment.cigarOffset indexes cigarPoolOut; *cigarWordsOut = words used) and the batch is processed in chunks whose
  * host-to-device copy, kernels and device-to-host copies overlap.  Pass page-locked host buffers for full copy speed.
  * ISAAC_EXT_E_CAPACITY if cigarPoolCapacity (in words) is too small; *cigarWordsOut then holds the required size. */
@@ -339,9 +344,10 @@ int isaac_ext_extend_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_e
                                    uint64_t *ungappedWordsOut, isaac_ext_fragment_t *gappedOut, uint32_t *gappedPoolOut,
                                    uint64_t gappedPoolCapacity, uint64_t *gappedWordsOut);
 
-/* Device-resident variants used to time the kernels alone: the candidate and result arrays are device
- * pointers, the launch goes to 'cudaStream' (a cudaStream_t passed as void*) and returns without
- * synchronising.  Same semantics as the host variants above. */
+/* Device-resident variants of isaac_ext_ungapped_batch / isaac_ext_gapped_batch (UngappedAligner::alignUngapped,
+ * UngappedAligner.cpp:39-92; GappedAligner::alignGapped, GappedAligner.cpp:167-249) used to time the kernels alone: the
+ * candidate and result arrays are device pointers, the launch goes to 'cudaStream' (a cudaStream_t passed as void*) and returns
+ * without synchronising.  Same semantics as the host variants above. */
 int isaac_ext_ungapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates,
                                     void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut,
                                     void *cudaStream);
