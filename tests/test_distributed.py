@@ -106,3 +106,51 @@ def test_two_rank_tls_broadcast(tmp_path):
     mp.spawn(_tls_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     a, b = (np.load(os.path.join(str(tmp_path), "tls%d.npy" % r)) for r in range(2))
     assert np.array_equal(a, b) and list(a) == [211, 498, 347, 33, 36, 2, 5, -1]
+
+
+def _template_stats_rank_main(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    from common_build import build_workload
+    from isaac_aligner_b200 import distributed
+    from isaac_aligner_b200.batch import MatchBatch, TemplateOptions, Tls
+    from isaac_aligner_b200.types import BWA_SCORES, Config, ReadSet
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    chk = oracle_lib.reference()
+    genome, sim, reads, mb = build_workload(n_pairs=1200, L=100, seed=33, masked=False)
+    cfg = Config.default(BWA_SCORES, max_read_length=200)
+    g = oracle_lib.GenomeHolder(genome)
+    tls, options = Tls.make(), TemplateOptions.make()
+    # every rank takes its contiguous cluster range of the tile (the statistics do not depend on how the tile is cut)
+    b, e = distributed.cluster_range_of_rank(reads.cluster_count, rank, world)
+    sub_reads = ReadSet(reads.bcl[b:e], reads.read_lengths)
+    begin = mb.begin[b:e + 1] - mb.begin[b]
+    sub_mb = MatchBatch(mb.matches[int(mb.begin[b]):int(mb.begin[e])], begin, mb.seeds)
+    mine = oracle_lib.template_stats(chk, g, sub_reads, cfg, sub_mb, tls, options)
+    t = torch.from_numpy(mine.view(np.int64).copy())
+    distributed.allreduce_stats(t)
+    if rank == 0:
+        whole = oracle_lib.template_stats(chk, g, reads, cfg, mb, tls, options)
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([np.array_equal(t.numpy().view(np.uint64), whole), int(whole[0][3]), int(mine[0][3])]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_template_stats_allreduce(tmp_path):
+    """the MatchSelectorStats summary of a tile = the sum of the summaries of its parts: two gloo ranks, each with its cluster
+    range, one all-reduce (the CPU checker stands in for the kernel as the producer of the per-rank vectors)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    chk = oracle_lib.reference()
+    if chk is None or not hasattr(chk.lib, "oracle_template_stats"):
+        pytest.skip("needs the reference build of the checker")
+    import torch.multiprocessing as mp
+    port = 30700 + os.getpid() % 500
+    mp.spawn(_template_stats_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok, total, local = np.load(os.path.join(str(tmp_path), "ok.npy"))
+    assert ok == 1 and total == 1200 and local == 600
