@@ -379,6 +379,50 @@ int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const void *dFra
 int isaac_ext_template_stats(isaac_ext_ctx *ctx, const struct isaac_ext_build_batch *batch, const struct isaac_ext_tls *tls,
                              const struct isaac_ext_template_result *templates, const uint8_t *pf, uint64_t *statsOut);
 
+/* ---- io::FragmentHeader bin records ------------------------------------------------------------------ */
+
+/* What matchSelector::FragmentCollector::add reads beyond the template itself (FragmentCollector.cpp:42-77): the Cluster
+ * fields MatchSelector::processMatchList initialises (MatchSelector.cpp:301-302) and the BinIndexMap of the run
+ * (BinIndexMap.hh:45-107, handed over as its per-contig vectors). */
+typedef struct isaac_ext_pack_options {
+    uint64_t tile;                    /* Cluster::getTile of the resident tile                                            */
+    uint32_t barcodeIdx;              /* the barcode index FragmentCollector::add is called with                          */
+    uint32_t keepUnaligned;           /* --keep-unaligned: store the templates that did not build too
+                                         (MatchSelector.cpp:311-314,331,355-358); else only templates with 'built'       */
+    const uint8_t  *pf;               /* Cluster::getPf per cluster, or NULL = every cluster passes                       */
+    const int32_t  *xy;               /* Cluster::getXy: x, y per cluster, or NULL = unset (POSITION_NOT_SET)             */
+    const uint64_t *barcodeSequence;  /* Cluster::getBarcodeSequence per cluster, or NULL = 0                             */
+    uint32_t distributionBinSize;     /* MatchDistribution::getBinSize; 0 = no bin map, mateStorageBin_ stays 0           */
+    uint32_t contigCount;             /* contigs the bin map covers                                                       */
+    const uint64_t *contigBinBegin;   /* contigCount + 1 offsets into binIndex: BinIndexMap::at(contigId + 1)             */
+    const uint32_t *binIndex;
+} isaac_ext_pack_options_t;
+
+/* matchSelector::FragmentBuffer after the tile (FragmentCollector.hh:44-310), owned by the context, valid until its next
+ * isaac_ext_pack_fragments.  records = data_: clusterCount fixed-size records, the fragment of (cluster, readIndex) at
+ * cluster * recordLength + readOffset[readIndex] as io::FragmentHeader (headerLength = sizeof = 112 bytes; the padding bytes 42..47,
+ * 108..111 and the six spare bits of flags_ are zero here, unspecified in the reference) followed by readLength BCL bytes
+ * (reverse-complemented for reverse fragments) and cigarLength CIGAR words; everything behind is zero, like the reference's
+ * freshly resized buffer.  fStrandPos / initialized = index_: IndexRecord::fStrandPos_ (ReferencePosition::getValue) and
+ * IndexRecord::initialized() per cluster * readCount + readIndex. */
+typedef struct isaac_ext_pack_result {
+    const uint8_t  *records;
+    const uint64_t *fStrandPos;
+    const uint8_t  *initialized;
+    uint32_t recordLength;            /* FragmentBuffer::getRecordLength (FragmentCollector.hh:283-289)                   */
+    uint32_t readOffset[2];           /* FragmentBuffer::getReadOffsets (:295-308)                                        */
+    uint32_t headerLength;
+    uint64_t storedFragments;         /* records initialised by this call                                                 */
+} isaac_ext_pack_result_t;
+
+/* FragmentCollector::add for every fragment of every template of the resident tile that MatchSelector::processMatchList stores
+ * (BufferingFragmentStorage::add, BufferingFragmentStorage.hh:64-70): io::FragmentHeader's paired / single-ended constructors
+ * (Fragment.hh:100-186: TLEN :209-237, mate anchor :489-497, duplicate rank :66-71), storeBclAndCigar
+ * (FragmentCollector.cpp:79-103).  templates = the result of isaac_ext_build_templates (host pointers); the BCL bytes are the
+ * resident read set's.  One kernel pass, one warp per cluster; the records travel back in one copy. */
+int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const struct isaac_ext_template_result *templates,
+                             const isaac_ext_pack_options_t *options, isaac_ext_pack_result_t *result);
+
 /* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
  * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
 int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);

@@ -116,3 +116,48 @@ class Templates:
     def cigar(self, i):
         f = self.fragments[i]
         return self.cigars[int(f["cigarOffset"]):int(f["cigarOffset"]) + int(f["cigarLength"])]
+
+
+class PackOptionsC(ctypes.Structure):
+    """isaac_ext_pack_options_t"""
+    _fields_ = [("tile", ctypes.c_uint64), ("barcodeIdx", ctypes.c_uint32), ("keepUnaligned", ctypes.c_uint32),
+                ("pf", ctypes.c_void_p), ("xy", ctypes.c_void_p), ("barcodeSequence", ctypes.c_void_p),
+                ("distributionBinSize", ctypes.c_uint32), ("contigCount", ctypes.c_uint32),
+                ("contigBinBegin", ctypes.c_void_p), ("binIndex", ctypes.c_void_p)]
+
+
+class PackOptions:
+    """What FragmentCollector::add reads beyond the template (isaac_ext_pack_options_t); keeps the arrays the struct points to.
+    bin_index: one uint32 array per contig = BinIndexMap::at(contigId + 1) (BinIndexMap.hh:45-107)."""
+
+    def __init__(self, tile=0, barcode_idx=0, keep_unaligned=False, pf=None, xy=None, barcode_sequence=None,
+                 distribution_bin_size=0, bin_index=None):
+        self.pf = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+        self.xy = None if xy is None else np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        self.barcode_sequence = None if barcode_sequence is None else np.ascontiguousarray(barcode_sequence, dtype=np.uint64)
+        self.bin_begin = self.bin_flat = None
+        contigs = 0
+        if distribution_bin_size:
+            contigs = len(bin_index)
+            self.bin_begin = np.zeros(contigs + 1, dtype=np.uint64)
+            self.bin_begin[1:] = np.cumsum([len(b) for b in bin_index])
+            self.bin_flat = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.uint32) for b in bin_index] + [np.zeros(1, np.uint32)]))
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        self.c = PackOptionsC(tile, barcode_idx, 1 if keep_unaligned else 0, ptr(self.pf), ptr(self.xy), ptr(self.barcode_sequence),
+                              distribution_bin_size, contigs, ptr(self.bin_begin), ptr(self.bin_flat))
+
+
+class PackResultC(ctypes.Structure):
+    """isaac_ext_pack_result_t"""
+    _fields_ = [("records", ctypes.c_void_p), ("fStrandPos", ctypes.c_void_p), ("initialized", ctypes.c_void_p),
+                ("recordLength", ctypes.c_uint32), ("readOffset", ctypes.c_uint32 * 2), ("headerLength", ctypes.c_uint32),
+                ("storedFragments", ctypes.c_uint64)]
+
+
+class PackedFragments:
+    """matchSelector::FragmentBuffer of a tile: records [clusters, recordLength] bytes, f_strand_pos / initialized
+    [clusters, readCount]; the record of (cluster, readIndex) starts at records[cluster, read_offset[readIndex]]"""
+
+    def __init__(self, records, f_strand_pos, initialized, record_length, read_offset, header_length, stored):
+        self.records, self.f_strand_pos, self.initialized = records, f_strand_pos, initialized
+        self.record_length, self.read_offset, self.header_length, self.stored = record_length, tuple(read_offset), header_length, stored

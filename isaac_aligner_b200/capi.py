@@ -35,7 +35,7 @@ EXPORTS = [
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
-    "isaac_ext_template_stats",
+    "isaac_ext_template_stats", "isaac_ext_pack_fragments",
 ]
 
 
@@ -227,6 +227,28 @@ class Context:
         self._check(_lib.isaac_ext_template_stats(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(res),
                                                   _p(pf_arr), _p(out)))
         return out
+
+    def pack_fragments(self, templates, options=None):
+        """matchSelector::FragmentCollector::add for every stored template of the resident tile (batch.Templates ->
+        batch.PackedFragments: the io::FragmentHeader bin records in FragmentBuffer layout)"""
+        from .batch import PackedFragments, PackOptions, PackResultC, TemplateResult
+        options = options if options is not None else PackOptions()
+        t = np.ascontiguousarray(templates.templates)
+        f = np.ascontiguousarray(templates.fragments)
+        cig = np.ascontiguousarray(templates.cigars, dtype=np.uint32)
+        tr = TemplateResult(t.ctypes.data, f.ctypes.data, cig.ctypes.data if cig.size else None, cig.size, 0)
+        res = PackResultC()
+        self._check(_lib.isaac_ext_pack_fragments(self._h, ctypes.byref(tr), ctypes.byref(options.c), ctypes.byref(res)))
+        n, rc = self.reads.cluster_count, self.reads.read_count
+
+        def arr(ptr, dtype, count):
+            buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype).copy()
+
+        return PackedFragments(arr(res.records, np.uint8, n * res.recordLength).reshape(n, res.recordLength),
+                               arr(res.fStrandPos, np.uint64, n * rc).reshape(n, rc), arr(res.initialized, np.uint8, n * rc).reshape(n, rc),
+                               int(res.recordLength), (int(res.readOffset[0]), int(res.readOffset[1])), int(res.headerLength),
+                               int(res.storedFragments))
 
     def tile_stats_device(self, n, d_fragments, d_stats, stream):
         """adds the K6 counters of n device-resident fragment records to the 64 u64 at d_stats"""

@@ -27,6 +27,8 @@ void releaseE2e(E2eState *state);
 struct TemplateState;                  // isaac_ext_templates.cuh
 } // namespace
 void releaseTemplates(TemplateState *state);
+struct PackState;                      // isaac_ext_pack.cuh
+void releasePack(PackState *state);
 
 struct isaac_ext_ctx
 {
@@ -51,6 +53,7 @@ struct isaac_ext_ctx
     PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows
     E2eState *e2e = nullptr;      // streams and chunk buffers of the *_batch_compact entry points
     TemplateState *templates = nullptr;   // buffers of isaac_ext_build_templates
+    PackState *pack = nullptr;            // buffers of isaac_ext_pack_fragments
     double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
@@ -255,6 +258,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->pipeline.release();
     releaseE2e(ctx->e2e);
     releaseTemplates(ctx->templates);
+    releasePack(ctx->pack);
     delete ctx;
 }
 
@@ -724,6 +728,7 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 #include "isaac_ext_e2e.cuh"
 #include "isaac_ext_templates.cuh"
 #include "isaac_ext_tls.cuh"
+#include "isaac_ext_pack.cuh"
 
 namespace
 {

@@ -91,6 +91,18 @@ int oracle_determine_template_length(const oracle_genome_t *genome, const isaac_
  * reference build exports it. */
 int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut);
 
+/* matchSelector::FragmentCollector::add for every stored template of a tile, see isaac_ext_pack_fragments: the records are
+ * written by the reference's own io::FragmentHeader constructors (Fragment.hh:100-186) from BamTemplate / FragmentMetadata /
+ * Cluster objects rebuilt from the flat template result.  barcodeBytes: barcodeLength BCL bytes per cluster in front of the
+ * reads (Cluster::getBarcodeSequence) or NULL.  headerMaskOut[headerLength]: 0xFF for the bytes of io::FragmentHeader that carry
+ * a member, 0 for padding.  layoutOut: recordLength, readOffset[0], readOffset[1], sizeof(io::FragmentHeader).  recordsOut may be
+ * NULL to query the layout only.  Only the reference build exports it. */
+int oracle_pack_fragments(const isaac_ext_reads_t *reads, const isaac_ext_template_t *templates,
+                          const isaac_ext_fragment_t *fragments, const uint32_t *cigars, uint64_t cigarWords,
+                          const isaac_ext_pack_options_t *options, const uint8_t *barcodeBytes, uint32_t barcodeLength,
+                          uint8_t *recordsOut, uint64_t *fStrandPosOut, uint8_t *initializedOut, uint8_t *headerMaskOut,
+                          uint32_t *layoutOut);
+
 #ifdef __cplusplus
 }
 #endif

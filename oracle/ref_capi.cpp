@@ -29,6 +29,8 @@
 #include "alignment/matchSelector/BamTemplateTileStatsAdapter.hh"
 #include "alignment/matchSelector/FragmentSequencingAdapterClipper.hh"
 #include "reference/Contig.hh"
+#include "oligo/Nucleotides.hh"
+#include "io/Fragment.hh"
 
 #include "oracle_api.h"
 
@@ -689,6 +691,122 @@ extern "C" int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint
             alignment::trimLowQualityEnds(holder.cluster, baseQualityCutoff);
             for (uint32_t r = 0; r < reads->readCount; ++r)
                 endCyclesMaskedOut[size_t(c) * reads->readCount + r] = uint16_t(holder.cluster[r].getEndCyclesMasked());
+        }
+        return ISAAC_EXT_OK;
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+}
+
+/* FragmentCollector::add for every stored template of a tile (FragmentCollector.cpp:42-77, storeBclAndCigar :79-103; the
+ * FragmentBuffer layout FragmentCollector.hh:283-308).  FragmentCollector.hh itself needs Boost.Filesystem (BinMetadata.hh), so
+ * its two short functions are followed here line by line; every byte of the header comes from the reference's own
+ * io::FragmentHeader constructors, getMaxTotalLength, BamTemplate and FragmentMetadata. */
+extern "C" int oracle_pack_fragments(const isaac_ext_reads_t *reads, const isaac_ext_template_t *templates,
+                                     const isaac_ext_fragment_t *fragments, const uint32_t *cigars, uint64_t cigarWords,
+                                     const isaac_ext_pack_options_t *options, const uint8_t *barcodeBytes, uint32_t barcodeLength,
+                                     uint8_t *recordsOut, uint64_t *fStrandPosOut, uint8_t *initializedOut, uint8_t *headerMaskOut,
+                                     uint32_t *layoutOut)
+{
+    try
+    {
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const uint32_t n = reads->clusterCount, rc = reads->readCount;
+        const unsigned len0 = reads->readLength[0], len1 = rc > 1 ? reads->readLength[1] : 0;
+        // FragmentBuffer::getRecordLength / getReadOffsets
+        const unsigned recordLength = io::FragmentHeader::getMaxTotalLength(len0) + (len1 ? io::FragmentHeader::getMaxTotalLength(len1) : 0);
+        const unsigned readOffsets[2] = {0, rc > 1 ? io::FragmentHeader::getMaxTotalLength(len0) : 0};
+        layoutOut[0] = recordLength; layoutOut[1] = readOffsets[0]; layoutOut[2] = readOffsets[1]; layoutOut[3] = sizeof(io::FragmentHeader);
+        if (headerMaskOut)
+        {
+            std::memset(headerMaskOut, 0, sizeof(io::FragmentHeader));
+#define ORACLE_MEMBER(m) std::memset(headerMaskOut + offsetof(io::FragmentHeader, m), 0xFF, sizeof(io::FragmentHeader::m))
+            ORACLE_MEMBER(bamTlen_); ORACLE_MEMBER(observedLength_); ORACLE_MEMBER(fStrandPosition_); ORACLE_MEMBER(lowClipped_);
+            ORACLE_MEMBER(highClipped_); ORACLE_MEMBER(alignmentScore_); ORACLE_MEMBER(templateAlignmentScore_);
+            ORACLE_MEMBER(mateFStrandPosition_); ORACLE_MEMBER(readLength_); ORACLE_MEMBER(cigarLength_); ORACLE_MEMBER(gapCount_);
+            ORACLE_MEMBER(editDistance_); ORACLE_MEMBER(tile_); ORACLE_MEMBER(barcode_); ORACLE_MEMBER(barcodeSequence_);
+            ORACLE_MEMBER(clusterId_); ORACLE_MEMBER(clusterX_); ORACLE_MEMBER(clusterY_); ORACLE_MEMBER(duplicateClusterRank_);
+            ORACLE_MEMBER(mateAnchor_); ORACLE_MEMBER(mateStorageBin_);
+#undef ORACLE_MEMBER
+            // the ten bit fields of Flags: found by setting each of them in an all-zero header
+            io::FragmentHeader probe;
+            std::memset(&probe, 0, sizeof(probe));
+            probe.flags_.paired_ = probe.flags_.unmapped_ = probe.flags_.mateUnmapped_ = probe.flags_.reverse_ = probe.flags_.mateReverse_ =
+                probe.flags_.firstRead_ = probe.flags_.secondRead_ = probe.flags_.failFilter_ = probe.flags_.properPair_ = probe.flags_.duplicate_ = true;
+            for (size_t i = 0; i < sizeof(probe); ++i) headerMaskOut[i] |= reinterpret_cast<const unsigned char *>(&probe)[i];
+        }
+        if (!recordsOut) return ISAAC_EXT_OK;
+        std::memset(recordsOut, 0, size_t(n) * recordLength);                       // FragmentBuffer::resize value-initialises data_
+        const unsigned maxReadLength = std::max(len0, len1);
+        std::vector<unsigned> cigarBuffer(cigars, cigars + cigarWords);
+        alignment::BamTemplate bam(cigarBuffer);
+        alignment::Cluster cluster(maxReadLength);
+        std::vector<char> bcl;
+        for (uint32_t c = 0; c < n; ++c)
+        {
+            for (uint32_t r = 0; r < rc; ++r) { fStrandPosOut[size_t(c) * rc + r] = 0; initializedOut[size_t(c) * rc + r] = 0; }
+            if (!(templates[c].built || options->keepUnaligned)) continue;
+            bcl.clear();
+            if (barcodeBytes) bcl.insert(bcl.end(), barcodeBytes + size_t(c) * barcodeLength, barcodeBytes + size_t(c + 1) * barcodeLength);
+            bcl.insert(bcl.end(), reads->bcl + size_t(c) * (len0 + len1), reads->bcl + size_t(c + 1) * (len0 + len1));
+            bcl.resize(bcl.size() + 64, 0);      // pack32BclBases reads 32 bytes whatever the read length
+            const alignment::ClusterXy xy = options->xy ? alignment::ClusterXy(options->xy[2 * size_t(c)], options->xy[2 * size_t(c) + 1])
+                                                        : alignment::ClusterXy();
+            cluster.init(rml, bcl.begin(), options->tile, c, xy, options->pf ? options->pf[c] != 0 : true, barcodeBytes ? barcodeLength : 0);
+            bam.initialize(rml, cluster);
+            bam.setAlignmentScore(templates[c].alignmentScore);
+            bam.setProperPair(templates[c].properPair);
+            for (uint32_t r = 0; r < rc; ++r)
+            {
+                const isaac_ext_fragment_t &f = fragments[size_t(c) * rc + r];
+                alignment::FragmentMetadata &m = bam.getFragmentMetadata(r);
+                m.contigId = f.contigId; m.position = f.position; m.observedLength = f.observedLength; m.reverse = f.reverse;
+                m.lowClipped = f.lowClipped; m.highClipped = f.highClipped; m.editDistance = f.editDistance; m.gapCount = f.gapCount;
+                m.mismatchCount = f.mismatchCount; m.cigarOffset = f.cigarOffset; m.cigarLength = f.cigarLength;
+                m.alignmentScore = templates[c].fragmentAlignmentScore[r];
+            }
+            for (unsigned k = 0; k < bam.getFragmentCount(); ++k)                     // BufferingFragmentStorage::add
+            {
+                // FragmentCollector::add
+                const alignment::FragmentMetadata &fragment = bam.getFragmentMetadata(k);
+                char *dataBytes = reinterpret_cast<char *>(recordsOut) + size_t(c) * recordLength + readOffsets[fragment.getReadIndex()];
+                const size_t slot = size_t(c) * rc + fragment.getReadIndex();
+                initializedOut[slot] = 1;
+                fStrandPosOut[slot] = fragment.getFStrandReferencePosition().getValue();
+                // storeBclAndCigar
+                char *variableData = dataBytes + sizeof(io::FragmentHeader);
+                std::vector<char>::const_iterator bclData = fragment.getBclData();
+                if (fragment.isReverse())
+                    variableData = std::transform(std::reverse_iterator<std::vector<char>::const_iterator>(bclData + fragment.getReadLength()),
+                                                  std::reverse_iterator<std::vector<char>::const_iterator>(bclData), variableData, oligo::getReverseBcl);
+                else
+                    variableData = std::copy(bclData, bclData + fragment.getReadLength(), variableData);
+                if (fragment.isAligned())
+                {
+                    const alignment::Cigar::const_iterator cigarBegin = fragment.cigarBuffer->begin() + fragment.cigarOffset;
+                    std::memcpy(variableData, &*cigarBegin, size_t(fragment.cigarLength) * sizeof(unsigned));
+                }
+                io::FragmentHeader header;
+                if (2 == bam.getFragmentCount())
+                {
+                    const alignment::FragmentMetadata &mate = bam.getMateFragmentMetadata(fragment);
+                    unsigned mateStorageBin = 0;
+                    if (!fragment.isNoMatch() && options->distributionBinSize)             // BinIndexMap::getBinIndex (BinIndexMap.hh:96-107)
+                    {
+                        const reference::ReferencePosition pos = mate.getFStrandReferencePosition();
+                        const uint64_t begin = options->contigBinBegin[pos.getContigId()];
+                        mateStorageBin = options->binIndex[begin + pos.getPosition() / options->distributionBinSize];
+                    }
+                    header = io::FragmentHeader(bam, fragment, mate, options->barcodeIdx, mateStorageBin);
+                }
+                else
+                {
+                    header = io::FragmentHeader(bam, fragment, options->barcodeIdx);
+                }
+                std::memcpy(dataBytes, &header, sizeof(header));
+            }
         }
         return ISAAC_EXT_OK;
     }

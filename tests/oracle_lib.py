@@ -192,6 +192,39 @@ def trim_low_quality_ends(oracle, reads, base_quality_cutoff):
     return out
 
 
+def pack_fragments(oracle, reads, templates, options, barcode_bytes=None, records=True):
+    """FragmentCollector::add for every stored template through the reference's own io::FragmentHeader (reference build only)
+    -> (batch.PackedFragments, header mask [headerLength] with 0xFF on the bytes that carry a member)"""
+    from isaac_aligner_b200.batch import PackedFragments
+    n, rc = reads.cluster_count, reads.read_count
+    layout = np.zeros(4, dtype=np.uint32)
+    mask = np.zeros(256, dtype=np.uint8)
+    t = np.ascontiguousarray(templates.templates)
+    f = np.ascontiguousarray(templates.fragments)
+    cig = np.ascontiguousarray(templates.cigars, dtype=np.uint32)
+    bar = None if barcode_bytes is None else np.ascontiguousarray(barcode_bytes, dtype=np.uint8).reshape(n, -1)
+
+    def call(rec, pos, init):
+        rc_ = oracle.lib.oracle_pack_fragments(
+            ctypes.byref(reads.c), ctypes.c_void_p(t.ctypes.data), ctypes.c_void_p(f.ctypes.data),
+            ctypes.c_void_p(cig.ctypes.data) if cig.size else None, ctypes.c_uint64(cig.size), ctypes.byref(options.c),
+            ctypes.c_void_p(bar.ctypes.data) if bar is not None else None, ctypes.c_uint32(bar.shape[1] if bar is not None else 0),
+            ctypes.c_void_p(rec.ctypes.data) if rec is not None else None, ctypes.c_void_p(pos.ctypes.data) if pos is not None else None,
+            ctypes.c_void_p(init.ctypes.data) if init is not None else None, ctypes.c_void_p(mask.ctypes.data),
+            ctypes.c_void_p(layout.ctypes.data))
+        if rc_:
+            raise RuntimeError("oracle_pack_fragments failed: %d" % rc_)
+
+    call(None, None, None)
+    rec = np.zeros((n, int(layout[0])), dtype=np.uint8)
+    pos = np.zeros((n, rc), dtype=np.uint64)
+    init = np.zeros((n, rc), dtype=np.uint8)
+    if records:
+        call(rec, pos, init)
+    return (PackedFragments(rec, pos, init, int(layout[0]), (int(layout[1]), int(layout[2])), int(layout[3]), int(init.sum())),
+            mask[:int(layout[3])].copy())
+
+
 def port():
     if not os.path.exists(PORT_SO):
         build("port")
