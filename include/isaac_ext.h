@@ -389,6 +389,10 @@ typedef struct isaac_ext_pack_options {
     uint32_t barcodeIdx;              /* the barcode index FragmentCollector::add is called with                          */
     uint32_t keepUnaligned;           /* --keep-unaligned: store the templates that did not build too
                                          (MatchSelector.cpp:311-314,331,355-358); else only templates with 'built'       */
+    uint32_t compact;                 /* 0: FragmentBuffer layout (fixed-size slots); 1: the stored records back to back, each
+                                         FragmentHeader::getTotalLength() bytes = what BufferingFragmentStorage::flush writes
+                                         to a bin file per fragment (BufferingFragmentStorage.cpp:108-116,184-188)           */
+    uint32_t pad;
     const uint8_t  *pf;               /* Cluster::getPf per cluster, or NULL = every cluster passes                       */
     const int32_t  *xy;               /* Cluster::getXy: x, y per cluster, or NULL = unset (POSITION_NOT_SET)             */
     const uint64_t *barcodeSequence;  /* Cluster::getBarcodeSequence per cluster, or NULL = 0                             */
@@ -404,7 +408,8 @@ typedef struct isaac_ext_pack_options {
  * 108..111 and the six spare bits of flags_ are zero here, unspecified in the reference) followed by readLength BCL bytes
  * (reverse-complemented for reverse fragments) and cigarLength CIGAR words; everything behind is zero, like the reference's
  * freshly resized buffer.  fStrandPos / initialized = index_: IndexRecord::fStrandPos_ (ReferencePosition::getValue) and
- * IndexRecord::initialized() per cluster * readCount + readIndex. */
+ * IndexRecord::initialized() per cluster * readCount + readIndex.  With options.compact the records lie back to back in
+ * (cluster, readIndex) order at recordOffset[], each cut to its FragmentHeader::getTotalLength(). */
 typedef struct isaac_ext_pack_result {
     const uint8_t  *records;
     const uint64_t *fStrandPos;
@@ -413,6 +418,9 @@ typedef struct isaac_ext_pack_result {
     uint32_t readOffset[2];           /* FragmentBuffer::getReadOffsets (:295-308)                                        */
     uint32_t headerLength;
     uint64_t storedFragments;         /* records initialised by this call                                                 */
+    const uint64_t *recordOffset;     /* clusterCount * readCount + 1: byte offset of every record in 'records' (compact: a
+                                         record that is not stored has length 0)                                           */
+    uint64_t recordBytes;             /* bytes at 'records'                                                               */
 } isaac_ext_pack_result_t;
 
 /* FragmentCollector::add for every fragment of every template of the resident tile that MatchSelector::processMatchList stores

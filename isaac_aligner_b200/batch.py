@@ -121,7 +121,7 @@ class Templates:
 class PackOptionsC(ctypes.Structure):
     """isaac_ext_pack_options_t"""
     _fields_ = [("tile", ctypes.c_uint64), ("barcodeIdx", ctypes.c_uint32), ("keepUnaligned", ctypes.c_uint32),
-                ("pf", ctypes.c_void_p), ("xy", ctypes.c_void_p), ("barcodeSequence", ctypes.c_void_p),
+                ("compact", ctypes.c_uint32), ("pad", ctypes.c_uint32), ("pf", ctypes.c_void_p), ("xy", ctypes.c_void_p), ("barcodeSequence", ctypes.c_void_p),
                 ("distributionBinSize", ctypes.c_uint32), ("contigCount", ctypes.c_uint32),
                 ("contigBinBegin", ctypes.c_void_p), ("binIndex", ctypes.c_void_p)]
 
@@ -131,7 +131,7 @@ class PackOptions:
     bin_index: one uint32 array per contig = BinIndexMap::at(contigId + 1) (BinIndexMap.hh:45-107)."""
 
     def __init__(self, tile=0, barcode_idx=0, keep_unaligned=False, pf=None, xy=None, barcode_sequence=None,
-                 distribution_bin_size=0, bin_index=None):
+                 distribution_bin_size=0, bin_index=None, compact=False):
         self.pf = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
         self.xy = None if xy is None else np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
         self.barcode_sequence = None if barcode_sequence is None else np.ascontiguousarray(barcode_sequence, dtype=np.uint64)
@@ -143,7 +143,7 @@ class PackOptions:
             self.bin_begin[1:] = np.cumsum([len(b) for b in bin_index])
             self.bin_flat = np.ascontiguousarray(np.concatenate([np.asarray(b, dtype=np.uint32) for b in bin_index] + [np.zeros(1, np.uint32)]))
         ptr = lambda a: a.ctypes.data if a is not None else None
-        self.c = PackOptionsC(tile, barcode_idx, 1 if keep_unaligned else 0, ptr(self.pf), ptr(self.xy), ptr(self.barcode_sequence),
+        self.c = PackOptionsC(tile, barcode_idx, 1 if keep_unaligned else 0, 1 if compact else 0, 0, ptr(self.pf), ptr(self.xy), ptr(self.barcode_sequence),
                               distribution_bin_size, contigs, ptr(self.bin_begin), ptr(self.bin_flat))
 
 
@@ -151,13 +151,31 @@ class PackResultC(ctypes.Structure):
     """isaac_ext_pack_result_t"""
     _fields_ = [("records", ctypes.c_void_p), ("fStrandPos", ctypes.c_void_p), ("initialized", ctypes.c_void_p),
                 ("recordLength", ctypes.c_uint32), ("readOffset", ctypes.c_uint32 * 2), ("headerLength", ctypes.c_uint32),
-                ("storedFragments", ctypes.c_uint64)]
+                ("storedFragments", ctypes.c_uint64), ("recordOffset", ctypes.c_void_p), ("recordBytes", ctypes.c_uint64)]
 
 
 class PackedFragments:
     """matchSelector::FragmentBuffer of a tile: records [clusters, recordLength] bytes, f_strand_pos / initialized
-    [clusters, readCount]; the record of (cluster, readIndex) starts at records[cluster, read_offset[readIndex]]"""
+    [clusters, readCount]; the record of (cluster, readIndex) starts at records[cluster, read_offset[readIndex]].
+    Compact results: records is flat, the record of (cluster, readIndex) is records[record_offset[i] : record_offset[i + 1]] with
+    i = cluster * readCount + readIndex."""
 
-    def __init__(self, records, f_strand_pos, initialized, record_length, read_offset, header_length, stored):
+    def __init__(self, records, f_strand_pos, initialized, record_length, read_offset, header_length, stored, record_offset=None):
         self.records, self.f_strand_pos, self.initialized = records, f_strand_pos, initialized
         self.record_length, self.read_offset, self.header_length, self.stored = record_length, tuple(read_offset), header_length, stored
+        self.record_offset = record_offset
+
+    def compacted(self):
+        """the compact form of a FragmentBuffer-layout result: every initialised record cut to FragmentHeader::getTotalLength()
+        (112 + readLength_ + 4 * cigarLength_, Fragment.hh:192-202), back to back in (cluster, readIndex) order -> (bytes, offsets)"""
+        n, rc = self.initialized.shape
+        parts, offsets = [], [0]
+        for c in range(n):
+            for r in range(rc):
+                length = 0
+                if self.initialized[c, r]:
+                    rec = self.records[c, self.read_offset[r]:]
+                    length = self.header_length + int(rec[32:34].view(np.uint16)[0]) + 4 * int(rec[34:36].view(np.uint16)[0])
+                    parts.append(rec[:length])
+                offsets.append(offsets[-1] + length)
+        return (np.concatenate(parts) if parts else np.zeros(0, np.uint8)), np.array(offsets, dtype=np.uint64)

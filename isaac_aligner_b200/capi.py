@@ -245,10 +245,13 @@ class Context:
             buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
             return np.frombuffer(buf, dtype=dtype).copy()
 
-        return PackedFragments(arr(res.records, np.uint8, n * res.recordLength).reshape(n, res.recordLength),
-                               arr(res.fStrandPos, np.uint64, n * rc).reshape(n, rc), arr(res.initialized, np.uint8, n * rc).reshape(n, rc),
-                               int(res.recordLength), (int(res.readOffset[0]), int(res.readOffset[1])), int(res.headerLength),
-                               int(res.storedFragments))
+        records = arr(res.records, np.uint8, int(res.recordBytes)) if res.recordBytes else np.zeros(0, np.uint8)
+        if not options.c.compact:
+            records = records.reshape(n, res.recordLength)
+        return PackedFragments(records, arr(res.fStrandPos, np.uint64, n * rc).reshape(n, rc),
+                               arr(res.initialized, np.uint8, n * rc).reshape(n, rc), int(res.recordLength),
+                               (int(res.readOffset[0]), int(res.readOffset[1])), int(res.headerLength), int(res.storedFragments),
+                               arr(res.recordOffset, np.uint64, n * rc + 1))
 
     def tile_stats_device(self, n, d_fragments, d_stats, stream):
         """adds the K6 counters of n device-resident fragment records to the 64 u64 at d_stats"""

@@ -8,7 +8,8 @@ struct PackState
     DeviceBuffer<isaac_ext_template_t> dTemplates;  DeviceBuffer<isaac_ext_fragment_t> dFragments;  DeviceBuffer<uint32_t> dCigars;
     DeviceBuffer<uint8_t> dPf, dRecords, dInitialized;
     DeviceBuffer<int32_t> dXy;
-    DeviceBuffer<uint64_t> dBarcodeSequence, dContigBinBegin, dFStrandPos;
+    DeviceBuffer<uint64_t> dBarcodeSequence, dContigBinBegin, dFStrandPos, dRecordOffset;
+    HostBuffer<uint64_t> recordOffset;
     DeviceBuffer<uint32_t> dBinIndex;
     DeviceBuffer<unsigned long long> dStored;
     PinnedBuffer<uint8_t> hRecords, hInitialized;
@@ -17,7 +18,7 @@ struct PackState
     void release()
     {
         dTemplates.release(); dFragments.release(); dCigars.release(); dPf.release(); dRecords.release(); dInitialized.release();
-        dXy.release(); dBarcodeSequence.release(); dContigBinBegin.release(); dFStrandPos.release(); dBinIndex.release(); dStored.release();
+        dXy.release(); dBarcodeSequence.release(); dContigBinBegin.release(); dFStrandPos.release(); dBinIndex.release(); dStored.release(); dRecordOffset.release();
         hRecords.release(); hInitialized.release(); hFStrandPos.release(); hStored.release();
     }
 };
@@ -59,7 +60,23 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
     packLayout(v);
     v.tile = options->tile; v.barcodeIdx = options->barcodeIdx; v.keepUnaligned = options->keepUnaligned;
     v.bcl = ctx->bclStage.p; v.bclBytes = uint64_t(n) * (v.readLength[0] + v.readLength[1]);
-    const size_t recordBytes = size_t(n) * v.recordLength;
+    // record offsets: FragmentBuffer slots, or (compact) the prefix sum of the records' total lengths, computed here from the
+    // host copy of the templates the kernel is about to get
+    st.recordOffset.reserve(count + 1);
+    uint64_t *offsets = st.recordOffset.p;
+    {
+        PackView h = v;
+        h.templates = templates->templates; h.fragments = templates->fragments;
+        parallelRanges(ctx->hostThreads, n, [&](unsigned, size_t b, size_t e) {
+            for (size_t c = b; c < e; ++c)
+                for (unsigned r = 0; r < rc; ++r)
+                    offsets[c * rc + r + 1] = options->compact ? packRecordBytes(h, uint32_t(c), r)
+                                                               : (r + 1 < rc ? h.readOffset[r + 1] : h.recordLength) - h.readOffset[r];
+        });
+        offsets[0] = 0;
+        for (size_t i = 1; i <= count; ++i) offsets[i] += offsets[i - 1];
+    }
+    const size_t recordBytes = offsets[count];
 
     CK(st.dTemplates.reserve(n)); CK(st.dFragments.reserve(count)); CK(st.dCigars.reserve(templates->cigarWords + 1));
     CK(st.dRecords.reserve(recordBytes)); CK(st.dFStrandPos.reserve(count)); CK(st.dInitialized.reserve(count)); CK(st.dStored.reserve(1));
@@ -97,6 +114,12 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
         v.contigBinBegin = st.dContigBinBegin.p; v.binIndex = st.dBinIndex.p;
         v.contigCount = options->contigCount; v.distributionBinSize = options->distributionBinSize;
     }
+    if (options->compact)
+    {
+        CK(st.dRecordOffset.reserve(count + 1));
+        CK(cudaMemcpyAsync(st.dRecordOffset.p, offsets, (count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+        v.recordOffset = st.dRecordOffset.p;
+    }
     v.records = st.dRecords.p; v.fStrandPos = st.dFStrandPos.p; v.initialized = st.dInitialized.p;
     CK(cudaMemsetAsync(st.dStored.p, 0, sizeof(unsigned long long), ctx->stream));
 
@@ -111,7 +134,7 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
     packFragmentsKernel<<<gridFor(ctx, uint64_t(n) * 32, block, 8), block, shared, ctx->stream>>>(v, st.dStored.p);
     ++ctx->launches;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(st.hRecords.p, st.dRecords.p, recordBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (recordBytes) CK(cudaMemcpyAsync(st.hRecords.p, st.dRecords.p, recordBytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(st.hFStrandPos.p, st.dFStrandPos.p, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(st.hInitialized.p, st.dInitialized.p, count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(st.hStored.p, st.dStored.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -121,5 +144,6 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
     result->recordLength = v.recordLength; result->readOffset[0] = v.readOffset[0]; result->readOffset[1] = v.readOffset[1];
     result->headerLength = PACK_HEADER_BYTES;
     result->storedFragments = *st.hStored.p;
+    result->recordOffset = offsets; result->recordBytes = recordBytes;
     return ISAAC_EXT_OK;
 }

@@ -8,7 +8,7 @@
 // template in, recordLength (1644 B for 2 x 150) out.
 //
 // Everything but the warp plumbing is ISAAC_HD and takes (lane, lanes): tests/cpp/test_pack_fragments.cpp runs the same functions
-// lane after lane on the CPU against the reference's own io::FragmentHeader (tests/test_pack_fragments.py).
+// lane after lane on the CPU against the reference's own io::FragmentHeader (tests/test_tile_pack_fragments.py).
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -138,7 +138,8 @@ struct PackView
     uint32_t clusterCount, readCount;
     uint32_t readLength[2];
     uint32_t recordLength, readOffset[2];
-    uint8_t *records;                          // clusterCount * recordLength
+    const uint64_t *recordOffset;              // null: FragmentBuffer slots; else clusterCount * readCount + 1 byte offsets (compact)
+    uint8_t *records;                          // clusterCount * recordLength, or recordOffset[clusterCount * readCount] bytes
     uint64_t *fStrandPos;                      // clusterCount * readCount
     uint8_t *initialized;                      // clusterCount * readCount
 };
@@ -338,8 +339,19 @@ ISAAC_HD inline unsigned packStageRecord(const PackView &v, const uint32_t clust
 ISAAC_HD inline void packStoreRecord(const PackView &v, const uint32_t cluster, const unsigned r, const unsigned used,
                                      const uint8_t *staging, const unsigned lane, const unsigned lanes)
 {
-    packStoreSlot(v.records + size_t(cluster) * v.recordLength + v.readOffset[r], reinterpret_cast<const uint32_t *>(staging), used,
-                  packMaxTotalLength(v.readLength[r]), lane, lanes);
+    if (v.recordOffset)         // compact: the used bytes only, at the offset the caller computed from the record lengths
+        packStoreSlot(v.records + v.recordOffset[size_t(cluster) * v.readCount + r], reinterpret_cast<const uint32_t *>(staging), used, used,
+                      lane, lanes);
+    else
+        packStoreSlot(v.records + size_t(cluster) * v.recordLength + v.readOffset[r], reinterpret_cast<const uint32_t *>(staging), used,
+                      packMaxTotalLength(v.readLength[r]), lane, lanes);
+}
+
+/// FragmentHeader::getTotalLength of the record of (cluster, r) (Fragment.hh:192-202), 0 for a template that is not stored: the
+/// caller's prefix sum over these is PackView::recordOffset
+ISAAC_HD inline unsigned packRecordBytes(const PackView &v, const uint32_t cluster, const unsigned r)
+{
+    return packStores(v, cluster) ? packUsedBytes(v, v.fragments[size_t(cluster) * v.readCount + r], r) : 0u;
 }
 
 #ifdef __CUDACC__

@@ -47,14 +47,16 @@ def cluster_match_begin(matches, cluster_count):
 
 
 class TileResult:
-    def __init__(self, templates, tls, tls_stable, stats, end_cycles_masked):
+    def __init__(self, templates, tls, tls_stable, stats, end_cycles_masked, packed=None):
         self.templates, self.tls, self.tls_stable, self.stats, self.end_cycles_masked = templates, tls, tls_stable, stats, end_cycles_masked
+        self.packed = packed
 
 
 def select_tile(ctx, bcl, read_lengths, matches, seeds, pf=None, base_quality_cutoff=0, tls=None, options=None,
-                mate_drift_range=-1, with_gaps=True):
+                mate_drift_range=-1, with_gaps=True, pack=None):
     """MatchSelector::parallelSelect for one tile on the context's GPU.  tls: user-defined template length statistics
-    (batch.Tls) or None = determine them from this tile."""
+    (batch.Tls) or None = determine them from this tile.  pack: batch.PackOptions = also leave the io::FragmentHeader bin
+    records FragmentCollector::add stores for the tile (TileResult.packed), None = skip that pass."""
     reads = ReadSet(bcl, tuple(read_lengths))
     ctx.set_reads(reads)
     masked = ctx.trim_low_quality_ends(base_quality_cutoff) if base_quality_cutoff else None
@@ -65,4 +67,5 @@ def select_tile(ctx, bcl, read_lengths, matches, seeds, pf=None, base_quality_cu
     options = options if options is not None else TemplateOptions.make()
     templates = ctx.build_templates(mb, tls, options)
     stats = ctx.template_stats(mb, tls, templates, pf)
-    return TileResult(templates, tls, stable, stats, masked)
+    packed = ctx.pack_fragments(templates, pack) if pack is not None else None
+    return TileResult(templates, tls, stable, stats, masked, packed)

@@ -1,5 +1,5 @@
 // pack_fragments.cuh on the CPU: the functions the warps of packFragmentsKernel run, called lane after lane with the two
-// phases of a record separated the way __syncwarp separates them.  Built as a shared library by tests/test_pack_fragments.py,
+// phases of a record separated the way __syncwarp separates them.  Built as a shared library by tests/test_tile_pack_fragments.py,
 // which compares the records with the reference's own io::FragmentHeader (oracle/_ref).  TEST CODE, not a product path.
 #include <cstdlib>
 #include <cstring>
@@ -13,7 +13,7 @@ extern "C" int pack_fragments_lanes(const isaac_ext_reads_t *reads, const isaac_
                                     const isaac_ext_fragment_t *fragments, const uint32_t *cigars,
                                     const isaac_ext_pack_options_t *options, unsigned lanes, unsigned misalign,
                                     uint8_t *recordsOut, uint64_t *fStrandPosOut, uint8_t *initializedOut, uint32_t *layoutOut,
-                                    uint64_t *storedOut)
+                                    uint64_t *storedOut, uint64_t *recordOffsetOut)
 {
     PackView v{};
     v.clusterCount = reads->clusterCount; v.readCount = reads->readCount;
@@ -28,8 +28,20 @@ extern "C" int pack_fragments_lanes(const isaac_ext_reads_t *reads, const isaac_
         v.contigCount = options->contigCount; v.distributionBinSize = options->distributionBinSize;
     }
     v.tile = options->tile; v.barcodeIdx = options->barcodeIdx; v.keepUnaligned = options->keepUnaligned;
+    // compact: the offsets the ABI computes on the host (isaac_ext_pack.cuh)
+    std::vector<uint64_t> offsets(size_t(v.clusterCount) * v.readCount + 1, 0);
+    size_t bytes = size_t(v.clusterCount) * v.recordLength;
+    if (options->compact)
+    {
+        for (uint32_t c = 0; c < v.clusterCount; ++c)
+            for (unsigned r = 0; r < v.readCount; ++r)
+                offsets[size_t(c) * v.readCount + r + 1] = offsets[size_t(c) * v.readCount + r] + packRecordBytes(v, c, r);
+        v.recordOffset = offsets.data();
+        bytes = offsets.back();
+        std::memcpy(recordOffsetOut, offsets.data(), offsets.size() * sizeof(uint64_t));
+    }
     // the record buffer at any alignment the caller asks for (cudaMalloc gives 256 bytes, the slots inside are at odd offsets)
-    std::vector<uint8_t> buffer(size_t(v.clusterCount) * v.recordLength + 16, 0xAB);
+    std::vector<uint8_t> buffer(bytes + 32, 0xAB);
     uint8_t *base = buffer.data();
     while (reinterpret_cast<uintptr_t>(base) % 8 != misalign % 8) ++base;
     v.records = base; v.fStrandPos = fStrandPosOut; v.initialized = initializedOut;
@@ -51,7 +63,10 @@ extern "C" int pack_fragments_lanes(const isaac_ext_reads_t *reads, const isaac_
             for (unsigned lane = 0; lane < lanes; ++lane) packStoreRecord(v, cluster, r, used, staging, lane, lanes);
         }
     }
-    std::memcpy(recordsOut, base, size_t(v.clusterCount) * v.recordLength);
+    std::memcpy(recordsOut, base, bytes);
     *storedOut = stored;
+    // nothing may be written in front of or behind the records
+    for (const uint8_t *p = buffer.data(); p < base; ++p) if (*p != 0xAB) return 2;
+    for (const uint8_t *p = base + bytes; p < buffer.data() + buffer.size(); ++p) if (*p != 0xAB) return 3;
     return 0;
 }

@@ -44,10 +44,10 @@ def random_cigar(rng, L, aligned_bases_zero=False):
     words, observed, gaps = [], 0, 0
     if lead:
         words.append((lead << 4) | 4)
-    n_gaps = int(rng.integers(0, 4)) if rng.random() < 0.4 else 0
+    n_gaps = int(rng.integers(0, 4)) if rng.random() < 0.4 and body >= 60 else 0
     left = body
     for g in range(n_gaps):
-        m = int(rng.integers(5, max(6, left // (n_gaps - g + 1))))
+        m = int(rng.integers(5, max(6, (left - 15) // (n_gaps - g + 1))))
         words.append((m << 4) | 0)
         observed += m
         left -= m
@@ -128,9 +128,9 @@ def bin_index():
     return out
 
 
-def make_options(rng, n, keep_unaligned, with_arrays=True, barcode_length=6):
+def make_options(rng, n, keep_unaligned, with_arrays=True, barcode_length=6, compact=False):
     if not with_arrays:
-        return PackOptions(tile=7, barcode_idx=3, keep_unaligned=keep_unaligned), None
+        return PackOptions(tile=7, barcode_idx=3, keep_unaligned=keep_unaligned, compact=compact), None
     xy = rng.integers(-5000, 250000, size=(n, 2)).astype(np.int32)
     xy[rng.random(n) < 0.1] = 0x7FFFFFFF
     barcode = random_bcl(rng, n, barcode_length)
@@ -138,7 +138,7 @@ def make_options(rng, n, keep_unaligned, with_arrays=True, barcode_length=6):
     for i in range(barcode_length):                                      # oligo::packBclBases (Nucleotides.hh:280-293)
         sequence |= (barcode[:, i].astype(np.uint64) & np.uint64(3)) << np.uint64(2 * i)
     return PackOptions(tile=1101, barcode_idx=5, keep_unaligned=keep_unaligned, pf=(rng.random(n) < 0.8).astype(np.uint8), xy=xy,
-                       barcode_sequence=sequence, distribution_bin_size=BIN_SIZE, bin_index=bin_index()), barcode
+                       barcode_sequence=sequence, distribution_bin_size=BIN_SIZE, bin_index=bin_index(), compact=compact), barcode
 
 
 def assert_packed_equal(got, want, mask, read_lengths, what):
@@ -186,11 +186,15 @@ def pack_lanes(lib, reads, templates, options, lanes, misalign):
     pos = np.zeros((n, rc), dtype=np.uint64)
     init = np.full((n, rc), 9, dtype=np.uint8)
     stored = ctypes.c_uint64()
+    offsets = np.zeros(n * rc + 1, dtype=np.uint64)
     t, f, cig = templates.templates, templates.fragments, templates.cigars
     p = lambda a: ctypes.c_void_p(a.ctypes.data)
     assert lib.pack_fragments_lanes(ctypes.byref(reads.c), p(t), p(f), p(cig), ctypes.byref(options.c), ctypes.c_uint(lanes),
-                                    ctypes.c_uint(misalign), p(rec), p(pos), p(init), p(layout), ctypes.byref(stored)) == 0
+                                    ctypes.c_uint(misalign), p(rec), p(pos), p(init), p(layout), ctypes.byref(stored), p(offsets)) == 0
     record_length = int(layout[0])
+    if options.c.compact:
+        return PackedFragments(rec[:int(offsets[-1])].copy(), pos, init, record_length, (int(layout[1]), int(layout[2])), int(layout[3]),
+                               int(stored.value), offsets)
     return PackedFragments(rec[:n * record_length].reshape(n, record_length).copy(), pos, init, record_length,
                            (int(layout[1]), int(layout[2])), int(layout[3]), int(stored.value))
 
@@ -226,6 +230,43 @@ def test_warp_functions_against_the_reference_on_the_cpu(lanes_lib, read_lengths
     assert_packed_equal(got, want, mask, read_lengths, "lanes %d, buffer at %d mod 8" % (lanes, misalign))
     if not keep:
         assert 0 < want.initialized.sum() < want.initialized.size
+
+
+def assert_compact_equal(got, want, mask, what):
+    """got: a compact result; want: the reference's FragmentBuffer, cut to the records' total lengths"""
+    data, offsets = want.compacted()
+    assert np.array_equal(got.record_offset, offsets), what + ": record offsets"
+    assert got.records.size == data.size, what
+    assert np.array_equal(got.initialized, want.initialized) and np.array_equal(got.f_strand_pos, want.f_strand_pos), what
+    keep = np.ones(data.size, dtype=bool)                                # all bytes but the padding of the headers
+    H = want.header_length
+    pad = np.nonzero(mask != 0xFF)[0]
+    starts = offsets[:-1][np.diff(offsets.astype(np.int64)) > 0].astype(np.int64)
+    for b in pad:
+        if mask[b] == 0:
+            keep[starts + b] = False
+    g, w = got.records.copy(), data.copy()
+    for b in pad:
+        if mask[b] != 0:
+            g[starts + b] &= mask[b]; w[starts + b] &= mask[b]
+    bad = np.nonzero((g != w) & keep)[0]
+    assert not bad.size, "%s: %d bytes differ, first at %d" % (what, bad.size, bad[0] if bad.size else -1)
+    assert H == 112
+
+
+@needs_reference
+@pytest.mark.parametrize("read_lengths,lanes,misalign,keep", [((150, 150), 32, 0, True), ((101, 76), 32, 3, False), ((151,), 3, 1, False),
+                                                              ((33, 32), 32, 2, True)])
+def test_compact_records_against_the_reference_on_the_cpu(lanes_lib, read_lengths, lanes, misalign, keep):
+    """options.compact: the bytes BufferingFragmentStorage::flush writes per fragment, back to back"""
+    rng = np.random.default_rng(hash((read_lengths, lanes, misalign, keep, "compact")) & 0xFFFFFFFF)
+    n = 500
+    reads = ReadSet(random_bcl(rng, n, sum(read_lengths)), read_lengths)
+    templates = random_templates(rng, n, read_lengths)
+    options, barcode = make_options(rng, n, keep, compact=True)
+    want, mask = oracle_lib.pack_fragments(oracle_lib.reference(), reads, templates, options, barcode_bytes=barcode)
+    got = pack_lanes(lanes_lib, reads, templates, options, lanes, misalign)
+    assert_compact_equal(got, want, mask, "compact, lanes %d" % lanes)
 
 
 def test_pack_kernel_compiles_for_the_device():
@@ -273,6 +314,22 @@ def test_pack_fragments_random_templates(capi, read_lengths, keep, arrays):
     assert_packed_equal(got, want, mask, read_lengths, "GPU, reads %r" % (read_lengths,))
     again = ctx.pack_fragments(templates, options)                       # buffers of the context reused
     assert np.array_equal(again.records, got.records)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@needs_reference
+@pytest.mark.parametrize("read_lengths,keep", [((150, 150), True), ((101, 76), False), ((151,), False)])
+def test_pack_fragments_compact(capi, read_lengths, keep):
+    rng = np.random.default_rng(hash((read_lengths, keep, "gpu compact")) & 0xFFFFFFFF)
+    n = 4000
+    reads = ReadSet(random_bcl(rng, n, sum(read_lengths)), read_lengths)
+    templates = random_templates(rng, n, read_lengths)
+    options, barcode = make_options(rng, n, keep, compact=True)
+    want, mask = oracle_lib.pack_fragments(oracle_lib.reference(), reads, templates, options, barcode_bytes=barcode)
+    ctx = gpu_context(capi, reads)
+    got = ctx.pack_fragments(templates, options)
+    assert_compact_equal(got, want, mask, "GPU compact, reads %r" % (read_lengths,))
     ctx.close()
 
 
