@@ -36,6 +36,7 @@ EXPORTS = [
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
     "isaac_ext_template_stats", "isaac_ext_pack_fragments",
+    "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
 ]
 
 
@@ -195,13 +196,15 @@ class Context:
 
     def build_templates(self, match_batch, tls, options=None, copy=True):
         """TemplateBuilder::buildFragments + buildTemplate for every cluster of the resident read set -> batch.Templates"""
-        from .batch import TEMPLATE_DTYPE, TemplateOptions, TemplateResult, Templates
+        from .batch import TemplateOptions, TemplateResult
         options = options if options is not None else TemplateOptions.make()
         res = TemplateResult()
         self._check(_lib.isaac_ext_build_templates(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(options),
                                                    ctypes.byref(res)))
-        if not copy:
-            return res
+        return self._templates(res) if copy else res
+
+    def _templates(self, res):
+        from .batch import TEMPLATE_DTYPE, Templates
         n = self.reads.cluster_count
 
         def arr(ptr, dtype, count):
@@ -212,6 +215,25 @@ class Context:
 
         return Templates(arr(res.templates, TEMPLATE_DTYPE, n), arr(res.fragments, FRAGMENT_DTYPE, n * self.reads.read_count),
                          arr(res.cigars, np.uint32, int(res.cigarWords)), int(res.rescueRequests))
+
+    def submit_build_templates(self, match_batch, tls, options=None):
+        """isaac_ext_submit_build_templates: returns a ticket at once, the call runs on a worker thread of the context; the
+        arrays of match_batch must stay alive and unchanged until wait_templates"""
+        from .batch import TemplateOptions
+        options = options if options is not None else TemplateOptions.make()
+        ticket = ctypes.c_uint64()
+        self._check(_lib.isaac_ext_submit_build_templates(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(options),
+                                                          ctypes.byref(ticket)))
+        self._in_flight = match_batch
+        return int(ticket.value)
+
+    def wait_templates(self, ticket):
+        """isaac_ext_wait for a ticket of submit_build_templates -> batch.Templates"""
+        from .batch import TemplateResult
+        res = TemplateResult()
+        self._check(_lib.isaac_ext_wait(self._h, ctypes.c_uint64(ticket), ctypes.byref(res)))
+        self._in_flight = None
+        return self._templates(res)
 
     def template_stats(self, match_batch, tls, templates, pf=None):
         """matchSelector::TileBarcodeStats of a tile's templates (batch.Templates) -> uint64 [4, TEMPLATE_STATS_COUNTERS],

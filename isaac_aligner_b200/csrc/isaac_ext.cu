@@ -29,6 +29,8 @@ struct TemplateState;                  // isaac_ext_templates.cuh
 void releaseTemplates(TemplateState *state);
 struct PackState;                      // isaac_ext_pack.cuh
 void releasePack(PackState *state);
+struct AsyncState;                     // isaac_ext_async.cuh
+void releaseAsync(AsyncState *state);
 
 struct isaac_ext_ctx
 {
@@ -54,6 +56,7 @@ struct isaac_ext_ctx
     E2eState *e2e = nullptr;      // streams and chunk buffers of the *_batch_compact entry points
     TemplateState *templates = nullptr;   // buffers of isaac_ext_build_templates
     PackState *pack = nullptr;            // buffers of isaac_ext_pack_fragments
+    AsyncState *async = nullptr;          // the call in flight between isaac_ext_submit_* and isaac_ext_wait
     double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
@@ -238,6 +241,8 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
 extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
 {
     if (!ctx) return;
+    releaseAsync(ctx->async);             // joins a submitted call that was never waited for
+    ctx->async = nullptr;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     ctx->tables.release(); ctx->refBases2.release(); ctx->refNmask.release(); ctx->refContigOffset.release();
@@ -729,6 +734,7 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 #include "isaac_ext_templates.cuh"
 #include "isaac_ext_tls.cuh"
 #include "isaac_ext_pack.cuh"
+#include "isaac_ext_async.cuh"
 
 namespace
 {
