@@ -55,8 +55,10 @@ def parse_args():
     p.add_argument("--cigar-stride", type=int, default=32)
     p.add_argument("--cpu-sample-per-core", type=int, default=40_000)
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--workload", default="micro", choices=["micro", "pairs"],
-                   help="micro: BASELINE configs[1] (default, the bench line); pairs: build + rescue pipeline, read pairs/s")
+    p.add_argument("--workload", default="micro", choices=["micro", "pairs", "pack"],
+                   help="micro: BASELINE configs[1] (default, the bench line); pairs: build + rescue pipeline, read pairs/s; "
+                        "pack: the io::FragmentHeader bin records of a tile's templates (isaac_ext_pack_fragments), fragments/s")
+    p.add_argument("--compact", action="store_true", help="--workload pack: records cut to their total length instead of FragmentBuffer slots")
     p.add_argument("--pairs", type=int, default=None,
                    help="read pairs per GPU of the pairs pipeline (default 200k as a side measurement of the micro run, 1M for --workload pairs; 0 disables)")
     p.add_argument("--contigs", type=int, default=1, help="contigs of the synthetic genome (SURVEY 8(d) G3100: 24)")
@@ -535,9 +537,73 @@ def run_pairs(args):
     ctx.close()
 
 
+def run_pack(args):
+    """--workload pack: isaac_ext_pack_fragments over the templates of a simulated tile.  value = fragments/s of the
+    kernel alone (CUDA events inside the library, records resident in HBM), e2e = the whole call with host templates in and host
+    records out; roofline: HBM, algorithmic bytes = BCL + fragment / template records + CIGAR words read, record bytes written.
+    One GPU (tiles shard over ranks like everywhere else; this workload is a kernel measurement)."""
+    import torch
+    from isaac_aligner_b200 import capi
+    from isaac_aligner_b200.batch import PackOptions
+    from isaac_aligner_b200.types import Config
+    if args.impl == "reference":
+        emit(json.dumps({"impl": "reference", "unavailable": "the pack workload has no reference arm: FragmentCollector needs the reference's bin storage (Boost.Filesystem)"}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
+    n_pairs = 500_000 if args.pairs is None else args.pairs
+    genome, reads, mb, tls = make_pairs_workload(args, 0, n_pairs)
+    ctx = capi.Context(Config.default(max_read_length=2 * args.read_length))
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    templates = ctx.build_templates(mb, tls)
+    options = PackOptions(tile=1101, barcode_idx=0, keep_unaligned=True, compact=args.compact)
+    sampler = ClockSampler(0)
+    for _ in range(max(3, args.warmup)):
+        res = ctx.pack_fragments(templates, options, copy=False)
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    kernel_ms, call_ms = [], []
+    launches0 = ctx.launches
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = ctx.pack_fragments(templates, options, copy=False)
+        call_ms.append((time.perf_counter() - t0) * 1e3)
+        kernel_ms.append(float(res.kernelMs))
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    fragments = int(res.storedFragments)
+    L = args.read_length
+    read_bytes = n_pairs * (2 * L + 2 * 64 + 16) + 4 * int(templates.fragments["cigarLength"].astype(np.int64).sum())
+    write_bytes = int(res.recordBytes) + n_pairs * 2 * 9
+    km, cm = float(np.mean(kernel_ms)), float(np.mean(call_ms))
+    hbm_peak, hbm_src = 6545.6, "fallback"
+    try:
+        hbm_peak, hbm_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except (OSError, KeyError, ValueError):
+        pass
+    achieved = (read_bytes + write_bytes) / (km * 1e-3) / 1e9
+    emit(json.dumps({"metric": "packed_fragments_per_s", "value": fragments / (km * 1e-3), "unit": "fragments/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": km, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": "io::FragmentHeader bin records (%s) of the templates of %d simulated 2x%d bp pairs, --keep-unaligned"
+                                             % ("compact" if args.compact else "FragmentBuffer slots", n_pairs, L),
+                                 "l2": "records written per step (%d MB) exceed the 126 MB L2" % (int(res.recordBytes) >> 20)},
+                      "e2e": {"value": fragments / (cm * 1e-3), "unit": "fragments/s", "ms_per_step": cm,
+                              "h2d_bytes_per_step": int(n_pairs * (2 * 64 + 16) + 4 * templates.cigars.size),
+                              "d2h_bytes_per_step": int(res.recordBytes) + n_pairs * 2 * 9},
+                      "gpu_launches": int(ctx.launches - launches0), "clocks": clocks,
+                      "roofline": {"bound": "hbm", "kernel": "packFragmentsKernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                   "read_bytes_per_launch": int(read_bytes), "write_bytes_per_launch": int(write_bytes), "ms_per_launch": km}}))
+    ctx.close()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.workload == "pairs":
+    if a.workload == "pack":
+        run_pack(a)
+    elif a.workload == "pairs":
         run_pairs(a)
     elif a.impl == "reference":
         run_reference(a)

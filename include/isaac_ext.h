@@ -436,6 +436,8 @@ typedef struct isaac_ext_pack_result {
     const uint64_t *recordOffset;     /* clusterCount * readCount + 1: byte offset of every record in 'records' (compact: a
                                          record that is not stored has length 0)                                           */
     uint64_t recordBytes;             /* bytes at 'records'                                                               */
+    float    kernelMs;                /* duration of the pack kernel alone (CUDA events on the context's stream), for bench.py */
+    uint32_t pad;
 } isaac_ext_pack_result_t;
 
 /* FragmentCollector::add for every fragment of every template of the resident tile that MatchSelector::processMatchList stores

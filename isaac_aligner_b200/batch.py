@@ -151,7 +151,8 @@ class PackResultC(ctypes.Structure):
     """isaac_ext_pack_result_t"""
     _fields_ = [("records", ctypes.c_void_p), ("fStrandPos", ctypes.c_void_p), ("initialized", ctypes.c_void_p),
                 ("recordLength", ctypes.c_uint32), ("readOffset", ctypes.c_uint32 * 2), ("headerLength", ctypes.c_uint32),
-                ("storedFragments", ctypes.c_uint64), ("recordOffset", ctypes.c_void_p), ("recordBytes", ctypes.c_uint64)]
+                ("storedFragments", ctypes.c_uint64), ("recordOffset", ctypes.c_void_p), ("recordBytes", ctypes.c_uint64),
+                ("kernelMs", ctypes.c_float), ("pad", ctypes.c_uint32)]
 
 
 class PackedFragments:

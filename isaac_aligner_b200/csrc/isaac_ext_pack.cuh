@@ -15,8 +15,12 @@ struct PackState
     PinnedBuffer<uint8_t> hRecords, hInitialized;
     PinnedBuffer<uint64_t> hFStrandPos;
     PinnedBuffer<unsigned long long> hStored;
+    cudaEvent_t kernelBegin = nullptr, kernelEnd = nullptr;       // timing of the kernel alone (isaac_ext_pack_result_t::kernelMs)
     void release()
     {
+        if (kernelBegin) cudaEventDestroy(kernelBegin);
+        if (kernelEnd) cudaEventDestroy(kernelEnd);
+        kernelBegin = kernelEnd = nullptr;
         dTemplates.release(); dFragments.release(); dCigars.release(); dPf.release(); dRecords.release(); dInitialized.release();
         dXy.release(); dBarcodeSequence.release(); dContigBinBegin.release(); dFStrandPos.release(); dBinIndex.release(); dStored.release(); dRecordOffset.release();
         hRecords.release(); hInitialized.release(); hFStrandPos.release(); hStored.release();
@@ -131,9 +135,12 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
     if (shared > 48 * 1024)
         CK(cudaFuncSetAttribute(packFragmentsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shared)));
     const unsigned block = warps * 32;
+    if (!st.kernelBegin) { CK(cudaEventCreate(&st.kernelBegin)); CK(cudaEventCreate(&st.kernelEnd)); }
+    CK(cudaEventRecord(st.kernelBegin, ctx->stream));
     packFragmentsKernel<<<gridFor(ctx, uint64_t(n) * 32, block, 8), block, shared, ctx->stream>>>(v, st.dStored.p);
     ++ctx->launches;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(st.kernelEnd, ctx->stream));
     if (recordBytes) CK(cudaMemcpyAsync(st.hRecords.p, st.dRecords.p, recordBytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(st.hFStrandPos.p, st.dFStrandPos.p, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(st.hInitialized.p, st.dInitialized.p, count, cudaMemcpyDeviceToHost, ctx->stream));
@@ -145,5 +152,7 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
     result->headerLength = PACK_HEADER_BYTES;
     result->storedFragments = *st.hStored.p;
     result->recordOffset = offsets; result->recordBytes = recordBytes;
+    result->kernelMs = 0.0f;
+    CK(cudaEventElapsedTime(&result->kernelMs, st.kernelBegin, st.kernelEnd));
     return ISAAC_EXT_OK;
 }
