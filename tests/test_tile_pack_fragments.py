@@ -269,6 +269,47 @@ def test_compact_records_against_the_reference_on_the_cpu(lanes_lib, read_length
     assert_compact_equal(got, want, mask, "compact, lanes %d" % lanes)
 
 
+def golden_cases():
+    import base64
+    import json
+    from isaac_aligner_b200.batch import PackedFragments
+    data = json.load(open(os.path.join(ROOT, "tests", "golden", "pack_fragments.json")))
+    for case in data["cases"]:
+        dec = lambda key, dtype: None if case[key] is None else np.frombuffer(base64.b64decode(case[key]), dtype=dtype).copy()
+        rl, n = tuple(case["readLengths"]), case["clusters"]
+        reads = ReadSet(dec("bcl", np.uint8), rl)
+        templates = Templates(dec("templates", TEMPLATE_DTYPE), dec("fragments", FRAGMENT_DTYPE), dec("cigars", np.uint32))
+        options = PackOptions(tile=case["tile"], barcode_idx=case["barcodeIdx"], keep_unaligned=case["keepUnaligned"], pf=dec("pf", np.uint8),
+                              xy=dec("xy", np.int32), barcode_sequence=dec("barcodeSequence", np.uint64),
+                              distribution_bin_size=case["distributionBinSize"],
+                              bin_index=[np.array(b, dtype=np.uint32) for b in case["binIndex"]] if case["binIndex"] else None)
+        want = PackedFragments(dec("records", np.uint8).reshape(n, case["recordLength"]), dec("fStrandPos", np.uint64).reshape(n, len(rl)),
+                               dec("initialized", np.uint8).reshape(n, len(rl)), case["recordLength"], tuple(case["readOffset"]),
+                               case["headerLength"], 0)
+        yield reads, templates, options, want, dec("headerMask", np.uint8), rl
+
+
+def test_warp_functions_against_the_golden_vectors(lanes_lib):
+    """tests/golden/pack_fragments.json (made by make_pack_goldens.py from the reference's io::FragmentHeader): no reference build needed"""
+    count = 0
+    for reads, templates, options, want, mask, rl in golden_cases():
+        got = pack_lanes(lanes_lib, reads, templates, options, 32, count % 4)
+        assert_packed_equal(got, want, mask, rl, "golden case %d" % count)
+        count += 1
+    assert count == 5
+
+
+@pytest.mark.gpu
+def test_pack_fragments_golden_vectors(capi):
+    count = 0
+    for reads, templates, options, want, mask, rl in golden_cases():
+        ctx = gpu_context(capi, reads)
+        assert_packed_equal(ctx.pack_fragments(templates, options), want, mask, rl, "GPU, golden case %d" % count)
+        ctx.close()
+        count += 1
+    assert count == 5
+
+
 def test_pack_kernel_compiles_for_the_device():
     """the kernel is part of libisaac_ext.so; its resources as ptxas reports them (no spills, no stack frame beyond the header)"""
     out = subprocess.run(["cuobjdump", "-res-usage", os.path.join(ROOT, "isaac_aligner_b200", "libisaac_ext.so")],
