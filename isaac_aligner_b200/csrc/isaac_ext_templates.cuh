@@ -67,33 +67,8 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
 
     const uint32_t n = ctx->clusterCount, readCount = ctx->reads.readCount;
     const unsigned T = ctx->hostThreads;
-    TemplateContext cx = {TemplateModel(*tls), options->scatterRepeats != 0, options->dodgyAlignmentScore, options->mapqThreshold,
-                          {0.0, 0.0}, 0.0, ctx->logMismatchQ40, readCount};
-    {
-        // RestOfGenomeCorrection (RestOfGenomeCorrection.hh:45-86, Quality.hh:87-91: genome length passes through 'unsigned')
-        uint64_t genomeLength = 0;
-        for (uint64_t l : ctx->contigLength) genomeLength += l;
-        auto correction = [&](unsigned readLength) {
-            const double c = exp(log(2.0) + log(double(unsigned(genomeLength))) - (log(4.0) * double(readLength)));
-            return std::max(c, DBL_MIN);
-        };
-        unsigned total = 0;
-        for (unsigned r = 0; r < readCount; ++r) { cx.rogRead[r] = correction(ctx->reads.readLength[r]); total += ctx->reads.readLength[r]; }
-        cx.rogAll = correction(total);
-    }
-    auto loadCluster = [&](TemplateWorker &w, uint32_t c) {
-        w.clusterId = c;
-        for (unsigned r = 0; r < 2; ++r)
-        {
-            w.frags[r].clear();
-            if (r >= readCount || !st.buildFlags[c]) continue;
-            for (uint64_t i = built.readFragmentBegin[size_t(c) * readCount + r]; i < built.readFragmentBegin[size_t(c) * readCount + r + 1]; ++i)
-            {
-                TFrag t; t.f = built.fragments[i]; t.alignmentScore = -1U; t.cigar = built.cigars + t.f.cigarOffset;
-                w.frags[r].push_back(t);
-            }
-        }
-    };
+    const TemplateContext cx = makeTemplateContext(*tls, *options, ctx->contigLength, readCount, ctx->reads.readLength, ctx->logMismatchQ40);
+    auto loadCluster = [&](TemplateWorker &w, uint32_t c) { loadClusterFragments(w, built, st.buildFlags[c] != 0, readCount, c); };
 
     // ---- plan / rescue / finish, software-pipelined over slices of the tile: while the GPU answers the rescueShadow calls of
     // slice s (one isaac_ext_rescue_shadows batch, on a helper thread), the host threads finish slice s - 1 and plan slice s + 1.
@@ -160,35 +135,19 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
             part.firstCluster = cb + b; part.endCluster = cb + e;
             for (size_t c = cb + b; c < cb + e; ++c)
             {
-                isaac_ext_template_t &o = st.templates.p[c];
-                std::memset(&o, 0, sizeof(o));
-                w.clusterId = uint32_t(c);
                 bool ok = false;
-                if (st.buildFlags[c])
+                const bool hadFragments = st.buildFlags[c] != 0;
+                if (hadFragments)
                 {
                     loadCluster(w, uint32_t(c));
                     w.nextRequest = st.clusterRequestBegin[c + 1];                   // offset of the cluster's first call in the slice's batch
                     ok = w.run();
-                    o.hadFragments = 1;
                 }
                 else
                 {
-                    w.frags[0].clear(); w.frags[1].clear(); w.ownCigars.clear();
-                    for (unsigned r = 0; r < 2; ++r) w.bam[r] = TFrag::unaligned(uint32_t(c) * readCount + std::min(r, readCount - 1), r);
-                    w.bamAlignmentScore = 0; w.bamProperPair = false;
+                    resetToUnaligned(w, uint32_t(c), readCount);
                 }
-                o.built = ok; o.alignmentScore = w.bamAlignmentScore; o.properPair = w.bamProperPair;
-                for (unsigned r = 0; r < readCount; ++r)
-                {
-                    const TFrag &src = w.bam[r];
-                    isaac_ext_fragment_t f = src.f;
-                    f.readId = uint32_t(c) * readCount + r;
-                    o.fragmentAlignmentScore[r] = src.alignmentScore;
-                    const uint32_t *words = w.cigarOf(src);
-                    f.cigarOffset = uint32_t(pool.size());                 // relative to this part, rebased below
-                    if (f.cigarLength && words) pool.insert(pool.end(), words, words + f.cigarLength);
-                    st.fragments.p[c * readCount + r] = f;
-                }
+                storeTemplate(w, ok, hadFragments, uint32_t(c), readCount, st.templates.p[c], st.fragments.p + c * readCount, pool);   // cigarOffset relative to this part, rebased below
             }
         });
     };

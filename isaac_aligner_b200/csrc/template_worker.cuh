@@ -738,4 +738,71 @@ struct TemplateWorker
     }
 };
 
+/// TemplateContext of a run: the template length model, the options and the rest-of-genome correction
+/// (RestOfGenomeCorrection.hh:45-86, Quality.hh:87-91: the genome length passes through 'unsigned')
+inline TemplateContext makeTemplateContext(const isaac_ext_tls_t &tls, const isaac_ext_template_options_t &options,
+                                           const std::vector<uint64_t> &contigLength, const uint32_t readCount,
+                                           const uint32_t (&readLength)[2], const double logMismatchQ40)
+{
+    TemplateContext cx = {TemplateModel(tls), options.scatterRepeats != 0, options.dodgyAlignmentScore, options.mapqThreshold,
+                          {0.0, 0.0}, 0.0, logMismatchQ40, readCount};
+    uint64_t genomeLength = 0;
+    for (uint64_t l : contigLength) genomeLength += l;
+    auto correction = [&](unsigned length) {
+        const double c = exp(log(2.0) + log(double(unsigned(genomeLength))) - (log(4.0) * double(length)));
+        return std::max(c, DBL_MIN);
+    };
+    unsigned total = 0;
+    for (unsigned r = 0; r < readCount; ++r) { cx.rogRead[r] = correction(readLength[r]); total += readLength[r]; }
+    cx.rogAll = correction(total);
+    return cx;
+}
+
+/// the candidate lists of cluster c from the flat result of isaac_ext_build_fragments (getFragments() of the reference's builder)
+inline void loadClusterFragments(TemplateWorker &w, const isaac_ext_build_result_t &built, const bool clusterBuilt,
+                                 const unsigned readCount, const uint32_t c)
+{
+    w.clusterId = c;
+    for (unsigned r = 0; r < 2; ++r)
+    {
+        w.frags[r].clear();
+        if (r >= readCount || !clusterBuilt) continue;
+        for (uint64_t i = built.readFragmentBegin[size_t(c) * readCount + r]; i < built.readFragmentBegin[size_t(c) * readCount + r + 1]; ++i)
+        {
+            TFrag t; t.f = built.fragments[i]; t.alignmentScore = -1U; t.cigar = built.cigars + t.f.cigarOffset;
+            w.frags[r].push_back(t);
+        }
+    }
+}
+
+/// the BamTemplate a finished worker holds, as the flat records of the result: template o, fragments[readCount], their CIGAR
+/// words appended to 'pool' (cigarOffset relative to the pool)
+inline void storeTemplate(const TemplateWorker &w, const bool ok, const bool hadFragments, const uint32_t c, const unsigned readCount,
+                          isaac_ext_template_t &o, isaac_ext_fragment_t *fragments, std::vector<uint32_t> &pool)
+{
+    std::memset(&o, 0, sizeof(o));
+    o.hadFragments = hadFragments;
+    o.built = ok; o.alignmentScore = w.bamAlignmentScore; o.properPair = w.bamProperPair;
+    for (unsigned r = 0; r < readCount; ++r)
+    {
+        const TFrag &src = w.bam[r];
+        isaac_ext_fragment_t f = src.f;
+        f.readId = c * readCount + r;
+        o.fragmentAlignmentScore[r] = src.alignmentScore;
+        const uint32_t *words = w.cigarOf(src);
+        f.cigarOffset = uint32_t(pool.size());
+        if (f.cigarLength && words) pool.insert(pool.end(), words, words + f.cigarLength);
+        fragments[r] = f;
+    }
+}
+
+/// a cluster without candidate fragments: BamTemplate::initialize (MatchSelector.cpp:300-314, 351-358)
+inline void resetToUnaligned(TemplateWorker &w, const uint32_t c, const unsigned readCount)
+{
+    w.clusterId = c;
+    w.frags[0].clear(); w.frags[1].clear(); w.ownCigars.clear();
+    for (unsigned r = 0; r < 2; ++r) w.bam[r] = TFrag::unaligned(c * readCount + std::min(r, readCount - 1), r);
+    w.bamAlignmentScore = 0; w.bamProperPair = false;
+}
+
 } // namespace

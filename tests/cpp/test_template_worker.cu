@@ -1,0 +1,91 @@
+// template_worker.cuh on the CPU: the plan and finish passes of isaac_ext_build_templates (isaac_ext_templates.cuh) around build
+// and rescue results that the CHECKER supplies (tests/test_template_worker.py: oracle_build_fragments / oracle_rescue_shadows of
+// the reference build), so that the host half of the product's TemplateBuilder is compared with the reference's own
+// TemplateBuilder without a GPU.  Host code of an nvcc-compiled shared library, no CUDA call.  TEST CODE, not a product path.
+#include <cstring>
+#include <vector>
+
+#include "../../include/isaac_ext.h"
+#include "../../isaac_aligner_b200/csrc/host_pipeline.cuh"
+using namespace isaac_b200;
+#include "../../isaac_aligner_b200/csrc/template_worker.cuh"
+
+namespace
+{
+double logMismatchQ40() { return std::log(std::pow(10.0, 40.0 / -10.0) / 3.0); }          // Quality.cpp:34-66, as isaac_ext_create computes it
+}
+
+/// plan: the rescueShadow calls every cluster makes, in cluster order.  clusterRequestBegin: clusterCount + 1 offsets.
+extern "C" int template_worker_plan(uint32_t clusterCount, uint32_t readCount, const uint32_t *readLength, uint32_t contigCount,
+                                    const uint64_t *contigLength, const isaac_ext_tls_t *tls, const isaac_ext_template_options_t *options,
+                                    const isaac_ext_build_result_t *built, uint64_t requestCapacity, isaac_ext_rescue_request_t *requestsOut,
+                                    uint64_t *clusterRequestBegin, unsigned threads)
+{
+    const std::vector<uint64_t> lengths(contigLength, contigLength + contigCount);
+    const uint32_t rl[2] = {readLength[0], readCount > 1 ? readLength[1] : 0};
+    const TemplateContext cx = makeTemplateContext(*tls, *options, lengths, readCount, rl, logMismatchQ40());
+    const unsigned parts = partitionCount(threads, clusterCount);
+    std::vector<std::vector<isaac_ext_rescue_request_t>> partRequests(parts);
+    parallelRanges(threads, clusterCount, [&](unsigned t, size_t b, size_t e) {
+        TemplateWorker w(cx);
+        w.planning = true; w.requests = &partRequests[t];
+        for (size_t c = b; c < e; ++c)
+        {
+            const size_t before = partRequests[t].size();
+            if (built->built[c]) { loadClusterFragments(w, *built, true, readCount, uint32_t(c)); w.run(); }
+            clusterRequestBegin[c + 1] = partRequests[t].size() - before;
+        }
+    });
+    uint64_t at = 0;
+    clusterRequestBegin[0] = 0;
+    for (size_t c = 0; c < clusterCount; ++c) { const uint64_t k = clusterRequestBegin[c + 1]; at += k; clusterRequestBegin[c + 1] = at; }
+    if (at > requestCapacity) return ISAAC_EXT_E_CAPACITY;
+    uint64_t o = 0;
+    for (const std::vector<isaac_ext_rescue_request_t> &p : partRequests) for (const isaac_ext_rescue_request_t &q : p) requestsOut[o++] = q;
+    return ISAAC_EXT_OK;
+}
+
+/// finish: the templates, the rescueShadow calls answered from 'rescued' in the order plan recorded them
+extern "C" int template_worker_finish(uint32_t clusterCount, uint32_t readCount, const uint32_t *readLength, uint32_t contigCount,
+                                      const uint64_t *contigLength, const isaac_ext_tls_t *tls, const isaac_ext_template_options_t *options,
+                                      const isaac_ext_build_result_t *built, const isaac_ext_rescue_result_t *rescued,
+                                      const uint64_t *clusterRequestBegin, isaac_ext_template_t *templatesOut,
+                                      isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut, uint64_t *cigarWordsOut,
+                                      unsigned threads)
+{
+    const std::vector<uint64_t> lengths(contigLength, contigLength + contigCount);
+    const uint32_t rl[2] = {readLength[0], readCount > 1 ? readLength[1] : 0};
+    const TemplateContext cx = makeTemplateContext(*tls, *options, lengths, readCount, rl, logMismatchQ40());
+    const unsigned parts = partitionCount(threads, clusterCount);
+    std::vector<std::vector<uint32_t>> pools(parts);
+    std::vector<size_t> partBegin(parts, clusterCount), partEnd(parts, clusterCount);
+    parallelRanges(threads, clusterCount, [&](unsigned t, size_t b, size_t e) {
+        TemplateWorker w(cx);
+        w.planning = false; w.rescueResult = rescued;
+        partBegin[t] = b; partEnd[t] = e;
+        for (size_t c = b; c < e; ++c)
+        {
+            bool ok = false;
+            const bool hadFragments = built->built[c] != 0;
+            if (hadFragments)
+            {
+                loadClusterFragments(w, *built, true, readCount, uint32_t(c));
+                w.nextRequest = clusterRequestBegin[c];
+                ok = w.run();
+            }
+            else resetToUnaligned(w, uint32_t(c), readCount);
+            storeTemplate(w, ok, hadFragments, uint32_t(c), readCount, templatesOut[c], fragmentsOut + c * readCount, pools[t]);
+        }
+    });
+    uint64_t words = 0;
+    for (unsigned t = 0; t < parts; ++t)
+    {
+        if (words + pools[t].size() > cigarCapacity) return ISAAC_EXT_E_CAPACITY;
+        if (!pools[t].empty()) std::memcpy(cigarsOut + words, pools[t].data(), pools[t].size() * sizeof(uint32_t));
+        for (size_t c = partBegin[t]; c < partEnd[t]; ++c)
+            for (unsigned r = 0; r < readCount; ++r) fragmentsOut[c * readCount + r].cigarOffset += uint32_t(words);
+        words += pools[t].size();
+    }
+    *cigarWordsOut = words;
+    return ISAAC_EXT_OK;
+}

@@ -1,0 +1,96 @@
+"""The host half of isaac_ext_build_templates on the CPU: csrc/template_worker.cuh (pair selection, rescue decisions, mapping
+scores: TemplateBuilder.cpp:97-1089 restated) driven by tests/cpp/test_template_worker.cu the way isaac_ext_templates.cuh drives
+it -- plan, ONE batch of rescueShadow calls, finish -- with the checker standing in for the two GPU batch calls
+(oracle_build_fragments / oracle_rescue_shadows of the reference build).  The templates must be the reference's own
+TemplateBuilder's (oracle_build_templates), bit for bit.  No GPU involved; the GPU tests (test_gpu_templates.py) check the same
+code behind the real kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from common_build import build_workload
+from isaac_aligner_b200.batch import (DODGY_ALIGNMENT_SCORE_UNALIGNED, DODGY_ALIGNMENT_SCORE_UNKNOWN, RESCUE_REQUEST_DTYPE, TEMPLATE_DTYPE,
+                                      BuildResult, RescueResult, Templates, Tls, TemplateOptions)
+from isaac_aligner_b200.types import FRAGMENT_DTYPE, Config
+from test_gpu_templates import assert_templates_equal
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.exists(oracle_lib.REF_SO) and not os.path.isdir("/root/reference/src/c++"),
+                                reason="the TemplateBuilder checker is the reference build only")
+
+
+@pytest.fixture(scope="module")
+def worker_lib():
+    so = os.path.join(ROOT, "build", "libtest_template_worker.so")
+    src = os.path.join(ROOT, "tests", "cpp", "test_template_worker.cu")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-O2", "--extended-lambda", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-cudart", "shared", "-shared", "-Xcompiler", "-fPIC", src, "-o", so])
+    return ctypes.CDLL(so)
+
+
+def p(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None and a.size else None
+
+
+def flat_view(flat, cls):
+    """FlatFragments (the checker's result) as the C struct the worker reads"""
+    return cls(flat.fragments.ctypes.data if flat.fragments.size else None, flat.begin.ctypes.data,
+               flat.cigars.ctypes.data if flat.cigars.size else None, flat.flags.ctypes.data, flat.fragments.size, flat.cigars.size)
+
+
+def worker_templates(lib, ref, genome, reads, config, mb, tls, options, threads=3):
+    g = oracle_lib.GenomeHolder(genome)
+    n, rc = reads.cluster_count, reads.read_count
+    built = oracle_lib.build_fragments(ref, g, reads, config, mb, threads=4)
+    built_c = flat_view(built, BuildResult)
+    read_length = np.array(list(reads.read_lengths) + [0] * (2 - rc), dtype=np.uint32)
+    contig_length = np.array([len(c) for c in genome], dtype=np.uint64)
+    requests = np.zeros(4 * n + 16, dtype=RESCUE_REQUEST_DTYPE)
+    request_begin = np.zeros(n + 1, dtype=np.uint64)
+    head = [ctypes.c_uint32(n), ctypes.c_uint32(rc), p(read_length), ctypes.c_uint32(len(contig_length)), p(contig_length),
+            ctypes.byref(tls), ctypes.byref(options), ctypes.byref(built_c)]
+    assert lib.template_worker_plan(*head, ctypes.c_uint64(requests.size), p(requests), p(request_begin), ctypes.c_uint(threads)) == 0
+    requests = requests[:int(request_begin[-1])].copy()
+    rescued = oracle_lib.rescue_shadows(ref, g, reads, config, tls, requests, threads=4, fragments_per_request=128)
+    rescued_c = flat_view(rescued, RescueResult)
+    templates = np.zeros(n, dtype=TEMPLATE_DTYPE)
+    fragments = np.zeros(n * rc, dtype=FRAGMENT_DTYPE)
+    cigars = np.zeros(64 * n + 1024, dtype=np.uint32)
+    words = ctypes.c_uint64()
+    assert lib.template_worker_finish(*head, ctypes.byref(rescued_c), p(request_begin), p(templates), p(fragments),
+                                      ctypes.c_uint64(cigars.size), p(cigars), ctypes.byref(words), ctypes.c_uint(threads)) == 0
+    return Templates(templates, fragments, cigars[:words.value].copy(), len(requests)), g
+
+
+@pytest.mark.parametrize("L,seed,options", [
+    (100, 41, dict()),
+    (150, 42, dict(mapq_threshold=10)),
+    (75, 43, dict(scatter_repeats=True, dodgy=DODGY_ALIGNMENT_SCORE_UNKNOWN)),
+    (100, 44, dict(dodgy=DODGY_ALIGNMENT_SCORE_UNALIGNED, mapq_threshold=3)),
+])
+def test_plan_and_finish_give_the_references_templates(worker_lib, L, seed, options):
+    ref = oracle_lib.reference()
+    genome, sim, reads, mb = build_workload(n_pairs=1200, L=L, seed=seed)
+    config = Config.default(max_read_length=2 * L)
+    tls, opt = Tls.make(), TemplateOptions.make(**options)
+    got, g = worker_templates(worker_lib, ref, genome, reads, config, mb, tls, opt)
+    want = oracle_lib.build_templates(ref, g, reads, config, mb, tls, opt, threads=4)
+    assert_templates_equal(got, want, "template worker on the CPU, L %d" % L)
+    for i in np.nonzero(want.fragments["cigarLength"])[0]:
+        assert np.array_equal(got.cigar(i), want.cigar(i)), i
+    assert got.rescue_requests > 0 and int(got.templates["built"].sum()) > 0
+
+
+def test_thread_count_changes_nothing(worker_lib):
+    ref = oracle_lib.reference()
+    genome, sim, reads, mb = build_workload(n_pairs=700, L=100, seed=47)
+    config = Config.default(max_read_length=200)
+    tls, opt = Tls.make(), TemplateOptions.make()
+    a, _ = worker_templates(worker_lib, ref, genome, reads, config, mb, tls, opt, threads=1)
+    b, _ = worker_templates(worker_lib, ref, genome, reads, config, mb, tls, opt, threads=5)
+    assert_templates_equal(a, b, "1 thread against 5")
