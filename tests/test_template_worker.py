@@ -94,3 +94,21 @@ def test_thread_count_changes_nothing(worker_lib):
     a, _ = worker_templates(worker_lib, ref, genome, reads, config, mb, tls, opt, threads=1)
     b, _ = worker_templates(worker_lib, ref, genome, reads, config, mb, tls, opt, threads=5)
     assert_templates_equal(a, b, "1 thread against 5")
+
+
+def test_single_ended_templates(worker_lib):
+    """single-ended data: pickBestFragment (TemplateBuilder.cpp:1035-1058), no rescueShadow call at all"""
+    from test_gpu_templates import single_ended
+    ref = oracle_lib.reference()
+    genome, sim, reads, mb = build_workload(n_pairs=800, L=100, seed=51)
+    reads1, mb1 = single_ended(genome, sim, reads, mb)
+    config = Config.default(max_read_length=200)
+    tls, opt = Tls.make(), TemplateOptions.make(mapq_threshold=4)
+    got, g = worker_templates(worker_lib, ref, genome, reads1, config, mb1, tls, opt)
+    want = oracle_lib.build_templates(ref, g, reads1, config, mb1, tls, opt, threads=4)
+    for name in ("hadFragments", "built", "properPair", "alignmentScore"):
+        assert np.array_equal(got.templates[name], want.templates[name]), name
+    assert np.array_equal(got.templates["fragmentAlignmentScore"][:, 0], want.templates["fragmentAlignmentScore"][:, 0])
+    for name in ("position", "contigId", "observedLength", "editDistance", "cigarLength", "reverse", "mismatchCount"):
+        assert np.array_equal(got.fragments[name], want.fragments[name]), name
+    assert got.rescue_requests == 0
