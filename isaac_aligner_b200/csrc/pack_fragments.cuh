@@ -8,7 +8,7 @@
 // template in, recordLength (1644 B for 2 x 150) out.
 //
 // Everything but the warp plumbing is ISAAC_HD and takes (lane, lanes): tests/cpp/test_pack_fragments.cpp runs the same functions
-// lane after lane on the CPU against the reference's own io::FragmentHeader (tests/test_tile_pack_fragments.py).
+// lane after lane on the CPU against the reference's own io::FragmentHeader (tests/test_tile_write_bin_records.py).
 #pragma once
 #include <cstddef>
 #include <cstdint>

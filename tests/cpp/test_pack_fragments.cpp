@@ -1,5 +1,5 @@
 // pack_fragments.cuh on the CPU: the functions the warps of packFragmentsKernel run, called lane after lane with the two
-// phases of a record separated the way __syncwarp separates them.  Built as a shared library by tests/test_tile_pack_fragments.py,
+// phases of a record separated the way __syncwarp separates them.  Built as a shared library by tests/test_tile_write_bin_records.py,
 // which compares the records with the reference's own io::FragmentHeader (oracle/_ref).  TEST CODE, not a product path.
 #include <cstdlib>
 #include <cstring>

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle_lib                                                       # noqa: E402
-import test_tile_pack_fragments as T                                    # noqa: E402
+import test_tile_write_bin_records as T                                    # noqa: E402
 from isaac_aligner_b200.types import ReadSet                            # noqa: E402
 
 OUT = os.path.join(HERE, "pack_fragments.json")
