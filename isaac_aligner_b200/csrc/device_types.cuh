@@ -5,6 +5,15 @@
 #include <cuda_runtime.h>
 #include "../../include/isaac_ext.h"
 
+// Accessors the CPU harnesses of tests/cpp run too (the end clippers, tests/cpp/test_clip_host.cu): device code is unchanged,
+// __ldg is the read-only load only where there is a device
+#define ISAAC_VIEW_FN __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define ISAAC_VIEW_LOAD(p) __ldg(p)
+#else
+#define ISAAC_VIEW_LOAD(p) (*(p))
+#endif
+
 namespace isaac_b200
 {
 
@@ -24,10 +33,10 @@ struct ReferenceView
     uint32_t contigCount;
     uint64_t totalBases;             // padded size of the packed arrays in bases
 
-    __device__ __forceinline__ unsigned code(uint64_t g) const
+    ISAAC_VIEW_FN unsigned code(uint64_t g) const
     {
-        const unsigned c = (__ldg(bases2 + (g >> 4)) >> ((unsigned(g) & 15u) * 2u)) & 3u;
-        const unsigned n = (__ldg(nmask + (g >> 5)) >> (unsigned(g) & 31u)) & 1u;
+        const unsigned c = (ISAAC_VIEW_LOAD(bases2 + (g >> 4)) >> ((unsigned(g) & 15u) * 2u)) & 3u;
+        const unsigned n = (ISAAC_VIEW_LOAD(nmask + (g >> 5)) >> (unsigned(g) & 31u)) & 1u;
         return n ? unsigned(CODE_REF_N) : c;
     }
 };
@@ -55,7 +64,7 @@ struct ReadSetView
     uint32_t firstCycle[2];
     uint32_t readTotal;              // clusterCount * readCount
 
-    __device__ __forceinline__ unsigned length(unsigned readId) const { return readLength[readId % readCount]; }
+    ISAAC_VIEW_FN unsigned length(unsigned readId) const { return readLength[readId % readCount]; }
     __device__ __forceinline__ const uint64_t *strandCodes(unsigned readId, bool reverse) const
     {
         return codes4 + (size_t(readId) * 2 + (reverse ? 1u : 0u)) * wordsC;
@@ -72,7 +81,7 @@ struct ReadSetView
     __device__ __forceinline__ unsigned codesClamp() const { return (wordsC - 2u) * 16u; }
 
     /// base code and quality of strand-order position i
-    __device__ __forceinline__ unsigned code(unsigned readId, unsigned L, bool reverse, unsigned i, unsigned &q) const
+    ISAAC_VIEW_FN unsigned code(unsigned readId, unsigned L, bool reverse, unsigned i, unsigned &q) const
     {
         const unsigned f = reverse ? L - 1 - i : i;
         q = quality[size_t(readId) * qualityStride + f];

@@ -45,11 +45,11 @@ struct ClipFragment
     unsigned L;
 };
 
-__device__ __forceinline__ bool clipIsAligned(const ClipFragment &x) { return x.n != 0; }
+ISAAC_VIEW_FN bool clipIsAligned(const ClipFragment &x) { return x.n != 0; }
 
 /// clipMismatches<5> (Alignment.hh:55-87) over strand positions seq0, seq0 + step, ... (count of them) against reference
 /// bases g0, g0 + step, ... (refCount of them)
-__device__ __forceinline__ void clipMismatches(const ReferenceView &ref, const ReadSetView &reads, const ClipFragment &x,
+ISAAC_VIEW_FN void clipMismatches(const ReferenceView &ref, const ReadSetView &reads, const ClipFragment &x,
                                                long seq0, long g0, int step, unsigned count, uint64_t refCount,
                                                unsigned &clippedBases, unsigned &clippedEdits)
 {
@@ -72,7 +72,7 @@ __device__ __forceinline__ void clipMismatches(const ReferenceView &ref, const R
 }
 
 /// SemialignedEndsClipper::clipLeftSide (:32-93)
-__device__ __forceinline__ bool clipLeftSide(const ReferenceView &ref, const ReadSetView &reads, ClipFragment &x)
+ISAAC_VIEW_FN bool clipLeftSide(const ReferenceView &ref, const ReadSetView &reads, ClipFragment &x)
 {
     unsigned first = 0;
     uint32_t op = x.cigar[0];
@@ -107,7 +107,7 @@ __device__ __forceinline__ bool clipLeftSide(const ReferenceView &ref, const Rea
 }
 
 /// SemialignedEndsClipper::clipRightSide (:95-157)
-__device__ __forceinline__ bool clipRightSide(const ReferenceView &ref, const ReadSetView &reads, ClipFragment &x)
+ISAAC_VIEW_FN bool clipRightSide(const ReferenceView &ref, const ReadSetView &reads, ClipFragment &x)
 {
     unsigned last = x.n - 1;
     uint32_t op = x.cigar[last];
@@ -137,7 +137,7 @@ __device__ __forceinline__ bool clipRightSide(const ReferenceView &ref, const Re
 }
 
 /// OverlappingEndsClipper::clip (:45-180)
-__device__ __forceinline__ void clipOverlappingEnds(const ReferenceView &ref, const ReadSetView &reads, ClipFragment &r1, ClipFragment &r2)
+ISAAC_VIEW_FN void clipOverlappingEnds(const ReferenceView &ref, const ReadSetView &reads, ClipFragment &r1, ClipFragment &r2)
 {
     if (!clipIsAligned(r1) || !clipIsAligned(r2) || r1.f.gapCount || r2.f.gapCount) return;
     // (:62-66 compares r1.contigId with itself: chimeric pairs are NOT skipped)
@@ -216,56 +216,64 @@ __device__ __forceinline__ void clipOverlappingEnds(const ReferenceView &ref, co
     }
 }
 
-/// One cluster per thread.  fragments[cluster * readCount + r] / cigarsIn + cigarOffset in; the record and its (possibly
-/// longer) CIGAR out at cigarsOut + outOffset[...], where the caller left room for cigarLength + 4 words per fragment.
+/// The end clippers on the template of cluster c (MatchSelector.cpp:336-346).  fragments[c * readCount + r] / cigarsIn + cigarOffset
+/// in; the record and its (possibly longer) CIGAR out at cigarsOut + cigarOffset + 4 * (c * readCount + r), where the caller left room
+/// for cigarLength + 4 words per fragment.  \return false, nothing written, when a CIGAR does not fit the clippers' scratch.
+ISAAC_VIEW_FN bool clipTemplateEndsOfCluster(const ReferenceView &ref, const ReadSetView &reads, const uint32_t c, const uint32_t clipFlags,
+                                             const isaac_ext_template_t *__restrict__ templates, isaac_ext_fragment_t *__restrict__ fragments,
+                                             const uint32_t *__restrict__ cigarsIn, uint32_t *__restrict__ cigarsOut)
+{
+    const unsigned readCount = reads.readCount;
+    ClipFragment x[2];
+    bool tooLong = false;
+    for (unsigned r = 0; r < readCount; ++r)
+    {
+        const size_t i = size_t(c) * readCount + r;
+        x[r].f = fragments[i];
+        x[r].n = x[r].f.cigarLength;
+        x[r].L = reads.length(x[r].f.readId);
+        if (x[r].n + 4 > CLIP_CIGAR_CAP) { tooLong = true; x[r].n = 0; continue; }
+        for (unsigned k = 0; k < x[r].n; ++k) x[r].cigar[k] = cigarsIn[x[r].f.cigarOffset + k];
+    }
+    if (tooLong) return false;
+    if (templates[c].built)
+    {
+        if (clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED)                                           // SemialignedEndsClipper::clip (:183-205)
+        {
+            for (unsigned k = 0; k < readCount; ++k)
+            {
+                if (!clipIsAligned(x[k])) continue;
+                bool changed = clipLeftSide(ref, reads, x[k]);
+                if (clipRightSide(ref, reads, x[k])) changed = true;
+                if (changed && 2 == readCount)
+                {
+                    ClipFragment &mate = x[1 - k];
+                    if (!clipIsAligned(mate)) { mate.f.position = x[k].f.position; break; }
+                }
+            }
+        }
+        if ((clipFlags & ISAAC_EXT_CLIP_OVERLAPPING) && 2 == readCount) clipOverlappingEnds(ref, reads, x[0], x[1]);
+    }
+    for (unsigned r = 0; r < readCount; ++r)
+    {
+        const size_t i = size_t(c) * readCount + r;
+        const uint32_t out = x[r].f.cigarOffset + 4u * uint32_t(i);
+        for (unsigned k = 0; k < x[r].n; ++k) cigarsOut[out + k] = x[r].cigar[k];
+        x[r].f.cigarOffset = x[r].n ? out : x[r].f.cigarOffset;
+        x[r].f.cigarLength = uint16_t(x[r].n);
+        fragments[i] = x[r].f;
+    }
+    return true;
+}
+
+/// One cluster per thread.
 __global__ void clipTemplateEndsKernel(const ReferenceView ref, const ReadSetView reads, const uint32_t clusterCount,
                                        const uint32_t clipFlags, const isaac_ext_template_t *__restrict__ templates,
                                        isaac_ext_fragment_t *__restrict__ fragments, const uint32_t *__restrict__ cigarsIn,
                                        uint32_t *__restrict__ cigarsOut, uint32_t *__restrict__ errorFlag)
 {
-    const unsigned readCount = reads.readCount;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < clusterCount; c += gridDim.x * blockDim.x)
-    {
-        ClipFragment x[2];
-        bool tooLong = false;
-        for (unsigned r = 0; r < readCount; ++r)
-        {
-            const size_t i = size_t(c) * readCount + r;
-            x[r].f = fragments[i];
-            x[r].n = x[r].f.cigarLength;
-            x[r].L = reads.length(x[r].f.readId);
-            if (x[r].n + 4 > CLIP_CIGAR_CAP) { tooLong = true; x[r].n = 0; continue; }
-            for (unsigned k = 0; k < x[r].n; ++k) x[r].cigar[k] = cigarsIn[x[r].f.cigarOffset + k];
-        }
-        if (tooLong) { atomicOr(errorFlag, 4u); continue; }
-        if (templates[c].built)
-        {
-            if (clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED)                                           // SemialignedEndsClipper::clip (:183-205)
-            {
-                for (unsigned k = 0; k < readCount; ++k)
-                {
-                    if (!clipIsAligned(x[k])) continue;
-                    bool changed = clipLeftSide(ref, reads, x[k]);
-                    if (clipRightSide(ref, reads, x[k])) changed = true;
-                    if (changed && 2 == readCount)
-                    {
-                        ClipFragment &mate = x[1 - k];
-                        if (!clipIsAligned(mate)) { mate.f.position = x[k].f.position; break; }
-                    }
-                }
-            }
-            if ((clipFlags & ISAAC_EXT_CLIP_OVERLAPPING) && 2 == readCount) clipOverlappingEnds(ref, reads, x[0], x[1]);
-        }
-        for (unsigned r = 0; r < readCount; ++r)
-        {
-            const size_t i = size_t(c) * readCount + r;
-            const uint32_t out = x[r].f.cigarOffset + 4u * uint32_t(i);
-            for (unsigned k = 0; k < x[r].n; ++k) cigarsOut[out + k] = x[r].cigar[k];
-            x[r].f.cigarOffset = x[r].n ? out : x[r].f.cigarOffset;
-            x[r].f.cigarLength = uint16_t(x[r].n);
-            fragments[i] = x[r].f;
-        }
-    }
+        if (!clipTemplateEndsOfCluster(ref, reads, c, clipFlags, templates, fragments, cigarsIn, cigarsOut)) atomicOr(errorFlag, 4u);
 }
 
 } // namespace isaac_b200

@@ -22,7 +22,7 @@ struct SwScores
     int init;                         // -32768 + open (BandedSmithWaterman.cpp:44)
 };
 
-__device__ __forceinline__ uint32_t cigarWord(uint32_t length, uint32_t op) { return (length << 4) | op; }
+__host__ __device__ __forceinline__ uint32_t cigarWord(uint32_t length, uint32_t op) { return (length << 4) | op; }
 
 /// \param src       src.q(i) = code of query base i, src.d(k) = code of database base k (k < L + 15)
 /// \param ops       thread-local buffer receiving the CIGAR in final (head first) order
