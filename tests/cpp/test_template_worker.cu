@@ -9,6 +9,7 @@
 #include "../../isaac_aligner_b200/csrc/host_pipeline.cuh"
 using namespace isaac_b200;
 #include "../../isaac_aligner_b200/csrc/template_worker.cuh"
+#include "../../isaac_aligner_b200/csrc/plan_device.cuh"
 
 namespace
 {
@@ -88,4 +89,23 @@ extern "C" int template_worker_finish(uint32_t clusterCount, uint32_t readCount,
     }
     *cigarWordsOut = words;
     return ISAAC_EXT_OK;
+}
+
+/// the same request list from plan_device.cuh (the libm-free plan pass written for device code), cluster after cluster
+extern "C" int plan_device_requests(uint32_t clusterCount, uint32_t readCount, const isaac_ext_tls_t *tls, const isaac_ext_template_options_t *options,
+                                    const isaac_ext_build_result_t *built, uint64_t requestCapacity, isaac_ext_rescue_request_t *requestsOut,
+                                    uint64_t *clusterRequestBegin)
+{
+    PlanView v;
+    v.fragments = built->fragments; v.readFragmentBegin = built->readFragmentBegin; v.built = built->built; v.readCount = readCount;
+    v.tlsMax = tls->max; v.bestModel[0] = tls->bestModel[0]; v.bestModel[1] = tls->bestModel[1]; v.scatterRepeats = options->scatterRepeats;
+    uint64_t at = 0;
+    clusterRequestBegin[0] = 0;
+    for (uint32_t c = 0; c < clusterCount; ++c)
+    {
+        const unsigned room = at < requestCapacity ? unsigned(std::min<uint64_t>(requestCapacity - at, 1u << 30)) : 0u;
+        at += planClusterRequests(v, c, requestsOut + at, room);
+        clusterRequestBegin[c + 1] = at;
+    }
+    return at > requestCapacity ? ISAAC_EXT_E_CAPACITY : ISAAC_EXT_OK;
 }

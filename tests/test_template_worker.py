@@ -112,3 +112,85 @@ def test_single_ended_templates(worker_lib):
     for name in ("position", "contigId", "observedLength", "editDistance", "cigarLength", "reverse", "mismatchCount"):
         assert np.array_equal(got.fragments[name], want.fragments[name]), name
     assert got.rescue_requests == 0
+
+
+@pytest.mark.parametrize("L,seed,scatter,kw", [(100, 71, False, {}), (100, 72, True, {"repeat_rate": 0.2, "neighbor_rate": 0.4}),
+                                               (150, 73, True, {"indel_rate": 1e-2}), (75, 74, False, {"neighbor_rate": 0.6})])
+def test_device_plan_pass_records_the_same_requests(worker_lib, L, seed, scatter, kw):
+    """csrc/plan_device.cuh (the plan pass without libm and without std::vector, for a one-thread-per-cluster kernel) against the
+    planning mode of template_worker.cuh: the same rescueShadow calls in the same order, byte for byte"""
+    ref = oracle_lib.reference()
+    genome, sim, reads, mb = build_workload(n_pairs=1500, L=L, seed=seed, **kw)
+    config = Config.default(max_read_length=2 * L)
+    g = oracle_lib.GenomeHolder(genome)
+    built = oracle_lib.build_fragments(ref, g, reads, config, mb, threads=4)
+    built_c = flat_view(built, BuildResult)
+    n, rc = reads.cluster_count, reads.read_count
+    read_length = np.array(list(reads.read_lengths), dtype=np.uint32)
+    contig_length = np.array([len(c) for c in genome], dtype=np.uint64)
+    for tls in (Tls.make(), Tls.make(mn=100, mx=300, median=200, low=20, high=20), Tls.make(mn=0xFFFFFFFF, mx=0xFFFFFFFF, median=0xFFFFFFFF, m0=8, m1=8)):
+        options = TemplateOptions.make(scatter_repeats=scatter)
+        want, want_begin = np.zeros(4 * n + 16, dtype=RESCUE_REQUEST_DTYPE), np.zeros(n + 1, dtype=np.uint64)
+        assert worker_lib.template_worker_plan(ctypes.c_uint32(n), ctypes.c_uint32(rc), p(read_length), ctypes.c_uint32(len(contig_length)),
+                                               p(contig_length), ctypes.byref(tls), ctypes.byref(options), ctypes.byref(built_c),
+                                               ctypes.c_uint64(want.size), p(want), p(want_begin), ctypes.c_uint(3)) == 0
+        got, got_begin = np.zeros(4 * n + 16, dtype=RESCUE_REQUEST_DTYPE), np.zeros(n + 1, dtype=np.uint64)
+        assert worker_lib.plan_device_requests(ctypes.c_uint32(n), ctypes.c_uint32(rc), ctypes.byref(tls), ctypes.byref(options),
+                                               ctypes.byref(built_c), ctypes.c_uint64(got.size), p(got), p(got_begin)) == 0
+        assert np.array_equal(got_begin, want_begin)
+        total = int(want_begin[-1])
+        assert got[:total].tobytes() == want[:total].tobytes()
+    assert total >= 0 and int(want_begin[-1]) == total
+
+
+def test_plan_device_compiles_for_the_device():
+    """plan_device.cuh through nvcc for sm_100a inside a one-thread-per-cluster kernel (device code generation only, no GPU needed)"""
+    src = os.path.join(ROOT, "build", "plan_device_kernel.cu")
+    os.makedirs(os.path.dirname(src), exist_ok=True)
+    with open(src, "w") as f:
+        f.write('#include "../isaac_aligner_b200/csrc/plan_device.cuh"\n'
+                '__global__ void planKernel(const isaac_b200::PlanView v, unsigned clusters, const unsigned long long *begin, isaac_ext_rescue_request_t *out, unsigned *counts)\n'
+                '{\n'
+                '    const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;\n'
+                '    if (c < clusters) counts[c] = isaac_b200::planClusterRequests(v, c, out + begin[c], unsigned(begin[c + 1] - begin[c]));\n'
+                '}\n')
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--extended-lambda",
+                           "-Xptxas", "-v", "-c", src, "-o", os.path.join(ROOT, "build", "plan_device_kernel.o")])
+
+
+def test_device_plan_pass_scatter_repeats_on_hand_made_ties(worker_lib):
+    """equally good pairs of different template lengths (a read placed on several copies of a tandem repeat): --scatter-repeats picks
+    the pair by cluster id, which changes the best template length the requests carry; equally good orphans likewise"""
+    from isaac_aligner_b200.batch import FlatFragments
+    from test_template_worker_goldens import fragment
+    n = 12
+    frags, begin, rng = [], [0], np.random.default_rng(5)
+    for c in range(n):
+        copies = 1 + c % 4
+        r1 = [fragment(0, 1000, 100, 0, 0, 0, 1, -9.0, 2)]
+        r2 = [fragment(0, 1200 + 37 * k, 100, 1, 1, 0, 1, -11.0 + (1e-9 if k % 2 else 0.0), 1) for k in range(copies)]
+        if c % 5 == 4:
+            r1.append(fragment(0, 1003, 100, 0, 0, 0, 1, -9.0, 0))     # a second, equally good placement of read 1
+        if c == 7:
+            r2 = []                                                      # orphan only: TemplateBuilder::rescueShadow
+        for f in r1 + r2:
+            f["readId"], f["editDistance"], f["smithWatermanScore"] = c * 2 + int(f["readIndex"]), 1 + int(rng.integers(0, 2)), 3
+        frags += r1 + r2
+        begin += [begin[-1] + len(r1), begin[-1] + len(r1) + len(r2)]
+    built = FlatFragments(np.array(frags, dtype=FRAGMENT_DTYPE), np.array(begin, dtype=np.uint64), np.full(8, 1600, dtype=np.uint32), np.ones(n, dtype=np.uint8))
+    built_c = flat_view(built, BuildResult)
+    read_length, contig_length = np.array([100, 100], dtype=np.uint32), np.array([100000], dtype=np.uint64)
+    lists = []
+    for scatter in (False, True):
+        tls, options = Tls.make(), TemplateOptions.make(scatter_repeats=scatter)
+        want, want_begin = np.zeros(256, dtype=RESCUE_REQUEST_DTYPE), np.zeros(n + 1, dtype=np.uint64)
+        assert worker_lib.template_worker_plan(ctypes.c_uint32(n), ctypes.c_uint32(2), p(read_length), ctypes.c_uint32(1), p(contig_length),
+                                               ctypes.byref(tls), ctypes.byref(options), ctypes.byref(built_c), ctypes.c_uint64(want.size),
+                                               p(want), p(want_begin), ctypes.c_uint(1)) == 0
+        got, got_begin = np.zeros(256, dtype=RESCUE_REQUEST_DTYPE), np.zeros(n + 1, dtype=np.uint64)
+        assert worker_lib.plan_device_requests(ctypes.c_uint32(n), ctypes.c_uint32(2), ctypes.byref(tls), ctypes.byref(options), ctypes.byref(built_c),
+                                               ctypes.c_uint64(got.size), p(got), p(got_begin)) == 0
+        total = int(want_begin[-1])
+        assert total > n and np.array_equal(got_begin, want_begin) and got[:total].tobytes() == want[:total].tobytes(), scatter
+        lists.append(want[:total].copy())
+    assert lists[0].tobytes() != lists[1].tobytes()                      # the option does change the requests of this tile
