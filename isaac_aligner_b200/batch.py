@@ -155,6 +155,24 @@ class PackResultC(ctypes.Structure):
                 ("kernelMs", ctypes.c_float), ("pad", ctypes.c_uint32)]
 
 
+# io::FragmentHeader as g++ lays it out on x86-64 (Fragment.hh:260-404), 112 bytes; flags: bit 0 paired, 1 unmapped, 2 mateUnmapped,
+# 3 reverse, 4 mateReverse, 5 firstRead, 6 secondRead, 7 failFilter, 8 properPair, 9 duplicate
+FRAGMENT_HEADER_DTYPE = np.dtype([
+    ("bamTlen", "<i4"), ("observedLength", "<u4"), ("fStrandPosition", "<u8"), ("lowClipped", "<u2"), ("highClipped", "<u2"),
+    ("alignmentScore", "<u2"), ("templateAlignmentScore", "<u2"), ("mateFStrandPosition", "<u8"), ("readLength", "<u2"),
+    ("cigarLength", "<u2"), ("gapCount", "<u2"), ("editDistance", "<u2"), ("flags", "<u2"), ("pad0", "<u2", (3,)), ("tile", "<u8"),
+    ("barcode", "<u8"), ("barcodeSequence", "<u8"), ("clusterId", "<u8"), ("clusterX", "<i4"), ("clusterY", "<i4"),
+    ("duplicateClusterRank", "<u8"), ("mateAnchor", "<u8"), ("mateStorageBin", "<u4"), ("pad1", "<u4")])
+assert FRAGMENT_HEADER_DTYPE.itemsize == 112
+NO_MATCH_POSITION = 0x7FFFFF << 41                                            # ReferencePosition(NoMatch).getValue()
+
+
+def reference_position(value):
+    """ReferencePosition::getValue() -> (contigId, position) (ReferencePosition.hh:68-78,105-111); contig 0x7FFFFE + 1 = no match"""
+    value = np.asarray(value, dtype=np.uint64)
+    return ((value >> np.uint64(41)).astype(np.int64) - 1), ((value >> np.uint64(1)) & np.uint64((1 << 40) - 1)).astype(np.int64)
+
+
 class PackedFragments:
     """matchSelector::FragmentBuffer of a tile: records [clusters, recordLength] bytes, f_strand_pos / initialized
     [clusters, readCount]; the record of (cluster, readIndex) starts at records[cluster, read_offset[readIndex]].
@@ -165,6 +183,11 @@ class PackedFragments:
         self.records, self.f_strand_pos, self.initialized = records, f_strand_pos, initialized
         self.record_length, self.read_offset, self.header_length, self.stored = record_length, tuple(read_offset), header_length, stored
         self.record_offset = record_offset
+
+    def headers(self, read_index):
+        """the io::FragmentHeader of every cluster's record of one read (FragmentBuffer layout) as a structured array"""
+        begin = self.read_offset[read_index]
+        return np.ascontiguousarray(self.records[:, begin:begin + self.header_length]).view(FRAGMENT_HEADER_DTYPE).reshape(-1)
 
     def compacted(self):
         """the compact form of a FragmentBuffer-layout result: every initialised record cut to FragmentHeader::getTotalLength()

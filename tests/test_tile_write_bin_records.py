@@ -310,6 +310,63 @@ def test_pack_fragments_golden_vectors(capi):
     assert count == 5
 
 
+def assert_round_trip(packed, reads, templates, options):
+    """size-independent properties of a FragmentBuffer-layout result, no checker involved: every stored record decodes back to the
+    template it was made from (positions, flags, scores, lengths), its bases are the read's BCL bytes (reverse-complemented back
+    for reverse fragments), its CIGAR words the fragment's, and everything behind them is zero"""
+    from isaac_aligner_b200.batch import NO_MATCH_POSITION, reference_position
+    n, rc = reads.cluster_count, reads.read_count
+    t, f = templates.templates, templates.fragments.reshape(n, rc)
+    stored = (t["built"] != 0) | bool(options.c.keepUnaligned)
+    assert np.array_equal(packed.initialized != 0, np.repeat(stored[:, None], rc, axis=1))
+    assert packed.stored == int(stored.sum()) * rc
+    offsets = np.concatenate([[0], np.cumsum(reads.read_lengths)])
+    for r in range(rc):
+        h, fr, L = packed.headers(r)[stored], f[stored, r], reads.read_lengths[r]
+        aligned = fr["cigarLength"] != 0
+        assert np.array_equal(h["readLength"], np.full(len(h), L)) and np.array_equal(h["cigarLength"], fr["cigarLength"])
+        assert np.array_equal(h["observedLength"], np.where(aligned, fr["observedLength"], 0))
+        assert np.array_equal(h["clusterId"], np.nonzero(stored)[0]) and (h["tile"] == options.c.tile).all() and (h["barcode"] == options.c.barcodeIdx).all()
+        assert np.array_equal(h["alignmentScore"], (t["fragmentAlignmentScore"][stored, r] & 0xFFFF).astype(np.uint16))
+        assert np.array_equal((h["flags"] >> 1) & 1, (~aligned).astype(np.uint16)) and np.array_equal((h["flags"] >> 3) & 1, fr["reverse"].astype(np.uint16))
+        assert np.array_equal((h["flags"] >> 8) & 1, t["properPair"][stored].astype(np.uint16)) if rc == 2 else ((h["flags"] >> 8) & 1 == 0).all()
+        assert np.array_equal((h["flags"] >> (5 + r)) & 1, np.ones(len(h), np.uint16)) and np.array_equal(h["flags"] & 1, np.full(len(h), rc - 1, np.uint16))
+        own = aligned | (rc == 1)                                        # a shadow carries its mate's position (Fragment.hh:111-113)
+        contig, position = reference_position(h["fStrandPosition"])
+        placed = own & (fr["contigId"] != 0x7FFFFF)
+        assert np.array_equal(contig[placed], fr["contigId"][placed].astype(np.int64)) and np.array_equal(position[placed], fr["position"][placed])
+        assert (h["fStrandPosition"][own & (fr["contigId"] == 0x7FFFFF)] == NO_MATCH_POSITION).all()
+        assert np.array_equal(packed.f_strand_pos[stored, r] == NO_MATCH_POSITION, fr["contigId"] == 0x7FFFFF)
+        # bases: forward fragments carry the BCL bytes, reverse ones their reverse complement (N stays 0)
+        begin = packed.read_offset[r] + packed.header_length
+        bases = packed.records[stored, begin:begin + L]
+        bcl = reads.bcl[stored, offsets[r]:offsets[r + 1]]
+        is_n = (bcl & 0xFC) == 0
+        back = np.where(is_n, 0, (bcl & 0xFC) | (3 - (bcl & 3)))[:, ::-1]
+        want = np.where((fr["reverse"] != 0)[:, None], back, bcl)
+        assert np.array_equal(bases, want)
+        # CIGAR words and the zero fill
+        end = packed.read_offset[r + 1] if r + 1 < rc else packed.record_length
+        tail = packed.records[stored, begin + L:end]
+        words = np.ascontiguousarray(tail[:, :(tail.shape[1] // 4) * 4]).view(np.uint32)
+        k = np.arange(words.shape[1])[None, :]
+        live = k < fr["cigarLength"][:, None]
+        index = np.minimum(fr["cigarOffset"][:, None].astype(np.int64) + k, templates.cigars.size - 1)
+        assert np.array_equal(np.where(live, words, 0), np.where(live, templates.cigars[index], 0)) and not words[~live].any()
+        assert not tail[:, words.shape[1] * 4:].any()
+    assert not packed.records[~stored].any()
+
+
+def test_round_trip_properties_on_the_cpu(lanes_lib):
+    rng = np.random.default_rng(77)
+    for read_lengths, keep in (((150, 150), True), ((101, 76), False), ((151,), True)):
+        n = 3000
+        reads = ReadSet(random_bcl(rng, n, sum(read_lengths)), read_lengths)
+        templates = random_templates(rng, n, read_lengths)
+        options, _ = make_options(rng, n, keep, with_arrays=False)
+        assert_round_trip(pack_lanes(lanes_lib, reads, templates, options, 32, 0), reads, templates, options)
+
+
 def test_pack_kernel_compiles_for_the_device():
     """the kernel is part of libisaac_ext.so; its resources as ptxas reports them (no spills, no stack frame beyond the header)"""
     out = subprocess.run(["cuobjdump", "-res-usage", os.path.join(ROOT, "isaac_aligner_b200", "libisaac_ext.so")],
@@ -397,6 +454,23 @@ def test_pack_fragments_of_a_simulated_tile(capi):
         got = ctx.pack_fragments(templates, options)
         assert_packed_equal(got, want, mask, reads.read_lengths, "simulated tile, keepUnaligned %d" % keep)
         assert got.stored >= 2 * int(templates.templates["built"].sum())
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_pack_fragments_round_trip_at_tile_size(capi):
+    """200 000 clusters (a 329 MB record buffer, larger than the 126 MB L2): the size-independent properties, no checker"""
+    rng = np.random.default_rng(78)
+    n, read_lengths = 200_000, (150, 150)
+    reads = ReadSet(random_bcl(rng, n, sum(read_lengths)), read_lengths)
+    small = random_templates(rng, 2000, read_lengths)                    # 2000 random templates tiled over the clusters
+    reps = n // 2000
+    fragments = np.tile(small.fragments, reps)
+    fragments["readId"] = np.arange(2 * n, dtype=np.uint32)
+    templates = Templates(np.tile(small.templates, reps), fragments, small.cigars)
+    options = PackOptions(tile=1101, barcode_idx=2, keep_unaligned=False)
+    ctx = gpu_context(capi, reads)
+    assert_round_trip(ctx.pack_fragments(templates, options), reads, templates, options)
     ctx.close()
 
 
