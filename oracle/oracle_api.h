@@ -91,6 +91,12 @@ int oracle_determine_template_length(const oracle_genome_t *genome, const isaac_
  * reference build exports it. */
 int oracle_trim_low_quality_ends(const isaac_ext_reads_t *reads, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut);
 
+/* calculateShadowRescueRange (ShadowAligner.cpp:119-149) and TemplateLengthStatistics::mateOrientation for every request:
+ * rangeOut[2 * i] / [2 * i + 1] = first / second of the pair the reference's function returns, orientationOut[i] the strand
+ * rescueShadow gives the shadow (:171).  Only the reference build exports it. */
+int oracle_shadow_rescue_range(const isaac_ext_reads_t *reads, const isaac_ext_tls_t *tls, uint32_t requestCount,
+                               const isaac_ext_rescue_request_t *requests, int64_t *rangeOut, uint8_t *orientationOut);
+
 /* matchSelector::FragmentCollector::add for every stored template of a tile, see isaac_ext_pack_fragments: the records are
  * written by the reference's own io::FragmentHeader constructors (Fragment.hh:100-186) from BamTemplate / FragmentMetadata /
  * Cluster objects rebuilt from the flat template result.  barcodeBytes: barcodeLength BCL bytes per cluster in front of the

@@ -815,3 +815,43 @@ extern "C" int oracle_pack_fragments(const isaac_ext_reads_t *reads, const isaac
         return ISAAC_EXT_E_INVALID_ARG;
     }
 }
+
+/* calculateShadowRescueRange is a free function of ShadowAligner.cpp with external linkage (:119-149), not declared in a header */
+namespace isaac { namespace alignment {
+std::pair<long, long> calculateShadowRescueRange(const FragmentMetadata &orphan, const TemplateLengthStatistics &templateLengthStatistics,
+                                                 const long bestTemplateLength);
+} }
+
+extern "C" int oracle_shadow_rescue_range(const isaac_ext_reads_t *reads, const isaac_ext_tls_t *tls, uint32_t requestCount,
+                                          const isaac_ext_rescue_request_t *requests, int64_t *rangeOut, uint8_t *orientationOut)
+{
+    try
+    {
+        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+        const alignment::TemplateLengthStatistics stats(
+            tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
+            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[1]), tls->mateDriftRange);
+        ClusterHolder holder(std::max(reads->readLength[0], reads->readLength[1]));
+        for (uint32_t i = 0; i < requestCount; ++i)
+        {
+            const isaac_ext_rescue_request_t &q = requests[i];
+            holder.load(reads, rml, q.orphanReadId / reads->readCount);
+            alignment::FragmentMetadata orphan;
+            orphan.cluster = &holder.cluster;
+            orphan.readIndex = q.orphanReadId % reads->readCount;
+            orphan.contigId = q.orphanContigStrand >> 1;
+            orphan.reverse = q.orphanContigStrand & 1;
+            orphan.position = q.orphanPosition;
+            orphan.observedLength = q.orphanObservedLength;
+            const std::pair<long, long> range = alignment::calculateShadowRescueRange(orphan, stats, q.bestTemplateLength);
+            rangeOut[2 * size_t(i)] = range.first; rangeOut[2 * size_t(i) + 1] = range.second;
+            orientationOut[i] = stats.mateOrientation(orphan.readIndex, orphan.reverse);
+        }
+        return ISAAC_EXT_OK;
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+}

@@ -10,6 +10,7 @@
 using namespace isaac_b200;
 #include "../../isaac_aligner_b200/csrc/template_worker.cuh"
 #include "../../isaac_aligner_b200/csrc/plan_device.cuh"
+#include "../../isaac_aligner_b200/csrc/shadow_window_device.cuh"
 
 namespace
 {
@@ -108,4 +109,24 @@ extern "C" int plan_device_requests(uint32_t clusterCount, uint32_t readCount, c
         clusterRequestBegin[c + 1] = at;
     }
     return at > requestCapacity ? ISAAC_EXT_E_CAPACITY : ISAAC_EXT_OK;
+}
+
+/// shadow_window_device.cuh: the scan window of every request; tasksOut: 4 x int64 per request = windowBegin, windowEnd, shadowReadId,
+/// contigStrand; rangeOut: first / second of calculateShadowRescueRange
+extern "C" int shadow_windows_device(const uint32_t *readLength, const isaac_ext_tls_t *tls, uint32_t requestCount,
+                                     const isaac_ext_rescue_request_t *requests, const uint64_t *contigLength, int64_t *tasksOut, int64_t *rangeOut)
+{
+    struct Task { int64_t windowBegin, windowEnd; uint32_t shadowReadId, contigStrand; };
+    const ShadowWindowModel m = makeShadowWindowModel(*tls);
+    for (uint32_t i = 0; i < requestCount; ++i)
+    {
+        Task t;
+        shadowWindowOf(m, requests[i], readLength, long(contigLength[requests[i].orphanContigStrand >> 1]), t);
+        tasksOut[4 * size_t(i)] = t.windowBegin; tasksOut[4 * size_t(i) + 1] = t.windowEnd;
+        tasksOut[4 * size_t(i) + 2] = t.shadowReadId; tasksOut[4 * size_t(i) + 3] = t.contigStrand;
+        long first, second;
+        shadowRescueRange(m, requests[i], readLength, first, second);
+        rangeOut[2 * size_t(i)] = first; rangeOut[2 * size_t(i) + 1] = second;
+    }
+    return shadowModelCoherent(m) ? 0 : 1;
 }

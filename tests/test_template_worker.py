@@ -194,3 +194,60 @@ def test_device_plan_pass_scatter_repeats_on_hand_made_ties(worker_lib):
         assert total > n and np.array_equal(got_begin, want_begin) and got[:total].tobytes() == want[:total].tobytes(), scatter
         lists.append(want[:total].copy())
     assert lists[0].tobytes() != lists[1].tobytes()                      # the option does change the requests of this tile
+
+
+def test_device_shadow_windows_against_the_references_rescue_range(worker_lib):
+    """csrc/shadow_window_device.cuh (R1 of the rescue pass for a one-thread-per-request kernel) against the reference's own
+    calculateShadowRescueRange and TemplateLengthStatistics::mateOrientation (oracle_shadow_rescue_range), with the clamps of
+    rescueShadow (ShadowAligner.cpp:179-197) restated here: orphans of both reads and strands, with and without a best template
+    length, near the contig ends, every coherent pair of models and mate drift ranges"""
+    ref = oracle_lib.reference()
+    rng = np.random.default_rng(81)
+    n, L0, L1 = 4000, 100, 76
+    contig_length = np.array([5000, 300, 120000], dtype=np.uint64)
+    bcl = (rng.integers(2, 42, size=(50, L0 + L1)).astype(np.uint8) << 2) | rng.integers(0, 4, size=(50, L0 + L1)).astype(np.uint8)
+    from isaac_aligner_b200.types import ReadSet
+    reads = ReadSet(bcl, (L0, L1))
+    read_length = np.array([L0, L1], dtype=np.uint32)
+    req = np.zeros(n, dtype=RESCUE_REQUEST_DTYPE)
+    contig = rng.integers(0, 3, size=n)
+    req["orphanReadId"] = rng.integers(0, 100, size=n)
+    req["orphanContigStrand"] = (contig << 1) | rng.integers(0, 2, size=n)
+    req["orphanPosition"] = np.where(rng.random(n) < 0.2, rng.integers(0, 30, size=n), (rng.random(n) * (contig_length[contig] - 1)).astype(np.int64))
+    req["orphanObservedLength"] = np.where(rng.random(n) < 0.1, 0, rng.integers(60, 140, size=n))
+    req["bestTemplateLength"] = np.where(rng.random(n) < 0.5, 0, rng.integers(1, 3000, size=n))
+    coherent = [(1, 6), (6, 1), (2, 5), (5, 2), (0, 7), (3, 4), (1, 2)]          # FRp/RFm, RFp/FRm, FFp/RRm, RRp/FFm, and one incoherent pair
+    for m0, m1 in coherent:
+        for drift in (-1, 0, 40):
+            tls = Tls.make(mn=int(rng.integers(50, 250)), mx=int(rng.integers(300, 900)), median=280, low=30, high=30, m0=m0, m1=m1, drift=drift)
+            tasks, got_range = np.zeros((n, 4), dtype=np.int64), np.zeros((n, 2), dtype=np.int64)
+            rc_ = worker_lib.shadow_windows_device(p(read_length), ctypes.byref(tls), ctypes.c_uint32(n), p(req), p(contig_length), p(tasks), p(got_range))
+            assert rc_ == (1 if (m0, m1) == (1, 2) else 0)                       # TemplateLengthStatistics::isCoherent
+            want_range, orientation = np.zeros((n, 2), dtype=np.int64), np.zeros(n, dtype=np.uint8)
+            assert ref.lib.oracle_shadow_rescue_range(ctypes.byref(reads.c), ctypes.byref(tls), ctypes.c_uint32(n), p(req), p(want_range), p(orientation)) == 0
+            assert np.array_equal(got_range, want_range), (m0, m1, drift)
+            first, second = want_range[:, 0], want_range[:, 1]
+            shadow_index = (req["orphanReadId"] + 1) % 2
+            begin = np.maximum(0, first)
+            end = np.minimum(contig_length[contig].astype(np.int64), second + 1)
+            empty = (second < first) | (second + 1 + read_length[shadow_index].astype(np.int64) < 0)
+            end = np.where(empty, begin, end)
+            assert np.array_equal(tasks[:, 0], begin) and np.array_equal(tasks[:, 1], end), (m0, m1, drift)
+            assert np.array_equal(tasks[:, 2], req["orphanReadId"] - req["orphanReadId"] % 2 + shadow_index)
+            assert np.array_equal(tasks[:, 3], (contig << 1) | orientation), (m0, m1, drift)
+
+
+def test_shadow_window_device_compiles_for_the_device():
+    src = os.path.join(ROOT, "build", "shadow_window_kernel.cu")
+    os.makedirs(os.path.dirname(src), exist_ok=True)
+    with open(src, "w") as f:
+        f.write('#include "../isaac_aligner_b200/csrc/shadow_window_device.cuh"\n'
+                'struct Task { long long windowBegin, windowEnd; unsigned shadowReadId, contigStrand; };\n'
+                '__global__ void windowKernel(const isaac_b200::ShadowWindowModel m, unsigned n, const isaac_ext_rescue_request_t *q, const unsigned *len,\n'
+                '                             const unsigned long long *contigLength, Task *tasks)\n'
+                '{\n'
+                '    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;\n'
+                '    if (i < n) isaac_b200::shadowWindowOf(m, q[i], len, long(contigLength[q[i].orphanContigStrand >> 1]), tasks[i]);\n'
+                '}\n')
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-c", src, "-o",
+                           os.path.join(ROOT, "build", "shadow_window_kernel.o")])
