@@ -1,7 +1,8 @@
 """Differential campaign of the product code that runs on the CPU harnesses (no GPU) against the reference build of the checker:
   * csrc/template_worker.cuh (plan / finish) + csrc/kernels_clip.cuh (clipTemplateEndsOfCluster) against the reference's
     TemplateBuilder + SemialignedEndsClipper + OverlappingEndsClipper on whole tiles;
-  * csrc/plan_device.cuh against the planning mode of the template worker (same rescueShadow requests, byte for byte);
+  * csrc/plan_device.cuh against the planning mode of the template worker (same rescueShadow requests, byte for byte) and
+    csrc/shadow_window_device.cuh on those requests against the reference's calculateShadowRescueRange;
   * csrc/pack_fragments.cuh (the warp functions of packFragmentsKernel, lane after lane) against the reference's io::FragmentHeader.
 Random read lengths, insert sizes, indel / neighbour / repeat rates, score presets, template length statistics, options, lane
 counts and buffer alignments.  Development aid:
@@ -83,6 +84,17 @@ def main(rounds, campaign=20261018):
         assert worker.plan_device_requests(ctypes.c_uint32(n), ctypes.c_uint32(rc), ctypes.byref(tls), ctypes.byref(plain), ctypes.byref(built_c),
                                            ctypes.c_uint64(b.size), W.p(b), W.p(bb)) == 0
         assert np.array_equal(ab, bb) and a[:int(ab[-1])].tobytes() == b[:int(ab[-1])].tobytes(), what
+        # ---- R1 of the rescue pass on those requests against the reference's calculateShadowRescueRange
+        total = int(ab[-1])
+        if total:
+            req = a[:total].copy()
+            tasks, got_range = np.zeros((total, 4), dtype=np.int64), np.zeros((total, 2), dtype=np.int64)
+            worker.shadow_windows_device(W.p(read_length), ctypes.byref(tls), ctypes.c_uint32(total), W.p(req), W.p(contig_length), W.p(tasks), W.p(got_range))
+            want_range, orientation = np.zeros((total, 2), dtype=np.int64), np.zeros(total, dtype=np.uint8)
+            assert ref.lib.oracle_shadow_rescue_range(ctypes.byref(reads.c), ctypes.byref(tls), ctypes.c_uint32(total), W.p(req), W.p(want_range),
+                                                      W.p(orientation)) == 0
+            assert np.array_equal(got_range, want_range), what
+            assert np.array_equal(tasks[:, 3] & 1, orientation) and np.array_equal(tasks[:, 0], np.maximum(0, want_range[:, 0])), what
         # ---- the record packer on the templates of this tile and on random template records
         keep, compact = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
         lanes, misalign = int(rng.choice([1, 3, 7, 31, 32])), int(rng.integers(0, 8))
