@@ -58,3 +58,32 @@ def test_product_does_not_touch_the_oracle():
                 if re.search(r"oracle[_/]|libisaac_oracle|libisaac_ref|oracle_api", text):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_python_mirrors_have_the_c_struct_sizes():
+    """every ctypes.Structure / numpy dtype the harness passes over the ABI against sizeof() of the header's struct (gcc)"""
+    import ctypes
+    import subprocess
+    from isaac_aligner_b200 import batch, synth, types
+    pairs = [("isaac_ext_config_t", ctypes.sizeof(types.Config)), ("isaac_ext_reads_t", ctypes.sizeof(types.Reads)),
+             ("isaac_ext_adapter_t", ctypes.sizeof(types.Adapter)), ("isaac_ext_fragment_t", types.FRAGMENT_DTYPE.itemsize),
+             ("isaac_ext_candidate_t", types.CANDIDATE_DTYPE.itemsize), ("isaac_ext_match_t", synth.MATCH_DTYPE.itemsize),
+             ("isaac_ext_seed_t", synth.SEED_DTYPE.itemsize), ("isaac_ext_build_batch_t", ctypes.sizeof(batch.BuildBatch)),
+             ("isaac_ext_build_result_t", ctypes.sizeof(batch.BuildResult)), ("isaac_ext_tls_t", ctypes.sizeof(batch.Tls)),
+             ("isaac_ext_rescue_request_t", batch.RESCUE_REQUEST_DTYPE.itemsize), ("isaac_ext_rescue_result_t", ctypes.sizeof(batch.RescueResult)),
+             ("isaac_ext_template_options_t", ctypes.sizeof(batch.TemplateOptions)), ("isaac_ext_template_t", batch.TEMPLATE_DTYPE.itemsize),
+             ("isaac_ext_template_result_t", ctypes.sizeof(batch.TemplateResult)), ("isaac_ext_pack_options_t", ctypes.sizeof(batch.PackOptionsC)),
+             ("isaac_ext_pack_result_t", ctypes.sizeof(batch.PackResultC))]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "build", "abi_sizes.c")
+    os.makedirs(os.path.dirname(src), exist_ok=True)
+    with open(src, "w") as f:
+        f.write('#include <stdio.h>\n#include "isaac_ext.h"\nint main(void) {\n')
+        for name, _ in pairs:
+            f.write('    printf("%s %%zu\\n", sizeof(%s));\n' % (name, name))
+        f.write("    return 0;\n}\n")
+    exe = os.path.join(root, "build", "abi_sizes")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), src, "-o", exe])
+    out = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, size in pairs:
+        assert int(out[name]) == size, (name, out[name], size)
