@@ -38,7 +38,8 @@ struct PipelineState
     DeviceBuffer<IndelResult> dIndel;
     DeviceBuffer<ShadowTask> dShadowTasks;
     DeviceBuffer<int> dShadowScratch;
-    DeviceBuffer<uint32_t> dTaskBegin, dTaskCount, dPoolSize;
+    DeviceBuffer<uint32_t> dTaskBegin, dTaskCount;
+    DeviceBuffer<unsigned long long> dPoolSize;
     // sequencing adapters: first candidate of every clipper slot, slot of every candidate (rescue)
     PinnedBuffer<isaac_ext_candidate_t> hAdapterFirst;
     DeviceBuffer<isaac_ext_candidate_t> dAdapterFirst;

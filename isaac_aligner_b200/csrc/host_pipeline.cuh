@@ -6,7 +6,7 @@
 //
 //   build:   P1 candidates (addMatch, repeat filter, consolidate)      -> K1 ungappedKernel
 //            P2 consolidate, pair adjacent candidates                   -> simpleIndelKernel
-//            P3 apply patches, consolidate, pick mismatchCount > 5      -> gappedKernel2
+//            P3 apply patches, consolidate, pick mismatchCount > 5      -> swForwardKernel + swTraceScoreKernel
 //            P4 acceptance rule, consolidate, flatten
 //   rescue:  R1 rescue windows from the template length statistics      -> shadowCandidates*Kernel, K1 ungappedKernel
 //            (everything behind R1 is on the device: the list bookkeeping R2 / R3 and the flat result are kernels_rescue.cuh)

@@ -40,11 +40,9 @@ struct isaac_ext_ctx
     cudaStream_t stream = nullptr;
     std::string error;
     uint64_t launches = 0;
-    // Tuning knobs (environment, read once at isaac_ext_create): ISAAC_EXT_SW_IMPL = 2 (packed 16x2, two alignments per
-    // thread, default) or 1 (scalar, one alignment per thread); ISAAC_EXT_SW_BLOCKS_PER_SM bounds the persistent grid.
-    // ISAAC_EXT_SW_IMPL = 3 (default): the packed kernel split into a forward and a trace+score kernel (kernels3.cuh),
-    // ISAAC_EXT_SW_CHUNK_WAVES = waves of forward blocks per chunk of that path.
-    int swImpl = 3;
+    // One Smith-Waterman path: the packed 16x2 forward kernel + the trace/score kernel (kernels3.cuh).  Tuning knobs
+    // (environment, read once at isaac_ext_create): ISAAC_EXT_SW_CHUNK_WAVES = waves of forward blocks per chunk,
+    // ISAAC_EXT_SW_BLOCKS_PER_SM bounds the persistent grid of the explicit-string micro kernel.
     unsigned swBlocksPerSm = 8;
     unsigned swChunkWaves = 2;
     cudaStream_t swStream[2] = {nullptr, nullptr};
@@ -144,7 +142,7 @@ bool swScoresSupported(int match, int mismatch, int open, int ext, unsigned maxR
 
 int ensureTraceback(isaac_ext_ctx *ctx, unsigned grid, unsigned block, unsigned maxQueryLength)
 {
-    const size_t words = size_t(grid) * block * (ctx->swImpl >= 2 ? SW2_FLAG_WORDS : 3u) * maxQueryLength;
+    const size_t words = size_t(grid) * block * SW2_FLAG_WORDS * maxQueryLength;
     return ctx->cuda(ctx->tbScratch.reserve(words), "cudaMalloc(traceback scratch)");
 }
 
@@ -197,7 +195,6 @@ extern "C" int isaac_ext_create(const isaac_ext_config_t *config, isaac_ext_ctx 
     isaac_ext_ctx *ctx = new isaac_ext_ctx();
     ctx->cfg = *config;
     ctx->hostThreads = config->hostThreads ? config->hostThreads : std::max(1u, std::thread::hardware_concurrency());
-    if (const char *e = std::getenv("ISAAC_EXT_SW_IMPL")) ctx->swImpl = std::max(1, std::min(3, std::atoi(e)));
     if (const char *e = std::getenv("ISAAC_EXT_SW_CHUNK_WAVES")) ctx->swChunkWaves = std::max(1, std::min(64, std::atoi(e)));
     if (const char *e = std::getenv("ISAAC_EXT_SW_BLOCKS_PER_SM")) ctx->swBlocksPerSm = std::max(1, std::min(16, std::atoi(e)));
     ctx->device = config->device;
@@ -565,26 +562,9 @@ static int gappedDevice(isaac_ext_ctx *ctx, uint32_t n, const void *dCandidates,
         CK(cudaGetLastError());
         adapterClip = ctx->dPrepWords.p;
     }
-    if (ctx->swImpl == 3)
-        return gappedSplit(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
-                           static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-                           static_cast<uint64_t *>(dMismatchMaskOut), cudaStream_t(cudaStream), adapterClip);
-    const unsigned items = ctx->swImpl == 2 ? (n + 1) / 2 : n;     // the packed kernel takes two candidates per thread
-    const unsigned grid = gridFor(ctx, items, SW_BLOCK, ctx->swBlocksPerSm);
-    const int rc = ensureTraceback(ctx, grid, SW_BLOCK, std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]));
-    if (rc) return rc;
-    if (ctx->swImpl == 2)
-        gappedKernel2<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
-            ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
-            static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p, adapterClip);
-    else
-        gappedKernel<<<grid, SW_BLOCK, 0, cudaStream_t(cudaStream)>>>(
-            ctx->ref, ctx->reads, ctx->sp, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
-            static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
-            static_cast<uint64_t *>(dMismatchMaskOut), ctx->tbScratch.p, ctx->errorFlag.p, adapterClip);
-    ++ctx->launches;
-    return ctx->cuda(cudaGetLastError(), "gappedKernel");
+    return gappedSplit(ctx, n, static_cast<const isaac_ext_candidate_t *>(dCandidates), cigarStride,
+                       static_cast<isaac_ext_fragment_t *>(dFragmentsOut), static_cast<uint32_t *>(dCigarOut),
+                       static_cast<uint64_t *>(dMismatchMaskOut), cudaStream_t(cudaStream), adapterClip);
 }
 
 static int extendHost(isaac_ext_ctx *ctx, bool gapped, uint32_t n, const isaac_ext_candidate_t *candidates, uint32_t cigarStride,
@@ -668,18 +648,13 @@ extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const c
     CK(cudaMemcpyAsync(ctx->dOffsets.p, queryOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dOffsets.p + n, databaseOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->dLengths.p, queryLengths, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    const unsigned grid = gridFor(ctx, ctx->swImpl == 2 ? (n + 1) / 2 : n, SW_BLOCK, ctx->swBlocksPerSm);
+    const unsigned grid = gridFor(ctx, (n + 1) / 2, SW_BLOCK, ctx->swBlocksPerSm);      // two alignments per thread
     int rc = ensureTraceback(ctx, grid, SW_BLOCK, maxLen);
     if (rc) return rc;
     const SwScores sw = {matchScore, mismatchScore, gapOpenScore, gapExtendScore, -32768 + gapOpenScore};
-    if (ctx->swImpl == 2)
-        bandedSwAsciiKernel2<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
+    bandedSwAsciiKernel2<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
                                                                  ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
                                                                  ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
-    else
-        bandedSwAsciiKernel<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
-                                                                ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
-                                                                ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cigarOut, ctx->dCigars.p, size_t(n) * cigarStride * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -462,9 +462,7 @@ static int rescueShadowsInto(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
         // ---- R1: rescue windows (calculateShadowRescueRange :119-149, rescueShadow :170-198)
         CK(ps.hShadowTasks.reserve(n));
         std::atomic<int> bad(0);
-        std::atomic<uint32_t> largeWindows(0);
         parallelRanges(T, n, [&](unsigned, size_t b, size_t e) {
-            uint32_t large = 0;
             for (size_t i = b; i < e; ++i)
             {
                 const isaac_ext_rescue_request_t &q = requests[i];
@@ -490,35 +488,34 @@ static int rescueShadowsInto(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
                 task.windowBegin = std::max(0L, first);                                                // :194
                 task.windowEnd = std::min(long(ctx->contigLength[contigId]), second + 1);              // :197
                 if (second < first || second + 1 + long(len[shadowReadIndex]) < 0) task.windowEnd = task.windowBegin;   // :179-190
-                large += task.windowEnd - task.windowBegin > long(SHADOW_WARP_WINDOW);
             }
-            largeWindows += large;
         });
         timer.mark("R1 windows");
         if (bad) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "rescue request refers to an unknown read or contig");
         // ---- K5: candidate positions of every request (:195-236).  Requests with a small window (nearly all) take one warp
-        // each, the others one CTA each with the full 4^7 table and the 10000 cap; each kernel skips the other's requests.
-        uint32_t largeCount = largeWindows;
-        if (std::max(ctx->reads.readLength[0], ctx->reads.readLength[1]) > SHADOW_WARP_MAX_READ) largeCount = n;
+        // each, the others one CTA each with the full 4^7 table and the 10000 cap.  Both kernels always get the whole request
+        // list and decide per request with the one predicate shadowTaskIsSmall (kernels_shadow.cuh), so every request is
+        // handled by exactly one of them whatever the mix of window sizes and read lengths.
         const unsigned grid = std::max(1u, std::min<unsigned>(n, unsigned(ctx->smCount) * 6));
         CK(ps.dShadowTasks.reserve(n)); CK(ps.dTaskBegin.reserve(n)); CK(ps.dTaskCount.reserve(n)); CK(ps.dPoolSize.reserve(1));
         CK(ps.dShadowScratch.reserve(size_t(grid) * SHADOW_SCRATCH));
         CK(cudaMemcpyAsync(ps.dShadowTasks.p, ps.hShadowTasks.p, size_t(n) * sizeof(ShadowTask), cudaMemcpyHostToDevice, ctx->stream));
         uint64_t capacity = std::max<uint64_t>(ps.dCand.capacity, uint64_t(n) * 24 + 4096);
-        uint32_t poolSize = 0;
+        unsigned long long poolSize64 = 0;
         for (int attempt = 0; attempt < 2; ++attempt)
         {
             CK(ps.dCand.reserve(capacity));
-            CK(cudaMemsetAsync(ps.dPoolSize.p, 0, sizeof(uint32_t), ctx->stream));
+            CK(cudaMemsetAsync(ps.dPoolSize.p, 0, sizeof(unsigned long long), ctx->stream));
+            // a request neither kernel takes cannot exist, but an empty list is the safe reading of a skipped one
+            CK(cudaMemsetAsync(ps.dTaskBegin.p, 0, size_t(n) * sizeof(uint32_t), ctx->stream));
+            CK(cudaMemsetAsync(ps.dTaskCount.p, 0, size_t(n) * sizeof(uint32_t), ctx->stream));
             const uint32_t poolCapacity = uint32_t(std::min<uint64_t>(ps.dCand.capacity, 0xFFFFFFFFull));
-            if (largeCount < n)
             {
                 shadowCandidatesWarpKernel<<<gridFor(ctx, uint64_t(n) * 32, SHADOW_WARPS * 32, 6), SHADOW_WARPS * 32, 0, ctx->stream>>>(
                     ctx->ref, ctx->reads, n, ps.dShadowTasks.p, ps.dCand.p, poolCapacity, ps.dPoolSize.p, ps.dTaskBegin.p, ps.dTaskCount.p,
                     ctx->errorFlag.p);
                 ++ctx->launches;
             }
-            if (largeCount)       // (a host count over a superset of the kernel's own test: an empty launch is harmless)
             {
                 shadowCandidatesKernel<<<grid, SHADOW_BLOCK, 0, ctx->stream>>>(ctx->ref, ctx->reads, n, ps.dShadowTasks.p, ps.dShadowScratch.p,
                                                                                 ps.dCand.p, poolCapacity, ps.dPoolSize.p, ps.dTaskBegin.p,
@@ -526,12 +523,15 @@ static int rescueShadowsInto(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
                 ++ctx->launches;
             }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(&poolSize, ps.dPoolSize.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&poolSize64, ps.dPoolSize.p, sizeof(poolSize64), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            if (poolSize <= ps.dCand.capacity) break;
-            capacity = uint64_t(poolSize) + 1024;                                // the pool was too small: the kernel reported the need
-            CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));
+            if (poolSize64 <= poolCapacity) break;
+            CK(cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream));   // bit 2: the pool was too small, the counter holds the need
+            if (attempt || poolSize64 > 0xFFFFFFF0ull)
+                return ctx->fail(ISAAC_EXT_E_CAPACITY, "too many shadow candidate positions in one rescue batch: split the batch");
+            capacity = poolSize64 + 1024;
         }
+        const uint32_t poolSize = uint32_t(poolSize64);
         timer.mark("K5 shadow candidates");
         if (poolSize)
         {

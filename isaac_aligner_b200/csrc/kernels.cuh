@@ -2,7 +2,6 @@
 //   packReferenceKernel   K0  ASCII contig -> 2-bit + N-mask            (ContigLoader product, ContigLoader.cpp:29-65)
 //   decodeBclKernel       K0b BCL bytes -> 2-bit + n-mask + qualities   (Read::decodeBcl, Read.cpp:32-73)
 //   ungappedKernel        K1  UngappedAligner::alignUngapped            (UngappedAligner.cpp:39-92)
-//   gappedKernel          K2+K4 GappedAligner::alignGapped = clipping + banded SW + traceback + re-score
 //                                                                        (GappedAligner.cpp:167-249)
 //   bandedSwAsciiKernel   K2  BandedSmithWaterman::align on explicit (query, database) strings
 #pragma once
@@ -172,86 +171,7 @@ __global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads,
     }
 }
 
-struct ResidentBaseSrc
-{
-    const ReferenceView &ref; const ReadSetView &reads;
-    unsigned readId, L; bool reverse; unsigned qBegin; uint64_t dBegin;
-    __device__ __forceinline__ unsigned q(unsigned i) const { unsigned qq; return reads.code(readId, L, reverse, qBegin + i, qq); }
-    __device__ __forceinline__ unsigned d(unsigned k) const { return ref.code(dBegin + k); }
-};
-
 constexpr unsigned SW_OPS_CAP = 64;
-
-/// K2+K4: one candidate per thread: clip, banded Smith-Waterman, traceback, re-score the gapped CIGAR.
-__global__ void gappedKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
-                             const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
-                             isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
-                             uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag,
-                             const uint32_t *__restrict__ adapterClip = nullptr)
-{
-    __shared__ double tables[201];
-    const ScoreParams sp = stageScoreTables(spGlobal, tables);
-    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
-    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
-    const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const isaac_ext_candidate_t c = candidates[i];
-        isaac_ext_fragment_t o;
-        initFragment(o, c, reads.readCount);
-        const unsigned contigId = c.contigStrand >> 1;
-        const unsigned L = reads.length(c.readId);
-        const long contigLength = long(ref.contigLength[contigId]);
-        uint64_t *mask = masks ? masks + size_t(i) * ISAAC_EXT_MASK_WORDS : nullptr;
-        if (mask) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
-        uint32_t *cigar = cigars + size_t(i) * cigarStride;
-        o.cigarOffset = i * cigarStride;
-        FragmentState f = {c.position, 0u, 0u, bool(c.contigStrand & 1u)};              // GappedAligner.cpp:175-176
-        long begin = 0, end = L;
-        if (adapterClip) applyAdapterClip(adapterClip[i], L, f, begin, end);            // :186
-        clipReadMasking(L, reads.endCyclesMasked[c.readId], f, begin, end);             // :187
-        clipReference(contigLength, f, begin, end);                                     // :189
-        o.lowClipped = uint16_t(f.lowClipped); o.highClipped = uint16_t(f.highClipped); o.position = f.position;
-        const unsigned sequenceLength = unsigned(end - begin);
-        long strandPosition = f.position;
-        // no gapped alignment if the reference is too short (:204-208)
-        if (sequenceLength && !(contigLength < long(sequenceLength) + strandPosition + 16) &&
-            !(adapterClip && (adapterClip[i] >> 31)))                                    // --avoid-smith-waterman (:218-226)
-        {
-            // getFlanks (:51-82)
-            unsigned left, right;
-            if (strandPosition >= 8)
-            {
-                if (strandPosition + sequenceLength + 8 < contigLength) { left = 8; right = 7; }
-                else { right = unsigned(contigLength - sequenceLength - strandPosition); left = 16 - right - 1; }
-            }
-            else { left = unsigned(strandPosition); right = 16 - left - 1; }
-            (void)right;
-            const ResidentBaseSrc src = {ref, reads, c.readId, L, f.reverse, unsigned(begin),
-                                         ref.contigOffset[contigId] + uint64_t(strandPosition - left)};
-            uint32_t ops[SW_OPS_CAP + 2];
-            unsigned nSw = 0; bool overflow = false;
-            unsigned nOps = 0;
-            uint32_t *swOps = ops + 1;
-            const unsigned ret = bandedSwAlign(src, sequenceLength, sw, tb, tbStride, swOps, SW_OPS_CAP, nSw, overflow);   // :231
-            uint32_t *all = swOps;
-            nOps = nSw;
-            if (begin) { ops[0] = cigarWord(uint32_t(begin), ISAAC_EXT_CIGAR_SOFT_CLIP); all = ops; ++nOps; }           // :191-195
-            if (long(L) - end) all[nOps++] = cigarWord(uint32_t(L - end), ISAAC_EXT_CIGAR_SOFT_CLIP);                   // :233-237
-            strandPosition += long(ret) - long(left);                                                                    // :231,240
-            if (overflow || nOps > cigarStride) { atomicOr(errorFlag, 1u); }
-            else
-            {
-                const unsigned matchCount = scoreCigar(ref, reads, sp, c.readId, L, f.reverse, ref.contigOffset[contigId],
-                                                       strandPosition, all, nOps, o, mask);                              // :245
-                for (unsigned k = 0; k < nOps; ++k) cigar[k] = all[k];
-                o.cigarLength = uint16_t(nOps);
-                (void)matchCount;
-            }
-        }
-        fragments[i] = o;
-    }
-}
 
 struct AsciiBaseSrc
 {
@@ -263,28 +183,6 @@ struct AsciiBaseSrc
     __device__ __forceinline__ unsigned q(unsigned i) const { return qcode(query[i]); }
     __device__ __forceinline__ unsigned d(unsigned k) const { return asciiRefCode(database[k]); }
 };
-
-/// BandedSmithWaterman::align on explicit strings (unit parity with testBandedSmithWaterman.cpp and kernel timing).
-__global__ void bandedSwAsciiKernel(uint32_t n, const unsigned char *__restrict__ queries, const uint64_t *__restrict__ queryOffsets,
-                                    const uint32_t *__restrict__ queryLengths, const unsigned char *__restrict__ databases,
-                                    const uint64_t *__restrict__ databaseOffsets, const SwScores sw, uint32_t cigarStride,
-                                    uint32_t *__restrict__ cigars, uint32_t *__restrict__ cigarLengths, uint32_t *__restrict__ offsets,
-                                    uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag)
-{
-    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
-    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-        const AsciiBaseSrc src = {queries + queryOffsets[i], databases + databaseOffsets[i]};
-        uint32_t ops[SW_OPS_CAP];
-        unsigned nOps = 0; bool overflow = false;
-        const unsigned ret = bandedSwAlign(src, queryLengths[i], sw, tb, tbStride, ops, SW_OPS_CAP, nOps, overflow);
-        if (overflow) atomicOr(errorFlag, 1u);
-        offsets[i] = ret;
-        cigarLengths[i] = nOps;
-        for (unsigned k = 0; k < nOps && k < cigarStride; ++k) cigars[size_t(i) * cigarStride + k] = ops[k];
-    }
-}
 
 } // namespace isaac_b200
 

@@ -1,5 +1,4 @@
 // Second-generation Smith-Waterman kernels: two alignments per thread in packed 16x2 form (sw2.cuh).
-//   gappedKernel2         GappedAligner::alignGapped for candidates (2t, 2t+1) in thread t
 //   bandedSwAsciiKernel2  BandedSmithWaterman::align on explicit strings, pairs (2t, 2t+1)
 #pragma once
 #include "kernels.cuh"
@@ -87,101 +86,6 @@ struct ResidentPairSrc
     }
 };
 
-#ifndef ISAAC_SW2_MIN_BLOCKS
-#define ISAAC_SW2_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(128, ISAAC_SW2_MIN_BLOCKS)
-gappedKernel2(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
-              const isaac_ext_candidate_t *__restrict__ candidates, uint32_t cigarStride,
-              isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigars,
-              uint64_t *__restrict__ masks, uint32_t *__restrict__ tbScratch, uint32_t *__restrict__ errorFlag,
-              const uint32_t *__restrict__ adapterClip = nullptr)
-{
-    // the two 100-entry log-probability tables are looked up once per base: keep them in shared memory
-    __shared__ double tables[201];      // [0,100) logMatch, [100,200) logMismatch, [200] = 0.0 (contiguous in global too)
-    for (unsigned i = threadIdx.x; i < 201; i += blockDim.x) tables[i] = spGlobal.logMatch[i];
-    __syncthreads();
-    ScoreParams sp = spGlobal;
-    sp.logMatch = tables; sp.logMismatch = tables + 100;
-
-    const size_t tbStride = size_t(gridDim.x) * blockDim.x;
-    uint32_t *tb = tbScratch + (blockIdx.x * blockDim.x + threadIdx.x);
-    const SwScores sw = {sp.swMatch, sp.swMismatch, sp.swOpen, sp.swExtend, -32768 + sp.swOpen};
-    const uint32_t pairs = (n + 1) / 2;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += gridDim.x * blockDim.x)
-    {
-        const uint32_t iA = 2 * t, iB = 2 * t + 1;
-        const bool haveB = iB < n;
-        const GappedPrep pa = prepareGapped(ref, reads, candidates[iA], adapterClip, iA);
-        GappedPrep pb = prepareGapped(ref, reads, candidates[haveB ? iB : iA], adapterClip, haveB ? iB : iA);
-        if (!haveB) pb.run = false;
-        const unsigned LA = pa.run ? pa.sequenceLength : 0u, LB = pb.run ? pb.sequenceLength : 0u;
-        int jj[2] = {0, 0}; unsigned type[2] = {0, 0};
-        if (LA | LB)
-        {
-            // a half that is not aligned (run == false) streams its own first bases: harmless, never stored
-            ResidentPairSrc src = {ref,
-                                   {reads.strandCodes(pa.c.readId, pa.f.reverse), reads.strandCodes(pb.c.readId, pb.f.reverse)},
-                                   {LA ? unsigned(pa.begin) : 0u, LB ? unsigned(pb.begin) : 0u},
-                                   {LA ? ref.contigOffset[pa.contigId] + uint64_t(pa.strandPosition - long(pa.left)) : 0ull,
-                                    LB ? ref.contigOffset[pb.contigId] + uint64_t(pb.strandPosition - long(pb.left)) : 0ull},
-                                   {0, 0}, {0, 0}, reads.codesClamp()};
-            sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);                                                 // :231
-        }
-        // ---- traceback of both halves in one pass over the rows
-        uint32_t opsA[SW_OPS_CAP + 2], opsB[SW_OPS_CAP + 2];
-        Sw2Walker wa, wb;
-        wa.start(LA, jj[0], type[0], opsA + 1, SW_OPS_CAP);
-        wb.start(LB, jj[1], type[1], opsB + 1, SW_OPS_CAP);
-        sw2TracebackPair(tb, tbStride, wa, wb);
-        unsigned nSwA = 0, nSwB = 0;
-        const unsigned retA = LA ? wa.finish(nSwA) : 0u, retB = LB ? wb.finish(nSwB) : 0u;
-        // ---- soft clips, position (:233-240) and updateFragmentCigar of both halves side by side (:245)
-        unsigned nOpsA = 0, nOpsB = 0;
-        uint32_t *allA = assembleGappedCigar(pa, opsA, nSwA, nOpsA), *allB = assembleGappedCigar(pb, opsB, nSwB, nOpsB);
-        const long posA = pa.strandPosition + long(retA) - long(pa.left), posB = pb.strandPosition + long(retB) - long(pb.left);
-        const bool okA = pa.run && !(wa.overflow || nOpsA > cigarStride), okB = haveB && pb.run && !(wb.overflow || nOpsB > cigarStride);
-        if ((pa.run && !okA) || (haveB && pb.run && !okB)) atomicOr(errorFlag, 1u);
-        uint64_t *maskA = masks ? masks + size_t(iA) * ISAAC_EXT_MASK_WORDS : nullptr;
-        uint64_t *maskB = masks && haveB ? masks + size_t(iB) * ISAAC_EXT_MASK_WORDS : nullptr;
-        if (maskA) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) maskA[k] = 0;
-        if (maskB) for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) maskB[k] = 0;
-        CigarScorer sa, sb;
-        sa.start(ref, reads, sp, pa.c.readId, okA ? pa.L : 0u, pa.f.reverse, ref.contigOffset[pa.contigId], posA, allA, nOpsA, maskA);
-        sb.start(ref, reads, sp, pb.c.readId, okB ? pb.L : 0u, pb.f.reverse, ref.contigOffset[pb.contigId], posB, allB, nOpsB, maskB);
-        const unsigned Lmax = max(sa.L, sb.L);
-        for (unsigned w = 0; w * 16u < Lmax; ++w) { sa.stepWord(w); sb.stepWord(w); }
-        {
-            isaac_ext_fragment_t o;
-            initFragment(o, pa.c, reads.readCount);
-            o.cigarOffset = iA * cigarStride;
-            o.lowClipped = uint16_t(pa.f.lowClipped); o.highClipped = uint16_t(pa.f.highClipped); o.position = pa.f.position;
-            if (okA)
-            {
-                sa.finish(o);
-                o.position = posA;
-                for (unsigned k = 0; k < nOpsA; ++k) cigars[size_t(iA) * cigarStride + k] = allA[k];
-                o.cigarLength = uint16_t(nOpsA);
-            }
-            fragments[iA] = o;
-        }
-        if (haveB)
-        {
-            isaac_ext_fragment_t o;
-            initFragment(o, pb.c, reads.readCount);
-            o.cigarOffset = iB * cigarStride;
-            o.lowClipped = uint16_t(pb.f.lowClipped); o.highClipped = uint16_t(pb.f.highClipped); o.position = pb.f.position;
-            if (okB)
-            {
-                sb.finish(o);
-                o.position = posB;
-                for (unsigned k = 0; k < nOpsB; ++k) cigars[size_t(iB) * cigarStride + k] = allB[k];
-                o.cigarLength = uint16_t(nOpsB);
-            }
-            fragments[iB] = o;
-        }
-    }
-}
 
 struct AsciiPairSrc
 {

@@ -69,7 +69,7 @@ __device__ __forceinline__ bool shadowTaskIsSmall(const ShadowTask &task, const 
 __global__ void __launch_bounds__(SHADOW_BLOCK)
 shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_t n, const ShadowTask *__restrict__ tasks,
                        int *__restrict__ scratch /* gridDim.x * SHADOW_SCRATCH */,
-                       isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity, uint32_t *__restrict__ poolSize,
+                       isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity, unsigned long long *__restrict__ poolSize,
                        uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount, uint32_t *__restrict__ errorFlag,
                        const bool largeOnly = false)
 {
@@ -77,7 +77,8 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
     __shared__ int warpLast[SHADOW_BLOCK / 32];
     __shared__ unsigned warpCount[SHADOW_BLOCK / 32];
     __shared__ int carryLast;
-    __shared__ unsigned pushed, base;
+    __shared__ unsigned pushed;
+    __shared__ unsigned long long base;         // 64-bit: n requests x up to 10000 candidates can pass 2^32
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int NONE = INT_MIN;
     int *cand = scratch + size_t(blockIdx.x) * SHADOW_SCRATCH;
@@ -204,7 +205,7 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
             uniqueCount = pushed;
             if (threadIdx.x == 0)
             {
-                base = atomicAdd(poolSize, uniqueCount);
+                base = atomicAdd(poolSize, (unsigned long long)uniqueCount);
                 if (base + uniqueCount > poolCapacity) atomicOr(errorFlag, 2u);
             }
             __syncthreads();
@@ -227,7 +228,7 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
                 }
             }
         }
-        if (threadIdx.x == 0) { taskBegin[t] = count ? base : 0u; taskCount[t] = uniqueCount; }
+        if (threadIdx.x == 0) { taskBegin[t] = count && base + uniqueCount <= poolCapacity ? uint32_t(base) : 0u; taskCount[t] = uniqueCount; }
         // ---- clear the table entries this request set
         if (warp == 0 && L >= ISAAC_EXT_SHADOW_KMER)
         {
@@ -255,7 +256,7 @@ constexpr unsigned SHADOW_WARPS = 8;
 
 __global__ void __launch_bounds__(SHADOW_WARPS * 32)
 shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uint32_t n, const ShadowTask *__restrict__ tasks, isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity,
-                           uint32_t *__restrict__ poolSize, uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount,
+                           unsigned long long *__restrict__ poolSize, uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount,
                            uint32_t *__restrict__ errorFlag)
 {
     __shared__ uint32_t hashAll[SHADOW_WARPS][SHADOW_WARP_SLOTS];
@@ -372,10 +373,10 @@ shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uin
             const bool head = i < count && (i == 0 || cand[i] != cand[i - 1]);
             uniqueCount += __popc(__ballot_sync(0xFFFFFFFFu, head));
         }
-        unsigned base = 0;
+        unsigned long long base = 0;
         if (lane == 0 && uniqueCount)
         {
-            base = atomicAdd(poolSize, uniqueCount);
+            base = atomicAdd(poolSize, (unsigned long long)uniqueCount);
             if (base + uniqueCount > poolCapacity) atomicOr(errorFlag, 2u);
         }
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -398,7 +399,7 @@ shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uin
                 before += __popc(heads);
             }
         }
-        if (lane == 0) { taskBegin[t] = count ? base : 0u; taskCount[t] = uniqueCount; }
+        if (lane == 0) { taskBegin[t] = count && base + uniqueCount <= poolCapacity ? uint32_t(base) : 0u; taskCount[t] = uniqueCount; }
         __syncwarp();
     }
 }

@@ -10,3 +10,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    """A `-m gpu` test that SKIPS because a CPU checker is missing is a failure: "parity against the reference" must never turn
+    silently into "not checked" (or into parity against the restatement alone) on the GPU box."""
+    outcome = yield
+    report = outcome.get_result()
+    if report.skipped and item.get_closest_marker("gpu") is not None and not hasattr(report, "wasxfail"):
+        reason = str(report.longrepr[2] if isinstance(report.longrepr, tuple) else report.longrepr).lower()
+        if any(word in reason for word in ("reference", "checker", "oracle")):
+            report.outcome = "failed"
+            report.longrepr = "gpu parity test skipped for lack of its checker: " + reason

@@ -231,6 +231,22 @@ def port():
     return Oracle(PORT_SO)
 
 
+def require_reference():
+    """The reference's own code for the `-m gpu` parity tests: a missing oracle/_ref/libisaac_ref.so is a FAILURE there, never a
+    silent downgrade to "parity against our own restatement" (build it with `make -C oracle ref` where /root/reference is
+    mounted; the built file travels to the GPU box with the snapshot)."""
+    ref = reference()
+    if ref is None:
+        import pytest
+        pytest.fail("oracle/_ref/libisaac_ref.so is missing: the GPU parity tests compare with the reference's own code")
+    return ref
+
+
+def gpu_checkers():
+    """both CPU checkers, for the `-m gpu` parity tests"""
+    return [port(), require_reference()]
+
+
 def reference():
     """The reference's own code; None when it was never built (needs /root/reference at build time)."""
     if not os.path.exists(REF_SO):
