@@ -96,8 +96,8 @@ struct HostPools
     long unclippedPosition(const WorkFragment &w) const { return long(w.f.position) - beginClipped(w); }   // :185-188
 };
 
-inline bool lpEquals(double a, double b) { return 0.0000001 >= std::fabs(a - b); }      // ISAAC_LP_EQUALS, Quality.hh:104-107
-inline bool lpLess(double a, double b) { return !lpEquals(a, b) && a < b; }             // ISAAC_LP_LESS,   Quality.hh:109-112
+__host__ __device__ inline bool lpEquals(double a, double b) { const double d = a - b; return 0.0000001 >= (d < 0 ? -d : d); }      // ISAAC_LP_EQUALS, Quality.hh:104-107
+__host__ __device__ inline bool lpLess(double a, double b) { return !lpEquals(a, b) && a < b; }             // ISAAC_LP_LESS,   Quality.hh:109-112
 
 /// FragmentMetadata::operator< (FragmentMetadata.hh:419-429)
 inline bool fragmentLess(const WorkFragment &a, const WorkFragment &b)
@@ -141,16 +141,16 @@ inline unsigned consolidateDuplicateFragments(WorkFragment *list, unsigned n, bo
 }
 
 /* the reference's packed Match fields (SeedId.hh:37-127, ReferencePosition.hh:51-188) */
-inline unsigned matchSeed(const isaac_ext_match_t &m) { return unsigned((m.seedId >> 1) & 0xFF); }
-inline bool matchReverse(const isaac_ext_match_t &m) { return m.seedId & 1; }
-inline bool matchIsNoMatch(const isaac_ext_match_t &m) { return m.location == (((~uint64_t(0)) >> 41) << 41); }
-inline bool matchIsTooMany(const isaac_ext_match_t &m) { return (m.location >> 1) == 0; }
-inline unsigned matchContig(const isaac_ext_match_t &m) { return unsigned(m.location >> 41) - 1; }
-inline long matchPosition(const isaac_ext_match_t &m) { return long((m.location >> 1) & ((uint64_t(1) << 40) - 1)); }
-inline bool matchHasNeighbors(const isaac_ext_match_t &m) { return m.location & 1; }
+__host__ __device__ inline unsigned matchSeed(const isaac_ext_match_t &m) { return unsigned((m.seedId >> 1) & 0xFF); }
+__host__ __device__ inline bool matchReverse(const isaac_ext_match_t &m) { return m.seedId & 1; }
+__host__ __device__ inline bool matchIsNoMatch(const isaac_ext_match_t &m) { return m.location == (((~uint64_t(0)) >> 41) << 41); }
+__host__ __device__ inline bool matchIsTooMany(const isaac_ext_match_t &m) { return (m.location >> 1) == 0; }
+__host__ __device__ inline unsigned matchContig(const isaac_ext_match_t &m) { return unsigned(m.location >> 41) - 1; }
+__host__ __device__ inline long matchPosition(const isaac_ext_match_t &m) { return long((m.location >> 1) & ((uint64_t(1) << 40) - 1)); }
+__host__ __device__ inline bool matchHasNeighbors(const isaac_ext_match_t &m) { return m.location & 1; }
 
 /// the kernel-computed fields of 'scored' replace those of 'w'; the seed bookkeeping of 'w' stays
-inline void adoptAlignment(WorkFragment &w, const isaac_ext_fragment_t &scored, uint32_t pool, uint32_t slot)
+__host__ __device__ inline void adoptAlignment(WorkFragment &w, const isaac_ext_fragment_t &scored, uint32_t pool, uint32_t slot)
 {
     isaac_ext_fragment_t &f = w.f;
     f.position = scored.position; f.logProbability = scored.logProbability; f.cigarOffset = scored.cigarOffset;
@@ -162,7 +162,7 @@ inline void adoptAlignment(WorkFragment &w, const isaac_ext_fragment_t &scored, 
 }
 
 /// the 5-clause acceptance rule of the gapped alignment (FragmentBuilder.cpp:202-205, ShadowAligner.cpp:259-262)
-inline bool acceptGapped(const isaac_ext_fragment_t &ungapped, const isaac_ext_fragment_t &gapped, unsigned gappedMismatchesMax)
+__host__ __device__ inline bool acceptGapped(const isaac_ext_fragment_t &ungapped, const isaac_ext_fragment_t &gapped, unsigned gappedMismatchesMax)
 {
     const unsigned observed = ungapped.cigarLength ? ungapped.observedLength : 0;       // getObservedLength()
     return gapped.matchCount && gapped.matchCount + ISAAC_EXT_BAND_WIDTH > observed &&

@@ -24,9 +24,11 @@ namespace
 thread_local std::string g_createError;
 struct E2eState;                       // isaac_ext_e2e.cuh
 void releaseE2e(E2eState *state);
-struct TemplateState;                  // isaac_ext_templates.cuh
+struct TemplateState;                  // isaac_ext_tls.cuh
+struct TileState;                      // isaac_ext_tile.cuh
 } // namespace
 void releaseTemplates(TemplateState *state);
+void releaseTile(TileState *state);
 struct PackState;                      // isaac_ext_pack.cuh
 void releasePack(PackState *state);
 struct AsyncState;                     // isaac_ext_async.cuh
@@ -52,7 +54,8 @@ struct isaac_ext_ctx
     uint32_t clusterCount = 0;    // of the resident read set
     PipelineState pipeline;       // buffers of isaac_ext_build_fragments / isaac_ext_rescue_shadows
     E2eState *e2e = nullptr;      // streams and chunk buffers of the *_batch_compact entry points
-    TemplateState *templates = nullptr;   // buffers of isaac_ext_build_templates
+    TemplateState *templates = nullptr;   // buffers of isaac_ext_template_stats
+    TileState *tile = nullptr;            // device-resident tile pipeline: isaac_ext_build_fragments / _rescue_shadows / _build_templates
     PackState *pack = nullptr;            // buffers of isaac_ext_pack_fragments
     AsyncState *async = nullptr;          // the call in flight between isaac_ext_submit_* and isaac_ext_wait
     double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
@@ -260,6 +263,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     ctx->pipeline.release();
     releaseE2e(ctx->e2e);
     releaseTemplates(ctx->templates);
+    releaseTile(ctx->tile);
     releasePack(ctx->pack);
     delete ctx;
 }
@@ -701,12 +705,11 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
     return ctx->cuda(cudaGetLastError(), "tileStatsKernel");
 }
 
-// isaac_ext_build_fragments, isaac_ext_rescue_shadows
-#include "isaac_ext_pipelines.cuh"
+// isaac_ext_build_fragments, isaac_ext_rescue_shadows, isaac_ext_build_templates
+#include "isaac_ext_tile.cuh"
 
 // isaac_ext_ungapped_batch_compact, isaac_ext_gapped_batch_compact
 #include "isaac_ext_e2e.cuh"
-#include "isaac_ext_templates.cuh"
 #include "isaac_ext_tls.cuh"
 #include "isaac_ext_pack.cuh"
 #include "isaac_ext_async.cuh"

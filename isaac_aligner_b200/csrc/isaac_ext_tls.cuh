@@ -9,6 +9,18 @@
 
 #include "template_length_host.cuh"
 
+namespace
+{
+/// buffers of isaac_ext_template_stats
+struct TemplateState
+{
+    DeviceBuffer<isaac_ext_template_t> dStatTemplates;  DeviceBuffer<isaac_ext_fragment_t> dStatFragments;
+    DeviceBuffer<uint32_t> dStatCigars;  DeviceBuffer<uint8_t> dStatBytes;  DeviceBuffer<unsigned long long> dStats;
+    ~TemplateState() { dStatTemplates.release(); dStatFragments.release(); dStatCigars.release(); dStatBytes.release(); dStats.release(); }
+};
+} // namespace
+void releaseTemplates(TemplateState *state) { delete state; }
+
 extern "C" int isaac_ext_determine_template_length(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const uint8_t *pf,
                                                    int32_t mateDriftRange, isaac_ext_tls_t *tlsOut, uint32_t *stableOut)
 {

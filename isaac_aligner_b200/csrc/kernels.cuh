@@ -142,6 +142,7 @@ __global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads,
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const isaac_ext_candidate_t c = candidates[i];
+        if (c.readId == 0xFFFFFFFFu) continue;          // a match slot of the tile pipeline that holds no candidate (kernels_tile.cuh)
         isaac_ext_fragment_t o;
         initFragment(o, c, reads.readCount);
         const unsigned contigId = c.contigStrand >> 1;

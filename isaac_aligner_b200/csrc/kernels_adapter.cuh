@@ -225,6 +225,7 @@ __global__ void adapterClipKernel(const ReferenceView ref, const ReadSetView rea
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const isaac_ext_candidate_t c = candidates[i];
+        if (c.readId == ADAPTER_NO_CANDIDATE) continue;      // a match slot of the tile pipeline that holds no candidate
         const uint32_t slot = slotOf ? slotOf[i] : c.readId * 2u + (c.contigStrand & 1u);
         clipOut[i] = adapterClipCandidate(ranges[slot], ref, reads, c);
     }

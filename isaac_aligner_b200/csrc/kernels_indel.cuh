@@ -62,12 +62,14 @@ struct IndelView
 };
 
 __global__ void simpleIndelKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
-                                  const IndelTask *__restrict__ tasks, IndelResult *__restrict__ results)
+                                  const IndelTask *__restrict__ tasks, IndelResult *__restrict__ results,
+                                  const uint8_t *__restrict__ valid = nullptr, uint32_t *__restrict__ cigarsOut = nullptr)
 {
     __shared__ double tables[201];
     const ScoreParams sp = stageScoreTables(spGlobal, tables);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
+        if (valid && !valid[i]) continue;               // tile pipeline: slot i holds a pair only where the flag is set (kernels_tile.cuh)
         const IndelTask t = tasks[i];
         IndelResult &out = results[i];
         out.accepted = 0;
@@ -184,6 +186,7 @@ __global__ void simpleIndelKernel(const ReferenceView ref, const ReadSetView rea
         o.cigarOffset = i * 5;
         out.fragment = o;
         for (unsigned k = 0; k < 5; ++k) out.cigar[k] = k < nOps ? ops[k] : 0u;
+        if (cigarsOut) for (unsigned k = 0; k < 5; ++k) cigarsOut[size_t(i) * 5 + k] = k < nOps ? ops[k] : 0u;      // the words as a pool of their own
         out.accepted = 1;
     }
 }

@@ -142,9 +142,10 @@ __global__ void shadowFlattenKernel(uint32_t requests, const uint32_t *__restric
                                     const isaac_ext_fragment_t *__restrict__ ungapped, const uint32_t *__restrict__ ungappedCigars,
                                     const isaac_ext_fragment_t *__restrict__ gapped, const uint32_t *__restrict__ gappedCigars,
                                     uint32_t gappedStride, isaac_ext_fragment_t *__restrict__ fragmentsOut, uint32_t *__restrict__ cigarsOut,
-                                    uint64_t *__restrict__ fragmentBeginOut)
+                                    uint64_t *__restrict__ fragmentBeginOut, const uint32_t fragmentTotal)
 {
     const uint32_t lane = threadIdx.x & 31u, warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) fragmentBeginOut[requests] = fragmentTotal;
     for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < requests; i += warpsPerGrid)
     {
         const uint32_t begin = taskBegin[i], size = counts[i], fb = fragmentBegin[i];

@@ -6,7 +6,7 @@
 // requests template_worker.cuh records in its planning mode, bit for bit.  No std::vector: the lists of equally good fragments
 // / pairs the reference keeps (of which only the entry picked by --scatter-repeats is ever read) are walked twice instead.
 // tests/cpp/test_template_worker.cu checks on the CPU that both give the same request lists (tests/test_template_worker.py).
-// NOT YET USED by the product path.
+// On the GPU it is the body of planRequestsKernel (kernels_templates.cuh).
 #pragma once
 #include <cfloat>
 #include <cstddef>
@@ -28,7 +28,7 @@ namespace isaac_b200
 struct PlanView
 {
     const isaac_ext_fragment_t *fragments;
-    const uint64_t *readFragmentBegin;      // clusterCount * readCount + 1
+    const uint32_t *listBegin, *listCount;  // the candidate list of (cluster, readIndex): fragments[listBegin[l] .. + listCount[l]), l = cluster * readCount + readIndex
     const uint8_t *built;                   // per cluster
     uint32_t readCount;
     uint32_t tlsMax, bestModel[2];          // TemplateLengthStatistics: getMax, getBestModel
@@ -164,9 +164,9 @@ ISAAC_HD inline unsigned planClusterRequests(const PlanView &v, const uint32_t c
 {
     unsigned count = 0;
     if (v.readCount != 2 || !v.built[cluster]) return 0;                                           // single-ended: pickBestFragment, no rescue
-    const uint64_t *begin = v.readFragmentBegin + size_t(cluster) * 2;
-    const isaac_ext_fragment_t *f[2] = {v.fragments + begin[0], v.fragments + begin[1]};
-    const int n[2] = {int(begin[1] - begin[0]), int(begin[2] - begin[1])};
+    const size_t l = size_t(cluster) * 2;
+    const isaac_ext_fragment_t *f[2] = {v.fragments + v.listBegin[l], v.fragments + v.listBegin[l + 1]};
+    const int n[2] = {int(v.listCount[l]), int(v.listCount[l + 1])};
     if (n[0] && n[1])                                                                              // pickBestPair
     {
         const PlanBestPair best = planLocateBestPair(v, f[0], n[0], f[1], n[1], cluster);

@@ -10,7 +10,7 @@
 #include <cstring>
 #include <vector>
 
-#include "host_pipeline.cuh"
+#include "../../isaac_aligner_b200/csrc/host_pipeline.cuh"
 
 namespace
 {

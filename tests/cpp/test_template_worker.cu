@@ -8,9 +8,10 @@
 #include "../../include/isaac_ext.h"
 #include "../../isaac_aligner_b200/csrc/host_pipeline.cuh"
 using namespace isaac_b200;
-#include "../../isaac_aligner_b200/csrc/template_worker.cuh"
+#include "template_worker.cuh"
 #include "../../isaac_aligner_b200/csrc/plan_device.cuh"
 #include "../../isaac_aligner_b200/csrc/shadow_window_device.cuh"
+#include "../../isaac_aligner_b200/csrc/finish_device.cuh"
 
 namespace
 {
@@ -97,8 +98,11 @@ extern "C" int plan_device_requests(uint32_t clusterCount, uint32_t readCount, c
                                     const isaac_ext_build_result_t *built, uint64_t requestCapacity, isaac_ext_rescue_request_t *requestsOut,
                                     uint64_t *clusterRequestBegin)
 {
+    const size_t lists = size_t(clusterCount) * readCount;
+    std::vector<uint32_t> listBegin(lists), listCount(lists);
+    for (size_t l = 0; l < lists; ++l) { listBegin[l] = uint32_t(built->readFragmentBegin[l]); listCount[l] = uint32_t(built->readFragmentBegin[l + 1] - built->readFragmentBegin[l]); }
     PlanView v;
-    v.fragments = built->fragments; v.readFragmentBegin = built->readFragmentBegin; v.built = built->built; v.readCount = readCount;
+    v.fragments = built->fragments; v.listBegin = listBegin.data(); v.listCount = listCount.data(); v.built = built->built; v.readCount = readCount;
     v.tlsMax = tls->max; v.bestModel[0] = tls->bestModel[0]; v.bestModel[1] = tls->bestModel[1]; v.scatterRepeats = options->scatterRepeats;
     uint64_t at = 0;
     clusterRequestBegin[0] = 0;
@@ -129,4 +133,50 @@ extern "C" int shadow_windows_device(const uint32_t *readLength, const isaac_ext
         rangeOut[2 * size_t(i)] = first; rangeOut[2 * size_t(i) + 1] = second;
     }
     return shadowModelCoherent(m) ? 0 : 1;
+}
+
+/// finish_device.cuh (the finish pass written for a one-thread-per-cluster kernel: glibc's exp / log10 replayed, no containers)
+/// cluster after cluster, on the same inputs as template_worker_finish; the CIGAR words are gathered the way
+/// gatherTemplateCigarsKernel gathers them
+extern "C" int finish_device_templates(uint32_t clusterCount, uint32_t readCount, const uint32_t *readLength, uint32_t contigCount,
+                                       const uint64_t *contigLength, const isaac_ext_tls_t *tls, const isaac_ext_template_options_t *options,
+                                       const isaac_ext_build_result_t *built, const isaac_ext_rescue_result_t *rescued,
+                                       const uint64_t *clusterRequestBegin, isaac_ext_template_t *templatesOut,
+                                       isaac_ext_fragment_t *fragmentsOut, uint64_t cigarCapacity, uint32_t *cigarsOut, uint64_t *cigarWordsOut)
+{
+    const size_t lists = size_t(clusterCount) * readCount;
+    std::vector<uint32_t> listBegin(lists), listCount(lists), requestBegin(size_t(clusterCount) + 1);
+    for (size_t l = 0; l < lists; ++l) { listBegin[l] = uint32_t(built->readFragmentBegin[l]); listCount[l] = uint32_t(built->readFragmentBegin[l + 1] - built->readFragmentBegin[l]); }
+    for (size_t c = 0; c <= clusterCount; ++c) requestBegin[c] = uint32_t(clusterRequestBegin[c]);
+    FinishView v;
+    v.fragments = built->fragments; v.listBegin = listBegin.data(); v.listCount = listCount.data(); v.built = built->built;
+    v.cigarPools[0] = built->cigars; v.cigarPools[1] = v.cigarPools[2] = nullptr; v.cigarPools[FINISH_POOL_RESCUE] = rescued->cigars;
+    v.rescueFragments = rescued->fragments; v.requestFragmentBegin = rescued->requestFragmentBegin; v.rescued = rescued->rescued;
+    v.clusterRequestBegin = requestBegin.data();
+    v.readCount = readCount; v.tlsMin = tls->min; v.tlsMax = tls->max; v.bestModel[0] = tls->bestModel[0]; v.bestModel[1] = tls->bestModel[1];
+    v.scatterRepeats = options->scatterRepeats; v.mapqThreshold = options->mapqThreshold; v.dodgyAlignmentScore = options->dodgyAlignmentScore;
+    v.logMismatchQ40 = logMismatchQ40();
+    const uint32_t rl[2] = {readLength[0], readCount > 1 ? readLength[1] : 0};
+    finishRestOfGenome(v, contigLength, contigCount, rl);
+    std::vector<unsigned char> scratch;
+    uint64_t words = 0;
+    for (uint32_t c = 0; c < clusterCount; ++c)
+    {
+        const uint64_t shadows = rescued->requestFragmentBegin[requestBegin[c + 1]] - rescued->requestFragmentBegin[requestBegin[c]];
+        uint64_t candidates = 0;
+        for (unsigned r = 0; r < readCount; ++r) candidates += listCount[size_t(c) * readCount + r];
+        scratch.assign(finishScratchBytes(shadows, candidates), 0xA5);
+        finishCluster(v, c, scratch.data(), shadows, candidates, templatesOut[c], fragmentsOut + size_t(c) * readCount);
+        for (unsigned r = 0; r < readCount; ++r)
+        {
+            isaac_ext_fragment_t &f = fragmentsOut[size_t(c) * readCount + r];
+            const uint32_t *src = f.cigarLength ? v.cigarPools[f.cigarOffset >> FINISH_POOL_SHIFT] + (f.cigarOffset & FINISH_POOL_MASK) : nullptr;
+            if (words + f.cigarLength > cigarCapacity) return ISAAC_EXT_E_CAPACITY;
+            for (unsigned k = 0; k < f.cigarLength; ++k) cigarsOut[words + k] = src[k];
+            f.cigarOffset = uint32_t(words);
+            words += f.cigarLength;
+        }
+    }
+    *cigarWordsOut = words;
+    return ISAAC_EXT_OK;
 }

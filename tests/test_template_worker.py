@@ -43,7 +43,7 @@ def flat_view(flat, cls):
                flat.cigars.ctypes.data if flat.cigars.size else None, flat.flags.ctypes.data, flat.fragments.size, flat.cigars.size)
 
 
-def worker_templates(lib, ref, genome, reads, config, mb, tls, options, threads=3):
+def worker_templates(lib, ref, genome, reads, config, mb, tls, options, threads=3, device_finish=True):
     g = oracle_lib.GenomeHolder(genome)
     n, rc = reads.cluster_count, reads.read_count
     built = oracle_lib.build_fragments(ref, g, reads, config, mb, threads=4)
@@ -64,6 +64,15 @@ def worker_templates(lib, ref, genome, reads, config, mb, tls, options, threads=
     words = ctypes.c_uint64()
     assert lib.template_worker_finish(*head, ctypes.byref(rescued_c), p(request_begin), p(templates), p(fragments),
                                       ctypes.c_uint64(cigars.size), p(cigars), ctypes.byref(words), ctypes.c_uint(threads)) == 0
+    if device_finish:
+        # the same inputs through finish_device.cuh (the body of finishTemplatesKernel): byte-identical records wanted
+        t2, f2, c2, w2 = np.zeros_like(templates), np.zeros_like(fragments), np.zeros_like(cigars), ctypes.c_uint64()
+        assert lib.finish_device_templates(*head, ctypes.byref(rescued_c), p(request_begin), p(t2), p(f2), ctypes.c_uint64(c2.size), p(c2),
+                                           ctypes.byref(w2)) == 0
+        assert t2.tobytes() == templates.tobytes(), "finish_device.cuh: templates differ from template_worker.cuh"
+        for name in FRAGMENT_DTYPE.names:
+            assert np.array_equal(f2[name], fragments[name]), "finish_device.cuh: fragment field %s differs" % name
+        assert w2.value == words.value and np.array_equal(c2[:w2.value], cigars[:words.value])
     return Templates(templates, fragments, cigars[:words.value].copy(), len(requests)), g
 
 
