@@ -60,9 +60,12 @@ def parse_args():
                         "pack: the io::FragmentHeader bin records of a tile's templates (isaac_ext_pack_fragments), fragments/s")
     p.add_argument("--compact", action="store_true", help="--workload pack: records cut to their total length instead of FragmentBuffer slots")
     p.add_argument("--pairs", type=int, default=None,
-                   help="read pairs per GPU of the pairs pipeline (default 200k as a side measurement of the micro run, 1M for --workload pairs; 0 disables)")
-    p.add_argument("--contigs", type=int, default=1, help="contigs of the synthetic genome (SURVEY 8(d) G3100: 24)")
-    p.add_argument("--n-fraction", type=float, default=0.0, help="fraction of the genome replaced by runs of N (G3100: 0.001)")
+                   help="read pairs per GPU of the pairs pipeline (default 2M: BASELINE configs[2] sharded, next to the micro run and for --workload pairs; 0 disables)")
+    p.add_argument("--pairs-genome-bases", type=int, default=3_100_000_000, help="genome of the pairs pipeline (SURVEY 8(d) G3100)")
+    p.add_argument("--pairs-contigs", type=int, default=24)
+    p.add_argument("--pairs-n-fraction", type=float, default=0.001)
+    p.add_argument("--contigs", type=int, default=1, help="contigs of the synthetic genome of the micro workload")
+    p.add_argument("--n-fraction", type=float, default=0.0, help="fraction of the micro workload's genome replaced by runs of N")
     p.add_argument("--indel-rate", type=float, default=5e-4, help="indel events per base of the simulated pairs (config 4: 1e-2)")
     return p.parse_args()
 
@@ -77,6 +80,25 @@ def make_workload(args, rank, n_candidates):
     reads = ReadSet(sim.bcl, (L, L))
     cand = synth.microbench_candidates(sim, genome, per_read=args.per_read, seed=synth.SEED_READS + 2 + 1000 * rank)
     return genome, reads, cand[:n_candidates]
+
+
+def bind_to_gpu_numa(device):
+    """Pins this rank to the host cores next to its GPU (NVML's ideal CPU affinity), so that the page-locked buffers it allocates
+    from here on and the threads that fill them live on the GPU's NUMA node.  Returns what it did, for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = sorted(64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1)
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"bound": False, "why": "no ideal core in this process's cpuset"}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "cores": "%d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))}
+    except Exception as e:      # noqa: BLE001
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
 
 
 class ClockSampler:
@@ -172,102 +194,125 @@ def workload_config(args):
                   % (args.candidates * (16 + 2 * 64 + (3 + args.cigar_stride) * 4) / 1e9)}
 
 
-def make_pairs_workload(args, rank, n_pairs):
-    """BASELINE configs[0]/[2]-style input: simulated FR pairs, seed matches from the error-free auto seeds + decoys,
-    explicit template length statistics."""
+def make_pairs_workload(args, rank, world, n_pairs):
+    """BASELINE configs[2] sharded over the ranks: the human-scale genome G3100 (3.1 Gbp in 24 contigs, 0.1 % N runs; every rank
+    holds the whole of it, like every GPU does), this rank's simulated FR pairs, seed matches from the error-free auto seeds +
+    decoys, explicit template length statistics.  Runs fork workers: call it before the process touches CUDA."""
     from isaac_aligner_b200 import synth
-    from isaac_aligner_b200.batch import MatchBatch, Tls
-    from isaac_aligner_b200.types import ReadSet
     L = args.read_length
-    genome = synth.make_genome(args.genome_bases, n_contigs=args.contigs, seed=synth.SEED_G5, n_fraction=args.n_fraction)
-    sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 7 + 1000 * rank, indel_rate=args.indel_rate,
-                               seed_offsets=synth.auto_seed_offsets(L))
+    workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    genome = synth.make_genome_parallel(args.pairs_genome_bases, n_contigs=args.pairs_contigs, seed=synth.SEED_G3100,
+                                        n_fraction=args.pairs_n_fraction, workers=workers)
+    sim = synth.simulate_pairs_parallel(genome, n_pairs, seed=synth.SEED_READS + 7 + 1000 * rank, workers=workers, L=L,
+                                        indel_rate=args.indel_rate, seed_offsets=synth.auto_seed_offsets(L))
     matches, begin = synth.make_matches(sim, genome, seed=synth.SEED_READS + 8 + 1000 * rank, decoy_rate=0.2)
-    return genome, ReadSet(sim.bcl, (L, L)), MatchBatch(matches, begin, synth.seed_table(sim), with_gaps=True), Tls.make()
+    return genome, sim.bcl, matches, begin, synth.seed_table(sim)
 
 
-def pairs_pipeline_gpu(ctx, reads, mb, tls, steps, warmup, all_ranks=False):
-    """FragmentBuilder::build for every cluster, then ShadowAligner::rescueShadow for every request of the stand-in
-    template policy, both through the host-pointer ABI (H2D / D2H inside).  Returns a dict with pairs/s."""
-    from isaac_aligner_b200 import synth
-    from isaac_aligner_b200.batch import copy_result
-    n = reads.cluster_count
-    flat = ctx.build_fragments(mb)                                       # also the first warm-up pass
-    req = synth.rescue_policy(flat.fragments, flat.begin, n)
-    resc = ctx.rescue_shadows(tls, req)
-    for _ in range(max(0, warmup - 1)):
-        ctx.build_fragments(mb, copy=False); ctx.rescue_shadows(tls, req, copy=False)
-    tb = tr = 0.0
-    l0 = ctx.launches
-    for _ in range(steps):
-        t0 = time.perf_counter(); ctx.build_fragments(mb, copy=False)
-        t1 = time.perf_counter(); ctx.rescue_shadows(tls, req, copy=False)
-        t2 = time.perf_counter()
-        tb += t1 - t0; tr += t2 - t1
-    tb /= steps; tr /= steps
-    # the whole TemplateBuilder (SURVEY 8f #1): build + the rescues the templates really ask for + pair selection / MAPQ
-    templates = ctx.build_templates(mb, tls)
-    tt = 0.0
-    for _ in range(steps):
-        t0 = time.perf_counter(); ctx.build_templates(mb, tls, copy=False); tt += time.perf_counter() - t0
-    tt /= steps
-    gaps = flat.fragments["gapCount"] > 0
-    # MatchSelectorStats of the tile (TileBarcodeStats per read and pass filter), summed over the ranks: the path's one exchange
+def pinned_like(a):
+    """a copy of numpy array `a` in page-locked host memory (what a caller that cares about transfer speed hands to the ABI)"""
     import torch
-    from isaac_aligner_b200 import distributed
+    t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+    v = t.numpy().view(a.dtype).reshape(a.shape)
+    v[...] = a
+    return v, t
+
+
+def pairs_pipeline_gpu(args, workload, local_rank, world, steps, warmup):
+    """aligned read pairs/s: per step ONE tile = isaac_ext_set_reads (BCL bytes up, decode) + isaac_ext_build_templates (seed matches
+    up, the whole TemplateBuilder on the device, templates down), host-pointer ABI with page-locked buffers = end to end.  Every rank
+    runs its own tiles (no data-path collective); the time is the maximum over the ranks; the one exchange is the sum of the tile
+    statistics.  Returns the dict of the bench line (rank 0) and what the CPU arm needs."""
+    import torch
+    from isaac_aligner_b200 import capi, distributed
+    from isaac_aligner_b200.batch import MatchBatch, Tls
+    from isaac_aligner_b200.types import Config, ReadSet
+    genome, bcl, matches, begin, seeds = workload
+    L = args.read_length
+    n = bcl.shape[0]
+    keep = []
+    bcl_p, t = pinned_like(bcl); keep.append(t)
+    matches_p, t = pinned_like(matches); keep.append(t)
+    begin_p, t = pinned_like(begin); keep.append(t)
+    reads = ReadSet(bcl_p, (L, L))
+    mb = MatchBatch(matches_p, begin_p, seeds, with_gaps=True)
+    tls = Tls.make()
+    config = Config.default(max_read_length=2 * L, device=local_rank, host_threads=max(1, (os.cpu_count() or 1) // world))
+    ctx = capi.Context(config)
+    ctx.set_reference(genome)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def tile():
+        ctx.set_reads(reads)
+        return ctx.build_templates(mb, tls, copy=False)
+
+    for _ in range(max(1, warmup)):
+        res = tile()
+    barrier()
+    l0 = ctx.launches
     t0 = time.perf_counter()
+    for _ in range(steps):
+        res = tile()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    launches = (ctx.launches - l0) // max(1, steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = ctx.build_templates(mb, tls, copy=False)           # the reads stay resident: the TemplateBuilder call alone
+    templates_ms = (time.perf_counter() - t0) * 1e3 / steps
+    d2h = n * 16 + 2 * n * 64 + int(res.cigarWords) * 4
+    times = torch.tensor([e2e_ms, templates_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms, templates_ms = (float(x) for x in times.cpu())
+    # MatchSelectorStats of the tile (TileBarcodeStats per read and pass filter), summed over the ranks: the path's one exchange
+    templates = ctx._templates(res)
     tile_stats = ctx.template_stats(mb, tls, templates)
-    stats_ms = (time.perf_counter() - t0) * 1e3
-    summed = torch.from_numpy(tile_stats.view(np.int64).copy())
-    # the all-reduce is a collective: only where every rank runs this function (the pairs workload; the side measurement of the
-    # micro workload runs on rank 0 alone)
-    if all_ranks and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-        summed = distributed.allreduce_stats(summed.cuda()).cpu()
-    read1 = summed.numpy().view(np.uint64)[0]
-    return {"pairs": n, "template_pairs_per_s": n / tt, "templates_ms": tt * 1e3, "template_stats_ms": stats_ms,
-            "match_selector_stats": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16]))),
-            "template_rescue_requests": int(templates.rescue_requests),
+    summed = torch.from_numpy(tile_stats.view(np.int64).copy()).cuda()
+    if world > 1:
+        summed = distributed.allreduce_stats(summed)
+    read1 = summed.cpu().numpy().view(np.uint64)[0]
+    line = {"workload": "BASELINE configs[2] sharded: %d simulated 2x%d bp FR pairs per GPU per step on the %d bp / %d contig / %.1f %% N "
+                        "synthetic genome resident on every GPU, indel events %.0e/base, seed matches from error-free auto seeds + 20 %% "
+                        "decoys, explicit TLS 245/350/455; one step = isaac_ext_set_reads + isaac_ext_build_templates of one tile"
+                        % (n, L, sum(int(c.size) for c in genome), len(genome), 100 * args.pairs_n_fraction, args.indel_rate),
+            "pairs_per_gpu": n, "n_gpus": world,
+            "value": world * n / (templates_ms * 1e-3), "unit": "pairs/s", "ms_per_step": templates_ms,
+            "value_is": "isaac_ext_build_templates alone (reads resident; matches up and templates down inside), max over ranks",
+            "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(bcl.nbytes + matches.nbytes + begin.nbytes), "d2h_bytes_per_step": int(d2h),
+                    "api": "isaac_ext_set_reads + isaac_ext_build_templates, page-locked host buffers"},
+            "gpu_launches_per_step": int(launches),
+            "matches_per_gpu": int(len(matches)), "rescue_requests": int(templates.rescue_requests),
             "templates_built": int(templates.templates["built"].sum()), "proper_pairs": int(templates.templates["properPair"].sum()),
-            "pairs_per_s": n / (tb + tr), "build_ms": tb * 1e3, "rescue_ms": tr * 1e3,
-            "matches": int(len(mb.matches)), "fragments": int(flat.fragments.size), "fragments_with_gaps": int(gaps.sum()),
-            "rescue_requests": int(len(req)), "rescued": int(resc.flags.sum()), "shadow_candidates": int(resc.fragments.size),
-            "gpu_launches_per_step": (ctx.launches - l0) // max(1, steps),
-            "policy": "template_*: isaac_ext_build_templates = the reference's TemplateBuilder end to end; pairs_per_s / build_ms / "
-                      "rescue_ms: the two batch calls alone with a stand-in policy (mates of all candidates are rescued unless both "
-                      "reads have an edit-distance-0 candidate)"}, flat, req
+            "match_selector_stats_all_ranks": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16])))}
+    ctx.close()
+    return line, (genome, ReadSet(bcl, (L, L)), MatchBatch(matches, begin, seeds, with_gaps=True), tls, config)
 
 
 def pairs_pipeline_cpu(genome, reads, mb, tls, config, sample_clusters):
-    """the same two calls through the reference's own code (or the scalar restatement) on all host threads, on the first
-    `sample_clusters` clusters"""
+    """the reference's own TemplateBuilder (oracle/_ref), one per host thread, on the first `sample_clusters` clusters"""
     import oracle_lib
-    from isaac_aligner_b200 import synth
-    from isaac_aligner_b200.batch import MatchBatch
+    from isaac_aligner_b200.batch import MatchBatch, TemplateOptions
     from isaac_aligner_b200.types import ReadSet
-    chk = oracle_lib.Oracle(oracle_lib.REF_SO) if os.path.exists(oracle_lib.REF_SO) else oracle_lib.port()
+    if not os.path.exists(oracle_lib.REF_SO):
+        return {"unavailable": "oracle/_ref/libisaac_ref.so did not travel to this box; TemplateBuilder has no second checker"}
+    chk = oracle_lib.Oracle(oracle_lib.REF_SO)
     cores = os.cpu_count() or 1
     k = min(sample_clusters, reads.cluster_count)
     sub_reads = ReadSet(reads.bcl[:k], reads.read_lengths)
     sub_mb = MatchBatch(mb.matches[:int(mb.begin[k])], mb.begin[:k + 1], mb.seeds, with_gaps=True)
     g = oracle_lib.GenomeHolder(genome)
+    oracle_lib.build_templates(chk, g, sub_reads, config, sub_mb, tls, TemplateOptions.make(), threads=cores)   # warm the genome cache
     t0 = time.perf_counter()
-    flat = oracle_lib.build_fragments(chk, g, sub_reads, config, sub_mb, threads=cores)
-    t1 = time.perf_counter()
-    req = synth.rescue_policy(flat.fragments, flat.begin, k)
-    t2 = time.perf_counter()
-    oracle_lib.rescue_shadows(chk, g, sub_reads, config, tls, req, threads=cores, fragments_per_request=96)
-    t3 = time.perf_counter()
-    sec = (t1 - t0) + (t3 - t2)
-    out = {"pairs": k, "pairs_per_s": k / sec, "build_ms": (t1 - t0) * 1e3, "rescue_ms": (t3 - t2) * 1e3, "cores": cores,
-           "kind": chk.kind}
-    if chk.kind == "reference":                          # the verbatim TemplateBuilder, one per host thread
-        from isaac_aligner_b200.batch import TemplateOptions
-        oracle_lib.build_templates(chk, g, sub_reads, config, sub_mb, tls, TemplateOptions.make(), threads=cores)   # warm the genome cache
-        t4 = time.perf_counter()
-        oracle_lib.build_templates(chk, g, sub_reads, config, sub_mb, tls, TemplateOptions.make(), threads=cores)
-        out["templates_ms"] = (time.perf_counter() - t4) * 1e3
-        out["template_pairs_per_s"] = k / (out["templates_ms"] * 1e-3)
-    return out
+    oracle_lib.build_templates(chk, g, sub_reads, config, sub_mb, tls, TemplateOptions.make(), threads=cores)
+    sec = time.perf_counter() - t0
+    return {"value": k / sec, "unit": "pairs/s", "cores": cores, "kind": chk.kind,
+            "sample": "first %d pairs of rank 0 through the reference's TemplateBuilder, one pass, %d host threads, %.2f s" % (k, cores, sec)}
 
 
 def run_b200(args):
@@ -278,6 +323,14 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the pairs workload is drawn by fork workers: before this process has a CUDA context
+    n_pairs = 2_000_000 if args.pairs is None else args.pairs
+    pairs_workload, pairs_error = None, None
+    if n_pairs:
+        try:
+            pairs_workload = make_pairs_workload(args, rank, world, n_pairs)
+        except Exception as e:      # noqa: BLE001
+            pairs_error = "%s: %s" % (type(e).__name__, e)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -287,6 +340,8 @@ def run_b200(args):
 
     L, n, stride = args.read_length, args.candidates, args.cigar_stride
     genome, reads, cand = make_workload(args, rank, n)
+    all_cores = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local_rank)
     n = len(cand)
     # the ranks of one box share its host cores: each context gets its share of the host threads
     config = Config.default(max_read_length=2 * L, device=local_rank, host_threads=max(1, (os.cpu_count() or 1) // world))
@@ -355,14 +410,16 @@ def run_b200(args):
         h_cand_t = pin((n, 16), torch.uint8)
         h_cand_t.numpy()[:] = cand.view(np.uint8).reshape(n, 16)
         h_cand = h_cand_t.numpy().reshape(-1).view(CANDIDATE_DTYPE)
-        # isaac_ext_*_batch_compact: 64-byte records + a dense CIGAR pool, chunked with overlapped copies
-        out_u = (pin((n, 64), torch.uint8), pin((n * 3,), torch.int32))
-        out_g = (pin((n, 64), torch.uint8), pin((n * 12,), torch.int32))
-        views = [(o[0].numpy().reshape(-1).view(FRAGMENT_DTYPE), o[1].numpy().view(np.uint32)) for o in (out_u, out_g)]
-        words = [0, 0]
+        # isaac_ext_align_batch_packed: what FragmentBuilder::alignFragments keeps of every candidate, 32 bytes each + the words of
+        # the accepted gapped CIGARs, chunked with overlapped copies
+        from isaac_aligner_b200.batch import expected_alignments
+        from isaac_aligner_b200.types import ALIGNMENT_DTYPE
+        out_a, out_p = pin((n, 32), torch.uint8), pin((n * 4,), torch.int32)
+        view_a, view_p = out_a.numpy().reshape(-1).view(ALIGNMENT_DTYPE), out_p.numpy().view(np.uint32)
+        words = [0]
 
         def e2e_step():
-            words[0], words[1] = ctx.extend_compact_both(h_cand, views[0][0], views[0][1], views[1][0], views[1][1])
+            words[0] = ctx.align_packed(h_cand, view_a, view_p)
 
         for _ in range(max(1, args.warmup // 2)):
             e2e_step()
@@ -377,18 +434,43 @@ def run_b200(args):
             import torch.distributed as dist
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item()) / args.steps
-        # the device results of the resident path and the host results of the e2e path must agree (all but cigarOffset)
-        res_dev = d_frag_g.cpu().numpy().reshape(-1).view(FRAGMENT_DTYPE)
-        for name in FRAGMENT_DTYPE.names:
-            if name != "cigarOffset":
-                assert np.array_equal(res_dev[name], views[1][0][name]), "resident and end-to-end results differ: " + name
+        # the host results of the e2e path must be what the device-resident results say (the acceptance rule applied in numpy)
+        res_u = d_frag_u.cpu().numpy().reshape(-1).view(FRAGMENT_DTYPE)
+        res_g = d_frag_g.cpu().numpy().reshape(-1).view(FRAGMENT_DTYPE)
+        want_a, want_p = expected_alignments(res_u, d_cig_u.cpu().numpy().view(np.uint32), res_g, d_cig_g.cpu().numpy().view(np.uint32), stride, L)
+        assert want_a.tobytes() == view_a.tobytes(), "resident and end-to-end results differ"
+        assert words[0] == len(want_p) and np.array_equal(view_p[:words[0]], want_p), "resident and end-to-end CIGAR pools differ"
+        del res_u, res_g, want_a, want_p
         e2e = {"value": world * cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 2 * n * 64 + 4 * (words[0] + words[1]),
-               "api": "isaac_ext_extend_batch_compact (ungapped + gapped records of every candidate), pinned host buffers"}
+               "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 32 + 4 * words[0],
+               "api": "isaac_ext_align_batch_packed (ungapped + gapped alignment of every candidate, the 32-byte record FragmentBuilder::alignFragments "
+                      "keeps of each + the accepted gapped CIGARs), page-locked host buffers; checked against the device-resident results"}
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
+    # ---- aligned read pairs/s (the other half of BASELINE.json's metric): configs[2] sharded over the ranks, every rank runs it.
+    # Whatever goes wrong in it is reported in its place and must not cost the bench line, but every rank must still take part
+    # in the collectives of the others: a failure on one rank is made a failure of all before any collective is entered.
+    pairs_line, pairs_cpu_inputs = None, None
+    if n_pairs:
+        ok = torch.tensor([0 if pairs_workload is None else 1], dtype=torch.int32, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()):
+            del d_cand, d_frag_u, d_cig_u, d_frag_g, d_cig_g
+            torch.cuda.empty_cache()
+            try:
+                pairs_line, pairs_cpu_inputs = pairs_pipeline_gpu(args, pairs_workload, local_rank, world, args.steps, args.warmup)
+            except Exception as e:      # noqa: BLE001
+                pairs_line = {"error": "%s: %s" % (type(e).__name__, e)}
+        else:
+            pairs_line = {"error": pairs_error or "the pairs workload could not be generated on another rank"}
+
     if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
         return
     tile_stats = dict(zip(distributed.STAT_NAMES, (int(x) for x in d_stats.cpu().numpy().view(np.uint64)[:8])))
     # ---- roofline of the dominant kernel, integer-pipe peak measured live
@@ -418,29 +500,24 @@ def run_b200(args):
         traffic_ungapped = int(entry["dram_bytes_per_launch"] * float(n) / entry["candidates"]) if L == 150 else None
     except (OSError, KeyError, ValueError):
         pass
-    # ---- CPU baseline on a bounded sample, same box
+    # ---- CPU baseline on a bounded sample, same box, on ALL its host cores (the GPU arm's NUMA binding is lifted)
+    os.sched_setaffinity(0, all_cores)
     cores = os.cpu_count() or 1
     ns = min(n, args.cpu_sample_per_core * cores)
     cpu_gcups, cpu_sec, kind, cores = cpu_arm(args, genome, reads, cand[:ns], config, 1, 0)
-    # ---- side measurement: the two TemplateBuilder-facing calls on simulated pairs (BASELINE "aligned read pairs/sec")
-    pairs_line = None
-    n_pairs = 200_000 if args.pairs is None else args.pairs
-    if n_pairs:
-        # a side measurement must not cost the bench line: whatever goes wrong in it is reported in its place
+    if pairs_line is not None and pairs_cpu_inputs is not None:
         try:
-            pgenome, preads, pmb, ptls = make_pairs_workload(args, rank, n_pairs)
-            ctx.set_reads(preads)
-            pairs_line, _, _ = pairs_pipeline_gpu(ctx, preads, pmb, ptls, max(1, args.steps // 2), 1)
-            pairs_line["cpu_baseline"] = pairs_pipeline_cpu(pgenome, preads, pmb, ptls, config, 4000 * cores)
+            pgenome, preads, pmb, ptls, pconfig = pairs_cpu_inputs
+            pairs_line["cpu_baseline"] = pairs_pipeline_cpu(pgenome, preads, pmb, ptls, pconfig, 4000 * cores)
         except Exception as e:      # noqa: BLE001
-            pairs_line = {"error": "%s: %s" % (type(e).__name__, e)}
+            pairs_line["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     emit(json.dumps({
         "metric": "banded_sw_gcups", "value": world * cells / (ms_per_step * 1e-3) / 1e9, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": workload_config(args),
-        "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks, "host": {"cores": os.cpu_count(), "numa_binding_rank0": numa},
         "tile_stats": tile_stats,
         "pairs_pipeline": pairs_line,
         "roofline": {"bound": "int32", "kernel": "swForwardKernel (timed with the swTraceScoreKernel launches it overlaps: "
@@ -468,78 +545,73 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def pairs_config(args, n_pairs):
-    return {"workload": "BASELINE configs[0]/[2] style: %d simulated 2x%d bp FR pairs per GPU per step on a %d bp random genome, "
-                        "indel events %.0e/base, seed matches from error-free auto seeds + 20%% decoys, explicit TLS 245/350/455, "
-                        "TemplateBuilder::buildFragments + buildTemplate of every cluster (isaac_ext_build_templates)"
-                        % (n_pairs, args.read_length, args.genome_bases, args.indel_rate),
-            "pairs_per_gpu": n_pairs, "read_length": args.read_length,
-            "l2": "per-step inputs+outputs exceed the 126 MB L2 for >= 500k pairs"}
-
-
 def run_pairs(args):
-    """--workload pairs: aligned read pairs/s of isaac_ext_build_templates (seed matches in, templates out, host-pointer ABI =
-    end to end), with the two batch calls underneath it timed separately in "pipeline"."""
+    """--workload pairs: the pairs pipeline alone as the bench line (metric aligned_read_pairs_per_s)."""
     import torch
-    from isaac_aligner_b200 import capi
-    from isaac_aligner_b200.types import Config
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n_pairs = 1_000_000 if args.pairs is None else args.pairs
+    n_pairs = 2_000_000 if args.pairs is None else args.pairs
+    cores = os.cpu_count() or 1
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
-        genome, reads, mb, tls = make_pairs_workload(args, 0, min(n_pairs, 6000 * cores))
-        config = Config.default(max_read_length=2 * args.read_length)
-        runs = [pairs_pipeline_cpu(genome, reads, mb, tls, config, reads.cluster_count) for _ in range(args.warmup + args.steps)][args.warmup:]
-        v = float(np.mean([r.get("template_pairs_per_s", r["pairs_per_s"]) for r in runs]))
-        sample = "%d pairs per step of the same generator, %d host threads" % (reads.cluster_count, cores)
+        from isaac_aligner_b200.batch import MatchBatch, Tls
+        from isaac_aligner_b200.types import Config, ReadSet
+        k = min(n_pairs, 6000 * cores)
+        genome, bcl, matches, begin, seeds = make_pairs_workload(args, 0, 1, k)
+        L = args.read_length
+        config = Config.default(max_read_length=2 * L)
+        runs = [pairs_pipeline_cpu(genome, ReadSet(bcl, (L, L)), MatchBatch(matches, begin, seeds, with_gaps=True), Tls.make(), config, k)
+                for _ in range(args.warmup + args.steps)][args.warmup:]
+        if "unavailable" in runs[0]:
+            emit(json.dumps({"impl": "reference", "unavailable": runs[0]["unavailable"]}))
+            return
+        v = float(np.mean([r["value"] for r in runs]))
         emit(json.dumps({"impl": "reference", "metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": reads.cluster_count / v * 1e3,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": k / v * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16+f64", "data": "synthetic",
-                          "config": pairs_config(args, n_pairs),
-                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": runs[0]["kind"], "sample": sample},
+                          "config": {"workload": "BASELINE configs[2] sharded, %d pairs per step of the same generator" % k},
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": runs[0]["kind"], "sample": runs[0]["sample"]},
                           "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+    workload = make_pairs_workload(args, rank, world, n_pairs)           # fork workers: before CUDA
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    genome, reads, mb, tls = make_pairs_workload(args, rank, n_pairs)
-    config = Config.default(max_read_length=2 * args.read_length, device=local_rank,
-                            host_threads=max(1, (os.cpu_count() or 1) // world))
-    ctx = capi.Context(config)
-    ctx.set_reference(genome)
-    ctx.set_reads(reads)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    all_cores = os.sched_getaffinity(0)
+    bind_to_gpu_numa(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.time()
+    line, cpu_inputs = pairs_pipeline_gpu(args, workload, local_rank, world, args.steps, args.warmup)
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
     if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    line, flat, req = pairs_pipeline_gpu(ctx, reads, mb, tls, args.steps, args.warmup, all_ranks=True)
-    t = torch.tensor([line["templates_ms"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    cpu = pairs_pipeline_cpu(genome, reads, mb, tls, config, 4000 * cores)
-    # one build_templates call: matches in; candidate records, rescue requests and shadow records cross PCIe inside it
-    h2d = len(mb.matches) * 16 + line["template_rescue_requests"] * 32
-    d2h = flat.fragments.size * 64 + flat.cigars.size * 4
-    v = world * n_pairs / (ms * 1e-3)
-    emit(json.dumps({"metric": "aligned_read_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                      "dtype": "int16+f64", "data": "synthetic", "config": pairs_config(args, n_pairs),
-                      "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                      "gpu_launches": int(line["gpu_launches_per_step"] * args.steps), "pipeline": line,
-                      "cpu_baseline": {"value": cpu.get("template_pairs_per_s", cpu["pairs_per_s"]), "unit": "pairs/s", "cores": cpu["cores"], "kind": cpu["kind"],
-                                       "sample": "first %d pairs of rank 0, one pass, %d host threads" % (cpu["pairs"], cpu["cores"])}}))
-    ctx.close()
+    pgenome, preads, pmb, ptls, pconfig = cpu_inputs
+    os.sched_setaffinity(0, all_cores)
+    cpu = pairs_pipeline_cpu(pgenome, preads, pmb, ptls, pconfig, 4000 * cores)
+    emit(json.dumps({"metric": "aligned_read_pairs_per_s", "value": line["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "int16+f64", "data": "synthetic", "config": {"workload": line["workload"], "pairs_per_gpu": n_pairs,
+                                                                              "l2": "per-step inputs + outputs exceed the 126 MB L2"},
+                      "e2e": line["e2e"], "gpu_launches": int(line["gpu_launches_per_step"] * args.steps), "clocks": clocks, "pipeline": line,
+                      "cpu_baseline": cpu}))
+
+
+def small_pairs_workload(args, n_pairs):
+    """a tile on the small genome for the kernel measurements that only need templates (--workload pack)"""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch, Tls
+    from isaac_aligner_b200.types import ReadSet
+    L = args.read_length
+    genome = synth.make_genome(args.genome_bases, n_contigs=args.contigs, seed=synth.SEED_G5, n_fraction=args.n_fraction)
+    sim = synth.simulate_pairs(genome, n_pairs, L=L, seed=synth.SEED_READS + 7, indel_rate=args.indel_rate, seed_offsets=synth.auto_seed_offsets(L))
+    matches, begin = synth.make_matches(sim, genome, seed=synth.SEED_READS + 8, decoy_rate=0.2)
+    return genome, ReadSet(sim.bcl, (L, L)), MatchBatch(matches, begin, synth.seed_table(sim), with_gaps=True), Tls.make()
 
 
 def run_pack(args):
@@ -557,7 +629,7 @@ def run_pack(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
     n_pairs = 500_000 if args.pairs is None else args.pairs
-    genome, reads, mb, tls = make_pairs_workload(args, 0, n_pairs)
+    genome, reads, mb, tls = small_pairs_workload(args, n_pairs)
     ctx = capi.Context(Config.default(max_read_length=2 * args.read_length))
     ctx.set_reference(genome)
     ctx.set_reads(reads)

@@ -359,6 +359,39 @@ int isaac_ext_extend_batch_compact(isaac_ext_ctx *ctx, uint32_t n, const isaac_e
                                    uint64_t *ungappedWordsOut, isaac_ext_fragment_t *gappedOut, uint32_t *gappedPoolOut,
                                    uint64_t gappedPoolCapacity, uint64_t *gappedWordsOut);
 
+/* What FragmentBuilder::alignFragments keeps of one candidate (FragmentBuilder.cpp:174-209), 32 bytes: the ungapped alignment, or
+ * the gapped one where the reference would have run the gapped aligner (more than BandedSmithWaterman::mismatchesCutoff = 5
+ * mismatches, :190-200) and its 5-clause rule accepts it (:202-209).  cigarLength = the alignment's words in the pool, one
+ * alignment after the other in candidate order.  An aligned record with cigarLength 0 has the CIGAR its clip counts imply --
+ * [leftClip S] [readLength - leftClip - rightClip M] [rightClip S], leftClip = reverse ? highClipped : lowClipped, rightClip the
+ * other one (UngappedAligner.cpp:64-81, FragmentMetadata::incrementClipLeft / Right) -- which is nearly every kept ungapped
+ * alignment (the exception: soft clips at a contig end, which the reference does not count in lowClipped / highClipped). */
+typedef struct isaac_ext_alignment {
+    int64_t  position;
+    double   logProbability;
+    uint16_t observedLength;
+    uint16_t mismatchCount;
+    uint16_t matchesInARow;
+    uint16_t editDistance;
+    uint16_t smithWatermanScore;
+    uint16_t lowClipped;
+    uint16_t highClipped;
+    uint8_t  gapsAndFlags;           /* gapCount | ISAAC_EXT_ALIGNMENT_ALIGNED | ISAAC_EXT_ALIGNMENT_GAPPED */
+    uint8_t  cigarLength;            /* words in the pool; 0 with _ALIGNED set: the implied CIGAR                     */
+} isaac_ext_alignment_t;
+#define ISAAC_EXT_ALIGNMENT_GAPS    0x3Fu
+#define ISAAC_EXT_ALIGNMENT_ALIGNED 0x40u   /* FragmentMetadata::isAligned of the kept alignment */
+#define ISAAC_EXT_ALIGNMENT_GAPPED  0x80u   /* the gapped alignment was accepted                 */
+
+/* alignUngapped + alignGapped + the acceptance rule for every candidate, chunked and overlapped like the calls above, with
+ * ONE 32-byte record per candidate on the way back (a quarter of the bytes of isaac_ext_extend_batch_compact: the copy back to the
+ * host is what bounds these calls, and on a box with several GPUs the host's ingest is shared).  The gapped aligner runs on every
+ * candidate (BASELINE configs[1] counts its cells that way); its result is only taken where the reference would have run it.
+ * ISAAC_EXT_E_UNSUPPORTED if a Smith-Waterman score does not fit 16 bits (scores far beyond the presets). */
+int isaac_ext_align_batch_packed(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                 isaac_ext_alignment_t *alignmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
+                                 uint64_t *cigarWordsOut);
+
 /* Device-resident variants of isaac_ext_ungapped_batch / isaac_ext_gapped_batch (UngappedAligner::alignUngapped,
  * UngappedAligner.cpp:39-92; GappedAligner::alignGapped, GappedAligner.cpp:167-249) used to time the kernels alone: the
  * candidate and result arrays are device pointers, the launch goes to 'cudaStream' (a cudaStream_t passed as void*) and returns

@@ -203,3 +203,61 @@ class PackedFragments:
                     parts.append(rec[:length])
                 offsets.append(offsets[-1] + length)
         return (np.concatenate(parts) if parts else np.zeros(0, np.uint8)), np.array(offsets, dtype=np.uint64)
+
+
+def expected_alignments(ungapped, ungapped_cigars, gapped, gapped_cigars, cigar_stride, read_length, gapped_mismatches_max=5, band=16, cutoff=5):
+    """What isaac_ext_align_batch_packed must return for candidates whose ungapped / gapped records (FRAGMENT_DTYPE, CIGARs at
+    strides 3 / cigar_stride) are known: FragmentBuilder::alignFragments' per-candidate decision (FragmentBuilder.cpp:190-209) in
+    numpy; one read length.  Returns (ALIGNMENT_DTYPE array, pool words).  Test / bench helper."""
+    from .types import ALIGNMENT_ALIGNED, ALIGNMENT_DTYPE, ALIGNMENT_GAPPED
+    u, g = ungapped, gapped
+    aligned = u["cigarLength"] > 0
+    d = u["logProbability"] - g["logProbability"]
+    lp_less = ~(np.abs(d) <= 0.0000001) & (u["logProbability"] < g["logProbability"])
+    observed = np.where(aligned, u["observedLength"], 0).astype(np.int64)
+    accept = (aligned & (u["mismatchCount"] > cutoff) & (g["matchCount"] > 0) & (g["matchCount"].astype(np.int64) + band > observed) &
+              (g["mismatchCount"] <= gapped_mismatches_max) & (u["mismatchCount"] > g["mismatchCount"]) & lp_less)
+    out = np.zeros(len(u), dtype=ALIGNMENT_DTYPE)
+    for name in ("position", "logProbability", "observedLength", "mismatchCount", "matchesInARow", "editDistance", "smithWatermanScore",
+                 "lowClipped", "highClipped"):
+        out[name] = np.where(accept, g[name], u[name])
+    gaps = np.where(accept, g["gapCount"], u["gapCount"]).astype(np.uint8)
+    out["gapsAndFlags"] = gaps | np.where(accept, ALIGNMENT_ALIGNED | ALIGNMENT_GAPPED, np.where(aligned, ALIGNMENT_ALIGNED, 0)).astype(np.uint8)
+    # the implied CIGAR of a kept ungapped alignment against its real one
+    cu = np.asarray(ungapped_cigars).reshape(-1, 3).astype(np.int64)
+    left = np.where(u["reverse"] != 0, u["highClipped"], u["lowClipped"]).astype(np.int64)
+    right = np.where(u["reverse"] != 0, u["lowClipped"], u["highClipped"]).astype(np.int64)
+    mid = read_length - left - right
+    w_left, w_mid, w_right = left << 4 | 4, mid << 4, right << 4 | 4
+    implied = np.zeros((len(u), 3), dtype=np.int64)
+    count = np.zeros(len(u), dtype=np.int64)
+    for present, word in ((left > 0, w_left), (mid > 0, w_mid), (right > 0, w_right)):
+        implied[np.arange(len(u)), np.minimum(count, 2)] = np.where(present, word, implied[np.arange(len(u)), np.minimum(count, 2)])
+        count += present
+    used = np.arange(3)[None, :] < u["cigarLength"].astype(np.int64)[:, None]
+    same = (count == u["cigarLength"]) & np.all(np.where(used, implied == cu, True), axis=1)
+    explicit = aligned & ~accept & ~same
+    out["cigarLength"] = np.where(accept, g["cigarLength"], np.where(explicit, u["cigarLength"], 0))
+    table = np.asarray(gapped_cigars).reshape(-1, cigar_stride)
+    rows = np.nonzero(accept | explicit)[0]
+    words = np.zeros((len(rows), cigar_stride), dtype=np.uint32)
+    is_gapped = accept[rows]
+    words[is_gapped] = table[rows[is_gapped]]
+    words[~is_gapped, :3] = cu[rows[~is_gapped]]
+    lens = out["cigarLength"][rows].astype(np.int64)
+    pool = words[np.arange(cigar_stride)[None, :] < lens[:, None]]
+    return out, pool.astype(np.uint32)
+
+
+def implied_ungapped_cigar(alignment, reverse, read_length):
+    """the CIGAR words of a kept ungapped alignment (see isaac_ext_alignment_t)"""
+    left = int(alignment["highClipped"] if reverse else alignment["lowClipped"])
+    right = int(alignment["lowClipped"] if reverse else alignment["highClipped"])
+    words = []
+    if left:
+        words.append(left << 4 | 4)
+    if read_length - left - right:
+        words.append((read_length - left - right) << 4)
+    if right:
+        words.append(right << 4 | 4)
+    return words

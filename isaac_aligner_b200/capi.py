@@ -35,7 +35,7 @@ EXPORTS = [
     "isaac_ext_tile_stats_device", "isaac_ext_ungapped_batch_compact", "isaac_ext_gapped_batch_compact",
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
-    "isaac_ext_template_stats", "isaac_ext_pack_fragments",
+    "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
 ]
 
@@ -155,6 +155,15 @@ class Context:
             self._h, ctypes.c_uint32(len(cand)), _p(cand), _p(ungapped_out), _p(ungapped_pool), ctypes.c_uint64(ungapped_pool.size),
             ctypes.byref(wu), _p(gapped_out), _p(gapped_pool), ctypes.c_uint64(gapped_pool.size), ctypes.byref(wg)))
         return int(wu.value), int(wg.value)
+
+    def align_packed(self, candidates, alignments_out, pool_out):
+        """isaac_ext_align_batch_packed: one 32-byte record per candidate (types.ALIGNMENT_DTYPE) + the words of the accepted gapped
+        CIGARs; returns the number of words"""
+        cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
+        w = ctypes.c_uint64()
+        self._check(_lib.isaac_ext_align_batch_packed(self._h, ctypes.c_uint32(len(cand)), _p(cand), _p(alignments_out), _p(pool_out),
+                                                      ctypes.c_uint64(pool_out.size), ctypes.byref(w)))
+        return int(w.value)
 
     def build_fragments(self, match_batch, copy=True):
         """FragmentBuilder::build for every cluster of the resident read set -> batch.FlatFragments

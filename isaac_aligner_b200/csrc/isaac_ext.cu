@@ -750,3 +750,12 @@ extern "C" int isaac_ext_extend_batch_compact(isaac_ext_ctx *ctx, uint32_t n, co
                          {true, gappedOut, gappedPoolOut, gappedPoolCapacity, gappedWordsOut}};
     return extendCompact(ctx, *ctx->e2e, n, candidates, passes, 2);
 }
+
+extern "C" int isaac_ext_align_batch_packed(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate_t *candidates,
+                                            isaac_ext_alignment_t *alignmentsOut, uint32_t *cigarPoolOut, uint64_t cigarPoolCapacity,
+                                            uint64_t *cigarWordsOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!ctx->e2e) ctx->e2e = new E2eState();
+    return alignPacked(ctx, *ctx->e2e, n, candidates, alignmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut);
+}

@@ -100,6 +100,65 @@ cigarCompactKernel(uint32_t n, isaac_ext_fragment_t *__restrict__ fragments, con
     }
 }
 
+/// FragmentBuilder::alignFragments' decision per candidate (FragmentBuilder.cpp:190-209): gapped[i] stays where the reference would
+/// have run the gapped aligner on the ungapped alignment and accepts the result, else it is replaced by ungapped[i].  A kept ungapped
+/// alignment whose CIGAR is the one its clip counts imply (isaac_ext_alignment_t) gets cigarLength 0 = no words for the pool; the
+/// others (soft clips at a contig end are not counted in lowClipped / highClipped, AlignerBase.cpp:50-82) take their words along in
+/// the gapped pass's CIGAR row.  status[i] = ISAAC_EXT_ALIGNMENT_ALIGNED / _GAPPED of the kept alignment.
+__global__ void selectAlignmentKernel(const ReadSetView reads, uint32_t n, const isaac_ext_fragment_t *__restrict__ ungapped,
+                                      const uint32_t *__restrict__ ungappedCigars, isaac_ext_fragment_t *__restrict__ gapped,
+                                      uint32_t *__restrict__ gappedCigars, uint32_t gappedStride, uint32_t gappedMismatchesMax,
+                                      uint8_t *__restrict__ status)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const isaac_ext_fragment_t u = ungapped[i];
+        const isaac_ext_fragment_t g = gapped[i];
+        const double d = u.logProbability - g.logProbability;
+        const bool lpLess = !(0.0000001 >= (d < 0 ? -d : d)) && u.logProbability < g.logProbability;          // ISAAC_LP_LESS (Quality.hh:104-112)
+        const unsigned observed = u.cigarLength ? u.observedLength : 0u;
+        const bool accept = u.cigarLength && ISAAC_EXT_SW_MISMATCH_CUTOFF < u.mismatchCount &&                 // :179 (unaligned are gone), :190-200
+                            g.matchCount && g.matchCount + ISAAC_EXT_BAND_WIDTH > observed && g.mismatchCount <= gappedMismatchesMax &&
+                            u.mismatchCount > g.mismatchCount && lpLess;                                       // :202-205
+        if (accept) { status[i] = uint8_t(ISAAC_EXT_ALIGNMENT_ALIGNED | ISAAC_EXT_ALIGNMENT_GAPPED); continue; }
+        isaac_ext_fragment_t k = u;
+        status[i] = u.cigarLength ? uint8_t(ISAAC_EXT_ALIGNMENT_ALIGNED) : uint8_t(0);
+        if (u.cigarLength)
+        {
+            const unsigned L = reads.length(u.readId);
+            const unsigned left = u.reverse ? u.highClipped : u.lowClipped, right = u.reverse ? u.lowClipped : u.highClipped;
+            uint32_t implied[3] = {0u, 0u, 0u}; unsigned words = 0;
+            if (left) implied[words++] = (left << 4) | ISAAC_EXT_CIGAR_SOFT_CLIP;
+            if (L > left + right) implied[words++] = ((L - left - right) << 4) | ISAAC_EXT_CIGAR_ALIGN;
+            if (right) implied[words++] = (right << 4) | ISAAC_EXT_CIGAR_SOFT_CLIP;
+            const uint32_t *actual = ungappedCigars + size_t(i) * 3;
+            bool same = words == u.cigarLength;
+            for (unsigned w = 0; same && w < words; ++w) same = implied[w] == actual[w];
+            if (same) k.cigarLength = 0;
+            else for (unsigned w = 0; w < u.cigarLength; ++w) gappedCigars[size_t(i) * gappedStride + w] = actual[w];
+        }
+        gapped[i] = k;
+    }
+}
+
+/// the kept 64-byte records as 32-byte isaac_ext_alignment_t; bit 16 of 'flag' if a score does not fit
+__global__ void packAlignmentsKernel(uint32_t n, const isaac_ext_fragment_t *__restrict__ kept, const uint8_t *__restrict__ status,
+                                     isaac_ext_alignment_t *__restrict__ out, uint32_t *__restrict__ flag)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const isaac_ext_fragment_t f = kept[i];
+        isaac_ext_alignment_t a;
+        a.position = f.position; a.logProbability = f.logProbability; a.observedLength = uint16_t(f.observedLength);
+        a.mismatchCount = f.mismatchCount; a.matchesInARow = f.matchesInARow; a.editDistance = f.editDistance;
+        a.smithWatermanScore = uint16_t(f.smithWatermanScore); a.lowClipped = f.lowClipped; a.highClipped = f.highClipped;
+        a.gapsAndFlags = uint8_t((f.gapCount & ISAAC_EXT_ALIGNMENT_GAPS) | status[i]);
+        a.cigarLength = uint8_t(f.cigarLength);
+        if (f.smithWatermanScore > 0xFFFFu || f.observedLength > 0xFFFFu || f.gapCount > ISAAC_EXT_ALIGNMENT_GAPS || f.cigarLength > 0xFFu) atomicOr(flag, 16u);
+        out[i] = a;
+    }
+}
+
 /// What validateCandidates does on the host for the one-shot entry points, on the device copy of a chunk: a candidate that
 /// names an unknown read / contig or lies outside [-ISAAC_EXT_MAX_CYCLES, contigLength] raises bit 1 / bit 2 of 'flag' (the
 /// call then fails as a whole) and is replaced by a harmless one so that the kernels behind never read out of bounds.

@@ -288,3 +288,66 @@ def make_matches(sim, genome, seed=SEED_READS + 3, decoy_rate=0.2, neighbor_rate
     begin = np.zeros(n + 1, dtype=np.uint64)
     np.cumsum(np.bincount(cluster.astype(np.int64), minlength=n), out=begin[1:])
     return m, begin
+
+
+# ---- bench-size workloads generated on several host cores (fork workers; call these BEFORE the process creates a CUDA context) ----
+_SHARED = {}
+
+
+def _genome_job(job):
+    c, n, seed, n_fraction, n_run = job
+    a = _SHARED["contigs"][c]
+    a[:] = make_genome(n, 1, seed=seed, n_fraction=n_fraction, n_run=n_run)[0]
+    return c
+
+
+def make_genome_parallel(total_bases, n_contigs=24, seed=SEED_G3100, n_fraction=0.001, n_run=(100, 10000), workers=8):
+    """like make_genome, one generator stream per contig (seed + contig index) so that the contigs can be
+    drawn side by side by fork workers that write into anonymous shared mappings."""
+    import mmap
+    import multiprocessing
+    per = -(-total_bases // n_contigs)
+    sizes = [min(per, total_bases - c * per) for c in range(n_contigs)]
+    contigs = [np.frombuffer(mmap.mmap(-1, max(1, n)), dtype=np.uint8, count=n) for n in sizes]
+    _SHARED["contigs"] = contigs
+    jobs = [(c, sizes[c], seed + c, n_fraction, n_run) for c in range(n_contigs)]
+    if workers <= 1:
+        for j in jobs:
+            _genome_job(j)
+    else:
+        with multiprocessing.get_context("fork").Pool(min(workers, n_contigs)) as pool:
+            pool.map(_genome_job, jobs, chunksize=1)
+    _SHARED.pop("contigs")
+    return contigs
+
+
+_SIM_FIELDS = ("bcl", "contig", "position", "reverse", "events", "seed_clean", "seed_shift")
+
+
+def _simulate_job(job):
+    n, seed, kw = job
+    sim = simulate_pairs(_SHARED["genome"], n, seed=seed, **kw)
+    return {f: getattr(sim, f) for f in _SIM_FIELDS if hasattr(sim, f)}
+
+
+def simulate_pairs_parallel(genome, n_pairs, seed=SEED_READS, workers=8, min_batch=50_000, **kw):
+    """simulate_pairs over sub-batches with their own generator streams (seed + 7919 * batch), drawn by fork workers and
+    concatenated in batch order: the result depends on (seed, workers, min_batch, n_pairs), not on scheduling."""
+    import multiprocessing
+    batches = max(1, min(workers, n_pairs // max(1, min_batch)))
+    sizes = [n_pairs * (k + 1) // batches - n_pairs * k // batches for k in range(batches)]
+    jobs = [(sizes[k], seed + 7919 * k, kw) for k in range(batches)]
+    _SHARED["genome"] = genome
+    if batches == 1:
+        parts = [_simulate_job(jobs[0])]
+    else:
+        with multiprocessing.get_context("fork").Pool(batches) as pool:
+            parts = pool.map(_simulate_job, jobs, chunksize=1)
+    _SHARED.pop("genome")
+    sim = Simulation(kw.get("L", 150))
+    for f in parts[0]:
+        setattr(sim, f, np.concatenate([p[f] for p in parts], axis=0))
+    if kw.get("seed_offsets") is not None:
+        sim.seed_offsets = tuple(kw["seed_offsets"])
+        sim.seed_length = kw.get("seed_length", 32)
+    return sim

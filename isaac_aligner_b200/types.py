@@ -100,3 +100,10 @@ class ReadSet:
 def cigar_to_string(words):
     ops = "MIDNSHP=X?"
     return "".join("%d%s" % (int(w) >> 4, ops[min(int(w) & 0xF, 9)]) for w in words)
+
+
+# isaac_ext_alignment_t (32 bytes): what FragmentBuilder::alignFragments keeps of one candidate
+ALIGNMENT_DTYPE = np.dtype([("position", "<i8"), ("logProbability", "<f8"), ("observedLength", "<u2"), ("mismatchCount", "<u2"),
+                            ("matchesInARow", "<u2"), ("editDistance", "<u2"), ("smithWatermanScore", "<u2"), ("lowClipped", "<u2"),
+                            ("highClipped", "<u2"), ("gapsAndFlags", "u1"), ("cigarLength", "u1")])
+ALIGNMENT_GAPS, ALIGNMENT_ALIGNED, ALIGNMENT_GAPPED = 0x3F, 0x40, 0x80

@@ -156,3 +156,50 @@ def test_compact_both_passes_in_one_call(capi):
         ctx.extend_compact_both(cand, fu, pu, fg, pg[:1000])
     assert e.value.code == 5
     ctx.close()
+
+
+@pytest.mark.parametrize("L,seed", [(100, 95), (150, 96)])
+def test_packed_alignments_are_what_align_fragments_keeps(capi, L, seed):
+    """isaac_ext_align_batch_packed: one 32-byte record per candidate = the ungapped alignment, or the gapped one where
+    FragmentBuilder::alignFragments would have run the gapped aligner and accepts it (FragmentBuilder.cpp:190-209); expected
+    records from BOTH checkers' ungapped / gapped results; the implied CIGAR of a kept ungapped alignment is its real one;
+    several chunks, masked read ends and candidates across both contig ends included"""
+    from isaac_aligner_b200.batch import expected_alignments, implied_ungapped_cigar
+    from isaac_aligner_b200.types import ALIGNMENT_DTYPE, ALIGNMENT_GAPPED
+    genome, sim, reads, cand = small_workload(n_pairs=2500, L=L, seed=seed, indel_rate=8e-3)
+    cfg = Config.default(max_read_length=2 * L)
+    ctx = capi.Context(cfg)
+    ctx.set_reference(genome)
+    ctx.set_reads(reads)
+    n = len(cand)
+    got, pool = np.zeros(n, dtype=ALIGNMENT_DTYPE), np.zeros(n * 8, dtype=np.uint32)
+    words = ctx.align_packed(cand, got, pool)
+    g = oracle_lib.GenomeHolder(genome)
+    for chk in checkers():
+        fu, cu, _ = chk.ungapped(g, reads, cfg, cand)
+        fg, cg, _ = chk.gapped(g, reads, cfg, cand, cigar_stride=32)
+        want, want_pool = expected_alignments(fu, cu, fg, cg, 32, L)
+        for name in ALIGNMENT_DTYPE.names:
+            x, y = got[name], want[name]
+            if name == "logProbability":
+                x, y = x.view(np.uint64), y.view(np.uint64)
+            assert np.array_equal(x, y), (chk.kind, name)
+        assert words == len(want_pool) and np.array_equal(pool[:words], want_pool), chk.kind
+        implied = np.nonzero((fu["cigarLength"] > 0) & (got["cigarLength"] == 0))[0]
+        assert len(implied) > n // 4
+        for i in implied[:: max(1, len(implied) // 3000)]:
+            k = int(fu["cigarLength"][i])
+            assert implied_ungapped_cigar(got[i], bool(fu["reverse"][i]), L) == [int(w) for w in cu.reshape(-1, 3)[i][:k]], i
+        # a kept ungapped alignment with explicit words: soft clips at a contig end (common.small_workload places candidates there)
+        assert ((got["cigarLength"] > 0) & ((got["gapsAndFlags"] & ALIGNMENT_GAPPED) == 0)).sum() > 0
+    assert ((got["gapsAndFlags"] & ALIGNMENT_GAPPED) != 0).sum() > 100
+    # many chunks of the same candidates: the same records, the pool in candidate order
+    big = np.concatenate([cand] * (1 + (3 * 1212416) // n))[:2 * 1212416 + 777]
+    gb, pb = np.zeros(len(big), dtype=ALIGNMENT_DTYPE), np.zeros(len(big) * 4, dtype=np.uint32)
+    wb = ctx.align_packed(big, gb, pb)
+    assert gb[:n].tobytes() == got.tobytes() and gb[n:2 * n].tobytes() == got.tobytes()
+    assert np.array_equal(pb[:words], pool[:words]) and wb == int(gb["cigarLength"].astype(np.int64).sum())
+    with pytest.raises(capi.ExtError) as e:
+        ctx.align_packed(big, gb, pb[:100])
+    assert e.value.code == 5
+    ctx.close()
