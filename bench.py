@@ -55,7 +55,9 @@ def parse_args():
     p.add_argument("--cigar-stride", type=int, default=32)
     p.add_argument("--cpu-sample-per-core", type=int, default=40_000)
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--workload", default="micro", choices=["micro", "pairs", "pack"],
+    p.add_argument("--band", type=int, default=32, help="--workload wide: lanes of the band (16 = the reference's, 32 = the widened band)")
+    p.add_argument("--alignments", type=int, default=2_000_000, help="--workload wide: alignments per GPU and step")
+    p.add_argument("--workload", default="micro", choices=["micro", "pairs", "pack", "wide"],
                    help="micro: BASELINE configs[1] (default, the bench line); pairs: build + rescue pipeline, read pairs/s; "
                         "pack: the io::FragmentHeader bin records of a tile's templates (isaac_ext_pack_fragments), fragments/s")
     p.add_argument("--compact", action="store_true", help="--workload pack: records cut to their total length instead of FragmentBuffer slots")
@@ -676,9 +678,184 @@ def run_pack(args):
     ctx.close()
 
 
+def make_wide_workload(args, rank, n):
+    """BASELINE configs[4]: 2x250 bp reads, widened band.  Every read of the simulated pairs against the window of the genome
+    around its true locus: band / 2 bases in front, band / 2 - 1 behind (GappedAligner's flanks, GappedAligner.cpp:51-82, scaled to
+    the band).  Returns ASCII queries [n, L] (strand order, 'n' for no-calls) and windows [n, L + band - 1]."""
+    from isaac_aligner_b200 import synth
+    L, W = args.read_length, args.band
+    genome = synth.make_genome(args.genome_bases, n_contigs=1, seed=synth.SEED_G5)
+    sim = synth.simulate_pairs(genome, -(-n // 2), L=L, seed=synth.SEED_READS + 5 + 1000 * rank, indel_rate=args.indel_rate)
+    bcl = sim.bcl.reshape(-1, 2, L)
+    fwd = bcl[:, 0, :]
+    rev = bcl[:, 1, ::-1]                                            # read 2 in strand order: reversed ...
+    acgt, comp = np.frombuffer(b"ACGT", dtype=np.uint8), np.frombuffer(b"TGCA", dtype=np.uint8)
+    q = np.empty((bcl.shape[0], 2, L), dtype=np.uint8)
+    q[:, 0, :] = np.where(fwd == 0, ord("n"), acgt[fwd & 3])
+    q[:, 1, :] = np.where(rev == 0, ord("n"), comp[rev & 3])       # ... and complemented
+    q = q.reshape(-1, L)[:n]
+    pos = sim.position.reshape(-1)[:n] - W // 2
+    idx = pos[:, None] + np.arange(L + W - 1)[None, :]
+    db = genome[0][idx]
+    return np.ascontiguousarray(q), np.ascontiguousarray(db)
+
+
+def run_wide(args):
+    """--workload wide: K3, the warp-wavefront banded Smith-Waterman with the widened band (isaac_ext_banded_sw_wide_batch).
+    value = GCUPS with the strings resident in HBM (band * L cells per alignment), e2e = the host-pointer entry point."""
+    import torch
+    from isaac_aligner_b200 import capi
+    from isaac_aligner_b200.types import Config
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.read_length == 150:
+        args.read_length = 250                                       # the workload's own default
+    L, W, n, stride = args.read_length, args.band, args.alignments, 32
+    scores = (0, -3, 11, 4)
+    cores = os.cpu_count() or 1
+    workload = {"workload": "BASELINE configs[4]: %d banded Smith-Waterman alignments per GPU per step, %d bp reads of simulated pairs against "
+                            "the %d-base windows around their loci, band of %d lanes (warp-wavefront kernel), bwa scores" % (n, L, L + W - 1, W),
+                "alignments_per_gpu": n, "read_length": L, "band": W,
+                "l2": "strings + results per step (%.1f GB) exceed the 126 MB L2" % (n * (2 * L + W + stride * 4 + 8) / 1e9)}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle_lib
+        k = min(n, 2000 * cores)
+        q, db = make_wide_workload(args, 0, k)
+        qoff, doff = np.arange(k, dtype=np.uint64) * L, np.arange(k, dtype=np.uint64) * (L + W - 1)
+        qlen = np.full(k, L, dtype=np.uint32)
+        # the reference itself has 16 lanes only: its own code at band 16, the band-width-parametrised restatement otherwise
+        chk = oracle_lib.Oracle(oracle_lib.REF_SO) if W == 16 and os.path.exists(oracle_lib.REF_SO) else oracle_lib.port()
+        times = []
+        for s_ in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            chk.banded_sw_flat(q.reshape(-1), qoff, qlen, db.reshape(-1), doff, scores, max_read_length=2 * L, cigar_stride=stride, threads=cores,
+                               band=None if W == 16 else W)
+            if s_ >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        sec = float(np.mean(times))
+        v = k * W * L / sec / 1e9
+        emit(json.dumps({"impl": "reference", "metric": "banded_sw_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "int16", "data": "synthetic", "config": workload,
+                          "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": chk.kind,
+                                           "sample": "%d alignments per step, %d host threads%s" % (k, cores, "" if W == 16 else
+                                                     "; the reference hard-wires 16 lanes, a wider band runs its scalar restatement")},
+                          "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    q, db = make_wide_workload(args, rank, n)
+    all_cores = os.sched_getaffinity(0)
+    bind_to_gpu_numa(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = capi.Context(Config.default(max_read_length=2 * L, device=local_rank))
+    qoff, doff = np.arange(n, dtype=np.uint64) * L, np.arange(n, dtype=np.uint64) * (L + W - 1)
+    qlen = np.full(n, L, dtype=np.uint32)
+    d_q, d_db = torch.from_numpy(q).to(dev), torch.from_numpy(db).to(dev)
+    d_qoff, d_doff = torch.from_numpy(qoff.view(np.int64)).to(dev), torch.from_numpy(doff.view(np.int64)).to(dev)
+    d_qlen = torch.from_numpy(qlen.view(np.int32)).to(dev)
+    d_cig = torch.empty((n, stride), dtype=torch.int32, device=dev)
+    d_len, d_off = torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ctx.banded_sw_wide_device(W, n, d_q.data_ptr(), d_qoff.data_ptr(), d_qlen.data_ptr(), d_db.data_ptr(), d_doff.data_ptr(), L, scores,
+                                  stride, d_cig.data_ptr(), d_len.data_ptr(), d_off.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    t_wall0 = time.time()
+    l0 = ctx.launches
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        step()
+    stop.record()
+    barrier()
+    launches = ctx.launches - l0
+    t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    cells = float(n) * W * L
+    # ---- end to end: host strings in, CIGARs out
+    hq, keep1 = pinned_like(q)
+    hdb, keep2 = pinned_like(db)
+
+    def e2e_step():
+        return ctx._check(capi._lib.isaac_ext_banded_sw_wide_batch(
+            ctx._h, W, n, hq.ctypes.data, qoff.ctypes.data, qlen.ctypes.data, hdb.ctypes.data, doff.ctypes.data, scores[0], scores[1], scores[2],
+            scores[3], stride, h_cig.ctypes.data, h_len.ctypes.data, h_off.ctypes.data))
+
+    h_cig, k3 = pinned_like(np.zeros((n, stride), dtype=np.uint32))
+    h_len, k4 = pinned_like(np.zeros(n, dtype=np.uint32))
+    h_off, k5 = pinned_like(np.zeros(n, dtype=np.uint32))
+    import ctypes
+    capi._lib.isaac_ext_banded_sw_wide_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32] + [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + \
+        [ctypes.c_uint32] + [ctypes.c_void_p] * 3
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    dt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = float(dt.item())
+    assert np.array_equal(h_len, d_len.cpu().numpy().view(np.uint32)) and np.array_equal(h_cig, d_cig.cpu().numpy().view(np.uint32)), "resident and end-to-end results differ"
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    peak_add = ctx.measure_int32_peak(0)
+    # ---- CPU baseline + parity of the sample: the band-width-parametrised restatement (the reference has 16 lanes only)
+    import oracle_lib
+    os.sched_setaffinity(0, all_cores)
+    k = min(n, 2000 * cores)
+    chk = oracle_lib.port()
+    t0 = time.perf_counter()
+    cr, lr, orf = chk.banded_sw_flat(q[:k].reshape(-1), qoff[:k], qlen[:k], db[:k].reshape(-1), doff[:k], scores, max_read_length=2 * L,
+                                     cigar_stride=stride, threads=cores, band=W)
+    sec = time.perf_counter() - t0
+    assert np.array_equal(lr, h_len[:k]) and np.array_equal(cr, h_cig[:k]) and np.array_equal(orf, h_off[:k]), "GPU and CPU model differ"
+    achieved = cells / (ms * 1e-3) * OPS_PER_CELL
+    emit(json.dumps({"metric": "banded_sw_gcups", "value": world * cells / (ms * 1e-3) / 1e9, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+                      "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "int16", "data": "synthetic", "config": workload,
+                      "e2e": {"value": world * cells / (e2e_ms * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms,
+                              "h2d_bytes_per_step": int(q.nbytes + db.nbytes + qoff.nbytes + doff.nbytes + qlen.nbytes),
+                              "d2h_bytes_per_step": int(h_cig.nbytes + h_len.nbytes + h_off.nbytes), "api": "isaac_ext_banded_sw_wide_batch, page-locked host buffers"},
+                      "gpu_launches": int(launches), "clocks": clocks,
+                      "roofline": {"bound": "int32", "kernel": "bandedSwWideKernel<%d>" % W, "achieved": achieved / 1e12, "peak": peak_add / 1e12, "unit": "TOP/s",
+                                   "frac": achieved / peak_add, "traffic": None, "ops_per_cell": OPS_PER_CELL, "ms_per_launch": ms,
+                                   "peak_source": "measured live by isaac_ext_measure_int32_peak (add.s32)",
+                                   "note": "a band lane per warp lane: the exchanges between band lanes are shuffles, which the thread-per-alignment kernel of the "
+                                           "16-lane band does not pay; direction planes stay in shared memory (no HBM traffic for them)"},
+                      "cpu_baseline": {"value": k * W * L / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": chk.kind,
+                                       "sample": "first %d alignments of rank 0 through the band-width-parametrised restatement (the reference hard-wires 16 lanes), "
+                                                 "%d host threads, %.2f s; results equal the GPU's" % (k, cores, sec)}}))
+    ctx.close()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.workload == "pack":
+    if a.workload == "wide":
+        run_wide(a)
+    elif a.workload == "pack":
         run_pack(a)
     elif a.workload == "pairs":
         run_pairs(a)

@@ -481,6 +481,59 @@ typedef struct isaac_ext_pack_result {
 int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const struct isaac_ext_template_result *templates,
                              const isaac_ext_pack_options_t *options, isaac_ext_pack_result_t *result);
 
+/* ---- one tile, the way MatchSelector::parallelSelect drives it (MatchSelector.cpp:370-443) ------------------------------ */
+/* Inputs as isaac-align leaves them for the match selector: the tile's BclClusters buffer and its match records (raw 16-byte
+ * alignment::Match as io::MatchWriter writes them, sorted by cluster / location / seed, SelectMatchesTransition.cpp:242-254;
+ * clusters are delimited by the cluster field of the seed ids like findNextCluster does, MatchSelector.cpp:262-277). */
+typedef struct isaac_ext_tile {
+    isaac_ext_reads_t reads;
+    const isaac_ext_match_t *matches;
+    uint64_t matchCount;
+    const isaac_ext_seed_t *seeds;
+    uint32_t seedCount;
+    uint32_t withGaps;
+    const uint8_t *pf;                    /* BclClusters::pf per cluster, or NULL = all pass                                  */
+    uint32_t baseQualityCutoff;           /* --base-quality-cutoff, 0 = none (MatchSelector.cpp:300)                          */
+    int32_t  mateDriftRange;
+    const isaac_ext_tls_t *tls;           /* user-defined / earlier tile's template length statistics, or NULL = determine them
+                                             from this tile (MatchSelector.cpp:401-417)                                       */
+    isaac_ext_template_options_t options;
+    const struct isaac_ext_pack_options *pack;   /* non-NULL: also leave the io::FragmentHeader records of the tile          */
+} isaac_ext_tile_t;
+
+typedef struct isaac_ext_tile_result {
+    isaac_ext_template_result_t templates;       /* owned by the context, valid until its next call                           */
+    isaac_ext_tls_t tls;                         /* the statistics the templates were built with                              */
+    uint32_t tlsStable;                          /* 1 when given by the caller or stable within the tile                      */
+    uint32_t packedValid;
+    uint64_t stats[4 * 32];                      /* isaac_ext_template_stats of the tile                                      */
+    const uint16_t *endCyclesMasked;             /* Read::endCyclesMasked_ after quality trimming, or NULL (no cutoff)        */
+} isaac_ext_tile_result_t;
+
+/* set_reads -> trim_low_quality_ends -> determine_template_length (unless given) -> build_templates -> template_stats
+ * (-> pack_fragments, result through isaac_ext_tile_packed): every step is a GPU pass of this library.  Tiles are independent once
+ * the statistics are fixed: with several GPUs rank r runs tiles r, r + G, ... and the callers sum result.stats. */
+int isaac_ext_select_tile(isaac_ext_ctx *ctx, const isaac_ext_tile_t *tile, isaac_ext_tile_result_t *result);
+/* the io::FragmentHeader records the last isaac_ext_select_tile with tile.pack left (see isaac_ext_pack_fragments) */
+int isaac_ext_tile_packed(isaac_ext_ctx *ctx, struct isaac_ext_pack_result *packedOut);
+
+/* BandedSmithWaterman::align on a band of bandWidth lanes as a warp-level wavefront (band lanes across the lanes of a warp,
+ * __shfl_sync between neighbouring band lanes, direction planes in shared memory): the variant for long reads and the widened band
+ * of BASELINE configs[4] (2x250 bp, bandWidth 32).  Same arguments and results as isaac_ext_banded_sw_batch; databases hold
+ * queryLength + bandWidth - 1 bases.  bandWidth 16 is the reference's band (bit-exact with BandedSmithWaterman.cpp:84-462);
+ * bandWidth 32 has no reference behaviour (the reference hard-wires 16 lanes, BandedSmithWaterman.hh:88-89): it is bit-exact
+ * with the band-width-parametrised model of oracle/ whose 16-lane instance equals the reference.  The _device variant takes
+ * device pointers and a stream and returns without synchronising. */
+int isaac_ext_banded_sw_wide_batch(isaac_ext_ctx *ctx, uint32_t bandWidth, uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                                   const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                                   int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                                   uint32_t cigarStride, uint32_t *cigarOut, uint32_t *cigarLengthOut, uint32_t *offsetOut);
+int isaac_ext_banded_sw_wide_batch_device(isaac_ext_ctx *ctx, uint32_t bandWidth, uint32_t n, const void *dQueries,
+                                          const void *dQueryOffsets, const void *dQueryLengths, const void *dDatabases,
+                                          const void *dDatabaseOffsets, uint32_t maxQueryLength, int matchScore, int mismatchScore,
+                                          int gapOpenScore, int gapExtendScore, uint32_t cigarStride, void *dCigarOut,
+                                          void *dCigarLengthOut, void *dOffsetOut, void *cudaStream);
+
 /* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
  * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
 int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);

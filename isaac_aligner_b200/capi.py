@@ -36,6 +36,7 @@ EXPORTS = [
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
     "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
+    "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
 ]
 
@@ -118,6 +119,28 @@ class Context:
             ctypes.c_int(scores[0]), ctypes.c_int(scores[1]), ctypes.c_int(scores[2]), ctypes.c_int(scores[3]),
             ctypes.c_uint32(cigar_stride), _p(cig), _p(ciglen), _p(off)))
         return cig, ciglen, off
+
+    def banded_sw_wide(self, band, queries, dbs, scores, cigar_stride=64):
+        """isaac_ext_banded_sw_wide_batch: the warp-wavefront kernel on a band of `band` lanes; lists of bytes in"""
+        qbuf = np.frombuffer(b"".join(queries), dtype=np.uint8)
+        dbuf = np.frombuffer(b"".join(dbs), dtype=np.uint8)
+        qlen = np.array([len(q) for q in queries], dtype=np.uint32)
+        qoff = np.concatenate([[0], np.cumsum(qlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        dlen = np.array([len(d) for d in dbs], dtype=np.uint64)
+        doff = np.concatenate([[0], np.cumsum(dlen[:-1], dtype=np.uint64)]).astype(np.uint64)
+        n = len(qlen)
+        cig, ciglen, off = np.zeros((n, cigar_stride), dtype=np.uint32), np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        self._check(_lib.isaac_ext_banded_sw_wide_batch(
+            self._h, ctypes.c_uint32(band), ctypes.c_uint32(n), _p(qbuf), _p(qoff), _p(qlen), _p(dbuf), _p(doff), ctypes.c_int(scores[0]),
+            ctypes.c_int(scores[1]), ctypes.c_int(scores[2]), ctypes.c_int(scores[3]), ctypes.c_uint32(cigar_stride), _p(cig), _p(ciglen), _p(off)))
+        return cig, ciglen, off
+
+    def banded_sw_wide_device(self, band, n, d_q, d_qoff, d_qlen, d_db, d_doff, max_len, scores, cigar_stride, d_cig, d_ciglen, d_off, stream):
+        self._check(_lib.isaac_ext_banded_sw_wide_batch_device(
+            self._h, ctypes.c_uint32(band), ctypes.c_uint32(n), ctypes.c_void_p(d_q), ctypes.c_void_p(d_qoff), ctypes.c_void_p(d_qlen),
+            ctypes.c_void_p(d_db), ctypes.c_void_p(d_doff), ctypes.c_uint32(max_len), ctypes.c_int(scores[0]), ctypes.c_int(scores[1]),
+            ctypes.c_int(scores[2]), ctypes.c_int(scores[3]), ctypes.c_uint32(cigar_stride), ctypes.c_void_p(d_cig), ctypes.c_void_p(d_ciglen),
+            ctypes.c_void_p(d_off), ctypes.c_void_p(stream)))
 
     def ungapped(self, candidates, with_masks=True, out=None):
         cand = np.ascontiguousarray(candidates, dtype=CANDIDATE_DTYPE)
@@ -272,6 +295,10 @@ class Context:
         self._check(_lib.isaac_ext_pack_fragments(self._h, ctypes.byref(tr), ctypes.byref(options.c), ctypes.byref(res)))
         if not copy:
             return res                     # pointers into the context's buffers (bench.py: no host copy inside the timed region)
+        return self._packed(res, bool(options.c.compact))
+
+    def _packed(self, res, compact=False):
+        from .batch import PackedFragments
         n, rc = self.reads.cluster_count, self.reads.read_count
 
         def arr(ptr, dtype, count):
@@ -279,7 +306,7 @@ class Context:
             return np.frombuffer(buf, dtype=dtype).copy()
 
         records = arr(res.records, np.uint8, int(res.recordBytes)) if res.recordBytes else np.zeros(0, np.uint8)
-        if not options.c.compact:
+        if not compact:
             records = records.reshape(n, res.recordLength)
         return PackedFragments(records, arr(res.fStrandPos, np.uint64, n * rc).reshape(n, rc),
                                arr(res.initialized, np.uint8, n * rc).reshape(n, rc), int(res.recordLength),

@@ -16,6 +16,7 @@
 #include "kernels_rescue.cuh"
 #include "host_build.cuh"
 #include "kernels_stats.cuh"
+#include "sw_wide.cuh"
 
 using namespace isaac_b200;
 
@@ -33,6 +34,8 @@ struct PackState;                      // isaac_ext_pack.cuh
 void releasePack(PackState *state);
 struct AsyncState;                     // isaac_ext_async.cuh
 void releaseAsync(AsyncState *state);
+struct SelectState;                    // isaac_ext_select.cuh
+void releaseSelect(SelectState *state);
 
 struct isaac_ext_ctx
 {
@@ -58,6 +61,7 @@ struct isaac_ext_ctx
     TileState *tile = nullptr;            // device-resident tile pipeline: isaac_ext_build_fragments / _rescue_shadows / _build_templates
     PackState *pack = nullptr;            // buffers of isaac_ext_pack_fragments
     AsyncState *async = nullptr;          // the call in flight between isaac_ext_submit_* and isaac_ext_wait
+    SelectState *select = nullptr;        // isaac_ext_select_tile
     double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
@@ -265,6 +269,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     releaseTemplates(ctx->templates);
     releaseTile(ctx->tile);
     releasePack(ctx->pack);
+    releaseSelect(ctx->select);
     delete ctx;
 }
 
@@ -667,6 +672,106 @@ extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const c
     return checkErrorFlag(ctx);
 }
 
+/// launch of the warp-wavefront kernel over device-resident strings
+static int bandedSwWideLaunch(isaac_ext_ctx *ctx, uint32_t bandWidth, uint32_t n, const unsigned char *dQueries, const uint64_t *dQueryOffsets,
+                              const uint32_t *dQueryLengths, const unsigned char *dDatabases, const uint64_t *dDatabaseOffsets,
+                              uint32_t maxQueryLength, int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                              uint32_t cigarStride, uint32_t *dCigarOut, uint32_t *dCigarLengthOut, uint32_t *dOffsetOut, cudaStream_t stream)
+{
+    if (bandWidth != 16 && bandWidth != 32) return ctx->fail(ISAAC_EXT_E_UNSUPPORTED, "band width must be 16 or 32 (the band lies across the lanes of one warp)");
+    std::string why;
+    if (maxQueryLength > ctx->cfg.maxReadLength) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "query longer than config.maxReadLength");
+    if (!swScoresSupported(matchScore, mismatchScore, gapOpenScore, gapExtendScore, ctx->cfg.maxReadLength, why))
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, why);
+    const unsigned perWarp = 32u / bandWidth;
+    const size_t shared = size_t(swWideSharedBytes(maxQueryLength, bandWidth)) * SW_WIDE_WARPS * perWarp;
+    if (shared > 200 * 1024) return ctx->fail(ISAAC_EXT_E_CAPACITY, "query too long for the direction planes of the wavefront kernel in shared memory");
+    const SwScores sw = {matchScore, mismatchScore, gapOpenScore, gapExtendScore, -32768 + gapOpenScore};
+    const uint64_t perBlock = uint64_t(SW_WIDE_WARPS) * perWarp;
+    // resident CTAs per SM by shared memory (227 KB), at most 8: a grid of whole waves
+    const unsigned perSm = unsigned(std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / std::max<size_t>(shared, 1))));
+    const unsigned grid = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((n + perBlock - 1) / perBlock, uint64_t(ctx->smCount) * perSm)));
+    if (bandWidth == 32)
+    {
+        if (shared > 48 * 1024) CK(cudaFuncSetAttribute(bandedSwWideKernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shared)));
+        bandedSwWideKernel<32><<<grid, SW_WIDE_WARPS * 32, shared, stream>>>(n, dQueries, dQueryOffsets, dQueryLengths, dDatabases, dDatabaseOffsets, sw,
+                                                                              maxQueryLength, cigarStride, dCigarOut, dCigarLengthOut, dOffsetOut, ctx->errorFlag.p);
+    }
+    else
+    {
+        if (shared > 48 * 1024) CK(cudaFuncSetAttribute(bandedSwWideKernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(shared)));
+        bandedSwWideKernel<16><<<grid, SW_WIDE_WARPS * 32, shared, stream>>>(n, dQueries, dQueryOffsets, dQueryLengths, dDatabases, dDatabaseOffsets, sw,
+                                                                              maxQueryLength, cigarStride, dCigarOut, dCigarLengthOut, dOffsetOut, ctx->errorFlag.p);
+    }
+    ++ctx->launches;
+    return ctx->cuda(cudaGetLastError(), "bandedSwWideKernel");
+}
+
+extern "C" int isaac_ext_banded_sw_wide_batch_device(isaac_ext_ctx *ctx, uint32_t bandWidth, uint32_t n, const void *dQueries,
+                                                     const void *dQueryOffsets, const void *dQueryLengths, const void *dDatabases,
+                                                     const void *dDatabaseOffsets, uint32_t maxQueryLength, int matchScore, int mismatchScore,
+                                                     int gapOpenScore, int gapExtendScore, uint32_t cigarStride, void *dCigarOut,
+                                                     void *dCigarLengthOut, void *dOffsetOut, void *cudaStream)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!n) return ISAAC_EXT_OK;
+    if (!dQueries || !dQueryOffsets || !dQueryLengths || !dDatabases || !dDatabaseOffsets || !dCigarOut || !dCigarLengthOut || !dOffsetOut ||
+        !cigarStride || !maxQueryLength)
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
+    return bandedSwWideLaunch(ctx, bandWidth, n, static_cast<const unsigned char *>(dQueries), static_cast<const uint64_t *>(dQueryOffsets),
+                              static_cast<const uint32_t *>(dQueryLengths), static_cast<const unsigned char *>(dDatabases),
+                              static_cast<const uint64_t *>(dDatabaseOffsets), maxQueryLength, matchScore, mismatchScore, gapOpenScore,
+                              gapExtendScore, cigarStride, static_cast<uint32_t *>(dCigarOut), static_cast<uint32_t *>(dCigarLengthOut),
+                              static_cast<uint32_t *>(dOffsetOut), cudaStream_t(cudaStream));
+}
+
+extern "C" int isaac_ext_banded_sw_wide_batch(isaac_ext_ctx *ctx, uint32_t bandWidth, uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                                              const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                                              int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                                              uint32_t cigarStride, uint32_t *cigarOut, uint32_t *cigarLengthOut, uint32_t *offsetOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!n) return ISAAC_EXT_OK;
+    if (!queries || !queryOffsets || !queryLengths || !databases || !databaseOffsets || !cigarOut || !cigarLengthOut || !offsetOut || !cigarStride)
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
+    if (bandWidth != 16 && bandWidth != 32) return ctx->fail(ISAAC_EXT_E_UNSUPPORTED, "band width must be 16 or 32 (the band lies across the lanes of one warp)");
+    uint32_t maxLen = 0; uint64_t qBytes = 0, dBytes = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (!queryLengths[i]) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "empty query");
+        maxLen = std::max(maxLen, queryLengths[i]);
+        qBytes = std::max(qBytes, queryOffsets[i] + queryLengths[i]);
+        dBytes = std::max(dBytes, databaseOffsets[i] + queryLengths[i] + bandWidth - 1);
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->dAscii.reserve(qBytes + dBytes));
+    CK(ctx->dOffsets.reserve(size_t(n) * 2));
+    CK(ctx->dLengths.reserve(size_t(n) * 3));
+    CK(ctx->dCigars.reserve(size_t(n) * cigarStride));
+    CK(cudaMemcpyAsync(ctx->dAscii.p, queries, qBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dAscii.p + qBytes, databases, dBytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dOffsets.p, queryOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dOffsets.p + n, databaseOffsets, size_t(n) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dLengths.p, queryLengths, size_t(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = bandedSwWideLaunch(ctx, bandWidth, n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes, ctx->dOffsets.p + n, maxLen,
+                                      matchScore, mismatchScore, gapOpenScore, gapExtendScore, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
+                                      ctx->dLengths.p + 2 * size_t(n), ctx->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(cigarOut, ctx->dCigars.p, size_t(n) * cigarStride * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cigarLengthOut, ctx->dLengths.p + n, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(offsetOut, ctx->dLengths.p + 2 * size_t(n), size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->errorFlag.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag)
+    {
+        cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream);
+        if (flag & 32u) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "query alphabet is ACGTn, database alphabet is ACGTN");
+        return ctx->fail(ISAAC_EXT_E_CAPACITY, "a gapped CIGAR did not fit the cigar stride");
+    }
+    return ISAAC_EXT_OK;
+}
+
 extern "C" int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond)
 {
     if (!ctx || !opsPerSecond || kind < 0 || kind > 2) return ISAAC_EXT_E_INVALID_ARG;
@@ -713,6 +818,7 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 #include "isaac_ext_tls.cuh"
 #include "isaac_ext_pack.cuh"
 #include "isaac_ext_async.cuh"
+#include "isaac_ext_select.cuh"
 
 namespace
 {

@@ -19,6 +19,7 @@ struct TileState
     DeviceBuffer<isaac_ext_fragment_t> dFrag1, dFrag3, dFinal;
     DeviceBuffer<uint32_t> dCig1, dCig3, dCigIndel, dGapCounts, dGapBegin;
     DeviceBuffer<IndelTask> dTasks;  DeviceBuffer<IndelResult> dIndel;  DeviceBuffer<uint8_t> dTaskValid;
+    DeviceBuffer<uint32_t> dTaskSlots;      // the match slots that hold a simple-indel pair, dense, [slots] = their number
     // the flat result of isaac_ext_build_fragments
     DeviceBuffer<uint32_t> dWords, dFragmentBegin, dWordBegin, dOutCigars;
     DeviceBuffer<isaac_ext_fragment_t> dOutFragments;  DeviceBuffer<uint64_t> dOutBegin;
@@ -35,7 +36,7 @@ struct TileState
     {
         dMatches.release(); dMatchBegin.release(); dSeeds.release(); dWork.release(); dListBegin.release(); dListCount.release(); dBuilt.release();
         dCand1.release(); dCand3.release(); dAdapterFirst.release(); dFrag1.release(); dFrag3.release(); dFinal.release(); dCig1.release();
-        dCig3.release(); dCigIndel.release(); dGapCounts.release(); dGapBegin.release(); dTasks.release(); dIndel.release(); dTaskValid.release();
+        dCig3.release(); dCigIndel.release(); dGapCounts.release(); dGapBegin.release(); dTasks.release(); dIndel.release(); dTaskValid.release(); dTaskSlots.release();
         dWords.release(); dFragmentBegin.release(); dWordBegin.release(); dOutCigars.release(); dOutFragments.release(); dOutBegin.release();
         hOutFragments.release(); hOutCigars.release(); hOutBegin.release(); hBuilt.release();
         dRequestCounts.release(); dRequestBegin.release(); dRequests.release(); dScratch.release(); dTemplates.release();
@@ -114,6 +115,7 @@ int tileBuildDevice(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch)
     CK(ts.dWork.reserve(slots)); CK(ts.dListBegin.reserve(lists + 1)); CK(ts.dListCount.reserve(lists + 1)); CK(ts.dBuilt.reserve(size_t(n) + 1));
     CK(ts.dCand1.reserve(slots)); CK(ts.dFrag1.reserve(slots)); CK(ts.dCig1.reserve(slots * 3)); CK(ts.dFinal.reserve(slots));
     CK(ts.dTasks.reserve(slots)); CK(ts.dIndel.reserve(slots)); CK(ts.dTaskValid.reserve(slots)); CK(ts.dCigIndel.reserve(slots * 5));
+    CK(ts.dTaskSlots.reserve(slots + 1));
     CK(ts.dGapCounts.reserve(lists + 1)); CK(ts.dGapBegin.reserve(lists + 1)); CK(ts.hTotals.reserve(8));
     if (M) CK(cudaMemcpyAsync(ts.dMatches.p, batch->matches, size_t(M) * sizeof(isaac_ext_match_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ts.dMatchBegin.p, batch->clusterMatchBegin, (size_t(n) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -143,9 +145,15 @@ int tileBuildDevice(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch)
     ++ctx->launches;
     if (ctx->cfg.semialignedGapLimit && M)
     {
-        simpleIndelKernel<<<gridFor(ctx, M, 128, 8), 128, 0, ctx->stream>>>(ctx->ref, ctx->reads, ctx->sp, uint32_t(M), ts.dTasks.p, ts.dIndel.p,
-                                                                         ts.dTaskValid.p, ts.dCigIndel.p);
-        ++ctx->launches;
+        // the slots that hold a pair as a dense list (a few percent of the slots): full warps for the indel search
+        size_t bytes = 0;
+        cub::CountingInputIterator<uint32_t> slotIds(0);
+        CK(cub::DeviceSelect::Flagged(nullptr, bytes, slotIds, ts.dTaskValid.p, ts.dTaskSlots.p, ts.dTaskSlots.p + M, int(M), ctx->stream));
+        CK(ctx->pipeline.dScanTemp.reserve(bytes + 16));
+        CK(cub::DeviceSelect::Flagged(ctx->pipeline.dScanTemp.p, bytes, slotIds, ts.dTaskValid.p, ts.dTaskSlots.p, ts.dTaskSlots.p + M, int(M), ctx->stream));
+        simpleIndelKernel<<<gridFor(ctx, (M + 7) / 8, 128, 8), 128, 0, ctx->stream>>>(ctx->ref, ctx->reads, ctx->sp, uint32_t(M), ts.dTasks.p, ts.dIndel.p,
+                                                                                   ts.dTaskSlots.p, ts.dTaskSlots.p + M, ts.dCigIndel.p);
+        ctx->launches += 2;
     }
     applyIndelKernel<<<listGrid, 128, 0, ctx->stream>>>(v, ts.dIndel.p, ts.dTaskValid.p, ts.dGapCounts.p);
     ++ctx->launches;

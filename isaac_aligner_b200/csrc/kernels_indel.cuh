@@ -63,13 +63,17 @@ struct IndelView
 
 __global__ void simpleIndelKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, uint32_t n,
                                   const IndelTask *__restrict__ tasks, IndelResult *__restrict__ results,
-                                  const uint8_t *__restrict__ valid = nullptr, uint32_t *__restrict__ cigarsOut = nullptr)
+                                  const uint32_t *__restrict__ slots = nullptr, const uint32_t *__restrict__ slotCount = nullptr,
+                                  uint32_t *__restrict__ cigarsOut = nullptr)
 {
     __shared__ double tables[201];
     const ScoreParams sp = stageScoreTables(spGlobal, tables);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    // tile pipeline (kernels_tile.cuh): the pairs live in the match slots slots[0 .. *slotCount) (a dense list made by
+    // cub::DeviceSelect), results go to the same slots; otherwise tasks[0 .. n)
+    const uint32_t count = slotCount ? *slotCount : n;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x)
     {
-        if (valid && !valid[i]) continue;               // tile pipeline: slot i holds a pair only where the flag is set (kernels_tile.cuh)
+        const uint32_t i = slots ? slots[j] : j;
         const IndelTask t = tasks[i];
         IndelResult &out = results[i];
         out.accepted = 0;

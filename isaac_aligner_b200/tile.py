@@ -10,12 +10,14 @@ BCL clusters + the tile's match records in, templates + template length statisti
  -> isaac_ext_build_templates                 buildFragments + buildTemplate + end clippers of every cluster (:323-349)
  -> isaac_ext_template_stats                  what threadStats_.recordTemplate collects (:306-358)
 
-This module is host plumbing only; every step is a call into libisaac_ext.so."""
+The chain itself is the C entry point isaac_ext_select_tile; this module reads the reference's files and calls it."""
+import ctypes
+
 import numpy as np
 
-from .batch import MatchBatch, TemplateOptions
-from .synth import MATCH_DTYPE
-from .types import ReadSet
+from .batch import MatchBatch, TemplateOptions, TemplateResult, Tls
+from .synth import MATCH_DTYPE, SEED_DTYPE
+from .types import Reads, ReadSet
 
 CLUSTER_SHIFT, CLUSTER_MASK = 9, (1 << 31) - 1          # SeedId: tile:12 barcode:12 cluster:31 seed:8 reverse:1 (SeedId.hh:37-127)
 
@@ -52,20 +54,50 @@ class TileResult:
         self.packed = packed
 
 
+class TileC(ctypes.Structure):
+    """isaac_ext_tile_t"""
+    _fields_ = [("reads", Reads), ("matches", ctypes.c_void_p), ("matchCount", ctypes.c_uint64), ("seeds", ctypes.c_void_p),
+                ("seedCount", ctypes.c_uint32), ("withGaps", ctypes.c_uint32), ("pf", ctypes.c_void_p),
+                ("baseQualityCutoff", ctypes.c_uint32), ("mateDriftRange", ctypes.c_int32), ("tls", ctypes.c_void_p),
+                ("options", TemplateOptions), ("pack", ctypes.c_void_p)]
+
+
+class TileResultC(ctypes.Structure):
+    """isaac_ext_tile_result_t"""
+    _fields_ = [("templates", TemplateResult), ("tls", Tls), ("tlsStable", ctypes.c_uint32), ("packedValid", ctypes.c_uint32),
+                ("stats", ctypes.c_uint64 * 128), ("endCyclesMasked", ctypes.c_void_p)]
+
+
 def select_tile(ctx, bcl, read_lengths, matches, seeds, pf=None, base_quality_cutoff=0, tls=None, options=None,
                 mate_drift_range=-1, with_gaps=True, pack=None):
-    """MatchSelector::parallelSelect for one tile on the context's GPU.  tls: user-defined template length statistics
-    (batch.Tls) or None = determine them from this tile.  pack: batch.PackOptions = also leave the io::FragmentHeader bin
-    records FragmentCollector::add stores for the tile (TileResult.packed), None = skip that pass."""
+    """MatchSelector::parallelSelect for one tile on the context's GPU = ONE call of isaac_ext_select_tile.  tls: user-defined
+    template length statistics (batch.Tls) or None = determine them from this tile.  pack: batch.PackOptions = also leave the
+    io::FragmentHeader bin records FragmentCollector::add stores for the tile (TileResult.packed), None = skip that pass."""
+    from . import capi
     reads = ReadSet(bcl, tuple(read_lengths))
-    ctx.set_reads(reads)
-    masked = ctx.trim_low_quality_ends(base_quality_cutoff) if base_quality_cutoff else None
-    mb = MatchBatch(matches, cluster_match_begin(matches, reads.cluster_count), seeds, with_gaps=with_gaps)
-    stable = True
-    if tls is None:
-        tls, stable = ctx.determine_template_length(mb, pf, mate_drift_range)
+    matches = np.ascontiguousarray(matches, dtype=MATCH_DTYPE)
+    seeds = np.ascontiguousarray(seeds, dtype=SEED_DTYPE)
+    pf_a = np.ascontiguousarray(pf, dtype=np.uint8) if pf is not None else None
     options = options if options is not None else TemplateOptions.make()
-    templates = ctx.build_templates(mb, tls, options)
-    stats = ctx.template_stats(mb, tls, templates, pf)
-    packed = ctx.pack_fragments(templates, pack) if pack is not None else None
-    return TileResult(templates, tls, stable, stats, masked, packed)
+    t = TileC(reads.c, matches.ctypes.data if matches.size else None, matches.size, seeds.ctypes.data, seeds.size, 1 if with_gaps else 0,
+              pf_a.ctypes.data if pf_a is not None else None, int(base_quality_cutoff), int(mate_drift_range),
+              ctypes.addressof(tls) if tls is not None else None, options, ctypes.addressof(pack.c) if pack is not None else None)
+    res = TileResultC()
+    ctx._check(capi._lib.isaac_ext_select_tile(ctx._h, ctypes.byref(t), ctypes.byref(res)))
+    ctx.reads = reads
+    templates = ctx._templates(res.templates)
+    out_tls = Tls()
+    ctypes.memmove(ctypes.byref(out_tls), ctypes.byref(res.tls), ctypes.sizeof(Tls))
+    stats = np.array(res.stats, dtype=np.uint64).reshape(4, 32)
+    masked = None
+    if res.endCyclesMasked:
+        count = reads.cluster_count * reads.read_count
+        buf = (ctypes.c_char * (count * 2)).from_address(res.endCyclesMasked)
+        masked = np.frombuffer(buf, dtype=np.uint16).copy().reshape(reads.cluster_count, reads.read_count)
+    packed = None
+    if pack is not None:
+        from .batch import PackResultC
+        pr = PackResultC()
+        ctx._check(capi._lib.isaac_ext_tile_packed(ctx._h, ctypes.byref(pr)))
+        packed = ctx._packed(pr, bool(pack.c.compact))
+    return TileResult(templates, out_tls, bool(res.tlsStable), stats, masked, packed)

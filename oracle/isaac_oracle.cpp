@@ -35,15 +35,21 @@ inline uint32_t cigarWord(uint32_t length, uint32_t op) { return (length << 4) |
 /* -------------------------------------------------------------------------------------------------
  * BandedSmithWaterman::align   lib/alignment/BandedSmithWaterman.cpp:84-462
  * ------------------------------------------------------------------------------------------------- */
-struct BandedSw
+/// WIDTH = lanes of the band.  WIDTH = 16 is the reference (BandedSmithWaterman.hh:88-89 hard-wires it); any other even width is
+/// the same recurrence, end-cell scan and traceback over more lanes: lane j of row i = database position i + WIDTH - 1 - j, the
+/// database window has L + WIDTH - 1 bases, the byte-pair merge of the G direction codes (:197) applies to every pair of lanes.
+/// The widened band of BASELINE configs[4] (2x250 bp) has no reference behaviour to match; this model is what the CUDA
+/// warp-wavefront kernel is compared with, and tests/test_wide_band_oracle.py proves that its WIDTH = 16 instance (the one every
+/// other function of this file uses) equals the reference's own code.
+template <unsigned WIDTH> struct BandedSwT
 {
     int match, mismatch, open, ext;     // open/ext positive as the constructor takes them (:36-43)
     int16_t init;                       // :44  numeric_limits<short>::min() + gapOpenScore
     bool valid;
     std::vector<uint8_t> T;             // 3 direction bytes x 16 lanes per row (:45, :306-308)
 
-    BandedSw(int m, int mm, int o, int e, unsigned maxReadLength)
-        : match(m), mismatch(mm), open(o), ext(e), init(int16_t(-32768 + o)), T(size_t(maxReadLength) * 48)
+    BandedSwT(int m, int mm, int o, int e, unsigned maxReadLength)
+        : match(m), mismatch(mm), open(o), ext(e), init(int16_t(-32768 + o)), T(size_t(maxReadLength) * 3 * WIDTH)
     {
         // overflow guard of the constructor (:47-53)
         const int maxScore = std::max(std::max(std::max(std::abs(m), std::abs(mm)), std::abs(o)), std::abs(e));
@@ -56,8 +62,8 @@ struct BandedSw
     unsigned align(const char *q, unsigned L, const char *db, std::vector<uint32_t> &cigar)
     {
         const size_t originalSize = cigar.size();
-        int16_t G[BAND], E[BAND], F[BAND], nG[BAND], nE[BAND], nF[BAND];
-        for (unsigned j = 0; j < BAND; ++j) { G[j] = init; E[j] = init; F[j] = 0; }     // :108-114 (F starts at 0)
+        int16_t G[WIDTH], E[WIDTH], F[WIDTH], nG[WIDTH], nE[WIDTH], nF[WIDTH];
+        for (unsigned j = 0; j < WIDTH; ++j) { G[j] = init; E[j] = init; F[j] = 0; }     // :108-114 (F starts at 0)
         G[0] = 0;                                                                         // :115
         // the score byte pair the SSE code builds with unpack(W, B) (:230-244): low byte = score, high byte = 0xFF
         // when the bases differ, 0x00 when equal
@@ -65,9 +71,9 @@ struct BandedSw
         const int16_t wMismatch = int16_t(uint16_t(0xFF00u | uint8_t(mismatch)));
         for (unsigned i = 0; i < L; ++i)
         {
-            uint8_t *TG = &T[size_t(i) * 48], *TE = TG + 16, *TF = TG + 32;
+            uint8_t *TG = &T[size_t(i) * 3 * WIDTH], *TE = TG + WIDTH, *TF = TG + 2 * WIDTH;
             // F: insertion, from lane j-1 of the previous row, zeros shifted into lane 0 (:132-173)
-            for (unsigned j = 0; j < BAND; ++j)
+            for (unsigned j = 0; j < WIDTH; ++j)
             {
                 const int16_t gp = j ? G[j - 1] : 0, ep = j ? E[j - 1] : 0, fp = j ? F[j - 1] : 0;
                 uint8_t tf = gp < ep ? 1 : 0;                                             // :142-145
@@ -80,18 +86,18 @@ struct BandedSw
             TF[0] = 0;                                                                    // :167
             nF[0] = init;                                                                 // :173
             // G: diagonal, same lane of the previous row (:176-190, :243-244)
-            uint8_t tgE[BAND], tgF[BAND];
-            for (unsigned j = 0; j < BAND; ++j)
+            uint8_t tgE[WIDTH], tgF[WIDTH];
+            for (unsigned j = 0; j < WIDTH; ++j)
             {
                 tgE[j] = G[j] < E[j] ? 1 : 0;
                 int16_t g = std::max(G[j], E[j]);
                 tgF[j] = g < F[j] ? 2 : 0;
                 g = std::max(g, F[j]);
-                const bool differ = q[i] != db[i + 15 - j];                               // raw byte compare (:200-205)
+                const bool differ = q[i] != db[i + (WIDTH - 1) - j];                               // raw byte compare (:200-205)
                 nG[j] = w16(g + (differ ? wMismatch : wMatch));
             }
             // the direction bytes of G are merged with a 16-bit signed max over BYTE PAIRS (:197), not per byte
-            for (unsigned p = 0; p < BAND / 2; ++p)
+            for (unsigned p = 0; p < WIDTH / 2; ++p)
             {
                 const int16_t x = int16_t(uint16_t(tgF[2 * p] | (tgF[2 * p + 1] << 8)));
                 const int16_t y = int16_t(uint16_t(tgE[2 * p] | (tgE[2 * p + 1] << 8)));
@@ -101,7 +107,7 @@ struct BandedSw
             }
             // E: deletion, serial from lane 15 down to lane 0 (:246-297)
             int16_t g = init, e = init, f = init;
-            for (int j = BAND - 1; j >= 0; --j)
+            for (int j = int(WIDTH) - 1; j >= 0; --j)
             {
                 int16_t mx = g; uint8_t t = 0;
                 if (e > g && e > f) { mx = e; t = 1; }
@@ -112,26 +118,26 @@ struct BandedSw
             std::memcpy(G, nG, sizeof(G)); std::memcpy(E, nE, sizeof(E)); std::memcpy(F, nF, sizeof(F));
         }
         // end cell: lanes 15..0, matrices G,E,F in that order, strict '>' (:349-379)
-        int16_t best = w16(G[15] - 1);
+        int16_t best = w16(G[WIDTH - 1] - 1);
         int ii = int(L) - 1, jj = ii; unsigned type = 0;
         const int16_t *M[3] = {G, E, F};
-        for (int j = BAND - 1; j >= 0; --j)
+        for (int j = int(WIDTH) - 1; j >= 0; --j)
             for (unsigned t = 0; t < 3; ++t)
                 if (M[t][j] > best) { best = M[t][j]; jj = j; type = t; }
         // traceback, ops emitted tail first (:381-435)
         static const uint32_t opOf[3] = {ISAAC_EXT_CIGAR_ALIGN, ISAAC_EXT_CIGAR_DELETE, ISAAC_EXT_CIGAR_INSERT};
         unsigned opLength = 0;
         if (jj > 0) cigar.push_back(cigarWord(jj, ISAAC_EXT_CIGAR_DELETE));
-        while (ii >= 0 && jj >= 0 && jj <= 15)
+        while (ii >= 0 && jj >= 0 && jj <= int(WIDTH) - 1)
         {
             ++opLength;
-            const unsigned next = T[(size_t(ii) * 3 + type) * 16 + jj];
+            const unsigned next = T[(size_t(ii) * 3 + type) * WIDTH + jj];
             if (next != type) { cigar.push_back(cigarWord(opLength, opOf[type])); opLength = 0; }
             if (type == 0) { --ii; } else if (type == 1) { ++jj; } else { --ii; --jj; }
             type = next;
         }
         if (type != 1 && opLength) { cigar.push_back(cigarWord(opLength, opOf[type])); opLength = 0; }
-        if (jj < 15) { cigar.push_back(cigarWord(opLength + 15 - jj, ISAAC_EXT_CIGAR_DELETE)); opLength = 0; }
+        if (jj < int(WIDTH) - 1) { cigar.push_back(cigarWord(opLength + (WIDTH - 1) - jj, ISAAC_EXT_CIGAR_DELETE)); opLength = 0; }
         // strip the deletion at the alignment start, reverse, strip the one at the end (:437-453)
         unsigned ret = 0;
         if ((cigar.back() & 0xF) == ISAAC_EXT_CIGAR_DELETE) { ret = cigar.back() >> 4; cigar.pop_back(); }
@@ -140,6 +146,7 @@ struct BandedSw
         return ret;
     }
 };
+typedef BandedSwT<BAND> BandedSw;       // the reference's band
 
 /* -------------------------------------------------------------------------------------------------
  * Quality tables  lib/alignment/Quality.cpp:34-66, include/alignment/Quality.hh:52-86
@@ -756,6 +763,46 @@ extern "C" int oracle_banded_sw_batch(uint32_t n, const char *queries, const uin
         }
     });
     return ISAAC_EXT_OK;
+}
+
+/// BandedSwT<bandWidth>::align over a batch (bandWidth 16, 32 or 64): the model of the widened band, this library only
+template <unsigned WIDTH> static int wideBatch(uint32_t n, const char *queries, const uint64_t *queryOffsets, const uint32_t *queryLengths,
+                                               const char *databases, const uint64_t *databaseOffsets, int matchScore, int mismatchScore,
+                                               int gapOpenScore, int gapExtendScore, uint32_t maxReadLength, uint32_t cigarStride,
+                                               uint32_t *cigarOut, uint32_t *cigarLengthOut, uint32_t *offsetOut, uint32_t threads)
+{
+    if (!BandedSwT<WIDTH>(matchScore, mismatchScore, gapOpenScore, gapExtendScore, maxReadLength).valid) return ISAAC_EXT_E_INVALID_ARG;
+    for (uint32_t i = 0; i < n; ++i) if (queryLengths[i] > maxReadLength || !queryLengths[i]) return ISAAC_EXT_E_INVALID_ARG;
+    parallelFor(n, threads, [&](uint32_t b, uint32_t e) {
+        BandedSwT<WIDTH> sw(matchScore, mismatchScore, gapOpenScore, gapExtendScore, maxReadLength);
+        std::vector<uint32_t> cigar;
+        for (uint32_t i = b; i < e; ++i)
+        {
+            cigar.clear();
+            offsetOut[i] = sw.align(queries + queryOffsets[i], queryLengths[i], databases + databaseOffsets[i], cigar);
+            cigarLengthOut[i] = cigar.size();
+            std::copy(cigar.begin(), cigar.begin() + std::min<size_t>(cigar.size(), cigarStride), cigarOut + size_t(i) * cigarStride);
+        }
+    });
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int oracle_banded_sw_wide_batch(uint32_t bandWidth, uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                                           const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                                           int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                                           uint32_t maxReadLength, uint32_t cigarStride, uint32_t *cigarOut,
+                                           uint32_t *cigarLengthOut, uint32_t *offsetOut, uint32_t threads)
+{
+#define ISAAC_WIDE(W) wideBatch<W>(n, queries, queryOffsets, queryLengths, databases, databaseOffsets, matchScore, mismatchScore, gapOpenScore, \
+                                   gapExtendScore, maxReadLength, cigarStride, cigarOut, cigarLengthOut, offsetOut, threads)
+    switch (bandWidth)
+    {
+    case 16: return ISAAC_WIDE(16);
+    case 32: return ISAAC_WIDE(32);
+    case 64: return ISAAC_WIDE(64);
+    default: return ISAAC_EXT_E_INVALID_ARG;
+    }
+#undef ISAAC_WIDE
 }
 
 extern "C" int oracle_ungapped_batch(const oracle_genome_t *genome, const isaac_ext_reads_t *reads,

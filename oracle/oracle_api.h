@@ -32,6 +32,13 @@ int oracle_set_adapters(uint32_t count, const isaac_ext_adapter_t *adapters);
 
 /* BandedSmithWaterman::align, see isaac_ext_banded_sw_batch.  threads > 1 splits the batch over std::threads
  * (one BandedSmithWaterman object per thread, like the reference keeps one per TemplateBuilder). */
+/* liboracle_port only: the same recurrence on a band of bandWidth lanes (16, 32, 64); database windows have
+ * queryLength + bandWidth - 1 bases.  bandWidth 16 is oracle_banded_sw_batch (the same template instance). */
+int oracle_banded_sw_wide_batch(uint32_t bandWidth, uint32_t n, const char *queries, const uint64_t *queryOffsets,
+                                const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
+                                int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,
+                                uint32_t maxReadLength, uint32_t cigarStride, uint32_t *cigarOut,
+                                uint32_t *cigarLengthOut, uint32_t *offsetOut, uint32_t threads);
 int oracle_banded_sw_batch(uint32_t n, const char *queries, const uint64_t *queryOffsets,
                            const uint32_t *queryLengths, const char *databases, const uint64_t *databaseOffsets,
                            int matchScore, int mismatchScore, int gapOpenScore, int gapExtendScore,

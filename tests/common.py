@@ -7,7 +7,7 @@ from isaac_aligner_b200.types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, ReadSet, c
 FRAGMENT_FIELDS = [n for n in FRAGMENT_DTYPE.names]
 
 
-def random_sw_cases(n, seed, lmin=30, lmax=250, with_n=True):
+def random_sw_cases(n, seed, lmin=30, lmax=250, with_n=True, band=16, max_indel=8):
     """Random (query, database) pairs like SURVEY Appendix A's validation set: the query is a copy of the database
     window at a random band offset with substitutions, 0-2 indels of 1-8 bases, optional 'n' in the query and 'N' in
     the database."""
@@ -15,12 +15,12 @@ def random_sw_cases(n, seed, lmin=30, lmax=250, with_n=True):
     queries, dbs = [], []
     for _ in range(n):
         L = int(rng.integers(lmin, lmax + 1))
-        db = rng.integers(0, 4, size=L + 15 + 32)
-        start = int(rng.integers(0, 16))
-        src = list(db[start:start + L + 16])
+        db = rng.integers(0, 4, size=L + band - 1 + 2 * band)
+        start = int(rng.integers(0, band))
+        src = list(db[start:start + L + band])
         for _e in range(int(rng.integers(0, 3))):
             p = int(rng.integers(5, max(6, len(src) - 20)))
-            ln = int(rng.integers(1, 9))
+            ln = int(rng.integers(1, max_indel + 1))
             if rng.random() < 0.5:
                 del src[p:p + ln]
             else:
@@ -31,13 +31,13 @@ def random_sw_cases(n, seed, lmin=30, lmax=250, with_n=True):
         sub = rng.random(L) < rng.choice([0.0, 0.02, 0.1, 0.5])
         q = np.where(sub, (q + rng.integers(1, 4, size=L)) & 3, q)
         qs = bytearray(b"ACGT"[int(c)] for c in q)
-        ds = bytearray(b"ACGT"[int(c)] for c in db[:L + 15])
+        ds = bytearray(b"ACGT"[int(c)] for c in db[:L + band - 1])
         if with_n and rng.random() < 0.2:
             for p in rng.integers(0, L, size=int(rng.integers(1, 4))):
                 qs[int(p)] = ord("n")
         if with_n and rng.random() < 0.1:
             p = int(rng.integers(0, L))
-            run = min(int(rng.integers(1, 6)), L + 15 - p)
+            run = min(int(rng.integers(1, 6)), L + band - 1 - p)
             ds[p:p + run] = b"N" * run
         queries.append(bytes(qs))
         dbs.append(bytes(ds))

@@ -49,7 +49,7 @@ class Oracle:
         if rc:
             raise RuntimeError("oracle_set_adapters failed: %d" % rc)
 
-    def banded_sw(self, queries, dbs, scores, max_read_length=None, cigar_stride=64, threads=1):
+    def banded_sw(self, queries, dbs, scores, max_read_length=None, cigar_stride=64, threads=1, band=None):
         """queries/dbs: lists of bytes.  scores = (match, mismatch, gapOpen>0, gapExtend>0).
         returns (list of cigar word arrays, offsets)"""
         n = len(queries)
@@ -58,17 +58,28 @@ class Oracle:
         qlen = np.array([len(q) for q in queries], dtype=np.uint32)
         qoff = np.concatenate([[0], np.cumsum(qlen[:-1], dtype=np.uint64)]).astype(np.uint64)
         dlen = np.array([len(d) for d in dbs], dtype=np.uint64)
-        assert np.all(dlen == qlen + 15)
+        assert np.all(dlen == qlen + (band or 16) - 1)
         doff = np.concatenate([[0], np.cumsum(dlen[:-1], dtype=np.uint64)]).astype(np.uint64)
-        return self.banded_sw_flat(qbuf, qoff, qlen, dbuf, doff, scores, max_read_length, cigar_stride, threads)
+        return self.banded_sw_flat(qbuf, qoff, qlen, dbuf, doff, scores, max_read_length, cigar_stride, threads, band)
 
-    def banded_sw_flat(self, qbuf, qoff, qlen, dbuf, doff, scores, max_read_length=None, cigar_stride=64, threads=1):
+    def banded_sw_flat(self, qbuf, qoff, qlen, dbuf, doff, scores, max_read_length=None, cigar_stride=64, threads=1, band=None):
+        """band=None: BandedSmithWaterman::align (both libraries); band=16/32/64: the band-width-parametrised model of the port"""
         n = len(qlen)
         if max_read_length is None:
             max_read_length = int(qlen.max())
         cig = np.zeros((n, cigar_stride), dtype=np.uint32)
         ciglen = np.zeros(n, dtype=np.uint32)
         off = np.zeros(n, dtype=np.uint32)
+        if band is not None:
+            rc = self.lib.oracle_banded_sw_wide_batch(
+                ctypes.c_uint32(band), ctypes.c_uint32(n), ctypes.c_void_p(qbuf.ctypes.data), ctypes.c_void_p(qoff.ctypes.data),
+                ctypes.c_void_p(qlen.ctypes.data), ctypes.c_void_p(dbuf.ctypes.data), ctypes.c_void_p(doff.ctypes.data),
+                ctypes.c_int(scores[0]), ctypes.c_int(scores[1]), ctypes.c_int(scores[2]), ctypes.c_int(scores[3]),
+                ctypes.c_uint32(max_read_length), ctypes.c_uint32(cigar_stride), ctypes.c_void_p(cig.ctypes.data),
+                ctypes.c_void_p(ciglen.ctypes.data), ctypes.c_void_p(off.ctypes.data), ctypes.c_uint32(threads))
+            if rc:
+                raise RuntimeError("oracle_banded_sw_wide_batch failed: %d" % rc)
+            return cig, ciglen, off
         rc = self.lib.oracle_banded_sw_batch(
             ctypes.c_uint32(n), ctypes.c_void_p(qbuf.ctypes.data), ctypes.c_void_p(qoff.ctypes.data),
             ctypes.c_void_p(qlen.ctypes.data), ctypes.c_void_p(dbuf.ctypes.data), ctypes.c_void_p(doff.ctypes.data),

@@ -64,10 +64,11 @@ def test_python_mirrors_have_the_c_struct_sizes():
     """every ctypes.Structure / numpy dtype the harness passes over the ABI against sizeof() of the header's struct (gcc)"""
     import ctypes
     import subprocess
-    from isaac_aligner_b200 import batch, synth, types
-    pairs = [("isaac_ext_config_t", ctypes.sizeof(types.Config)), ("isaac_ext_reads_t", ctypes.sizeof(types.Reads)),
+    from isaac_aligner_b200 import batch, synth, tile, types
+    pairs = [("isaac_ext_tile_t", ctypes.sizeof(tile.TileC)), ("isaac_ext_tile_result_t", ctypes.sizeof(tile.TileResultC)),
+             ("isaac_ext_config_t", ctypes.sizeof(types.Config)), ("isaac_ext_reads_t", ctypes.sizeof(types.Reads)),
              ("isaac_ext_adapter_t", ctypes.sizeof(types.Adapter)), ("isaac_ext_fragment_t", types.FRAGMENT_DTYPE.itemsize),
-             ("isaac_ext_candidate_t", types.CANDIDATE_DTYPE.itemsize), ("isaac_ext_match_t", synth.MATCH_DTYPE.itemsize),
+             ("isaac_ext_candidate_t", types.CANDIDATE_DTYPE.itemsize), ("isaac_ext_alignment_t", types.ALIGNMENT_DTYPE.itemsize), ("isaac_ext_match_t", synth.MATCH_DTYPE.itemsize),
              ("isaac_ext_seed_t", synth.SEED_DTYPE.itemsize), ("isaac_ext_build_batch_t", ctypes.sizeof(batch.BuildBatch)),
              ("isaac_ext_build_result_t", ctypes.sizeof(batch.BuildResult)), ("isaac_ext_tls_t", ctypes.sizeof(batch.Tls)),
              ("isaac_ext_rescue_request_t", batch.RESCUE_REQUEST_DTYPE.itemsize), ("isaac_ext_rescue_result_t", ctypes.sizeof(batch.RescueResult)),
