@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def human():
-    workers = max(1, min(16, os.cpu_count() or 1))
+    workers = 1          # no fork workers inside a pytest process that already holds a CUDA context
     genome = synth.make_genome_parallel(3_100_000_000, n_contigs=24, seed=synth.SEED_G3100, n_fraction=0.001, workers=workers)
     from isaac_aligner_b200 import capi
     ctx = capi.Context(Config.default(max_read_length=300))
