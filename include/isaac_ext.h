@@ -269,6 +269,19 @@ int isaac_ext_set_adapters(isaac_ext_ctx *ctx, uint32_t count, const isaac_ext_a
  * by the batch calls below.  Stays valid until the next isaac_ext_set_reads on this context. */
 int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *reads);
 
+/* Double buffering of tiles (SelectMatchesTransition.cpp:316-340 loads the next tile while the current one is processed): starts
+ * the upload and decode of the NEXT tile's BCL bytes into the context's second read-set slot on its own stream and returns at
+ * once; the calls on the current tile go on next to it (copy engine + a few SMs).  A later isaac_ext_set_reads with the same
+ * description (same pointers, counts, lengths) takes the prefetched slot over instead of uploading again; any other
+ * isaac_ext_set_reads simply uploads as usual.  reads->bcl (page-locked memory, for the copy to overlap) and
+ * reads->endCyclesMasked must stay unchanged until that isaac_ext_set_reads.  One prefetch at a time. */
+int isaac_ext_prefetch_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *reads);
+/* The same for the NEXT tile's seed matches (clusterCount = the clusters of that tile), after its isaac_ext_prefetch_reads: the
+ * isaac_ext_set_reads that takes the prefetched reads over takes the matches with them, and the first isaac_ext_build_fragments /
+ * isaac_ext_build_templates / isaac_ext_determine_template_length on that tile with the same batch (same pointers) finds them on
+ * the device.  With both prefetches a tile starts computing at once: its inputs went up under the previous tile's kernels. */
+int isaac_ext_prefetch_batch(isaac_ext_ctx *ctx, const struct isaac_ext_build_batch *batch, uint32_t clusterCount);
+
 /* alignment::trimLowQualityEnds (Quality.cpp:71-120, --base-quality-cutoff, MatchSelector.cpp:300): recomputes
  * Read::endCyclesMasked_ of every resident read from its qualities, replacing what isaac_ext_set_reads was given.
  * baseQualityCutoff 0 = no masking.  endCyclesMaskedOut (clusterCount * readCount values) may be NULL. */

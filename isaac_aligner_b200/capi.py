@@ -36,7 +36,7 @@ EXPORTS = [
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
     "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
-    "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed",
+    "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed", "isaac_ext_prefetch_reads", "isaac_ext_prefetch_batch",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
 ]
 
@@ -94,6 +94,17 @@ class Context:
         from .types import adapter_array
         arr = adapter_array(adapters)
         self._check(_lib.isaac_ext_set_adapters(self._h, ctypes.c_uint32(len(adapters)), arr))
+
+    def prefetch_reads(self, reads):
+        """isaac_ext_prefetch_reads: the next tile's reads go up while the calls on the current tile run; set_reads(reads) takes them over"""
+        assert isinstance(reads, ReadSet)
+        self._check(_lib.isaac_ext_prefetch_reads(self._h, ctypes.byref(reads.c)))
+        self._prefetched = reads          # keeps the host buffers alive
+
+    def prefetch_batch(self, match_batch, cluster_count):
+        """isaac_ext_prefetch_batch: the next tile's seed matches go up while the current tile is processed"""
+        self._check(_lib.isaac_ext_prefetch_batch(self._h, ctypes.byref(match_batch.c), ctypes.c_uint32(cluster_count)))
+        self._prefetched_batch = match_batch
 
     def set_reads(self, reads):
         assert isinstance(reads, ReadSet)

@@ -38,7 +38,7 @@ struct PipelineState
     DeviceBuffer<IndelResult> dIndel;
     DeviceBuffer<ShadowTask> dShadowTasks;
     DeviceBuffer<int> dShadowScratch;
-    DeviceBuffer<uint32_t> dTaskBegin, dTaskCount;
+    DeviceBuffer<uint32_t> dTaskBegin, dTaskCount, dLargeTasks;
     DeviceBuffer<unsigned long long> dPoolSize;
     // sequencing adapters: first candidate of every clipper slot, slot of every candidate (rescue)
     PinnedBuffer<isaac_ext_candidate_t> hAdapterFirst;
@@ -76,7 +76,7 @@ struct PipelineState
         dOutFragments.release(); dOutBegin.release(); hTotals.release();
         for (int k = 0; k < 2; ++k) { hOutCigars[k].release(); hOutFragments[k].release(); hOutBegin[k].release(); hRescued[k].release(); }
         dCand.release(); dFrag.release(); dCig.release(); dTasks.release(); dIndel.release(); dShadowTasks.release();
-        dShadowScratch.release(); dTaskBegin.release(); dTaskCount.release(); dPoolSize.release();
+        dShadowScratch.release(); dTaskBegin.release(); dTaskCount.release(); dPoolSize.release(); dLargeTasks.release();
     }
 };
 

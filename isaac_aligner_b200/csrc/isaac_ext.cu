@@ -30,6 +30,7 @@ struct TileState;                      // isaac_ext_tile.cuh
 } // namespace
 void releaseTemplates(TemplateState *state);
 void releaseTile(TileState *state);
+void tileTakeOverPrefetchedBatch(isaac_ext_ctx *ctx);
 struct PackState;                      // isaac_ext_pack.cuh
 void releasePack(PackState *state);
 struct AsyncState;                     // isaac_ext_async.cuh
@@ -75,14 +76,32 @@ struct isaac_ext_ctx
     ReferenceView ref{};
     bool haveReference = false;
 
-    // resident read set
-    DeviceBuffer<uint32_t> readBases2, readNmask;
-    DeviceBuffer<uint8_t> readQuality, bclStage;
-    DeviceBuffer<uint64_t> readCodes4, readStrand2;
-    DeviceBuffer<uint8_t> readQualityStrand;
-    DeviceBuffer<uint16_t> readMasked;
-    ReadSetView reads{};
+    // resident read set: two slots, the tile the calls work on and the one isaac_ext_prefetch_reads fills meanwhile
+    struct ReadSlot
+    {
+        DeviceBuffer<uint32_t> bases2, nmask;
+        DeviceBuffer<uint8_t> quality, bclStage, qualityStrand;
+        DeviceBuffer<uint64_t> codes4, strand2;
+        DeviceBuffer<uint16_t> masked;
+        ReadSetView view{};
+        uint32_t clusterCount = 0;
+        isaac_ext_reads_t key{};          // what was uploaded (prefetch: what set_reads must be called with to take the slot over)
+        bool staged = false;              // filled by isaac_ext_prefetch_reads, not yet taken over
+        cudaEvent_t ready = nullptr;
+        void release()
+        {
+            bases2.release(); nmask.release(); quality.release(); bclStage.release(); qualityStrand.release(); codes4.release();
+            strand2.release(); masked.release();
+            if (ready) cudaEventDestroy(ready);
+            ready = nullptr;
+        }
+    };
+    ReadSlot readSlot[2];
+    unsigned activeSlot = 0;
+    cudaStream_t stageStream = nullptr;   // uploads + decodes the prefetched tile next to the kernels of the current one
+    ReadSetView reads{};                  // = readSlot[activeSlot].view
     bool haveReads = false;
+    ReadSlot &slot() { return readSlot[activeSlot]; }
 
     // sequencing adapters (isaac_ext_set_adapters; kernels_adapter.cuh); count == 0: no adapter kernel ever runs
     DeviceBuffer<uint8_t> adapterCodes, adapterReverse;
@@ -250,8 +269,9 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     ctx->tables.release(); ctx->refBases2.release(); ctx->refNmask.release(); ctx->refContigOffset.release();
-    ctx->refContigLength.release(); ctx->readBases2.release(); ctx->readNmask.release(); ctx->readQuality.release();
-    ctx->bclStage.release(); ctx->readCodes4.release(); ctx->readStrand2.release(); ctx->readQualityStrand.release(); ctx->readMasked.release(); ctx->dCandidates.release(); ctx->dFragments.release();
+    ctx->refContigLength.release();
+    if (ctx->stageStream) { cudaStreamSynchronize(ctx->stageStream); cudaStreamDestroy(ctx->stageStream); }
+    ctx->readSlot[0].release(); ctx->readSlot[1].release(); ctx->dCandidates.release(); ctx->dFragments.release();
     ctx->dCigars.release(); ctx->dMasks.release(); ctx->tbScratch.release(); ctx->errorFlag.release();
     ctx->dAscii.release(); ctx->dOffsets.release(); ctx->dLengths.release();
     ctx->adapterCodes.release(); ctx->adapterReverse.release(); ctx->adapterKmers.release(); ctx->adapterLength.release();
@@ -367,9 +387,9 @@ extern "C" int isaac_ext_set_adapters(isaac_ext_ctx *ctx, uint32_t count, const 
     return ISAAC_EXT_OK;
 }
 
-extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *r)
+/// Read::decodeBcl of a tile into 'slot', enqueued on 'stream' (upload, two decode kernels); the caller synchronises
+static int loadReads(isaac_ext_ctx *ctx, isaac_ext_ctx::ReadSlot &slot, const isaac_ext_reads_t *r, cudaStream_t stream)
 {
-    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     if (!r || !r->bcl || !r->clusterCount || r->readCount < 1 || r->readCount > 2) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "bad read set");
     const uint32_t len0 = r->readLength[0], len1 = r->readCount > 1 ? r->readLength[1] : 0;
     const uint32_t maxLen = std::max(len0, len1);
@@ -379,38 +399,81 @@ extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *
     const uint64_t readTotal = uint64_t(r->clusterCount) * r->readCount;
     const uint32_t wordsN = (maxLen + 31) / 32, words2 = wordsN * 2, qualityStride = wordsN * 32;
     const uint64_t bclBytes = uint64_t(r->clusterCount) * (len0 + len1);
-    CK(ctx->readBases2.reserve(readTotal * words2));
-    CK(ctx->readNmask.reserve(readTotal * wordsN));
-    CK(ctx->readQuality.reserve(readTotal * qualityStride));
-    CK(ctx->readMasked.reserve(readTotal));
-    CK(ctx->bclStage.reserve(bclBytes));
-    CK(cudaMemcpyAsync(ctx->bclStage.p, r->bcl, bclBytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (r->endCyclesMasked)
-        CK(cudaMemcpyAsync(ctx->readMasked.p, r->endCyclesMasked, readTotal * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-    else
-        CK(cudaMemsetAsync(ctx->readMasked.p, 0, readTotal * sizeof(uint16_t), ctx->stream));
-    decodeBclKernel<<<gridFor(ctx, readTotal * wordsN, 256, 16), 256, 0, ctx->stream>>>(
-        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, words2, wordsN, qualityStride,
-        ctx->readBases2.p, ctx->readNmask.p, ctx->readQuality.p);
-    ++ctx->launches;
-    CK(cudaGetLastError());
     const uint32_t wordsC = (maxLen + 15) / 16 + 2;
-    CK(ctx->readCodes4.reserve(readTotal * 2 * wordsC));
-    CK(ctx->readStrand2.reserve(readTotal * 2 * wordsC));
-    CK(ctx->readQualityStrand.reserve(readTotal * 2 * qualityStride));
-    encodeStrandCodesKernel<<<gridFor(ctx, readTotal * 2 * wordsC, 256, 16), 256, 0, ctx->stream>>>(
-        ctx->bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, ctx->readCodes4.p, ctx->readStrand2.p, qualityStride,
-        ctx->readQualityStrand.p);
-    ++ctx->launches;
+    CK(slot.bases2.reserve(readTotal * words2));
+    CK(slot.nmask.reserve(readTotal * wordsN));
+    CK(slot.quality.reserve(readTotal * qualityStride));
+    CK(slot.masked.reserve(readTotal));
+    CK(slot.bclStage.reserve(bclBytes));
+    CK(slot.codes4.reserve(readTotal * 2 * wordsC));
+    CK(slot.strand2.reserve(readTotal * 2 * wordsC));
+    CK(slot.qualityStrand.reserve(readTotal * 2 * qualityStride));
+    CK(cudaMemcpyAsync(slot.bclStage.p, r->bcl, bclBytes, cudaMemcpyHostToDevice, stream));
+    if (r->endCyclesMasked)
+        CK(cudaMemcpyAsync(slot.masked.p, r->endCyclesMasked, readTotal * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+    else
+        CK(cudaMemsetAsync(slot.masked.p, 0, readTotal * sizeof(uint16_t), stream));
+    decodeBclKernel<<<gridFor(ctx, readTotal * wordsN, 256, 16), 256, 0, stream>>>(
+        slot.bclStage.p, r->clusterCount, r->readCount, len0, len1, words2, wordsN, qualityStride, slot.bases2.p, slot.nmask.p, slot.quality.p);
+    encodeStrandCodesKernel<<<gridFor(ctx, readTotal * 2 * wordsC, 256, 16), 256, 0, stream>>>(
+        slot.bclStage.p, r->clusterCount, r->readCount, len0, len1, wordsC, slot.codes4.p, slot.strand2.p, qualityStride, slot.qualityStrand.p);
+    ctx->launches += 2;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    ReadSetView &v = ctx->reads;
-    v.codes4 = ctx->readCodes4.p; v.strand2 = ctx->readStrand2.p; v.wordsC = wordsC; v.qualityStrand = ctx->readQualityStrand.p;
-    v.bases2 = ctx->readBases2.p; v.nmask = ctx->readNmask.p; v.quality = ctx->readQuality.p; v.endCyclesMasked = ctx->readMasked.p;
+    ReadSetView &v = slot.view;
+    v.codes4 = slot.codes4.p; v.strand2 = slot.strand2.p; v.wordsC = wordsC; v.qualityStrand = slot.qualityStrand.p;
+    v.bases2 = slot.bases2.p; v.nmask = slot.nmask.p; v.quality = slot.quality.p; v.endCyclesMasked = slot.masked.p;
     v.words2 = words2; v.wordsN = wordsN; v.qualityStride = qualityStride; v.readCount = r->readCount;
     v.readLength[0] = len0; v.readLength[1] = len1; v.firstCycle[0] = r->firstCycle[0]; v.firstCycle[1] = r->firstCycle[1];
     v.readTotal = uint32_t(readTotal);
-    ctx->clusterCount = r->clusterCount;
+    slot.clusterCount = r->clusterCount;
+    slot.key = *r;
+    return ISAAC_EXT_OK;
+}
+
+static bool sameReads(const isaac_ext_reads_t &a, const isaac_ext_reads_t &b)
+{
+    return a.bcl == b.bcl && a.endCyclesMasked == b.endCyclesMasked && a.clusterCount == b.clusterCount && a.readCount == b.readCount &&
+           a.readLength[0] == b.readLength[0] && a.readLength[1] == b.readLength[1] && a.firstCycle[0] == b.firstCycle[0] &&
+           a.firstCycle[1] == b.firstCycle[1];
+}
+
+extern "C" int isaac_ext_prefetch_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *r)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->stageStream) CK(cudaStreamCreateWithFlags(&ctx->stageStream, cudaStreamNonBlocking));
+    isaac_ext_ctx::ReadSlot &standby = ctx->readSlot[ctx->activeSlot ^ 1u];
+    if (!standby.ready) CK(cudaEventCreateWithFlags(&standby.ready, cudaEventDisableTiming));
+    standby.staged = false;
+    const int rc = loadReads(ctx, standby, r, ctx->stageStream);
+    if (rc) return rc;
+    CK(cudaEventRecord(standby.ready, ctx->stageStream));
+    standby.staged = true;
+    return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *r)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!r) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "bad read set");
+    isaac_ext_ctx::ReadSlot &standby = ctx->readSlot[ctx->activeSlot ^ 1u];
+    if (standby.staged && sameReads(standby.key, *r))
+    {
+        // the tile was prefetched: wait for its decode (long done when the previous tile took longer than the upload), take it over
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaEventSynchronize(standby.ready));
+        standby.staged = false;
+        ctx->activeSlot ^= 1u;
+        tileTakeOverPrefetchedBatch(ctx);       // the tile's matches, if they were prefetched too
+    }
+    else
+    {
+        const int rc = loadReads(ctx, ctx->slot(), r, ctx->stream);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->reads = ctx->slot().view;
+    ctx->clusterCount = ctx->slot().clusterCount;
     ctx->haveReads = true;
     return ISAAC_EXT_OK;
 }

@@ -63,7 +63,7 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
     v.readLength[0] = ctx->reads.readLength[0]; v.readLength[1] = rc > 1 ? ctx->reads.readLength[1] : 0;
     packLayout(v);
     v.tile = options->tile; v.barcodeIdx = options->barcodeIdx; v.keepUnaligned = options->keepUnaligned;
-    v.bcl = ctx->bclStage.p; v.bclBytes = uint64_t(n) * (v.readLength[0] + v.readLength[1]);
+    v.bcl = ctx->slot().bclStage.p; v.bclBytes = uint64_t(n) * (v.readLength[0] + v.readLength[1]);
     // record offsets: FragmentBuffer slots, or (compact) the prefix sum of the records' total lengths, computed here from the
     // host copy of the templates the kernel is about to get
     st.recordOffset.reserve(count + 1);

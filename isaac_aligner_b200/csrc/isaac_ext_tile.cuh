@@ -9,10 +9,22 @@
 namespace
 {
 
+/// the seed matches of a tile on the device: two slots, the tile in work and the one isaac_ext_prefetch_batch fills meanwhile
+struct TileInput
+{
+    DeviceBuffer<isaac_ext_match_t> dMatches;  DeviceBuffer<uint64_t> dMatchBegin;  DeviceBuffer<isaac_ext_seed_t> dSeeds;
+    isaac_ext_build_batch_t key{};  uint32_t clusters = 0;  bool staged = false;  cudaEvent_t ready = nullptr;
+    void release()
+    {
+        dMatches.release(); dMatchBegin.release(); dSeeds.release();
+        if (ready) cudaEventDestroy(ready);
+        ready = nullptr;
+    }
+};
+
 struct TileState
 {
-    // the tile's seed matches
-    DeviceBuffer<isaac_ext_match_t> dMatches;  DeviceBuffer<uint64_t> dMatchBegin;  DeviceBuffer<isaac_ext_seed_t> dSeeds;
+    TileInput input[2];  unsigned activeInput = 0;
     // candidate lists in match slots and the pools of the build pass
     DeviceBuffer<WorkFragment> dWork;  DeviceBuffer<uint32_t> dListBegin, dListCount;  DeviceBuffer<uint8_t> dBuilt;
     DeviceBuffer<isaac_ext_candidate_t> dCand1, dCand3, dAdapterFirst;
@@ -34,7 +46,7 @@ struct TileState
     uint64_t matchTotal = 0;
     ~TileState()
     {
-        dMatches.release(); dMatchBegin.release(); dSeeds.release(); dWork.release(); dListBegin.release(); dListCount.release(); dBuilt.release();
+        input[0].release(); input[1].release(); dWork.release(); dListBegin.release(); dListCount.release(); dBuilt.release();
         dCand1.release(); dCand3.release(); dAdapterFirst.release(); dFrag1.release(); dFrag3.release(); dFinal.release(); dCig1.release();
         dCig3.release(); dCigIndel.release(); dGapCounts.release(); dGapBegin.release(); dTasks.release(); dIndel.release(); dTaskValid.release(); dTaskSlots.release();
         dWords.release(); dFragmentBegin.release(); dWordBegin.release(); dOutCigars.release(); dOutFragments.release(); dOutBegin.release();
@@ -78,10 +90,23 @@ int checkTileFlag(isaac_ext_ctx *ctx, const uint32_t flag, const char *malformed
     return ctx->fail(ISAAC_EXT_E_CAPACITY, "a gapped CIGAR did not fit the cigar stride");
 }
 
+/// the tile's matches on 'stream' into 'in' (enqueue only)
+int uploadBatch(isaac_ext_ctx *ctx, TileInput &in, const isaac_ext_build_batch_t *batch, const uint32_t n, cudaStream_t stream)
+{
+    const uint64_t M = batch->clusterMatchBegin[n];
+    CK(in.dMatches.reserve(size_t(M) + 1)); CK(in.dMatchBegin.reserve(size_t(n) + 1)); CK(in.dSeeds.reserve(batch->seedCount));
+    if (M) CK(cudaMemcpyAsync(in.dMatches.p, batch->matches, size_t(M) * sizeof(isaac_ext_match_t), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(in.dMatchBegin.p, batch->clusterMatchBegin, (size_t(n) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(in.dSeeds.p, batch->seeds, batch->seedCount * sizeof(isaac_ext_seed_t), cudaMemcpyHostToDevice, stream));
+    in.key = *batch; in.clusters = n;
+    return ISAAC_EXT_OK;
+}
+
 TileView tileViewOf(isaac_ext_ctx *ctx, TileState &ts, const isaac_ext_build_batch_t *batch)
 {
     TileView v;
-    v.matches = ts.dMatches.p; v.clusterMatchBegin = ts.dMatchBegin.p; v.seeds = ts.dSeeds.p; v.seedCount = batch->seedCount;
+    const TileInput &in = ts.input[ts.activeInput];
+    v.matches = in.dMatches.p; v.clusterMatchBegin = in.dMatchBegin.p; v.seeds = in.dSeeds.p; v.seedCount = batch->seedCount;
     v.clusters = ctx->clusterCount; v.readCount = ctx->reads.readCount; v.repeatThreshold = ctx->cfg.repeatThreshold;
     v.gapLimit = ctx->cfg.semialignedGapLimit; v.withGaps = batch->withGaps ? 1u : 0u; v.gappedMismatchesMax = ctx->cfg.gappedMismatchesMax;
     v.readLength[0] = ctx->reads.readLength[0]; v.readLength[1] = ctx->reads.readLength[1];
@@ -111,15 +136,28 @@ int tileBuildDevice(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch)
     ts.matchTotal = M;
     PhaseTimer timer("build");
     const size_t slots = size_t(M) + 1;
-    CK(ts.dMatches.reserve(slots)); CK(ts.dMatchBegin.reserve(size_t(n) + 1)); CK(ts.dSeeds.reserve(batch->seedCount));
     CK(ts.dWork.reserve(slots)); CK(ts.dListBegin.reserve(lists + 1)); CK(ts.dListCount.reserve(lists + 1)); CK(ts.dBuilt.reserve(size_t(n) + 1));
     CK(ts.dCand1.reserve(slots)); CK(ts.dFrag1.reserve(slots)); CK(ts.dCig1.reserve(slots * 3)); CK(ts.dFinal.reserve(slots));
     CK(ts.dTasks.reserve(slots)); CK(ts.dIndel.reserve(slots)); CK(ts.dTaskValid.reserve(slots)); CK(ts.dCigIndel.reserve(slots * 5));
     CK(ts.dTaskSlots.reserve(slots + 1));
     CK(ts.dGapCounts.reserve(lists + 1)); CK(ts.dGapBegin.reserve(lists + 1)); CK(ts.hTotals.reserve(8));
-    if (M) CK(cudaMemcpyAsync(ts.dMatches.p, batch->matches, size_t(M) * sizeof(isaac_ext_match_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ts.dMatchBegin.p, batch->clusterMatchBegin, (size_t(n) + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ts.dSeeds.p, batch->seeds, batch->seedCount * sizeof(isaac_ext_seed_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        // the matches: on the device already when isaac_ext_prefetch_batch was given this batch and the isaac_ext_set_reads of this
+        // tile took it over (trusted once: the caller's buffers may change afterwards), else uploaded now
+        TileInput &in = ts.input[ts.activeInput];
+        if (in.staged && in.clusters == n && in.key.matches == batch->matches && in.key.clusterMatchBegin == batch->clusterMatchBegin &&
+            in.key.seeds == batch->seeds && in.key.seedCount == batch->seedCount)
+        {
+            CK(cudaEventSynchronize(in.ready));
+            in.staged = false;
+        }
+        else
+        {
+            in.staged = false;
+            const int rcu = uploadBatch(ctx, in, batch, n, ctx->stream);
+            if (rcu) return rcu;
+        }
+    }
     CK(cudaMemsetAsync(ts.dCand1.p, 0xFF, slots * sizeof(isaac_ext_candidate_t), ctx->stream));      // readId = TILE_NO_CANDIDATE everywhere
     CK(cudaMemsetAsync(ts.dTaskValid.p, 0, slots, ctx->stream));
     const bool withAdapters = ctx->adapters.count != 0;
@@ -195,6 +233,32 @@ int tileBuildDevice(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch)
 
 void releaseTile(TileState *state) { delete state; }
 
+/// isaac_ext_set_reads of a prefetched tile: the batch prefetched with it becomes the current one
+void tileTakeOverPrefetchedBatch(isaac_ext_ctx *ctx)
+{
+    if (!ctx->tile) return;
+    TileState &ts = *ctx->tile;
+    if (ts.input[ts.activeInput ^ 1u].staged) ts.activeInput ^= 1u;
+}
+
+extern "C" int isaac_ext_prefetch_batch(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, uint32_t clusterCount)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!batch || !batch->clusterMatchBegin || !batch->seeds || !batch->seedCount || !clusterCount) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null batch");
+    if (batch->clusterMatchBegin[clusterCount] && !batch->matches) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null matches");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->stageStream) CK(cudaStreamCreateWithFlags(&ctx->stageStream, cudaStreamNonBlocking));
+    if (!ctx->tile) ctx->tile = new TileState();
+    TileInput &standby = ctx->tile->input[ctx->tile->activeInput ^ 1u];
+    if (!standby.ready) CK(cudaEventCreateWithFlags(&standby.ready, cudaEventDisableTiming));
+    standby.staged = false;
+    const int rc = uploadBatch(ctx, standby, batch, clusterCount, ctx->stageStream);
+    if (rc) return rc;
+    CK(cudaEventRecord(standby.ready, ctx->stageStream));
+    standby.staged = true;
+    return ISAAC_EXT_OK;
+}
+
 extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, isaac_ext_build_result_t *result)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
@@ -262,7 +326,7 @@ int rescueDeviceCore(isaac_ext_ctx *ctx, const uint32_t n, RescueTotals &totals)
     // list and decide per request with the one predicate shadowTaskIsSmall (kernels_shadow.cuh), so every request is
     // handled by exactly one of them whatever the mix of window sizes and read lengths.
     const unsigned grid = std::max(1u, std::min<unsigned>(n, unsigned(ctx->smCount) * 6));
-    CK(ps.dTaskBegin.reserve(n)); CK(ps.dTaskCount.reserve(n)); CK(ps.dPoolSize.reserve(1));
+    CK(ps.dTaskBegin.reserve(n)); CK(ps.dTaskCount.reserve(n)); CK(ps.dPoolSize.reserve(1)); CK(ps.dLargeTasks.reserve(size_t(n) + 1));
     CK(ps.dShadowScratch.reserve(size_t(grid) * SHADOW_SCRATCH));
     uint64_t capacity = std::max<uint64_t>(ps.dCand.capacity, uint64_t(n) * 24 + 4096);
     unsigned long long poolSize64 = 0;
@@ -274,11 +338,13 @@ int rescueDeviceCore(isaac_ext_ctx *ctx, const uint32_t n, RescueTotals &totals)
         CK(cudaMemsetAsync(ps.dTaskBegin.p, 0, size_t(n) * sizeof(uint32_t), ctx->stream));
         CK(cudaMemsetAsync(ps.dTaskCount.p, 0, size_t(n) * sizeof(uint32_t), ctx->stream));
         const uint32_t poolCapacity = uint32_t(std::min<uint64_t>(ps.dCand.capacity, 0xFFFFFFFFull));
+        CK(cudaMemsetAsync(ps.dLargeTasks.p + n, 0, sizeof(uint32_t), ctx->stream));
         shadowCandidatesWarpKernel<<<gridFor(ctx, uint64_t(n) * 32, SHADOW_WARPS * 32, 6), SHADOW_WARPS * 32, 0, ctx->stream>>>(
-            ctx->ref, ctx->reads, n, ps.dShadowTasks.p, ps.dCand.p, poolCapacity, ps.dPoolSize.p, ps.dTaskBegin.p, ps.dTaskCount.p, ctx->errorFlag.p);
+            ctx->ref, ctx->reads, n, ps.dShadowTasks.p, ps.dCand.p, poolCapacity, ps.dPoolSize.p, ps.dTaskBegin.p, ps.dTaskCount.p, ctx->errorFlag.p,
+            ps.dLargeTasks.p, ps.dLargeTasks.p + n);
         shadowCandidatesKernel<<<grid, SHADOW_BLOCK, 0, ctx->stream>>>(ctx->ref, ctx->reads, n, ps.dShadowTasks.p, ps.dShadowScratch.p, ps.dCand.p,
                                                                         poolCapacity, ps.dPoolSize.p, ps.dTaskBegin.p, ps.dTaskCount.p,
-                                                                        ctx->errorFlag.p, true);
+                                                                        ctx->errorFlag.p, ps.dLargeTasks.p, ps.dLargeTasks.p + n);
         ctx->launches += 2;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&poolSize64, ps.dPoolSize.p, sizeof(poolSize64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -503,7 +569,7 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     CK(ts.dScratch.reserve(scratchBytes));
     CK(ts.dTemplates.reserve(size_t(n) + 1)); CK(ts.dTemplateFragments.reserve(count + 1));
     CK(ts.dTemplateWords.reserve(count + 1)); CK(ts.dTemplateWordBegin.reserve(count + 1));
-    finishTemplatesKernel<<<clusterGrid, 128, 0, ctx->stream>>>(fv, n, ts.dMatchBegin.p, ts.dScratch.p, ts.dTemplates.p, ts.dTemplateFragments.p,
+    finishTemplatesKernel<<<clusterGrid, 128, 0, ctx->stream>>>(fv, n, ts.input[ts.activeInput].dMatchBegin.p, ts.dScratch.p, ts.dTemplates.p, ts.dTemplateFragments.p,
                                                                 ts.dTemplateWords.p);
     ++ctx->launches;
     CK(cudaGetLastError());
@@ -556,10 +622,10 @@ extern "C" int isaac_ext_trim_low_quality_ends(isaac_ext_ctx *ctx, uint32_t base
     if (!ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reads first");
     CK(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->reads.readTotal;
-    trimLowQualityEndsKernel<<<gridFor(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->reads, baseQualityCutoff, ctx->readMasked.p);
+    trimLowQualityEndsKernel<<<gridFor(ctx, n, 256, 8), 256, 0, ctx->stream>>>(ctx->reads, baseQualityCutoff, ctx->slot().masked.p);
     ++ctx->launches;
     CK(cudaGetLastError());
-    if (endCyclesMaskedOut) CK(cudaMemcpyAsync(endCyclesMaskedOut, ctx->readMasked.p, size_t(n) * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (endCyclesMaskedOut) CK(cudaMemcpyAsync(endCyclesMaskedOut, ctx->slot().masked.p, size_t(n) * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ISAAC_EXT_OK;
 }

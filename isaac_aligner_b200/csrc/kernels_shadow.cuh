@@ -71,7 +71,7 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
                        int *__restrict__ scratch /* gridDim.x * SHADOW_SCRATCH */,
                        isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity, unsigned long long *__restrict__ poolSize,
                        uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount, uint32_t *__restrict__ errorFlag,
-                       const bool largeOnly = false)
+                       const uint32_t *__restrict__ taskList = nullptr, const uint32_t *__restrict__ taskListCount = nullptr)
 {
     __shared__ uint16_t table[SHADOW_TABLE];
     __shared__ int warpLast[SHADOW_BLOCK / 32];
@@ -84,11 +84,14 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
     int *cand = scratch + size_t(blockIdx.x) * SHADOW_SCRATCH;
     for (unsigned i = threadIdx.x; i < SHADOW_TABLE; i += blockDim.x) table[i] = SHADOW_EMPTY;
     __syncthreads();
-    for (uint32_t t = blockIdx.x; t < n; t += gridDim.x)
+    // with a task list (the requests the warp kernel left aside: windows beyond a warp's scratch, reads beyond its hash) the CTA
+    // walks that list only
+    const uint32_t total = taskListCount ? min(*taskListCount, n) : n;
+    for (uint32_t k = blockIdx.x; k < total; k += gridDim.x)
     {
+        const uint32_t t = taskList ? taskList[k] : k;
         const ShadowTask task = tasks[t];
         const unsigned L = reads.length(task.shadowReadId);
-        if (largeOnly && shadowTaskIsSmall(task, L)) continue;       // uniform for the CTA, before any barrier of this request
         const uint64_t *strandWords = reads.strandCodes(task.shadowReadId, task.contigStrand & 1u);
         const long window = task.windowEnd - task.windowBegin;
         // ---- hashShadowKmers (:53-72): first position of every 7-mer of the shadow; warp 0 walks the read in order
@@ -254,10 +257,17 @@ shadowCandidatesKernel(const ReferenceView ref, const ReadSetView reads, uint32_
 constexpr unsigned SHADOW_WARP_SLOTS = 512;
 constexpr unsigned SHADOW_WARPS = 8;
 
+/// first slot of a 7-mer: multiplicative hashing (neighbouring 7-mers of a read share six bases, an xor-fold of their codes
+/// sends them to neighbouring slots and linear probing then walks long runs: 3.8 probes per window position measured, 1.3 now)
+__device__ __forceinline__ unsigned shadowWarpSlot(const unsigned kmer) { return (kmer * 0x9E3779B1u) >> 23; }
+static_assert(SHADOW_WARP_SLOTS == 512, "shadowWarpSlot keeps the top 9 bits");
+
+/// The k-mers here are 14-bit fields cut straight out of the 2-bit packed words (base i at bits 2i; any one-to-one code of a
+/// 7-mer serves the hash as long as read and window use the same): no unpacking to one code per nibble on either side.
 __global__ void __launch_bounds__(SHADOW_WARPS * 32)
 shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uint32_t n, const ShadowTask *__restrict__ tasks, isaac_ext_candidate_t *__restrict__ pool, uint32_t poolCapacity,
                            unsigned long long *__restrict__ poolSize, uint32_t *__restrict__ taskBegin, uint32_t *__restrict__ taskCount,
-                           uint32_t *__restrict__ errorFlag)
+                           uint32_t *__restrict__ errorFlag, uint32_t *__restrict__ largeTasks, uint32_t *__restrict__ largeTaskCount)
 {
     __shared__ uint32_t hashAll[SHADOW_WARPS][SHADOW_WARP_SLOTS];
     __shared__ short candAll[SHADOW_WARPS][SHADOW_WARP_WINDOW];     // a hit = window position - read position: within +-1024
@@ -270,18 +280,28 @@ shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uin
     {
         const ShadowTask task = tasks[t];
         const unsigned L = reads.length(task.shadowReadId);
-        if (!shadowTaskIsSmall(task, L)) continue;
-        const uint64_t *strandWords = reads.strandCodes(task.shadowReadId, task.contigStrand & 1u);
+        if (!shadowTaskIsSmall(task, L))
+        {
+            if (lane == 0) largeTasks[atomicAdd(largeTaskCount, 1u)] = t;      // the CTA kernel's share
+            continue;
+        }
+        const uint64_t *strandWords = reads.strandWords2(task.shadowReadId, task.contigStrand & 1u);
         const long window = task.windowEnd - task.windowBegin;
-        for (unsigned i = lane; i < SHADOW_WARP_SLOTS; i += 32) hash[i] = EMPTY;
+        {
+            uint4 *h4 = reinterpret_cast<uint4 *>(hash);
+            for (unsigned i = lane; i < SHADOW_WARP_SLOTS / 4; i += 32) h4[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+        }
         __syncwarp();
         // ---- hashShadowKmers (:53-72): the first position of every 7-mer of the shadow
         for (unsigned p = lane; p + ISAAC_EXT_SHADOW_KMER <= L; p += 32)
         {
-            unsigned kmer;
-            if (!kmerOf(readCodes16(strandWords, p), kmer)) continue;
+            const uint64_t w0 = strandWords[p >> 4], w1 = strandWords[(p >> 4) + 1];
+            const unsigned off = p & 15u;
+            const uint32_t nFlags = (uint32_t(w0 >> 32) & 0xFFFFu) | (uint32_t(w1 >> 32) << 16);
+            if ((nFlags >> off) & 0x7Fu) continue;                              // a 7-mer with 'n' is never looked up
+            const unsigned kmer = __funnelshift_r(uint32_t(w0), uint32_t(w1), off * 2u) & 0x3FFFu;
             const uint32_t entry = (kmer << 16) | p;
-            unsigned h = (kmer ^ (kmer >> 5)) & (SHADOW_WARP_SLOTS - 1u);
+            unsigned h = shadowWarpSlot(kmer);
             while (true)
             {
                 const uint32_t seen = atomicCAS(&hash[h], EMPTY, entry);
@@ -293,29 +313,39 @@ shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uin
         __syncwarp();
         // ---- findShadowCandidatePositions (:74-102): lane l scans positions [l * piece, (l + 1) * piece) of the window
         const unsigned positions = window >= long(ISAAC_EXT_SHADOW_KMER) ? unsigned(window - long(ISAAC_EXT_SHADOW_KMER) + 1) : 0u;
-        const unsigned piece = (positions + 31u) / 32u;
-        const unsigned first = lane * piece, last = min(first + piece, positions);
-        const uint64_t g0 = ref.contigOffset[task.contigStrand >> 1] + uint64_t(task.windowBegin);
-        short *mine = cand + first;                     // at most 'piece' (<= 32) hits, kept in place until the compaction
+        const unsigned piece = (positions + 31u) / 32u;                         // <= 32
+        const unsigned first = min(lane * piece, positions), last = min(first + piece, positions);
+        const uint64_t gs = ref.contigOffset[task.contigStrand >> 1] + uint64_t(task.windowBegin) + first;
+        short *mine = cand + first;                     // at most 'piece' hits, kept in place until the compaction
         unsigned nKeep = 0;
         int firstHit = NONE, lastHit = NONE;
-        for (unsigned p0 = first; p0 < last; p0 += 10)  // a 16-base fetch holds ten 7-mers
+        if (first < last)
         {
-            uint64_t x = referenceCodes16(ref, g0 + p0);
-            const unsigned stop = min(p0 + 10u, last);
-            for (unsigned p = p0; p < stop; ++p, x >>= 4)
-            {
-                unsigned kmer;
-                if (!kmerOf(x, kmer)) continue;
-                unsigned h = (kmer ^ (kmer >> 5)) & (SHADOW_WARP_SLOTS - 1u);
+            // the piece's bases (at most 32 + 6) as three words aligned to its first base, its 'N' flags as two
+            const uint32_t *b = ref.bases2 + (gs >> 4);
+            const uint32_t w0 = __ldg(b), w1 = __ldg(b + 1), w2 = __ldg(b + 2), w3 = __ldg(b + 3);
+            const unsigned s2 = (unsigned(gs) & 15u) * 2u;
+            const uint32_t a0 = __funnelshift_r(w0, w1, s2), a1 = __funnelshift_r(w1, w2, s2), a2 = __funnelshift_r(w2, w3, s2);
+            const uint32_t *m = ref.nmask + (gs >> 5);
+            const uint32_t m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+            const unsigned s1 = unsigned(gs) & 31u;
+            const uint32_t n0 = __funnelshift_r(m0, m1, s1), n1 = __funnelshift_r(m1, m2, s1);
+            const bool anyN = (n0 | n1) != 0u;
+            const unsigned count = last - first;
+            auto look = [&](const unsigned q, const unsigned kmer) {
+                if (anyN && (__funnelshift_r(n0, n1, q) & 0x7Fu)) return;
+                unsigned h = shadowWarpSlot(kmer);
                 uint32_t seen;
                 while ((seen = hash[h]) != EMPTY && (seen >> 16) != kmer) h = (h + 1u) & (SHADOW_WARP_SLOTS - 1u);
-                if (seen == EMPTY) continue;
-                const int hit = int(p) - int(seen & 0xFFFFu);                                           // :89
+                if (seen == EMPTY) return;
+                const int hit = int(first + q) - int(seen & 0xFFFFu);                                   // :89
                 if (firstHit == NONE) firstHit = hit;
                 if (hit != lastHit) mine[nKeep++] = short(hit);                                         // :90-91 inside the lane
                 lastHit = hit;
-            }
+            };
+            const unsigned firstHalf = min(count, 16u);
+            for (unsigned q = 0; q < firstHalf; ++q) look(q, __funnelshift_r(a0, a1, q * 2u) & 0x3FFFu);
+            for (unsigned q = 16; q < count; ++q) look(q, __funnelshift_r(a1, a2, (q - 16u) * 2u) & 0x3FFFu);
         }
         // the last hit of the nearest lane before this one that had a hit: its equal drops this lane's first kept hit
         int incl = lastHit;
@@ -337,66 +367,117 @@ shadowCandidatesWarpKernel(const ReferenceView ref, const ReadSetView reads, uin
             if (lane >= d) scan += o;
         }
         const unsigned count = __shfl_sync(0xFFFFFFFFu, scan, 31);
-        // compaction in scan order: read all own hits first (the destinations of lower lanes may overlap this lane's piece)
-        short hold[32];
+        __syncwarp();
+        unsigned uniqueCount = 0;
+        unsigned long long base = 0;
+        if (count <= 32u)
+        {
+            // ---- the common case: the kept hits fit one register per lane.  Lane k takes the k-th hit in scan order: the lane whose
+            // range [scan - kept, scan) holds k, then sort (bitonic network over the lanes) + unique (:105-111)
+            const unsigned at = scan - kept;
+            // source lane of slot 'lane': the number of lanes whose inclusive count is <= lane
+            unsigned src = 0;
 #pragma unroll
-        for (unsigned k = 0; k < 32; ++k) hold[k] = k < kept ? mine[k + (dropFirst ? 1u : 0u)] : short(0);
-        __syncwarp();
-        const unsigned at = scan - kept;
-#pragma unroll
-        for (unsigned k = 0; k < 32; ++k) if (k < kept) cand[at + k] = hold[k];
-        __syncwarp();
-        // ---- sort + unique (:105-111)
-        unsigned n2 = 1;
-        while (n2 < count) n2 <<= 1;
-        for (unsigned i = count + lane; i < n2; i += 32) cand[i] = SHRT_MAX;
-        __syncwarp();
-        for (unsigned k = 2; k <= n2; k <<= 1)
-            for (unsigned j = k >> 1; j > 0; j >>= 1)
+            for (unsigned d = 16; d; d >>= 1)
             {
-                for (unsigned i = lane; i < n2; i += 32)
+                const unsigned probe = src + d - 1u;
+                const unsigned upTo = __shfl_sync(0xFFFFFFFFu, scan, probe);
+                if (upTo <= lane) src += d;
+            }
+            src = min(src, 31u);
+            const unsigned srcAt = __shfl_sync(0xFFFFFFFFu, at, src), srcFirst = __shfl_sync(0xFFFFFFFFu, first + (dropFirst ? 1u : 0u), src);
+            int value = lane < count ? int(cand[srcFirst + (lane - srcAt)]) : int(SHRT_MAX);
+#pragma unroll
+            for (unsigned k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                for (unsigned jj = k >> 1; jj > 0; jj >>= 1)
                 {
-                    const unsigned l = i ^ j;
-                    if (l > i)
-                    {
-                        const short a = cand[i], b = cand[l];
-                        if (((i & k) == 0) == (a > b)) { cand[i] = b; cand[l] = a; }
-                    }
+                    const int other = __shfl_xor_sync(0xFFFFFFFFu, value, jj);
+                    const bool up = (lane & k) == 0, lower = (lane & jj) == 0;
+                    value = (up == lower) ? min(value, other) : max(value, other);
                 }
+            const int before = __shfl_up_sync(0xFFFFFFFFu, value, 1);
+            const bool head = lane < count && (lane == 0 || value != before);
+            const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+            uniqueCount = __popc(heads);
+            if (lane == 0 && uniqueCount)
+            {
+                base = atomicAdd(poolSize, (unsigned long long)uniqueCount);
+                if (base + uniqueCount > poolCapacity) atomicOr(errorFlag, 2u);
+            }
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (head && base + uniqueCount <= poolCapacity)
+            {
+                isaac_ext_candidate_t c;
+                c.position = task.windowBegin + long(value);                                            // :216
+                c.readId = task.shadowReadId;
+                c.contigStrand = task.contigStrand;
+                pool[base + __popc(heads & ((1u << lane) - 1u))] = c;
+            }
+        }
+        else
+        {
+            // ---- many hits (a low-complexity shadow): compaction in scan order lane after lane (the destination of a lane ends
+            // in front of the pieces of the lanes behind it), bitonic sort in shared memory, unique in order
+            const unsigned at = scan - kept;
+            for (unsigned sl = 0; sl < 32; ++sl)
+            {
+                const unsigned k = __shfl_sync(0xFFFFFFFFu, kept, sl);
+                if (!k) continue;
+                const unsigned from = __shfl_sync(0xFFFFFFFFu, first + (dropFirst ? 1u : 0u), sl), to = __shfl_sync(0xFFFFFFFFu, at, sl);
+                const short v = lane < k ? cand[from + lane] : short(0);
+                __syncwarp();
+                if (lane < k) cand[to + lane] = v;
                 __syncwarp();
             }
-        // ordered unique: heads counted per group of 32 elements
-        unsigned uniqueCount = 0;
-        for (unsigned i0 = 0; i0 < count; i0 += 32)
-        {
-            const unsigned i = i0 + lane;
-            const bool head = i < count && (i == 0 || cand[i] != cand[i - 1]);
-            uniqueCount += __popc(__ballot_sync(0xFFFFFFFFu, head));
-        }
-        unsigned long long base = 0;
-        if (lane == 0 && uniqueCount)
-        {
-            base = atomicAdd(poolSize, (unsigned long long)uniqueCount);
-            if (base + uniqueCount > poolCapacity) atomicOr(errorFlag, 2u);
-        }
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (uniqueCount && base + uniqueCount <= poolCapacity)
-        {
-            unsigned before = 0;
+            unsigned n2 = 1;
+            while (n2 < count) n2 <<= 1;
+            for (unsigned i = count + lane; i < n2; i += 32) cand[i] = SHRT_MAX;
+            __syncwarp();
+            for (unsigned k = 2; k <= n2; k <<= 1)
+                for (unsigned jj = k >> 1; jj > 0; jj >>= 1)
+                {
+                    for (unsigned i = lane; i < n2; i += 32)
+                    {
+                        const unsigned l = i ^ jj;
+                        if (l > i)
+                        {
+                            const short x = cand[i], y = cand[l];
+                            if (((i & k) == 0) == (x > y)) { cand[i] = y; cand[l] = x; }
+                        }
+                    }
+                    __syncwarp();
+                }
             for (unsigned i0 = 0; i0 < count; i0 += 32)
             {
                 const unsigned i = i0 + lane;
                 const bool head = i < count && (i == 0 || cand[i] != cand[i - 1]);
-                const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
-                if (head)
+                uniqueCount += __popc(__ballot_sync(0xFFFFFFFFu, head));
+            }
+            if (lane == 0 && uniqueCount)
+            {
+                base = atomicAdd(poolSize, (unsigned long long)uniqueCount);
+                if (base + uniqueCount > poolCapacity) atomicOr(errorFlag, 2u);
+            }
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (uniqueCount && base + uniqueCount <= poolCapacity)
+            {
+                unsigned before = 0;
+                for (unsigned i0 = 0; i0 < count; i0 += 32)
                 {
-                    isaac_ext_candidate_t c;
-                    c.position = task.windowBegin + long(cand[i]);                                      // :216
-                    c.readId = task.shadowReadId;
-                    c.contigStrand = task.contigStrand;
-                    pool[base + before + __popc(heads & ((1u << lane) - 1u))] = c;
+                    const unsigned i = i0 + lane;
+                    const bool head = i < count && (i == 0 || cand[i] != cand[i - 1]);
+                    const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+                    if (head)
+                    {
+                        isaac_ext_candidate_t c;
+                        c.position = task.windowBegin + long(cand[i]);                                  // :216
+                        c.readId = task.shadowReadId;
+                        c.contigStrand = task.contigStrand;
+                        pool[base + before + __popc(heads & ((1u << lane) - 1u))] = c;
+                    }
+                    before += __popc(heads);
                 }
-                before += __popc(heads);
             }
         }
         if (lane == 0) { taskBegin[t] = count && base + uniqueCount <= poolCapacity ? uint32_t(base) : 0u; taskCount[t] = uniqueCount; }
