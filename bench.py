@@ -295,11 +295,19 @@ def pairs_pipeline_gpu(args, workload, local_rank, world, steps, warmup):
     e2e_ms, templates_ms = (float(x) for x in times.cpu())
     # MatchSelectorStats of the tile (TileBarcodeStats per read and pass filter), summed over the ranks: the path's one exchange
     templates = ctx._templates(res)
+    t0 = time.perf_counter()
+    cycle_stats = ctx.tile_cycle_stats()                         # matchSelector::TileStats: 4 x 47105 u64 (score histograms, per-cycle arrays)
+    cycle_ms = (time.perf_counter() - t0) * 1e3
     tile_stats = ctx.template_stats(mb, tls, templates)
-    summed = torch.from_numpy(tile_stats.view(np.int64).copy()).cuda()
+    payload = torch.from_numpy(np.concatenate([tile_stats.reshape(-1), cycle_stats.reshape(-1)]).view(np.int64).copy()).cuda()
+    t0 = time.perf_counter()
     if world > 1:
-        summed = distributed.allreduce_stats(summed)
-    read1 = summed.cpu().numpy().view(np.uint64)[0]
+        payload = distributed.allreduce_stats(payload)
+        torch.cuda.synchronize()
+    allreduce_ms = (time.perf_counter() - t0) * 1e3
+    payload = payload.cpu().numpy().view(np.uint64)
+    read1 = payload[:32]
+    cycles = payload[tile_stats.size:].reshape(4, -1)
     line = {"workload": "BASELINE configs[2] sharded: %d simulated 2x%d bp FR pairs per GPU per step on the %d bp / %d contig / %.1f %% N "
                         "synthetic genome resident on every GPU, indel events %.0e/base, seed matches from error-free auto seeds + 20 %% "
                         "decoys, explicit TLS 245/350/455; one step = isaac_ext_set_reads + isaac_ext_build_templates of one tile"
@@ -314,7 +322,12 @@ def pairs_pipeline_gpu(args, workload, local_rank, world, steps, warmup):
             "gpu_launches_per_step": int(launches),
             "matches_per_gpu": int(len(matches)), "rescue_requests": int(templates.rescue_requests),
             "templates_built": int(templates.templates["built"].sum()), "proper_pairs": int(templates.templates["properPair"].sum()),
-            "match_selector_stats_all_ranks": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16])))}
+            "match_selector_stats_all_ranks": dict(zip(distributed.TEMPLATE_STAT_NAMES, (int(x) for x in read1[:16]))),
+            "tile_stats_all_ranks": {"payload_u64": int(payload.size), "tile_cycle_stats_ms": cycle_ms, "allreduce_ms": allreduce_ms,
+                                     "read1_cycleMismatches": int(cycles[0, 34816:35840].sum()), "read1_cycleBlanks": int(cycles[0, 32768:33792].sum()),
+                                     "read1_uniquelyAlignedFragments": int(cycles[0, 47104]),
+                                     "is": "TileBarcodeStats summary + the full matchSelector::TileStats of every (read, pass filter), summed over "
+                                           "the ranks with one all-reduce: the path's only collective"}}
     ctx.close()
     return line, (genome, ReadSet(bcl, (L, L)), MatchBatch(matches, begin, seeds, with_gaps=True), tls, config)
 

@@ -494,6 +494,22 @@ typedef struct isaac_ext_pack_result {
 int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const struct isaac_ext_template_result *templates,
                              const isaac_ext_pack_options_t *options, isaac_ext_pack_result_t *result);
 
+/* matchSelector::TileStats of MatchSelectorStats (TileStats.hh:68-142, recorded like MatchSelectorStats.hh:77-103) for the templates
+ * the last isaac_ext_build_templates / isaac_ext_select_tile of this context left on the device (no other tile call in between): the
+ * alignment score histograms of fragments and templates and the per-cycle arrays (blanks, mismatches, fragments with 1 / 2 / 3 /
+ * 4 / 5 mismatches so far; each again for uniquely aligned fragments), one kernel pass.  statsOut: 4 blocks of
+ * ISAAC_EXT_TILE_CYCLE_STATS_WORDS u64, block = readIndex * 2 + passesFilter, each laid out like the struct:
+ * alignmentScoreFragments_[8192], alignmentScoreMismatches_[8192], alignmentScoreTemplates_[8192],
+ * alignmentScoreTemplateMismatches_[8192], cycleBlanks_[1024], cycleUniquelyAlignedBlanks_, cycleMismatches_,
+ * cycleUniquelyAlignedMismatches_, cycleUniquelyAligned{1,2,3,4,More}MismatchFragments_, cycle{1,2,3,4,More}MismatchFragments_,
+ * uniquelyAlignedFragmentCount_ -- the raw counters, which the ranks of a multi-GPU run sum with one all-reduce (the reference sums
+ * its per-thread TileStats, MatchSelector.cpp:439-442, TileStats.hh:144-237); isaac_ext_tile_cycle_stats_finalize then applies
+ * TileStats::finalize (:239-340) to one block.  A mismatch cycle is the reference's: the cycles of the alignment the template took
+ * the fragment from, cut to the fragment's final mismatch count (the end clippers and the low-quality filter leave the list alone). */
+#define ISAAC_EXT_TILE_CYCLE_STATS_WORDS 47105
+int isaac_ext_tile_cycle_stats(isaac_ext_ctx *ctx, const uint8_t *pf, uint64_t *statsOut);
+void isaac_ext_tile_cycle_stats_finalize(uint64_t *statsBlock);
+
 /* ---- one tile, the way MatchSelector::parallelSelect drives it (MatchSelector.cpp:370-443) ------------------------------ */
 /* Inputs as isaac-align leaves them for the match selector: the tile's BclClusters buffer and its match records (raw 16-byte
  * alignment::Match as io::MatchWriter writes them, sorted by cluster / location / seed, SelectMatchesTransition.cpp:242-254;
@@ -512,6 +528,8 @@ typedef struct isaac_ext_tile {
                                              from this tile (MatchSelector.cpp:401-417)                                       */
     isaac_ext_template_options_t options;
     const struct isaac_ext_pack_options *pack;   /* non-NULL: also leave the io::FragmentHeader records of the tile          */
+    uint32_t cycleStats;                  /* non-zero: also the TileStats of the tile (isaac_ext_tile_cycle_stats)             */
+    uint32_t pad;
 } isaac_ext_tile_t;
 
 typedef struct isaac_ext_tile_result {
@@ -521,10 +539,11 @@ typedef struct isaac_ext_tile_result {
     uint32_t packedValid;
     uint64_t stats[4 * 32];                      /* isaac_ext_template_stats of the tile                                      */
     const uint16_t *endCyclesMasked;             /* Read::endCyclesMasked_ after quality trimming, or NULL (no cutoff)        */
+    const uint64_t *cycleStats;                  /* 4 * ISAAC_EXT_TILE_CYCLE_STATS_WORDS raw counters, or NULL                */
 } isaac_ext_tile_result_t;
 
 /* set_reads -> trim_low_quality_ends -> determine_template_length (unless given) -> build_templates -> template_stats
- * (-> pack_fragments, result through isaac_ext_tile_packed): every step is a GPU pass of this library.  Tiles are independent once
+ * (-> tile_cycle_stats) (-> pack_fragments, result through isaac_ext_tile_packed): every step is a GPU pass of this library.  Tiles are independent once
  * the statistics are fixed: with several GPUs rank r runs tiles r, r + G, ... and the callers sum result.stats. */
 int isaac_ext_select_tile(isaac_ext_ctx *ctx, const isaac_ext_tile_t *tile, isaac_ext_tile_result_t *result);
 /* the io::FragmentHeader records the last isaac_ext_select_tile with tile.pack left (see isaac_ext_pack_fragments) */

@@ -36,7 +36,7 @@ EXPORTS = [
     "isaac_ext_build_templates", "isaac_ext_trim_low_quality_ends", "isaac_ext_set_adapters",
     "isaac_ext_determine_template_length", "isaac_ext_extend_batch_compact",
     "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
-    "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed", "isaac_ext_prefetch_reads", "isaac_ext_prefetch_batch",
+    "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed", "isaac_ext_prefetch_reads", "isaac_ext_prefetch_batch", "isaac_ext_tile_cycle_stats", "isaac_ext_tile_cycle_stats_finalize",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
 ]
 
@@ -291,6 +291,18 @@ class Context:
         out = np.zeros((4, TEMPLATE_STATS_COUNTERS), dtype=np.uint64)
         self._check(_lib.isaac_ext_template_stats(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(res),
                                                   _p(pf_arr), _p(out)))
+        return out
+
+    def tile_cycle_stats(self, pf=None, finalize=False):
+        """matchSelector::TileStats (score histograms + per-cycle arrays) of the templates the last build_templates / select_tile
+        left on the device -> uint64 [4, TILE_CYCLE_STATS_WORDS], row = readIndex * 2 + passesFilter"""
+        words = 47105
+        out = np.zeros((4, words), dtype=np.uint64)
+        pf_arr = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+        self._check(_lib.isaac_ext_tile_cycle_stats(self._h, _p(pf_arr), _p(out)))
+        if finalize:
+            for k in range(4):
+                _lib.isaac_ext_tile_cycle_stats_finalize(ctypes.c_void_p(out[k].ctypes.data))
         return out
 
     def pack_fragments(self, templates, options=None, copy=True):

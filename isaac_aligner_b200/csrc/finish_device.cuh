@@ -78,11 +78,26 @@ struct FinishView
     double rogRead[2], rogAll, logMismatchQ40;
 };
 
+/// Where the alignment of a template fragment came from: the candidate record as it was when the template took it.  The flags the
+/// template logic applies afterwards (setNoMatch, filterLowQualityFragments) and the end clippers leave mismatchCount and
+/// mismatchCycles of the reference's FragmentMetadata alone, and TileStats::recordFragment reads them (TileStats.hh:125-142): the
+/// per-cycle statistics re-derive the cycles from this alignment.
+struct FinishSource
+{
+    int64_t position;
+    uint32_t cigarOffset;           // pool << 30 | word index
+    uint32_t contigId;
+    uint16_t cigarLength;
+    uint8_t reverse, valid;
+    uint32_t pad;
+};
+
 /// FragmentMetadata as TemplateBuilder sees it; f.cigarOffset carries pool << 30 | word index
 struct FinishFragment
 {
     isaac_ext_fragment_t f;
     uint32_t alignmentScore;
+    FinishSource src;
 };
 
 /// TemplateBuilder::ShadowProbability (TemplateBuilder.hh:165-207)
@@ -232,13 +247,20 @@ struct FinishWorker
         f.repeatSeedsCount = 0; f.nonUniqueSeedOffsetFirst = 0xFFFF; f.nonUniqueSeedOffsetSecond = 0; f.firstSeedIndex = -1; f.lowClipped = 0;
         f.highClipped = 0; f.cigarLength = 0; f.reverse = 0; f.readIndex = uint8_t(readIndex); f.matchCount = 0;
         t.alignmentScore = ~0u;
+        t.src.position = 0; t.src.cigarOffset = 0; t.src.contigId = 0; t.src.cigarLength = 0; t.src.reverse = 0; t.src.valid = 0; t.src.pad = 0;
         return t;
     }
-    ISAAC_HD static FinishFragment fromRecord(const isaac_ext_fragment_t &f) { FinishFragment t; t.f = f; t.alignmentScore = ~0u; return t; }
+    ISAAC_HD static void rememberSource(FinishFragment &t)
+    {
+        t.src.position = t.f.position; t.src.cigarOffset = t.f.cigarOffset; t.src.contigId = t.f.contigId; t.src.cigarLength = t.f.cigarLength;
+        t.src.reverse = t.f.reverse; t.src.valid = 1; t.src.pad = 0;
+    }
+    ISAAC_HD static FinishFragment fromRecord(const isaac_ext_fragment_t &f) { FinishFragment t; t.f = f; t.alignmentScore = ~0u; rememberSource(t); return t; }
     ISAAC_HD FinishFragment fromRescue(const uint32_t index) const
     {
         FinishFragment t = fromRecord(v.rescueFragments[index]);
         t.f.cigarOffset = (FINISH_POOL_RESCUE << FINISH_POOL_SHIFT) | t.f.cigarOffset;
+        rememberSource(t);
         return t;
     }
 
@@ -604,7 +626,7 @@ struct FinishWorker
 /// the BamTemplate of one cluster as the flat records of the result; fragment.cigarOffset stays pool << 30 | word index, the
 /// caller gathers the words (gatherTemplateCigars below / gatherTemplateCigarsKernel)
 ISAAC_HD inline void finishCluster(const FinishView &v, const uint32_t cluster, unsigned char *scratch, const uint64_t shadows, const uint64_t candidates,
-                                   isaac_ext_template_t &o, isaac_ext_fragment_t *fragments)
+                                   isaac_ext_template_t &o, isaac_ext_fragment_t *fragments, FinishSource *sources = nullptr)
 {
     FinishWorker w(v, cluster, scratch, shadows, candidates);
     const bool ok = w.run();
@@ -616,6 +638,7 @@ ISAAC_HD inline void finishCluster(const FinishView &v, const uint32_t cluster, 
         f.readId = cluster * v.readCount + r;
         o.fragmentAlignmentScore[r] = w.bam[r].alignmentScore;
         fragments[r] = f;
+        if (sources) sources[r] = w.bam[r].src;
     }
 }
 

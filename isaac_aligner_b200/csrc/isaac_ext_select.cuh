@@ -6,6 +6,7 @@ struct SelectState
 {
     std::vector<uint64_t> clusterMatchBegin;
     std::vector<uint16_t> endCyclesMasked;
+    std::vector<uint64_t> cycleStats;
     isaac_ext_pack_result_t packed;
 };
 void releaseSelect(SelectState *state) { delete state; }
@@ -58,6 +59,13 @@ extern "C" int isaac_ext_select_tile(isaac_ext_ctx *ctx, const isaac_ext_tile_t 
     }
     rc = isaac_ext_build_templates(ctx, &batch, &result->tls, &tile->options, &result->templates);
     if (rc) return rc;
+    if (tile->cycleStats)                     // first: it reads the templates the build left on the device
+    {
+        st.cycleStats.resize(4 * size_t(ISAAC_EXT_TILE_CYCLE_STATS_WORDS));
+        rc = isaac_ext_tile_cycle_stats(ctx, tile->pf, st.cycleStats.data());
+        if (rc) return rc;
+        result->cycleStats = st.cycleStats.data();
+    }
     rc = isaac_ext_template_stats(ctx, &batch, &result->tls, &result->templates, tile->pf, result->stats);
     if (rc) return rc;
     if (tile->pack)

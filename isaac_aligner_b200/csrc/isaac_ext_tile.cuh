@@ -44,6 +44,9 @@ struct TileState
     PinnedBuffer<isaac_ext_template_t> hTemplates;  PinnedBuffer<isaac_ext_fragment_t> hTemplateFragments;  PinnedBuffer<uint32_t> hTemplateCigars;
     PinnedBuffer<uint32_t> hTotals;
     uint64_t matchTotal = 0;
+    // what isaac_ext_tile_cycle_stats needs of the last isaac_ext_build_templates
+    DeviceBuffer<FinishSource> dTemplateSources;  DeviceBuffer<unsigned long long> dCycleStats;  DeviceBuffer<uint8_t> dPf;
+    bool templatesResident = false;
     ~TileState()
     {
         input[0].release(); input[1].release(); dWork.release(); dListBegin.release(); dListCount.release(); dBuilt.release();
@@ -54,6 +57,7 @@ struct TileState
         dRequestCounts.release(); dRequestBegin.release(); dRequests.release(); dScratch.release(); dTemplates.release();
         dTemplateFragments.release(); dTemplateWords.release(); dTemplateWordBegin.release(); dTemplateCigars.release(); dClippedCigars.release();
         hTemplates.release(); hTemplateFragments.release(); hTemplateCigars.release(); hTotals.release();
+        dTemplateSources.release(); dCycleStats.release(); dPf.release();
     }
 };
 
@@ -134,6 +138,7 @@ int tileBuildDevice(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch)
     if (!ctx->tile) ctx->tile = new TileState();
     TileState &ts = *ctx->tile;
     ts.matchTotal = M;
+    ts.templatesResident = false;
     PhaseTimer timer("build");
     const size_t slots = size_t(M) + 1;
     CK(ts.dWork.reserve(slots)); CK(ts.dListBegin.reserve(lists + 1)); CK(ts.dListCount.reserve(lists + 1)); CK(ts.dBuilt.reserve(size_t(n) + 1));
@@ -568,9 +573,9 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     const uint64_t scratchBytes = finishScratchBytes(totals.fragments, ts.matchTotal) + uint64_t(n) * finishScratchBytes(0, 0);
     CK(ts.dScratch.reserve(scratchBytes));
     CK(ts.dTemplates.reserve(size_t(n) + 1)); CK(ts.dTemplateFragments.reserve(count + 1));
-    CK(ts.dTemplateWords.reserve(count + 1)); CK(ts.dTemplateWordBegin.reserve(count + 1));
+    CK(ts.dTemplateWords.reserve(count + 1)); CK(ts.dTemplateWordBegin.reserve(count + 1)); CK(ts.dTemplateSources.reserve(count + 1));
     finishTemplatesKernel<<<clusterGrid, 128, 0, ctx->stream>>>(fv, n, ts.input[ts.activeInput].dMatchBegin.p, ts.dScratch.p, ts.dTemplates.p, ts.dTemplateFragments.p,
-                                                                ts.dTemplateWords.p);
+                                                                ts.dTemplateWords.p, ts.dTemplateSources.p);
     ++ctx->launches;
     CK(cudaGetLastError());
     CK(exclusiveSum(ctx, ts.dTemplateWords.p, ts.dTemplateWordBegin.p, count));
@@ -613,7 +618,56 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     timer.mark("gather + clip + copies");
     result->templates = ts.hTemplates.p; result->fragments = ts.hTemplateFragments.p; result->cigars = ts.hTemplateCigars.p;
     result->cigarWords = words; result->rescueRequests = requestTotal;
+    ts.templatesResident = true;
     return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_tile_cycle_stats(isaac_ext_ctx *ctx, const uint8_t *pf, uint64_t *statsOut)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!statsOut) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
+    if (!ctx->tile || !ctx->tile->templatesResident)
+        return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "no templates on the device: isaac_ext_build_templates / isaac_ext_select_tile of the tile first");
+    CK(cudaSetDevice(ctx->device));
+    TileState &ts = *ctx->tile;
+    PipelineState &ps = ctx->pipeline;
+    const uint32_t n = ctx->clusterCount;
+    const size_t words = 4 * size_t(ISAAC_EXT_TILE_CYCLE_STATS_WORDS);
+    CK(ts.dCycleStats.reserve(words));
+    CK(cudaMemsetAsync(ts.dCycleStats.p, 0, words * sizeof(unsigned long long), ctx->stream));
+    if (pf) { CK(ts.dPf.reserve(n)); CK(cudaMemcpyAsync(ts.dPf.p, pf, n, cudaMemcpyHostToDevice, ctx->stream)); }
+    tileCycleStatsKernel<<<gridFor(ctx, n, 128, 16), 128, 0, ctx->stream>>>(ctx->ref, ctx->reads, ctx->sp, n, ts.dTemplates.p, ts.dTemplateFragments.p,
+                                                                          ts.dTemplateSources.p, ts.dCig1.p, ts.dCigIndel.p, ts.dCig3.p, ps.dOutCigars.p,
+                                                                          pf ? ts.dPf.p : nullptr, ts.dCycleStats.p, ctx->errorFlag.p);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(statsOut, ts.dCycleStats.p, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->errorFlag.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag)
+    {
+        cudaMemsetAsync(ctx->errorFlag.p, 0, sizeof(uint32_t), ctx->stream);
+        return ctx->fail(ISAAC_EXT_E_CAPACITY, "an alignment score exceeds TileStats::maxAlignmentScore_ (0x1FFF; the reference asserts)");
+    }
+    return ISAAC_EXT_OK;
+}
+
+/// TileStats::finalize (TileStats.hh:239-340) on the raw counters of one block: the five "fragments with X mismatches so far"
+/// arrays (plain and uniquely aligned) become per-cycle counts of fragments that have exactly 1, <= 2, <= 3, <= 4, <= 5 mismatches
+extern "C" void isaac_ext_tile_cycle_stats_finalize(uint64_t *block)
+{
+    for (unsigned group = 0; group < 2; ++group)
+    {
+        long *x[5];
+        for (unsigned k = 0; k < 5; ++k) x[k] = reinterpret_cast<long *>(block) + (group ? TCS_X : TCS_UNIQUE_X) + k * 1024;
+        // a mismatch seen at one cycle stays for all later cycles (:242-262, 295-313)
+        for (unsigned k = 0; k < 5; ++k) for (unsigned c = 1; c < 1024; ++c) x[k][c] += x[k][c - 1];
+        // a fragment with a second mismatch stops being a one-mismatch fragment (:264-276, 315-327)
+        for (unsigned k = 0; k + 1 < 5; ++k) for (unsigned c = 0; c < 1024; ++c) x[k][c] -= x[k + 1][c];
+        // two-mismatch fragments include the one-mismatch ones and so on (:278-290, 329-340)
+        for (unsigned k = 1; k < 5; ++k) for (unsigned c = 0; c < 1024; ++c) x[k][c] += x[k - 1][c];
+    }
 }
 
 extern "C" int isaac_ext_trim_low_quality_ends(isaac_ext_ctx *ctx, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut)

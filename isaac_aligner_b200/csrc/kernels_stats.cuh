@@ -4,6 +4,8 @@
 // include/alignment/matchSelector/TileStats.hh:68-93).
 #pragma once
 #include "device_types.cuh"
+#include "finish_device.cuh"
+#include "score.cuh"
 
 namespace isaac_b200
 {
@@ -157,6 +159,140 @@ __global__ void templateStatsKernel(const ReadSetView reads, const TlsDevice tls
     __syncthreads();
     for (unsigned i = threadIdx.x; i < 4 * TS_COUNT; i += blockDim.x)
         if (block[i]) atomicAdd(&stats[i], block[i]);
+}
+
+// ---- matchSelector::TileStats of a tile's templates (TileStats.hh:68-142): the alignment score histograms and the per-cycle
+// arrays, recorded the way MatchSelectorStats::recordTemplate does (MatchSelectorStats.hh:77-103).  One cluster per thread; the
+// counters are global u64 words (one block of TILE_CYCLE_STATS_WORDS per read index and pass filter), the score histograms
+// warp-aggregated (most fragments of a tile share a few scores).
+// mismatchCycles of a FragmentMetadata are filled by the updateFragmentCigar call that scored its alignment and are NOT touched by
+// what happens to the fragment afterwards (setNoMatch, filterLowQualityFragments, the end clippers only change mismatchCount): the
+// reference reads the first mismatchCount entries of that list.  Here the list is re-derived by scoring the alignment the template
+// took the fragment from (FinishSource) once more, and cut to the final mismatchCount.
+enum : unsigned
+{
+    TCS_SCORE_FRAGMENTS = 0, TCS_SCORE_MISMATCHES = 8192, TCS_SCORE_TEMPLATES = 16384, TCS_SCORE_TEMPLATE_MISMATCHES = 24576,
+    TCS_BLANKS = 32768, TCS_UNIQUE_BLANKS = 33792, TCS_MISMATCHES = 34816, TCS_UNIQUE_MISMATCHES = 35840,
+    TCS_UNIQUE_X = 36864,           // five arrays: 1, 2, 3, 4, "more" (= exactly 5) mismatches so far
+    TCS_X = 41984,                  // five arrays
+    TCS_UNIQUE_FRAGMENTS = 47104, TCS_WORDS = ISAAC_EXT_TILE_CYCLE_STATS_WORDS
+};
+static_assert(TCS_WORDS == 47105, "TileStats layout");
+
+__global__ void tileCycleStatsKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams spGlobal, const uint32_t clusters,
+                                     const isaac_ext_template_t *__restrict__ templates, const isaac_ext_fragment_t *__restrict__ fragments,
+                                     const FinishSource *__restrict__ sources, const uint32_t *pool0, const uint32_t *pool1, const uint32_t *pool2,
+                                     const uint32_t *pool3, const uint8_t *__restrict__ pf, unsigned long long *__restrict__ stats,
+                                     uint32_t *__restrict__ errorFlag)
+{
+    __shared__ double tables[201];
+    const ScoreParams sp = stageScoreTables(spGlobal, tables);
+    const unsigned rc = reads.readCount, lane = threadIdx.x & 31u;
+    const uint32_t perGrid = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < clusters; base += perGrid)
+    {
+        const uint32_t c = base + lane;
+        const bool live = c < clusters;
+        const bool passes = live && (!pf || pf[c]);
+        isaac_ext_template_t t;
+        if (live) t = templates[c];
+        unsigned templateMismatches = 0, firstReadIndex = 0;
+        for (unsigned r = 0; r < rc; ++r)
+        {
+            isaac_ext_fragment_t f;
+            uint32_t score = 0xFFFFFFFFu;
+            if (live) { f = fragments[size_t(c) * rc + r]; score = t.fragmentAlignmentScore[r]; }
+            const bool hasScore = live && score != 0xFFFFFFFFu;
+            if (hasScore && score > 0x1FFFu) { atomicOr(errorFlag, 64u); score = 0x1FFFu; }      // the reference asserts (TileStats.hh:128)
+            const bool unique = live && f.cigarLength != 0 && hasScore && score > 3u;            // FragmentMetadata.hh:268
+            if (live) { templateMismatches += f.mismatchCount; if (!r) firstReadIndex = f.readIndex; }
+            // ---- alignment score histogram of the fragments: one add per distinct (score, pass) of the warp
+            {
+                const unsigned key = hasScore ? score * 2u + (passes ? 1u : 0u) : 0xFFFFFFFFu - lane;
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+                if (hasScore && lane == __ffs(peers) - 1u)
+                {
+                    atomicAdd(stats + size_t(r * 2) * TCS_WORDS + TCS_SCORE_FRAGMENTS + score, (unsigned long long)__popc(peers));
+                    if (passes) atomicAdd(stats + size_t(r * 2 + 1) * TCS_WORDS + TCS_SCORE_FRAGMENTS + score, (unsigned long long)__popc(peers));
+                }
+                if (hasScore && f.mismatchCount)
+                    for (unsigned p = 0; p < (passes ? 2u : 1u); ++p)
+                        atomicAdd(stats + size_t(r * 2 + p) * TCS_WORDS + TCS_SCORE_MISMATCHES + score, (unsigned long long)f.mismatchCount);
+            }
+            if (!live) continue;
+            const unsigned L = reads.readLength[r], firstCycle = reads.firstCycle[r];
+            const uint32_t readId = c * rc + r;
+            // ---- blanks: the 'n' of the forward sequence per cycle
+            for (unsigned w = 0; w * 32u < L; ++w)
+            {
+                uint32_t n = reads.nmask[size_t(readId) * reads.wordsN + w];
+                while (n)
+                {
+                    const unsigned i = w * 32u + (__ffs(n) - 1u);
+                    n &= n - 1u;
+                    if (i >= L) break;
+                    for (unsigned p = 0; p < (passes ? 2u : 1u); ++p)
+                    {
+                        unsigned long long *s = stats + size_t(r * 2 + p) * TCS_WORDS;
+                        atomicAdd(s + TCS_BLANKS + firstCycle + i, 1ull);
+                        if (unique) atomicAdd(s + TCS_UNIQUE_BLANKS + firstCycle + i, 1ull);
+                    }
+                }
+            }
+            if (unique) for (unsigned p = 0; p < (passes ? 2u : 1u); ++p) atomicAdd(stats + size_t(r * 2 + p) * TCS_WORDS + TCS_UNIQUE_FRAGMENTS, 1ull);
+            // ---- mismatch cycles
+            const FinishSource src = sources[size_t(c) * rc + r];
+            unsigned wanted = f.mismatchCount;
+            if (!wanted || !src.valid || !src.cigarLength) continue;
+            uint64_t mask[ISAAC_EXT_MASK_WORDS];
+            for (unsigned k = 0; k < ISAAC_EXT_MASK_WORDS; ++k) mask[k] = 0;
+            {
+                const uint32_t pool = src.cigarOffset >> FINISH_POOL_SHIFT;
+                const uint32_t *cigar = (pool == 0 ? pool0 : pool == 1 ? pool1 : pool == 2 ? pool2 : pool3) + (src.cigarOffset & FINISH_POOL_MASK);
+                isaac_ext_fragment_t scratch;
+                scoreCigar(ref, reads, sp, readId, L, src.reverse != 0, ref.contigOffset[src.contigId], long(src.position), cigar, src.cigarLength, scratch, mask);
+            }
+            const unsigned total = wanted;
+            unsigned k = 0;
+            for (unsigned w = 0; w < ISAAC_EXT_MASK_WORDS && k < total; ++w)
+            {
+                uint64_t m = mask[w];
+                while (m && k < total)
+                {
+                    const unsigned i = w * 64u + (__ffsll((long long)m) - 1u);
+                    m &= m - 1ull;
+                    const unsigned cycle = src.reverse ? firstCycle + L - 1u - i : firstCycle + i;           // AlignerBase.cpp:171
+                    const unsigned number = src.reverse ? total - k : k + 1u;                                // cycleMismatchNumber
+                    ++k;
+                    for (unsigned p = 0; p < (passes ? 2u : 1u); ++p)
+                    {
+                        unsigned long long *s = stats + size_t(r * 2 + p) * TCS_WORDS;
+                        atomicAdd(s + TCS_MISMATCHES + cycle, 1ull);
+                        if (number <= 5u) atomicAdd(s + TCS_X + (number - 1u) * 1024u + cycle, 1ull);
+                        if (unique)
+                        {
+                            atomicAdd(s + TCS_UNIQUE_MISMATCHES + cycle, 1ull);
+                            if (number <= 5u) atomicAdd(s + TCS_UNIQUE_X + (number - 1u) * 1024u + cycle, 1ull);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- the template's own score (recordTemplate, TileStats.hh:113-123): under the read index of fragment 0
+        {
+            uint32_t score = live ? t.alignmentScore : 0xFFFFFFFFu;
+            const bool hasScore = live && score != 0xFFFFFFFFu;
+            if (hasScore && score > 0x1FFFu) { atomicOr(errorFlag, 64u); score = 0x1FFFu; }
+            const unsigned key = hasScore ? (score * 2u + (passes ? 1u : 0u)) * 2u + firstReadIndex : 0xFFFFFFFFu - lane;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+            if (hasScore && lane == __ffs(peers) - 1u)
+                for (unsigned p = 0; p < (passes ? 2u : 1u); ++p)
+                    atomicAdd(stats + size_t(firstReadIndex * 2 + p) * TCS_WORDS + TCS_SCORE_TEMPLATES + score, (unsigned long long)__popc(peers));
+            if (hasScore && templateMismatches)
+                for (unsigned p = 0; p < (passes ? 2u : 1u); ++p)
+                    atomicAdd(stats + size_t(firstReadIndex * 2 + p) * TCS_WORDS + TCS_SCORE_TEMPLATE_MISMATCHES + score, (unsigned long long)templateMismatches);
+        }
+    }
 }
 
 } // namespace isaac_b200

@@ -389,7 +389,8 @@ __global__ void shadowWindowsKernel(const uint32_t n, const isaac_ext_rescue_req
 /// the match batch's own offsets without another prefix sum.
 __global__ void finishTemplatesKernel(const FinishView v, const uint32_t clusters, const uint64_t *__restrict__ clusterMatchBegin,
                                       unsigned char *__restrict__ scratch, isaac_ext_template_t *__restrict__ templates,
-                                      isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigarLengths)
+                                      isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigarLengths,
+                                      FinishSource *__restrict__ sources)
 {
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < clusters; c += gridDim.x * blockDim.x)
     {
@@ -399,12 +400,14 @@ __global__ void finishTemplatesKernel(const FinishView v, const uint32_t cluster
         unsigned char *slice = scratch + (finishScratchBytes(shadowsBefore, candidatesBefore) + uint64_t(c) * finishScratchBytes(0, 0) - finishScratchBytes(0, 0));
         isaac_ext_template_t o;
         isaac_ext_fragment_t f[2];
-        finishCluster(v, c, slice, shadows, candidates, o, f);
+        FinishSource src[2];
+        finishCluster(v, c, slice, shadows, candidates, o, f, src);
         templates[c] = o;
         for (unsigned r = 0; r < v.readCount; ++r)
         {
             fragments[size_t(c) * v.readCount + r] = f[r];
             cigarLengths[size_t(c) * v.readCount + r] = f[r].cigarLength;
+            sources[size_t(c) * v.readCount + r] = src[r];
         }
     }
 }

@@ -49,9 +49,9 @@ def cluster_match_begin(matches, cluster_count):
 
 
 class TileResult:
-    def __init__(self, templates, tls, tls_stable, stats, end_cycles_masked, packed=None):
+    def __init__(self, templates, tls, tls_stable, stats, end_cycles_masked, packed=None, cycle_stats=None):
         self.templates, self.tls, self.tls_stable, self.stats, self.end_cycles_masked = templates, tls, tls_stable, stats, end_cycles_masked
-        self.packed = packed
+        self.packed, self.cycle_stats = packed, cycle_stats
 
 
 class TileC(ctypes.Structure):
@@ -59,17 +59,17 @@ class TileC(ctypes.Structure):
     _fields_ = [("reads", Reads), ("matches", ctypes.c_void_p), ("matchCount", ctypes.c_uint64), ("seeds", ctypes.c_void_p),
                 ("seedCount", ctypes.c_uint32), ("withGaps", ctypes.c_uint32), ("pf", ctypes.c_void_p),
                 ("baseQualityCutoff", ctypes.c_uint32), ("mateDriftRange", ctypes.c_int32), ("tls", ctypes.c_void_p),
-                ("options", TemplateOptions), ("pack", ctypes.c_void_p)]
+                ("options", TemplateOptions), ("pack", ctypes.c_void_p), ("cycleStats", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
 
 
 class TileResultC(ctypes.Structure):
     """isaac_ext_tile_result_t"""
     _fields_ = [("templates", TemplateResult), ("tls", Tls), ("tlsStable", ctypes.c_uint32), ("packedValid", ctypes.c_uint32),
-                ("stats", ctypes.c_uint64 * 128), ("endCyclesMasked", ctypes.c_void_p)]
+                ("stats", ctypes.c_uint64 * 128), ("endCyclesMasked", ctypes.c_void_p), ("cycleStats", ctypes.c_void_p)]
 
 
 def select_tile(ctx, bcl, read_lengths, matches, seeds, pf=None, base_quality_cutoff=0, tls=None, options=None,
-                mate_drift_range=-1, with_gaps=True, pack=None):
+                mate_drift_range=-1, with_gaps=True, pack=None, cycle_stats=False):
     """MatchSelector::parallelSelect for one tile on the context's GPU = ONE call of isaac_ext_select_tile.  tls: user-defined
     template length statistics (batch.Tls) or None = determine them from this tile.  pack: batch.PackOptions = also leave the
     io::FragmentHeader bin records FragmentCollector::add stores for the tile (TileResult.packed), None = skip that pass."""
@@ -81,7 +81,8 @@ def select_tile(ctx, bcl, read_lengths, matches, seeds, pf=None, base_quality_cu
     options = options if options is not None else TemplateOptions.make()
     t = TileC(reads.c, matches.ctypes.data if matches.size else None, matches.size, seeds.ctypes.data, seeds.size, 1 if with_gaps else 0,
               pf_a.ctypes.data if pf_a is not None else None, int(base_quality_cutoff), int(mate_drift_range),
-              ctypes.addressof(tls) if tls is not None else None, options, ctypes.addressof(pack.c) if pack is not None else None)
+              ctypes.addressof(tls) if tls is not None else None, options, ctypes.addressof(pack.c) if pack is not None else None,
+              1 if cycle_stats else 0, 0)
     res = TileResultC()
     ctx._check(capi._lib.isaac_ext_select_tile(ctx._h, ctypes.byref(t), ctypes.byref(res)))
     ctx.reads = reads
@@ -100,4 +101,8 @@ def select_tile(ctx, bcl, read_lengths, matches, seeds, pf=None, base_quality_cu
         pr = PackResultC()
         ctx._check(capi._lib.isaac_ext_tile_packed(ctx._h, ctypes.byref(pr)))
         packed = ctx._packed(pr, bool(pack.c.compact))
-    return TileResult(templates, out_tls, bool(res.tlsStable), stats, masked, packed)
+    cycles = None
+    if res.cycleStats:
+        buf = (ctypes.c_char * (4 * 47105 * 8)).from_address(res.cycleStats)
+        cycles = np.frombuffer(buf, dtype=np.uint64).copy().reshape(4, 47105)
+    return TileResult(templates, out_tls, bool(res.tlsStable), stats, masked, packed, cycles)

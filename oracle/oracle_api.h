@@ -116,6 +116,13 @@ int oracle_pack_fragments(const isaac_ext_reads_t *reads, const isaac_ext_templa
                           uint8_t *recordsOut, uint64_t *fStrandPosOut, uint8_t *initializedOut, uint8_t *headerMaskOut,
                           uint32_t *layoutOut);
 
+/* liboracle_ref only: matchSelector::TileStats (score histograms + per-cycle arrays) of the tile's templates, see
+ * isaac_ext_tile_cycle_stats; finalize != 0 applies TileStats::finalize */
+int oracle_tile_cycle_stats(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *config,
+                            const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                            const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t finalize,
+                            uint32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "alignment/BandedSmithWaterman.hh"
+#include "alignment/matchSelector/TileStats.hh"
 #include "alignment/FragmentBuilder.hh"
 #include "alignment/ShadowAligner.hh"
 #include "alignment/TemplateBuilder.hh"
@@ -531,6 +532,83 @@ static void flattenStats(const alignment::matchSelector::TileBarcodeStats &s, ui
     out[29] += s.fragmentCount_;
 }
 
+/// every cluster of the tile through the template pipeline, recorded into parts[thread][readIndex * 2 + passesFilter] the way
+/// MatchSelectorStats::recordTemplate dispatches (MatchSelectorStats.hh:77-103); Stats = TileBarcodeStats or TileStats
+template <class Stats>
+static void recordTileTemplates(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
+                                const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls, const isaac_ext_template_options_t *options,
+                                const uint8_t *pf, std::vector<std::vector<Stats> > &parts, uint32_t threads)
+{
+    using namespace alignment::matchSelector;
+    const std::vector<reference::Contig> &contigs = makeContigs(genome);
+    const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
+    const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
+    const SequencingAdapterList &adapterList = currentAdapters();
+    alignment::SeedMetadataList seeds;
+    for (uint32_t s = 0; s < batch->seedCount; ++s)
+        seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
+    const alignment::TemplateLengthStatistics stats(
+        tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
+        alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
+        alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[1]), tls->mateDriftRange);
+    const alignment::RestOfGenomeCorrection rog(contigs, rml);
+    const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
+    const uint32_t n = reads->clusterCount;
+    parallelFor(n, threads, [&](uint32_t t, uint32_t b, uint32_t e) {
+        std::unique_ptr<alignment::TemplateBuilder> builder(new alignment::TemplateBuilder(
+            layouts, cfg->repeatThreshold, cfg->maxSeedsPerRead, options->scatterRepeats != 0, cfg->gappedMismatchesMax,
+            cfg->avoidSmithWaterman, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore,
+            cfg->minGapExtendScore, cfg->semialignedGapLimit,
+            alignment::TemplateBuilder::DodgyAlignmentScore(options->dodgyAlignmentScore)));
+        ClusterHolder holder(maxReadLength);
+        std::vector<alignment::Match> matches;
+        SemialignedEndsClipper semialignedClipper;
+        OverlappingEndsClipper overlappingClipper;
+        std::vector<Stats> &mine = parts[t];
+        for (uint32_t c = b; c < e; ++c)
+        {
+            holder.load(reads, rml, c, !pf || pf[c]);
+            matches.clear();
+            for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
+                matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
+                                                   reference::ReferencePosition(batch->matches[m].location)));
+            alignment::BamTemplate &bam = builder->getBamTemplate();
+            TemplateAlignmentType type = Normal;
+            if (matches.empty() || matches.front().location.isNoMatch())                      // MatchSelector.cpp:302-313
+            {
+                bam.initialize(rml, holder.cluster);
+                type = !matches.empty() && matches.front().getSeedId().isNSeedId() ? Qc : NmNm;
+            }
+            else if (builder->buildFragments(contigs, rml, seeds, adapterList, matches.begin(), matches.end(), holder.cluster,
+                                             batch->withGaps != 0))
+            {
+                if (builder->buildTemplate(contigs, rog, rml, adapterList, holder.cluster, stats, options->mapqThreshold)) // :329-347
+                {
+                    if (options->clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED) { semialignedClipper.reset(); semialignedClipper.clip(contigs, bam); }
+                    if (options->clipFlags & ISAAC_EXT_CLIP_OVERLAPPING) { overlappingClipper.reset(); overlappingClipper.clip(contigs, bam); }
+                }
+            }
+            else
+            {
+                bam.initialize(rml, holder.cluster);
+                type = Rm;
+            }
+            // MatchSelectorStats::recordTemplate (MatchSelectorStats.hh:77-103)
+            BamTemplateTileStatsAdapter templateAdapter(stats, bam, type);
+            const unsigned r0 = bam.getFragmentMetadata(0).getReadIndex();
+            if (bam.getPassesFilter()) mine[r0 * 2 + 1].recordTemplate(templateAdapter);
+            mine[r0 * 2].recordTemplate(templateAdapter);
+            for (unsigned i = 0; bam.getFragmentCount() > i; ++i)
+            {
+                const alignment::FragmentMetadata &fragment = bam.getFragmentMetadata(i);
+                FragmentMetadataTileStatsAdapter fragmentAdapter(fragment);
+                if (bam.getPassesFilter()) mine[fragment.getReadIndex() * 2 + 1].recordFragment(fragmentAdapter, rml.at(i));
+                mine[fragment.getReadIndex() * 2].recordFragment(fragmentAdapter, rml.at(i));
+            }
+        }
+    });
+}
+
 extern "C" int oracle_template_stats(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
                                      const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
                                      const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t threads)
@@ -538,83 +616,48 @@ extern "C" int oracle_template_stats(const oracle_genome_t *genome, const isaac_
     using namespace alignment::matchSelector;
     try
     {
-        const std::vector<reference::Contig> &contigs = makeContigs(genome);
-        const flowcell::ReadMetadataList rml = makeReadMetadata(reads);
-        const flowcell::FlowcellLayoutList layouts(1, flowcell::Layout(rml));
-        const SequencingAdapterList &adapterList = currentAdapters();
-        alignment::SeedMetadataList seeds;
-        for (uint32_t s = 0; s < batch->seedCount; ++s)
-            seeds.push_back(alignment::SeedMetadata(batch->seeds[s].offset, batch->seeds[s].length, batch->seeds[s].readIndex, s));
-        const alignment::TemplateLengthStatistics stats(
-            tls->min, tls->max, tls->median, tls->lowStdDev, tls->highStdDev,
-            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[0]),
-            alignment::TemplateLengthStatistics::AlignmentModel(tls->bestModel[1]), tls->mateDriftRange);
-        const alignment::RestOfGenomeCorrection rog(contigs, rml);
-        const unsigned maxReadLength = std::max(reads->readLength[0], reads->readLength[1]);
-        const uint32_t n = reads->clusterCount;
         if (threads < 1) threads = 1;
-        if (n < 2 * threads) threads = 1;
+        if (reads->clusterCount < 2 * threads) threads = 1;
         std::vector<std::vector<TileBarcodeStats> > parts(threads, std::vector<TileBarcodeStats>(4));   // [readIndex * 2 + passesFilter]
         // TileBarcodeStats::reset() zeroes the eight real models but not alignmentModelCounts_[InvalidAlignmentModel]
         // (TileBarcodeStats.hh:62-69): the reference counts the pairs without a model on top of uninitialised memory
         for (std::vector<TileBarcodeStats> &p : parts)
             for (TileBarcodeStats &s : p) s.alignmentModelCounts_[alignment::TemplateLengthStatistics::InvalidAlignmentModel] = 0;
-        parallelFor(n, threads, [&](uint32_t t, uint32_t b, uint32_t e) {
-            std::unique_ptr<alignment::TemplateBuilder> builder(new alignment::TemplateBuilder(
-                layouts, cfg->repeatThreshold, cfg->maxSeedsPerRead, options->scatterRepeats != 0, cfg->gappedMismatchesMax,
-                cfg->avoidSmithWaterman, cfg->gapMatchScore, cfg->gapMismatchScore, cfg->gapOpenScore, cfg->gapExtendScore,
-                cfg->minGapExtendScore, cfg->semialignedGapLimit,
-                alignment::TemplateBuilder::DodgyAlignmentScore(options->dodgyAlignmentScore)));
-            ClusterHolder holder(maxReadLength);
-            std::vector<alignment::Match> matches;
-            SemialignedEndsClipper semialignedClipper;
-            OverlappingEndsClipper overlappingClipper;
-            std::vector<TileBarcodeStats> &mine = parts[t];
-            for (uint32_t c = b; c < e; ++c)
-            {
-                holder.load(reads, rml, c, !pf || pf[c]);
-                matches.clear();
-                for (uint64_t m = batch->clusterMatchBegin[c]; m < batch->clusterMatchBegin[c + 1]; ++m)
-                    matches.push_back(alignment::Match(alignment::SeedId(batch->matches[m].seedId),
-                                                       reference::ReferencePosition(batch->matches[m].location)));
-                alignment::BamTemplate &bam = builder->getBamTemplate();
-                TemplateAlignmentType type = Normal;
-                if (matches.empty() || matches.front().location.isNoMatch())                      // MatchSelector.cpp:302-313
-                {
-                    bam.initialize(rml, holder.cluster);
-                    type = !matches.empty() && matches.front().getSeedId().isNSeedId() ? Qc : NmNm;
-                }
-                else if (builder->buildFragments(contigs, rml, seeds, adapterList, matches.begin(), matches.end(), holder.cluster,
-                                                 batch->withGaps != 0))
-                {
-                    if (builder->buildTemplate(contigs, rog, rml, adapterList, holder.cluster, stats, options->mapqThreshold)) // :329-347
-                    {
-                        if (options->clipFlags & ISAAC_EXT_CLIP_SEMIALIGNED) { semialignedClipper.reset(); semialignedClipper.clip(contigs, bam); }
-                        if (options->clipFlags & ISAAC_EXT_CLIP_OVERLAPPING) { overlappingClipper.reset(); overlappingClipper.clip(contigs, bam); }
-                    }
-                }
-                else
-                {
-                    bam.initialize(rml, holder.cluster);
-                    type = Rm;
-                }
-                // MatchSelectorStats::recordTemplate (MatchSelectorStats.hh:77-103)
-                BamTemplateTileStatsAdapter templateAdapter(stats, bam, type);
-                const unsigned r0 = bam.getFragmentMetadata(0).getReadIndex();
-                if (bam.getPassesFilter()) mine[r0 * 2 + 1].recordTemplate(templateAdapter);
-                mine[r0 * 2].recordTemplate(templateAdapter);
-                for (unsigned i = 0; bam.getFragmentCount() > i; ++i)
-                {
-                    const alignment::FragmentMetadata &fragment = bam.getFragmentMetadata(i);
-                    FragmentMetadataTileStatsAdapter fragmentAdapter(fragment);
-                    if (bam.getPassesFilter()) mine[fragment.getReadIndex() * 2 + 1].recordFragment(fragmentAdapter, rml.at(i));
-                    mine[fragment.getReadIndex() * 2].recordFragment(fragmentAdapter, rml.at(i));
-                }
-            }
-        });
+        recordTileTemplates(genome, reads, cfg, batch, tls, options, pf, parts, threads);
         std::memset(statsOut, 0, 4 * ISAAC_EXT_TEMPLATE_STATS_COUNTERS * sizeof(uint64_t));
         for (const std::vector<TileBarcodeStats> &p : parts)
             for (unsigned k = 0; k < 4; ++k) flattenStats(p[k], statsOut + k * ISAAC_EXT_TEMPLATE_STATS_COUNTERS);
+    }
+    catch (const std::exception &e)
+    {
+        return ISAAC_EXT_E_INVALID_ARG;
+    }
+    return ISAAC_EXT_OK;
+}
+
+/* The TileStats of MatchSelectorStats (TileStats.hh:68-142) for one tile: the same walk, recorded into the reference's own TileStats.
+ * statsOut: 4 blocks of ISAAC_EXT_TILE_CYCLE_STATS_WORDS u64 in the member order of the struct (= its memory layout), summed over
+ * the threads with TileStats::operator+=; finalize != 0 applies TileStats::finalize to every block. */
+extern "C" int oracle_tile_cycle_stats(const oracle_genome_t *genome, const isaac_ext_reads_t *reads, const isaac_ext_config_t *cfg,
+                                       const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                       const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t finalize,
+                                       uint32_t threads)
+{
+    using namespace alignment::matchSelector;
+    static_assert(sizeof(TileStats) == ISAAC_EXT_TILE_CYCLE_STATS_WORDS * sizeof(uint64_t), "TileStats is a plain block of 64-bit counters");
+    try
+    {
+        if (threads < 1) threads = 1;
+        if (reads->clusterCount < 2 * threads) threads = 1;
+        std::vector<std::vector<TileStats> > parts(threads, std::vector<TileStats>(4));
+        recordTileTemplates(genome, reads, cfg, batch, tls, options, pf, parts, threads);
+        for (unsigned k = 0; k < 4; ++k)
+        {
+            TileStats sum;
+            for (const std::vector<TileStats> &p : parts) sum += p[k];
+            if (finalize) sum.finalize();
+            std::memcpy(statsOut + size_t(k) * ISAAC_EXT_TILE_CYCLE_STATS_WORDS, &sum, sizeof(sum));
+        }
     }
     catch (const std::exception &e)
     {

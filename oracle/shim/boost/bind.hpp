@@ -35,3 +35,8 @@ template <class L, class V> struct AtLeastValue { L l; V v; template <class... A
 }
 template <class L, class V, class = typename std::enable_if<std::is_bind_expression<L>::value && std::is_arithmetic<V>::value>::type>
 boost_shim::AtLeastValue<L, V> operator>=(L l, V v) { return boost_shim::AtLeastValue<L, V>{l, v}; }
+// boost::bind evaluates a nested "bind == value" with the outer call's arguments (TileStats.hh:118-121: plus(_2, bind(cref, _1) == 'n'));
+// std::bind does that for the types it knows as bind expressions
+namespace std {
+template <class L, class V> struct is_bind_expression<boost_shim::EqualsValue<L, V> > : true_type {};
+}

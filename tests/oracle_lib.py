@@ -178,6 +178,27 @@ def template_stats(oracle, genome, reads, config, match_batch, tls, options, pf=
     return out
 
 
+TILE_CYCLE_STATS_WORDS = 47105
+TILE_CYCLE_STATS_FIELDS = [("alignmentScoreFragments", 8192), ("alignmentScoreMismatches", 8192), ("alignmentScoreTemplates", 8192),
+                           ("alignmentScoreTemplateMismatches", 8192), ("cycleBlanks", 1024), ("cycleUniquelyAlignedBlanks", 1024),
+                           ("cycleMismatches", 1024), ("cycleUniquelyAlignedMismatches", 1024)] + \
+                          [("cycleUniquelyAligned%sMismatchFragments" % k, 1024) for k in ("1", "2", "3", "4", "More")] + \
+                          [("cycle%sMismatchFragments" % k, 1024) for k in ("1", "2", "3", "4", "More")] + [("uniquelyAlignedFragmentCount", 1)]
+
+
+def tile_cycle_stats(oracle, genome, reads, config, match_batch, tls, options, pf=None, finalize=False, threads=1):
+    """matchSelector::TileStats of the tile's templates through the reference's own class (reference build only) -> uint64 [4, 47105]"""
+    pf_arr = None if pf is None else np.ascontiguousarray(pf, dtype=np.uint8)
+    out = np.zeros((4, TILE_CYCLE_STATS_WORDS), dtype=np.uint64)
+    rc = oracle.lib.oracle_tile_cycle_stats(
+        ctypes.byref(genome.c), ctypes.byref(reads.c), ctypes.byref(config), ctypes.byref(match_batch.c), ctypes.byref(tls),
+        ctypes.byref(options), ctypes.c_void_p(pf_arr.ctypes.data) if pf_arr is not None else None,
+        ctypes.c_void_p(out.ctypes.data), ctypes.c_uint32(1 if finalize else 0), ctypes.c_uint32(threads))
+    if rc:
+        raise RuntimeError("oracle_tile_cycle_stats failed: %d" % rc)
+    return out
+
+
 def determine_template_length(oracle, genome, reads, config, match_batch, pf=None, mate_drift_range=-1):
     """MatchSelector::determineTemplateLength for the tile (reference build only) -> (batch.Tls, stable)"""
     from isaac_aligner_b200.batch import Tls

@@ -50,7 +50,7 @@ def test_select_tile_matches_the_reference_steps(tmp_path, user_tls):
     ctx = capi.Context(cfg)
     ctx.set_reference(genome)
     got = tile.select_tile(ctx, tile.read_bcl_clusters(os.path.join(str(tmp_path), "clusters.bcl"), (L, L)), (L, L),
-                           tile.read_match_file(path), mb.seeds, pf=pf, base_quality_cutoff=cutoff, tls=tls_in, options=options)
+                           tile.read_match_file(path), mb.seeds, pf=pf, base_quality_cutoff=cutoff, tls=tls_in, options=options, cycle_stats=True)
     ctx.close()
     # the same steps through the reference's own code
     g = oracle_lib.GenomeHolder(genome)
@@ -66,3 +66,4 @@ def test_select_tile_matches_the_reference_steps(tmp_path, user_tls):
         assert np.array_equal(got.templates.fragments[name], want.fragments[name]), name
     assert np.array_equal(got.stats, oracle_lib.template_stats(chk, g, trimmed, cfg, mb, want_tls, options, pf, threads=8))
     assert got.stats[0][3] == n and 0 < got.stats[1][3] < n
+    assert np.array_equal(got.cycle_stats, oracle_lib.tile_cycle_stats(chk, g, trimmed, cfg, mb, want_tls, options, pf, threads=8))
