@@ -570,8 +570,10 @@ def run_b200(args):
                                     "16x2 max %.1f TOP/s" % (peak_add / 1e12, peak_max / 1e12, peak_dpx / 1e12)},
         "roofline_ungapped": {"bound": "hbm", "kernel": "ungappedKernel", "achieved": ungapped_gbs, "peak": hbm_peak,
                               "unit": "GB/s", "frac": ungapped_gbs / hbm_peak, "traffic": traffic_ungapped, "ms_per_launch": ms_ungapped,
-                              "limited_by": "integer pipe (ncu: ALU 66 %, issue 61 %; profiles/r1_u_ncu_ungappedKernel.txt): the ordered "
-                                            "FP64 sum and the longest-run counter cost about 290 instructions per 16 bases",
+                              "limited_by": "the L1 data pipe and the issue slots, not HBM (ncu, profiles/r2_n_ncu_ungappedKernel.txt: LSU wavefronts 74 % of "
+                                            "peak, issue 66 %, DRAM 1.4 GB per 10 M candidates = the algorithmic bytes): the reference's ordered FP64 sum is one "
+                                            "8-byte shared-memory table lookup + one DADD per base (2 wavefronts each, 16 per 16 bases) and cannot be reassociated; "
+                                            "230 instructions per 16 bases, 64 of them that chain",
                               "peak_source": hbm_src, "candidates_per_s": n / (ms_ungapped * 1e-3)},
         "cpu_baseline": {"value": cpu_gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
                          "sample": "first %d of the %d candidates of rank 0, one pass, %d host threads, %.2f s"

@@ -163,8 +163,8 @@ __global__ void ungappedKernel(const ReferenceView ref, const ReadSetView reads,
             if (begin) ops[nOps++] = cigarWord(uint32_t(begin), ISAAC_EXT_CIGAR_SOFT_CLIP);            // :64-68
             if (end - begin) ops[nOps++] = cigarWord(uint32_t(end - begin), ISAAC_EXT_CIGAR_ALIGN);    // :70-75
             if (long(L) - end) ops[nOps++] = cigarWord(uint32_t(L - end), ISAAC_EXT_CIGAR_SOFT_CLIP);  // :77-81
-            const unsigned matchCount = scoreCigar(ref, reads, sp, c.readId, L, f.reverse, ref.contigOffset[contigId],
-                                                   f.position, ops, nOps, o, mask);
+            const unsigned matchCount = scoreUngapped(ref, reads, sp, c.readId, L, f.reverse, ref.contigOffset[contigId],
+                                                      f.position, unsigned(begin), unsigned(end), o, mask);
             for (unsigned k = 0; k < 3; ++k) cigar[k] = k < nOps ? ops[k] : 0u;
             o.cigarLength = matchCount ? uint16_t(nOps) : 0;                                           // setUnaligned (:86-89)
         }

@@ -289,6 +289,129 @@ struct CigarScorer
     }
 };
 
+/// updateFragmentCigar for the CIGAR of an UNGAPPED alignment, [begin S] [end - begin M] [L - end S] (UngappedAligner.cpp:64-81):
+/// the same result as scoreCigar on those three operations, without walking operations.  Per 16-base word: one XOR of the read's
+/// 2-bit codes against the reference window (its words are fetched once, the window runs on contiguously), the masks of the word,
+/// popcounts; a word whose aligned bases all match takes a short cut through the counters.  What stays per base is the
+/// reference's left-to-right FP64 sum.  \return matchCount
+__device__ __forceinline__ unsigned scoreUngapped(const ReferenceView &ref, const ReadSetView &reads, const ScoreParams &sp,
+                                                  const unsigned readId, const unsigned L, const bool reverse, const uint64_t contigOffset,
+                                                  const long strandPosition, const unsigned begin, const unsigned end,
+                                                  isaac_ext_fragment_t &out, uint64_t *mask)
+{
+    const uint64_t *strandWords = reads.strandWords2(readId, reverse);
+    const uint8_t *quality = reads.strandQuality(readId, reverse);
+    const uint32_t tableShared = uint32_t(__cvta_generic_to_shared(sp.logMatch));
+    // reference index of strand position 0 if the alignment ran on to the left of 'begin' (may lie in front of the packed array
+    // for a read clipped at the start of the first contig: such positions are never looked at)
+    const long r0 = long(contigOffset) + strandPosition - long(begin);
+    double lp = 0.0;
+    unsigned matchCount = 0, mismatchCount = 0, editDistance = 0, matchesInARow = 0, run = 0;
+    for (unsigned w = 0; w * 16u < L; ++w)
+    {
+        const unsigned P0 = w * 16u;
+        const unsigned cnt = min(16u, L - P0);
+        const uint64_t sword = strandWords[w];
+        const uint32_t valid = (1u << cnt) - 1u;
+        // the aligned bases of the word: [max(begin, P0), min(end, P0 + 16)) - P0
+        const unsigned lo = begin > P0 ? min(begin - P0, 16u) : 0u, hi = end > P0 ? min(end - P0, 16u) : 0u;
+        const uint32_t aligned = hi > lo ? (((1u << (hi - lo)) - 1u) << lo) : 0u;
+        uint32_t mism16 = 0;
+        if (aligned)
+        {
+            const uint32_t read2 = uint32_t(sword), readN = uint32_t(sword >> 32) & 0xFFFFu;
+            const long rw = r0 + long(P0);                                   // reference index under bit 0 of the word
+            uint32_t d2, dN;
+            if (rw >= 0)
+            {
+                const uint32_t *b2 = ref.bases2 + (rw >> 4);
+                d2 = __funnelshift_r(__ldg(b2), __ldg(b2 + 1), (unsigned(rw) & 15u) * 2u);
+                const uint32_t *bn = ref.nmask + (rw >> 5);
+                dN = __funnelshift_r(__ldg(bn), __ldg(bn + 1), unsigned(rw) & 31u);
+            }
+            else
+            {
+                const unsigned back = unsigned(-rw);                         // < 16: the word holds 'begin'
+                d2 = __ldg(ref.bases2) << (2u * back);
+                dN = __ldg(ref.nmask) << back;
+            }
+            const uint32_t x = read2 ^ d2;
+            uint32_t neq = (x | (x >> 1)) & 0x55555555u;                     // even bits -> 16 dense bits
+            neq = (neq | (neq >> 1)) & 0x33333333u;
+            neq = (neq | (neq >> 2)) & 0x0F0F0F0Fu;
+            neq = (neq | (neq >> 4)) & 0x00FF00FFu;
+            neq = (neq | (neq >> 8)) & 0x0000FFFFu;
+            const uint32_t differ = aligned & (neq | (dN & 0xFFFFu) | readN); // the bytes differ (:176-179): 'n' and 'N' differ from everything
+            mism16 = differ & ~readN;                                        // !isMatch (Alignment.hh:44-47): 'n' in the read matches anything
+            const uint32_t match16 = aligned & ~mism16;
+            editDistance += __popc(differ);
+            mismatchCount += __popc(mism16);
+            matchCount += __popc(match16);
+            if (mask && mism16) mask[P0 >> 6] |= uint64_t(mism16) << (P0 & 63u);   // addMismatchCycle (:171), as a bit over base index
+            // longest run of matches (:158-170): the ALIGN operation starts a new run at 'begin'
+            if (begin >= P0 && begin < P0 + 16u) run = 0;
+            if (!mism16)
+            {
+                run += hi - lo;
+                matchesInARow = max(matchesInARow, run);
+            }
+            else
+            {
+                const uint32_t m = match16 >> lo;                            // the aligned piece, bits [0, len)
+                const unsigned len = hi - lo;
+                const unsigned lead = __ffs(~m) - 1u;                        // ones at the bottom; < len here
+                matchesInARow = max(matchesInARow, run + lead);
+                const uint32_t p2 = m & (m >> 1), p4 = p2 & (p2 >> 2), p8 = p4 & (p4 >> 4);
+                uint32_t cur = ~0u, t; unsigned n = 0;
+                t = cur & p8;        if (t) { cur = t; n = 8; }
+                t = cur & (p4 >> n); if (t) { cur = t; n += 4; }
+                t = cur & (p2 >> n); if (t) { cur = t; n += 2; }
+                t = cur & (m >> n);  if (t) { n += 1; }
+                matchesInARow = max(matchesInARow, n);
+                run = __clz(~(m << (32u - len)));                           // ones at the top of the piece
+            }
+        }
+        // ---- the sequential part: the FP64 sum, one table lookup + one DADD per base in read order (soft-clipped bases add
+        // logMatch, :199-213).  Table index bytes: quality, + 100 for a mismatch, 200 (the +0.0 entry) past the end of the read.
+        const uint4 qv = *reinterpret_cast<const uint4 *>(quality + P0);
+        unsigned qw[4] = {qv.x, qv.y, qv.z, qv.w};
+        if (cnt < 16u)
+        {
+            const uint32_t zero16 = 0xFFFFu & ~valid;
+#pragma unroll
+            for (unsigned k = 0; k < 4; ++k)
+            {
+                const uint32_t bytes = ((((zero16 >> (4u * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+                qw[k] = (qw[k] & ~bytes) | (bytes & 0xC8C8C8C8u);
+            }
+        }
+        if (mism16)
+        {
+#pragma unroll
+            for (unsigned k = 0; k < 4; ++k)
+                qw[k] += ((((mism16 >> (4u * k)) & 0xFu) * 0x00204081u) & 0x01010101u) * 100u;
+        }
+#pragma unroll
+        for (unsigned b = 0; b < 16; ++b)
+        {
+            const unsigned idx = __byte_perm(qw[b >> 2], 0u, 0x4440u + (b & 3u));
+            double v;
+            asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(tableShared + idx * 8u));
+            lp += v;
+        }
+    }
+    out.position = strandPosition;
+    out.observedLength = end - begin;
+    out.logProbability = lp;
+    out.mismatchCount = uint16_t(mismatchCount);
+    out.matchesInARow = uint16_t(matchesInARow);
+    out.gapCount = 0;
+    out.editDistance = uint16_t(editDistance);
+    out.smithWatermanScore = mismatchCount * sp.mismatch;                                        // :173
+    out.matchCount = uint16_t(matchCount);
+    return matchCount;
+}
+
 /// updateFragmentCigar of one fragment.  \return matchCount
 __device__ __forceinline__ unsigned scoreCigar(const ReferenceView &ref, const ReadSetView &reads, const ScoreParams &sp,
                                                const unsigned readId, const unsigned L, const bool reverse,
