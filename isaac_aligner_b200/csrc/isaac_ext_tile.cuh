@@ -425,7 +425,7 @@ int rescueDeviceCore(isaac_ext_ctx *ctx, const uint32_t n, RescueTotals &totals)
     totals.fragments = ps.hTotals.p[1]; totals.words = ps.hTotals.p[2];
     timer.mark("K2 gapped + R3 accept");
     CK(ps.dOutFragments.reserve(size_t(totals.fragments) + 1)); CK(ps.dOutCigars.reserve(size_t(totals.words) + 1));
-    shadowFlattenKernel<<<gridFor(ctx, uint64_t(n) * 32, 128, 16), 128, 0, ctx->stream>>>(
+    shadowFlattenKernel<<<gridFor(ctx, n, 128, 16), 128, 0, ctx->stream>>>(
         n, ps.dTaskBegin.p, listCounts, fragmentBegin, wordBegin, ps.dKept.p, ps.dAdoptedBy.p, ps.dFrag.p, ps.dCig.p, ps.dFrag3.p, ps.dCig3.p,
         TILE_GAPPED_STRIDE, ps.dOutFragments.p, ps.dOutCigars.p, ps.dOutBegin.p, totals.fragments);
     ++ctx->launches;

@@ -7,7 +7,7 @@
 //   shadowGapKernel      writes those gapped candidates, in list order, at the request's place of the gapped batch
 //   shadowAcceptKernel   after the gapped pass: the acceptance rule, the new best, best first (:255-288); final size of the list
 //                        and of its CIGARs
-//   shadowFlattenKernel  one warp per request: the final records and their CIGAR words to the flat result arrays
+//   shadowFlattenKernel  one thread per request: the final records and their CIGAR words to the flat result arrays
 //
 // Prefix sums between them (cub::DeviceScan) give every request its place in the gapped batch and in the result.
 #pragma once
@@ -133,9 +133,9 @@ __global__ void shadowAcceptKernel(uint32_t requests, const uint32_t *__restrict
     }
 }
 
-/// One warp per request: its final list to fragmentsOut[fragmentBegin[i] ..] with the CIGAR words behind each other from
-/// wordBegin[i] on (fragment.cigarOffset indexes cigarsOut).  An adopted entry takes the alignment of its gapped record; the
-/// seed bookkeeping of a rescued shadow is the same in both records.
+/// One thread per request (a list has one to three entries, rarely more): its final list to fragmentsOut[fragmentBegin[i] ..] with
+/// the CIGAR words behind each other from wordBegin[i] on (fragment.cigarOffset indexes cigarsOut).  An adopted entry takes the
+/// alignment of its gapped record; the seed bookkeeping of a rescued shadow is the same in both records.
 __global__ void shadowFlattenKernel(uint32_t requests, const uint32_t *__restrict__ taskBegin, const uint32_t *__restrict__ counts,
                                     const uint32_t *__restrict__ fragmentBegin, const uint32_t *__restrict__ wordBegin,
                                     const uint32_t *__restrict__ kept, const uint32_t *__restrict__ adoptedBy,
@@ -144,34 +144,21 @@ __global__ void shadowFlattenKernel(uint32_t requests, const uint32_t *__restric
                                     uint32_t gappedStride, isaac_ext_fragment_t *__restrict__ fragmentsOut, uint32_t *__restrict__ cigarsOut,
                                     uint64_t *__restrict__ fragmentBeginOut, const uint32_t fragmentTotal)
 {
-    const uint32_t lane = threadIdx.x & 31u, warpsPerGrid = gridDim.x * (blockDim.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0) fragmentBeginOut[requests] = fragmentTotal;
-    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < requests; i += warpsPerGrid)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < requests; i += gridDim.x * blockDim.x)
     {
         const uint32_t begin = taskBegin[i], size = counts[i], fb = fragmentBegin[i];
-        if (lane == 0) fragmentBeginOut[i] = fb;
-        uint32_t wordsBefore = wordBegin[i];
-        for (uint32_t j0 = 0; j0 < size; j0 += 32)
+        fragmentBeginOut[i] = fb;
+        uint32_t offset = wordBegin[i];
+        for (uint32_t j = 0; j < size; ++j)
         {
-            const uint32_t j = j0 + lane;
-            uint32_t length = 0, adopted = 0, source = 0;
-            if (j < size)
-            {
-                adopted = adoptedBy[begin + j]; source = kept[begin + j];
-                length = adopted ? gapped[adopted - 1].cigarLength : ungapped[source].cigarLength;
-            }
-            uint32_t incl = length;                                  // CIGAR offset of every entry: prefix sum over the 32 entries
-            for (unsigned d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
-            const uint32_t offset = wordsBefore + incl - length;
-            if (j < size)
-            {
-                isaac_ext_fragment_t f = adopted ? gapped[adopted - 1] : ungapped[source];
-                const uint32_t *src = adopted ? gappedCigars + size_t(adopted - 1) * gappedStride : ungappedCigars + size_t(source) * 3;
-                for (uint32_t k = 0; k < length; ++k) cigarsOut[offset + k] = src[k];
-                f.cigarOffset = offset;
-                fragmentsOut[fb + j] = f;
-            }
-            wordsBefore += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t adopted = adoptedBy[begin + j], source = kept[begin + j];
+            isaac_ext_fragment_t f = adopted ? gapped[adopted - 1] : ungapped[source];
+            const uint32_t *src = adopted ? gappedCigars + size_t(adopted - 1) * gappedStride : ungappedCigars + size_t(source) * 3;
+            for (uint32_t k = 0; k < f.cigarLength; ++k) cigarsOut[offset + k] = src[k];
+            f.cigarOffset = offset;
+            offset += f.cigarLength;
+            fragmentsOut[fb + j] = f;
         }
     }
 }

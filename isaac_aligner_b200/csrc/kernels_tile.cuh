@@ -37,6 +37,9 @@ constexpr uint32_t TILE_NO_CANDIDATE = 0xFFFFFFFFu;       // readId of a match s
 constexpr unsigned TILE_MAX_SEEDS = 64;                   // seeds of a cluster (both reads); the reference's default is 4 per read
 constexpr uint32_t TILE_ERROR_MATCHES = 8u;               // errorFlag bit: malformed match batch
 constexpr uint32_t TILE_GAPPED_STRIDE = 32;
+#ifndef FINISH_MIN_BLOCKS
+#define FINISH_MIN_BLOCKS 8
+#endif
 
 struct TileView
 {
@@ -387,7 +390,7 @@ __global__ void shadowWindowsKernel(const uint32_t n, const isaac_ext_rescue_req
 /// finish: the BamTemplate of every cluster (finish_device.cuh).  The scratch slice of cluster c starts where the slices of the
 /// clusters before it end; finishScratchBytes is linear in (shadows, candidates), so that place follows from the rescue pass's and
 /// the match batch's own offsets without another prefix sum.
-__global__ void finishTemplatesKernel(const FinishView v, const uint32_t clusters, const uint64_t *__restrict__ clusterMatchBegin,
+__global__ void __launch_bounds__(128, FINISH_MIN_BLOCKS) finishTemplatesKernel(const FinishView v, const uint32_t clusters, const uint64_t *__restrict__ clusterMatchBegin,
                                       unsigned char *__restrict__ scratch, isaac_ext_template_t *__restrict__ templates,
                                       isaac_ext_fragment_t *__restrict__ fragments, uint32_t *__restrict__ cigarLengths,
                                       FinishSource *__restrict__ sources)

@@ -14,20 +14,20 @@ from isaac_aligner_b200.types import CANDIDATE_DTYPE, FRAGMENT_DTYPE, Config, Re
 
 pytestmark = pytest.mark.gpu
 
-N = 10_000_000
-L = 150
 STRIDE = 32
+SIZES = [(10_000_000, 150), (4_000_000, 250)]        # BASELINE configs[1]; the read length of configs[4] at a size that keeps the suite short
 
 
 def checkers():
     return oracle_lib.gpu_checkers()        # fails when the reference build did not travel
 
 
-@pytest.fixture(scope="module")
-def full():
+@pytest.fixture(scope="module", params=SIZES, ids=["10M_x_150bp", "4M_x_250bp"])
+def full(request):
     """the workload of bench.py (same generator, same seeds) and the results of one full-size pass"""
     import torch
     from isaac_aligner_b200 import capi
+    N, L = request.param
     genome = synth.make_genome(5_000_000, n_contigs=1, seed=synth.SEED_G5)
     sim = synth.simulate_pairs(genome, -(-N // 16), L=L, seed=synth.SEED_READS + 1)
     reads = ReadSet(sim.bcl, (L, L))
@@ -51,7 +51,7 @@ def full():
         torch.cuda.synchronize()
         return frag, cig
 
-    state = {"ctx": ctx, "genome": genome, "reads": reads, "cand": cand, "run": run, "torch": torch, "dev": dev}
+    state = {"ctx": ctx, "genome": genome, "reads": reads, "cand": cand, "run": run, "torch": torch, "dev": dev, "N": N, "L": L}
     state["ungapped"] = run(False)
     state["gapped"] = run(True)
     yield state
@@ -74,6 +74,7 @@ def cigar_lengths(cig, lengths):
 
 @pytest.mark.parametrize("which", ["ungapped", "gapped"])
 def test_every_record_is_well_formed(full, which):
+    N, L = full["N"], full["L"]
     f, c = host(*full[which])
     aligned = f["cigarLength"] > 0
     assert aligned.mean() > 0.7
@@ -94,7 +95,8 @@ def test_every_record_is_well_formed(full, which):
 
 
 def test_sampled_parity_with_the_cpu_checkers(full):
-    """30 000 random candidates of the 10 M: the full-size results equal the oracle's, bit for bit"""
+    """30 000 random candidates of the batch: the full-size results equal the oracle's, bit for bit"""
+    N = full["N"]
     fu, cu = host(*full["ungapped"])
     fg, cg = host(*full["gapped"])
     rng = np.random.default_rng(2024)
@@ -115,8 +117,9 @@ def test_sampled_parity_with_the_cpu_checkers(full):
 def test_sub_batches_equal_the_full_batch(full):
     """slices that start and end off the chunk / pair boundaries of the split kernels give the same records"""
     chunk = 2 * 148 * 4 * 128 * 2
+    N = full["N"]
     fg, cg = host(*full["gapped"])
-    for first, count in [(0, chunk - 1), (1, chunk), (chunk - 3, 2 * chunk + 5), (N - 777, 777), (5_000_001, 1)]:
+    for first, count in [(0, chunk - 1), (1, chunk), (chunk - 3, 2 * chunk + 5), (N - 777, 777), (N // 2 + 1, 1)]:
         f, c = host(*full["run"](True, first, count))
         ref = fg[first:first + count].copy()
         ref["cigarOffset"] -= first * STRIDE
@@ -132,7 +135,7 @@ def test_idempotent(full):
 
 def test_tile_statistics_are_linear(full):
     """K6 counters of the whole batch = sum over four tiles = the same sums taken on the host"""
-    torch, ctx = full["torch"], full["ctx"]
+    torch, ctx, N = full["torch"], full["ctx"], full["N"]
     frag = full["gapped"][0]
     stream = torch.cuda.current_stream().cuda_stream
     whole = torch.zeros(64, dtype=torch.int64, device=full["dev"])
