@@ -1,8 +1,8 @@
-// FragmentBuilder::consolidateDuplicateFragments (FragmentBuilder.cpp:279-324) for host AND device code: the same function as
-// consolidateDuplicateFragments of host_pipeline.cuh with the library's std::sort replaced by its replay (sort_replay.cuh), so
+// FragmentBuilder::consolidateDuplicateFragments (FragmentBuilder.cpp:279-324) for host AND device code: the reference's loop
+// with the library's std::sort replaced by its replay (sort_replay.cuh), so
 // that the entry that survives a group of duplicates -- and with it firstSeedIndex and the seed bookkeeping -- is the one the
 // reference keeps.  tests/cpp/test_consolidate_replay.cu checks on the CPU that both give the same lists, byte for
-// byte.  NOT YET USED by the product path (building block of the device-side build_fragments).
+// byte.  Used by the B1-B4 kernels of kernels_tile.cuh.
 #pragma once
 #include "sort_replay.cuh"
 #include "../../include/isaac_ext.h"

@@ -1,15 +1,8 @@
-// Host side of the two TemplateBuilder-facing calls: the per-cluster bookkeeping of FragmentBuilder::build and
-// ShadowAligner::rescueShadow (candidate lists, std::sort + consolidate, pairing, acceptance rules) between the kernel
-// passes.  Everything here is integer bookkeeping on fragment records; every base comparison, score, k-mer scan and
-// Smith-Waterman cell is computed by the kernels (kernels*.cuh).  The reference keeps this logic per cluster and per
-// thread (MatchSelector.cpp:258-368); here a tile is processed phase by phase:
-//
-//   build:   P1 candidates (addMatch, repeat filter, consolidate)      -> K1 ungappedKernel
-//            P2 consolidate, pair adjacent candidates                   -> simpleIndelKernel
-//            P3 apply patches, consolidate, pick mismatchCount > 5      -> swForwardKernel + swTraceScoreKernel
-//            P4 acceptance rule, consolidate, flatten
-//   rescue:  R1 rescue windows from the template length statistics      -> shadowCandidates*Kernel, K1 ungappedKernel
-//            (everything behind R1 is on the device: the list bookkeeping R2 / R3 and the flat result are kernels_rescue.cuh)
+// Small host-side helpers of the tile calls (page-locked buffers, phase timing, a fixed-partition parallel loop) and the record
+// helpers the kernels of kernels_tile.cuh share with them: the work record of a candidate, the reference's packed Match fields,
+// the 1e-7-tolerant comparisons, the adoption of a kernel's result into a work record, the 5-clause acceptance rule.
+// (Round 1 ran the bookkeeping of FragmentBuilder::build between the kernel passes on host threads from here; it is all kernels
+// now, see kernels_tile.cuh.)
 #pragma once
 #include <algorithm>
 #include <atomic>
@@ -73,72 +66,12 @@ inline unsigned partitionCount(unsigned threads, size_t n) { return unsigned(std
 struct WorkFragment
 {
     isaac_ext_fragment_t f;
-    uint32_t pool;            // index into HostPools::pools
+    uint32_t pool;            // 0 ungapped, 1 simple indel, 2 gapped: the pass whose CIGAR pool holds the record's words
     uint32_t slot;            // dense index of the record in the kernel pass that last scored it
-};
-
-struct HostPools
-{
-    const uint32_t *pools[4] = {nullptr, nullptr, nullptr, nullptr};      // 0 ungapped, 1 simple indel, 2 gapped
-    const uint32_t *cigar(const WorkFragment &w) const { return pools[w.pool] + w.f.cigarOffset; }
-    long beginClipped(const WorkFragment &w) const                        // FragmentMetadata::getBeginClippedLength (:148-159)
-    {
-        if (!w.f.cigarLength) return 0;
-        const uint32_t word = cigar(w)[0];
-        return (word & 0xFu) == ISAAC_EXT_CIGAR_SOFT_CLIP ? long(word >> 4) : 0;
-    }
-    long endClipped(const WorkFragment &w) const                          // getEndClippedLength (:161-172)
-    {
-        if (!w.f.cigarLength) return 0;
-        const uint32_t word = cigar(w)[w.f.cigarLength - 1];
-        return (word & 0xFu) == ISAAC_EXT_CIGAR_SOFT_CLIP ? long(word >> 4) : 0;
-    }
-    long unclippedPosition(const WorkFragment &w) const { return long(w.f.position) - beginClipped(w); }   // :185-188
 };
 
 __host__ __device__ inline bool lpEquals(double a, double b) { const double d = a - b; return 0.0000001 >= (d < 0 ? -d : d); }      // ISAAC_LP_EQUALS, Quality.hh:104-107
 __host__ __device__ inline bool lpLess(double a, double b) { return !lpEquals(a, b) && a < b; }             // ISAAC_LP_LESS,   Quality.hh:109-112
-
-/// FragmentMetadata::operator< (FragmentMetadata.hh:419-429)
-inline bool fragmentLess(const WorkFragment &a, const WorkFragment &b)
-{
-    return a.f.contigId < b.f.contigId ||
-           (a.f.contigId == b.f.contigId &&
-            (a.f.position < b.f.position ||
-             (a.f.position == b.f.position &&
-              (a.f.reverse < b.f.reverse || (a.f.reverse == b.f.reverse && a.f.observedLength < b.f.observedLength)))));
-}
-
-/// FragmentBuilder::consolidateDuplicateFragments (FragmentBuilder.cpp:279-324) on list[0..n); returns the new size.
-/// std::sort is the same libstdc++ introsort the reference runs, on the same comparator and input order, so the entry
-/// (and its firstSeedIndex) that survives a group of duplicates is the same one.
-inline unsigned consolidateDuplicateFragments(WorkFragment *list, unsigned n, bool removeUnaligned)
-{
-    std::sort(list, list + n, fragmentLess);
-    unsigned first = 0;
-    while (first != n && removeUnaligned && !list[first].f.cigarLength) ++first;
-    if (first) { std::copy(list + first, list + n, list); n -= first; }
-    if (n < 2) return n;
-    unsigned last = 0;
-    for (unsigned cur = 1; cur != n; ++cur)
-    {
-        if (removeUnaligned && !list[cur].f.cigarLength) continue;
-        isaac_ext_fragment_t &l = list[last].f;
-        const isaac_ext_fragment_t &c = list[cur].f;
-        if (l.position == c.position && l.contigId == c.contigId && l.reverse == c.reverse && l.observedLength == c.observedLength)
-        {
-            l.uniqueSeedCount = uint16_t(l.uniqueSeedCount + c.uniqueSeedCount);        // FragmentMetadata::consolidate (:470-475)
-            l.nonUniqueSeedOffsetFirst = std::min(l.nonUniqueSeedOffsetFirst, c.nonUniqueSeedOffsetFirst);
-            l.nonUniqueSeedOffsetSecond = std::max(l.nonUniqueSeedOffsetSecond, c.nonUniqueSeedOffsetSecond);
-        }
-        else
-        {
-            ++last;
-            if (last != cur) list[last] = list[cur];
-        }
-    }
-    return last + 1;
-}
 
 /* the reference's packed Match fields (SeedId.hh:37-127, ReferencePosition.hh:51-188) */
 __host__ __device__ inline unsigned matchSeed(const isaac_ext_match_t &m) { return unsigned((m.seedId >> 1) & 0xFF); }

@@ -1,10 +1,9 @@
 // R1 of the rescue pass for host AND device code: the window of reference positions ShadowAligner::rescueShadow scans for the mate of
 // an orphan (calculateShadowRescueRange, ShadowAligner.cpp:119-149; the clamps of rescueShadow, :170-198) from the mate model of the
 // template length statistics (TemplateLengthStatistics::mateOrientation / mateMinPosition / mateMaxPosition,
-// TemplateLengthStatistics.cpp:186-238).  The same arithmetic as the host loop of rescueShadowsInto (isaac_ext_pipelines.cuh), as a
-// function a one-thread-per-request kernel can call behind plan_device.cuh, so that requests never visit the host.
+// TemplateLengthStatistics.cpp:186-238) as a function a one-thread-per-request kernel calls (planWriteKernel behind plan_device.cuh,
+// shadowWindowsKernel for requests that come from the caller), so that requests never visit the host.
 // tests/test_template_worker.py checks it on the CPU against the reference's own calculateShadowRescueRange.
-// NOT YET USED by the product path.
 #pragma once
 #include <cstdint>
 #include "../../include/isaac_ext.h"

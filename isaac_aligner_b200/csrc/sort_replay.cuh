@@ -11,7 +11,7 @@
 // its threshold of 16) on a plain pointer range.  tests/cpp/test_sort_replay.cpp checks on the CPU that it produces the same
 // permutation as std::sort, element for element, on millions of lists full of equivalent keys.
 //
-// NOT YET USED by the product path: it is the verified building block of the device-side consolidate.
+// Used by consolidate_device.cuh (the B1-B4 kernels of kernels_tile.cuh) and by finish_device.cuh (the probability lists of TemplateBuilder).
 #pragma once
 
 #if defined(__CUDACC__)

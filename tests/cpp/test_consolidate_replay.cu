@@ -1,11 +1,11 @@
-// consolidate_device.cuh against consolidateDuplicateFragments of host_pipeline.cuh (std::sort of this box's libstdc++), on the CPU:
+// consolidate_device.cuh against consolidateDuplicateFragments of host_consolidate_reference.hh (std::sort of this box's libstdc++), on the CPU:
 // random candidate lists like FragmentBuilder sees them (a few loci hit by several seeds, both strands, aligned and unaligned
 // entries), both values of removeUnaligned: the same surviving records, byte for byte.
 #include <cstdio>
 #include <cstring>
 #include <vector>
 
-#include "../../isaac_aligner_b200/csrc/host_pipeline.cuh"
+#include "host_consolidate_reference.hh"
 #include "../../isaac_aligner_b200/csrc/consolidate_device.cuh"
 
 using namespace isaac_b200;

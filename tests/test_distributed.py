@@ -154,3 +154,52 @@ def test_two_rank_template_stats_allreduce(tmp_path):
     mp.spawn(_template_stats_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     ok, total, local = np.load(os.path.join(str(tmp_path), "ok.npy"))
     assert ok == 1 and total == 1200 and local == 600
+
+
+def _rank_tile_stats(rank, world, port, out_dir):
+    """the full matchSelector::TileStats payload (4 x 47105 u64 + the 4 x 32 summary counters) of two half tiles, summed over two
+    gloo ranks, against the whole tile's: the reference's own TileStats / TileBarcodeStats stand in for the kernels"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    from common_build import build_workload
+    from isaac_aligner_b200 import distributed
+    from isaac_aligner_b200.batch import MatchBatch, Tls, TemplateOptions
+    from isaac_aligner_b200.types import Config, ReadSet
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    genome, sim, reads, mb = build_workload(n_pairs=900, L=100, seed=77, masked=False)
+    cfg, tls, options = Config.default(max_read_length=200), Tls.make(), TemplateOptions.make(clip_semialigned=True)
+    ref = oracle_lib.reference()
+    g = oracle_lib.GenomeHolder(genome)
+
+    def payload(b, e):
+        sub_reads = ReadSet(reads.bcl[b:e], reads.read_lengths)
+        m0, m1 = int(mb.begin[b]), int(mb.begin[e])
+        sub_mb = MatchBatch(mb.matches[m0:m1], mb.begin[b:e + 1] - mb.begin[b], mb.seeds, with_gaps=True)
+        summary = oracle_lib.template_stats(ref, g, sub_reads, cfg, sub_mb, tls, options)
+        cycles = oracle_lib.tile_cycle_stats(ref, g, sub_reads, cfg, sub_mb, tls, options)
+        return np.concatenate([summary.reshape(-1), cycles.reshape(-1)])
+
+    b, e = distributed.cluster_range_of_rank(reads.cluster_count, rank, world)
+    t = torch.from_numpy(payload(b, e).view(np.int64).copy())
+    distributed.allreduce_stats(t)
+    if rank == 0:
+        want = payload(0, reads.cluster_count)
+        got = t.numpy().view(np.uint64)
+        np.save(os.path.join(out_dir, "ok.npy"), np.array([np.array_equal(got, want), got.size, int(want[128 + 34816:128 + 35840].sum())]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/c++") and not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libisaac_ref.so")),
+                    reason="TileStats has the reference build as its only producer on the CPU")
+def test_two_rank_full_tile_stats_payload(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + 17) % 500
+    mp.spawn(_rank_tile_stats, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ok, size, mismatches = np.load(os.path.join(str(tmp_path), "ok.npy"))
+    assert ok == 1 and size == 4 * 32 + 4 * 47105 and mismatches > 0
