@@ -310,13 +310,15 @@ int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
 int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
                               const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result);
 
-/* The three tile calls above without blocking the caller: a submitted call runs on a worker thread of the context (its own CUDA
- * streams) while the caller loads and sorts the next tile's matches, the way the reference runs its load / compute / flush slots
- * side by side (SelectMatchesTransition.cpp:316-340).  The small argument structs are copied at submit; the arrays they point to
- * (matches, offsets, seeds, requests) must stay valid and unchanged until the wait, and isaac_ext_set_reads must not be called in
- * between.  One call is in flight per context (a context is no more re-entrant than the reference's per-thread builders,
- * MatchSelector.cpp:143-163): a second submit before the wait returns ISAAC_EXT_E_UNSUPPORTED.  isaac_ext_wait blocks, returns
- * the status of the call and fills *resultOut, which is the result struct of the call that was submitted
+/* The three tile calls above without blocking the caller: a submitted call runs on a worker thread of the context, on the
+ * context's own streams and buffers, while the caller loads and sorts the next tile's matches, the way the reference runs its
+ * load / compute / flush slots side by side (SelectMatchesTransition.cpp:316-340).  The small argument structs are copied at
+ * submit; the arrays they point to (matches, offsets, seeds, requests) must stay valid and unchanged until the wait.  One call is
+ * in flight per context (a context is no more re-entrant than the reference's per-thread builders, MatchSelector.cpp:143-163):
+ * until the wait, a second submit AND every blocking entry point of the context (isaac_ext_set_reads included) return
+ * ISAAC_EXT_E_UNSUPPORTED without touching the context -- all but isaac_ext_prefetch_reads / isaac_ext_prefetch_batch, which stage
+ * the next tile into the standby slots on their own stream, and isaac_ext_last_error / isaac_ext_version.  isaac_ext_wait blocks,
+ * returns the status of the call and fills *resultOut, which is the result struct of the call that was submitted
  * (isaac_ext_build_result_t / isaac_ext_rescue_result_t / isaac_ext_template_result_t), valid until the next call on the context. */
 int isaac_ext_submit_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, uint64_t *ticketOut);
 int isaac_ext_submit_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t requestCount,

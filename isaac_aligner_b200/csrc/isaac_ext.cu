@@ -134,6 +134,12 @@ struct isaac_ext_ctx
 
 #define CK(call) do { const int rc_ = ctx->cuda((call), #call); if (rc_) return rc_; } while (0)
 
+/// a call submitted with isaac_ext_submit_* owns the context's stream, buffers and error text until isaac_ext_wait: every other
+/// entry point but the two prefetches (they work on the standby slots and their own stream) refuses to run next to it
+bool asyncCallInFlight(const isaac_ext_ctx *ctx);       // isaac_ext_async.cuh
+#define REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx) \
+    do { if (asyncCallInFlight(ctx)) return ISAAC_EXT_E_UNSUPPORTED; } while (0)
+
 namespace
 {
 
@@ -297,6 +303,7 @@ extern "C" int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
                                        const uint64_t *contigLengths)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!contigCount || !contigBases || !contigLengths) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "empty reference");
     CK(cudaSetDevice(ctx->device));
     std::vector<uint64_t> offset(contigCount);
@@ -343,6 +350,7 @@ extern "C" int isaac_ext_set_reference(isaac_ext_ctx *ctx, uint32_t contigCount,
 extern "C" int isaac_ext_set_adapters(isaac_ext_ctx *ctx, uint32_t count, const isaac_ext_adapter_t *adapters)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (count && !adapters) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null adapter list");
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
@@ -455,6 +463,7 @@ extern "C" int isaac_ext_prefetch_reads(isaac_ext_ctx *ctx, const isaac_ext_read
 extern "C" int isaac_ext_set_reads(isaac_ext_ctx *ctx, const isaac_ext_reads_t *r)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!r) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "bad read set");
     isaac_ext_ctx::ReadSlot &standby = ctx->readSlot[ctx->activeSlot ^ 1u];
     if (standby.staged && sameReads(standby.key, *r))
@@ -542,6 +551,7 @@ extern "C" int isaac_ext_ungapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, c
                                                void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
     const uint32_t *clip = nullptr;
@@ -604,6 +614,7 @@ extern "C" int isaac_ext_gapped_batch_device(isaac_ext_ctx *ctx, uint32_t n, con
                                              void *dFragmentsOut, void *dCigarOut, void *dMismatchMaskOut, void *cudaStream)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
     const uint32_t *clip = nullptr;
@@ -643,6 +654,7 @@ static int extendHost(isaac_ext_ctx *ctx, bool gapped, uint32_t n, const isaac_e
                       isaac_ext_fragment_t *fragmentsOut, uint32_t *cigarOut, uint64_t *maskOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     if (!n) return ISAAC_EXT_OK;
     if (!candidates || !fragmentsOut || !cigarOut || cigarStride < 3) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
@@ -684,6 +696,7 @@ extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const c
                                          uint32_t cigarStride, uint32_t *cigarOut, uint32_t *cigarLengthOut, uint32_t *offsetOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!n) return ISAAC_EXT_OK;
     if (!queries || !queryOffsets || !queryLengths || !databases || !databaseOffsets || !cigarOut || !cigarLengthOut || !offsetOut || !cigarStride)
         return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
@@ -777,6 +790,7 @@ extern "C" int isaac_ext_banded_sw_wide_batch_device(isaac_ext_ctx *ctx, uint32_
                                                      void *dCigarLengthOut, void *dOffsetOut, void *cudaStream)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!n) return ISAAC_EXT_OK;
     if (!dQueries || !dQueryOffsets || !dQueryLengths || !dDatabases || !dDatabaseOffsets || !dCigarOut || !dCigarLengthOut || !dOffsetOut ||
         !cigarStride || !maxQueryLength)
@@ -794,6 +808,7 @@ extern "C" int isaac_ext_banded_sw_wide_batch(isaac_ext_ctx *ctx, uint32_t bandW
                                               uint32_t cigarStride, uint32_t *cigarOut, uint32_t *cigarLengthOut, uint32_t *offsetOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!n) return ISAAC_EXT_OK;
     if (!queries || !queryOffsets || !queryLengths || !databases || !databaseOffsets || !cigarOut || !cigarLengthOut || !offsetOut || !cigarStride)
         return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null buffer");
@@ -838,6 +853,7 @@ extern "C" int isaac_ext_banded_sw_wide_batch(isaac_ext_ctx *ctx, uint32_t bandW
 extern "C" int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond)
 {
     if (!ctx || !opsPerSecond || kind < 0 || kind > 2) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     CK(cudaSetDevice(ctx->device));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -865,6 +881,7 @@ extern "C" int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double
 extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const void *dFragments, void *dStats, void *cudaStream)
 {
     if (!ctx || !dStats || (n && !dFragments)) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     static_assert(STAT_COUNT == ISAAC_EXT_STATS_COUNTERS, "counter layout");
     if (!n) return ISAAC_EXT_OK;
     tileStatsKernel<<<gridFor(ctx, n, 256, 8), 256, 0, cudaStream_t(cudaStream)>>>(
@@ -893,6 +910,7 @@ extern "C" int isaac_ext_ungapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, 
                                                 uint64_t *cigarWordsOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->e2e) ctx->e2e = new E2eState();
     E2ePass pass = {false, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut};
     return extendCompact(ctx, *ctx->e2e, n, candidates, &pass, 1);
@@ -903,6 +921,7 @@ extern "C" int isaac_ext_gapped_batch_compact(isaac_ext_ctx *ctx, uint32_t n, co
                                               uint64_t *cigarWordsOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->e2e) ctx->e2e = new E2eState();
     E2ePass pass = {true, fragmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut};
     return extendCompact(ctx, *ctx->e2e, n, candidates, &pass, 1);
@@ -914,6 +933,7 @@ extern "C" int isaac_ext_extend_batch_compact(isaac_ext_ctx *ctx, uint32_t n, co
                                               uint64_t gappedPoolCapacity, uint64_t *gappedWordsOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->e2e) ctx->e2e = new E2eState();
     E2ePass passes[2] = {{false, ungappedOut, ungappedPoolOut, ungappedPoolCapacity, ungappedWordsOut},
                          {true, gappedOut, gappedPoolOut, gappedPoolCapacity, gappedWordsOut}};
@@ -925,6 +945,7 @@ extern "C" int isaac_ext_align_batch_packed(isaac_ext_ctx *ctx, uint32_t n, cons
                                             uint64_t *cigarWordsOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->e2e) ctx->e2e = new E2eState();
     return alignPacked(ctx, *ctx->e2e, n, candidates, alignmentsOut, cigarPoolOut, cigarPoolCapacity, cigarWordsOut);
 }

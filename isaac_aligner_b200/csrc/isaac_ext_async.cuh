@@ -1,15 +1,18 @@
 // isaac_ext_submit_* / isaac_ext_wait: the three tile calls without blocking the caller ("async submit, wait on a
 // ticket").  The reference overlaps the loading and sorting of the next tile's matches with the processing of the current one
 // (SelectMatchesTransition.cpp:316-340 runs load / compute / flush slots side by side); a submitted call runs on a worker thread of
-// the context with its own CUDA streams while the caller's thread goes on.  A context is not re-entrant (like the reference's
+// the context (on the context's streams) while the caller's thread goes on -- e.g. with isaac_ext_prefetch_reads / _batch of the next
+// tile, the only calls the context accepts from other threads meanwhile.  A context is not re-entrant (like the reference's
 // per-thread builders), so one call is in flight per context: a second submit before the wait is refused.  Included by isaac_ext.cu.
 #pragma once
+#include <atomic>
 #include <thread>
 
 struct AsyncState
 {
     std::thread worker;
-    bool inFlight = false;
+    std::atomic<std::thread::id> workerId;
+    std::atomic<bool> inFlight{false};
     uint64_t ticket = 0;
     int status = ISAAC_EXT_OK;
     int kind = 0;                                   // 1 build_fragments, 2 rescue_shadows, 3 build_templates
@@ -23,6 +26,12 @@ struct AsyncState
     isaac_ext_rescue_result_t rescue;
     isaac_ext_template_result_t templates;
 };
+
+/// true for every thread but the worker itself while a submitted call runs (the error text is not touched: it belongs to that call)
+bool asyncCallInFlight(const isaac_ext_ctx *ctx)
+{
+    return ctx && ctx->async && ctx->async->inFlight && std::this_thread::get_id() != ctx->async->workerId.load();
+}
 
 void releaseAsync(AsyncState *state)
 {
@@ -38,10 +47,12 @@ int submitCall(isaac_ext_ctx *ctx, int kind, uint64_t *ticketOut)
     AsyncState &a = *ctx->async;
     a.kind = kind;
     a.status = ISAAC_EXT_OK;
+    a.workerId = std::thread::id();                 // nobody until the worker names itself
     a.inFlight = true;
     *ticketOut = ++a.ticket;
     a.worker = std::thread([ctx, kind]() {
         AsyncState &s = *ctx->async;
+        s.workerId = std::this_thread::get_id();        // before its first entry point: asyncCallInFlight lets only this thread through
         s.status = kind == 1 ? isaac_ext_build_fragments(ctx, &s.batch, &s.build)
                  : kind == 2 ? isaac_ext_rescue_shadows(ctx, &s.tls, s.requestCount, s.requests, &s.rescue)
                              : isaac_ext_build_templates(ctx, &s.batch, &s.tls, &s.options, &s.templates);

@@ -33,6 +33,7 @@ extern "C" int isaac_ext_pack_fragments(isaac_ext_ctx *ctx, const isaac_ext_temp
                                         const isaac_ext_pack_options_t *options, isaac_ext_pack_result_t *result)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!templates || !options || !result) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (!ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reads first");
     if (!templates->templates || !templates->fragments || (templates->cigarWords && !templates->cigars))

@@ -14,6 +14,7 @@ void releaseSelect(SelectState *state) { delete state; }
 extern "C" int isaac_ext_select_tile(isaac_ext_ctx *ctx, const isaac_ext_tile_t *tile, isaac_ext_tile_result_t *result)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!tile || !result) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (tile->matchCount && !tile->matches) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null matches");
     if (!ctx->select) ctx->select = new SelectState();

@@ -267,6 +267,7 @@ extern "C" int isaac_ext_prefetch_batch(isaac_ext_ctx *ctx, const isaac_ext_buil
 extern "C" int isaac_ext_build_fragments(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, isaac_ext_build_result_t *result)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!result) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null result");
     int rc = tileBuildDevice(ctx, batch);
     if (rc) return rc;
@@ -484,6 +485,8 @@ static int rescueShadowsInto(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
 extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uint32_t n,
                                         const isaac_ext_rescue_request_t *requests, isaac_ext_rescue_result_t *result)
 {
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     return rescueShadowsInto(ctx, tls, n, requests, result, 0);
 }
 
@@ -496,6 +499,7 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
                                          const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!batch || !tls || !options || !result) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     PhaseTimer timer("templates");
     int rc = tileBuildDevice(ctx, batch);
@@ -625,6 +629,7 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
 extern "C" int isaac_ext_tile_cycle_stats(isaac_ext_ctx *ctx, const uint8_t *pf, uint64_t *statsOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!statsOut) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (!ctx->tile || !ctx->tile->templatesResident)
         return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "no templates on the device: isaac_ext_build_templates / isaac_ext_select_tile of the tile first");
@@ -673,6 +678,7 @@ extern "C" void isaac_ext_tile_cycle_stats_finalize(uint64_t *block)
 extern "C" int isaac_ext_trim_low_quality_ends(isaac_ext_ctx *ctx, uint32_t baseQualityCutoff, uint16_t *endCyclesMaskedOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reads first");
     CK(cudaSetDevice(ctx->device));
     const uint32_t n = ctx->reads.readTotal;

@@ -25,6 +25,7 @@ extern "C" int isaac_ext_determine_template_length(isaac_ext_ctx *ctx, const isa
                                                    int32_t mateDriftRange, isaac_ext_tls_t *tlsOut, uint32_t *stableOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!batch || !tlsOut || !stableOut) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (!ctx->haveReference || !ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reference / set_reads first");
     TemplateLengthDistributionHost distribution(mateDriftRange);
@@ -58,6 +59,7 @@ extern "C" int isaac_ext_template_stats(isaac_ext_ctx *ctx, const isaac_ext_buil
                                         const isaac_ext_template_result_t *templates, const uint8_t *pf, uint64_t *statsOut)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
     if (!batch || !tls || !templates || !statsOut) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "null argument");
     if (!ctx->haveReads) return ctx->fail(ISAAC_EXT_E_NO_REFERENCE, "set_reads first");
     const uint32_t n = ctx->clusterCount, rc = ctx->reads.readCount;

@@ -27,6 +27,12 @@ def test_submit_wait_build_templates():
     assert second.value.code == 4
     with pytest.raises(capi.ExtError):                                   # not the ticket that is in flight
         ctx.wait_templates(ticket + 1)
+    for blocking in (lambda: ctx.set_reads(reads), lambda: ctx.build_templates(mb, tls, options),
+                     lambda: ctx.determine_template_length(mb), lambda: ctx.trim_low_quality_ends(10)):
+        with pytest.raises(capi.ExtError) as refused:                    # the context belongs to the submitted call until the wait
+            blocking()
+        assert refused.value.code == 4
+    ctx.prefetch_reads(reads)                                            # staging the next tile is the one thing allowed meanwhile
     host_work = int(np.sort(np.arange(200_000)[::-1]).sum())             # the caller's thread is free meanwhile
     got = ctx.wait_templates(ticket)
     assert host_work > 0
