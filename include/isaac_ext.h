@@ -568,6 +568,66 @@ int isaac_ext_banded_sw_wide_batch_device(isaac_ext_ctx *ctx, uint32_t bandWidth
                                           int gapOpenScore, int gapExtendScore, uint32_t cigarStride, void *dCigarOut,
                                           void *dCigarLengthOut, void *dOffsetOut, void *cudaStream);
 
+/* ---- SURVEY 8(f) #4, last part: build::GapRealigner over one bin -------------------------------------------------------- */
+/* The reference realigns bin by bin (BinSorter::process, BinSorter.hh:161-175): collectGaps walks every record of the bin's data and
+ * gathers the insertions and deletions of their CIGARs per gap group (BinSorter.cpp:389-405, RealignerGaps::addGaps
+ * GapRealigner.hh:52-97, finalizeGaps GapRealigner.cpp:86-94), then realignGaps calls GapRealigner::realign for every entry of the
+ * bin's index in index order (BinSorter.cpp:407-418, GapRealigner.cpp:1061-1267).  A bin here is what the reference holds at that
+ * point: the io::FragmentHeader records back to back (the layout isaac_ext_pack_fragments leaves with options.compact, = the bin
+ * file) and PackedFragmentBuffer::Index without its pointers. */
+typedef struct isaac_ext_bin_index {
+    uint64_t dataOffset;              /* PackedFragmentBuffer::Index::dataOffset_: byte offset of the record in the bin's data  */
+    uint64_t mateDataOffset;          /* ::mateDataOffset_; = dataOffset for single-ended records and mates stored in another bin */
+} isaac_ext_bin_index_t;
+
+/* gapRealigner::Gap (Gap.hh:32-80) */
+typedef struct isaac_ext_gap {
+    uint64_t position;                /* ReferencePosition::getValue of Gap::pos_                                               */
+    int32_t  length;                  /* > 0 deletion from the reference, < 0 insertion                                         */
+    uint32_t group;                   /* gap group (BinSorter::getGapGroupIndex, BinSorter.cpp:355-370)                         */
+} isaac_ext_gap_t;
+
+typedef struct isaac_ext_realign_options {
+    uint64_t binStart, binEnd;        /* ReferencePosition::getValue of BinMetadata::getBinStart / getBinEnd                    */
+    uint32_t realignGapsVigorously;   /* --realign-vigorously                                                                  */
+    uint32_t realignDodgyFragments;   /* --realign-dodgy                                                                       */
+    uint32_t mismatchCost, gapOpenCost, gapExtendCost;   /* BinSorter constructs the realigner with 3, 4, 0 (BinSorter.hh:97)  */
+    uint32_t clipSemialigned;         /* --clip-semialigned: build::SemialignedEndsClipper after a realignment                 */
+    uint32_t barcodeCount;            /* barcodes the records may name (FragmentHeader::barcode_ < barcodeCount)                */
+    uint32_t pad;
+    const struct isaac_ext_tls *barcodeTls;     /* barcodeCount template length statistics (updatePairDetails, :267-269)        */
+    const uint32_t *barcodeGapGroup;  /* gap group of every barcode (REALIGN_SAMPLE / REALIGN_PROJECT), NULL = one group (REALIGN_ALL) */
+} isaac_ext_realign_options_t;
+
+#define ISAAC_EXT_REALIGN_OWN_CIGAR 0xFFFFFFFFu
+/* Owned by the context, valid until its next isaac_ext_realign_bin.  The records themselves are updated in the caller's buffer the
+ * way the reference updates its PackedFragmentBuffer (fStrandPosition_, observedLength_, editDistance_, bamTlen_,
+ * mateFStrandPosition_, flags_.properPair_ of the fragment and its mate; the CIGAR bytes of a record are never rewritten). */
+typedef struct isaac_ext_realign_result {
+    const uint64_t *position;         /* Index::pos_ of every index entry after the pass (ReferencePosition::getValue)          */
+    const uint32_t *cigarOffset;      /* first word of the entry's CIGAR in realignedCigars, ISAAC_EXT_REALIGN_OWN_CIGAR = the
+                                         record's own CIGAR is still the one (Index::cigarBegin_ / cigarEnd_)                    */
+    const uint32_t *cigarLength;      /* operations of the entry's CIGAR                                                       */
+    const uint32_t *realignedCigars;  /* GapRealigner::realignedCigars_: one CIGAR per realigned entry, in no particular order  */
+    uint64_t realignedCigarWords;
+    uint64_t realignedFragments;      /* entries that left with a new CIGAR                                                     */
+    const isaac_ext_gap_t *gaps;      /* RealignerGaps::gapGroups_ of every group after finalizeGaps: by group, start, signed length */
+    const isaac_ext_gap_t *deletionsByEnd;   /* RealignerGaps::deletionEndGroups_: the deletions by group and end position       */
+    uint64_t gapCount, deletionCount;
+    float    collectMs, realignMs;    /* duration of the two device phases alone (CUDA events), for bench.py                    */
+} isaac_ext_realign_result_t;
+
+/* collectGaps + realignGaps of one bin on the context's GPU against the resident reference.  data: the bin's records (read and
+ * updated in place); recordOffset: byte offset of each of the recordCount records of the bin in 'data' (collectGaps reads them all,
+ * whether the index still names them or not), NULL = the library walks the chain of FragmentHeader::getTotalLength itself.
+ * Independent of the order of bins and, inside a bin, of the order of templates: the two mates of a pair are realigned in index
+ * order by one thread, because the second one reads what the first one's updatePairDetails left (GapRealigner.cpp:222-270,
+ * 1112-1113); nothing else is shared between index entries (the gaps are final before the first realign call).
+ * Limits: records of more than 1024 bases, or original CIGARs of more than 64 operations, are ISAAC_EXT_E_UNSUPPORTED. */
+int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign_options_t *options, uint8_t *data, uint64_t dataBytes,
+                          const uint64_t *recordOffset, uint64_t recordCount, const isaac_ext_bin_index_t *index,
+                          uint64_t indexCount, isaac_ext_realign_result_t *result);
+
 /* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
  * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
 int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);

@@ -123,6 +123,17 @@ int oracle_tile_cycle_stats(const oracle_genome_t *genome, const isaac_ext_reads
                             const isaac_ext_template_options_t *options, const uint8_t *pf, uint64_t *statsOut, uint32_t finalize,
                             uint32_t threads);
 
+/* liboracle_ref only: BinSorter::collectGaps + BinSorter::realignGaps of one bin through the reference's own RealignerGaps and
+ * GapRealigner (see isaac_ext_realign_bin): data is updated in place; positionOut / cigarOffsetOut / cigarLengthOut per index entry
+ * (cigarOffset 0xFFFFFFFF = the record's own CIGAR), the realigned CIGARs copied to cigarsOut back to back in index order;
+ * gapsOut / deletionsOut = gapGroups_ / deletionEndGroups_ of every group in group order, countsOut = {gaps, deletions, cigar words}.
+ * threadsafe (no static state but the contig cache). */
+int oracle_realign_bin(const oracle_genome_t *genome, const isaac_ext_realign_options_t *options, uint8_t *data, uint64_t dataBytes,
+                       const uint64_t *recordOffset, uint64_t recordCount, const isaac_ext_bin_index_t *index, uint64_t indexCount,
+                       uint64_t *positionOut, uint32_t *cigarOffsetOut, uint32_t *cigarLengthOut, uint32_t *cigarsOut,
+                       uint64_t cigarCapacity, isaac_ext_gap_t *gapsOut, isaac_ext_gap_t *deletionsOut, uint64_t gapCapacity,
+                       uint64_t *countsOut);
+
 #ifdef __cplusplus
 }
 #endif

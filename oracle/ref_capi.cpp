@@ -84,6 +84,11 @@ const std::vector<reference::Contig> &makeContigs(const oracle_genome_t *g)
     return cached;
 }
 
+} // namespace
+const std::vector<reference::Contig> &oracleContigs(const oracle_genome_t *g) { return makeContigs(g); }   // ref_capi_realign.cpp
+namespace
+{
+
 flowcell::ReadMetadataList makeReadMetadata(const isaac_ext_reads_t *r)
 {
     std::vector<flowcell::ReadMetadata> v;

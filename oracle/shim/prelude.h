@@ -11,6 +11,8 @@
 #include <vector>
 #include <iostream>
 #include <iterator>
+#include <iomanip>
+#include <functional>
 #include <stdint.h>
 #include <boost/noncopyable.hpp>
 #include <boost/format.hpp>
@@ -20,8 +22,12 @@
 #include <boost/numeric/conversion/cast.hpp>
 #include <boost/assign.hpp>
 #include <boost/array.hpp>
+#include <boost/lexical_cast.hpp>
+#include <boost/ref.hpp>
+#include <boost/filesystem.hpp>
 #define BOOST_STATIC_ASSERT(x) static_assert(x, "")
 #define BOOST_CURRENT_FUNCTION __func__
 #include "common/Debug.hh"
 #include "common/Exceptions.hh"
 #include "alignment/SeedMetadata.hh"   // the reference's flowcell/Layout.hh brings this in
+#include "common/FiniteCapacityVector.hh"

@@ -287,3 +287,37 @@ def reference():
         else:
             return None
     return Oracle(REF_SO)
+
+
+def _realign_call(fn, head_args, bin_, options, cigar_capacity=None, gap_capacity=None):
+    """shared argument plumbing of oracle_realign_bin and tests/cpp's realign_bin_host; returns bins.RealignResult + counts"""
+    from isaac_aligner_b200 import bins
+    n = len(bin_.index)
+    data = bin_.data.copy()
+    cigar_capacity = cigar_capacity or (n * 96 + 64)
+    gap_capacity = gap_capacity or (len(bin_.record_offset) * 8 + 16)
+    position = np.zeros(n, dtype=np.uint64)
+    cigar_offset = np.zeros(n, dtype=np.uint32)
+    cigar_length = np.zeros(n, dtype=np.uint32)
+    cigars = np.zeros(cigar_capacity, dtype=np.uint32)
+    gaps = np.zeros(gap_capacity, dtype=bins.GAP_DTYPE)
+    deletions = np.zeros(gap_capacity, dtype=bins.GAP_DTYPE)
+    counts = np.zeros(8, dtype=np.uint64)
+    index = np.ascontiguousarray(bin_.index)
+    offsets = np.ascontiguousarray(bin_.record_offset, dtype=np.uint64)
+    rc = fn(*head_args, ctypes.byref(options.c), ctypes.c_void_p(data.ctypes.data), ctypes.c_uint64(data.size),
+            ctypes.c_void_p(offsets.ctypes.data), ctypes.c_uint64(offsets.size), ctypes.c_void_p(index.ctypes.data), ctypes.c_uint64(n),
+            ctypes.c_void_p(position.ctypes.data), ctypes.c_void_p(cigar_offset.ctypes.data), ctypes.c_void_p(cigar_length.ctypes.data),
+            ctypes.c_void_p(cigars.ctypes.data), ctypes.c_uint64(cigar_capacity), ctypes.c_void_p(gaps.ctypes.data),
+            ctypes.c_void_p(deletions.ctypes.data), ctypes.c_uint64(gap_capacity), ctypes.c_void_p(counts.ctypes.data))
+    if rc:
+        raise RuntimeError("realign call failed: %d" % rc)
+    res = bins.RealignResult(data, position, cigar_offset, cigar_length, cigars[:int(counts[2])], gaps[:int(counts[0])],
+                             deletions[:int(counts[1])])
+    return res, counts
+
+
+def realign_bin(oracle, genome, bin_, options):
+    """BinSorter::collectGaps + realignGaps through the reference's own classes (liboracle_ref only)"""
+    res, _ = _realign_call(oracle.lib.oracle_realign_bin, (ctypes.byref(genome.c),), bin_, options)
+    return res
