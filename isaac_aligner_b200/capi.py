@@ -38,6 +38,7 @@ EXPORTS = [
     "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
     "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed", "isaac_ext_prefetch_reads", "isaac_ext_prefetch_batch", "isaac_ext_tile_cycle_stats", "isaac_ext_tile_cycle_stats_finalize",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
+    "isaac_ext_realign_bin",
 ]
 
 
@@ -319,6 +320,32 @@ class Context:
         if not copy:
             return res                     # pointers into the context's buffers (bench.py: no host copy inside the timed region)
         return self._packed(res, bool(options.c.compact))
+
+    def realign_bin(self, bin_, options):
+        """build::GapRealigner over one bin (bins.Bin, bins.RealignOptions -> bins.RealignResult): BinSorter::collectGaps +
+        BinSorter::realignGaps on the GPU against the resident reference; bin_.data is left as it was, the updated records are in
+        the result"""
+        from . import bins
+        data = np.ascontiguousarray(bin_.data).copy()
+        offsets = np.ascontiguousarray(bin_.record_offset, dtype=np.uint64) if bin_.record_offset is not None else None
+        index = np.ascontiguousarray(bin_.index)
+        res = bins.RealignResultC()
+        self._check(_lib.isaac_ext_realign_bin(self._h, ctypes.byref(options.c), ctypes.c_void_p(data.ctypes.data), ctypes.c_uint64(data.size),
+                                               ctypes.c_void_p(offsets.ctypes.data) if offsets is not None else None,
+                                               ctypes.c_uint64(offsets.size if offsets is not None else 0),
+                                               ctypes.c_void_p(index.ctypes.data), ctypes.c_uint64(index.size), ctypes.byref(res)))
+
+        def arr(ptr, dtype, count):
+            if not count:
+                return np.zeros(0, dtype=dtype)
+            buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype).copy()
+
+        n = index.size
+        return bins.RealignResult(data, arr(res.position, np.uint64, n), arr(res.cigarOffset, np.uint32, n), arr(res.cigarLength, np.uint32, n),
+                                  arr(res.realignedCigars, np.uint32, int(res.realignedCigarWords)), arr(res.gaps, bins.GAP_DTYPE, int(res.gapCount)),
+                                  arr(res.deletionsByEnd, bins.GAP_DTYPE, int(res.deletionCount)), int(res.realignedFragments),
+                                  float(res.collectMs), float(res.realignMs))
 
     def _packed(self, res, compact=False):
         from .batch import PackedFragments

@@ -37,6 +37,8 @@ struct AsyncState;                     // isaac_ext_async.cuh
 void releaseAsync(AsyncState *state);
 struct SelectState;                    // isaac_ext_select.cuh
 void releaseSelect(SelectState *state);
+struct RealignState;                   // isaac_ext_realign.cuh
+void releaseRealign(RealignState *state);
 
 struct isaac_ext_ctx
 {
@@ -63,6 +65,7 @@ struct isaac_ext_ctx
     PackState *pack = nullptr;            // buffers of isaac_ext_pack_fragments
     AsyncState *async = nullptr;          // the call in flight between isaac_ext_submit_* and isaac_ext_wait
     SelectState *select = nullptr;        // isaac_ext_select_tile
+    RealignState *realign = nullptr;      // buffers of isaac_ext_realign_bin
     double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
 
     // score tables (host libm, Quality.cpp:34-66) and parameters
@@ -296,6 +299,7 @@ extern "C" void isaac_ext_destroy(isaac_ext_ctx *ctx)
     releaseTile(ctx->tile);
     releasePack(ctx->pack);
     releaseSelect(ctx->select);
+    releaseRealign(ctx->realign);
     delete ctx;
 }
 
@@ -899,6 +903,7 @@ extern "C" int isaac_ext_tile_stats_device(isaac_ext_ctx *ctx, uint32_t n, const
 #include "isaac_ext_pack.cuh"
 #include "isaac_ext_async.cuh"
 #include "isaac_ext_select.cuh"
+#include "isaac_ext_realign.cuh"
 
 namespace
 {

@@ -64,7 +64,7 @@ def test_python_mirrors_have_the_c_struct_sizes():
     """every ctypes.Structure / numpy dtype the harness passes over the ABI against sizeof() of the header's struct (gcc)"""
     import ctypes
     import subprocess
-    from isaac_aligner_b200 import batch, synth, tile, types
+    from isaac_aligner_b200 import batch, bins, synth, tile, types
     pairs = [("isaac_ext_tile_t", ctypes.sizeof(tile.TileC)), ("isaac_ext_tile_result_t", ctypes.sizeof(tile.TileResultC)),
              ("isaac_ext_config_t", ctypes.sizeof(types.Config)), ("isaac_ext_reads_t", ctypes.sizeof(types.Reads)),
              ("isaac_ext_adapter_t", ctypes.sizeof(types.Adapter)), ("isaac_ext_fragment_t", types.FRAGMENT_DTYPE.itemsize),
@@ -74,7 +74,9 @@ def test_python_mirrors_have_the_c_struct_sizes():
              ("isaac_ext_rescue_request_t", batch.RESCUE_REQUEST_DTYPE.itemsize), ("isaac_ext_rescue_result_t", ctypes.sizeof(batch.RescueResult)),
              ("isaac_ext_template_options_t", ctypes.sizeof(batch.TemplateOptions)), ("isaac_ext_template_t", batch.TEMPLATE_DTYPE.itemsize),
              ("isaac_ext_template_result_t", ctypes.sizeof(batch.TemplateResult)), ("isaac_ext_pack_options_t", ctypes.sizeof(batch.PackOptionsC)),
-             ("isaac_ext_pack_result_t", ctypes.sizeof(batch.PackResultC))]
+             ("isaac_ext_pack_result_t", ctypes.sizeof(batch.PackResultC)), ("isaac_ext_bin_index_t", bins.BIN_INDEX_DTYPE.itemsize),
+             ("isaac_ext_gap_t", bins.GAP_DTYPE.itemsize), ("isaac_ext_realign_options_t", ctypes.sizeof(bins.RealignOptionsC)),
+             ("isaac_ext_realign_result_t", ctypes.sizeof(bins.RealignResultC))]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = os.path.join(root, "build", "abi_sizes.c")
     os.makedirs(os.path.dirname(src), exist_ok=True)

@@ -1,0 +1,107 @@
+"""isaac_ext_realign_bin on the GPU against the reference's own build::RealignerGaps / build::GapRealigner /
+build::SemialignedEndsClipper (oracle_realign_bin): every byte of the bin's data afterwards, Index::pos_ and the CIGAR of every index
+entry, gapGroups_ and deletionEndGroups_ -- the latter also where the reference's unstable std::sort decides the order of ties."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from isaac_aligner_b200 import bins
+from isaac_aligner_b200.batch import Tls
+from isaac_aligner_b200.types import Config
+from test_realign_host import compare, make_contigs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return oracle_lib.require_reference()
+
+
+@pytest.fixture(scope="module")
+def ctx_and_contigs():
+    from isaac_aligner_b200 import capi
+    contigs = make_contigs(77, lengths=(3000, 120000))
+    ctx = capi.Context(Config.default(max_read_length=256))
+    ctx.set_reference(contigs)
+    yield ctx, contigs
+    ctx.close()
+
+
+def data_only_record(contig, position, cigar, read_length=100, barcode=0):
+    """a record that only brings gaps along (it is in the bin's data, not in its index)"""
+    h = np.zeros(1, dtype=bins.HEADER_DTYPE)[0]
+    h["fStrandPosition"] = bins.reference_position(contig, position)
+    h["mateFStrandPosition"] = bins.reference_position(contig, position)
+    h["readLength"], h["cigarLength"] = read_length, len(cigar)
+    h["gapCount"] = sum(1 for _, op in cigar if op in (bins.OP_INSERT, bins.OP_DELETE))
+    h["flags"] = bins.FLAG_PAIRED | bins.FLAG_FIRST_READ
+    h["barcode"] = barcode
+    words = np.array([(n << 4) | op for n, op in cigar], dtype=np.uint32)
+    return h.tobytes() + bytes(read_length) + words.tobytes()
+
+
+@pytest.mark.parametrize("seed,vigorous,clip,dodgy,L,spacing", [(11, False, False, False, 100, 220), (12, False, True, False, 150, 120),
+                                                                  (13, True, True, True, 100, 60), (14, True, False, False, 250, 220),
+                                                                  (15, False, True, True, 36, 25)])
+def test_realign_bin_equals_reference(ctx_and_contigs, ref, seed, vigorous, clip, dodgy, L, spacing):
+    ctx, contigs = ctx_and_contigs
+    genome = oracle_lib.GenomeHolder(contigs)
+    bin_ = bins.simulate_bin(contigs, contig=1, region=(1500, 90000), n_pairs=12000, read_length=L, seed=seed, barcodes=3,
+                             variant_spacing=spacing, template_mean=int(2.6 * L) + 60, edge_fraction=0.01)
+    tls = [Tls.make(mn=int(2.0 * L), mx=int(3.4 * L) + 120, median=int(2.6 * L) + 60) for _ in range(3)]
+    options = bins.RealignOptions(bin_.bin_start, bin_.bin_end, tls, vigorous=vigorous, dodgy=dodgy, clip_semialigned=clip,
+                                  gap_groups=[0, 1, 0] if seed % 2 else None)
+    want = oracle_lib.realign_bin(ref, genome, bin_, options)
+    got = ctx.realign_bin(bin_, options)
+    realigned = compare(bin_, got, want)
+    assert realigned > 200 and got.realigned == realigned
+
+
+def test_deletions_that_end_at_the_same_base(ctx_and_contigs, ref):
+    """ties in deletionEndGroups_: more than 16 deletions with pairwise equal ends, so that the reference's introsort partitions"""
+    ctx, contigs = ctx_and_contigs
+    genome = oracle_lib.GenomeHolder(contigs)
+    bin_ = bins.simulate_bin(contigs, contig=1, region=(1500, 40000), n_pairs=3000, read_length=100, seed=21)
+    rng = np.random.default_rng(5)
+    extra, offsets, at = [], [], int(bin_.data.size)
+    for k in range(160):
+        p = 2000 + 37 * (k // 4)
+        first = 30 + 2 * (k % 4)                                             # 30M8D, 32M6D, 34M4D, 36M2D: all four end at p + 38
+        blob = data_only_record(1, p, [(first, bins.OP_ALIGN), (8 - 2 * (k % 4), bins.OP_DELETE), (100 - first, bins.OP_ALIGN)])
+        extra.append(blob); offsets.append(at); at += len(blob)
+    order = rng.permutation(len(extra))
+    data = np.concatenate([bin_.data] + [np.frombuffer(extra[i], dtype=np.uint8) for i in order])
+    offs, at = [], int(bin_.data.size)
+    for i in order:
+        offs.append(at); at += len(extra[i])
+    tied = bins.Bin(data, np.concatenate([bin_.record_offset, np.array(offs, dtype=np.uint64)]), bin_.index, bin_.bin_start, bin_.bin_end)
+    options = bins.RealignOptions(tied.bin_start, tied.bin_end, [Tls.make()], clip_semialigned=True)
+    want = oracle_lib.realign_bin(ref, genome, tied, options)
+    ends = want.deletions["position"] + 2 * want.deletions["length"].astype(np.uint64)
+    assert np.count_nonzero(ends[1:] == ends[:-1]) >= 100
+    stable = np.lexsort((want.deletions["length"], want.deletions["position"], ends))
+    assert not np.array_equal(want.deletions[stable], want.deletions)        # the reference's order is not the stable one: the host step matters
+    got = ctx.realign_bin(tied, options)
+    compare(tied, got, want)
+    # the chain of records walked by the library itself gives the same
+    walked = bins.Bin(data, None, bin_.index, bin_.bin_start, bin_.bin_end)
+    again = ctx.realign_bin(walked, options)
+    assert np.array_equal(again.data, got.data) and np.array_equal(again.deletions, got.deletions)
+
+
+def test_argument_errors(ctx_and_contigs):
+    from isaac_aligner_b200 import capi
+    ctx, contigs = ctx_and_contigs
+    bin_ = bins.simulate_bin(contigs, contig=1, region=(1500, 9000), n_pairs=300, read_length=100, seed=3)
+    good = bins.RealignOptions(bin_.bin_start, bin_.bin_end, [Tls.make()])
+    broken = bins.Bin(bin_.data[:-5], bin_.record_offset, bin_.index, bin_.bin_start, bin_.bin_end)
+    with pytest.raises(capi.ExtError) as e:
+        ctx.realign_bin(broken, good)                                        # the last record runs out of the data
+    assert e.value.code == 1
+    elsewhere = bins.RealignOptions(bins.reference_position(7, 0), bins.reference_position(7, 100), [Tls.make()])
+    with pytest.raises(capi.ExtError):
+        ctx.realign_bin(bin_, elsewhere)                                     # no such contig
+    empty = bins.Bin(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=bins.BIN_INDEX_DTYPE), bin_.bin_start, bin_.bin_end)
+    res = ctx.realign_bin(empty, good)
+    assert res.position.size == 0 and res.gaps.size == 0
