@@ -57,9 +57,11 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--band", type=int, default=32, help="--workload wide: lanes of the band (16 = the reference's, 32 = the widened band)")
     p.add_argument("--alignments", type=int, default=2_000_000, help="--workload wide: alignments per GPU and step")
-    p.add_argument("--workload", default="micro", choices=["micro", "pairs", "pack", "wide"],
+    p.add_argument("--workload", default="micro", choices=["micro", "pairs", "pack", "wide", "realign"],
                    help="micro: BASELINE configs[1] (default, the bench line); pairs: build + rescue pipeline, read pairs/s; "
                         "pack: the io::FragmentHeader bin records of a tile's templates (isaac_ext_pack_fragments), fragments/s")
+    p.add_argument("--bins", type=int, default=16, help="--workload realign: bins per step")
+    p.add_argument("--bin-pairs", type=int, default=40_000, help="--workload realign: read pairs sampled per bin")
     p.add_argument("--compact", action="store_true", help="--workload pack: records cut to their total length instead of FragmentBuffer slots")
     p.add_argument("--pairs", type=int, default=None,
                    help="read pairs per GPU of the pairs pipeline (default 2M: BASELINE configs[2] sharded, next to the micro run and for --workload pairs; 0 disables)")
@@ -889,9 +891,169 @@ def run_wide(args):
     ctx.close()
 
 
+def _realign_bin_worker(job):
+    from isaac_aligner_b200 import bins
+    contig_bases, region, n_pairs, L, seed = job
+    b = bins.simulate_bin([contig_bases], contig=0, region=region, n_pairs=n_pairs, read_length=L, seed=seed, template_mean=int(2.6 * L) + 60,
+                          variant_spacing=300, max_indel=12)
+    return b.data, b.record_offset, b.index, b.bin_start, b.bin_end
+
+
+def run_realign(args):
+    """--workload realign: isaac_ext_realign_bin (build::GapRealigner, SURVEY 8f #4) over --bins bins of one contig, each the records
+    of --bin-pairs pairs sampled at ~20x from a haplotype with shared indels.  One step = every bin once (BinSorter::process per bin).
+    value = index entries/s over the device phases alone (CUDA events inside the library: collectGaps + realignGaps), e2e = the same
+    through the C call with host buffers (records up, updated records + positions + CIGARs down); cpu_baseline / --impl reference =
+    the reference's own GapRealigner on the same bins, one bin per host thread.  Results are compared bin by bin."""
+    import ctypes
+    import multiprocessing
+    import torch
+    from isaac_aligner_b200 import bins, synth
+    from isaac_aligner_b200.batch import Tls
+    from isaac_aligner_b200.types import Config
+    L, B, n_pairs = args.read_length, args.bins, args.bin_pairs
+    span = int(n_pairs * 2 * L / 20)                                 # ~20x
+    genome = synth.make_genome((span + 4000) * B + 4000, n_contigs=1, seed=synth.SEED_G5)
+    contig = genome[0]
+    jobs = [(contig, (2000 + k * (span + 4000), 2000 + k * (span + 4000) + span), n_pairs, L, 900 + k) for k in range(B)]
+    cores = sorted(os.sched_getaffinity(0))
+    with multiprocessing.get_context("fork").Pool(min(len(cores), B)) as pool:
+        made = pool.map(_realign_bin_worker, jobs)
+    the_bins = [bins.Bin(*m) for m in made]
+    tls = [Tls.make(mn=int(2.0 * L), mx=int(3.4 * L) + 120, median=int(2.6 * L) + 60)]
+    options = [bins.RealignOptions(b.bin_start, b.bin_end, tls, clip_semialigned=True) for b in the_bins]
+    entries = sum(len(b.index) for b in the_bins)
+    records = sum(len(b.record_offset) for b in the_bins)
+    data_bytes = sum(int(b.data.size) for b in the_bins)
+    workload = {"workload": "build::GapRealigner over %d bins of one contig: %d index entries / %d records / %d MB per step, 2x%d bp pairs at ~20x from a "
+                            "haplotype with an indel or SNP every ~300 bases, --clip-semialigned, costs 3/4/0" % (B, entries, records, data_bytes >> 20, L),
+                "l2": "each bin's records are uploaded fresh and read once"}
+
+    def reference_pass(threads):
+        import oracle_lib
+        ref = oracle_lib.require_reference() if False else oracle_lib.reference()
+        if ref is None:
+            return None
+        holder = oracle_lib.GenomeHolder(genome)
+        out = [None] * B
+        import threading
+        lock = threading.Lock()
+        todo = list(range(B))
+
+        def work():
+            while True:
+                with lock:
+                    if not todo:
+                        return
+                    k = todo.pop()
+                out[k] = oracle_lib.realign_bin(ref, holder, the_bins[k], options[k])
+        oracle_lib.realign_bin(ref, holder, the_bins[0], options[0])          # the contig copy of the checker is made outside the timing
+        t0 = time.perf_counter()
+        pool = [threading.Thread(target=work) for _ in range(min(threads, B))]
+        for t in pool:
+            t.start()
+        for t in pool:
+            t.join()
+        return out, time.perf_counter() - t0, min(threads, B)
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if args.impl == "reference":
+        done = reference_pass(len(cores))
+        if done is None:
+            emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libisaac_ref.so did not travel"}))
+            return
+        times = []
+        for _ in range(max(1, args.steps)):
+            _, sec, used = reference_pass(len(cores))
+            times.append(sec)
+        sec = float(np.mean(times))
+        emit(json.dumps({"impl": "reference", "metric": "gap_realigner_fragments_per_s", "value": entries / sec, "unit": "fragments/s", "n_gpus": 1,
+                          "steps": args.steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u8", "data": "synthetic", "config": workload,
+                          "cpu_baseline": {"value": entries / sec, "unit": "fragments/s", "cores": used, "kind": "reference",
+                                           "sample": "every bin of the step, one bin per host thread"},
+                          "e2e": {"value": entries / sec, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the gap realigner has no CPU fallback")
+    from isaac_aligner_b200 import capi
+    bind_to_gpu_numa(0)
+    ctx = capi.Context(Config.default(max_read_length=2 * L))
+    ctx.set_reference(genome)
+    lib = capi._lib
+    # page-locked working copies: a step starts from the original records every time (the call updates them in place)
+    work = [torch.empty(int(b.data.size), dtype=torch.uint8).pin_memory() for b in the_bins]
+    offs = [torch.from_numpy(np.ascontiguousarray(b.record_offset, dtype=np.uint64).view(np.int64)).pin_memory() for b in the_bins]
+    idx = [torch.from_numpy(np.ascontiguousarray(b.index).view(np.int64).reshape(-1)).pin_memory() for b in the_bins]
+    results = [bins.RealignResultC() for _ in the_bins]
+
+    def step(collect=None):
+        for k, b in enumerate(the_bins):
+            work[k].numpy()[:] = b.data
+        device_ms = 0.0
+        t0 = time.perf_counter()
+        for k, b in enumerate(the_bins):
+            ctx._check(lib.isaac_ext_realign_bin(ctx._h, ctypes.byref(options[k].c), ctypes.c_void_p(work[k].data_ptr()), ctypes.c_uint64(b.data.size),
+                                                 ctypes.c_void_p(offs[k].data_ptr()), ctypes.c_uint64(len(b.record_offset)),
+                                                 ctypes.c_void_p(idx[k].data_ptr()), ctypes.c_uint64(len(b.index)), ctypes.byref(results[k])))
+            device_ms += float(results[k].collectMs) + float(results[k].realignMs)
+            if collect is not None:
+                n = len(b.index)
+                collect.append((np.frombuffer((ctypes.c_char * (8 * n)).from_address(results[k].position), dtype=np.uint64).copy(),
+                                work[k].numpy().copy(), int(results[k].realignedFragments)))
+        return (time.perf_counter() - t0) * 1e3, device_ms
+
+    sampler = ClockSampler(0)
+    for _ in range(max(3, args.warmup)):
+        step()
+    launches0 = ctx.launches
+    t_wall0 = time.time()
+    call_ms, dev_ms = [], []
+    for _ in range(args.steps):
+        c, d = step()
+        call_ms.append(c); dev_ms.append(d)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    launches = ctx.launches - launches0
+    got = []
+    step(got)
+    realigned = sum(g[2] for g in got)
+    cm, dm = float(np.mean(call_ms)), float(np.mean(dev_ms))
+    line = {"metric": "gap_realigner_fragments_per_s", "value": entries / (dm * 1e-3), "unit": "fragments/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": dm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload,
+            "e2e": {"value": entries / (cm * 1e-3), "unit": "fragments/s", "ms_per_step": cm, "h2d_bytes_per_step": int(data_bytes + 8 * records + 16 * entries),
+                    "d2h_bytes_per_step": int(16 * entries + 56 * 2 * realigned + 4 * sum(int(r.realignedCigarWords) for r in results) +
+                                              16 * sum(int(r.gapCount) + int(r.deletionCount) for r in results)),
+                    "api": "isaac_ext_realign_bin per bin, page-locked host buffers; of the records only the rewritten headers come back"},
+            "gpu_launches": int(launches), "clocks": clocks, "realigned_fragments": int(realigned)}
+    hbm_peak, hbm_src = 6545.6, "fallback"
+    try:
+        hbm_peak, hbm_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except (OSError, KeyError, ValueError):
+        pass
+    achieved = (2 * data_bytes + 8 * records + 32 * entries) / (dm * 1e-3) / 1e9
+    line["roofline"] = {"bound": "hbm", "kernel": "realignBinKernel (+ the collectGaps passes)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src, "ms_per_launch": dm,
+                        "note": "algorithmic bytes = the records read by collectGaps and by realign, offsets, index and results; the kernel is bound by the "
+                                "divergent per-fragment search over gap combinations, not by HBM"}
+    done = reference_pass(len(cores))
+    if done is not None:
+        want, sec, used = done
+        for k in range(B):
+            assert np.array_equal(got[k][0], want[k].position) and np.array_equal(got[k][1], want[k].data), "GPU and reference differ in bin %d" % k
+        line["cpu_baseline"] = {"value": entries / sec, "unit": "fragments/s", "cores": used, "kind": "reference",
+                                "sample": "every bin of the step through the reference's own GapRealigner, one bin per host thread, %.2f s; "
+                                          "records and positions equal the GPU's" % sec}
+    emit(json.dumps(line))
+    ctx.close()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.workload == "wide":
+    if a.workload == "realign":
+        run_realign(a)
+    elif a.workload == "wide":
         run_wide(a)
     elif a.workload == "pack":
         run_pack(a)

@@ -17,15 +17,16 @@
 
 struct RealignState
 {
-    DeviceBuffer<uint8_t> dData, dTemp;
-    DeviceBuffer<uint64_t> dRecordOffset, dPosition;
+    DeviceBuffer<uint8_t> dData, dTemp, dChangedHeader;
+    DeviceBuffer<uint64_t> dRecordOffset, dPosition, dChangedOffset;
     DeviceBuffer<isaac_ext_bin_index_t> dIndex;
     DeviceBuffer<uint32_t> dGapsOfRecord, dGapBegin, dRecordIndex, dCigarOffset, dCigarLength, dCigarPool, dGroupBegin, dBarcodeGapGroup, dCounters;
     DeviceBuffer<GapRecord> dGapsRaw, dGaps, dDeletions;
     DeviceBuffer<isaac_ext_tls_t> dTls;
     DeviceBuffer<unsigned long long> dLongCounters;
     HostBuffer<uint64_t> walked;
-    PinnedBuffer<uint64_t> hPosition;
+    PinnedBuffer<uint64_t> hPosition, hChangedOffset;
+    PinnedBuffer<uint8_t> hChangedHeader;
     PinnedBuffer<uint32_t> hCigarOffset, hCigarLength, hCigarPool, hCounters;
     PinnedBuffer<GapRecord> hGaps, hDeletions;
     PinnedBuffer<unsigned long long> hLongCounters;
@@ -36,7 +37,7 @@ struct RealignState
         dData.release(); dTemp.release(); dRecordOffset.release(); dPosition.release(); dIndex.release(); dGapsOfRecord.release();
         dGapBegin.release(); dRecordIndex.release(); dCigarOffset.release(); dCigarLength.release(); dCigarPool.release();
         dGroupBegin.release(); dBarcodeGapGroup.release(); dCounters.release(); dGapsRaw.release(); dGaps.release(); dDeletions.release();
-        dTls.release(); dLongCounters.release();
+        dTls.release(); dLongCounters.release(); dChangedHeader.release(); dChangedOffset.release(); hChangedOffset.release(); hChangedHeader.release();
         hPosition.release(); hCigarOffset.release(); hCigarLength.release(); hCigarPool.release(); hCounters.release(); hGaps.release();
         hDeletions.release(); hLongCounters.release();
     }
@@ -68,6 +69,7 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     RealignState &st = *ctx->realign;
     for (cudaEvent_t &e : st.ev) if (!e) CK(cudaEventCreate(&e));
     cudaStream_t s = ctx->stream;
+    PhaseTimer timer("realign_bin");
 
     // ---- the records of the bin: the caller's offsets, or the chain of FragmentHeader::getTotalLength walked here
     if (!recordOffset)
@@ -83,20 +85,8 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
         for (uint64_t p = 0; p < dataBytes; p += binRecordLength(data + p)) st.walked.p[n++] = p;
         recordOffset = st.walked.p; recordCount = n;
     }
-    // every record and every index entry inside the data (the kernels trust them after this)
-    {
-        std::atomic<int> bad(0);
-        parallelRanges(ctx->hostThreads, recordCount, [&](unsigned, size_t b, size_t e) {
-            for (size_t r = b; r < e; ++r)
-                if (recordOffset[r] + BIN_HEADER_BYTES > dataBytes || recordOffset[r] + binRecordLength(data + recordOffset[r]) > dataBytes) bad = 1;
-        });
-        parallelRanges(ctx->hostThreads, indexCount, [&](unsigned, size_t b, size_t e) {
-            for (size_t i = b; i < e; ++i)
-                for (const uint64_t o : {index[i].dataOffset, index[i].mateDataOffset})
-                    if (o + BIN_HEADER_BYTES > dataBytes || o + binRecordLength(data + o) > dataBytes) bad = 1;
-        });
-        if (bad) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "a record or an index entry lies outside the bin's data");
-    }
+    // whether every record and every index entry lies inside the data is checked by the first kernel that touches them
+    timer.mark("validate");
     uint32_t groups = 1;
     if (options->barcodeGapGroup)
         for (uint32_t b = 0; b < options->barcodeCount; ++b) groups = std::max(groups, options->barcodeGapGroup[b] + 1);
@@ -105,8 +95,8 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     CK(st.dData.reserve(dataBytes + 8)); CK(st.dRecordOffset.reserve(recordCount + 1)); CK(st.dIndex.reserve(indexCount + 1));
     CK(st.dGapsOfRecord.reserve(recordCount + 1)); CK(st.dGapBegin.reserve(recordCount + 1));
     CK(st.dTls.reserve(options->barcodeCount)); CK(st.dBarcodeGapGroup.reserve(options->barcodeCount));
-    CK(st.dCounters.reserve(8)); CK(st.dLongCounters.reserve(2)); CK(st.dGroupBegin.reserve(2 * (size_t(groups) + 1)));
-    CK(st.hCounters.reserve(8)); CK(st.hLongCounters.reserve(2));
+    CK(st.dCounters.reserve(8)); CK(st.dLongCounters.reserve(4)); CK(st.dGroupBegin.reserve(2 * (size_t(groups) + 1)));
+    CK(st.hCounters.reserve(8)); CK(st.hLongCounters.reserve(4));
     if (dataBytes) CK(cudaMemcpyAsync(st.dData.p, data, dataBytes, cudaMemcpyHostToDevice, s));
     if (recordCount) CK(cudaMemcpyAsync(st.dRecordOffset.p, recordOffset, recordCount * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     if (indexCount) CK(cudaMemcpyAsync(st.dIndex.p, index, indexCount * sizeof(isaac_ext_bin_index_t), cudaMemcpyHostToDevice, s));
@@ -114,7 +104,7 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     if (options->barcodeGapGroup)
         CK(cudaMemcpyAsync(st.dBarcodeGapGroup.p, options->barcodeGapGroup, options->barcodeCount * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(st.dCounters.p, 0, 8 * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(st.dLongCounters.p, 0, 2 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(st.dLongCounters.p, 0, 4 * sizeof(unsigned long long), s));
 
     // ---- BinSorter::collectGaps
     CK(cudaEventRecord(st.ev[0], s));
@@ -122,7 +112,7 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     uint32_t rawGaps = 0;
     if (recordCount)
     {
-        countRecordGapsKernel<<<gridFor(ctx, recordCount, 256, 16), 256, 0, s>>>(st.dData.p, st.dRecordOffset.p, recordCount, st.dGapsOfRecord.p,
+        countRecordGapsKernel<<<gridFor(ctx, recordCount, 256, 16), 256, 0, s>>>(st.dData.p, dataBytes, st.dRecordOffset.p, recordCount, st.dGapsOfRecord.p,
                                                                                 options->barcodeCount, st.dCounters.p + RC_ERRORS);
         ++ctx->launches;
         CK(cudaGetLastError());
@@ -136,6 +126,7 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
         CK(cudaStreamSynchronize(s));
         rawGaps = st.hCounters.p[0];
     }
+    timer.mark("upload + count gaps");
     CK(st.dGapsRaw.reserve(size_t(rawGaps) + 1)); CK(st.dGaps.reserve(size_t(rawGaps) + 1)); CK(st.dDeletions.reserve(size_t(rawGaps) + 1));
     if (rawGaps)
     {
@@ -198,10 +189,12 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     CK(cudaGetLastError());
     if (groups > 255) return ctx->fail(ISAAC_EXT_E_UNSUPPORTED, "more than 255 gap groups");
     CK(cudaEventRecord(st.ev[1], s));
+    timer.mark("sort gaps");
 
     // ---- BinSorter::realignGaps
     CK(st.dRecordIndex.reserve((dataBytes >> 6) + 2)); CK(st.dPosition.reserve(indexCount + 1));
     CK(st.dCigarOffset.reserve(indexCount + 1)); CK(st.dCigarLength.reserve(indexCount + 1));
+    CK(st.dChangedOffset.reserve(2 * indexCount + 2)); CK(st.dChangedHeader.reserve((2 * indexCount + 2) * REALIGN_CHANGED_STRIDE));
     CK(st.hPosition.reserve(indexCount + 1)); CK(st.hCigarOffset.reserve(indexCount + 1)); CK(st.hCigarLength.reserve(indexCount + 1));
     uint64_t poolCapacity = std::max<uint64_t>(st.dCigarPool.capacity, indexCount * 8 + 4096);
     float realignMs = 0.0f;
@@ -209,9 +202,9 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     {
         CK(st.dCigarPool.reserve(poolCapacity));
         CK(cudaMemsetAsync(st.dRecordIndex.p, 0xFF, ((dataBytes >> 6) + 2) * sizeof(uint32_t), s));
-        CK(cudaMemsetAsync(st.dLongCounters.p, 0, 2 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(st.dLongCounters.p, 0, 4 * sizeof(unsigned long long), s));
         RealignBinView v{};
-        v.data = st.dData.p; v.index = st.dIndex.p; v.indexCount = indexCount; v.recordIndex = st.dRecordIndex.p;
+        v.data = st.dData.p; v.dataBytes = dataBytes; v.index = st.dIndex.p; v.indexCount = indexCount; v.recordIndex = st.dRecordIndex.p;
         v.gaps = reinterpret_cast<const isaac_ext_gap_t *>(st.dGaps.p); v.gapGroupBegin = st.dGroupBegin.p;
         v.deletions = reinterpret_cast<const isaac_ext_gap_t *>(st.dDeletions.p); v.deletionGroupBegin = st.dGroupBegin.p + groups + 1;
         v.barcodeGapGroup = options->barcodeGapGroup ? st.dBarcodeGapGroup.p : nullptr; v.barcodeTls = st.dTls.p; v.barcodeCount = options->barcodeCount;
@@ -222,20 +215,22 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
         v.position = st.dPosition.p; v.cigarOffset = st.dCigarOffset.p; v.cigarLength = st.dCigarLength.p;
         v.cigarPool = st.dCigarPool.p; v.cigarPoolUsed = st.dLongCounters.p; v.cigarPoolCapacity = poolCapacity;
         v.realignedFragments = st.dLongCounters.p + 1; v.errorFlags = st.dCounters.p + RC_ERRORS;
+        v.changedOffset = st.dChangedOffset.p; v.changedHeader = st.dChangedHeader.p; v.changedCount = st.dLongCounters.p + 2;
         CK(cudaEventRecord(st.ev[2], s));
         if (indexCount)
         {
-            recordIndexKernel<<<gridFor(ctx, indexCount, 256, 16), 256, 0, s>>>(st.dIndex.p, indexCount, st.dRecordIndex.p);
+            recordIndexKernel<<<gridFor(ctx, indexCount, 256, 16), 256, 0, s>>>(st.dData.p, dataBytes, st.dIndex.p, indexCount, st.dRecordIndex.p, st.dCounters.p + RC_ERRORS);
             realignBinKernel<<<unsigned((indexCount + 127) / 128), 128, 0, s>>>(v);
             ctx->launches += 2;
             CK(cudaGetLastError());
         }
         CK(cudaEventRecord(st.ev[3], s));
         CK(cudaMemcpyAsync(st.hCounters.p, st.dCounters.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(st.hLongCounters.p, st.dLongCounters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(st.hLongCounters.p, st.dLongCounters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         const int rcSync = ctx->cuda(cudaStreamSynchronize(s), "realignBinKernel");
         if (rcSync) return rcSync;
         CK(cudaEventElapsedTime(&realignMs, st.ev[2], st.ev[3]));
+        timer.mark("realign");
         const uint32_t errors = st.hCounters.p[RC_ERRORS];
         if ((errors & REALIGN_ERROR_POOL) && attempt == 0)
         {
@@ -246,6 +241,7 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
             CK(cudaMemsetAsync(st.dCounters.p + RC_ERRORS, 0, sizeof(uint32_t), s));
             continue;
         }
+        if (errors & REALIGN_ERROR_BOUNDS) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "a record or an index entry lies outside the bin's data");
         if (errors & REALIGN_ERROR_BARCODE) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "a record names a barcode outside the barcode tables");
         if (errors & REALIGN_ERROR_UNSUPPORTED_RECORD) return ctx->fail(ISAAC_EXT_E_UNSUPPORTED, "a record has more than 512 bases or a CIGAR of more than 64 operations");
         if (errors & REALIGN_ERROR_OVERLAPS) return ctx->fail(ISAAC_EXT_E_UNSUPPORTED, "more than 30 groups of overlapping gaps around one fragment (the reference asserts)");
@@ -256,7 +252,14 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     const uint64_t words = st.hLongCounters.p[0];
     const uint32_t uniqueGaps = st.hCounters.p[RC_GAPS], deletions = st.hCounters.p[RC_DELETIONS];
     CK(st.hCigarPool.reserve(words + 1)); CK(st.hGaps.reserve(size_t(uniqueGaps) + 1)); CK(st.hDeletions.reserve(size_t(deletions) + 1));
-    if (dataBytes) CK(cudaMemcpyAsync(data, st.dData.p, dataBytes, cudaMemcpyDeviceToHost, s));
+    // of the records only the headers a call rewrote travel back: offset + leading bytes, scattered into the caller's data below
+    const uint64_t changed = st.hLongCounters.p[2];
+    CK(st.hChangedOffset.reserve(changed + 1)); CK(st.hChangedHeader.reserve((changed + 1) * REALIGN_CHANGED_STRIDE));
+    if (changed)
+    {
+        CK(cudaMemcpyAsync(st.hChangedOffset.p, st.dChangedOffset.p, changed * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(st.hChangedHeader.p, st.dChangedHeader.p, changed * REALIGN_CHANGED_STRIDE, cudaMemcpyDeviceToHost, s));
+    }
     if (indexCount)
     {
         CK(cudaMemcpyAsync(st.hPosition.p, st.dPosition.p, indexCount * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
@@ -267,6 +270,13 @@ extern "C" int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign
     if (uniqueGaps) CK(cudaMemcpyAsync(st.hGaps.p, st.dGaps.p, size_t(uniqueGaps) * sizeof(GapRecord), cudaMemcpyDeviceToHost, s));
     if (deletions) CK(cudaMemcpyAsync(st.hDeletions.p, st.dDeletions.p, size_t(deletions) * sizeof(GapRecord), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    for (uint64_t c = 0; c < changed; ++c)
+    {
+        // the targets are scattered over the whole bin: ask for the lines a few records ahead
+        if (c + 16 < changed) __builtin_prefetch(data + st.hChangedOffset.p[c + 16], 1);
+        std::memcpy(data + st.hChangedOffset.p[c], st.hChangedHeader.p + c * REALIGN_CHANGED_STRIDE, REALIGN_CHANGED_BYTES);
+    }
+    timer.mark("download");
     result->position = st.hPosition.p; result->cigarOffset = st.hCigarOffset.p; result->cigarLength = st.hCigarLength.p;
     result->realignedCigars = st.hCigarPool.p; result->realignedCigarWords = words; result->realignedFragments = st.hLongCounters.p[1];
     result->gaps = reinterpret_cast<const isaac_ext_gap_t *>(st.hGaps.p); result->deletionsByEnd = reinterpret_cast<const isaac_ext_gap_t *>(st.hDeletions.p);

@@ -41,12 +41,20 @@ struct GapByDeletionEnd
 };
 struct GapIsDeletion { __host__ __device__ bool operator()(const GapRecord &g) const { return g.length > 0; } };
 
+/// does the record at 'offset' lie inside the bin's data, header and all?
+__device__ __forceinline__ bool recordInside(const uint8_t *data, const uint64_t dataBytes, const uint64_t offset)
+{
+    return offset + BIN_HEADER_BYTES <= dataBytes && offset + binRecordLength(data + offset) <= dataBytes;
+}
+
 /// insertions and deletions in the CIGAR of every record that says it has gaps (BinSorter.cpp:391-400)
-__global__ void countRecordGapsKernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ recordOffset, const uint64_t recordCount,
-                                      uint32_t *__restrict__ gapsOfRecord, const uint32_t barcodeCount, uint32_t *__restrict__ errorFlags)
+__global__ void countRecordGapsKernel(const uint8_t *__restrict__ data, const uint64_t dataBytes, const uint64_t *__restrict__ recordOffset,
+                                      const uint64_t recordCount, uint32_t *__restrict__ gapsOfRecord, const uint32_t barcodeCount,
+                                      uint32_t *__restrict__ errorFlags)
 {
     for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < recordCount; r += uint64_t(gridDim.x) * blockDim.x)
     {
+        if (!recordInside(data, dataBytes, recordOffset[r])) { atomicOr(errorFlags, REALIGN_ERROR_BOUNDS); gapsOfRecord[r] = 0; continue; }
         const uint8_t *record = data + recordOffset[r];
         uint32_t n = 0;
         if (binGet16(record + BIN_GAP_COUNT))
@@ -69,7 +77,7 @@ __global__ void writeRecordGapsKernel(const uint8_t *__restrict__ data, const ui
 {
     for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < recordCount; r += uint64_t(gridDim.x) * blockDim.x)
     {
-        if (!gapsOfRecord[r]) continue;
+        if (!gapsOfRecord[r]) continue;                                        // also every record that failed the bounds check
         const uint8_t *record = data + recordOffset[r];
         const uint64_t barcode = binGet64(record + BIN_BARCODE);
         const uint32_t group = (barcodeGapGroup && barcode < barcodeCount) ? barcodeGapGroup[barcode] : 0u;
@@ -104,15 +112,25 @@ __global__ void deletionEndTiesKernel(const GapRecord *__restrict__ byEnd, const
         if (byEnd[i].group == byEnd[i + 1].group && GapByDeletionEnd::end(byEnd[i]) == GapByDeletionEnd::end(byEnd[i + 1])) atomicAdd(ties, 1u);
 }
 
-__global__ void recordIndexKernel(const isaac_ext_bin_index_t *__restrict__ index, const uint64_t indexCount, uint32_t *__restrict__ recordIndex)
+/// also the bounds check of the index entries: the realign kernel runs only when no entry points outside the data
+__global__ void recordIndexKernel(const uint8_t *__restrict__ data, const uint64_t dataBytes, const isaac_ext_bin_index_t *__restrict__ index,
+                                  const uint64_t indexCount, uint32_t *__restrict__ recordIndex, uint32_t *__restrict__ errorFlags)
 {
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < indexCount; i += uint64_t(gridDim.x) * blockDim.x)
+    {
+        if (!recordInside(data, dataBytes, index[i].dataOffset) || !recordInside(data, dataBytes, index[i].mateDataOffset))
+        {
+            atomicOr(errorFlags, REALIGN_ERROR_BOUNDS);
+            continue;
+        }
         recordIndex[index[i].dataOffset >> 6] = uint32_t(i);
+    }
 }
 
 __global__ void __launch_bounds__(128)
 realignBinKernel(const RealignBinView v)
 {
+    if (*v.errorFlags & REALIGN_ERROR_BOUNDS) return;                         // set by the passes before this one
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
     if (i < v.indexCount) realignTemplate(v, i);
 }

@@ -53,7 +53,8 @@ enum : uint32_t
     REALIGN_ERROR_POOL = 2,                 // the realigned CIGAR pool is full
     REALIGN_ERROR_OVERLAPS = 4,             // more than REALIGN_MAX_OVERLAPS overlap groups (the reference's FiniteCapacityVector asserts)
     REALIGN_ERROR_CIGAR = 8,                // a CIGAR under construction outgrew REALIGN_CIGAR_CAP / an unexpected operation / no mapped base
-    REALIGN_ERROR_BARCODE = 16              // FragmentHeader::barcode_ outside the barcode tables
+    REALIGN_ERROR_BARCODE = 16,             // FragmentHeader::barcode_ outside the barcode tables
+    REALIGN_ERROR_BOUNDS = 32               // a record or an index entry lies outside the bin's data
 };
 
 /// byte offsets of io::FragmentHeader (Fragment.hh:260-404, checked against the reference's struct by tests/test_tile_write_bin_records.py)
@@ -102,7 +103,7 @@ struct RealignGap
 /// the CPU harness
 struct RealignBinView
 {
-    uint8_t *data;                               // the bin's records
+    uint8_t *data; uint64_t dataBytes;           // the bin's records
     const isaac_ext_bin_index_t *index; uint64_t indexCount;
     const uint32_t *recordIndex;                 // index entry of the record at byte offset o: recordIndex[o >> 6], 0xFFFFFFFF = not indexed
     const isaac_ext_gap_t *gaps;                 // gapGroups_ of every group back to back: by group, start, signed length; unique
@@ -120,7 +121,11 @@ struct RealignBinView
     uint32_t *cigarPool; unsigned long long *cigarPoolUsed; uint64_t cigarPoolCapacity;
     unsigned long long *realignedFragments;
     uint32_t *errorFlags;
+    // the records a call updated: byte offset + the REALIGN_CHANGED_BYTES leading header bytes that hold every field store() writes,
+    // so that only those travel back to the host (null in the CPU harness, which works on the caller's bytes directly)
+    uint64_t *changedOffset; uint8_t *changedHeader; unsigned long long *changedCount;
 };
+constexpr unsigned REALIGN_CHANGED_BYTES = 42, REALIGN_CHANGED_STRIDE = 48;
 
 ISAAC_HD inline void realignFlag(const RealignBinView &v, const uint32_t bit)
 {
@@ -990,14 +995,27 @@ ISAAC_HD inline void realignTemplate(const RealignBinView &v, const uint64_t i)
     // the positions the index holds are the records' as they were loaded: the second entry's must be taken before the first call
     // may move a shadow (updatePairDetails)
     const int64_t secondLoadedPos = hasMate ? second.fStrandPosition : 0;
-    const bool firstChanged = run(i, first, hasMate ? &second : nullptr);
-    if (firstChanged) { first.store(); if (hasMate) second.store(); }
+    bool changed = run(i, first, hasMate ? &second : nullptr);
     if (mateEntry != 0xFFFFFFFFu)
     {
         // the mate's own call sees the record as the first call left it; its Index::pos_ is the loaded one until realign() refreshes it
         const bool secondChanged = run(mateEntry, second, &first);
-        if (secondChanged) { second.store(); first.store(); }
-        else if (second.flags & BIN_FLAG_UNMAPPED) v.position[mateEntry] = realignValue(secondLoadedPos);
+        changed |= secondChanged;
+        if (!secondChanged && (second.flags & BIN_FLAG_UNMAPPED)) v.position[mateEntry] = realignValue(secondLoadedPos);
+    }
+    if (!changed) return;
+    first.store();
+    if (hasMate) second.store();
+    if (v.changedCount)
+    {
+        const unsigned n = hasMate ? 2u : 1u;
+        const unsigned long long at = realignTake(v.changedCount, n);
+        for (unsigned k = 0; k < n; ++k)
+        {
+            const RealignFragment &f = k ? second : first;
+            v.changedOffset[at + k] = uint64_t(f.record - v.data);
+            for (unsigned b = 0; b < REALIGN_CHANGED_BYTES; ++b) v.changedHeader[(at + k) * REALIGN_CHANGED_STRIDE + b] = f.record[b];
+        }
     }
 }
 

@@ -97,7 +97,7 @@ extern "C" int realign_bin_host(uint32_t contigCount, const char *bases, const u
     unsigned long long poolUsed = 0, realigned = 0;
     uint32_t errors = 0;
     RealignBinView v{};
-    v.data = data; v.index = index; v.indexCount = indexCount; v.recordIndex = recordIndex.data();
+    v.data = data; v.dataBytes = dataBytes; v.index = index; v.indexCount = indexCount; v.recordIndex = recordIndex.data();
     v.gaps = gaps.data(); v.gapGroupBegin = gapGroupBegin.data(); v.deletions = deletions.data(); v.deletionGroupBegin = deletionGroupBegin.data();
     v.barcodeGapGroup = o->barcodeGapGroup; v.barcodeTls = o->barcodeTls; v.barcodeCount = o->barcodeCount;
     v.ref = reference.view;
