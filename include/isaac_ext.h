@@ -628,6 +628,32 @@ int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign_options_t 
                           const uint64_t *recordOffset, uint64_t recordCount, const isaac_ext_bin_index_t *index,
                           uint64_t indexCount, isaac_ext_realign_result_t *result);
 
+/* Several bins in one call (BinSorter::process runs on a pool of threads, one bin each): the jobs are taken in turn by two slots of
+ * the context, each with its own stream, so that the upload of one bin runs next to the kernels and the download of the other.
+ * Everything a job names is the caller's memory (page-locked memory makes the copies asynchronous): data is updated in place like
+ * isaac_ext_realign_bin does; position / cigarOffset / cigarLength hold indexCount entries; realignedCigars has room for
+ * realignedCigarCapacity words (8 + 2 per index entry is ample; a job whose CIGARs do not fit ends with ISAAC_EXT_E_CAPACITY).
+ * status is the job's own result; the call returns the first status that is not ISAAC_EXT_OK. */
+typedef struct isaac_ext_realign_job {
+    const isaac_ext_realign_options_t *options;
+    uint8_t *data;
+    uint64_t dataBytes;
+    const uint64_t *recordOffset;     /* or NULL */
+    uint64_t recordCount;
+    const isaac_ext_bin_index_t *index;
+    uint64_t indexCount;
+    uint64_t *position;               /* out */
+    uint32_t *cigarOffset;            /* out */
+    uint32_t *cigarLength;            /* out */
+    uint32_t *realignedCigars;        /* out */
+    uint64_t realignedCigarCapacity;
+    uint64_t realignedCigarWords;     /* out */
+    uint64_t realignedFragments;      /* out */
+    int32_t  status;                  /* out */
+    uint32_t pad;
+} isaac_ext_realign_job_t;
+int isaac_ext_realign_bins(isaac_ext_ctx *ctx, isaac_ext_realign_job_t *jobs, uint32_t jobCount);
+
 /* Integer-pipe throughput probe used as the roofline denominator of the Smith-Waterman kernel (operations per
  * second over the whole chip).  kind 0: 32-bit add, 1: 32-bit max, 2: packed 16x2 max counted as two operations. */
 int isaac_ext_measure_int32_peak(isaac_ext_ctx *ctx, int kind, double *opsPerSecond);

@@ -50,6 +50,15 @@ class RealignResultC(ctypes.Structure):
                 ("deletionCount", ctypes.c_uint64), ("collectMs", ctypes.c_float), ("realignMs", ctypes.c_float)]
 
 
+class RealignJobC(ctypes.Structure):
+    """isaac_ext_realign_job_t"""
+    _fields_ = [("options", ctypes.c_void_p), ("data", ctypes.c_void_p), ("dataBytes", ctypes.c_uint64), ("recordOffset", ctypes.c_void_p),
+                ("recordCount", ctypes.c_uint64), ("index", ctypes.c_void_p), ("indexCount", ctypes.c_uint64), ("position", ctypes.c_void_p),
+                ("cigarOffset", ctypes.c_void_p), ("cigarLength", ctypes.c_void_p), ("realignedCigars", ctypes.c_void_p),
+                ("realignedCigarCapacity", ctypes.c_uint64), ("realignedCigarWords", ctypes.c_uint64), ("realignedFragments", ctypes.c_uint64),
+                ("status", ctypes.c_int32), ("pad", ctypes.c_uint32)]
+
+
 class RealignOptions:
     """keeps the arrays the C struct points to alive"""
 

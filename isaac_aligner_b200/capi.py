@@ -38,7 +38,7 @@ EXPORTS = [
     "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
     "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed", "isaac_ext_prefetch_reads", "isaac_ext_prefetch_batch", "isaac_ext_tile_cycle_stats", "isaac_ext_tile_cycle_stats_finalize",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
-    "isaac_ext_realign_bin",
+    "isaac_ext_realign_bin", "isaac_ext_realign_bins",
 ]
 
 
@@ -346,6 +346,35 @@ class Context:
                                   arr(res.realignedCigars, np.uint32, int(res.realignedCigarWords)), arr(res.gaps, bins.GAP_DTYPE, int(res.gapCount)),
                                   arr(res.deletionsByEnd, bins.GAP_DTYPE, int(res.deletionCount)), int(res.realignedFragments),
                                   float(res.collectMs), float(res.realignMs))
+
+    def realign_bins(self, bin_list, options_list):
+        """isaac_ext_realign_bins: every bin of the list in one call (two slots of the context take them in turn); returns one
+        bins.RealignResult per bin (without the gap lists, which only the single-bin call hands out)"""
+        from . import bins
+        n = len(bin_list)
+        jobs = (bins.RealignJobC * n)()
+        keep = []
+        for k, (b, o) in enumerate(zip(bin_list, options_list)):
+            data = np.ascontiguousarray(b.data).copy()
+            offsets = np.ascontiguousarray(b.record_offset, dtype=np.uint64) if b.record_offset is not None else None
+            index = np.ascontiguousarray(b.index)
+            m = index.size
+            position, cigar_offset, cigar_length = np.zeros(m, np.uint64), np.zeros(m, np.uint32), np.zeros(m, np.uint32)
+            cigars = np.zeros(16 * m + 64, np.uint32)
+            keep.append((data, offsets, index, position, cigar_offset, cigar_length, cigars))
+            j = jobs[k]
+            j.options = ctypes.addressof(o.c)
+            j.data, j.dataBytes = data.ctypes.data if data.size else None, data.size
+            j.recordOffset, j.recordCount = (offsets.ctypes.data if offsets is not None and offsets.size else None), (offsets.size if offsets is not None else 0)
+            j.index, j.indexCount = index.ctypes.data if m else None, m
+            j.position, j.cigarOffset, j.cigarLength = position.ctypes.data, cigar_offset.ctypes.data, cigar_length.ctypes.data
+            j.realignedCigars, j.realignedCigarCapacity = cigars.ctypes.data, cigars.size
+        self._check(_lib.isaac_ext_realign_bins(self._h, jobs, ctypes.c_uint32(n)))
+        out = []
+        for k, (data, offsets, index, position, cigar_offset, cigar_length, cigars) in enumerate(keep):
+            out.append(bins.RealignResult(data, position, cigar_offset, cigar_length, cigars[:int(jobs[k].realignedCigarWords)], None, None,
+                                          int(jobs[k].realignedFragments)))
+        return out
 
     def _packed(self, res, compact=False):
         from .batch import PackedFragments

@@ -37,8 +37,8 @@ struct AsyncState;                     // isaac_ext_async.cuh
 void releaseAsync(AsyncState *state);
 struct SelectState;                    // isaac_ext_select.cuh
 void releaseSelect(SelectState *state);
-struct RealignState;                   // isaac_ext_realign.cuh
-void releaseRealign(RealignState *state);
+struct RealignSlots;                   // isaac_ext_realign.cuh
+void releaseRealign(RealignSlots *state);
 
 struct isaac_ext_ctx
 {
@@ -65,7 +65,7 @@ struct isaac_ext_ctx
     PackState *pack = nullptr;            // buffers of isaac_ext_pack_fragments
     AsyncState *async = nullptr;          // the call in flight between isaac_ext_submit_* and isaac_ext_wait
     SelectState *select = nullptr;        // isaac_ext_select_tile
-    RealignState *realign = nullptr;      // buffers of isaac_ext_realign_bin
+    RealignSlots *realign = nullptr;      // buffers and streams of isaac_ext_realign_bin / _bins
     double logMismatchQ40 = 0.0;  // LOG_MISMATCH_Q40 (Quality.hh:100)
 
     // score tables (host libm, Quality.cpp:34-66) and parameters

@@ -76,7 +76,7 @@ def test_python_mirrors_have_the_c_struct_sizes():
              ("isaac_ext_template_result_t", ctypes.sizeof(batch.TemplateResult)), ("isaac_ext_pack_options_t", ctypes.sizeof(batch.PackOptionsC)),
              ("isaac_ext_pack_result_t", ctypes.sizeof(batch.PackResultC)), ("isaac_ext_bin_index_t", bins.BIN_INDEX_DTYPE.itemsize),
              ("isaac_ext_gap_t", bins.GAP_DTYPE.itemsize), ("isaac_ext_realign_options_t", ctypes.sizeof(bins.RealignOptionsC)),
-             ("isaac_ext_realign_result_t", ctypes.sizeof(bins.RealignResultC))]
+             ("isaac_ext_realign_result_t", ctypes.sizeof(bins.RealignResultC)), ("isaac_ext_realign_job_t", ctypes.sizeof(bins.RealignJobC))]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = os.path.join(root, "build", "abi_sizes.c")
     os.makedirs(os.path.dirname(src), exist_ok=True)

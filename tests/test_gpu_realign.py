@@ -90,6 +90,41 @@ def test_deletions_that_end_at_the_same_base(ctx_and_contigs, ref):
     assert np.array_equal(again.data, got.data) and np.array_equal(again.deletions, got.deletions)
 
 
+def test_several_bins_in_one_call(ctx_and_contigs, ref):
+    """isaac_ext_realign_bins: two slots of the context take the bins in turn; every bin as if it had been realigned alone"""
+    from isaac_aligner_b200 import capi
+    ctx, contigs = ctx_and_contigs
+    genome = oracle_lib.GenomeHolder(contigs)
+    bin_list, options = [], []
+    for k in range(7):
+        b = bins.simulate_bin(contigs, contig=1, region=(1500 + 9000 * k, 1500 + 9000 * (k + 1)), n_pairs=400 + 700 * (k % 3), read_length=100, seed=40 + k)
+        bin_list.append(b)
+        options.append(bins.RealignOptions(b.bin_start, b.bin_end, [Tls.make()], vigorous=bool(k % 2), clip_semialigned=True))
+    empty = bins.Bin(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=bins.BIN_INDEX_DTYPE), bin_list[0].bin_start, bin_list[0].bin_end)
+    bin_list.insert(3, empty); options.insert(3, options[0])
+    got = ctx.realign_bins(bin_list, options)
+    for k, (b, o) in enumerate(zip(bin_list, options)):
+        if not len(b.index):
+            assert got[k].position.size == 0
+            continue
+        want = oracle_lib.realign_bin(ref, genome, b, o)
+        got[k].gaps, got[k].deletions = want.gaps, want.deletions           # the batched call does not hand the gap lists out
+        assert compare(b, got[k], want) == got[k].realigned
+    # a pool that is too small for one job: that job alone fails, loudly
+    jobs_small = ctx.realign_bins  # the harness sizes the pools generously; the C call with a tiny pool is exercised here
+    import ctypes
+    b, o = bin_list[0], options[0]
+    data = b.data.copy(); index = np.ascontiguousarray(b.index); m = index.size
+    pos, co, cl, cig = np.zeros(m, np.uint64), np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(4, np.uint32)
+    job = (bins.RealignJobC * 1)()
+    job[0].options = ctypes.addressof(o.c); job[0].data = data.ctypes.data; job[0].dataBytes = data.size
+    job[0].index = index.ctypes.data; job[0].indexCount = m
+    job[0].position, job[0].cigarOffset, job[0].cigarLength = pos.ctypes.data, co.ctypes.data, cl.ctypes.data
+    job[0].realignedCigars, job[0].realignedCigarCapacity = cig.ctypes.data, cig.size
+    rc = capi._lib.isaac_ext_realign_bins(ctx._h, job, ctypes.c_uint32(1))
+    assert rc == 5 and job[0].status == 5                                   # ISAAC_EXT_E_CAPACITY
+
+
 def test_argument_errors(ctx_and_contigs):
     from isaac_aligner_b200 import capi
     ctx, contigs = ctx_and_contigs
