@@ -911,11 +911,17 @@ def run_realign(args):
     from isaac_aligner_b200 import bins, synth
     from isaac_aligner_b200.batch import Tls
     from isaac_aligner_b200.types import Config
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return                                                       # the reference arm runs on rank 0 alone
     L, B, n_pairs = args.read_length, args.bins, args.bin_pairs
     span = int(n_pairs * 2 * L / 20)                                 # ~20x
     genome = synth.make_genome((span + 4000) * B + 4000, n_contigs=1, seed=synth.SEED_G5)
     contig = genome[0]
-    jobs = [(contig, (2000 + k * (span + 4000), 2000 + k * (span + 4000) + span), n_pairs, L, 900 + k) for k in range(B)]
+    # bins are independent: every rank realigns its own --bins bins of the run (weak scaling, no exchange of any kind)
+    jobs = [(contig, (2000 + k * (span + 4000), 2000 + k * (span + 4000) + span), n_pairs, L, 900 + k + 1000 * rank) for k in range(B)]
     cores = sorted(os.sched_getaffinity(0))
     with multiprocessing.get_context("fork").Pool(min(len(cores), B)) as pool:
         made = pool.map(_realign_bin_worker, jobs)
@@ -977,8 +983,13 @@ def run_realign(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the gap realigner has no CPU fallback")
     from isaac_aligner_b200 import capi
-    bind_to_gpu_numa(0)
-    ctx = capi.Context(Config.default(max_read_length=2 * L))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    bind_to_gpu_numa(local_rank)
+    cfg = Config.default(max_read_length=2 * L)
+    cfg.device = local_rank
+    ctx = capi.Context(cfg)
     ctx.set_reference(genome)
     lib = capi._lib
     # page-locked working copies: a step starts from the original records every time (the call updates them in place)
@@ -1030,7 +1041,18 @@ def run_realign(args):
                 collect.append((o_pos[k].numpy().view(np.uint64).copy(), work[k].numpy().copy(), int(jobs[k].realignedFragments)))
         return ms
 
-    sampler = ClockSampler(0)
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+
+    def over_ranks(values, op):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(t, op=op)
+        return [float(x) for x in t.tolist()]
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(3, args.warmup)):
         step()
         step_batched()
@@ -1042,26 +1064,36 @@ def run_realign(args):
         single_ms.append(c); dev_ms.append(d)
     launches = ctx.launches - launches0
     for _ in range(args.steps):
+        barrier()                                                            # every rank starts its step together (they share the host)
         call_ms.append(step_batched())
+    barrier()
     t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     got, got_batched = [], []
     step(got)
     step_batched(got_batched)
     for k in range(B):
         assert np.array_equal(got[k][0], got_batched[k][0]) and np.array_equal(got[k][1], got_batched[k][1]), "single and batched calls differ in bin %d" % k
     realigned = sum(g[2] for g in got)
-    cm, dm = float(np.mean(call_ms)), float(np.mean(dev_ms))
-    line = {"metric": "gap_realigner_fragments_per_s", "value": entries / (dm * 1e-3), "unit": "fragments/s", "n_gpus": 1, "steps": args.steps,
+    # the slowest rank counts; the fragments of all ranks are the job
+    cm, dm = over_ranks([float(np.mean(call_ms)), float(np.mean(dev_ms))], torch.distributed.ReduceOp.MAX)
+    entries_rank = entries
+    entries, realigned_all = [int(x) for x in over_ranks([entries, realigned], torch.distributed.ReduceOp.SUM)]
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        ctx.close()
+        return
+    line = {"metric": "gap_realigner_fragments_per_s", "value": entries / (dm * 1e-3), "unit": "fragments/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": dm, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": workload,
-            "e2e": {"value": entries / (cm * 1e-3), "unit": "fragments/s", "ms_per_step": cm, "h2d_bytes_per_step": int(data_bytes + 8 * records + 16 * entries),
-                    "d2h_bytes_per_step": int(16 * entries + 56 * 2 * realigned + 4 * sum(int(r.realignedCigarWords) for r in results) +
+            "e2e": {"value": entries / (cm * 1e-3), "unit": "fragments/s", "ms_per_step": cm, "h2d_bytes_per_step": int(data_bytes + 8 * records + 16 * entries_rank),
+                    "d2h_bytes_per_step": int(16 * entries_rank + 56 * 2 * realigned + 4 * sum(int(r.realignedCigarWords) for r in results) +
                                               16 * sum(int(r.gapCount) + int(r.deletionCount) for r in results)),
-                    "api": "one isaac_ext_realign_bins call per step (two slots of the context take the bins in turn), page-locked host buffers; "
+                    "api": "one isaac_ext_realign_bins call per step and GPU (three slots of the context take the bins in turn), page-locked host buffers; "
                            "of the records only the rewritten headers come back",
                     "one_bin_per_call_ms_per_step": float(np.mean(single_ms))},
-            "gpu_launches": int(launches), "clocks": clocks, "realigned_fragments": int(realigned)}
+            "gpu_launches": int(launches), "clocks": clocks, "realigned_fragments": int(realigned_all), "fragments_per_gpu": int(entries_rank)}
     hbm_peak, hbm_src = 6545.6, "fallback"
     try:
         hbm_peak, hbm_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
@@ -1077,8 +1109,8 @@ def run_realign(args):
         want, sec, used = done
         for k in range(B):
             assert np.array_equal(got[k][0], want[k].position) and np.array_equal(got[k][1], want[k].data), "GPU and reference differ in bin %d" % k
-        line["cpu_baseline"] = {"value": entries / sec, "unit": "fragments/s", "cores": used, "kind": "reference",
-                                "sample": "every bin of the step through the reference's own GapRealigner, one bin per host thread, %.2f s; "
+        line["cpu_baseline"] = {"value": entries_rank / sec, "unit": "fragments/s", "cores": used, "kind": "reference",
+                                "sample": "every bin of the step through the reference's own GapRealigner, one bin per host thread, %.2f s (the bins of rank 0); "
                                           "records and positions equal the GPU's" % sec}
     emit(json.dumps(line))
     ctx.close()
