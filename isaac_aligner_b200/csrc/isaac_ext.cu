@@ -167,6 +167,12 @@ bool swScoresSupported(int match, int mismatch, int open, int ext, unsigned maxR
         why = "BandedSmithWaterman: unsupported read length for these scores: use smaller scores or shorter reads";
         return false;
     }
+    // sw2.cuh keeps row-relative values lifted by readLength * match: twice that must fit next to the largest score
+    if (2L * long(maxReadLength) * match + long(maxReadLength) * maxScore >= 32768 - open)
+    {
+        why = "BandedSmithWaterman: match score times read length too large for the packed 16-bit kernel";
+        return false;
+    }
     if (match < 0 || mismatch > 0 || open < 0 || ext < 0 || ext > open)
     {
         why = "BandedSmithWaterman: scores must satisfy match >= 0 >= mismatch and 0 <= gapExtend <= gapOpen";

@@ -35,16 +35,26 @@ struct Sw2Consts
 {
     uint32_t negOpen32;    // (-open) * 0x10001 as a 32-bit addend
     uint32_t negExt16x2;   // (65536 - ext) in both halves, for the wrapping per-half add of VIADDMNMX
+    uint32_t negOpenRow32; // the same two for the step from one row to the next (F): (-(open + match)), 65536 - (ext + match)
+    uint32_t negExtRow16x2;
     uint32_t match32;      // match * 0x10001
     int delta;             // mismatch - match
     uint32_t init2;        // biased init (= open) in both halves
 };
 
+// Row-relative values.  Every cell of row i is kept as value - (i + 1) * match (+ a constant that keeps it non-negative, see
+// sw2Forward): the diagonal step nG = max(...) + match + t * (mismatch - match) then is one multiply-add instead of an add and a
+// multiply-add, the step from row to row (F) takes its constants less 'match', the step inside a row (E) is unchanged, and the two
+// cells a row seeds with 'init' take a register that drops by 'match' per row.  Every comparison the recurrence makes is between
+// cells of one row, so all the flags -- the only thing that leaves the kernel besides the end cell, which is also picked inside
+// one row -- are the ones the plain values give.
 __device__ __forceinline__ Sw2Consts makeSw2Consts(const SwScores s)
 {
     Sw2Consts c;
     c.negOpen32 = uint32_t(-s.open) * 0x10001u;
     c.negExt16x2 = (uint32_t(65536 - s.ext) & 0xFFFFu) * 0x10001u;
+    c.negOpenRow32 = uint32_t(-(s.open + s.match)) * 0x10001u;
+    c.negExtRow16x2 = (uint32_t(65536 - (s.ext + s.match)) & 0xFFFFu) * 0x10001u;
     c.match32 = uint32_t(s.match) * 0x10001u;
     c.delta = s.mismatch - s.match;
     c.init2 = uint32_t(s.init + 32768) * 0x10001u;
@@ -231,18 +241,23 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
                                            int (&jj)[2], unsigned (&type)[2])
 {
     const Sw2Consts c = makeSw2Consts(s);
+    const unsigned Lmax = max(LA, LB);
+    // the constant that keeps the row-relative values non-negative: the last row has dropped by Lmax * match (the host admits only
+    // scores and read lengths for which value + 32768 + Lmax * match stays below 65536, swScoresSupported)
+    const uint32_t lift = Lmax * c.match32;
+    uint32_t initRow = c.init2 + lift;                              // 'init' as the row about to be computed holds it
     uint32_t G[16], E[16], F[16], D[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { G[j] = c.init2; E[j] = c.init2; F[j] = 0x80008000u; D[j] = 0; }   // :108-114
-    G[0] = 0x80008000u;                                                                               // :115
+    for (int j = 0; j < 16; ++j) { G[j] = initRow; E[j] = initRow; F[j] = 0x80008000u + lift; D[j] = 0; }   // :108-114
+    G[0] = 0x80008000u + lift;                                                                        // :115
     // D[j] = database codes seen by lane j = db[i + 15 - j]; preload db[0..14] (:117-122)
 #pragma unroll
     for (int k = 0; k < 15; ++k) D[14 - k] = src.d2(k);
     jj[0] = int(LA) - 1; jj[1] = int(LB) - 1; type[0] = 0; type[1] = 0;
-    const unsigned Lmax = max(LA, LB);
 #pragma unroll 1
     for (unsigned i = 0; i < Lmax; ++i)
     {
+        initRow -= c.match32;
 #pragma unroll
         for (int j = 15; j > 0; --j) D[j] = D[j - 1];
         D[0] = src.d2(i + 15);
@@ -258,15 +273,15 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
             {
                 constexpr int jm = j > 0 ? j - 1 : 0;
                 mPrev = sw2MaxFlag<jm>(G[jm], E[jm], fE);
-                const uint32_t a = mPrev + c.negOpen32;
-                nF = __viaddmax_u16x2(F[jm], c.negExt16x2, a);
+                const uint32_t a = mPrev + c.negOpenRow32;
+                nF = __viaddmax_u16x2(F[jm], c.negExtRow16x2, a);
                 fAB = fAB * 2u + __vminu2(nF - a, 0x00010001u);
             }
-            else { nF = c.init2; fAB = fAB * 2u; }                                // :167, :173
+            else { nF = initRow; fAB = fAB * 2u; }                                // :167, :173
             // ---- G of lane j from the same lane (:176-190, :230-244)
             const uint32_t g = sw2MaxFlag<j>(mCur, F[j], fF);
             const uint32_t t = __vminu2(D[j] ^ Q, 0x00010001u);
-            const uint32_t nG = g + c.match32 + t * uint32_t(c.delta);
+            const uint32_t nG = g + t * uint32_t(c.delta);
             // ---- E of lane j from lane j+1 of THIS row (:261-297)
             uint32_t nE;
             if (j < 15)
@@ -274,7 +289,7 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
                 nE = __viaddmax_u16x2(nEnext, c.negExt16x2, hOnext);
                 fHE = fHE * 2u + __vminu2(nE - hOnext, 0x00010001u);
             }
-            else { nE = c.init2; fHE = fHE * 2u; }
+            else { nE = initRow; fHE = fHE * 2u; }
             const uint32_t h = sw2MaxFlag<j>(nG, nF, fGF);
             hOnext = h + c.negOpen32;
             nEnext = nE;
