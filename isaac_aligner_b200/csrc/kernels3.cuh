@@ -1,6 +1,6 @@
 // Third-generation gapped path: the packed 16x2 Smith-Waterman of sw2.cuh split into two kernels.
 //
-//   swForwardKernel      forward DP of candidate pairs (2t, 2t+1): writes the six direction planes of every row and the
+//   swForwardKernel      forward DP of candidate pairs (2t, 2t+1): writes the flag masks of every row and the
 //                        end cell of both halves.  128 registers, nothing but the DP loop in its instruction footprint.
 //   swTraceScoreKernel   one thread per candidate: traceback from the planes, CIGAR assembly, updateFragmentCigar.  These
 //                        phases are chains of dependent loads and FP64 adds; with a third of the registers they run at
@@ -82,15 +82,14 @@ swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const Score
         uint32_t ops[SW_OPS_CAP + 2];
         Sw2Walker w;
         w.start(p.sequenceLength, int(cell & 0xFFu), (cell >> 8) & 0xFFu, ops + 1, SW_OPS_CAP);
-        // every row from L-1 down to 0 is visited once: keep the three plane words of this half of AHEAD rows in flight
-        const uint32_t *tb = planes + size_t(i & 1u) * 3u * pairStride + pair;
+        // every row from L-1 down to 0 is visited once: the one word a walk on the diagonal needs of AHEAD rows is kept in flight;
+        // the five masks are fetched only for a row in which some walk of the warp leaves the diagonal
+        const unsigned half = i & 1u;
+        const uint32_t *tb = planes + pair;
         const size_t rowStride = size_t(SW2_FLAG_WORDS) * pairStride;
-        auto load = [&](int r, uint32_t (&q)[3]) {
-            const uint32_t *row = tb + size_t(max(r, 0)) * rowStride;
-            q[0] = row[0]; q[1] = row[pairStride]; q[2] = row[2 * size_t(pairStride)];
-        };
+        auto load = [&](int r, uint32_t &q) { q = tb[size_t(max(r, 0)) * rowStride]; };
         constexpr int AHEAD = ISAAC_TRACE_ROWS_AHEAD;
-        uint32_t q[AHEAD][3];
+        uint32_t q[AHEAD];
         const int top = w.ii;
 #pragma unroll
         for (int k = 0; k < AHEAD; ++k) load(top - k, q[k]);
@@ -99,7 +98,22 @@ swTraceScoreKernel(const ReferenceView ref, const ReadSetView reads, const Score
 #pragma unroll
             for (int k = 0; k < AHEAD; ++k)
             {
-                if (r >= k) w.stepRowConverged(r - k, q[k][0], q[k][1], q[k][2]);
+                const int row = r - k;
+                if (row >= 0 && w.active && w.ii == row)
+                {
+                    // when all lanes stay on the diagonal the row costs a handful of instructions; otherwise all lanes run the
+                    // same general step once (no per-lane slow path for the others to wait for)
+                    const bool diagonal = w.staysOnDiagonal(q[k], half);
+                    if (__all_sync(__activemask(), diagonal)) w.diagonalStep();
+                    else
+                    {
+                        const uint32_t *f = tb + size_t(row) * rowStride + pairStride;
+                        const size_t ps = pairStride;
+                        uint32_t p[SW2_PLANE_WORDS];
+                        sw2Planes(f[0], f[ps], f[2 * ps], f[3 * ps], f[4 * ps], p);
+                        w.stepsInRow(row, p[half * 3u], p[half * 3u + 1u], p[half * 3u + 2u]);
+                    }
+                }
                 load(r - k - AHEAD, q[k]);
             }
         }

@@ -18,12 +18,14 @@
 //        fAB bit j: max(G,E)[j-1]-open < F[j-1]-ext   (TF of lane j)
 //        fGF bit j: newG[j] < newF[j]            (TE of lane j-1)
 //        fHE bit j: max(newG,newF)[j+1]-open < newE[j+1]-ext   (TE of lane j)
-//   * at the end of a row the five masks are turned, with a dozen bitwise operations on whole masks (both halves at
-//     once), into the SIX bit planes the traceback reads: (tg1,tg2) (te1,te2) (tf1,tf2), plane 1 = "direction is E",
-//     plane 2 = "direction is F" of the three direction matrices TG/TE/TF -- including the reference's
-//     _mm_max_epi16-on-byte-pairs coupling of lanes 2p/2p+1 in TG (:197).  6 words per row and thread pair are stored
-//     (12 bytes per alignment row, what the reference's 3 x 16 direction bytes compress to), three per half, each
-//     holding plane 1 in its low and plane 2 in its high 16 bits.
+//   * what a row leaves for the traceback is SIX words per thread pair (12 bytes per alignment row, what the reference's
+//     3 x 16 direction bytes compress to), half A in the low and half B in the high 16 bits of each: first the lanes whose
+//     G direction is not "stay on the diagonal" (sw2OffDiagonal: a handful of operations on fE and fF, including the
+//     reference's _mm_max_epi16-on-byte-pairs coupling of lanes 2p/2p+1 in TG, :197) -- the one word nearly every step of
+//     nearly every walk reads --, then the five masks as they are.  The walk turns them into the six bit planes
+//     (tg1,tg2) (te1,te2) (tf1,tf2), plane 1 = "direction is E", plane 2 = "direction is F" of the three direction matrices
+//     TG/TE/TF (sw2Planes, a dozen bitwise operations on whole masks), only in the rows where it leaves the diagonal: the
+//     forward loop, which is what the pass waits for, does not pay for directions nobody looks at.
 #pragma once
 #include "device_types.cuh"
 #include "sw.cuh"
@@ -61,7 +63,8 @@ __device__ __forceinline__ Sw2Consts makeSw2Consts(const SwScores s)
     return c;
 }
 
-constexpr unsigned SW2_FLAG_WORDS = 6;
+constexpr unsigned SW2_FLAG_WORDS = 6;           // sw2OffDiagonal, then fE, fF, fAB, fGF, fHE of a row: half A in the low, half B in the high 16 bits
+constexpr unsigned SW2_PLANE_WORDS = 6;
 
 /// max(a, b) of both halves, and bit J (half A) / bit 16+J (half B) of 'flags' set where the maximum is not a, i.e. a < b.
 /// ptxas folds the max and the two equality tests into ONE VIMNMX.U16x2 with two predicate outputs; each flag then
@@ -99,7 +102,7 @@ __device__ __forceinline__ void sw2ScanEnd(const uint32_t (&G)[16], const uint32
 
 /// The six direction planes of a row from its five flag masks; every word holds the 16 lanes of half A in its low and
 /// of half B in its high 16 bits, shifts by one lane are masked so that nothing crosses the halves.
-__device__ __forceinline__ void sw2Planes(uint32_t fE, uint32_t fF, uint32_t fAB, uint32_t fGF, uint32_t fHE, uint32_t (&p)[SW2_FLAG_WORDS])
+__device__ __forceinline__ void sw2Planes(uint32_t fE, uint32_t fF, uint32_t fAB, uint32_t fGF, uint32_t fHE, uint32_t (&p)[SW2_PLANE_WORDS])
 {
     const uint32_t EVEN = 0x55555555u, ODD = 0xAAAAAAAAu;
     // TG (:176-197).  Odd lane (high byte of the pair): F wins over E.  Even lane: the pair with the larger high byte
@@ -117,6 +120,17 @@ __device__ __forceinline__ void sw2Planes(uint32_t fE, uint32_t fF, uint32_t fAB
     // so that a walk reads three words per row and finds both planes of its state in one of them
     p[0] = __byte_perm(tg1, tg2, 0x5410); p[1] = __byte_perm(te1, te2, 0x5410); p[2] = __byte_perm(tf1, tf2, 0x5410);
     p[3] = __byte_perm(tg1, tg2, 0x7632); p[4] = __byte_perm(te1, te2, 0x7632); p[5] = __byte_perm(tf1, tf2, 0x7632);
+}
+
+/// The lanes of a row whose G direction is not "stay on the diagonal" (tg1 | tg2 of sw2Planes), from the two masks it depends on:
+/// what a walk that is in G -- nearly every step of nearly every walk -- needs of a row.
+__device__ __forceinline__ uint32_t sw2OffDiagonal(const uint32_t fE, const uint32_t fF)
+{
+    const uint32_t EVEN = 0x55555555u, ODD = 0xAAAAAAAAu;
+    const uint32_t hF = (fF >> 1) & EVEN, hE = (fE >> 1) & EVEN;
+    const uint32_t tg2 = (fF & ODD) | (fF & EVEN & (hF | ~hE));
+    const uint32_t tg1 = (fE & ~fF & ODD) | (fE & EVEN & ~hF & (hE | ~fF));
+    return tg1 | tg2;
 }
 
 /// One traceback in progress (one half of a pair).
@@ -141,42 +155,10 @@ struct Sw2Walker
         overflow = false; active = L != 0;
         if (active && jj > 0) push(unsigned(jj), 1);                           // :388-391
     }
-    /// all steps of this walk that happen in row 'row' (:392-423); tg/te/tf = the three plane words of this half
-    /// (plane 1 in the low, plane 2 in the high 16 bits)
-    __device__ __forceinline__ void stepRow(int row, const uint32_t tg, const uint32_t te, const uint32_t tf)
+    /// the general step(s) of this walk in row 'row' (:392-423) on the three plane words of its half (plane 1 in the low, plane 2 in
+    /// the high 16 bits): one step, or several while the walk stays in the row (a deletion)
+    __device__ __forceinline__ void stepsInRow(int row, const uint32_t tg, const uint32_t te, const uint32_t tf)
     {
-        if (!active || ii != row) return;
-        // the overwhelmingly common step: on the diagonal and staying there
-        if (type == 0 && (((tg | (tg >> 16)) >> jj) & 1u) == 0)
-        {
-            ++opLength; --ii;
-            active = ii >= 0;
-            return;
-        }
-        while (active && ii == row)
-        {
-            ++opLength;
-            const uint32_t p = (type == 0 ? tg : (type == 1 ? te : tf)) >> jj;
-            const unsigned next = (p & 1u) | ((p >> 15) & 2u);
-            if (next != type) { push(opLength, type); opLength = 0; }
-            if (type == 0) { --ii; } else if (type == 1) { ++jj; } else { --ii; --jj; }
-            type = next;
-            active = ii >= 0 && jj >= 0 && jj <= 15;
-        }
-    }
-    /// stepRow for a kernel in which every lane of the warp walks its own alignment through the same rows: when all
-    /// lanes stay on the diagonal the row costs a handful of instructions; otherwise all lanes run the same general
-    /// step once (no per-lane slow path for the others to wait for) and only a walk in a deletion iterates again.
-    __device__ __forceinline__ void stepRowConverged(int row, const uint32_t tg, const uint32_t te, const uint32_t tf)
-    {
-        if (!active || ii != row) return;
-        const bool diagonal = type == 0 && (((tg | (tg >> 16)) >> jj) & 1u) == 0;
-        if (__all_sync(__activemask(), diagonal))
-        {
-            ++opLength; --ii;
-            active = ii >= 0;
-            return;
-        }
         do
         {
             ++opLength;
@@ -188,6 +170,21 @@ struct Sw2Walker
             type = next;
             active = ii >= 0 && jj >= 0 && jj <= 15;
         } while (active && ii == row);
+    }
+    /// is the step of this walk in its current row "on the diagonal and staying there"?  offDiagonal = sw2OffDiagonal of the row
+    __device__ __forceinline__ bool staysOnDiagonal(const uint32_t offDiagonal, const unsigned half) const
+    {
+        return type == 0 && ((offDiagonal >> (jj + int(half) * 16)) & 1u) == 0;
+    }
+    __device__ __forceinline__ void diagonalStep() { ++opLength; --ii; active = ii >= 0; }
+    /// all steps of this walk in row 'row' from the six words of the row
+    __device__ __forceinline__ void stepRow(int row, const uint32_t (&f)[SW2_FLAG_WORDS], const unsigned half)
+    {
+        if (!active || ii != row) return;
+        if (staysOnDiagonal(f[0], half)) { diagonalStep(); return; }
+        uint32_t p[SW2_PLANE_WORDS];
+        sw2Planes(f[1], f[2], f[3], f[4], f[5], p);
+        stepsInRow(row, p[half * 3u], p[half * 3u + 1u], p[half * 3u + 2u]);
     }
     /// :425-453: flush, strip a deletion at either end; \return the stripped leading deletion, ops[0..nOps) head first
     __device__ __forceinline__ unsigned finish(unsigned &nOps)
@@ -204,7 +201,7 @@ struct Sw2Walker
 };
 
 /// Traceback of both halves of a pair in one pass over the rows (every row from L-1 down to 0 is visited exactly once
-/// by each walk, so the row order is known in advance): the six plane words of four rows ahead are kept in flight in
+/// by each walk, so the row order is known in advance): the six words of four rows ahead are kept in flight in
 /// registers, turning the walk's chain of dependent loads into a software pipeline.
 __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb, const size_t tbStride,
                                                  Sw2Walker &a, Sw2Walker &b)
@@ -218,8 +215,8 @@ __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb
     };
     auto process = [&](int r, const uint32_t (&w)[SW2_FLAG_WORDS]) {
         if (r < 0) return;
-        a.stepRow(r, w[0], w[1], w[2]);
-        b.stepRow(r, w[3], w[4], w[5]);
+        a.stepRow(r, w, 0u);
+        b.stepRow(r, w, 1u);
     };
     uint32_t w0[SW2_FLAG_WORDS], w1[SW2_FLAG_WORDS], w2[SW2_FLAG_WORDS], w3[SW2_FLAG_WORDS];
     load(top, w0); load(top - 1, w1); load(top - 2, w2); load(top - 3, w3);
@@ -300,11 +297,13 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
         lane(Sw2Lane<11>()); lane(Sw2Lane<10>()); lane(Sw2Lane<9>()); lane(Sw2Lane<8>());
         lane(Sw2Lane<7>()); lane(Sw2Lane<6>()); lane(Sw2Lane<5>()); lane(Sw2Lane<4>());
         lane(Sw2Lane<3>()); lane(Sw2Lane<2>()); lane(Sw2Lane<1>()); lane(Sw2Lane<0>());
-        uint32_t planes[SW2_FLAG_WORDS];
-        sw2Planes(fE, fF, fAB, fGF, fHE, planes);
-        uint32_t *row = tb + size_t(i) * SW2_FLAG_WORDS * tbStride;                                      // :306-308
+        // the five masks leave as they are (:306-308 stores direction bytes), in front of them the one word nearly every step of
+        // nearly every walk needs: the lanes whose G direction leaves the diagonal.  Turning the masks into directions is left
+        // to the walk, for the few rows in which it needs them
+        const uint32_t flags[SW2_FLAG_WORDS] = {sw2OffDiagonal(fE, fF), fE, fF, fAB, fGF, fHE};
+        uint32_t *row = tb + size_t(i) * SW2_FLAG_WORDS * tbStride;
 #pragma unroll
-        for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) row[k * tbStride] = planes[k];
+        for (unsigned k = 0; k < SW2_FLAG_WORDS; ++k) row[k * tbStride] = flags[k];
         if (i + 1 == LA || i + 1 == LB)                        // last row of a half: its end cell (one copy of the scan)
         {
 #pragma unroll 1
