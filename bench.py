@@ -566,7 +566,7 @@ def run_b200(args):
                      "unit": "TOP/s", "frac": achieved / peak_add, "traffic": traffic,
                      "hbm_gbs": (traffic / (ms_gapped * 1e-3) / 1e9) if traffic else None,
                      "hbm_frac": (traffic / (ms_gapped * 1e-3) / 1e9 / hbm_peak) if traffic else None,
-                     "plane_bytes_per_launch": int(n) * L * 12 * 2,
+                     "plane_bytes_per_launch": int(n) * L * 12,
                      "ops_per_cell": OPS_PER_CELL, "gcups_kernel": sw_gcups_kernel, "ms_per_launch": ms_gapped,
                      "peak_source": "measured live by isaac_ext_measure_int32_peak: add.s32 %.1f, max.s32 %.1f, "
                                     "16x2 max %.1f TOP/s" % (peak_add / 1e12, peak_max / 1e12, peak_dpx / 1e12)},
