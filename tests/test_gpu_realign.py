@@ -140,3 +140,53 @@ def test_argument_errors(ctx_and_contigs):
     empty = bins.Bin(np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=bins.BIN_INDEX_DTYPE), bin_.bin_start, bin_.bin_end)
     res = ctx.realign_bin(empty, good)
     assert res.position.size == 0 and res.gaps.size == 0
+
+
+def test_records_of_the_tile_pipeline_feed_the_realigner(ref):
+    """the chain a run takes: match selection of a tile -> io::FragmentHeader records (isaac_ext_select_tile with pack, compact =
+    the bin file) -> gap realigner over those very bytes.  The reference's GapRealigner runs on the same bytes: it asserts the
+    coherence of what it reads (TLEN of mates, soft clips against lowClipped / highClipped, CIGAR lengths), so this is also the
+    check that the packed records are bins the build stage accepts."""
+    from common_build import build_workload
+    from isaac_aligner_b200 import capi, tile
+    from isaac_aligner_b200.batch import PackOptions, TemplateOptions
+    n, L = 12000, 100
+    genome, sim, reads, mb = build_workload(n_pairs=n, L=L, seed=808, genome_bases=150_000, indel_rate=6e-3, masked=False)   # ~16x, gaps everywhere
+    ctx = capi.Context(Config.default(max_read_length=2 * L))
+    ctx.set_reference(genome)
+    pack = PackOptions(tile=1101, barcode_idx=0, keep_unaligned=False, compact=True)
+    tls = Tls.make()
+    got_tile = tile.select_tile(ctx, reads.bcl, (L, L), mb.matches, mb.seeds, tls=tls, options=TemplateOptions.make(clip_semialigned=True), pack=pack)
+    packed = got_tile.packed
+    offsets = packed.record_offset
+    lengths = np.diff(offsets.astype(np.int64))
+    stored = np.flatnonzero(lengths > 0)
+    assert stored.size > 1.5 * n
+    data = np.ascontiguousarray(packed.records)
+    # one bin per contig: the records whose position lies on it; index in (cluster, read) order, mates linked when both are in the bin
+    total = 0
+    for contig, bases in enumerate(genome):
+        start, end = bins.reference_position(contig, 0), bins.reference_position(contig, len(bases))
+        headers = {int(i): np.frombuffer(data[int(offsets[i]):int(offsets[i]) + 112].tobytes(), dtype=bins.HEADER_DTYPE)[0] for i in stored}
+        inside = [i for i in stored if start <= int(headers[int(i)]["fStrandPosition"]) < end]
+        if not inside:
+            continue
+        # the bin's own data: its records back to back
+        blob, new_offset = [], {}
+        at = 0
+        for i in inside:
+            new_offset[int(i)] = at
+            blob.append(data[int(offsets[i]):int(offsets[i + 1])]); at += int(lengths[i])
+        bin_data = np.concatenate(blob)
+        index = []
+        for i in inside:
+            mate = int(i) ^ 1
+            index.append((new_offset[int(i)], new_offset.get(mate, new_offset[int(i)])))
+        b = bins.Bin(bin_data, np.array([new_offset[int(i)] for i in inside], dtype=np.uint64), np.array(index, dtype=bins.BIN_INDEX_DTYPE), start, end)
+        options = bins.RealignOptions(start, end, [tls], clip_semialigned=True)
+        want = oracle_lib.realign_bin(ref, oracle_lib.GenomeHolder(genome), b, options)
+        got = ctx.realign_bin(b, options)
+        total += compare(b, got, want)
+        assert got.gaps.size > 100
+    assert total > 0                                             # some read was repaired with a gap another read brought along
+    ctx.close()
