@@ -371,6 +371,12 @@ def run_b200(args):
             pairs_workload = make_pairs_workload(args, rank, world, n_pairs)
         except Exception as e:      # noqa: BLE001
             pairs_error = "%s: %s" % (type(e).__name__, e)
+    realign_workload = None
+    if world == 1 and n_pairs:                                       # the side measurements go together: --pairs 0 gives the bare micro run
+        try:
+            realign_workload = make_realign_workload(args, rank)
+        except Exception as e:      # noqa: BLE001
+            realign_workload = "%s: %s" % (type(e).__name__, e)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the candidate-extension path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -545,6 +551,14 @@ def run_b200(args):
     cores = os.cpu_count() or 1
     ns = min(n, args.cpu_sample_per_core * cores)
     cpu_gcups, cpu_sec, kind, cores = cpu_arm(args, genome, reads, cand[:ns], config, 1, 0)
+    realign_line = None
+    if isinstance(realign_workload, str):
+        realign_line = {"error": realign_workload}
+    elif realign_workload is not None:
+        try:
+            realign_line = run_realign(args, workload=realign_workload, embedded=True)       # build::GapRealigner over 16 bins
+        except Exception as e:      # noqa: BLE001
+            realign_line = {"error": "%s: %s" % (type(e).__name__, e)}
     if pairs_line is not None and pairs_cpu_inputs is not None:
         try:
             pgenome, preads, pmb, ptls, pconfig = pairs_cpu_inputs
@@ -560,6 +574,7 @@ def run_b200(args):
         "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks, "host": {"cores": os.cpu_count(), "numa_binding_rank0": numa},
         "tile_stats": tile_stats,
         "pairs_pipeline": pairs_line,
+        "gap_realigner": realign_line,
         "roofline": {"bound": "int32", "kernel": "swForwardKernel (timed with the swTraceScoreKernel launches it overlaps: "
                                                   "the whole isaac_ext_gapped_batch_device call)",
                      "achieved": achieved / 1e12, "peak": peak_add / 1e12,
@@ -899,23 +914,10 @@ def _realign_bin_worker(job):
     return b.data, b.record_offset, b.index, b.bin_start, b.bin_end
 
 
-def run_realign(args):
-    """--workload realign: isaac_ext_realign_bin (build::GapRealigner, SURVEY 8f #4) over --bins bins of one contig, each the records
-    of --bin-pairs pairs sampled at ~20x from a haplotype with shared indels.  One step = every bin once (BinSorter::process per bin).
-    value = index entries/s over the device phases alone (CUDA events inside the library: collectGaps + realignGaps), e2e = the same
-    through the C call with host buffers (records up, updated records + positions + CIGARs down); cpu_baseline / --impl reference =
-    the reference's own GapRealigner on the same bins, one bin per host thread.  Results are compared bin by bin."""
-    import ctypes
+def make_realign_workload(args, rank):
+    """the genome and the bins of one rank, drawn by fork workers (before the process has a CUDA context)"""
     import multiprocessing
-    import torch
-    from isaac_aligner_b200 import bins, synth
-    from isaac_aligner_b200.batch import Tls
-    from isaac_aligner_b200.types import Config
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return                                                       # the reference arm runs on rank 0 alone
+    from isaac_aligner_b200 import synth
     L, B, n_pairs = args.read_length, args.bins, args.bin_pairs
     span = int(n_pairs * 2 * L / 20)                                 # ~20x
     genome = synth.make_genome((span + 4000) * B + 4000, n_contigs=1, seed=synth.SEED_G5)
@@ -925,6 +927,29 @@ def run_realign(args):
     cores = sorted(os.sched_getaffinity(0))
     with multiprocessing.get_context("fork").Pool(min(len(cores), B)) as pool:
         made = pool.map(_realign_bin_worker, jobs)
+    return genome, made
+
+
+def run_realign(args, workload=None, embedded=False):
+    """--workload realign: isaac_ext_realign_bin (build::GapRealigner, SURVEY 8f #4) over --bins bins of one contig, each the records
+    of --bin-pairs pairs sampled at ~20x from a haplotype with shared indels.  One step = every bin once (BinSorter::process per bin).
+    value = index entries/s over the device phases alone (CUDA events inside the library: collectGaps + realignGaps), e2e = the same
+    through the C call with host buffers (records up, updated records + positions + CIGARs down); cpu_baseline / --impl reference =
+    the reference's own GapRealigner on the same bins, one bin per host thread.  Results are compared bin by bin.
+    embedded: called from the default run on an initialised device (one GPU); returns the line instead of printing it."""
+    import ctypes
+    import torch
+    from isaac_aligner_b200 import bins
+    from isaac_aligner_b200.batch import Tls
+    from isaac_aligner_b200.types import Config
+    world = 1 if embedded else int(os.environ.get("WORLD_SIZE", "1"))
+    rank = 0 if embedded else int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return                                                       # the reference arm runs on rank 0 alone
+    L, B, n_pairs = args.read_length, args.bins, args.bin_pairs
+    cores = sorted(os.sched_getaffinity(0))
+    genome, made = workload if workload is not None else make_realign_workload(args, rank)
     the_bins = [bins.Bin(*m) for m in made]
     tls = [Tls.make(mn=int(2.0 * L), mx=int(3.4 * L) + 120, median=int(2.6 * L) + 60)]
     options = [bins.RealignOptions(b.bin_start, b.bin_end, tls, clip_semialigned=True) for b in the_bins]
@@ -983,10 +1008,11 @@ def run_realign(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the gap realigner has no CPU fallback")
     from isaac_aligner_b200 import capi
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    bind_to_gpu_numa(local_rank)
+    if not embedded:
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        bind_to_gpu_numa(local_rank)
     cfg = Config.default(max_read_length=2 * L)
     cfg.device = local_rank
     ctx = capi.Context(cfg)
@@ -1052,7 +1078,7 @@ def run_realign(args):
             torch.distributed.all_reduce(t, op=op)
         return [float(x) for x in t.tolist()]
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not embedded else None
     for _ in range(max(3, args.warmup)):
         step()
         step_batched()
@@ -1112,8 +1138,10 @@ def run_realign(args):
         line["cpu_baseline"] = {"value": entries_rank / sec, "unit": "fragments/s", "cores": used, "kind": "reference",
                                 "sample": "every bin of the step through the reference's own GapRealigner, one bin per host thread, %.2f s (the bins of rank 0); "
                                           "records and positions equal the GPU's" % sec}
-    emit(json.dumps(line))
     ctx.close()
+    if embedded:
+        return line
+    emit(json.dumps(line))
 
 
 if __name__ == "__main__":
