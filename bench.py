@@ -62,6 +62,7 @@ def parse_args():
                         "pack: the io::FragmentHeader bin records of a tile's templates (isaac_ext_pack_fragments), fragments/s")
     p.add_argument("--bins", type=int, default=16, help="--workload realign: bins per step")
     p.add_argument("--bin-pairs", type=int, default=40_000, help="--workload realign: read pairs sampled per bin")
+    p.add_argument("--variant-spacing", type=int, default=300, help="--workload realign: a SNP or indel of the haplotype every ~this many bases")
     p.add_argument("--compact", action="store_true", help="--workload pack: records cut to their total length instead of FragmentBuffer slots")
     p.add_argument("--pairs", type=int, default=None,
                    help="read pairs per GPU of the pairs pipeline (default 2M: BASELINE configs[2] sharded, next to the micro run and for --workload pairs; 0 disables)")
@@ -908,9 +909,9 @@ def run_wide(args):
 
 def _realign_bin_worker(job):
     from isaac_aligner_b200 import bins
-    contig_bases, region, n_pairs, L, seed = job
+    contig_bases, region, n_pairs, L, seed, spacing = job
     b = bins.simulate_bin([contig_bases], contig=0, region=region, n_pairs=n_pairs, read_length=L, seed=seed, template_mean=int(2.6 * L) + 60,
-                          variant_spacing=300, max_indel=12)
+                          variant_spacing=spacing, max_indel=12)
     return b.data, b.record_offset, b.index, b.bin_start, b.bin_end
 
 
@@ -923,7 +924,7 @@ def make_realign_workload(args, rank):
     genome = synth.make_genome((span + 4000) * B + 4000, n_contigs=1, seed=synth.SEED_G5)
     contig = genome[0]
     # bins are independent: every rank realigns its own --bins bins of the run (weak scaling, no exchange of any kind)
-    jobs = [(contig, (2000 + k * (span + 4000), 2000 + k * (span + 4000) + span), n_pairs, L, 900 + k + 1000 * rank) for k in range(B)]
+    jobs = [(contig, (2000 + k * (span + 4000), 2000 + k * (span + 4000) + span), n_pairs, L, 900 + k + 1000 * rank, args.variant_spacing) for k in range(B)]
     cores = sorted(os.sched_getaffinity(0))
     with multiprocessing.get_context("fork").Pool(min(len(cores), B)) as pool:
         made = pool.map(_realign_bin_worker, jobs)
@@ -957,7 +958,7 @@ def run_realign(args, workload=None, embedded=False):
     records = sum(len(b.record_offset) for b in the_bins)
     data_bytes = sum(int(b.data.size) for b in the_bins)
     workload = {"workload": "build::GapRealigner over %d bins of one contig: %d index entries / %d records / %d MB per step, 2x%d bp pairs at ~20x from a "
-                            "haplotype with an indel or SNP every ~300 bases, --clip-semialigned, costs 3/4/0" % (B, entries, records, data_bytes >> 20, L),
+                            "haplotype with an indel or SNP every ~%d bases, --clip-semialigned, costs 3/4/0" % (B, entries, records, data_bytes >> 20, L, args.variant_spacing),
                 "l2": "each bin's records are uploaded fresh and read once"}
 
     def reference_pass(threads):
