@@ -153,6 +153,9 @@ __global__ void buildCandidatesKernel(const TileView v, isaac_ext_candidate_t *_
             }
             else f.uniqueSeedCount = 1;
             w.pool = 0; w.slot = 0;
+            // a read position behind the end of the contig cannot come from a seed that lies on the contig; the reference does not
+            // survive such a match either (it reads qualities and bases off the end of its vectors and trips the assertion of
+            // Quality.hh's lookup, checked with the reference build), so the batch is refused rather than aligned
             if (f.contigId >= v.contigCount || f.position > long(v.contigLength[f.contigId])) { bad = true; continue; }
             list[seed.readIndex][filled[seed.readIndex]++] = w;
         }
