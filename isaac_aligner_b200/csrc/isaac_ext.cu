@@ -167,12 +167,6 @@ bool swScoresSupported(int match, int mismatch, int open, int ext, unsigned maxR
         why = "BandedSmithWaterman: unsupported read length for these scores: use smaller scores or shorter reads";
         return false;
     }
-    // sw2.cuh keeps row-relative values lifted by readLength * match: twice that must fit next to the largest score
-    if (2L * long(maxReadLength) * match + long(maxReadLength) * maxScore >= 32768 - open)
-    {
-        why = "BandedSmithWaterman: match score times read length too large for the packed 16-bit kernel";
-        return false;
-    }
     if (match < 0 || mismatch > 0 || open < 0 || ext < 0 || ext > open)
     {
         why = "BandedSmithWaterman: scores must satisfy match >= 0 >= mismatch and 0 <= gapExtend <= gapOpen";
@@ -599,7 +593,9 @@ static int gappedSplit(isaac_ext_ctx *ctx, uint32_t n, const isaac_ext_candidate
         const size_t firstCandidate = first * 2;
         const uint32_t count = uint32_t(std::min<size_t>(chunkPairs * 2, n - firstCandidate));
         const uint32_t chunk = (count + 1) / 2;
-        swForwardKernel<<<(chunk + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
+        // row-relative cell values where the scores leave room for them (sw2.cuh), the plain ones otherwise
+        (sw2RowRelativeFits(ctx->sp.swMatch, maxLength) ? swForwardKernel<true> : swForwardKernel<false>)
+            <<<(chunk + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
             ctx->ref, ctx->reads, ctx->sp, count, dCandidates + firstCandidate, ctx->swPlanes[k].p, uint32_t(stride),
             ctx->swEndCells[k].p, adapterClip ? adapterClip + firstCandidate : nullptr);
         swTraceScoreKernel<<<(count + SW_BLOCK - 1) / SW_BLOCK, SW_BLOCK, 0, ctx->swStream[k]>>>(
@@ -747,7 +743,7 @@ extern "C" int isaac_ext_banded_sw_batch(isaac_ext_ctx *ctx, uint32_t n, const c
     int rc = ensureTraceback(ctx, grid, SW_BLOCK, maxLen);
     if (rc) return rc;
     const SwScores sw = {matchScore, mismatchScore, gapOpenScore, gapExtendScore, -32768 + gapOpenScore};
-    bandedSwAsciiKernel2<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
+    (sw2RowRelativeFits(matchScore, maxLen) ? bandedSwAsciiKernel2<true> : bandedSwAsciiKernel2<false>)<<<grid, SW_BLOCK, 0, ctx->stream>>>(n, ctx->dAscii.p, ctx->dOffsets.p, ctx->dLengths.p, ctx->dAscii.p + qBytes,
                                                                  ctx->dOffsets.p + n, sw, cigarStride, ctx->dCigars.p, ctx->dLengths.p + n,
                                                                  ctx->dLengths.p + 2 * size_t(n), ctx->tbScratch.p, ctx->errorFlag.p);
     ++ctx->launches;

@@ -100,6 +100,7 @@ struct AsciiPairSrc
     }
 };
 
+template <bool ROW_RELATIVE>
 __global__ void __launch_bounds__(128)
 bandedSwAsciiKernel2(uint32_t n, const unsigned char *__restrict__ queries, const uint64_t *__restrict__ queryOffsets,
                      const uint32_t *__restrict__ queryLengths, const unsigned char *__restrict__ databases,
@@ -118,7 +119,7 @@ bandedSwAsciiKernel2(uint32_t n, const unsigned char *__restrict__ queries, cons
         AsciiPairSrc src = {{queries + queryOffsets[iA], queries + queryOffsets[iB]},
                             {databases + databaseOffsets[iA], databases + databaseOffsets[iB]}, {LA, LB}};
         int jj[2]; unsigned type[2];
-        sw2Forward(src, LA, LB, sw, tb, tbStride, jj, type);
+        sw2Forward<ROW_RELATIVE>(src, LA, LB, sw, tb, tbStride, jj, type);
         uint32_t opsA[SW_OPS_CAP], opsB[SW_OPS_CAP];
         Sw2Walker wa, wb;
         wa.start(LA, jj[0], type[0], opsA, SW_OPS_CAP);

@@ -26,6 +26,7 @@ namespace isaac_b200
 {
 
 /// plane layout of a chunk: planes[(row * SW2_FLAG_WORDS + k) * pairStride + pair]
+template <bool ROW_RELATIVE>
 __global__ void __launch_bounds__(128, 4)
 swForwardKernel(const ReferenceView ref, const ReadSetView reads, const ScoreParams sp, uint32_t n,
                 const isaac_ext_candidate_t *__restrict__ candidates, uint32_t *__restrict__ planes, uint32_t pairStride,
@@ -50,7 +51,7 @@ swForwardKernel(const ReferenceView ref, const ReadSetView reads, const ScorePar
                                {LA ? ref.contigOffset[pa.contigId] + uint64_t(pa.strandPosition - long(pa.left)) : 0ull,
                                 LB ? ref.contigOffset[pb.contigId] + uint64_t(pb.strandPosition - long(pb.left)) : 0ull},
                                {0, 0}, {0, 0}, reads.codesClamp()};
-        sw2Forward(src, LA, LB, sw, planes + t, pairStride, jj, type);
+        sw2Forward<ROW_RELATIVE>(src, LA, LB, sw, planes + t, pairStride, jj, type);
     }
     endCells[t] = uint32_t(jj[0] & 0xFF) | (type[0] << 8) | (uint32_t(jj[1] & 0xFF) << 16) | (type[1] << 24);
 }

@@ -33,6 +33,12 @@
 namespace isaac_b200
 {
 
+/// may the forward pass keep row-relative values?  The largest stored value is score + 32768 + 2 * readLength * match
+__host__ __device__ inline bool sw2RowRelativeFits(const int match, const unsigned maxReadLength)
+{
+    return 2ll * (long long)(maxReadLength) * match < 32768ll;
+}
+
 struct Sw2Consts
 {
     uint32_t negOpen32;    // (-open) * 0x10001 as a 32-bit addend
@@ -232,16 +238,19 @@ __device__ __forceinline__ void sw2TracebackPair(const uint32_t *__restrict__ tb
 /// Forward pass over max(LA, LB) rows for the pair.  src.q2(i) / src.d2(k) return the base codes of both halves (they
 /// must tolerate indices past the own length of a half: any code will do there).  On return jj/type hold the end cell
 /// of each half.
-template <class PairSrc>
+/// ROW_RELATIVE: the cells are kept less (row + 1) * match (makeSw2Consts), which needs room for Lmax * match above the largest
+/// score; where the scores and the read length do not leave it (sw2RowRelativeFits) the plain values are used, one add per cell more
+template <bool ROW_RELATIVE, class PairSrc>
 __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, const unsigned LB, const SwScores s,
                                            uint32_t *__restrict__ tb, const size_t tbStride,
                                            int (&jj)[2], unsigned (&type)[2])
 {
-    const Sw2Consts c = makeSw2Consts(s);
+    Sw2Consts c = makeSw2Consts(s);
+    if (!ROW_RELATIVE) { c.negOpenRow32 = c.negOpen32; c.negExtRow16x2 = c.negExt16x2; }
     const unsigned Lmax = max(LA, LB);
     // the constant that keeps the row-relative values non-negative: the last row has dropped by Lmax * match (the host admits only
     // scores and read lengths for which value + 32768 + Lmax * match stays below 65536, swScoresSupported)
-    const uint32_t lift = Lmax * c.match32;
+    const uint32_t lift = ROW_RELATIVE ? Lmax * c.match32 : 0u;
     uint32_t initRow = c.init2 + lift;                              // 'init' as the row about to be computed holds it
     uint32_t G[16], E[16], F[16], D[16];
 #pragma unroll
@@ -254,7 +263,7 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
 #pragma unroll 1
     for (unsigned i = 0; i < Lmax; ++i)
     {
-        initRow -= c.match32;
+        if (ROW_RELATIVE) initRow -= c.match32;
 #pragma unroll
         for (int j = 15; j > 0; --j) D[j] = D[j - 1];
         D[0] = src.d2(i + 15);
@@ -278,7 +287,7 @@ __device__ __forceinline__ void sw2Forward(PairSrc &src, const unsigned LA, cons
             // ---- G of lane j from the same lane (:176-190, :230-244)
             const uint32_t g = sw2MaxFlag<j>(mCur, F[j], fF);
             const uint32_t t = __vminu2(D[j] ^ Q, 0x00010001u);
-            const uint32_t nG = g + t * uint32_t(c.delta);
+            const uint32_t nG = ROW_RELATIVE ? g + t * uint32_t(c.delta) : g + c.match32 + t * uint32_t(c.delta);
             // ---- E of lane j from lane j+1 of THIS row (:261-297)
             uint32_t nE;
             if (j < 15)
