@@ -310,6 +310,20 @@ int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_t *tls, uin
 int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
                               const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result);
 
+/* isaac_ext_build_templates whose result comes back on a copy stream of its own: the call returns once the tile's kernels are
+ * queued (it still waits for the handful of totals that size its passes), result points at one of two host result sets of the
+ * context and is VALID ONLY AFTER isaac_ext_fetch_templates(ctx, result) has returned ISAAC_EXT_OK -- which also is where a malformed
+ * match batch or a capacity error of that tile is reported.  What the caller gains: the download of tile k (≈ 150 B per pair) runs
+ * next to the kernels of tile k + 1 instead of in front of them,
+ *     set_reads(k); build_templates_deferred(k, &r[k % 2]); set_reads(k + 1); build_templates_deferred(k + 1, &r[(k + 1) % 2]);
+ *     fetch_templates(&r[k % 2]); ... use tile k ...
+ * At most two tiles may be waiting to be fetched (a third deferred call returns ISAAC_EXT_E_UNSUPPORTED); a result set is reused by
+ * the deferred call after the next one, so tile k must have been consumed before tile k + 2 is built.  The device-resident result
+ * (isaac_ext_template_stats, isaac_ext_tile_cycle_stats, isaac_ext_pack_fragments) is that of the last tile built, as always. */
+int isaac_ext_build_templates_deferred(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                       const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result);
+int isaac_ext_fetch_templates(isaac_ext_ctx *ctx, const isaac_ext_template_result_t *result);
+
 /* The three tile calls above without blocking the caller: a submitted call runs on a worker thread of the context, on the
  * context's own streams and buffers, while the caller loads and sorts the next tile's matches, the way the reference runs its
  * load / compute / flush slots side by side (SelectMatchesTransition.cpp:316-340).  The small argument structs are copied at

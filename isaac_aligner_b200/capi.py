@@ -38,7 +38,7 @@ EXPORTS = [
     "isaac_ext_template_stats", "isaac_ext_pack_fragments", "isaac_ext_align_batch_packed",
     "isaac_ext_banded_sw_wide_batch", "isaac_ext_banded_sw_wide_batch_device", "isaac_ext_select_tile", "isaac_ext_tile_packed", "isaac_ext_prefetch_reads", "isaac_ext_prefetch_batch", "isaac_ext_tile_cycle_stats", "isaac_ext_tile_cycle_stats_finalize",
     "isaac_ext_submit_build_fragments", "isaac_ext_submit_rescue_shadows", "isaac_ext_submit_build_templates", "isaac_ext_wait",
-    "isaac_ext_realign_bin", "isaac_ext_realign_bins",
+    "isaac_ext_realign_bin", "isaac_ext_realign_bins", "isaac_ext_build_templates_deferred", "isaac_ext_fetch_templates",
 ]
 
 
@@ -247,9 +247,26 @@ class Context:
                                                    ctypes.byref(res)))
         return self._templates(res) if copy else res
 
-    def _templates(self, res):
+    def build_templates_deferred(self, match_batch, tls, options=None):
+        """isaac_ext_build_templates_deferred: the tile's kernels are queued and sized, the download runs on a copy stream next to
+        whatever is called next; returns the handle fetch_templates takes (at most two may be waiting)"""
+        from .batch import TemplateOptions, TemplateResult
+        options = options if options is not None else TemplateOptions.make()
+        res = TemplateResult()
+        self._check(_lib.isaac_ext_build_templates_deferred(self._h, ctypes.byref(match_batch.c), ctypes.byref(tls), ctypes.byref(options),
+                                                            ctypes.byref(res)))
+        return res, self.reads.cluster_count, self.reads.read_count
+
+    def fetch_templates(self, handle, copy=True):
+        """isaac_ext_fetch_templates: waits for the download of a deferred tile -> batch.Templates"""
+        res, n, rc = handle
+        self._check(_lib.isaac_ext_fetch_templates(self._h, ctypes.byref(res)))
+        return self._templates(res, n, rc) if copy else res
+
+    def _templates(self, res, n=None, read_count=None):
         from .batch import TEMPLATE_DTYPE, Templates
-        n = self.reads.cluster_count
+        n = self.reads.cluster_count if n is None else n
+        read_count = self.reads.read_count if read_count is None else read_count
 
         def arr(ptr, dtype, count):
             if not count:
@@ -257,7 +274,7 @@ class Context:
             buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
             return np.frombuffer(buf, dtype=dtype).copy()
 
-        return Templates(arr(res.templates, TEMPLATE_DTYPE, n), arr(res.fragments, FRAGMENT_DTYPE, n * self.reads.read_count),
+        return Templates(arr(res.templates, TEMPLATE_DTYPE, n), arr(res.fragments, FRAGMENT_DTYPE, n * read_count),
                          arr(res.cigars, np.uint32, int(res.cigarWords)), int(res.rescueRequests))
 
     def submit_build_templates(self, match_batch, tls, options=None):

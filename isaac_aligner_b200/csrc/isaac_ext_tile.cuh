@@ -43,6 +43,21 @@ struct TileState
     DeviceBuffer<uint32_t> dTemplateWords, dTemplateWordBegin, dTemplateCigars, dClippedCigars;
     PinnedBuffer<isaac_ext_template_t> hTemplates;  PinnedBuffer<isaac_ext_fragment_t> hTemplateFragments;  PinnedBuffer<uint32_t> hTemplateCigars;
     PinnedBuffer<uint32_t> hTotals;
+    // isaac_ext_build_templates_deferred: two host result sets filled by a copy stream of their own, so that the download of one tile
+    // runs next to the kernels of the next; copyDone[set] also holds back the kernels that rewrite the device result (finish pass)
+    struct DeferredSet
+    {
+        PinnedBuffer<isaac_ext_template_t> templates;  PinnedBuffer<isaac_ext_fragment_t> fragments;  PinnedBuffer<uint32_t> cigars, flag;
+        cudaEvent_t copyDone = nullptr;
+        bool pending = false;
+        const char *what = nullptr;
+    };
+    DeferredSet deferred[2];
+    DeviceBuffer<uint32_t> dDeferredFlag;        // snapshot of the error flag at the end of the deferred tile's kernels
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t kernelsDone = nullptr;
+    unsigned deferredSet = 0;
+    bool copyInFlight = false;                   // a deferred download may still be reading the device result
     uint64_t matchTotal = 0;
     // what isaac_ext_tile_cycle_stats needs of the last isaac_ext_build_templates
     DeviceBuffer<FinishSource> dTemplateSources;  DeviceBuffer<unsigned long long> dCycleStats;  DeviceBuffer<uint8_t> dPf;
@@ -57,7 +72,14 @@ struct TileState
         dRequestCounts.release(); dRequestBegin.release(); dRequests.release(); dScratch.release(); dTemplates.release();
         dTemplateFragments.release(); dTemplateWords.release(); dTemplateWordBegin.release(); dTemplateCigars.release(); dClippedCigars.release();
         hTemplates.release(); hTemplateFragments.release(); hTemplateCigars.release(); hTotals.release();
-        dTemplateSources.release(); dCycleStats.release(); dPf.release();
+        dTemplateSources.release(); dCycleStats.release(); dPf.release(); dDeferredFlag.release();
+        for (DeferredSet &d : deferred)
+        {
+            d.templates.release(); d.fragments.release(); d.cigars.release(); d.flag.release();
+            if (d.copyDone) cudaEventDestroy(d.copyDone);
+        }
+        if (copyStream) cudaStreamDestroy(copyStream);
+        if (kernelsDone) cudaEventDestroy(kernelsDone);
     }
 };
 
@@ -495,8 +517,8 @@ extern "C" int isaac_ext_rescue_shadows(isaac_ext_ctx *ctx, const isaac_ext_tls_
 /// whether a call is made never depends on the outcome of another call (TemplateBuilder.cpp:519-525, 746-753), so the calls of the
 /// whole tile are planned first (plan_device.cuh), answered in one rescue pass and consumed in plan order by the finish pass
 /// (finish_device.cuh).
-extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
-                                         const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result)
+static int buildTemplatesCore(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                              const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result, const bool deferred)
 {
     if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
     REFUSE_NEXT_TO_A_SUBMITTED_CALL(ctx);
@@ -578,6 +600,12 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     CK(ts.dScratch.reserve(scratchBytes));
     CK(ts.dTemplates.reserve(size_t(n) + 1)); CK(ts.dTemplateFragments.reserve(count + 1));
     CK(ts.dTemplateWords.reserve(count + 1)); CK(ts.dTemplateWordBegin.reserve(count + 1)); CK(ts.dTemplateSources.reserve(count + 1));
+    if (ts.copyInFlight)
+    {
+        // the download of the previous (deferred) tile reads the buffers the finish pass is about to rewrite
+        for (TileState::DeferredSet &d : ts.deferred) if (d.pending) CK(cudaStreamWaitEvent(ctx->stream, d.copyDone, 0));
+        ts.copyInFlight = false;
+    }
     finishTemplatesKernel<<<clusterGrid, 128, 0, ctx->stream>>>(fv, n, ts.input[ts.activeInput].dMatchBegin.p, ts.dScratch.p, ts.dTemplates.p, ts.dTemplateFragments.p,
                                                                 ts.dTemplateWords.p, ts.dTemplateSources.p);
     ++ctx->launches;
@@ -610,6 +638,36 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
         CK(cudaGetLastError());
         dCigars = ts.dClippedCigars.p; words = outWords;
     }
+    if (deferred)
+    {
+        // ---- one download, on the copy stream: the call returns as soon as it is queued (isaac_ext_fetch_templates waits for it)
+        if (!ts.copyStream)
+        {
+            CK(cudaStreamCreateWithFlags(&ts.copyStream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ts.kernelsDone, cudaEventDisableTiming));
+            for (TileState::DeferredSet &d : ts.deferred) CK(cudaEventCreateWithFlags(&d.copyDone, cudaEventDisableTiming));
+        }
+        ts.deferredSet ^= 1u;
+        TileState::DeferredSet &d = ts.deferred[ts.deferredSet];
+        if (d.pending) return ctx->fail(ISAAC_EXT_E_UNSUPPORTED, "two deferred tiles are waiting to be fetched: isaac_ext_fetch_templates first");
+        CK(d.templates.reserve(size_t(n) + 1)); CK(d.fragments.reserve(count + 1)); CK(d.cigars.reserve(words + 1)); CK(d.flag.reserve(1));
+        CK(ts.dDeferredFlag.reserve(2));
+        CK(cudaMemcpyAsync(ts.dDeferredFlag.p + ts.deferredSet, ctx->errorFlag.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaEventRecord(ts.kernelsDone, ctx->stream));
+        CK(cudaStreamWaitEvent(ts.copyStream, ts.kernelsDone, 0));
+        CK(cudaMemcpyAsync(d.templates.p, ts.dTemplates.p, size_t(n) * sizeof(isaac_ext_template_t), cudaMemcpyDeviceToHost, ts.copyStream));
+        CK(cudaMemcpyAsync(d.fragments.p, ts.dTemplateFragments.p, count * sizeof(isaac_ext_fragment_t), cudaMemcpyDeviceToHost, ts.copyStream));
+        if (words) CK(cudaMemcpyAsync(d.cigars.p, dCigars, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ts.copyStream));
+        CK(cudaMemcpyAsync(d.flag.p, ts.dDeferredFlag.p + ts.deferredSet, sizeof(uint32_t), cudaMemcpyDeviceToHost, ts.copyStream));
+        CK(cudaEventRecord(d.copyDone, ts.copyStream));
+        d.pending = true;
+        ts.copyInFlight = true;
+        timer.mark("gather + clip (download queued)");
+        result->templates = d.templates.p; result->fragments = d.fragments.p; result->cigars = d.cigars.p;
+        result->cigarWords = words; result->rescueRequests = requestTotal;
+        ts.templatesResident = true;
+        return ISAAC_EXT_OK;
+    }
     // ---- one download
     CK(ts.hTemplates.reserve(size_t(n) + 1)); CK(ts.hTemplateFragments.reserve(count + 1)); CK(ts.hTemplateCigars.reserve(words + 1));
     CK(cudaMemcpyAsync(ts.hTemplates.p, ts.dTemplates.p, size_t(n) * sizeof(isaac_ext_template_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -624,6 +682,33 @@ extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_bui
     result->cigarWords = words; result->rescueRequests = requestTotal;
     ts.templatesResident = true;
     return ISAAC_EXT_OK;
+}
+
+extern "C" int isaac_ext_build_templates(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                         const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result)
+{
+    return buildTemplatesCore(ctx, batch, tls, options, result, false);
+}
+
+extern "C" int isaac_ext_build_templates_deferred(isaac_ext_ctx *ctx, const isaac_ext_build_batch_t *batch, const isaac_ext_tls_t *tls,
+                                                  const isaac_ext_template_options_t *options, isaac_ext_template_result_t *result)
+{
+    return buildTemplatesCore(ctx, batch, tls, options, result, true);
+}
+
+extern "C" int isaac_ext_fetch_templates(isaac_ext_ctx *ctx, const isaac_ext_template_result_t *result)
+{
+    if (!ctx) return ISAAC_EXT_E_INVALID_ARG;
+    if (!result || !ctx->tile) return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "no deferred result to fetch");
+    TileState &ts = *ctx->tile;
+    for (TileState::DeferredSet &d : ts.deferred)
+    {
+        if (!d.pending || result->templates != d.templates.p) continue;
+        CK(cudaEventSynchronize(d.copyDone));
+        d.pending = false;
+        return checkTileFlag(ctx, d.flag.p[0], "malformed match batch (offsets, seed index or contig out of range)");
+    }
+    return ctx->fail(ISAAC_EXT_E_INVALID_ARG, "this result is not waiting to be fetched");
 }
 
 extern "C" int isaac_ext_tile_cycle_stats(isaac_ext_ctx *ctx, const uint8_t *pf, uint64_t *statsOut)

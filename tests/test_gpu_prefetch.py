@@ -105,3 +105,42 @@ def test_uploads_overlap_the_previous_tiles_kernels(capi):
     # measured on a B200: 22.9 -> 20.4 ms per 400 k pairs (profiles/); the bound here only catches a prefetch that serialises
     assert overlapped < inline * 1.05, (inline, overlapped)
     ctx.close()
+
+
+def test_deferred_templates_equal_the_blocking_call(capi):
+    """isaac_ext_build_templates_deferred / isaac_ext_fetch_templates: the same templates as the blocking call, with the download of
+    one tile queued behind its kernels while the next tile is built; two result sets, a third waiting tile is refused"""
+    from isaac_aligner_b200 import synth
+    from isaac_aligner_b200.batch import MatchBatch
+    genome, sim, reads_a, mb_a = build_workload(n_pairs=5000, L=100, seed=931)
+    sim_b = synth.simulate_pairs(genome, 3000, L=100, seed=9321, indel_rate=4e-3, seed_offsets=synth.auto_seed_offsets(100))
+    matches_b, begin_b = synth.make_matches(sim_b, genome, seed=9322, decoy_rate=0.3)
+    reads_b, mb_b = ReadSet(sim_b.bcl, (100, 100)), MatchBatch(matches_b, begin_b, synth.seed_table(sim_b), with_gaps=True)
+    ctx = capi.Context(Config.default(max_read_length=200))
+    ctx.set_reference(genome)
+    tls, opt = Tls.make(), TemplateOptions.make(clip_semialigned=True, clip_overlapping=True)
+    ctx.set_reads(reads_a)
+    want_a = ctx.build_templates(mb_a, tls, opt)
+    ctx.set_reads(reads_b)
+    want_b = ctx.build_templates(mb_b, tls, opt)
+    # A deferred, B deferred on top of it, then both fetched in order; and once more the other way round
+    for first, second, want_first, want_second in ((reads_a, reads_b, want_a, want_b), (reads_b, reads_a, want_b, want_a)):
+        mb_first, mb_second = (mb_a, mb_b) if first is reads_a else (mb_b, mb_a)
+        ctx.set_reads(first)
+        h1 = ctx.build_templates_deferred(mb_first, tls, opt)
+        ctx.set_reads(second)
+        h2 = ctx.build_templates_deferred(mb_second, tls, opt)
+        with pytest.raises(capi.ExtError) as e:
+            ctx.build_templates_deferred(mb_second, tls, opt)                   # two tiles are waiting already
+        assert e.value.code == 4
+        assert same(want_first, ctx.fetch_templates(h1))
+        with pytest.raises(capi.ExtError):
+            ctx.fetch_templates(h1)                                             # fetched already
+        assert same(want_second, ctx.fetch_templates(h2))
+    # a blocking call between deferred ones, and the device-resident result of the last tile built
+    ctx.set_reads(reads_a)
+    h = ctx.build_templates_deferred(mb_a, tls, opt)
+    ctx.set_reads(reads_b)
+    assert same(want_b, ctx.build_templates(mb_b, tls, opt))
+    assert same(want_a, ctx.fetch_templates(h))
+    ctx.close()
