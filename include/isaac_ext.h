@@ -637,7 +637,8 @@ typedef struct isaac_ext_realign_result {
  * Independent of the order of bins and, inside a bin, of the order of templates: the two mates of a pair are realigned in index
  * order by one thread, because the second one reads what the first one's updatePairDetails left (GapRealigner.cpp:222-270,
  * 1112-1113); nothing else is shared between index entries (the gaps are final before the first realign call).
- * Limits: records of more than 1024 bases, or original CIGARs of more than 64 operations, are ISAAC_EXT_E_UNSUPPORTED. */
+ * Limits: records of more than 512 bases, or original CIGARs of more than 64 operations, are ISAAC_EXT_E_UNSUPPORTED when the
+ * realigner has gaps to try on them; more than 255 gap groups are ISAAC_EXT_E_UNSUPPORTED. */
 int isaac_ext_realign_bin(isaac_ext_ctx *ctx, const isaac_ext_realign_options_t *options, uint8_t *data, uint64_t dataBytes,
                           const uint64_t *recordOffset, uint64_t recordCount, const isaac_ext_bin_index_t *index,
                           uint64_t indexCount, isaac_ext_realign_result_t *result);

@@ -105,9 +105,6 @@ def cigar_string(words):
     return "".join("%d%s" % (int(w) >> 4, "MID?S"[int(w) & 15] if (int(w) & 15) < 5 else "?") for w in words)
 
 
-_COMPLEMENT = np.zeros(256, dtype=np.uint8)
-for _a, _b in zip(b"ACGTN", b"TGCAN"):
-    _COMPLEMENT[_a] = _b
 _CODE = np.full(256, 255, dtype=np.uint8)
 for _i, _a in enumerate(b"ACGT"):
     _CODE[_a] = _i

@@ -54,7 +54,7 @@ void releaseRealign(RealignSlots *state) { if (state) { for (RealignState &s : s
 namespace
 {
 // dCounters: 0 unique gaps, 1 deletions, 2 ties among deletion ends, 3 error flags
-enum { RC_GAPS = 0, RC_DELETIONS = 1, RC_TIES = 2, RC_ERRORS = 3, RC_WORDS = 4 };
+enum { RC_GAPS = 0, RC_DELETIONS = 1, RC_TIES = 2, RC_ERRORS = 3 };
 }
 
 namespace

@@ -44,7 +44,6 @@ constexpr unsigned REALIGN_FOUND_CAPACITY = 100;     // currentAttemptGaps_.rese
 constexpr unsigned REALIGN_CIGAR_CAP = 80;           // words of a CIGAR under construction: 2 per gap + clips + the clippers' splits
 constexpr unsigned REALIGN_MAX_ORIGINAL_CIGAR = 64;
 constexpr unsigned REALIGN_MAX_READ = 512;           // bases of a record the packed read buffer holds
-constexpr int REALIGN_MISMATCH_PERCENT_REDUCTION_MIN = 20;
 constexpr uint16_t REALIGN_DODGY_ALIGNMENT_SCORE = 0xFFFFu;       // io::FragmentHeader::DODGY_ALIGNMENT_SCORE (Fragment.hh:304)
 
 enum : uint32_t
