@@ -585,7 +585,10 @@ def run_b200(args):
         "roofline": {"bound": "int32", "kernel": "swForwardKernel (timed with the swTraceScoreKernel launches it overlaps: "
                                                   "the whole isaac_ext_gapped_batch_device call)",
                      "achieved": achieved / 1e12, "peak": peak_add / 1e12,
-                     "unit": "TOP/s", "frac": achieved / peak_add, "traffic": traffic,
+                     "unit": "TOP/s", "frac": achieved / peak_add,
+                     # the same against the packed 16x2 rate (two cells per instruction is what the kernel's VIMNMX / VIADDMNMX do; the adds,
+                     # flag bookkeeping and multiply-adds around them are 32-bit instructions, so 1.0 here is not reachable)
+                     "frac_vs_16x2_peak": achieved / peak_dpx, "traffic": traffic,
                      "hbm_gbs": (traffic / (ms_gapped * 1e-3) / 1e9) if traffic else None,
                      "hbm_frac": (traffic / (ms_gapped * 1e-3) / 1e9 / hbm_peak) if traffic else None,
                      "plane_bytes_per_launch": int(n) * L * 12,
