@@ -203,3 +203,52 @@ def test_two_rank_full_tile_stats_payload(tmp_path):
     mp.spawn(_rank_tile_stats, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     ok, size, mismatches = np.load(os.path.join(str(tmp_path), "ok.npy"))
     assert ok == 1 and size == 4 * 32 + 4 * 47105 and mismatches > 0
+
+
+def _bins_rank_main(rank, world, port, out_dir):
+    """the gap realigner's sharding: the bins of a run are dealt over the ranks like tiles (bin r, r + G, ...), every rank realigns its
+    own against its replica of the reference, nothing of the bins is exchanged; only the count of realigned fragments is summed here,
+    as a run's statistics would be.  The reference's own GapRealigner stands in for the kernels."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    from isaac_aligner_b200 import bins, distributed
+    from isaac_aligner_b200.batch import Tls
+    from test_realign_host import make_contigs
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ref = oracle_lib.reference()
+    contigs = make_contigs(3, lengths=(3000, 60000))
+    genome = oracle_lib.GenomeHolder(contigs)
+    n_bins = 5
+    regions = [(2000 + 9000 * k, 2000 + 9000 * (k + 1)) for k in range(n_bins)]
+
+    def realigned_in(k):
+        b = bins.simulate_bin(contigs, contig=1, region=regions[k], n_pairs=500, read_length=100, seed=60 + k)
+        o = bins.RealignOptions(b.bin_start, b.bin_end, [Tls.make()], clip_semialigned=True)
+        res = oracle_lib.realign_bin(ref, genome, b, o)
+        return int(np.count_nonzero(res.cigar_offset != bins.OWN_CIGAR))
+
+    mine = distributed.tiles_of_rank(n_bins, rank, world)
+    local = sum(realigned_in(k) for k in mine)
+    t = torch.tensor([local, len(mine)], dtype=torch.int64)
+    dist.all_reduce(t)
+    if rank == 0:
+        want = sum(realigned_in(k) for k in range(n_bins))
+        np.save(os.path.join(out_dir, "bins.npy"), np.array([int(t[0]), want, int(t[1]), local]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bins_of_the_gap_realigner(tmp_path):
+    import oracle_lib
+    if oracle_lib.reference() is None:
+        pytest.skip("oracle/_ref/libisaac_ref.so not built (needs /root/reference)")
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + 77) % 500
+    mp.spawn(_bins_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    total, want, bins_done, local = np.load(os.path.join(str(tmp_path), "bins.npy"))
+    assert total == want and want > 0 and bins_done == 5 and 0 < local < total
