@@ -175,9 +175,9 @@ struct RealignRead
         for (unsigned w = 0; w < REALIGN_MAX_READ / 32 + 1; ++w) n[w] = 0;
         for (unsigned i = 0; i < readLength; ++i)
         {
-            const uint8_t b = bases[i];
-            if (b & 0xFCu) codes[i >> 4] |= uint32_t(b & 3u) << ((i & 15u) * 2u);
-            else n[i >> 5] |= 1u << (i & 31u);
+            const uint32_t b = bases[i], called = (b & 0xFCu) != 0u;
+            codes[i >> 4] |= (called ? (b & 3u) : 0u) << ((i & 15u) * 2u);
+            n[i >> 5] |= (called ^ 1u) << (i & 31u);
         }
     }
     /// 'A' 'C' 'G' 'T' = 0..3, 'N' = 4
@@ -238,6 +238,15 @@ struct RealignCigar
     uint32_t w[REALIGN_CIGAR_CAP];
     unsigned n;
     bool overflow;
+    RealignCigar() = default;
+    /// only the words in use travel (a plain struct copy moves all REALIGN_CIGAR_CAP of them through thread-local memory)
+    ISAAC_HD RealignCigar(const RealignCigar &o) : n(o.n), overflow(o.overflow) { for (unsigned k = 0; k < o.n; ++k) w[k] = o.w[k]; }
+    ISAAC_HD RealignCigar &operator=(const RealignCigar &o)
+    {
+        n = o.n; overflow = o.overflow;
+        for (unsigned k = 0; k < o.n; ++k) w[k] = o.w[k];
+        return *this;
+    }
     ISAAC_HD void clear() { n = 0; overflow = false; }
     ISAAC_HD void push(const uint32_t length, const uint32_t op) { if (n < REALIGN_CIGAR_CAP) w[n++] = (length << 4) | op; else overflow = true; }
     ISAAC_HD uint32_t length(const unsigned i) const { return w[i] >> 4; }
