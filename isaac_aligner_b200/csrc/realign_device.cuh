@@ -171,8 +171,8 @@ struct RealignRead
     ISAAC_HD void load(const uint8_t *bases, const unsigned readLength)
     {
         bcl = bases; length = readLength;
-        for (unsigned w = 0; w < REALIGN_MAX_READ / 16 + 1; ++w) codes[w] = 0;
-        for (unsigned w = 0; w < REALIGN_MAX_READ / 32 + 1; ++w) n[w] = 0;
+        for (unsigned w = 0; w < readLength / 16 + 2 && w < REALIGN_MAX_READ / 16 + 1; ++w) codes[w] = 0;      // the words in use + the spare one
+        for (unsigned w = 0; w < readLength / 32 + 2 && w < REALIGN_MAX_READ / 32 + 1; ++w) n[w] = 0;
         for (unsigned i = 0; i < readLength; ++i)
         {
             const uint32_t b = bases[i], called = (b & 0xFCu) != 0u;
