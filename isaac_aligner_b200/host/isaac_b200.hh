@@ -20,6 +20,7 @@
 
 #include <cstdint>
 #include <stdexcept>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -380,6 +381,78 @@ public:
 } // namespace fragmentBuilder
 
 } // namespace alignment
+
+namespace io
+{
+/// io::FragmentHeader as the reference lays it out on x86-64 (include/io/Fragment.hh:73-404): the record of a bin, followed by
+/// readLength_ BCL bytes and cigarLength_ CIGAR words
+struct FragmentHeader
+{
+    int32_t bamTlen_; uint32_t observedLength_; uint64_t fStrandPosition_; uint16_t lowClipped_, highClipped_, alignmentScore_,
+        templateAlignmentScore_; uint64_t mateFStrandPosition_; uint16_t readLength_, cigarLength_, gapCount_, editDistance_, flags_, pad0_[3];
+    uint64_t tile_, barcode_, barcodeSequence_, clusterId_; int32_t clusterX_, clusterY_; uint64_t duplicateClusterRank_, mateAnchor_;
+    uint32_t mateStorageBin_, pad1_;
+    enum { PAIRED = 1, UNMAPPED = 2, MATE_UNMAPPED = 4, REVERSE = 8, MATE_REVERSE = 16, FIRST_READ = 32, SECOND_READ = 64, FAIL_FILTER = 128, PROPER_PAIR = 256 };
+    unsigned getTotalLength() const { return unsigned(sizeof(FragmentHeader)) + readLength_ + 4u * cigarLength_; }
+};
+/// reference::ReferencePosition(contigId, position).getValue() (include/reference/ReferencePosition.hh:68-78)
+inline uint64_t referencePosition(uint64_t contigId, uint64_t position) { return (((contigId + 1) << 40) | position) << 1; }
+} // namespace io
+
+namespace build
+{
+/// build::PackedFragmentBuffer::Index (include/build/PackedFragmentBuffer.hh:36-91)
+struct Index
+{
+    uint64_t pos_;                       // ReferencePosition::getValue
+    unsigned long dataOffset_, mateDataOffset_;
+    const uint32_t *cigarBegin_, *cigarEnd_;
+};
+
+/// build::GapRealigner driven the way BinSorter drives it (lib/build/BinSorter.cpp:389-418): collectGaps + realignGaps of one bin
+/// in one call on the context's GPU
+class GapRealigner
+{
+public:
+    GapRealigner(Context &context, bool realignGapsVigorously, bool realignDodgyFragments, unsigned /*realignedGapsPerFragment*/,
+                 unsigned mismatchCost, unsigned gapOpenCost, unsigned gapExtendCost, bool clipSemialigned,
+                 const std::vector<isaac_ext_tls_t> &barcodeTemplateLengthStatistics)
+        : context_(context), tls_(barcodeTemplateLengthStatistics)
+    {
+        std::memset(&options_, 0, sizeof(options_));
+        options_.realignGapsVigorously = realignGapsVigorously; options_.realignDodgyFragments = realignDodgyFragments;
+        options_.mismatchCost = mismatchCost; options_.gapOpenCost = gapOpenCost; options_.gapExtendCost = gapExtendCost;
+        options_.clipSemialigned = clipSemialigned;
+    }
+    /// data: the bin's records back to back (updated in place); index: its entries in processing order, their pos_ and CIGAR
+    /// pointers are refreshed (a realigned entry points into this object's buffer, valid until the next call)
+    void realignBin(uint64_t binStart, uint64_t binEnd, std::vector<char> &data, std::vector<Index> &index)
+    {
+        options_.binStart = binStart; options_.binEnd = binEnd;
+        options_.barcodeCount = uint32_t(tls_.size()); options_.barcodeTls = tls_.data(); options_.barcodeGapGroup = 0;
+        std::vector<isaac_ext_bin_index_t> flat;
+        for (size_t i = 0; i < index.size(); ++i) { const isaac_ext_bin_index_t e = {index[i].dataOffset_, index[i].mateDataOffset_}; flat.push_back(e); }
+        isaac_ext_realign_result_t r;
+        context_.check(isaac_ext_realign_bin(context_.get(), &options_, reinterpret_cast<uint8_t *>(data.data()), data.size(), 0, 0,
+                                             flat.data(), flat.size(), &r));
+        realignedCigars_.assign(r.realignedCigars, r.realignedCigars + r.realignedCigarWords);
+        for (size_t i = 0; i < index.size(); ++i)
+        {
+            index[i].pos_ = r.position[i];
+            if (ISAAC_EXT_REALIGN_OWN_CIGAR != r.cigarOffset[i])
+            {
+                index[i].cigarBegin_ = realignedCigars_.data() + r.cigarOffset[i];
+                index[i].cigarEnd_ = index[i].cigarBegin_ + r.cigarLength[i];
+            }
+        }
+    }
+private:
+    Context &context_;
+    std::vector<isaac_ext_tls_t> tls_;
+    isaac_ext_realign_options_t options_;
+    std::vector<uint32_t> realignedCigars_;
+};
+} // namespace build
 } // namespace isaac_b200
 
 #endif // ISAAC_B200_HH

@@ -4,6 +4,7 @@
 // testSimpleIndelAligner.cpp:264-277 through FragmentBuilder::build.  Exits 0 when every check passes.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "../../isaac_aligner_b200/host/isaac_b200.hh"
@@ -239,6 +240,74 @@ static void testSequencingAdapter()
     }
 }
 
+/// One record of a bin: io::FragmentHeader + BCL bytes (quality 30) + CIGAR words
+static void appendRecord(std::vector<char> &data, const std::string &bases, uint64_t position, const std::vector<uint32_t> &cigar,
+                         unsigned editDistance, unsigned gapCount, unsigned observedLength)
+{
+    io::FragmentHeader h;
+    std::memset(&h, 0, sizeof(h));
+    h.observedLength_ = observedLength; h.fStrandPosition_ = io::referencePosition(0, position);
+    h.alignmentScore_ = 100; h.templateAlignmentScore_ = 100; h.mateFStrandPosition_ = io::referencePosition(0, position);
+    h.readLength_ = uint16_t(bases.size()); h.cigarLength_ = uint16_t(cigar.size()); h.gapCount_ = uint16_t(gapCount);
+    h.editDistance_ = uint16_t(editDistance);
+    h.flags_ = io::FragmentHeader::MATE_UNMAPPED | io::FragmentHeader::FIRST_READ | io::FragmentHeader::SECOND_READ;     // single-ended
+    h.tile_ = 1; h.clusterX_ = h.clusterY_ = 0x7FFFFFFF;
+    const char *raw = reinterpret_cast<const char *>(&h);
+    data.insert(data.end(), raw, raw + sizeof(h));
+    for (size_t i = 0; i < bases.size(); ++i) data.push_back(char((30 << 2) | std::string("ACGT").find(bases[i])));
+    const char *words = reinterpret_cast<const char *>(cigar.data());
+    data.insert(data.end(), words, words + 4 * cigar.size());
+}
+
+/// build::GapRealigner: a read that crosses a deletion 30 bases from its start and was laid down without a gap is repaired with the
+/// deletion another read of the bin brought along (the situation the class exists for, lib/build/GapRealigner.cpp:1061-1267)
+static void testGapRealigner()
+{
+    const std::string genome = getGenome(600);
+    const std::string haplotype = genome.substr(0, 150) + genome.substr(155);             // five bases of the reference deleted
+    Context context(makeConfig(2, -1, -15, -3, -25, 300));
+    std::vector<reference::Contig> contigs(1, reference::Contig(0, "c0"));
+    contigs[0].forward_ = v(genome);
+    context.setReference(contigs);
+    const uint32_t M = ISAAC_EXT_CIGAR_ALIGN, D = ISAAC_EXT_CIGAR_DELETE;
+    std::vector<char> data;
+    std::vector<build::Index> index;
+    // read A: haplotype [100, 200) with its true alignment 50M5D50M at 100
+    const std::vector<uint32_t> cigarA = {(50u << 4) | M, (5u << 4) | D, (50u << 4) | M};
+    appendRecord(data, haplotype.substr(100, 100), 100, cigarA, 5, 1, 105);
+    // read B: haplotype [120, 220) laid down as 100M at 120: everything behind the deletion is shifted
+    const std::string readB = haplotype.substr(120, 100);
+    unsigned mismatches = 0;
+    for (unsigned i = 0; i < 100; ++i) mismatches += readB[i] != genome[120 + i];
+    const std::vector<uint32_t> cigarB = {(100u << 4) | M};
+    const size_t offsetB = data.size();
+    appendRecord(data, readB, 120, cigarB, mismatches, 0, 100);
+    for (size_t offset = 0, k = 0; offset < data.size(); ++k)
+    {
+        const io::FragmentHeader *h = reinterpret_cast<const io::FragmentHeader *>(&data[offset]);
+        const uint32_t *cigar = reinterpret_cast<const uint32_t *>(&data[offset] + sizeof(io::FragmentHeader) + h->readLength_);
+        const build::Index e = {h->fStrandPosition_, offset, offset, cigar, cigar + h->cigarLength_};
+        index.push_back(e);
+        offset += h->getTotalLength();
+    }
+    CHECK(mismatches > 20);
+    const std::vector<isaac_ext_tls_t> tls(1, isaac_ext_tls_t{245, 455, 350, 35, 35, {1, 6}, -1});
+    build::GapRealigner realigner(context, false, false, 1, 3, 4, 0, false, tls);
+    realigner.realignBin(io::referencePosition(0, 0), io::referencePosition(0, genome.size()), data, index);
+    CHECK_EQ(index[0].cigarEnd_ - index[0].cigarBegin_, 3);                               // read A is left alone
+    CHECK_EQ(index[1].pos_, io::referencePosition(0, 120));
+    CHECK_EQ(index[1].cigarEnd_ - index[1].cigarBegin_, 3);
+    if (index[1].cigarEnd_ - index[1].cigarBegin_ == 3)
+    {
+        CHECK_EQ(index[1].cigarBegin_[0], (30u << 4) | M);
+        CHECK_EQ(index[1].cigarBegin_[1], (5u << 4) | D);
+        CHECK_EQ(index[1].cigarBegin_[2], (70u << 4) | M);
+    }
+    const io::FragmentHeader *b = reinterpret_cast<const io::FragmentHeader *>(&data[offsetB]);
+    CHECK_EQ(b->editDistance_, 5);
+    CHECK_EQ(b->observedLength_, 105u);
+}
+
 int main()
 {
     testSequencingAdapter();
@@ -246,6 +315,7 @@ int main()
     testBandedSmithWaterman();
     testSimpleDeletionThroughFragmentBuilder();
     testTemplateBuilder();
+    testGapRealigner();
     std::printf(failures ? "%d checks FAILED\n" : "all checks passed\n", failures);
     return failures ? 1 : 0;
 }
