@@ -30,11 +30,12 @@ def main():
         a = int(rng.integers(0, max(1, n // 4)))
         b = int(rng.integers(n // 2, n + 200))                                  # may lie behind the end of the contig
         spacing = int(rng.choice([25, 60, 120, 220, 400]))
-        L = int(rng.choice([36, 75, 100, 150, 250]))
+        L = int(rng.choice([36, 75, 100, 150, 250, 400, 500]))
         barcodes = int(rng.integers(1, 4))
         bin_ = bins.simulate_bin(contigs, contig=contig, region=(a, min(b, n)), n_pairs=int(rng.integers(300, 1500)), read_length=L, seed=seed,
                                  variant_spacing=spacing, gapped_fraction=float(rng.choice([0.3, 0.6, 0.9])), barcodes=barcodes,
-                                 clip_fraction=float(rng.choice([0.0, 0.1, 0.4])), edge_fraction=float(rng.choice([0.0, 0.05])),
+                                 clip_fraction=float(rng.choice([0.0, 0.1, 0.4, 0.9])), singleton_fraction=float(rng.choice([0.03, 0.3])),
+                                 single_ended_fraction=float(rng.choice([0.03, 0.5])), dodgy_fraction=float(rng.choice([0.03, 0.4])), n_fraction=float(rng.choice([0.002, 0.05])), edge_fraction=float(rng.choice([0.0, 0.05])),
                                  max_indel=int(rng.choice([3, 14, 40])), template_mean=int(2.6 * L) + 60, error_rate=float(rng.choice([0.0, 0.004, 0.02])))
         bin_.bin_end = bins.reference_position(contig, b)
         tls = [Tls.make(mn=int(2.0 * L), mx=int(3.4 * L) + 120, median=int(2.6 * L) + 60) for _ in range(barcodes)]
