@@ -90,3 +90,40 @@ def test_python_mirrors_have_the_c_struct_sizes():
     out = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
     for name, size in pairs:
         assert int(out[name]) == size, (name, out[name], size)
+
+
+def test_bin_record_layouts_agree():
+    """io::FragmentHeader has four statements here: the host mirror (host/isaac_b200.hh), the realigner's byte offsets
+    (csrc/realign_device.cuh), the packer's struct (csrc/pack_fragments.cuh) and the harness dtype (bins.HEADER_DTYPE)"""
+    import subprocess
+    from isaac_aligner_b200 import bins
+    src = os.path.join(ROOT, "build", "bin_layout.cu")
+    os.makedirs(os.path.dirname(src), exist_ok=True)
+    fields = ["bamTlen", "observedLength", "fStrandPosition", "lowClipped", "highClipped", "alignmentScore", "templateAlignmentScore",
+              "mateFStrandPosition", "readLength", "cigarLength", "gapCount", "editDistance", "flags", "tile", "barcode", "barcodeSequence",
+              "clusterId", "clusterX", "clusterY", "duplicateClusterRank", "mateAnchor", "mateStorageBin"]
+    with open(src, "w") as f:
+        f.write('#include <cstdio>\n#include <cstddef>\n#include "../isaac_aligner_b200/host/isaac_b200.hh"\n'
+                '#include "../isaac_aligner_b200/csrc/realign_device.cuh"\n#include "../isaac_aligner_b200/csrc/pack_fragments.cuh"\n'
+                'int main() {\n  using isaac_b200::io::FragmentHeader; using isaac_b200::PackedFragmentHeader;\n')
+        for name in fields:
+            f.write('  std::printf("%s %%zu %%zu\\n", offsetof(FragmentHeader, %s_), offsetof(PackedFragmentHeader, %s));\n' % (name, name, name))
+        f.write('  std::printf("sizeof %zu %zu\\n", sizeof(FragmentHeader), sizeof(PackedFragmentHeader));\n')
+        for name in ("BAM_TLEN", "OBSERVED_LENGTH", "F_STRAND_POSITION", "LOW_CLIPPED", "HIGH_CLIPPED", "ALIGNMENT_SCORE", "TEMPLATE_ALIGNMENT_SCORE",
+                     "MATE_F_STRAND_POSITION", "READ_LENGTH", "CIGAR_LENGTH", "GAP_COUNT", "EDIT_DISTANCE", "FLAGS", "BARCODE", "CLUSTER_ID"):
+            f.write('  std::printf("BIN_%s %%u\\n", unsigned(isaac_b200::BIN_%s));\n' % (name, name))
+        f.write("  return 0;\n}\n")
+    exe = os.path.join(ROOT, "build", "bin_layout")
+    subprocess.check_call(["nvcc", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    rows = dict((line.split()[0], [int(x) for x in line.split()[1:]]) for line in out if line.strip())
+    for name in fields:
+        want = bins.HEADER_DTYPE.fields[name][1]
+        assert rows[name] == [want, want], (name, rows[name], want)
+    assert rows["sizeof"] == [112, 112] and bins.HEADER_DTYPE.itemsize == 112
+    camel = {"BAM_TLEN": "bamTlen", "OBSERVED_LENGTH": "observedLength", "F_STRAND_POSITION": "fStrandPosition", "LOW_CLIPPED": "lowClipped",
+             "HIGH_CLIPPED": "highClipped", "ALIGNMENT_SCORE": "alignmentScore", "TEMPLATE_ALIGNMENT_SCORE": "templateAlignmentScore",
+             "MATE_F_STRAND_POSITION": "mateFStrandPosition", "READ_LENGTH": "readLength", "CIGAR_LENGTH": "cigarLength", "GAP_COUNT": "gapCount",
+             "EDIT_DISTANCE": "editDistance", "FLAGS": "flags", "BARCODE": "barcode", "CLUSTER_ID": "clusterId"}
+    for key, name in camel.items():
+        assert rows["BIN_" + key] == [bins.HEADER_DTYPE.fields[name][1]], key
