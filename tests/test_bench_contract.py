@@ -27,7 +27,7 @@ def test_reference_arm_line():
 
 
 def test_committed_cuda_arm_line_has_the_contract_keys():
-    path = os.path.join(ROOT, "profiles", "r1_zb_bench_micro.json")
+    path = os.path.join(ROOT, "profiles", "r2_an_bench_default.json")            # the default command on one B200, final state of round 2
     d = json.loads([l for l in open(path) if l.startswith("{")][-1])
     for key in BASE_KEYS + ("gpu_launches", "clocks", "roofline"):
         assert key in d, key
@@ -41,3 +41,11 @@ def test_committed_cuda_arm_line_has_the_contract_keys():
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
     c = d["cpu_baseline"]
     assert c["kind"] == "reference" and c["cores"] >= 1 and 0 < c["value"] < d["value"] / 50
+    # the two side measurements of the default line carry their own end-to-end figure and CPU baseline
+    p = d["pairs_pipeline"]
+    assert p["unit"] == "pairs/s" and 0 < p["e2e"]["value"] < p["value"] and p["e2e"]["h2d_bytes_per_step"] > 0 and p["e2e"]["d2h_bytes_per_step"] > 0
+    assert p["cpu_baseline"]["kind"] == "reference" and 0 < p["cpu_baseline"]["value"] < p["value"] / 50
+    g = d["gap_realigner"]
+    assert g["unit"] == "fragments/s" and 0 < g["e2e"]["value"] < g["value"] and g["cpu_baseline"]["kind"] == "reference"
+    assert 0 < g["cpu_baseline"]["value"] < g["e2e"]["value"] / 5 and g["realigned_fragments"] > 0
+    assert 0 < d["roofline"]["frac_vs_16x2_peak"] < d["roofline"]["frac"]
