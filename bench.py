@@ -326,8 +326,9 @@ def pairs_pipeline_gpu(args, workload, local_rank, world, steps, warmup):
             "value_is": "isaac_ext_build_templates alone (reads resident; matches up and templates down inside), max over ranks",
             "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(bcl.nbytes + matches.nbytes + begin.nbytes), "d2h_bytes_per_step": int(d2h),
-                    "api": "per tile isaac_ext_set_reads + isaac_ext_build_templates, the next tile's bytes uploaded meanwhile "
-                           "(isaac_ext_prefetch_reads / _batch), page-locked host buffers; %d tiles back to back" % steps},
+                    "api": "per tile isaac_ext_set_reads + isaac_ext_build_templates_deferred / isaac_ext_fetch_templates: the next tile's bytes go "
+                           "up (isaac_ext_prefetch_reads / _batch) and the previous tile's templates come down while a tile is processed; "
+                           "page-locked host buffers; %d tiles back to back" % steps},
             "gpu_launches_per_step": int(launches),
             "matches_per_gpu": int(len(matches)), "rescue_requests": int(templates.rescue_requests),
             "templates_built": int(templates.templates["built"].sum()), "proper_pairs": int(templates.templates["properPair"].sum()),
