@@ -27,7 +27,7 @@ def test_reference_arm_line():
 
 
 def test_committed_cuda_arm_line_has_the_contract_keys():
-    path = os.path.join(ROOT, "profiles", "r2_an_bench_default.json")            # the default command on one B200, final state of round 2
+    path = os.path.join(ROOT, "profiles", "r2_aq_bench_default.json")            # the default command on one B200, final state of round 2
     d = json.loads([l for l in open(path) if l.startswith("{")][-1])
     for key in BASE_KEYS + ("gpu_launches", "clocks", "roofline"):
         assert key in d, key
